@@ -1,0 +1,454 @@
+#!/usr/bin/env python
+"""bench.py -- count + locate throughput of the B200 FM-index query engine.
+
+One "step" = one pass of the hot path (backward search of every pattern, then locate of every
+match) over one batch of synthetic patterns.  Default workload = BASELINE.json configs[1]:
+FMIndexWithLocate, sampling level 2, 1M 32-mers (50 % sampled from the text, 50 % uniform random)
+over 100 MB synthetic DNA.  Prints ONE JSON line (see the contract in the task description).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (text_len, npat, pattern_len, sigma, max_character, level, description)
+    "cfg2_dna100m": (100_000_000, 1_000_000, 32, 4, 4, 2,
+                     "BASELINE configs[1]: FMIndexWithLocate level 2, 1M 32-mers over 100 MB synthetic DNA"),
+    "target_dna1g": (1_000_000_000, 100_000_000, 32, 4, 4, 2,
+                     "north-star target: 100M 32-mers over 1 GB synthetic DNA, level 2"),
+    "cfg1_dna1m": (1_000_000, 10_000, 20, 4, 4, 2, "BASELINE configs[0] shape (CPU-runnable)"),
+    "dna16m": (16_000_000, 1_000_000, 32, 4, 4, 2, "small smoke workload"),
+}
+
+
+def mix64(x: np.ndarray) -> np.ndarray:
+    """splitmix64 finaliser, vectorised: a self-contained, reproducible generator."""
+    x = (x + np.uint64(0x9E3779B97F4A7C15)).astype(np.uint64)
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return x ^ (x >> np.uint64(31))
+
+
+def gen_text(n: int, sigma: int, seed: int) -> np.ndarray:
+    out = np.empty(n + 1, dtype=np.uint8)
+    chunk = 1 << 24
+    with np.errstate(over="ignore"):
+        for lo in range(0, n, chunk):
+            hi = min(n, lo + chunk)
+            r = mix64(np.arange(lo, hi, dtype=np.uint64) + np.uint64(seed) * np.uint64(0x1000000000))
+            out[lo:hi] = (r % np.uint64(sigma)).astype(np.uint8) + 1
+    out[n] = 0
+    return out
+
+
+def gen_patterns(text: np.ndarray, npat: int, m: int, sigma: int, seed: int):
+    """even patterns: substrings at uniform random offsets (>= 1 hit); odd: uniform random."""
+    n = text.size - 1
+    with np.errstate(over="ignore"):
+        r = mix64(np.arange(npat, dtype=np.uint64) + np.uint64(seed) * np.uint64(0x1000000000))
+        starts = (r % np.uint64(n - m)).astype(np.int64)
+        pats = np.empty((npat, m), dtype=np.uint8)
+        chunk = 1 << 20
+        for lo in range(0, npat, chunk):
+            hi = min(npat, lo + chunk)
+            k = np.arange(lo, hi, dtype=np.uint64)
+            rnd = mix64(k[:, None] * np.uint64(64) + np.arange(m, dtype=np.uint64)[None, :]
+                        + np.uint64(seed + 1) * np.uint64(0x1000000000))
+            blk = (rnd % np.uint64(sigma)).astype(np.uint8) + 1
+            samp = text[starts[lo:hi, None] + np.arange(m)[None, :]]
+            even = (np.arange(lo, hi) % 2 == 0)[:, None]
+            pats[lo:hi] = np.where(even, samp, blk)
+    return pats, starts
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region (NVML)."""
+
+    def __init__(self, dev_index: int):
+        super().__init__(daemon=True)
+        self.dev_index = dev_index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = dev_index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[dev_index])
+                except Exception:
+                    phys = dev_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)),
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, v in names.items():
+                    if bits & v:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.ok:
+            self.join(timeout=2)
+        return {
+            "sm_mhz": float(np.median(self.samples)) if self.samples else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.samples),
+        }
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_cpu_path(oracle_index, pats, nthreads, locate=True):
+    """the restated CPU path (oracle, OpenMP over patterns): returns (seconds, s, e, hit_off, pos)"""
+    npat, m = pats.shape
+    flat, off = pats.reshape(-1), np.arange(npat + 1, dtype=np.uint64) * np.uint64(m)
+    t0 = time.perf_counter()
+    s, e = oracle_index.search_batch(flat, off, nthreads=nthreads)
+    hit_off, pos, _ = oracle_index.locate_batch(s, e, nthreads=nthreads)
+    dt = time.perf_counter() - t0
+    return dt, s, e, hit_off, pos
+
+
+def reference_arm(args, wl_name, wl):
+    """--impl reference: the reference's CPU implementation of the path.  The crate cannot be built
+    here (no Rust toolchain, vers-vecs un-vendored), so this is the oracle port of it, run on all
+    host threads over a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle as orc
+
+    n, npat, m, sigma, mc, level, desc = wl
+    nthreads = host_threads()
+    text = gen_text(n, sigma, 3)
+    sample = min(npat, args.cpu_sample)
+    pats, _ = gen_patterns(text, sample, m, sigma, 4)
+    t0 = time.perf_counter()
+    oracle_index = orc.OracleIndex(text, orc.FM, level=level, max_character=mc)
+    build_s = time.perf_counter() - t0
+    times = []
+    hits = 0
+    for it in range(args.warmup + args.steps):
+        dt, s, e, hit_off, pos = run_cpu_path(oracle_index, pats, nthreads)
+        hits = int(hit_off[-1])
+        if it >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = sample / (ms * 1e-3)
+    line = {
+        "impl": "reference", "metric": "count+locate queries/s", "value": value, "unit": "queries/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32/u64 integer",
+        "data": "synthetic",
+        "config": {"workload": wl_name, "description": desc, "text_len": n + 1, "patterns_per_step": sample,
+                   "pattern_len": m, "pattern_mix": "50% sampled from text / 50% uniform random",
+                   "index": "FMIndexWithLocate", "sampling_level": level, "wavelet_levels": int(mc).bit_length()},
+        "located_hits_per_s": hits / (ms * 1e-3),
+        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": nthreads, "kind": "port",
+                         "sample": f"first {sample} patterns of the workload, count+locate, {args.steps} passes",
+                         "cpu_model": cpu_model(), "index_build_s": round(build_s, 1)},
+        "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2_dna100m", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sample", type=int, default=200_000, help="patterns in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gather-peak", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return reference_arm(args, args.workload, wl)
+
+    import torch
+    import torch.distributed as dist
+
+    import fmx_pkg
+
+    fmx = fmx_pkg.load()
+    L = fmx.load_library()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    n, npat, m, sigma, mc, level, desc = wl
+    text = gen_text(n, sigma, 3)
+    # index replicated on every GPU; each rank answers its own batch (weak scaling, no collective
+    # on the query path)
+    pats, starts = gen_patterns(text, npat, m, sigma, 4 + 1000 * rank)
+    t0 = time.perf_counter()
+    index = fmx.FMIndexWithLocate.new(fmx.Text.with_max_character(text, mc), level, device=local)
+    build_s = time.perf_counter() - t0
+    h = index._h
+    stream = torch.cuda.current_stream()
+    sp = C.c_void_p(stream.cuda_stream)
+
+    d_pat = torch.from_numpy(pats).cuda()
+    d_s = torch.empty(npat, dtype=torch.int64, device="cuda")
+    d_e = torch.empty(npat, dtype=torch.int64, device="cuda")
+    d_hoff = torch.empty(npat + 1, dtype=torch.int64, device="cuda")
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def chk(rc):
+        if rc != 0:
+            raise RuntimeError(L.fmx_last_error().decode())
+
+    d_pos = [torch.empty(1, dtype=torch.int64, device="cuda")]
+    total = C.c_uint64(0)
+
+    def search():
+        chk(L.fmx_search_batch_device(h, 0, d_pat.data_ptr(), None, m, npat, None, None, d_s.data_ptr(),
+                                      d_e.data_ptr(), sp))
+
+    def locate():
+        chk(L.fmx_locate_count_device(h, 0, d_s.data_ptr(), d_e.data_ptr(), npat, d_hoff.data_ptr(), C.byref(total), sp))
+        if d_pos[0].numel() < total.value:
+            d_pos[0] = torch.empty(total.value + 1024, dtype=torch.int64, device="cuda")
+        chk(L.fmx_locate_fill_device(h, 0, d_s.data_ptr(), d_e.data_ptr(), npat, d_hoff.data_ptr(), total.value,
+                                     d_pos[0].data_ptr(), None, sp))
+
+    for _ in range(args.warmup):
+        flush.zero_()
+        search()
+        locate()
+    chk(L.fmx_search_check(h, sp))
+    search_steps, lf_steps = index.last_work(sp)
+    hits = total.value
+    torch.cuda.synchronize()
+
+    # ---- timed region (device-resident inputs)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    sampler = ClockSampler(local)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = L.fmx_launch_count()
+    sampler.start()
+    wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()  # L2 flush between timed iterations
+        ev[k][0].record(stream)
+        search()
+        ev[k][1].record(stream)
+        locate()
+        ev[k][2].record(stream)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    launches = L.fmx_launch_count() - launches0
+    if world > 1:
+        dist.barrier()
+    t_search = np.array([ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps)])
+    t_locate = np.array([ev[k][1].elapsed_time(ev[k][2]) for k in range(args.steps)])
+    t_step = np.array([ev[k][0].elapsed_time(ev[k][2]) for k in range(args.steps)])
+    ms_total = float(t_step.sum())
+    if world > 1:
+        tt = torch.tensor([ms_total, float(t_search.sum()), float(t_locate.sum())], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total, ms_search_total, ms_locate_total = [float(v) for v in tt.tolist()]
+        hh = torch.tensor([hits], device="cuda", dtype=torch.int64)
+        dist.all_reduce(hh, op=dist.ReduceOp.SUM)
+        hits_all = int(hh.item())
+    else:
+        ms_search_total, ms_locate_total = float(t_search.sum()), float(t_locate.sum())
+        hits_all = hits
+    ms_per_step = ms_total / args.steps
+    value = world * npat / (ms_per_step * 1e-3)
+
+    # ---- end to end through the host-buffer C ABI: pinned host inputs, H2D + D2H inside the timed region
+    h_pat = torch.from_numpy(pats).pin_memory()
+    h_s = torch.empty(npat, dtype=torch.int64).pin_memory()
+    h_e = torch.empty(npat, dtype=torch.int64).pin_memory()
+    h_hoff = torch.empty(npat + 1, dtype=torch.int64).pin_memory()
+    ppos = C.c_void_p()
+
+    def e2e_step():
+        chk(L.fmx_search_batch(h, 0, h_pat.data_ptr(), None, m, npat, None, None, h_s.data_ptr(), h_e.data_ptr()))
+        chk(L.fmx_locate_batch(h, 0, h_s.data_ptr(), h_e.data_ptr(), npat, h_hoff.data_ptr(), C.byref(ppos), None))
+        nh = int(h_hoff[npat])
+        L.fmx_free(ppos)
+        return nh
+
+    for _ in range(2):
+        e2e_step()
+    e2e_steps = max(3, min(args.steps, 10))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        nh = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        tt = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    h2d = npat * m + 2 * 8 * npat
+    d2h = 2 * 8 * npat + 8 * (npat + 1) + 8 * nh
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (k_search): algorithmic bytes = 32 B x 2 x L x executed steps
+    Lw = int(mc).bit_length()
+    peak, peak_src = measured_peaks()
+    ms_search = ms_search_total / args.steps
+    alg_bytes_search = 32.0 * 2 * Lw * search_steps
+    alg_bytes_locate = 32.0 * (Lw * lf_steps + hits)
+    achieved = alg_bytes_search / (ms_search * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_search", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes_search, "kernel_ms": ms_search,
+                "executed_search_steps": int(search_steps), "executed_lf_steps": int(lf_steps),
+                "locate_kernel": {"achieved": alg_bytes_locate / (max(ms_locate_total / args.steps, 1e-9) * 1e-3) / 1e9,
+                                  "phase_ms": ms_locate_total / args.steps}}
+    if not args.no_gather_peak:
+        try:
+            gp = fmx.random_gather_peak(local, nbytes=4 << 30, nloads=1 << 28, iters=3)
+            sect = alg_bytes_search / 32.0 / (ms_search * 1e-3)
+            roofline["random_access"] = {"peak_sectors_per_s": gp, "peak_GBps": gp * 32 / 1e9,
+                                         "achieved_sectors_per_s": sect, "frac": sect / gp,
+                                         "how": "independent random 32 B gathers over a 4 GiB buffer, best of 3"}
+        except Exception as ex:  # pragma: no cover
+            roofline["random_access"] = {"error": str(ex)}
+
+    # ---- CPU baseline beside it: the oracle port on all host threads, bounded sample; also the parity check
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import oracle as orc
+
+        nthreads = host_threads()
+        sample = min(npat, args.cpu_sample)
+        tb = time.perf_counter()
+        oracle_index = orc.OracleIndex(text, orc.FM, level=level, max_character=mc)
+        obuild = time.perf_counter() - tb
+        best = None
+        for _ in range(2):
+            dt, s, e, ohoff, opos = run_cpu_path(oracle_index, pats[:sample], nthreads)
+            best = dt if best is None else min(best, dt)
+        g_s = d_s[:sample].cpu().numpy().view(np.uint64)
+        g_e = d_e[:sample].cpu().numpy().view(np.uint64)
+        g_hoff = d_hoff[: sample + 1].cpu().numpy().view(np.uint64)
+        g_pos = d_pos[0][: int(g_hoff[-1])].cpu().numpy().view(np.uint64)
+        parity = bool(np.array_equal(g_s, s) and np.array_equal(g_e, e) and np.array_equal(g_hoff, ohoff)
+                      and np.array_equal(g_pos, opos))
+        cpu = {"value": sample / best, "unit": "queries/s", "cores": nthreads, "kind": "port",
+               "sample": f"first {sample} patterns of the workload, count+locate, best of 2",
+               "located_hits_per_s": int(ohoff[-1]) / best, "cpu_model": cpu_model(),
+               "index_build_s": round(obuild, 1), "gpu_matches_oracle_on_sample": parity}
+        if not parity:
+            print("PARITY FAILURE: GPU results differ from the oracle on the sample", file=sys.stderr)
+
+    line = {
+        "metric": "count+locate queries/s", "value": value, "unit": "queries/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32/u64 integer", "data": "synthetic",
+        "config": {"workload": args.workload, "description": desc, "text_len": n + 1, "patterns_per_step_per_gpu": npat,
+                   "pattern_len": m, "pattern_mix": "50% sampled from text / 50% uniform random",
+                   "index": "FMIndexWithLocate", "sampling_level": level, "wavelet_levels": Lw,
+                   "index_device_bytes": index.heap_size(), "l2": "flushed between timed iterations (512 MiB memset)",
+                   "parallelism": f"index replicated x{world}, query batches sharded", "index_build_s": round(build_s, 1)},
+        "count_queries_per_s": world * npat / (ms_search_total / args.steps * 1e-3),
+        "located_hits_per_s": hits_all / (ms_per_step * 1e-3),
+        "hits_per_step": hits_all,
+        "e2e": {"value": world * npat / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s * 1e3, "api": "fmx_search_batch + fmx_locate_batch (host buffers, pinned inputs)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "wall_ms_per_step_incl_flush": wall / args.steps * 1e3,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,447 @@
+"""fmx -- B200-native batched FM-index query engine.
+
+Host-side mirror of the reference crate's public API (ajalab/fm-index 0.3.1, src/frontend.rs,
+src/text.rs) over the C ABI in include/fmx.h: same type names, same argument meaning, same
+error behaviour, plus the batched entries the GPU path exists for.  All queries run as CUDA
+kernels on a B200; there is no CPU fallback (a missing CUDA library or device is an error).
+
+    text  = Text.new(b"mississippi\\0")
+    index = FMIndexWithLocate.new(text, 2)
+    s = index.search(b"ssi")
+    s.count(); [m.locate() for m in s.iter_matches()]
+    batch = index.search_batch([b"ssi", b"pp"])          # many patterns, one launch
+    batch.count(); batch.locate()
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import load as load_library
+
+__all__ = [
+    "Text", "Error", "InvalidText", "PieceId", "FMIndex", "FMIndexWithLocate", "RLFMIndex",
+    "RLFMIndexWithLocate", "FMIndexMultiPieces", "FMIndexMultiPiecesWithLocate", "Search", "Match",
+    "SearchBatch", "load_library", "suffix_array", "random_gather_peak",
+]
+
+KIND_FM, KIND_RLFM, KIND_MULTI = 0, 1, 2
+SEARCH, SEARCH_PREFIX, SEARCH_SUFFIX, SEARCH_EXACT = 0, 1, 2, 3
+_NONE = (1 << 64) - 1
+
+
+class Error(Exception):
+    """src/error.rs:1-20"""
+
+    def __init__(self, msg, code=0):
+        super().__init__(msg)
+        self.code = code
+
+
+class InvalidText(Error):
+    """Error::InvalidText (src/error.rs:5)"""
+
+    def __str__(self):
+        return "invalid text: " + super().__str__()
+
+
+def _check(rc):
+    if rc == 0:
+        return
+    msg = (load_library().fmx_last_error() or b"").decode()
+    if rc == -1:
+        raise InvalidText(msg, rc)
+    if rc == -5:
+        raise IndexError(msg)  # the reference panics with an index-out-of-bounds (fm_index.rs:94)
+    raise Error(msg, rc)
+
+
+def _as_u8(x) -> np.ndarray:
+    if isinstance(x, np.ndarray):
+        return np.ascontiguousarray(x, dtype=np.uint8)
+    if isinstance(x, str):
+        x = x.encode()
+    if isinstance(x, (bytes, bytearray, memoryview)):
+        return np.frombuffer(bytes(x), dtype=np.uint8)
+    return np.ascontiguousarray(np.asarray(list(x), dtype=np.uint8))
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class PieceId(int):
+    """src/piece.rs:1-15"""
+
+    def __repr__(self):
+        return f"PieceId({int(self)})"
+
+
+class Text:
+    """src/text.rs:10-64 (u8 characters)."""
+
+    def __init__(self, text, max_character=255):
+        self._text = _as_u8(text)
+        self._max_character = int(max_character)
+
+    @classmethod
+    def new(cls, text):
+        """Text::new: max_character = C::max_value() (text.rs:28-33)"""
+        return cls(text, 255)
+
+    @classmethod
+    def with_max_character(cls, text, max_character):
+        """text.rs:44-49"""
+        return cls(text, max_character)
+
+    def text(self):
+        return self._text
+
+    def max_character(self):
+        return self._max_character
+
+    def max_bits(self):
+        """text.rs:61-63"""
+        return int(self._max_character).bit_length()
+
+
+def _pack(patterns):
+    """-> (flat u8, offsets u64 or None, fixed_len, npat)"""
+    if isinstance(patterns, np.ndarray) and patterns.ndim == 2:
+        p = np.ascontiguousarray(patterns, dtype=np.uint8)
+        return p.reshape(-1), None, p.shape[1], p.shape[0]
+    if isinstance(patterns, tuple) and len(patterns) == 2:
+        flat = np.ascontiguousarray(patterns[0], dtype=np.uint8)
+        off = np.ascontiguousarray(patterns[1], dtype=np.uint64)
+        return flat, off, 0, off.size - 1
+    arrs = [_as_u8(p) for p in patterns]
+    off = np.zeros(len(arrs) + 1, dtype=np.uint64)
+    if arrs:
+        off[1:] = np.cumsum([a.size for a in arrs], dtype=np.uint64)
+    flat = np.concatenate(arrs) if arrs and int(off[-1]) > 0 else np.zeros(0, dtype=np.uint8)
+    return np.ascontiguousarray(flat), off, 0, len(arrs)
+
+
+class _Index:
+    """Common part of the six index types (SearchIndex trait, frontend.rs:26-45)."""
+
+    _kind = KIND_FM
+    _locate = False
+
+    def __init__(self, text: Text, level=None, device=0, _handle=None):
+        L = load_library()
+        self._L = L
+        if _handle is not None:
+            self._h = _handle
+            return
+        if not isinstance(text, Text):
+            text = Text.new(text)
+        lvl = -1
+        if self._locate:
+            if level is None:
+                raise TypeError("a sampling level is required (FMIndexWithLocate::new(&text, level))")
+            lvl = int(level)
+        t = text.text()
+        h = C.c_void_p()
+        _check(L.fmx_index_build(_ptr(t), t.size, 1, text.max_character(), self._kind, lvl, device, C.byref(h)))
+        self._h = h
+
+    @classmethod
+    def new(cls, text, *args, **kw):
+        return cls(text, *args, **kw)
+
+    @classmethod
+    def load(cls, path, device=0):
+        L = load_library()
+        h = C.c_void_p()
+        _check(L.fmx_index_load(str(path).encode(), device, C.byref(h)))
+        self = cls(None, _handle=h)
+        if L.fmx_index_kind(h) != cls._kind or bool(L.fmx_index_has_locate(h)) != cls._locate:
+            L.fmx_index_free(h)
+            self._h = None
+            raise Error("index file holds a different index type")
+        return self
+
+    def save(self, path):
+        _check(self._L.fmx_index_save(self._h, str(path).encode()))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._L.fmx_index_free(h)
+            self._h = None
+
+    # ---- SearchIndex
+    def len(self):
+        return int(self._L.fmx_index_len(self._h))
+
+    __len__ = len
+
+    def heap_size(self):
+        """frontend.rs:41-44; here: bytes of the device-resident index."""
+        return int(self._L.fmx_index_device_bytes(self._h))
+
+    def search(self, pattern):
+        return Search(self, SEARCH)._refine(pattern)
+
+    # ---- batched entries
+    def search_batch(self, patterns, mode=SEARCH, init=None):
+        """Batched SearchIndex::search over many patterns (one kernel launch)."""
+        flat, off, fixed, npat = _pack(patterns)
+        s = np.zeros(npat, dtype=np.uint64)
+        e = np.zeros(npat, dtype=np.uint64)
+        ins = ine = None
+        if init is not None:
+            ins = np.ascontiguousarray(init[0], dtype=np.uint64)
+            ine = np.ascontiguousarray(init[1], dtype=np.uint64)
+        _check(self._L.fmx_search_batch(self._h, mode, _ptr(flat), _ptr(off), fixed, npat, _ptr(ins), _ptr(ine),
+                                        _ptr(s), _ptr(e)))
+        return SearchBatch(self, mode, s, e)
+
+    def locate_batch(self, s, e, prefix_only=False, piece_ids=False):
+        s = np.ascontiguousarray(s, dtype=np.uint64)
+        e = np.ascontiguousarray(e, dtype=np.uint64)
+        npat = s.size
+        off = np.zeros(npat + 1, dtype=np.uint64)
+        ppos, ppid = C.c_void_p(), C.c_void_p()
+        _check(self._L.fmx_locate_batch(self._h, int(prefix_only), _ptr(s), _ptr(e), npat, _ptr(off), C.byref(ppos),
+                                        C.byref(ppid) if piece_ids else None))
+        total = int(off[-1])
+
+        def take(p):
+            if not p.value:
+                return np.zeros(0, dtype=np.uint64)
+            a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(total,)).copy()
+            self._L.fmx_free(p)
+            return a
+
+        pos = take(ppos)
+        return (off, pos, take(ppid)) if piece_ids else (off, pos)
+
+    def extract_batch(self, rows, k, forward):
+        rows = np.ascontiguousarray(rows, dtype=np.uint64)
+        out = np.zeros((rows.size, k), dtype=np.uint8)
+        out_len = np.zeros(rows.size, dtype=np.uint32)
+        _check(self._L.fmx_extract_batch(self._h, _ptr(rows), rows.size, k, int(forward), _ptr(out), _ptr(out_len)))
+        return out, out_len
+
+    def rows_op(self, op, rows):
+        rows = np.ascontiguousarray(rows, dtype=np.uint64)
+        out = np.zeros(rows.size, dtype=np.uint64)
+        _check(self._L.fmx_rows_op(self._h, op, _ptr(rows), rows.size, _ptr(out)))
+        return out
+
+    def lf_map2_batch(self, c, i):
+        c = np.ascontiguousarray(c, dtype=np.uint8)
+        i = np.ascontiguousarray(i, dtype=np.uint64)
+        out = np.zeros(i.size, dtype=np.uint64)
+        _check(self._L.fmx_lf_map2_batch(self._h, _ptr(c), _ptr(i), i.size, _ptr(out)))
+        return out
+
+    def last_work(self, stream=None):
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        _check(self._L.fmx_last_work(self._h, stream, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+
+class _MultiMixin:
+    """SearchIndexWithMultiPieces (frontend.rs:47-63)."""
+
+    def search_prefix(self, pattern):
+        return Search(self, SEARCH_PREFIX)._refine(pattern)
+
+    def search_suffix(self, pattern):
+        return Search(self, SEARCH_SUFFIX)._refine(pattern)
+
+    def search_exact(self, pattern):
+        return Search(self, SEARCH_EXACT)._refine(pattern)
+
+    def pieces_count(self):
+        return int(self._L.fmx_index_pieces_count(self._h))
+
+
+class FMIndex(_Index):
+    """frontend.rs:110, :195-203"""
+    _kind, _locate = KIND_FM, False
+
+
+class FMIndexWithLocate(_Index):
+    """frontend.rs:124-126, :205-218"""
+    _kind, _locate = KIND_FM, True
+
+
+class RLFMIndex(_Index):
+    """frontend.rs:139, :220-228"""
+    _kind, _locate = KIND_RLFM, False
+
+
+class RLFMIndexWithLocate(_Index):
+    """frontend.rs:153-155, :230-243"""
+    _kind, _locate = KIND_RLFM, True
+
+
+class FMIndexMultiPieces(_MultiMixin, _Index):
+    """frontend.rs:168-170, :245-252"""
+    _kind, _locate = KIND_MULTI, False
+
+
+class FMIndexMultiPiecesWithLocate(_MultiMixin, _Index):
+    """frontend.rs:184-186, :254-267"""
+    _kind, _locate = KIND_MULTI, True
+
+
+class Search:
+    """Search trait (frontend.rs:65-83) over wrapper.rs:14-23."""
+
+    def __init__(self, index, mode, s=None, e=None):
+        self._index = index
+        self._mode = mode
+        self._s = s
+        self._e = e
+        self._cache = None
+
+    def _refine(self, pattern):
+        p = _as_u8(pattern)
+        init = None if self._s is None else (np.array([self._s], dtype=np.uint64), np.array([self._e], dtype=np.uint64))
+        b = self._index.search_batch([p], self._mode, init)
+        return Search(self._index, self._mode, int(b.s[0]), int(b.e[0]))
+
+    def search(self, pattern):
+        """Refine: prepends `pattern` (wrapper.rs:99-124)."""
+        return self._refine(pattern)
+
+    def get_range(self):
+        """wrapper.rs:126-129 (test-only in the reference)"""
+        return self._s, self._e
+
+    def count(self):
+        """wrapper.rs:132-134: e - s, ignoring the prefix filter."""
+        return self._e - self._s
+
+    @property
+    def _prefix_only(self):
+        return self._mode in (SEARCH_PREFIX, SEARCH_EXACT)
+
+    def _rows(self):
+        if self._e <= self._s:
+            return np.zeros(0, dtype=np.uint64)
+        rows = np.arange(self._s, self._e, dtype=np.uint64)
+        if self._prefix_only:  # wrapper.rs:208
+            rows = rows[self._index.rows_op(0, rows) == 0]
+        return rows
+
+    def _hits(self):
+        if self._cache is None:
+            rows = self._rows()
+            pos = pid = None
+            if self._index._locate and rows.size:
+                if self._index._kind == KIND_MULTI:
+                    _, pos, pid = self._index.locate_batch([self._s], [self._e], self._prefix_only, piece_ids=True)
+                else:
+                    _, pos = self._index.locate_batch([self._s], [self._e], self._prefix_only)
+            self._cache = (rows, pos, pid)
+        return self._cache
+
+    def iter_matches(self):
+        """wrapper.rs:137-139, 203-217: ascending SA-row order."""
+        rows, pos, pid = self._hits()
+        for k in range(rows.size):
+            yield Match(self._index, int(rows[k]), None if pos is None else int(pos[k]),
+                        None if pid is None else int(pid[k]))
+
+
+class Match:
+    """Match / MatchWithLocate / MatchWithPieceId (frontend.rs:85-104) over wrapper.rs:219-248."""
+
+    def __init__(self, index, row, position=None, piece=None):
+        self._index = index
+        self._i = row
+        self._position = position
+        self._piece = piece
+
+    def row(self):
+        return self._i
+
+    def locate(self):
+        if not self._index._locate:
+            raise AttributeError("locate() needs a ...WithLocate index (MatchWithLocate, frontend.rs:94-98)")
+        if self._position is None:
+            self._position = int(self._index.rows_op(4, [self._i])[0])
+        return self._position
+
+    def piece_id(self):
+        if not (self._index._locate and self._index._kind == KIND_MULTI):
+            raise AttributeError("piece_id() needs FMIndexMultiPiecesWithLocate (frontend.rs:542)")
+        if self._piece is None:
+            _, _, pid = self._index.locate_batch([self._i], [self._i + 1], False, piece_ids=True)
+            self._piece = int(pid[0])
+        return PieceId(self._piece)
+
+    def _iter(self, forward):
+        k, done = 32, 0
+        while True:
+            out, ln = self._index.extract_batch([self._i], k, forward)
+            n = int(ln[0])
+            for t in range(done, n):
+                yield int(out[0, t])
+            if n < k:  # forward ended (fl_map None, multi_pieces.rs:171-181)
+                return
+            done, k = n, k * 2
+
+    def iter_chars_forward(self):
+        """wrapper.rs:229-231, 175-183"""
+        return self._iter(True)
+
+    def iter_chars_backward(self):
+        """wrapper.rs:233-235, 154-161 (never ends: the walk is cyclic)"""
+        return self._iter(False)
+
+
+class SearchBatch:
+    """Result of a batched search: SA ranges of many patterns, resident on the host."""
+
+    def __init__(self, index, mode, s, e):
+        self._index, self._mode, self.s, self.e = index, mode, s, e
+
+    def __len__(self):
+        return self.s.size
+
+    def count(self):
+        return self.e - self.s
+
+    def search_batch(self, patterns):
+        return self._index.search_batch(patterns, self._mode, init=(self.s, self.e))
+
+    def locate(self, piece_ids=False):
+        """-> (hit_off[npat+1], positions[, piece_ids]); matches of pattern p are
+        positions[hit_off[p]:hit_off[p+1]] in the reference's iteration order."""
+        return self._index.locate_batch(self.s, self.e, self._mode in (SEARCH_PREFIX, SEARCH_EXACT), piece_ids)
+
+
+def suffix_array(text) -> np.ndarray:
+    """sais::build_suffix_array (sais.rs:115-144) through the C ABI (host side)."""
+    t = _as_u8(text)
+    sa = np.zeros(max(t.size, 1), dtype=np.uint64)
+    _check(load_library().fmx_build_suffix_array(_ptr(t), t.size, 1, _ptr(sa)))
+    return sa[: t.size]
+
+
+def blob_build(text: Text, kind, level=None) -> np.ndarray:
+    """Host-only half of construction: the device-layout blob as bytes."""
+    L = load_library()
+    t = text.text()
+    p, nb = C.c_void_p(), C.c_uint64(0)
+    _check(L.fmx_blob_build(_ptr(t), t.size, 1, text.max_character(), kind, -1 if level is None else level,
+                            C.byref(p), C.byref(nb)))
+    a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(nb.value,)).copy()
+    L.fmx_free(p)
+    return a
+
+
+def random_gather_peak(device=0, nbytes=4 << 30, nloads=1 << 28, iters=3) -> float:
+    """Measured peak random 32-byte sector gather rate (sectors/s): the random-access roofline."""
+    v = C.c_double(0)
+    _check(load_library().fmx_random_gather_bench(device, nbytes, nloads, iters, C.byref(v)))
+    return v.value

@@ -1,0 +1,343 @@
+// builder.cpp -- host-side index construction: text -> device-layout blob.
+//
+// Restates the host-side producers of the hot path's inputs:
+//   sais.rs:9-32 (cs), sais.rs:115-144 (validation + SA), fm_index.rs:44-58 (BWT into a
+//   wavelet matrix), sample.rs:21-44 (suffix-order sampling), rlfmi.rs:37-96 (run heads, b, bp,
+//   run-count cs), multi_pieces.rs:53-97 (doc array, sa_idx_first_text)
+// and lays the result out for the GPU (fmx_layout.h).  Construction is not the hot path.
+#include "builder.h"
+
+#include <algorithm>
+#include <cstring>
+
+#include "../../include/fmx.h"
+#include "sais.hpp"
+
+namespace fmx {
+
+static inline uint32_t log2_u64(uint64_t x) { return 63u - (uint32_t)__builtin_clzll(x); }  // util.rs:1-3
+
+// sais.rs:121-139
+static int validate_text(const uint8_t *text, uint64_t n, std::string &err) {
+    if (n <= 1) return 0;
+    if (text[0] == 0) {
+        err = "the given text must not start with zero character";
+        return FMX_ERR_INVALID_TEXT;
+    }
+    if (!(text[n - 1] == 0 && text[n - 2] != 0)) {
+        err = "the given text must end with exactly one zero character";
+        return FMX_ERR_INVALID_TEXT;
+    }
+    return 0;
+}
+
+// Suffix array as u32 (n < 2^32).
+static void suffix_array_u32(const uint8_t *text, uint64_t n, std::vector<uint32_t> &sa) {
+    sa.resize(n);
+    if (n == 0) return;
+    // the trailing \0 is a unique minimum iff the text has no interior zero
+    bool unique = text[n - 1] == 0 && std::memchr(text, 0, n - 1) == nullptr;
+    if (n < (1ull << 31) - 2) {
+        suffix_array_bytes<int32_t>(text, n, reinterpret_cast<int32_t *>(sa.data()), unique);
+    } else {
+        std::vector<int64_t> tmp(n);
+        suffix_array_bytes<int64_t>(text, n, tmp.data(), unique);
+        for (uint64_t i = 0; i < n; i++) sa[i] = (uint32_t)tmp[i];
+    }
+}
+
+int build_suffix_array(const uint8_t *text, uint64_t n, uint64_t *sa_out, std::string &err) {
+    int rc = validate_text(text, n, err);
+    if (rc) return rc;
+    if (n >= (1ull << 32) - 1) {
+        err = "text length must be below 2^32 - 1";
+        return FMX_ERR_UNSUPPORTED;
+    }
+    std::vector<uint32_t> sa;
+    suffix_array_u32(text, n, sa);
+    for (uint64_t i = 0; i < n; i++) sa_out[i] = sa[i];
+    return 0;
+}
+
+// One rank-able bit vector in RB32 form (fmx_layout.h).
+struct RBVec {
+    uint64_t nbits, nblk;
+    std::vector<uint32_t> w;
+    explicit RBVec(uint64_t nbits_ = 0) : nbits(nbits_), nblk(nbits_ / FMX_RB_BITS + 1), w(8 * (nbits_ / FMX_RB_BITS + 1), 0) {}
+    inline void set(uint64_t pos) {
+        uint64_t b = pos / FMX_RB_BITS;
+        uint32_t r = (uint32_t)(pos - b * FMX_RB_BITS);
+        w[b * 8 + 1 + (r >> 5)] |= 1u << (r & 31);
+    }
+    uint64_t finish() {
+        uint64_t acc = 0;
+        for (uint64_t b = 0; b < nblk; b++) {
+            w[b * 8] = (uint32_t)acc;
+            for (int k = 1; k < 8; k++) acc += (uint64_t)__builtin_popcount(w[b * 8 + k]);
+        }
+        return acc;
+    }
+    uint64_t rank1(uint64_t pos) const {
+        uint64_t b = pos / FMX_RB_BITS;
+        uint32_t r = (uint32_t)(pos - b * FMX_RB_BITS);
+        uint64_t c = w[b * 8];
+        for (uint32_t k = 0; k < 7; k++) {
+            if (r >= 32 * (k + 1)) c += (uint64_t)__builtin_popcount(w[b * 8 + 1 + k]);
+            else if (r > 32 * k) c += (uint64_t)__builtin_popcount(w[b * 8 + 1 + k] & ((1u << (r - 32 * k)) - 1u));
+        }
+        return c;
+    }
+    uint64_t bytes() const { return w.size() * 4; }
+};
+
+struct WMat {
+    uint32_t L = 0;
+    uint64_t n = 0;
+    std::vector<RBVec> lv;
+    std::vector<uint64_t> zeros;
+    // walk of position `pos` along symbol c's path
+    uint64_t walk(uint64_t pos, uint32_t c) const {
+        for (uint32_t l = 0; l < L; l++) {
+            uint64_t ones = lv[l].rank1(pos);
+            pos = ((c >> (L - 1 - l)) & 1) ? zeros[l] + ones : pos - ones;
+        }
+        return pos;
+    }
+};
+
+// vers WaveletMatrix::from_slice semantics: level 0 = MSB, stable zero/one partition per level
+static void build_wavelet(const uint8_t *seq, uint64_t n, uint32_t L, WMat &m) {
+    m.L = L;
+    m.n = n;
+    m.lv.clear();
+    m.zeros.assign(L, 0);
+    std::vector<uint8_t> cur(seq, seq + n), nxt(n);
+    for (uint32_t l = 0; l < L; l++) {
+        uint32_t sh = L - 1 - l;
+        m.lv.emplace_back(n);
+        RBVec &v = m.lv.back();
+        uint64_t z = 0;
+        for (uint64_t i = 0; i < n; i++) {
+            if ((cur[i] >> sh) & 1) v.set(i); else z++;
+        }
+        v.finish();
+        m.zeros[l] = z;
+        if (l + 1 < L) {
+            uint64_t p0 = 0, p1 = z;
+            for (uint64_t i = 0; i < n; i++) {
+                if ((cur[i] >> sh) & 1) nxt[p1++] = cur[i]; else nxt[p0++] = cur[i];
+            }
+            cur.swap(nxt);
+        }
+    }
+}
+
+struct SectionData {
+    const void *ptr = nullptr;
+    uint64_t bytes = 0;
+};
+
+int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level,
+               std::vector<uint8_t> &blob, std::string &err) {
+    if (mc == 0 || mc > 255) {
+        err = "max_character must be in 1..=255 for u8 texts";
+        return FMX_ERR_INVALID_ARG;
+    }
+    if (kind != FMX_KIND_FM && kind != FMX_KIND_RLFM && kind != FMX_KIND_MULTI) {
+        err = "unknown index kind";
+        return FMX_ERR_INVALID_ARG;
+    }
+    if (n >= (1ull << 32) - 1) {
+        err = "text length must be below 2^32 - 1 (u32 rank counts in the device layout)";
+        return FMX_ERR_UNSUPPORTED;
+    }
+    for (uint64_t i = 0; i < n; i++) {
+        if (text[i] > mc) {  // sais.rs:16-18 would index occs out of bounds (panic)
+            err = "text contains a character larger than max_character";
+            return FMX_ERR_INVALID_ARG;
+        }
+    }
+    int rc = validate_text(text, n, err);
+    if (rc) return rc;
+
+    const uint32_t L = log2_u64(mc) + 1;  // text.rs:61-63
+    const uint32_t cs_len = (uint32_t)mc + 1;
+
+    std::vector<uint32_t> sa;
+    suffix_array_u32(text, n, sa);
+
+    // BWT: bw[i] = text[sa[i]-1], 0 when sa[i] == 0 (fm_index.rs:48-55; rlfmi.rs:49-53 uses
+    // text[n-1] there, which is the same \0 for every text that passes validation with n >= 2)
+    std::vector<uint8_t> bwt(n);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; i++) bwt[i] = sa[i] ? text[sa[i] - 1] : (kind == FMX_KIND_RLFM && n ? text[n - 1] : 0);
+
+    FmxBlobHeader hdr;
+    std::memset(&hdr, 0, sizeof(hdr));
+    hdr.magic = FMX_BLOB_MAGIC;
+    hdr.version = FMX_BLOB_VERSION;
+    hdr.kind = (uint32_t)kind;
+    hdr.n = n;
+    hdr.levels = L;
+    hdr.max_character = (uint32_t)mc;
+    hdr.cs_len = cs_len;
+
+    WMat wm;
+    std::vector<uint32_t> cs(cs_len + 1, 0), adj(cs_len, 0);
+    std::vector<uint32_t> doc, piece_end, bsel, bpsel;
+    RBVec rb_b(0), rb_bp(0);
+
+    if (kind == FMX_KIND_FM || kind == FMX_KIND_MULTI) {
+        std::vector<uint64_t> occ(cs_len, 0);
+        for (uint64_t i = 0; i < n; i++) occ[text[i]]++;
+        uint64_t sum = 0;
+        for (uint32_t c = 0; c < cs_len; c++) {  // sais.rs:21-32
+            cs[c] = (uint32_t)sum;
+            sum += occ[c];
+        }
+        cs[cs_len] = (uint32_t)n;
+        build_wavelet(bwt.data(), n, L, wm);
+        hdr.seq_len = n;
+        if (kind == FMX_KIND_MULTI) {
+            // multi_pieces.rs:53-79
+            for (uint64_t i = 0; i < n; i++)
+                if (text[i] == 0) piece_end.push_back((uint32_t)i);
+            uint64_t zc = piece_end.size();
+            doc.assign(zc, 0);
+            uint64_t k = 0;
+            for (uint64_t p = 0; p < n; p++) {
+                if (bwt[p] != 0) continue;  // p = select(bw, k, 0)
+                if (k >= zc) {               // the reference would index doc out of bounds (panic)
+                    err = "text without a \\0 terminator cannot be indexed as multi-pieces";
+                    return FMX_ERR_INVALID_TEXT;
+                }
+                uint64_t em = sa[p] ? sa[p] - 1 : n - 1;  // modular_sub(sa[p], 1, n)
+                uint64_t pid = (uint64_t)(std::lower_bound(piece_end.begin(), piece_end.end(), (uint32_t)em) - piece_end.begin());
+                if (pid == zc - 1) hdr.first_row = p;
+                doc[k++] = (uint32_t)pid;
+            }
+            hdr.ndoc = zc;
+        }
+    } else {
+        // rlfmi.rs:37-96
+        std::vector<uint8_t> heads;
+        std::vector<uint32_t> starts;
+        rb_b = RBVec(n);
+        rb_bp = RBVec(n);
+        uint32_t c0 = 0;
+        for (uint64_t i = 0; i < n; i++) {
+            uint32_t c = bwt[i];
+            if (c0 != c) {
+                heads.push_back((uint8_t)c);
+                starts.push_back((uint32_t)i);
+                rb_b.set(i);
+            } else if (heads.empty()) {
+                err = "text not representable by RLFMIndex (the reference hits unreachable!() at rlfmi.rs:62)";
+                return FMX_ERR_INVALID_TEXT;
+            }
+            c0 = c;
+        }
+        rb_b.finish();
+        uint64_t r = heads.size();
+        hdr.runs = r;
+        hdr.seq_len = r;
+        build_wavelet(heads.data(), r, L, wm);
+        bsel.assign(r + 1, (uint32_t)n);
+        for (uint64_t j = 0; j < r; j++) bsel[j] = starts[j];
+        // cs over run heads; bp groups runs by head character, stably
+        std::vector<uint64_t> cnt(cs_len, 0), len_by_c(cs_len, 0);
+        for (uint64_t j = 0; j < r; j++) {
+            cnt[heads[j]]++;
+            len_by_c[heads[j]] += (uint64_t)bsel[j + 1] - bsel[j];
+        }
+        std::vector<uint64_t> next_run(cs_len, 0), next_pos(cs_len, 0);
+        uint64_t acc = 0, pacc = 0;
+        for (uint32_t c = 0; c < cs_len; c++) {
+            cs[c] = (uint32_t)acc;
+            next_run[c] = acc;
+            next_pos[c] = pacc;
+            acc += cnt[c];
+            pacc += len_by_c[c];
+        }
+        cs[cs_len] = (uint32_t)r;
+        bpsel.assign(r + 1, (uint32_t)n);
+        for (uint64_t j = 0; j < r; j++) {
+            uint8_t c = heads[j];
+            rb_bp.set(next_pos[c]);
+            bpsel[next_run[c]++] = (uint32_t)next_pos[c];
+            next_pos[c] += (uint64_t)bsel[j + 1] - bsel[j];
+        }
+        rb_bp.finish();
+    }
+    for (uint32_t l = 0; l < L; l++) hdr.zeros[l] = wm.zeros[l];
+    for (uint32_t c = 0; c < cs_len; c++) adj[c] = cs[c] - (uint32_t)wm.walk(0, c);
+
+    // sample.rs:21-44
+    std::vector<uint32_t> samples;
+    if (level >= 0) {
+        hdr.has_locate = 1;
+        uint32_t lvl = (uint32_t)level;
+        if (n > 0) {
+            hdr.sa_word_size = log2_u64(n) + 1;
+            if (lvl >= 63 || n <= (1ull << lvl)) lvl = 0;  // sample.rs:28-31
+            hdr.sa_level = lvl;
+            hdr.sa_count = ((n - 1) >> lvl) + 1;
+            samples.resize(hdr.sa_count);
+#pragma omp parallel for schedule(static)
+            for (int64_t i = 0; i < (int64_t)hdr.sa_count; i++) samples[i] = sa[(uint64_t)i << lvl];
+        }
+    }
+    std::vector<uint32_t>().swap(sa);
+
+    // ---- assemble
+    SectionData sec[SEC_COUNT];
+    for (uint32_t l = 0; l < L; l++) sec[SEC_LEVEL0 + l] = {wm.lv[l].w.data(), wm.lv[l].bytes()};
+    sec[SEC_ADJ] = {adj.data(), adj.size() * 4};
+    sec[SEC_CS] = {cs.data(), cs.size() * 4};
+    if (!samples.empty()) sec[SEC_SA] = {samples.data(), samples.size() * 4};
+    if (!doc.empty()) sec[SEC_DOC] = {doc.data(), doc.size() * 4};
+    if (!piece_end.empty()) sec[SEC_PIECE_END] = {piece_end.data(), piece_end.size() * 4};
+    if (kind == FMX_KIND_RLFM) {
+        sec[SEC_RL_B] = {rb_b.w.data(), rb_b.bytes()};
+        sec[SEC_RL_BP] = {rb_bp.w.data(), rb_bp.bytes()};
+        sec[SEC_RL_BSEL] = {bsel.data(), bsel.size() * 4};
+        sec[SEC_RL_BPSEL] = {bpsel.data(), bpsel.size() * 4};
+    }
+    uint64_t off = (sizeof(FmxBlobHeader) + FMX_SECTION_ALIGN - 1) / FMX_SECTION_ALIGN * FMX_SECTION_ALIGN;
+    for (int k = 0; k < (int)SEC_COUNT; k++) {
+        hdr.sec[k].offset = sec[k].bytes ? off : 0;
+        hdr.sec[k].bytes = sec[k].bytes;
+        off += (sec[k].bytes + FMX_SECTION_ALIGN - 1) / FMX_SECTION_ALIGN * FMX_SECTION_ALIGN;
+    }
+    hdr.total_bytes = off;
+    blob.assign(off, 0);
+    std::memcpy(blob.data(), &hdr, sizeof(hdr));
+    for (int k = 0; k < (int)SEC_COUNT; k++)
+        if (sec[k].bytes) std::memcpy(blob.data() + hdr.sec[k].offset, sec[k].ptr, sec[k].bytes);
+    return 0;
+}
+
+int check_blob(const void *blob, uint64_t bytes, FmxBlobHeader &hdr, std::string &err) {
+    if (!blob || bytes < sizeof(FmxBlobHeader)) {
+        err = "blob too small";
+        return FMX_ERR_INVALID_ARG;
+    }
+    std::memcpy(&hdr, blob, sizeof(hdr));
+    if (hdr.magic != FMX_BLOB_MAGIC || hdr.version != FMX_BLOB_VERSION) {
+        err = "not an fmx blob (bad magic or version)";
+        return FMX_ERR_INVALID_ARG;
+    }
+    if (hdr.total_bytes != bytes || hdr.levels == 0 || hdr.levels > FMX_MAX_LEVELS || hdr.kind > 2) {
+        err = "corrupt fmx blob header";
+        return FMX_ERR_INVALID_ARG;
+    }
+    for (int k = 0; k < (int)SEC_COUNT; k++) {
+        if (hdr.sec[k].bytes && (hdr.sec[k].offset % FMX_SECTION_ALIGN || hdr.sec[k].offset + hdr.sec[k].bytes > bytes)) {
+            err = "corrupt fmx blob section table";
+            return FMX_ERR_INVALID_ARG;
+        }
+    }
+    return 0;
+}
+
+}  // namespace fmx

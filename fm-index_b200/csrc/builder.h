@@ -1,0 +1,22 @@
+// builder.h -- host-side index construction: text -> device-layout blob (fmx_layout.h).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "fmx_layout.h"
+
+namespace fmx {
+
+// Returns 0 or a negative fmx_status; on failure `err` holds the message
+// (for invalid texts: the reference's Error::InvalidText strings, sais.rs:128-139).
+int build_blob(const uint8_t *text, uint64_t n, uint64_t max_character, int kind, int level,
+               std::vector<uint8_t> &blob, std::string &err);
+
+// sais.rs:115-144 (validation + suffix array)
+int build_suffix_array(const uint8_t *text, uint64_t n, uint64_t *sa_out, std::string &err);
+
+// Validates a blob's header/section table; fills `hdr`.
+int check_blob(const void *blob, uint64_t bytes, FmxBlobHeader &hdr, std::string &err);
+
+}  // namespace fmx

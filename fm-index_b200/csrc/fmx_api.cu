@@ -1,0 +1,753 @@
+// fmx_api.cu -- the C ABI (include/fmx.h) over the CUDA kernels.  No CPU fallback anywhere:
+// every query entry point launches kernels on the index's GPU or fails with FMX_ERR_CUDA.
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/fmx.h"
+#include "builder.h"
+#include "kernels.cuh"
+
+using namespace fmx;
+
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                             \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail(FMX_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));         \
+    } while (0)
+#define LAUNCH_CHECK()                                                                             \
+    do {                                                                                           \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                        \
+        cudaError_t _e = cudaGetLastError();                                                       \
+        if (_e != cudaSuccess) return fail(FMX_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(_e)); \
+    } while (0)
+
+// grow-only device scratch buffer
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(FMX_ERR_OOM, std::string("cudaMalloc scratch: ") + cudaGetErrorString(e));
+        }
+        cap = want;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+enum { B_PAT, B_OFF, B_S, B_E, B_INS, B_INE, B_CNT, B_HOFF, B_OWNER, B_ROWS, B_ROWS2, B_FLAG, B_FPOS, B_TILES, B_POS, B_PID,
+       B_OUT8, B_OUT32, B_COUNT };
+
+struct fmx_index {
+    FmxBlobHeader hdr;
+    FmxDev dev;
+    void *d_blob = nullptr;
+    std::vector<uint8_t> host_blob;  // kept for save()
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t *d_err = nullptr;             // [0] pattern-char error flag
+    unsigned long long *d_work = nullptr;  // [0] search iterations, [1] LF steps
+    mutable DevBuf buf[B_COUNT];
+    mutable std::mutex mu;
+};
+
+static inline cudaStream_t pick_stream(const fmx_index *idx, void *stream) {
+    return stream ? reinterpret_cast<cudaStream_t>(stream) : idx->stream;
+}
+static inline unsigned grid_for(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+
+extern "C" {
+
+const char *fmx_last_error(void) { return g_err.c_str(); }
+int fmx_version(void) { return 100; }
+uint64_t fmx_launch_count(void) { return g_launches.load(); }
+void fmx_free(void *p) { std::free(p); }
+
+int fmx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int fmx_build_suffix_array(const void *text, uint64_t n, uint32_t char_width, uint64_t *sa_out) {
+    if (char_width != 1) return fail(FMX_ERR_UNSUPPORTED, "only u8 texts (char_width == 1) are supported");
+    std::string err;
+    int rc = build_suffix_array(static_cast<const uint8_t *>(text), n, sa_out, err);
+    return rc ? fail(rc, err) : FMX_OK;
+}
+
+int fmx_blob_build(const void *text, uint64_t n, uint32_t char_width, uint64_t max_character, int kind, int level,
+                   void **blob, uint64_t *blob_bytes) {
+    if (!blob || !blob_bytes || (!text && n)) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    if (char_width != 1) return fail(FMX_ERR_UNSUPPORTED, "only u8 texts (char_width == 1) are supported");
+    std::vector<uint8_t> b;
+    std::string err;
+    int rc = build_blob(static_cast<const uint8_t *>(text), n, max_character, kind, level, b, err);
+    if (rc) return fail(rc, err);
+    void *p = std::malloc(b.size());
+    if (!p) return fail(FMX_ERR_OOM, "malloc blob");
+    std::memcpy(p, b.data(), b.size());
+    *blob = p;
+    *blob_bytes = b.size();
+    return FMX_OK;
+}
+
+static int upload(std::vector<uint8_t> &&blob, int device, fmx_index **out) {
+    FmxBlobHeader hdr;
+    std::string err;
+    int rc = check_blob(blob.data(), blob.size(), hdr, err);
+    if (rc) return fail(rc, err);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(FMX_ERR_CUDA, "no CUDA device available (the engine has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(FMX_ERR_INVALID_ARG, "device ordinal out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    fmx_index *idx = new fmx_index();
+    idx->hdr = hdr;
+    idx->device = device;
+    cudaError_t e = cudaMalloc(&idx->d_blob, blob.size());
+    if (e != cudaSuccess) {
+        delete idx;
+        cudaGetLastError();
+        return fail(FMX_ERR_OOM, std::string("cudaMalloc index: ") + cudaGetErrorString(e));
+    }
+    e = cudaMemcpy(idx->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&idx->d_err, 256);
+    if (e == cudaSuccess) e = cudaMemset(idx->d_err, 0, 256);
+    if (e != cudaSuccess) {
+        cudaFree(idx->d_blob);
+        delete idx;
+        return fail(FMX_ERR_CUDA, std::string("index upload: ") + cudaGetErrorString(e));
+    }
+    idx->d_work = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(idx->d_err) + 64);
+    const char *base = static_cast<const char *>(idx->d_blob);
+    auto sec = [&](int k) -> const void * { return hdr.sec[k].bytes ? base + hdr.sec[k].offset : nullptr; };
+    FmxDev &d = idx->dev;
+    std::memset(&d, 0, sizeof(d));
+    for (uint32_t l = 0; l < hdr.levels; l++) {
+        d.lv[l] = static_cast<const uint4 *>(sec(SEC_LEVEL0 + l));
+        d.zeros[l] = (uint32_t)hdr.zeros[l];
+    }
+    d.adj = static_cast<const uint32_t *>(sec(SEC_ADJ));
+    d.cs = static_cast<const uint32_t *>(sec(SEC_CS));
+    d.sa = static_cast<const uint32_t *>(sec(SEC_SA));
+    d.doc = static_cast<const uint32_t *>(sec(SEC_DOC));
+    d.piece_end = static_cast<const uint32_t *>(sec(SEC_PIECE_END));
+    d.rl_b = static_cast<const uint4 *>(sec(SEC_RL_B));
+    d.rl_bp = static_cast<const uint4 *>(sec(SEC_RL_BP));
+    d.rl_bsel = static_cast<const uint32_t *>(sec(SEC_RL_BSEL));
+    d.rl_bpsel = static_cast<const uint32_t *>(sec(SEC_RL_BPSEL));
+    d.n = (uint32_t)hdr.n;
+    d.seq_len = (uint32_t)hdr.seq_len;
+    d.levels = hdr.levels;
+    d.max_character = hdr.max_character;
+    d.cs_len = hdr.cs_len;
+    d.kind = hdr.kind;
+    d.has_locate = hdr.has_locate;
+    d.sa_level = hdr.sa_level;
+    d.ndoc = (uint32_t)hdr.ndoc;
+    d.first_row = (uint32_t)hdr.first_row;
+    d.runs = (uint32_t)hdr.runs;
+    idx->host_blob = std::move(blob);
+    *out = idx;
+    return FMX_OK;
+}
+
+int fmx_index_from_blob(const void *blob, uint64_t blob_bytes, int device, fmx_index **out) {
+    if (!blob || !out) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    std::vector<uint8_t> b(static_cast<const uint8_t *>(blob), static_cast<const uint8_t *>(blob) + blob_bytes);
+    return upload(std::move(b), device, out);
+}
+
+int fmx_index_build(const void *text, uint64_t n, uint32_t char_width, uint64_t max_character, int kind, int level,
+                    int device, fmx_index **out) {
+    if (!out || (!text && n)) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    if (char_width != 1) return fail(FMX_ERR_UNSUPPORTED, "only u8 texts (char_width == 1) are supported");
+    std::vector<uint8_t> b;
+    std::string err;
+    int rc = build_blob(static_cast<const uint8_t *>(text), n, max_character, kind, level, b, err);
+    if (rc) return fail(rc, err);
+    return upload(std::move(b), device, out);
+}
+
+int fmx_index_save(const fmx_index *idx, const char *path) {
+    if (!idx || !path) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    FILE *f = std::fopen(path, "wb");
+    if (!f) return fail(FMX_ERR_IO, std::string("cannot open ") + path);
+    size_t w = std::fwrite(idx->host_blob.data(), 1, idx->host_blob.size(), f);
+    std::fclose(f);
+    return w == idx->host_blob.size() ? FMX_OK : fail(FMX_ERR_IO, "short write");
+}
+
+int fmx_index_load(const char *path, int device, fmx_index **out) {
+    if (!path || !out) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    FILE *f = std::fopen(path, "rb");
+    if (!f) return fail(FMX_ERR_IO, std::string("cannot open ") + path);
+    std::fseek(f, 0, SEEK_END);
+    long sz = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    std::vector<uint8_t> b((size_t)(sz > 0 ? sz : 0));
+    size_t r = std::fread(b.data(), 1, b.size(), f);
+    std::fclose(f);
+    if (r != b.size()) return fail(FMX_ERR_IO, "short read");
+    return upload(std::move(b), device, out);
+}
+
+void fmx_index_free(fmx_index *idx) {
+    if (!idx) return;
+    cudaSetDevice(idx->device);
+    for (auto &b : idx->buf) b.release();
+    if (idx->d_blob) cudaFree(idx->d_blob);
+    if (idx->d_err) cudaFree(idx->d_err);
+    if (idx->stream) cudaStreamDestroy(idx->stream);
+    delete idx;
+}
+
+uint64_t fmx_index_len(const fmx_index *idx) { return idx ? idx->hdr.n : 0; }
+uint64_t fmx_index_device_bytes(const fmx_index *idx) { return idx ? idx->hdr.total_bytes : 0; }
+uint64_t fmx_index_pieces_count(const fmx_index *idx) { return idx ? idx->hdr.ndoc : 0; }
+int fmx_index_kind(const fmx_index *idx) { return idx ? (int)idx->hdr.kind : -1; }
+int fmx_index_has_locate(const fmx_index *idx) { return idx ? (int)idx->hdr.has_locate : 0; }
+int fmx_index_device(const fmx_index *idx) { return idx ? idx->device : -1; }
+uint32_t fmx_index_wavelet_levels(const fmx_index *idx) { return idx ? idx->hdr.levels : 0; }
+uint32_t fmx_index_sample_level(const fmx_index *idx) { return idx ? idx->hdr.sa_level : 0; }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ scans
+
+template <class Tin, class Tout, class Op, bool EXCL>
+static int device_scan(const Tin *in, uint64_t n, Tout *out, Op op, bool write_total, DevBuf &tiles, cudaStream_t st) {
+    if (n == 0) {
+        if (EXCL && write_total) CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(Tout), st));
+        return 0;
+    }
+    uint64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (ntiles == 1) {
+        k_scan_apply<Tin, Tout, Op, EXCL><<<1, SCAN_THREADS, 0, st>>>(in, n, nullptr, out, op, write_total ? 1 : 0);
+        LAUNCH_CHECK();
+        return 0;
+    }
+    // tile sums for every level live in one scratch buffer
+    uint64_t need = 0;
+    for (uint64_t m = ntiles; m > 1; m = (m + SCAN_TILE - 1) / SCAN_TILE) need += 2 * m;
+    need += 2;
+    int rc = tiles.ensure(need * sizeof(uint64_t));
+    if (rc) return rc;
+    uint64_t *sum0 = tiles.as<uint64_t>();
+    uint64_t *pre0 = sum0 + ntiles;
+    k_scan_reduce<Tin, Op><<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(in, n, sum0, op);
+    LAUNCH_CHECK();
+    // exclusive scan of the tile sums (recursive on the same buffer tail)
+    struct Level {
+        uint64_t *sum, *pre, n;
+    };
+    std::vector<Level> lv;
+    lv.push_back({sum0, pre0, ntiles});
+    uint64_t *cursor = pre0 + ntiles;
+    while (lv.back().n > SCAN_TILE) {
+        uint64_t m = (lv.back().n + SCAN_TILE - 1) / SCAN_TILE;
+        Level nx{cursor, cursor + m, m};
+        cursor += 2 * m;
+        k_scan_reduce<uint64_t, Op><<<(unsigned)m, SCAN_THREADS, 0, st>>>(lv.back().sum, lv.back().n, nx.sum, op);
+        LAUNCH_CHECK();
+        lv.push_back(nx);
+    }
+    for (size_t k = lv.size(); k-- > 0;) {
+        const uint64_t *carry = (k + 1 < lv.size()) ? lv[k + 1].pre : nullptr;
+        unsigned g = (unsigned)((lv[k].n + SCAN_TILE - 1) / SCAN_TILE);
+        k_scan_apply<uint64_t, uint64_t, Op, true><<<g, SCAN_THREADS, 0, st>>>(lv[k].sum, lv[k].n, carry, lv[k].pre, op, 0);
+        LAUNCH_CHECK();
+    }
+    k_scan_apply<Tin, Tout, Op, EXCL><<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(in, n, pre0, out, op, write_total ? 1 : 0);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ search
+
+template <int KIND>
+static int launch_search(const fmx_index *idx, const SearchArgs &a, cudaStream_t st) {
+    if (a.npat == 0) return 0;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, idx->device);
+    uint64_t blocks = (a.npat + 255) / 256;
+    uint64_t cap = (uint64_t)sms * 8 * 8;  // grid-stride beyond 8 waves of 8 CTAs/SM
+    if (blocks > cap) blocks = cap;
+    k_search<KIND><<<(unsigned)blocks, 256, 0, st>>>(idx->dev, a);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+static int search_device(const fmx_index *idx, int mode, const uint8_t *d_pat, const uint64_t *d_pat_off,
+                         uint64_t fixed_len, uint64_t npat, const uint64_t *d_is, const uint64_t *d_ie,
+                         uint64_t *d_os, uint64_t *d_oe, cudaStream_t st) {
+    if (mode < FMX_SEARCH || mode > FMX_SEARCH_EXACT) return fail(FMX_ERR_INVALID_ARG, "bad search mode");
+    if (mode != FMX_SEARCH && idx->hdr.kind != FMX_KIND_MULTI)
+        return fail(FMX_ERR_UNSUPPORTED, "search_prefix/suffix/exact need a MultiPieces index (frontend.rs:369-390)");
+    if ((d_is == nullptr) != (d_ie == nullptr)) return fail(FMX_ERR_INVALID_ARG, "init_s and init_e must both be given");
+    SearchArgs a;
+    a.pat = d_pat;
+    a.pat_off = d_pat_off;
+    a.fixed_len = fixed_len;
+    a.npat = npat;
+    a.init_s = d_is;
+    a.init_e = d_ie;
+    a.s0 = 0;  // wrapper.rs:41, 65, 73, 81
+    a.e0 = (mode == FMX_SEARCH_SUFFIX || mode == FMX_SEARCH_EXACT) ? (uint32_t)idx->hdr.ndoc : (uint32_t)idx->hdr.n;
+    a.out_s = d_os;
+    a.out_e = d_oe;
+    a.err = idx->d_err;
+    a.work = idx->d_work;
+    CUDA_TRY(cudaMemsetAsync(idx->d_work, 0, sizeof(unsigned long long), st));
+    switch (idx->hdr.kind) {
+        case FMX_KIND_FM: return launch_search<FMX_KIND_FM_>(idx, a, st);
+        case FMX_KIND_RLFM: return launch_search<FMX_KIND_RLFM_>(idx, a, st);
+        default: return launch_search<FMX_KIND_MULTI_>(idx, a, st);
+    }
+}
+
+static int check_err_flag(const fmx_index *idx, cudaStream_t st) {
+    uint32_t flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, idx->d_err, sizeof(flag), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (flag) {
+        CUDA_TRY(cudaMemsetAsync(idx->d_err, 0, sizeof(uint32_t), st));
+        return fail(FMX_ERR_PATTERN_CHAR,
+                    "pattern contains a character larger than max_character (the reference panics: fm_index.rs:94)");
+    }
+    return FMX_OK;
+}
+
+extern "C" int fmx_search_batch_device(const fmx_index *idx, int mode, const uint8_t *d_pat, const uint64_t *d_pat_off,
+                                       uint64_t fixed_len, uint64_t npat, const uint64_t *d_init_s,
+                                       const uint64_t *d_init_e, uint64_t *d_out_s, uint64_t *d_out_e, void *stream) {
+    if (!idx || !d_out_s || !d_out_e) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(idx->device));
+    return search_device(idx, mode, d_pat, d_pat_off, fixed_len, npat, d_init_s, d_init_e, d_out_s, d_out_e,
+                         pick_stream(idx, stream));
+}
+
+extern "C" int fmx_search_check(const fmx_index *idx, void *stream) {
+    if (!idx) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(idx->device));
+    return check_err_flag(idx, pick_stream(idx, stream));
+}
+
+extern "C" int fmx_search_batch(const fmx_index *idx, int mode, const uint8_t *pat, const uint64_t *pat_off,
+                                uint64_t fixed_len, uint64_t npat, const uint64_t *init_s, const uint64_t *init_e,
+                                uint64_t *out_s, uint64_t *out_e) {
+    if (!idx || !out_s || !out_e) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    if (npat == 0) return FMX_OK;
+    std::lock_guard<std::mutex> lk(idx->mu);
+    CUDA_TRY(cudaSetDevice(idx->device));
+    cudaStream_t st = idx->stream;
+    uint64_t pat_bytes = pat_off ? pat_off[npat] : npat * fixed_len;
+    if (pat_bytes && !pat) return fail(FMX_ERR_INVALID_ARG, "null pattern buffer");
+    int rc;
+    if ((rc = idx->buf[B_PAT].ensure(pat_bytes + 16))) return rc;
+    if ((rc = idx->buf[B_S].ensure(npat * 8))) return rc;
+    if ((rc = idx->buf[B_E].ensure(npat * 8))) return rc;
+    if (pat_bytes) CUDA_TRY(cudaMemcpyAsync(idx->buf[B_PAT].p, pat, pat_bytes, cudaMemcpyHostToDevice, st));
+    const uint64_t *d_off = nullptr;
+    if (pat_off) {
+        if ((rc = idx->buf[B_OFF].ensure((npat + 1) * 8))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(idx->buf[B_OFF].p, pat_off, (npat + 1) * 8, cudaMemcpyHostToDevice, st));
+        d_off = idx->buf[B_OFF].as<uint64_t>();
+    }
+    const uint64_t *d_is = nullptr, *d_ie = nullptr;
+    if (init_s && init_e) {
+        if ((rc = idx->buf[B_INS].ensure(npat * 8))) return rc;
+        if ((rc = idx->buf[B_INE].ensure(npat * 8))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(idx->buf[B_INS].p, init_s, npat * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(idx->buf[B_INE].p, init_e, npat * 8, cudaMemcpyHostToDevice, st));
+        d_is = idx->buf[B_INS].as<uint64_t>();
+        d_ie = idx->buf[B_INE].as<uint64_t>();
+    } else if (init_s || init_e) {
+        return fail(FMX_ERR_INVALID_ARG, "init_s and init_e must both be given");
+    }
+    rc = search_device(idx, mode, idx->buf[B_PAT].as<uint8_t>(), d_off, fixed_len, npat, d_is, d_ie,
+                       idx->buf[B_S].as<uint64_t>(), idx->buf[B_E].as<uint64_t>(), st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_s, idx->buf[B_S].p, npat * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(out_e, idx->buf[B_E].p, npat * 8, cudaMemcpyDeviceToHost, st));
+    return check_err_flag(idx, st);
+}
+
+// ------------------------------------------------------------------ locate
+
+// candidate rows of every range, in pattern order then ascending row order; applies the L == 0
+// filter by flag / scan / compaction.  On return d_hit_off holds the final offsets and
+// buf[B_ROWS] (or B_ROWS2 when filtered) the hit rows.  *rows_out points at them.
+static int locate_prepare(const fmx_index *idx, int prefix_only, const uint64_t *d_s, const uint64_t *d_e,
+                          uint64_t npat, uint64_t *d_hit_off, uint64_t *total_out, const uint32_t **rows_out,
+                          cudaStream_t st) {
+    int rc;
+    *rows_out = nullptr;
+    if (npat >= 0xFFFFFFFFull) return fail(FMX_ERR_UNSUPPORTED, "at most 2^32 - 2 patterns per locate call");
+    if ((rc = idx->buf[B_CNT].ensure((npat + 1) * 8))) return rc;
+    uint64_t *d_cnt = idx->buf[B_CNT].as<uint64_t>();
+    // unfiltered offsets go to d_hit_off directly when there is no filter
+    uint64_t *d_off = d_hit_off;
+    if (prefix_only) {
+        if ((rc = idx->buf[B_HOFF].ensure((npat + 1) * 8))) return rc;
+        d_off = idx->buf[B_HOFF].as<uint64_t>();
+    }
+    if (npat) {
+        k_range_counts<<<grid_for(npat, 256), 256, 0, st>>>(d_s, d_e, npat, d_cnt);
+        LAUNCH_CHECK();
+    }
+    if ((rc = device_scan<uint64_t, uint64_t, OpSum, true>(d_cnt, npat, d_off, OpSum(), true, idx->buf[B_TILES], st))) return rc;
+    uint64_t total = 0;
+    CUDA_TRY(cudaMemcpyAsync(&total, d_off + npat, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (total >= 0xFFFFFFFFull * 4) return fail(FMX_ERR_UNSUPPORTED, "too many candidate rows in one locate call");
+    if (total == 0) {
+        if (prefix_only) CUDA_TRY(cudaMemsetAsync(d_hit_off, 0, (npat + 1) * 8, st));
+        *total_out = 0;
+        return 0;
+    }
+    if ((rc = idx->buf[B_OWNER].ensure(total * 4))) return rc;
+    if ((rc = idx->buf[B_ROWS].ensure(total * 4))) return rc;
+    uint32_t *d_owner = idx->buf[B_OWNER].as<uint32_t>();
+    uint32_t *d_rows = idx->buf[B_ROWS].as<uint32_t>();
+    CUDA_TRY(cudaMemsetAsync(d_owner, 0, total * 4, st));
+    k_mark_owners<<<grid_for(npat, 256), 256, 0, st>>>(d_off, npat, d_owner);
+    LAUNCH_CHECK();
+    if ((rc = device_scan<uint32_t, uint32_t, OpMax, false>(d_owner, total, d_owner, OpMax(), false, idx->buf[B_TILES], st))) return rc;
+    k_expand_rows<<<grid_for(total, 256), 256, 0, st>>>(d_s, d_off, d_owner, total, d_rows);
+    LAUNCH_CHECK();
+    if (!prefix_only) {
+        *total_out = total;
+        *rows_out = d_rows;
+        return 0;
+    }
+    // wrapper.rs:208: keep rows whose L is \0
+    if ((rc = idx->buf[B_FLAG].ensure(total * 4))) return rc;
+    if ((rc = idx->buf[B_FPOS].ensure((total + 1) * 8))) return rc;
+    uint32_t *d_flag = idx->buf[B_FLAG].as<uint32_t>();
+    uint64_t *d_fpos = idx->buf[B_FPOS].as<uint64_t>();
+    switch (idx->hdr.kind) {
+        case FMX_KIND_FM: k_flag_prefix<FMX_KIND_FM_><<<grid_for(total, 256), 256, 0, st>>>(idx->dev, d_rows, total, d_flag); break;
+        case FMX_KIND_RLFM: k_flag_prefix<FMX_KIND_RLFM_><<<grid_for(total, 256), 256, 0, st>>>(idx->dev, d_rows, total, d_flag); break;
+        default: k_flag_prefix<FMX_KIND_MULTI_><<<grid_for(total, 256), 256, 0, st>>>(idx->dev, d_rows, total, d_flag); break;
+    }
+    LAUNCH_CHECK();
+    if ((rc = device_scan<uint32_t, uint64_t, OpSum, true>(d_flag, total, d_fpos, OpSum(), true, idx->buf[B_TILES], st))) return rc;
+    uint64_t kept = 0;
+    CUDA_TRY(cudaMemcpyAsync(&kept, d_fpos + total, 8, cudaMemcpyDeviceToHost, st));
+    k_filtered_offsets<<<grid_for(npat + 1, 256), 256, 0, st>>>(d_off, d_fpos, npat, d_hit_off);
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (kept) {
+        if ((rc = idx->buf[B_ROWS2].ensure(kept * 4))) return rc;
+        k_compact_rows<<<grid_for(total, 256), 256, 0, st>>>(d_rows, d_flag, d_fpos, total, idx->buf[B_ROWS2].as<uint32_t>());
+        LAUNCH_CHECK();
+        *rows_out = idx->buf[B_ROWS2].as<uint32_t>();
+    }
+    *total_out = kept;
+    return 0;
+}
+
+static int locate_fill(const fmx_index *idx, const uint32_t *d_rows, uint64_t total, uint64_t *d_pos, uint64_t *d_pid,
+                       cudaStream_t st) {
+    CUDA_TRY(cudaMemsetAsync(idx->d_work + 1, 0, sizeof(unsigned long long), st));
+    if (total == 0) return 0;
+    LocateArgs a;
+    a.rows = d_rows;
+    a.total = total;
+    a.positions = d_pos;
+    a.piece_ids = d_pid;
+    a.work = idx->d_work;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, idx->device);
+    uint64_t blocks = (total + 255) / 256;
+    uint64_t cap = (uint64_t)sms * 8 * 8;
+    if (blocks > cap) blocks = cap;
+    switch (idx->hdr.kind) {
+        case FMX_KIND_FM: k_locate<FMX_KIND_FM_><<<(unsigned)blocks, 256, 0, st>>>(idx->dev, a); break;
+        case FMX_KIND_RLFM: k_locate<FMX_KIND_RLFM_><<<(unsigned)blocks, 256, 0, st>>>(idx->dev, a); break;
+        default: k_locate<FMX_KIND_MULTI_><<<(unsigned)blocks, 256, 0, st>>>(idx->dev, a); break;
+    }
+    LAUNCH_CHECK();
+    return 0;
+}
+
+static int locate_args_ok(const fmx_index *idx, bool want_pid) {
+    if (!idx->hdr.has_locate)
+        return fail(FMX_ERR_NO_LOCATE, "index was built without a sampled suffix array (count-only variant)");
+    if (want_pid && idx->hdr.kind != FMX_KIND_MULTI)
+        return fail(FMX_ERR_UNSUPPORTED, "piece_id needs a MultiPieces index (frontend.rs:542)");
+    return 0;
+}
+
+extern "C" int fmx_locate_count_device(const fmx_index *idx, int prefix_only, const uint64_t *d_s, const uint64_t *d_e,
+                                       uint64_t npat, uint64_t *d_hit_off, uint64_t *total_hits, void *stream) {
+    if (!idx || !d_hit_off || !total_hits) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    int rc = locate_args_ok(idx, false);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(idx->device));
+    const uint32_t *rows;
+    return locate_prepare(idx, prefix_only, d_s, d_e, npat, d_hit_off, total_hits, &rows, pick_stream(idx, stream));
+}
+
+extern "C" int fmx_locate_fill_device(const fmx_index *idx, int prefix_only, const uint64_t *d_s, const uint64_t *d_e,
+                                      uint64_t npat, const uint64_t *d_hit_off, uint64_t total_hits,
+                                      uint64_t *d_positions, uint64_t *d_piece_ids, void *stream) {
+    if (!idx) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    int rc = locate_args_ok(idx, d_piece_ids != nullptr);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(idx->device));
+    (void)d_s;
+    (void)d_e;
+    (void)npat;
+    (void)d_hit_off;
+    // the rows prepared by the matching fmx_locate_count_device call are still in scratch
+    const uint32_t *rows = prefix_only ? idx->buf[B_ROWS2].as<uint32_t>() : idx->buf[B_ROWS].as<uint32_t>();
+    return locate_fill(idx, rows, total_hits, d_positions, d_piece_ids, pick_stream(idx, stream));
+}
+
+extern "C" int fmx_locate_batch(const fmx_index *idx, int prefix_only, const uint64_t *s, const uint64_t *e, uint64_t npat,
+                                uint64_t *hit_off, uint64_t **positions, uint64_t **piece_ids) {
+    if (!idx || !hit_off || (!s && npat) || (!e && npat)) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    if (positions) *positions = nullptr;
+    if (piece_ids) *piece_ids = nullptr;
+    int rc = locate_args_ok(idx, piece_ids != nullptr);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(idx->mu);
+    CUDA_TRY(cudaSetDevice(idx->device));
+    cudaStream_t st = idx->stream;
+    if ((rc = idx->buf[B_S].ensure(npat * 8 + 8))) return rc;
+    if ((rc = idx->buf[B_E].ensure(npat * 8 + 8))) return rc;
+    if ((rc = idx->buf[B_OFF].ensure((npat + 1) * 8))) return rc;
+    if (npat) {
+        CUDA_TRY(cudaMemcpyAsync(idx->buf[B_S].p, s, npat * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(idx->buf[B_E].p, e, npat * 8, cudaMemcpyHostToDevice, st));
+    }
+    uint64_t total = 0;
+    const uint32_t *rows = nullptr;
+    uint64_t *d_hoff = idx->buf[B_OFF].as<uint64_t>();
+    if ((rc = locate_prepare(idx, prefix_only, idx->buf[B_S].as<uint64_t>(), idx->buf[B_E].as<uint64_t>(), npat, d_hoff,
+                             &total, &rows, st)))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(hit_off, d_hoff, (npat + 1) * 8, cudaMemcpyDeviceToHost, st));
+    uint64_t *h_pos = nullptr, *h_pid = nullptr;
+    if (total) {
+        uint64_t *d_pos = nullptr, *d_pid = nullptr;
+        if (positions) {
+            if ((rc = idx->buf[B_POS].ensure(total * 8))) return rc;
+            d_pos = idx->buf[B_POS].as<uint64_t>();
+        }
+        if (piece_ids) {
+            if ((rc = idx->buf[B_PID].ensure(total * 8))) return rc;
+            d_pid = idx->buf[B_PID].as<uint64_t>();
+        }
+        if ((rc = locate_fill(idx, rows, total, d_pos, d_pid, st))) return rc;
+        if (positions) {
+            h_pos = static_cast<uint64_t *>(std::malloc(total * 8));
+            if (!h_pos) return fail(FMX_ERR_OOM, "malloc positions");
+            CUDA_TRY(cudaMemcpyAsync(h_pos, d_pos, total * 8, cudaMemcpyDeviceToHost, st));
+        }
+        if (piece_ids) {
+            h_pid = static_cast<uint64_t *>(std::malloc(total * 8));
+            if (!h_pid) {
+                std::free(h_pos);
+                return fail(FMX_ERR_OOM, "malloc piece ids");
+            }
+            CUDA_TRY(cudaMemcpyAsync(h_pid, d_pid, total * 8, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (positions) *positions = h_pos;
+    if (piece_ids) *piece_ids = h_pid;
+    return FMX_OK;
+}
+
+// ------------------------------------------------------------------ extraction / primitives
+
+static int extract_device(const fmx_index *idx, const uint64_t *d_rows, uint64_t nrows, uint32_t k, int forward,
+                          uint8_t *d_out, uint32_t *d_len, cudaStream_t st) {
+    if (nrows == 0 || k == 0) return 0;
+    unsigned g = grid_for(nrows, 256);
+    switch (idx->hdr.kind) {
+        case FMX_KIND_FM: k_extract<FMX_KIND_FM_><<<g, 256, 0, st>>>(idx->dev, d_rows, nrows, k, forward, d_out, d_len); break;
+        case FMX_KIND_RLFM: k_extract<FMX_KIND_RLFM_><<<g, 256, 0, st>>>(idx->dev, d_rows, nrows, k, forward, d_out, d_len); break;
+        default: k_extract<FMX_KIND_MULTI_><<<g, 256, 0, st>>>(idx->dev, d_rows, nrows, k, forward, d_out, d_len); break;
+    }
+    LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int fmx_extract_batch_device(const fmx_index *idx, const uint64_t *d_rows, uint64_t nrows, uint32_t k,
+                                        int forward, uint8_t *d_out, uint32_t *d_out_len, void *stream) {
+    if (!idx || (!d_rows && nrows) || (!d_out && nrows && k)) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(idx->device));
+    return extract_device(idx, d_rows, nrows, k, forward, d_out, d_out_len, pick_stream(idx, stream));
+}
+
+extern "C" int fmx_extract_batch(const fmx_index *idx, const uint64_t *rows, uint64_t nrows, uint32_t k, int forward,
+                                 uint8_t *out, uint32_t *out_len) {
+    if (!idx || (!rows && nrows) || (!out && nrows && k)) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    if (nrows == 0) return FMX_OK;
+    for (uint64_t r = 0; r < nrows; r++)
+        if (rows[r] >= idx->hdr.n) return fail(FMX_ERR_INVALID_ARG, "row out of range");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    CUDA_TRY(cudaSetDevice(idx->device));
+    cudaStream_t st = idx->stream;
+    int rc;
+    if ((rc = idx->buf[B_S].ensure(nrows * 8))) return rc;
+    if ((rc = idx->buf[B_OUT8].ensure(nrows * (uint64_t)k + 16))) return rc;
+    if ((rc = idx->buf[B_OUT32].ensure(nrows * 4))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(idx->buf[B_S].p, rows, nrows * 8, cudaMemcpyHostToDevice, st));
+    if ((rc = extract_device(idx, idx->buf[B_S].as<uint64_t>(), nrows, k, forward, idx->buf[B_OUT8].as<uint8_t>(),
+                             idx->buf[B_OUT32].as<uint32_t>(), st)))
+        return rc;
+    if (k) CUDA_TRY(cudaMemcpyAsync(out, idx->buf[B_OUT8].p, nrows * (uint64_t)k, cudaMemcpyDeviceToHost, st));
+    if (out_len) {
+        if (k) CUDA_TRY(cudaMemcpyAsync(out_len, idx->buf[B_OUT32].p, nrows * 4, cudaMemcpyDeviceToHost, st));
+        else std::memset(out_len, 0, nrows * 4);
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return FMX_OK;
+}
+
+extern "C" int fmx_rows_op(const fmx_index *idx, int op, const uint64_t *rows, uint64_t nrows, uint64_t *out) {
+    if (!idx || (!rows && nrows) || (!out && nrows)) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    if (op < 0 || op > 5) return fail(FMX_ERR_INVALID_ARG, "bad op");
+    if (nrows == 0) return FMX_OK;
+    if (op == 4 && !idx->hdr.has_locate) return fail(FMX_ERR_NO_LOCATE, "index has no sampled suffix array");
+    if (op == 5 && idx->hdr.kind != FMX_KIND_MULTI) return fail(FMX_ERR_UNSUPPORTED, "piece_id needs a MultiPieces index");
+    for (uint64_t r = 0; r < nrows; r++)
+        if (rows[r] >= idx->hdr.n) return fail(FMX_ERR_INVALID_ARG, "row out of range");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    CUDA_TRY(cudaSetDevice(idx->device));
+    cudaStream_t st = idx->stream;
+    int rc;
+    if ((rc = idx->buf[B_S].ensure(nrows * 8))) return rc;
+    if ((rc = idx->buf[B_E].ensure(nrows * 8))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(idx->buf[B_S].p, rows, nrows * 8, cudaMemcpyHostToDevice, st));
+    unsigned g = grid_for(nrows, 256);
+    const uint64_t *d_rows = idx->buf[B_S].as<uint64_t>();
+    uint64_t *d_out = idx->buf[B_E].as<uint64_t>();
+    switch (idx->hdr.kind) {
+        case FMX_KIND_FM: k_rows_op<FMX_KIND_FM_><<<g, 256, 0, st>>>(idx->dev, op, d_rows, nrows, d_out); break;
+        case FMX_KIND_RLFM: k_rows_op<FMX_KIND_RLFM_><<<g, 256, 0, st>>>(idx->dev, op, d_rows, nrows, d_out); break;
+        default: k_rows_op<FMX_KIND_MULTI_><<<g, 256, 0, st>>>(idx->dev, op, d_rows, nrows, d_out); break;
+    }
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaMemcpyAsync(out, d_out, nrows * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return FMX_OK;
+}
+
+extern "C" int fmx_lf_map2_batch(const fmx_index *idx, const uint8_t *c, const uint64_t *i, uint64_t nrows, uint64_t *out) {
+    if (!idx || ((!c || !i || !out) && nrows)) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    if (nrows == 0) return FMX_OK;
+    for (uint64_t r = 0; r < nrows; r++) {
+        if (i[r] > idx->hdr.n) return fail(FMX_ERR_INVALID_ARG, "row out of range");
+        if (c[r] > idx->hdr.max_character) return fail(FMX_ERR_PATTERN_CHAR, "character larger than max_character");
+    }
+    std::lock_guard<std::mutex> lk(idx->mu);
+    CUDA_TRY(cudaSetDevice(idx->device));
+    cudaStream_t st = idx->stream;
+    int rc;
+    if ((rc = idx->buf[B_S].ensure(nrows * 8))) return rc;
+    if ((rc = idx->buf[B_E].ensure(nrows * 8))) return rc;
+    if ((rc = idx->buf[B_PAT].ensure(nrows + 16))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(idx->buf[B_S].p, i, nrows * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(idx->buf[B_PAT].p, c, nrows, cudaMemcpyHostToDevice, st));
+    unsigned g = grid_for(nrows, 256);
+    const uint8_t *d_c = idx->buf[B_PAT].as<uint8_t>();
+    const uint64_t *d_i = idx->buf[B_S].as<uint64_t>();
+    uint64_t *d_out = idx->buf[B_E].as<uint64_t>();
+    switch (idx->hdr.kind) {
+        case FMX_KIND_FM: k_lf_map2<FMX_KIND_FM_><<<g, 256, 0, st>>>(idx->dev, d_c, d_i, nrows, d_out); break;
+        case FMX_KIND_RLFM: k_lf_map2<FMX_KIND_RLFM_><<<g, 256, 0, st>>>(idx->dev, d_c, d_i, nrows, d_out); break;
+        default: k_lf_map2<FMX_KIND_MULTI_><<<g, 256, 0, st>>>(idx->dev, d_c, d_i, nrows, d_out); break;
+    }
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaMemcpyAsync(out, d_out, nrows * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return FMX_OK;
+}
+
+// ------------------------------------------------------------------ measurement helpers
+
+extern "C" int fmx_last_work(const fmx_index *idx, void *stream, uint64_t *search_steps, uint64_t *lf_steps) {
+    if (!idx) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(idx->device));
+    cudaStream_t st = pick_stream(idx, stream);
+    unsigned long long w[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(w, idx->d_work, sizeof(w), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (search_steps) *search_steps = w[0];
+    if (lf_steps) *lf_steps = w[1];
+    return FMX_OK;
+}
+
+extern "C" int fmx_random_gather_bench(int device, uint64_t bytes, uint64_t nloads, int iters, double *sectors_per_s) {
+    if (!sectors_per_s || bytes < 4096 || nloads == 0 || iters <= 0) return fail(FMX_ERR_INVALID_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(device));
+    void *buf = nullptr;
+    uint32_t *sink = nullptr;
+    CUDA_TRY(cudaMalloc(&buf, bytes));
+    CUDA_TRY(cudaMalloc(&sink, 256));
+    CUDA_TRY(cudaMemset(buf, 1, bytes));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    unsigned grid = (unsigned)sms * 8;
+    uint64_t nsectors = bytes / 32;
+    double best = 0;
+    for (int it = 0; it < iters + 1; it++) {
+        CUDA_TRY(cudaEventRecord(e0, 0));
+        k_random_gather<<<grid, 256>>>(static_cast<const uint4 *>(buf), nsectors, nloads, 0x1234567ull * (it + 1), sink);
+        LAUNCH_CHECK();
+        CUDA_TRY(cudaEventRecord(e1, 0));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        double rate = (double)nloads / (ms * 1e-3);
+        if (it > 0 && rate > best) best = rate;  // first iteration is warm-up
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    cudaFree(sink);
+    *sectors_per_s = best;
+    return FMX_OK;
+}

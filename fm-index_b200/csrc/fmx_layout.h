@@ -1,0 +1,96 @@
+// fmx_layout.h -- the device layout ("blob") shared by the host builder and the kernels.
+//
+// One contiguous allocation in HBM: BlobHeader followed by 256-byte aligned sections.
+//
+// RANK BLOCKS ("RB32").  Every rank-able bit vector (each wavelet-matrix level, and the
+// RLFM run-start vectors b / bp) is an array of 32-byte blocks
+//       word 0    : u32  number of 1-bits in all preceding blocks of this vector
+//       word 1..7 : 224 payload bits, LSB first
+// so rank1(pos) -- and the bit at pos, for access -- costs exactly ONE 32-byte HBM
+// sector plus an in-register popcount.  The reference's dependency (vers-vecs RsVec)
+// keeps bits, 512-bit block counts and 8192-bit super-block counts in three separate
+// arrays, i.e. up to three cache lines per rank.  u32 counts bound the text length to
+// n < 2^32 (every BASELINE config; the largest is 3*10^9).
+//
+// WAVELET MATRIX.  L = Text::max_bits() levels (text.rs:61-63), level 0 = most significant
+// bit, zeros stably partitioned before ones -- the structure of vers' WaveletMatrix, which
+// the reference stores its BWT in (fm_index.rs:44-58).  rank(i, c) walks ONE position down
+// the levels (the walk of position 0 is a per-symbol constant, folded into `adj`):
+//       lf_map2(c, i) = adj[c] + walk_c(i),   adj[c] = cs[c] - walk_c(0)      (mod 2^32)
+#pragma once
+#include <stdint.h>
+#include <vector_types.h>  // uint4 (CUDA toolkit header, host-safe)
+
+#define FMX_BLOB_MAGIC 0x3030324258584d46ull /* "FMXXB200" little endian-ish tag */
+#define FMX_BLOB_VERSION 1u
+#define FMX_MAX_LEVELS 8
+#define FMX_RB_BITS 224u
+#define FMX_SECTION_ALIGN 256u
+
+enum FmxSection : uint32_t {
+    SEC_LEVEL0 = 0,  // .. SEC_LEVEL0 + 7 : wavelet levels (RB32)
+    SEC_ADJ = 8,     // u32[cs_len]   adj[c] = cs[c] - walk_c(0)
+    SEC_CS = 9,      // u32[cs_len+1] cs[c] (sais.rs:21-32), cs[cs_len] = n (FM/MULTI) or runs (RLFM)
+    SEC_SA = 10,     // u32[((n-1)>>level)+1]  sampled suffix array, sa[i << level]  (sample.rs:33-37)
+    SEC_DOC = 11,    // u32[ndoc]     multi_pieces.rs:53-79
+    SEC_PIECE_END = 12,  // u32[ndoc]  text position of the k-th \0 (piece k is [end[k-1]+1, end[k]])
+    SEC_RL_B = 13,   // RB32 over n bits: run starts in L order  (rlfmi.rs:40-67)
+    SEC_RL_BP = 14,  // RB32 over n bits: run starts in F order  (rlfmi.rs:70-83)
+    SEC_RL_BSEL = 15,   // u32[runs+1]  select1(b, j), [runs] = n
+    SEC_RL_BPSEL = 16,  // u32[runs+1]  select1(bp, j), [runs] = n
+    SEC_COUNT = 17
+};
+
+struct FmxSectionEntry {
+    uint64_t offset;  // from the start of the blob
+    uint64_t bytes;
+};
+
+struct FmxBlobHeader {
+    uint64_t magic;
+    uint32_t version;
+    uint32_t kind;           // fmx_kind
+    uint64_t n;              // text length incl. the trailing \0 (SearchIndex::len)
+    uint64_t seq_len;        // length of the wavelet-matrix sequence: n (FM/MULTI) or runs (RLFM)
+    uint32_t levels;         // L
+    uint32_t max_character;
+    uint32_t cs_len;         // max_character + 1
+    uint32_t has_locate;
+    uint32_t sa_level;       // effective level (0 if n <= 2^level, sample.rs:28-31)
+    uint32_t sa_word_size;   // floor(log2 n) + 1: width the reference packs samples with
+    uint64_t sa_count;
+    uint64_t ndoc;           // pieces_count
+    uint64_t first_row;      // sa_idx_first_text (multi_pieces.rs:23)
+    uint64_t runs;
+    uint64_t zeros[FMX_MAX_LEVELS];  // zeros per level
+    uint64_t total_bytes;
+    FmxSectionEntry sec[SEC_COUNT];
+    uint64_t reserved[8];
+};
+
+// What the kernels see (passed by value as a __grid_constant__ parameter).
+struct FmxDev {
+    const uint4 *lv[FMX_MAX_LEVELS];
+    uint32_t zeros[FMX_MAX_LEVELS];
+    const uint32_t *adj;
+    const uint32_t *cs;
+    const uint32_t *sa;
+    const uint32_t *doc;
+    const uint32_t *piece_end;
+    const uint4 *rl_b;
+    const uint4 *rl_bp;
+    const uint32_t *rl_bsel;
+    const uint32_t *rl_bpsel;
+    uint32_t n;
+    uint32_t seq_len;
+    uint32_t levels;
+    uint32_t max_character;
+    uint32_t cs_len;
+    uint32_t kind;
+    uint32_t has_locate;
+    uint32_t sa_level;
+    uint32_t ndoc;
+    uint32_t first_row;
+    uint32_t runs;
+    uint32_t pad;
+};

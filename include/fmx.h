@@ -1,0 +1,180 @@
+/*
+ * fmx.h -- C ABI of the B200-native batched FM-index query engine.
+ *
+ * This is the drop-in boundary for the one hot path of ajalab/fm-index 0.3.1:
+ * backward search (count), LF walks to sampled suffix-array entries (locate) and the
+ * character-extraction walks, for FMIndex / RLFMIndex / FMIndexMultiPieces with and
+ * without locate support.  The reference has no FFI of its own;
+ * each entry point below names the reference interface it replaces (paths relative to
+ * the reference crate root).  A Rust facade binds these with `extern "C"` (see
+ * INTEGRATION.md); include/fmx.hpp is the same facade in C++.
+ *
+ * Conventions
+ *   - every function returns FMX_OK (0) or a negative fmx_status; fmx_last_error()
+ *     returns a thread-local message for the last failure.  Nothing unwinds across the ABI.
+ *   - positions, rows and counts are uint64_t (Rust usize).  Characters are bytes (u8).
+ *   - input buffers are caller-owned; buffers returned through `T**` are library-owned
+ *     and released with fmx_free().
+ *   - "_device" entry points take raw device pointers resident in the index's GPU and an
+ *     optional cudaStream_t (as void*, NULL = the index's own stream); they are
+ *     asynchronous unless stated.  The host-buffer entry points copy H2D/D2H themselves
+ *     and are synchronous.
+ *   - there is no CPU fallback: without a usable CUDA device every query entry point
+ *     fails with FMX_ERR_CUDA.
+ */
+#ifndef FMX_H
+#define FMX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fmx_index fmx_index; /* opaque; owns the device-resident index */
+
+typedef enum fmx_status {
+    FMX_OK = 0,
+    FMX_ERR_INVALID_TEXT = -1,  /* Error::InvalidText, src/error.rs:3-6 (same messages as sais.rs:128-139) */
+    FMX_ERR_INVALID_ARG = -2,
+    FMX_ERR_CUDA = -3,
+    FMX_ERR_NO_LOCATE = -4,     /* index built without a sampled SA (DiscardedSuffixArray, discard.rs) */
+    FMX_ERR_PATTERN_CHAR = -5,  /* a processed pattern char > max_character: the reference panics (fm_index.rs:94) */
+    FMX_ERR_OOM = -6,
+    FMX_ERR_UNSUPPORTED = -7,
+    FMX_ERR_IO = -8
+} fmx_status;
+
+/* src/frontend.rs:110-193: the three backends; locate support is chosen by `level` */
+typedef enum fmx_kind {
+    FMX_KIND_FM = 0,    /* FMIndex / FMIndexWithLocate            (src/fm_index.rs) */
+    FMX_KIND_RLFM = 1,  /* RLFMIndex / RLFMIndexWithLocate        (src/rlfmi.rs) */
+    FMX_KIND_MULTI = 2  /* FMIndexMultiPieces(/WithLocate)        (src/multi_pieces.rs) */
+} fmx_kind;
+
+/* src/wrapper.rs:37-42, 61-82: initial SA range and the prefix filter */
+typedef enum fmx_mode {
+    FMX_SEARCH = 0,         /* (0, n),            all rows */
+    FMX_SEARCH_PREFIX = 1,  /* (0, n),            rows with L == 0 only */
+    FMX_SEARCH_SUFFIX = 2,  /* (0, pieces_count), all rows */
+    FMX_SEARCH_EXACT = 3    /* (0, pieces_count), rows with L == 0 only */
+} fmx_mode;
+
+#define FMX_LEVEL_COUNT_ONLY (-1)
+
+const char *fmx_last_error(void);
+int fmx_version(void);
+int fmx_device_count(void);
+void fmx_free(void *p);
+
+/* ---------------------------------------------------------------- construction
+ * Replaces Text::{new, with_max_character} (src/text.rs:28-49) + the six ::new
+ * constructors (src/frontend.rs:195-267).  char_width must be 1 (u8 texts).
+ * max_character = 255 is Text::new; anything else is Text::with_max_character.
+ * level = FMX_LEVEL_COUNT_ONLY builds the count-only variant; level >= 0 the
+ * ...WithLocate variant with that sampling level (sample.rs:21-44).
+ * Text validation and its messages follow sais.rs:128-139. */
+int fmx_index_build(const void *text, uint64_t n, uint32_t char_width, uint64_t max_character,
+                    int kind, int level, int device, fmx_index **out);
+
+/* Host-only half of construction: text -> device-layout blob (no GPU needed). */
+int fmx_blob_build(const void *text, uint64_t n, uint32_t char_width, uint64_t max_character,
+                   int kind, int level, void **blob, uint64_t *blob_bytes);
+/* Upload a blob (serialised once; the reference only has un-exposed serde derives,
+ * fm_index.rs:13, rlfmi.rs:15, multi_pieces.rs:16, sample.rs:12). */
+int fmx_index_from_blob(const void *blob, uint64_t blob_bytes, int device, fmx_index **out);
+int fmx_index_save(const fmx_index *idx, const char *path);
+int fmx_index_load(const char *path, int device, fmx_index **out);
+void fmx_index_free(fmx_index *idx);
+
+/* Suffix array of a text exactly as sais::build_suffix_array (sais.rs:115-144) returns it. */
+int fmx_build_suffix_array(const void *text, uint64_t n, uint32_t char_width, uint64_t *sa_out);
+
+/* SearchIndex::len (frontend.rs:35-39), heap_size (:41-44, here: device bytes),
+ * HasMultiPieces::pieces_count (multi_pieces.rs:220-222) */
+uint64_t fmx_index_len(const fmx_index *idx);
+uint64_t fmx_index_device_bytes(const fmx_index *idx);
+uint64_t fmx_index_pieces_count(const fmx_index *idx);
+int fmx_index_kind(const fmx_index *idx);
+int fmx_index_has_locate(const fmx_index *idx);
+int fmx_index_device(const fmx_index *idx);
+uint32_t fmx_index_wavelet_levels(const fmx_index *idx); /* Text::max_bits, text.rs:61-63 */
+uint32_t fmx_index_sample_level(const fmx_index *idx);
+
+/* ---------------------------------------------------------------- search / count
+ * Batched SearchIndex::search / search_prefix / search_suffix / search_exact and
+ * Search::search (refinement) -- src/wrapper.rs:37-42, 61-82, 99-124.
+ * Patterns are concatenated in `pat`; pattern p is pat[pat_off[p] .. pat_off[p+1]).
+ * If pat_off is NULL every pattern has `fixed_len` characters.
+ * init_s/init_e: NULL for a fresh search, else the ranges being refined (the new
+ * pattern is prepended, wrapper.rs:115).  out_s/out_e receive the SA range; count
+ * (wrapper.rs:132-134) is out_e - out_s.  The loop breaks as soon as s == e exactly
+ * as the reference does, so (s, e) are bit-identical, not just the count. */
+int fmx_search_batch(const fmx_index *idx, int mode, const uint8_t *pat, const uint64_t *pat_off,
+                     uint64_t fixed_len, uint64_t npat, const uint64_t *init_s,
+                     const uint64_t *init_e, uint64_t *out_s, uint64_t *out_e);
+int fmx_search_batch_device(const fmx_index *idx, int mode, const uint8_t *d_pat,
+                            const uint64_t *d_pat_off, uint64_t fixed_len, uint64_t npat,
+                            const uint64_t *d_init_s, const uint64_t *d_init_e, uint64_t *d_out_s,
+                            uint64_t *d_out_e, void *stream);
+/* after a *_device search on `stream` has completed: FMX_ERR_PATTERN_CHAR if any processed
+ * pattern character exceeded max_character.  Synchronises the stream. */
+int fmx_search_check(const fmx_index *idx, void *stream);
+
+/* ---------------------------------------------------------------- locate
+ * Batched Search::iter_matches + MatchWithLocate::locate (+ MatchWithPieceId::piece_id)
+ * -- src/wrapper.rs:137-139, 203-217, 238-248; get_sa: fm_index.rs:127-140,
+ * rlfmi.rs:176-189, multi_pieces.rs:188-201; piece_id: multi_pieces.rs:208-218.
+ * For each range [s[p], e[p]) the matches are emitted in ascending SA-row order (the
+ * reference's iteration order); with prefix_only != 0 only rows whose L is 0 are kept
+ * (wrapper.rs:208).  hit_off (npat+1 entries, caller-owned) receives the exclusive
+ * prefix sum of hit counts; *positions (and *piece_ids if non-NULL; MultiPieces only)
+ * receive hit_off[npat] values each and are released with fmx_free(). */
+int fmx_locate_batch(const fmx_index *idx, int prefix_only, const uint64_t *s, const uint64_t *e,
+                     uint64_t npat, uint64_t *hit_off, uint64_t **positions, uint64_t **piece_ids);
+/* two-phase device form: count (synchronous, returns the total), then fill (async). */
+int fmx_locate_count_device(const fmx_index *idx, int prefix_only, const uint64_t *d_s,
+                            const uint64_t *d_e, uint64_t npat, uint64_t *d_hit_off,
+                            uint64_t *total_hits, void *stream);
+int fmx_locate_fill_device(const fmx_index *idx, int prefix_only, const uint64_t *d_s,
+                           const uint64_t *d_e, uint64_t npat, const uint64_t *d_hit_off,
+                           uint64_t total_hits, uint64_t *d_positions, uint64_t *d_piece_ids,
+                           void *stream);
+
+/* ---------------------------------------------------------------- extraction
+ * Batched Match::iter_chars_backward / iter_chars_forward taken k characters deep
+ * -- src/wrapper.rs:143-183, 229-235.  rows are SA rows (the `i` of a Match).
+ * out is nrows*k bytes, row-major; out_len[r] is the number of characters produced
+ * (always k backward; forward stops early on MultiPieces when fl_map is None,
+ * multi_pieces.rs:171-181).  Unproduced bytes are 0. */
+int fmx_extract_batch(const fmx_index *idx, const uint64_t *rows, uint64_t nrows, uint32_t k,
+                      int forward, uint8_t *out, uint32_t *out_len);
+int fmx_extract_batch_device(const fmx_index *idx, const uint64_t *d_rows, uint64_t nrows,
+                             uint32_t k, int forward, uint8_t *d_out, uint32_t *d_out_len,
+                             void *stream);
+
+/* Backend primitives over a batch of rows (crate-private seam src/backend.rs:5-40),
+ * exposed for parity tests: op 0 = get_l, 1 = lf_map, 2 = get_f, 3 = fl_map (UINT64_MAX = None),
+ * 4 = get_sa, 5 = piece_id via the reference's literal LF walk. */
+int fmx_rows_op(const fmx_index *idx, int op, const uint64_t *rows, uint64_t nrows, uint64_t *out);
+/* lf_map2(c[k], i[k]) for a batch (backend.rs:16). */
+int fmx_lf_map2_batch(const fmx_index *idx, const uint8_t *c, const uint64_t *i, uint64_t nrows,
+                      uint64_t *out);
+
+/* ---------------------------------------------------------------- measurement helpers */
+/* Work counters of the last search / locate-fill launch (executed backward-search
+ * iterations, executed LF steps): the roofline numerator.  Synchronises the stream. */
+int fmx_last_work(const fmx_index *idx, void *stream, uint64_t *search_steps, uint64_t *lf_steps);
+/* Peak random 32-byte-sector gather rate microbenchmark over `bytes` of device memory
+ * (independent random loads, no dependent chain): the random-access roofline denominator.
+ * Returns sectors per second. */
+int fmx_random_gather_bench(int device, uint64_t bytes, uint64_t nloads, int iters,
+                            double *sectors_per_s);
+/* number of kernel launches issued by this library since load */
+uint64_t fmx_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FMX_H */

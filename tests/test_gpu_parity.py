@@ -1,0 +1,366 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (include/fmx.h) via the Python mirror of
+the reference API, against (1) the reference's golden vectors, (2) the CPU oracle on seeded inputs,
+(3) a naive scan (the reference's own differential method, tests/testutil/mod.rs).
+Bit-exact: SA ranges, counts, locate positions IN THE REFERENCE'S ORDER, piece ids, extracted chars."""
+import os
+
+import numpy as np
+import pytest
+
+import fmx_pkg
+from oracle import oracle as orc
+from refutil import (TEXT_README, TEXT_TWINKLE, build_text, naive_search, random_cases)
+
+pytestmark = pytest.mark.gpu
+fmx = fmx_pkg.load()
+
+MISS = b"mississippi\0"
+KINDS = {
+    orc.FM: (fmx.FMIndex, fmx.FMIndexWithLocate),
+    orc.RLFM: (fmx.RLFMIndex, fmx.RLFMIndexWithLocate),
+    orc.MULTI: (fmx.FMIndexMultiPieces, fmx.FMIndexMultiPiecesWithLocate),
+}
+
+
+def chain(index, op, start, n):
+    i, out = start, []
+    for _ in range(n):
+        i = int(index.rows_op(op, [i])[0])
+        out.append(i)
+    return out
+
+
+# ---- src/fm_index.rs:148-173, src/rlfmi.rs:255-351
+@pytest.mark.parametrize("kind", [orc.FM, orc.RLFM, orc.MULTI])
+def test_mississippi_golden(kind):
+    index = KINDS[kind][1].new(fmx.Text.new(MISS), 2)
+    assert chain(index, 1, 0, 12) == [1, 6, 7, 2, 8, 10, 3, 9, 11, 4, 5, 0]
+    rows = np.arange(12)
+    assert bytes(index.rows_op(0, rows).astype(np.uint8)) == b"ipssm\0pissii"
+    assert bytes(index.rows_op(2, rows).astype(np.uint8)) == bytes(sorted(MISS))
+    if kind != orc.MULTI:
+        assert list(index.rows_op(3, rows)) == [5, 0, 7, 10, 11, 4, 1, 6, 2, 3, 8, 9]
+    n = index.len()
+    for c, r in [(0, (0, 1)), (ord("i"), (1, 5)), (ord("m"), (5, 6)), (ord("p"), (6, 8)), (ord("s"), (8, 12))]:
+        if kind == orc.MULTI and c == 0:
+            continue
+        assert tuple(index.lf_map2_batch([c, c], [0, n])) == r
+    for pat, r in [(b"iss", (3, 5)), (b"ppi", (7, 8)), (b"si", (8, 10)), (b"ssi", (10, 12))]:
+        assert index.search(pat).get_range() == r
+
+
+# ---- README.md:49-85
+def test_readme_doctest():
+    index = fmx.FMIndexWithLocate.new(fmx.Text.new(TEXT_README), 2)
+    search = index.search("dolor")
+    assert search.count() == 4
+    assert [m.locate() for m in search.iter_matches()] == [246, 12, 300, 103]
+    import itertools
+    prefix = list(itertools.islice(next(iter(search.iter_matches())).iter_chars_backward(), 16))
+    assert bytes(reversed(prefix)) == b"Duis aute irure "
+    m3 = list(search.iter_matches())[3]
+    assert bytes(itertools.islice(m3.iter_chars_forward(), 20)) == b"dolore magna aliqua."
+
+
+# ---- examples/multi_pieces.rs:34-88
+def test_multi_pieces_example():
+    import itertools
+    index = fmx.FMIndexMultiPiecesWithLocate.new(fmx.Text.new(TEXT_TWINKLE), 2)
+    assert index.search("star").count() == 4
+    assert sorted(int(m.piece_id()) for m in index.search("How I wonder").iter_matches()) == [0, 0, 1, 2]
+    pre = [bytes(itertools.takewhile(lambda c: c != ord(" "), m.iter_chars_backward()))
+           for m in index.search(" in the dark").iter_matches()]
+    assert pre == [b"rellevart"]
+    suc = [bytes(itertools.takewhile(lambda c: c != ord(","), m.iter_chars_forward()))
+           for m in index.search("ing ").iter_matches()]
+    assert suc == [b"ing shines upon", b"ing sun is gone"]
+    assert sorted(int(m.piece_id()) for m in index.search_prefix("Twinkle").iter_matches()) == [0]
+    assert sorted(int(m.piece_id()) for m in index.search_suffix("what you are!\n").iter_matches()) == [0, 1, 2]
+
+
+# ---- tests/test_fmindex.rs:6-24, test_rlfmindex.rs, test_multi_pieces.rs:8-41, test_api.rs
+@pytest.mark.parametrize("kind", [orc.FM, orc.RLFM, orc.MULTI])
+def test_small_and_api(kind):
+    index = KINDS[kind][1].new(fmx.Text.new(b"a\0"), 2)
+    assert index.search("a").count() == 1
+    assert [m.locate() for m in index.search("a").iter_matches()] == [0]
+    if kind == orc.MULTI:
+        assert [int(m.piece_id()) for m in index.search("a").iter_matches()] == [0]
+    count_only = KINDS[kind][0].new(fmx.Text.new(b"text\0"))
+    assert count_only.len() == 5 and count_only.heap_size() > 0
+    assert count_only.search("t").count() == 2
+    with pytest.raises(fmx.Error):
+        count_only.locate_batch([0], [1])                 # DiscardedSuffixArray: no locate
+    with pytest.raises(fmx.InvalidText, match="must not start with zero"):
+        KINDS[kind][0].new(fmx.Text.new(b"\0a\0"))
+
+
+# ---- the reference's randomized differential tests, against BOTH the oracle and the naive scan
+@pytest.mark.parametrize("kind", [orc.FM, orc.RLFM, orc.MULTI])
+def test_random_differential(kind):
+    multi = kind == orc.MULTI
+    for text, level, pats in random_cases(seed=100 + kind, texts=40, patterns=100, text_size_max=1024,
+                                          alphabet_size=8, level_max=3, pattern_size_max=10, multi_pieces=multi):
+        index = KINDS[kind][1].new(fmx.Text.new(text), level)
+        oracle = orc.OracleIndex(text, kind, level=level)
+        flat, off = orc.pack_patterns(pats)
+        modes = [fmx.SEARCH] + ([fmx.SEARCH_PREFIX, fmx.SEARCH_SUFFIX, fmx.SEARCH_EXACT] if multi else [])
+        for mode in modes:
+            b = index.search_batch(pats, mode)
+            os_, oe = oracle.search_batch(flat, off, mode)
+            assert np.array_equal(b.s, os_) and np.array_equal(b.e, oe)
+            po = mode in (fmx.SEARCH_PREFIX, fmx.SEARCH_EXACT)
+            if multi:
+                hoff, pos, pid = b.locate(piece_ids=True)
+                ooff, opos, opid = oracle.locate_batch(os_, oe, prefix_only=po, want_piece_ids=True)
+                assert np.array_equal(pid, opid)
+            else:
+                hoff, pos = b.locate()
+                ooff, opos, _ = oracle.locate_batch(os_, oe, prefix_only=po)
+            assert np.array_equal(hoff, ooff) and np.array_equal(pos, opos)     # order included
+            for k, pat in enumerate(pats[:25]):
+                exp = naive_search(text, pat, mode in (1, 3), mode in (2, 3))
+                got = sorted(int(v) for v in pos[int(hoff[k]):int(hoff[k + 1])])
+                assert got == [p for p, _ in exp]
+                if mode == fmx.SEARCH:
+                    assert int(b.e[k] - b.s[k]) == len(exp)
+                if multi:
+                    assert sorted(int(v) for v in pid[int(hoff[k]):int(hoff[k + 1])]) == [d for _, d in exp]
+
+
+@pytest.mark.parametrize("kind", [orc.FM, orc.RLFM, orc.MULTI])
+def test_backend_primitives_vs_oracle(kind):
+    rng = np.random.default_rng(kind)
+    for mc in (4, 7, 255):
+        text = build_text(rng, 3000, min(mc, 8), kind == orc.MULTI)
+        index = KINDS[kind][1].new(fmx.Text.with_max_character(text, mc), 3)
+        oracle = orc.OracleIndex(text, kind, level=3, max_character=mc)
+        n = len(text)
+        rows = np.arange(n, dtype=np.uint64)
+        assert list(index.rows_op(0, rows)) == [oracle.get_l(i) for i in range(n)]
+        assert list(index.rows_op(1, rows)) == [oracle.lf_map(i) for i in range(n)]
+        assert list(index.rows_op(2, rows)) == [oracle.get_f(i) for i in range(n)]
+        exp_fl = [oracle.fl_map(i) for i in range(n)]
+        assert list(index.rows_op(3, rows)) == [(1 << 64) - 1 if v is None else v for v in exp_fl]
+        assert list(index.rows_op(4, rows)) == [oracle.get_sa(i) for i in range(n)]
+        if kind == orc.MULTI:
+            assert list(index.rows_op(5, rows)) == [oracle.piece_id(i) for i in range(n)]   # literal walk
+        cs, is_ = [], []
+        for c in sorted(set(text)) + [mc]:
+            for i in list(rng.integers(0, n + 1, 300)) + [0, n]:
+                cs.append(c)
+                is_.append(int(i))
+        assert list(index.lf_map2_batch(cs, is_)) == [oracle.lf_map2(c, i) for c, i in zip(cs, is_)]
+
+
+@pytest.mark.parametrize("kind", [orc.FM, orc.RLFM, orc.MULTI])
+def test_extraction_vs_oracle(kind):
+    rng = np.random.default_rng(50 + kind)
+    text = build_text(rng, 5000, 8, kind == orc.MULTI)
+    index = KINDS[kind][0].new(fmx.Text.new(text))
+    oracle = orc.OracleIndex(text, kind)
+    rows = rng.integers(0, len(text), 500).astype(np.uint64)
+    for fwd in (False, True):
+        out, ln = index.extract_batch(rows, 37, fwd)
+        oout, oln = oracle.extract_batch(rows, 37, fwd)
+        assert np.array_equal(ln, oln) and np.array_equal(out, oout)
+
+
+def test_refinement_and_empty_pattern():
+    index = fmx.FMIndexWithLocate.new(fmx.Text.new(MISS), 0)
+    assert index.search(b"").get_range() == (0, 12)
+    assert index.search(b"si").search(b"s").get_range() == index.search(b"ssi").get_range()
+    b = index.search_batch([b"si", b"pi", b"i"]).search_batch([b"s", b"p", b"ss"])
+    assert [tuple(x) for x in zip(b.s, b.e)] == [index.search(p).get_range() for p in (b"ssi", b"ppi", b"ssi")]
+    empty = index.search_batch([])
+    assert len(empty) == 0
+    hoff, pos = empty.locate()
+    assert list(hoff) == [0] and pos.size == 0
+
+
+def test_pattern_char_above_max_character():
+    text = bytes([1, 2, 3, 4, 1, 2, 0])
+    index = fmx.FMIndex.new(fmx.Text.with_max_character(text, 4))
+    with pytest.raises(IndexError):
+        index.search(bytes([1, 5]))
+    r = index.search(bytes([5, 4, 4])).get_range()       # range empties before the bad char is reached
+    assert r[0] == r[1]
+    assert index.search(bytes([1, 2])).count() == 2       # the handle stays usable after the error
+
+
+def test_save_load_roundtrip(tmp_path):
+    rng = np.random.default_rng(9)
+    text = build_text(rng, 20000, 5, False)
+    index = fmx.RLFMIndexWithLocate.new(fmx.Text.with_max_character(text, 4), 2)
+    p = tmp_path / "index.fmx"
+    index.save(p)
+    again = fmx.RLFMIndexWithLocate.load(p)
+    pats = [text[i:i + 12] for i in range(0, 5000, 97)]
+    a, b = index.search_batch(pats), again.search_batch(pats)
+    assert np.array_equal(a.s, b.s) and np.array_equal(a.e, b.e)
+    assert all(np.array_equal(x, y) for x, y in zip(a.locate(), b.locate()))
+    with pytest.raises(fmx.Error):
+        fmx.FMIndex.load(p)
+
+
+def dna(n, seed):
+    rng = np.random.default_rng(seed)
+    return np.append(rng.integers(1, 5, n, dtype=np.uint8), np.uint8(0))
+
+
+def mixed_patterns(text, npat, m, seed, sigma=4):
+    rng = np.random.default_rng(seed)
+    pats = rng.integers(1, sigma + 1, (npat, m), dtype=np.uint8)
+    starts = rng.integers(0, text.size - 1 - m, npat)
+    idx = np.arange(m)
+    sampled = text[starts[:, None] + idx[None, :]]
+    pats[::2] = sampled[::2]
+    return pats, starts
+
+
+# ---- BASELINE config 1: 10k random 20-mers over 1 MB random ACGT + \0 (+ the reference's own
+# bench shape, benches/count.rs:23-24: 50 000 binary symbols, all 256 8-mers)
+def test_config1_count_parity():
+    text = dna(1_000_000, 1)
+    pats, _ = mixed_patterns(text, 10_000, 20, 2)
+    index = fmx.FMIndex.new(fmx.Text.with_max_character(text, 4))
+    oracle = orc.OracleIndex(text, orc.FM, max_character=4)
+    b = index.search_batch(pats)
+    s, e, steps = oracle.search_batch(pats.reshape(-1), np.arange(10_001, dtype=np.uint64) * 20, want_steps=True)
+    assert np.array_equal(b.s, s) and np.array_equal(b.e, e)
+    assert index.last_work()[0] == int(steps.sum())           # executed iterations: the roofline numerator
+
+    rng = np.random.default_rng(0)
+    btext = np.append(np.where(rng.random(50_000) < 0.5, ord("0"), ord("1")).astype(np.uint8), np.uint8(0))
+    bpats = np.array([[ord("0") + ((v >> (7 - k)) & 1) for k in range(8)] for v in range(256)], dtype=np.uint8)
+    for cls, kind in ((fmx.FMIndexWithLocate, orc.FM), (fmx.RLFMIndexWithLocate, orc.RLFM)):
+        ix = cls.new(fmx.Text.with_max_character(btext, ord("1")), 2)
+        oc = orc.OracleIndex(btext, kind, level=2, max_character=ord("1"))
+        bb = ix.search_batch(bpats)
+        s, e = oc.search_batch(bpats.reshape(-1), np.arange(257, dtype=np.uint64) * 8)
+        assert np.array_equal(bb.s, s) and np.array_equal(bb.e, e)
+        hoff, pos = bb.locate()
+        ooff, opos, _ = oc.locate_batch(s, e)
+        assert np.array_equal(hoff, ooff) and np.array_equal(pos, opos)
+        assert int(hoff[-1]) == 50_000 - 7
+
+
+# ---- config 2 shape at a size the oracle finishes in seconds, + size-independent properties
+@pytest.mark.parametrize("n,npat", [(4_000_000, 200_000)])
+def test_config2_locate_parity_and_properties(n, npat):
+    text = dna(n, 3)
+    pats, starts = mixed_patterns(text, npat, 32, 4)
+    index = fmx.FMIndexWithLocate.new(fmx.Text.with_max_character(text, 4), 2)
+    oracle = orc.OracleIndex(text, orc.FM, level=2, max_character=4)
+    b = index.search_batch(pats)
+    hoff, pos = b.locate()
+    s, e = oracle.search_batch(pats.reshape(-1), np.arange(npat + 1, dtype=np.uint64) * 32)
+    ooff, opos, _ = oracle.locate_batch(s, e)
+    assert np.array_equal(b.s, s) and np.array_equal(b.e, e)
+    assert np.array_equal(hoff, ooff) and np.array_equal(pos, opos)
+    check_locate_properties(text, pats, starts, b, hoff, pos)
+
+
+def check_locate_properties(text, pats, starts, b, hoff, pos):
+    """Size-independent properties: every located position really holds the pattern; every sampled
+    pattern finds its own origin; counts equal hit counts; positions are distinct per pattern."""
+    npat, m = pats.shape
+    cnt = (b.e - b.s).astype(np.int64)
+    assert np.array_equal(np.diff(hoff.astype(np.int64)), cnt)
+    owner = np.repeat(np.arange(npat), cnt)
+    got = text[pos.astype(np.int64)[:, None] + np.arange(m)[None, :]]
+    assert np.array_equal(got, pats[owner])
+    sampled = np.arange(0, npat, 2)
+    assert np.all(cnt[sampled] >= 1)
+    # origin among the hits of each sampled pattern
+    first = hoff[sampled].astype(np.int64)
+    found = np.zeros(sampled.size, dtype=bool)
+    for k in range(int(cnt[sampled].max())):
+        ok = k < cnt[sampled]
+        idx = np.where(ok, first + k, 0)
+        found |= ok & (pos[idx].astype(np.int64) == starts[sampled])
+    assert found.all()
+
+
+@pytest.mark.parametrize("kind", [orc.RLFM, orc.MULTI])
+def test_medium_repetitive_and_multi(kind):
+    rng = np.random.default_rng(21)
+    if kind == orc.RLFM:      # config 3 shape, scaled: mutated copies of one haplotype
+        base = rng.integers(1, 5, 50_000, dtype=np.uint8)
+        copies = []
+        for _ in range(16):
+            c = base.copy()
+            mut = rng.random(c.size) < 0.001
+            c[mut] = rng.integers(1, 5, int(mut.sum()), dtype=np.uint8)
+            copies.append(c)
+        text = np.append(np.concatenate(copies), np.uint8(0))
+    else:                     # config 4 shape, scaled: 24 chromosome-like pieces
+        lens = (rng.integers(20_000, 60_000, 24))
+        text = np.concatenate([np.append(rng.integers(1, 5, int(l), dtype=np.uint8), np.uint8(0)) for l in lens])
+    pats, starts = mixed_patterns(text, 20_000, 32, 5)
+    index = KINDS[kind][1].new(fmx.Text.with_max_character(text, 4), 2)
+    oracle = orc.OracleIndex(text, kind, level=2, max_character=4)
+    b = index.search_batch(pats)
+    s, e = oracle.search_batch(pats.reshape(-1), np.arange(20_001, dtype=np.uint64) * 32)
+    assert np.array_equal(b.s, s) and np.array_equal(b.e, e)
+    if kind == orc.MULTI:
+        hoff, pos, pid = b.locate(piece_ids=True)
+        ooff, opos, opid = oracle.locate_batch(s, e, want_piece_ids=False)
+        assert np.array_equal(hoff, ooff) and np.array_equal(pos, opos)
+        ends = np.flatnonzero(text == 0)
+        assert np.array_equal(pid, np.searchsorted(ends, pos, side="left"))   # piece id = zeros before position
+    else:
+        hoff, pos = b.locate()
+        ooff, opos, _ = oracle.locate_batch(s, e)
+        assert np.array_equal(hoff, ooff) and np.array_equal(pos, opos)
+
+
+# ---- config 5 shape, scaled: byte alphabet (L = 8), ragged pattern lengths 8..64
+def test_byte_alphabet_ragged():
+    rng = np.random.default_rng(80)
+    n = 2_000_000
+    text = np.append(rng.integers(1, 256, n, dtype=np.uint8), np.uint8(0))
+    lens = rng.integers(8, 65, 50_000)
+    starts = rng.integers(0, n - 64, 50_000)
+    pats = []
+    for k in range(50_000):
+        pats.append(text[starts[k]:starts[k] + lens[k]].tobytes() if k & 1 else
+                    rng.integers(1, 256, int(lens[k]), dtype=np.uint8).tobytes())
+    flat, off = orc.pack_patterns(pats)
+    index = fmx.FMIndexWithLocate.new(fmx.Text.new(text), 2)
+    oracle = orc.OracleIndex(text, orc.FM, level=2)
+    b = index.search_batch((flat, off))
+    s, e = oracle.search_batch(flat, off)
+    assert np.array_equal(b.s, s) and np.array_equal(b.e, e)
+    hoff, pos = b.locate()
+    ooff, opos, _ = oracle.locate_batch(s, e)
+    assert np.array_equal(hoff, ooff) and np.array_equal(pos, opos)
+
+
+def test_huge_range_locate():
+    """A pattern matching a large share of the text: one pattern, many hits (load balance path)."""
+    text = dna(300_000, 77)
+    index = fmx.FMIndexWithLocate.new(fmx.Text.with_max_character(text, 4), 3)
+    oracle = orc.OracleIndex(text, orc.FM, level=3, max_character=4)
+    b = index.search_batch([bytes([1]), bytes([2, 3]), b""])
+    hoff, pos = b.locate()
+    s, e = oracle.search_batch(*orc.pack_patterns([bytes([1]), bytes([2, 3]), b""]))
+    ooff, opos, _ = oracle.locate_batch(s, e)
+    assert np.array_equal(hoff, ooff) and np.array_equal(pos, opos)
+    assert int(hoff[-1]) > 300_000 and sorted(pos[int(hoff[2]):]) == list(range(300_001))
+
+
+@pytest.mark.skipif(os.environ.get("FMX_SKIP_FULL") == "1", reason="full-size run disabled")
+def test_config2_full_size_properties():
+    """BASELINE config 2 at full size (100 MB DNA, 1M 32-mers, level 2): size-independent
+    properties (bench.py checks bit-exact parity with the oracle on a sample of this workload)."""
+    n, npat = 100_000_000, 1_000_000
+    text = dna(n, 3)
+    pats, starts = mixed_patterns(text, npat, 32, 4)
+    index = fmx.FMIndexWithLocate.new(fmx.Text.with_max_character(text, 4), 2)
+    b = index.search_batch(pats)
+    hoff, pos = b.locate()
+    check_locate_properties(text, pats, starts, b, hoff, pos)
+    # checksum of checksums: the batch split in two halves gives the same answers
+    b1, b2 = index.search_batch(pats[: npat // 2]), index.search_batch(pats[npat // 2:])
+    assert np.array_equal(np.concatenate([b1.s, b2.s]), b.s) and np.array_equal(np.concatenate([b1.e, b2.e]), b.e)

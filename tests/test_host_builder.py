@@ -1,0 +1,108 @@
+"""Host-side logic without a GPU: the builder's device-layout blob, read back on the CPU,
+agrees with the oracle; the C-ABI library loads and exports every declared symbol."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import fmx_pkg
+from oracle import oracle as orc
+from refutil import TEXT_README, TEXT_TWINKLE, build_text
+from blobreader import Blob
+
+fmx = fmx_pkg.load()
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = fmx.load_library()
+    hdr = open(os.path.join(ROOT, "include", "fmx.h")).read()
+    declared = set(re.findall(r"\b(fmx_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"fmx_index", "fmx_status", "fmx_kind", "fmx_mode"}
+    assert len(declared) >= 30
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/fmx.h but not exported"
+    assert set(fmx._lib.SIGNATURES) == declared
+    assert L.fmx_version() == 100
+
+
+def test_no_gpu_means_loud_failure():
+    L = fmx.load_library()
+    if L.fmx_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(fmx.Error, match="no CUDA device"):
+        fmx.FMIndex.new(fmx.Text.new(b"abc\0"))
+
+
+@pytest.mark.parametrize("text,msg", [
+    (b"\0abc\0", "must not start with zero"),
+    (b"abc", "must end with exactly one zero"),
+    (b"abc\0\0", "must end with exactly one zero"),
+])
+def test_invalid_text_messages(text, msg):
+    with pytest.raises(fmx.InvalidText, match=msg):      # sais.rs:128-139 through the C ABI
+        fmx.blob_build(fmx.Text.new(text), fmx.KIND_FM, 2)
+    with pytest.raises(fmx.InvalidText, match=msg):
+        fmx.suffix_array(text)
+
+
+def test_char_above_max_character_rejected():
+    with pytest.raises(fmx.Error):
+        fmx.blob_build(fmx.Text.with_max_character(bytes([1, 2, 9, 0]), 4), fmx.KIND_FM)
+
+
+def test_suffix_array_matches_oracle():
+    rng = np.random.default_rng(3)
+    for t in range(60):
+        n = int(rng.integers(2, 2000))
+        text = build_text(rng, n, int(rng.choice([2, 4, 8, 200])), multi_pieces=bool(t & 1))
+        assert np.array_equal(fmx.suffix_array(text), orc.suffix_array(text))
+    big = build_text(rng, 300_000, 4, False)
+    assert np.array_equal(fmx.suffix_array(big), orc.suffix_array(big))
+    rep = (build_text(rng, 5000, 4, False)[:-1] * 40) + b"\0"      # highly repetitive
+    assert np.array_equal(fmx.suffix_array(rep), orc.suffix_array(rep))
+
+
+CASES = [
+    (b"mississippi\0", 255, 2), (TEXT_README, 255, 2), (TEXT_TWINKLE, 255, 2), (b"a\0", 255, 2),
+]
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_blob_reader_matches_oracle(kind):
+    rng = np.random.default_rng(kind + 40)
+    cases = list(CASES)
+    for _ in range(6):
+        mc = int(rng.choice([4, 7, 255]))
+        text = build_text(rng, int(rng.integers(2, 700)), min(mc, 8) if kind == 2 else min(mc, 7), kind == 2)
+        cases.append((text, mc, int(rng.integers(0, 4))))
+    for text, mc, level in cases:
+        if kind != 2 and 0 in text[:-1]:
+            continue
+        o = orc.OracleIndex(text, kind, level=level, max_character=mc)
+        b = Blob(fmx.blob_build(fmx.Text.with_max_character(text, mc), kind, level))
+        n = len(text)
+        assert (b.n, b.kind, b.levels, b.cs_len) == (n, kind, int(mc).bit_length(), mc + 1)
+        assert b.sa_level == orc.lib().orc_sample_level(o._h)
+        assert b.sa_word_size == orc.lib().orc_sample_word_size(o._h)
+        rows = range(n) if n < 300 else [int(v) for v in rng.integers(0, n, 200)]
+        for i in rows:
+            c, nx = b.lf_step(i)
+            assert c == o.get_l(i) and nx == o.lf_map(i)
+            assert b.get_sa(i) == o.get_sa(i)
+        chars = sorted(set(text)) + [c for c in (1, mc) if c not in text]
+        for c in chars:
+            for i in list(rows)[:80] + [n]:
+                assert b.lf_map2(c, i) == o.lf_map2(c, i), (c, i)
+        for _ in range(30):
+            m = int(rng.integers(1, 8))
+            p0 = int(rng.integers(0, max(1, n - m)))
+            pat = text[p0:p0 + m] if rng.random() < 0.7 else bytes(int(x) for x in rng.integers(1, mc + 1, m))
+            assert b.search(pat) == o.search(pat)
+            if kind == 2:
+                for mode in (1, 2, 3):
+                    assert b.search(pat, mode) == o.search(pat, mode)
+        if kind == 2:
+            assert b.ndoc == o.pieces_count() and b.first_row == orc.lib().orc_first_row(o._h)
+            assert [int(v) for v in b.doc] == [orc.lib().orc_doc(o._h, k) for k in range(b.ndoc)]

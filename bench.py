@@ -34,43 +34,58 @@ WORKLOADS = {
 }
 
 
-def mix64(x: np.ndarray) -> np.ndarray:
-    """splitmix64 finaliser, vectorised: a self-contained, reproducible generator."""
-    x = (x + np.uint64(0x9E3779B97F4A7C15)).astype(np.uint64)
-    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
-    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-    return x ^ (x >> np.uint64(31))
+def _s64(c: int) -> int:
+    return c - (1 << 64) if c >= (1 << 63) else c
 
 
-def gen_text(n: int, sigma: int, seed: int) -> np.ndarray:
-    out = np.empty(n + 1, dtype=np.uint8)
-    chunk = 1 << 24
-    with np.errstate(over="ignore"):
-        for lo in range(0, n, chunk):
-            hi = min(n, lo + chunk)
-            r = mix64(np.arange(lo, hi, dtype=np.uint64) + np.uint64(seed) * np.uint64(0x1000000000))
-            out[lo:hi] = (r % np.uint64(sigma)).astype(np.uint8) + 1
+def _lsr(x, k: int):
+    """logical right shift of an int64 torch tensor"""
+    return (x >> k) & ((1 << (64 - k)) - 1)
+
+
+def mix64(x):
+    """splitmix64 finaliser on int64 torch tensors (wrapping arithmetic): a self-contained,
+    reproducible generator that runs identically on CPU and GPU."""
+    x = x + _s64(0x9E3779B97F4A7C15)
+    x = (x ^ _lsr(x, 30)) * _s64(0xBF58476D1CE4E5B9)
+    x = (x ^ _lsr(x, 27)) * _s64(0x94D049BB133111EB)
+    return x ^ _lsr(x, 31)
+
+
+def gen_text(n: int, sigma: int, seed: int, device="cpu"):
+    """n symbols uniform over 1..=sigma followed by the \\0 terminator (torch uint8 tensor on `device`)."""
+    import torch
+
+    out = torch.empty(n + 1, dtype=torch.uint8, device=device)
+    chunk = 1 << 26
+    for lo in range(0, n, chunk):
+        hi = min(n, lo + chunk)
+        r = mix64(torch.arange(lo, hi, dtype=torch.int64, device=device) + seed * 0x1000000000)
+        out[lo:hi] = (_lsr(r, 33) % sigma + 1).to(torch.uint8)
     out[n] = 0
     return out
 
 
-def gen_patterns(text: np.ndarray, npat: int, m: int, sigma: int, seed: int):
-    """even patterns: substrings at uniform random offsets (>= 1 hit); odd: uniform random."""
-    n = text.size - 1
-    with np.errstate(over="ignore"):
-        r = mix64(np.arange(npat, dtype=np.uint64) + np.uint64(seed) * np.uint64(0x1000000000))
-        starts = (r % np.uint64(n - m)).astype(np.int64)
-        pats = np.empty((npat, m), dtype=np.uint8)
-        chunk = 1 << 20
-        for lo in range(0, npat, chunk):
-            hi = min(npat, lo + chunk)
-            k = np.arange(lo, hi, dtype=np.uint64)
-            rnd = mix64(k[:, None] * np.uint64(64) + np.arange(m, dtype=np.uint64)[None, :]
-                        + np.uint64(seed + 1) * np.uint64(0x1000000000))
-            blk = (rnd % np.uint64(sigma)).astype(np.uint8) + 1
-            samp = text[starts[lo:hi, None] + np.arange(m)[None, :]]
-            even = (np.arange(lo, hi) % 2 == 0)[:, None]
-            pats[lo:hi] = np.where(even, samp, blk)
+def gen_patterns(text, npat: int, m: int, sigma: int, seed: int):
+    """even patterns: substrings at uniform random offsets (>= 1 hit); odd: uniform random.
+    `text` is a torch uint8 tensor; returns (patterns [npat, m] uint8, starts [npat] int64) on its device."""
+    import torch
+
+    device = text.device
+    n = text.numel() - 1
+    pats = torch.empty((npat, m), dtype=torch.uint8, device=device)
+    starts = torch.empty(npat, dtype=torch.int64, device=device)
+    cols = torch.arange(m, dtype=torch.int64, device=device)[None, :]
+    chunk = 1 << 21
+    for lo in range(0, npat, chunk):
+        hi = min(npat, lo + chunk)
+        k = torch.arange(lo, hi, dtype=torch.int64, device=device)
+        st = _lsr(mix64(k + seed * 0x1000000000), 1) % (n - m)
+        rnd = mix64(k[:, None] * 64 + cols + (seed + 1) * 0x1000000000)
+        blk = (_lsr(rnd, 33) % sigma + 1).to(torch.uint8)
+        samp = text[st[:, None] + cols]
+        pats[lo:hi] = torch.where((k % 2 == 0)[:, None], samp, blk)
+        starts[lo:hi] = st
     return pats, starts
 
 
@@ -185,9 +200,10 @@ def reference_arm(args, wl_name, wl):
 
     n, npat, m, sigma, mc, level, desc = wl
     nthreads = host_threads()
-    text = gen_text(n, sigma, 3)
+    text_t = gen_text(n, sigma, 3)
     sample = min(npat, args.cpu_sample)
-    pats, _ = gen_patterns(text, sample, m, sigma, 4)
+    pats = gen_patterns(text_t, sample, m, sigma, 4)[0].numpy()
+    text = text_t.numpy()
     t0 = time.perf_counter()
     oracle_index = orc.OracleIndex(text, orc.FM, level=level, max_character=mc)
     build_s = time.perf_counter() - t0
@@ -226,6 +242,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2_dna100m", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample", type=int, default=200_000, help="patterns in the CPU baseline sample")
+    ap.add_argument("--npat", type=int, default=0, help="override the workload's patterns per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gather-peak", action="store_true")
     args = ap.parse_args()
@@ -253,18 +270,27 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     n, npat, m, sigma, mc, level, desc = wl
-    text = gen_text(n, sigma, 3)
+    if args.npat:
+        npat = args.npat
+    # synthetic text and patterns are generated on the GPU (same integer arithmetic as on the CPU)
+    d_text = gen_text(n, sigma, 3, device="cuda")
     # index replicated on every GPU; each rank answers its own batch (weak scaling, no collective
     # on the query path)
-    pats, starts = gen_patterns(text, npat, m, sigma, 4 + 1000 * rank)
+    d_pat, _ = gen_patterns(d_text, npat, m, sigma, 4 + 1000 * rank)
+    text = d_text.cpu().numpy()
+    del d_text
+    torch.cuda.empty_cache()
     t0 = time.perf_counter()
     index = fmx.FMIndexWithLocate.new(fmx.Text.with_max_character(text, mc), level, device=local)
     build_s = time.perf_counter() - t0
     h = index._h
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: the library launches on the stream it is handed, and the CUDA
+    # events below must sit on that same stream
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     sp = C.c_void_p(stream.cuda_stream)
+    assert stream.cuda_stream != 0
 
-    d_pat = torch.from_numpy(pats).cuda()
     d_s = torch.empty(npat, dtype=torch.int64, device="cuda")
     d_e = torch.empty(npat, dtype=torch.int64, device="cuda")
     d_hoff = torch.empty(npat + 1, dtype=torch.int64, device="cuda")
@@ -337,7 +363,8 @@ def main():
     value = world * npat / (ms_per_step * 1e-3)
 
     # ---- end to end through the host-buffer C ABI: pinned host inputs, H2D + D2H inside the timed region
-    h_pat = torch.from_numpy(pats).pin_memory()
+    h_pat = torch.empty((npat, m), dtype=torch.uint8).pin_memory()
+    h_pat.copy_(d_pat)
     h_s = torch.empty(npat, dtype=torch.int64).pin_memory()
     h_e = torch.empty(npat, dtype=torch.int64).pin_memory()
     h_hoff = torch.empty(npat + 1, dtype=torch.int64).pin_memory()
@@ -408,7 +435,7 @@ def main():
         obuild = time.perf_counter() - tb
         best = None
         for _ in range(2):
-            dt, s, e, ohoff, opos = run_cpu_path(oracle_index, pats[:sample], nthreads)
+            dt, s, e, ohoff, opos = run_cpu_path(oracle_index, h_pat[:sample].numpy(), nthreads)
             best = dt if best is None else min(best, dt)
         g_s = d_s[:sample].cpu().numpy().view(np.uint64)
         g_e = d_e[:sample].cpu().numpy().view(np.uint64)

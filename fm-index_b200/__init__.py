@@ -440,8 +440,8 @@ def blob_build(text: Text, kind, level=None) -> np.ndarray:
     return a
 
 
-def random_gather_peak(device=0, nbytes=4 << 30, nloads=1 << 28, iters=3) -> float:
-    """Measured peak random 32-byte sector gather rate (sectors/s): the random-access roofline."""
+def random_gather_peak(device=0, nbytes=4 << 30, nloads=1 << 28, iters=3, load_bytes=32) -> float:
+    """Measured peak random gather rate in 32-byte sectors/s: the random-access roofline."""
     v = C.c_double(0)
-    _check(load_library().fmx_random_gather_bench(device, nbytes, nloads, iters, C.byref(v)))
+    _check(load_library().fmx_random_gather_bench(device, nbytes, nloads, iters, load_bytes, C.byref(v)))
     return v.value

@@ -42,7 +42,7 @@ SIGNATURES = {
     "fmx_rows_op": (_int, [_vp, _int, _vp, _u64, _vp]),
     "fmx_lf_map2_batch": (_int, [_vp, _vp, _vp, _u64, _vp]),
     "fmx_last_work": (_int, [_vp, _vp, _u64p, _u64p]),
-    "fmx_random_gather_bench": (_int, [_int, _u64, _u64, _int, C.POINTER(C.c_double)]),
+    "fmx_random_gather_bench": (_int, [_int, _u64, _u64, _int, _u32, C.POINTER(C.c_double)]),
     "fmx_launch_count": (_u64, []),
 }
 

@@ -717,8 +717,11 @@ extern "C" int fmx_last_work(const fmx_index *idx, void *stream, uint64_t *searc
     return FMX_OK;
 }
 
-extern "C" int fmx_random_gather_bench(int device, uint64_t bytes, uint64_t nloads, int iters, double *sectors_per_s) {
+extern "C" int fmx_random_gather_bench(int device, uint64_t bytes, uint64_t nloads, int iters, uint32_t load_bytes,
+                                       double *sectors_per_s) {
     if (!sectors_per_s || bytes < 4096 || nloads == 0 || iters <= 0) return fail(FMX_ERR_INVALID_ARG, "bad argument");
+    if (load_bytes != 32 && load_bytes != 64 && load_bytes != 128) return fail(FMX_ERR_INVALID_ARG, "load_bytes must be 32, 64 or 128");
+    if (bytes / 32 >= 0xFFFFFFFFull) return fail(FMX_ERR_INVALID_ARG, "buffer too large (max 128 GiB)");
     CUDA_TRY(cudaSetDevice(device));
     void *buf = nullptr;
     uint32_t *sink = nullptr;
@@ -731,17 +734,21 @@ extern "C" int fmx_random_gather_bench(int device, uint64_t bytes, uint64_t nloa
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     unsigned grid = (unsigned)sms * 8;
-    uint64_t nsectors = bytes / 32;
+    uint64_t nunits = bytes / load_bytes;
     double best = 0;
     for (int it = 0; it < iters + 1; it++) {
         CUDA_TRY(cudaEventRecord(e0, 0));
-        k_random_gather<<<grid, 256>>>(static_cast<const uint4 *>(buf), nsectors, nloads, 0x1234567ull * (it + 1), sink);
+        const uint4 *b4 = static_cast<const uint4 *>(buf);
+        uint64_t sd = 0x1234567ull * (it + 1);
+        if (load_bytes == 32) k_random_gather<32><<<grid, 256>>>(b4, nunits, nloads, sd, sink);
+        else if (load_bytes == 64) k_random_gather<64><<<grid, 256>>>(b4, nunits, nloads, sd, sink);
+        else k_random_gather<128><<<grid, 256>>>(b4, nunits, nloads, sd, sink);
         LAUNCH_CHECK();
         CUDA_TRY(cudaEventRecord(e1, 0));
         CUDA_TRY(cudaEventSynchronize(e1));
         float ms = 0;
         CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
-        double rate = (double)nloads / (ms * 1e-3);
+        double rate = (double)nloads * (load_bytes / 32) / (ms * 1e-3);
         if (it > 0 && rate > best) best = rate;  // first iteration is warm-up
     }
     cudaEventDestroy(e0);

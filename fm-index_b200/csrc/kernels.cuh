@@ -651,20 +651,26 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const Tin *in, uint
 }
 
 // ------------------------------------------------------------------ random gather microbenchmark
-// independent random 32-byte sector loads (no dependent chain): the random-access roofline denominator
-__global__ void __launch_bounds__(256) k_random_gather(const uint4 *buf, uint64_t nsectors, uint64_t nloads,
+// independent random loads of WIDTH bytes (32 = one sector, 64, 128 = a full line), no dependent
+// chain: the random-access roofline denominator
+template <int WIDTH>
+__global__ void __launch_bounds__(256) k_random_gather(const uint4 *buf, uint64_t nunits, uint64_t nloads,
                                                        uint64_t seed, uint32_t *sink) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     uint32_t acc = 0;
+#pragma unroll 4
     for (uint64_t k = t; k < nloads; k += stride) {
         uint64_t z = (k + seed) * 0x9E3779B97F4A7C15ull;  // splitmix64 finaliser
         z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
         z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
         z ^= z >> 31;
-        uint32_t blk = (uint32_t)(z % nsectors);
-        RB b = rb_load(buf, blk);
-        acc += b.w[0] ^ b.w[7];
+        uint64_t unit = z % nunits;
+#pragma unroll
+        for (int q = 0; q < WIDTH / 32; q++) {
+            RB b = rb_load(buf, (uint32_t)(unit * (WIDTH / 32) + q));
+            acc += b.w[0] ^ b.w[7];
+        }
     }
     if (acc == 0x12345678u) *sink = acc;
 }

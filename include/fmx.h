@@ -166,11 +166,11 @@ int fmx_lf_map2_batch(const fmx_index *idx, const uint8_t *c, const uint64_t *i,
 /* Work counters of the last search / locate-fill launch (executed backward-search
  * iterations, executed LF steps): the roofline numerator.  Synchronises the stream. */
 int fmx_last_work(const fmx_index *idx, void *stream, uint64_t *search_steps, uint64_t *lf_steps);
-/* Peak random 32-byte-sector gather rate microbenchmark over `bytes` of device memory
- * (independent random loads, no dependent chain): the random-access roofline denominator.
- * Returns sectors per second. */
+/* Peak random gather rate microbenchmark over `bytes` of device memory (independent random
+ * loads of load_bytes = 32 (one sector), 64 or 128 bytes each; no dependent chain): the
+ * random-access roofline denominator.  Returns 32-byte sectors per second. */
 int fmx_random_gather_bench(int device, uint64_t bytes, uint64_t nloads, int iters,
-                            double *sectors_per_s);
+                            uint32_t load_bytes, double *sectors_per_s);
 /* number of kernel launches issued by this library since load */
 uint64_t fmx_launch_count(void);
 

@@ -190,7 +190,7 @@ def test_pattern_char_above_max_character():
 
 def test_save_load_roundtrip(tmp_path):
     rng = np.random.default_rng(9)
-    text = build_text(rng, 20000, 5, False)
+    text = build_text(rng, 20000, 4, False)
     index = fmx.RLFMIndexWithLocate.new(fmx.Text.with_max_character(text, 4), 2)
     p = tmp_path / "index.fmx"
     index.save(p)

@@ -240,6 +240,10 @@ class _Index:
         _check(self._L.fmx_lf_map2_batch(self._h, _ptr(c), _ptr(i), i.size, _ptr(out)))
         return out
 
+    def set_option(self, key, value):
+        """tuning knobs for A/B measurements; results never change"""
+        _check(self._L.fmx_index_set_option(self._h, key.encode(), int(value)))
+
     def last_work(self, stream=None):
         a, b = C.c_uint64(0), C.c_uint64(0)
         _check(self._L.fmx_last_work(self._h, stream, C.byref(a), C.byref(b)))

@@ -8,6 +8,7 @@
 #include "builder.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/fmx.h"
@@ -59,7 +60,7 @@ int build_suffix_array(const uint8_t *text, uint64_t n, uint64_t *sa_out, std::s
     return 0;
 }
 
-// One rank-able bit vector in RB32 form (fmx_layout.h).
+// One rank-able bit vector in RB192 form (fmx_layout.h).
 struct RBVec {
     uint64_t nbits, nblk;
     std::vector<uint32_t> w;
@@ -67,24 +68,28 @@ struct RBVec {
     inline void set(uint64_t pos) {
         uint64_t b = pos / FMX_RB_BITS;
         uint32_t r = (uint32_t)(pos - b * FMX_RB_BITS);
-        w[b * 8 + 1 + (r >> 5)] |= 1u << (r & 31);
+        w[b * 8 + 2 + (r >> 5)] |= 1u << (r & 31);
     }
+    static inline uint32_t pop64(const uint32_t *p) { return (uint32_t)(__builtin_popcount(p[0]) + __builtin_popcount(p[1])); }
     uint64_t finish() {
         uint64_t acc = 0;
         for (uint64_t b = 0; b < nblk; b++) {
-            w[b * 8] = (uint32_t)acc;
-            for (int k = 1; k < 8; k++) acc += (uint64_t)__builtin_popcount(w[b * 8 + k]);
+            uint32_t *blk = &w[b * 8];
+            uint32_t p0 = pop64(blk + 2), p1 = pop64(blk + 4), p2 = pop64(blk + 6);
+            blk[0] = (uint32_t)acc;
+            blk[1] = (p0 << 8) | ((p0 + p1) << 16);
+            acc += p0 + p1 + p2;
         }
         return acc;
     }
     uint64_t rank1(uint64_t pos) const {
         uint64_t b = pos / FMX_RB_BITS;
         uint32_t r = (uint32_t)(pos - b * FMX_RB_BITS);
-        uint64_t c = w[b * 8];
-        for (uint32_t k = 0; k < 7; k++) {
-            if (r >= 32 * (k + 1)) c += (uint64_t)__builtin_popcount(w[b * 8 + 1 + k]);
-            else if (r > 32 * k) c += (uint64_t)__builtin_popcount(w[b * 8 + 1 + k] & ((1u << (r - 32 * k)) - 1u));
-        }
+        const uint32_t *blk = &w[b * 8];
+        uint32_t j = r >> 6, x = r & 63;
+        uint64_t word = (uint64_t)blk[2 + 2 * j] | ((uint64_t)blk[3 + 2 * j] << 32);
+        uint64_t c = (uint64_t)blk[0] + ((blk[1] >> (8 * j)) & 0xFF);
+        if (x) c += (uint64_t)__builtin_popcountll(word & ((1ull << x) - 1));
         return c;
     }
     uint64_t bytes() const { return w.size() * 4; }
@@ -130,6 +135,40 @@ static void build_wavelet(const uint8_t *seq, uint64_t n, uint32_t L, WMat &m) {
             cur.swap(nxt);
         }
     }
+}
+
+// One quaternary level (fmx_layout.h): cnt[4] + 64 two-bit codes per 32-byte block.
+struct Q4Vec {
+    std::vector<uint32_t> w;
+    std::vector<uint32_t> exc;
+    void build(const uint8_t *seq, uint64_t n) {
+        uint64_t nblk = n / 64 + 1;
+        w.assign(nblk * 8, 0);
+        exc.clear();
+        uint32_t cnt[4] = {0, 0, 0, 0};
+        for (uint64_t b = 0; b < nblk; b++) {
+            uint32_t *blk = &w[b * 8];
+            for (int c = 0; c < 4; c++) blk[c] = cnt[c];
+            uint64_t lo = b * 64, hi = lo + 64 < n ? lo + 64 : n;
+            for (uint64_t i = lo; i < hi; i++) {
+                uint32_t sym = seq[i];
+                if (sym == 0) exc.push_back((uint32_t)i);
+                uint32_t code = sym ? sym - 1 : 0;
+                uint32_t t = (uint32_t)(i - lo);
+                blk[4 + (t >> 4)] |= code << (2 * (t & 15));
+                cnt[code]++;
+            }
+        }
+    }
+};
+
+static bool want_q4(uint64_t mc, const uint8_t *seq, uint64_t n) {
+    const char *force = std::getenv("FMX_FORCE_WAVELET");
+    if (force && force[0] && force[0] != '0') return false;
+    if (mc > 4) return false;
+    uint64_t zeros = 0;
+    for (uint64_t i = 0; i < n; i++) zeros += seq[i] == 0;
+    return zeros <= FMX_MAX_EXC;
 }
 
 struct SectionData {
@@ -183,6 +222,8 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
     hdr.cs_len = cs_len;
 
     WMat wm;
+    Q4Vec q4;
+    bool use_q4 = false;
     std::vector<uint32_t> cs(cs_len + 1, 0), adj(cs_len, 0);
     std::vector<uint32_t> doc, piece_end, bsel, bpsel;
     RBVec rb_b(0), rb_bp(0);
@@ -196,7 +237,9 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
             sum += occ[c];
         }
         cs[cs_len] = (uint32_t)n;
-        build_wavelet(bwt.data(), n, L, wm);
+        use_q4 = want_q4(mc, bwt.data(), n);
+        if (use_q4) q4.build(bwt.data(), n);
+        else build_wavelet(bwt.data(), n, L, wm);
         hdr.seq_len = n;
         if (kind == FMX_KIND_MULTI) {
             // multi_pieces.rs:53-79
@@ -241,7 +284,9 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
         uint64_t r = heads.size();
         hdr.runs = r;
         hdr.seq_len = r;
-        build_wavelet(heads.data(), r, L, wm);
+        use_q4 = want_q4(mc, heads.data(), r);
+        if (use_q4) q4.build(heads.data(), r);
+        else build_wavelet(heads.data(), r, L, wm);
         bsel.assign(r + 1, (uint32_t)n);
         for (uint64_t j = 0; j < r; j++) bsel[j] = starts[j];
         // cs over run heads; bp groups runs by head character, stably
@@ -269,8 +314,14 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
         }
         rb_bp.finish();
     }
-    for (uint32_t l = 0; l < L; l++) hdr.zeros[l] = wm.zeros[l];
-    for (uint32_t c = 0; c < cs_len; c++) adj[c] = cs[c] - (uint32_t)wm.walk(0, c);
+    if (use_q4) {
+        hdr.layout = FMX_LAYOUT_QUAT;
+        hdr.nexc = (uint32_t)q4.exc.size();
+    } else {
+        hdr.layout = FMX_LAYOUT_WAVELET;
+        for (uint32_t l = 0; l < L; l++) hdr.zeros[l] = wm.zeros[l];
+        for (uint32_t c = 0; c < cs_len; c++) adj[c] = cs[c] - (uint32_t)wm.walk(0, c);
+    }
 
     // sample.rs:21-44
     std::vector<uint32_t> samples;
@@ -291,7 +342,12 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
 
     // ---- assemble
     SectionData sec[SEC_COUNT];
-    for (uint32_t l = 0; l < L; l++) sec[SEC_LEVEL0 + l] = {wm.lv[l].w.data(), wm.lv[l].bytes()};
+    if (use_q4) {
+        sec[SEC_LEVEL0] = {q4.w.data(), q4.w.size() * 4};
+        if (!q4.exc.empty()) sec[SEC_EXC] = {q4.exc.data(), q4.exc.size() * 4};
+    } else {
+        for (uint32_t l = 0; l < L; l++) sec[SEC_LEVEL0 + l] = {wm.lv[l].w.data(), wm.lv[l].bytes()};
+    }
     sec[SEC_ADJ] = {adj.data(), adj.size() * 4};
     sec[SEC_CS] = {cs.data(), cs.size() * 4};
     if (!samples.empty()) sec[SEC_SA] = {samples.data(), samples.size() * 4};
@@ -327,7 +383,8 @@ int check_blob(const void *blob, uint64_t bytes, FmxBlobHeader &hdr, std::string
         err = "not an fmx blob (bad magic or version)";
         return FMX_ERR_INVALID_ARG;
     }
-    if (hdr.total_bytes != bytes || hdr.levels == 0 || hdr.levels > FMX_MAX_LEVELS || hdr.kind > 2) {
+    if (hdr.total_bytes != bytes || hdr.levels == 0 || hdr.levels > FMX_MAX_LEVELS || hdr.kind > 2 || hdr.layout > 1 ||
+        hdr.nexc > FMX_MAX_EXC) {
         err = "corrupt fmx blob header";
         return FMX_ERR_INVALID_ARG;
     }

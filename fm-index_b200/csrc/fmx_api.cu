@@ -6,6 +6,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/fmx.h"
@@ -61,7 +62,7 @@ struct DevBuf {
     T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-enum { B_PAT, B_OFF, B_S, B_E, B_INS, B_INE, B_CNT, B_HOFF, B_OWNER, B_ROWS, B_ROWS2, B_FLAG, B_FPOS, B_TILES, B_POS, B_PID,
+enum { B_QUEUE, B_PAT, B_OFF, B_S, B_E, B_INS, B_INE, B_CNT, B_HOFF, B_OWNER, B_ROWS, B_ROWS2, B_FLAG, B_FPOS, B_TILES, B_POS, B_PID,
        B_OUT8, B_OUT32, B_COUNT };
 
 struct fmx_index {
@@ -73,14 +74,39 @@ struct fmx_index {
     cudaStream_t stream = nullptr;
     uint32_t *d_err = nullptr;             // [0] pattern-char error flag
     unsigned long long *d_work = nullptr;  // [0] search iterations, [1] LF steps
+    uint2 *d_kmer_tab = nullptr;           // memoised first kmer_k search iterations (see SearchArgs)
+    uint8_t *d_kmer_steps = nullptr;
+    uint32_t kmer_k = 0;
+    uint64_t kmer_entries = 0;
+    int sms = 148;
+    int persist_blocks_per_sm = 4;
+    // tuning knobs (fmx_index_set_option)
+    int opt_persistent = 0;  // 1: persistent refill search kernels instead of one pattern per thread
+    int opt_kmer = 1;
     mutable DevBuf buf[B_COUNT];
     mutable std::mutex mu;
 };
+
+static int build_kmer_table(fmx_index *idx);
 
 static inline cudaStream_t pick_stream(const fmx_index *idx, void *stream) {
     return stream ? reinterpret_cast<cudaStream_t>(stream) : idx->stream;
 }
 static inline unsigned grid_for(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// run f(K, LY) with the index's (kind, layout) as compile-time constants
+template <class F>
+static void dispatch(const fmx_index *idx, F &&f) {
+    using std::integral_constant;
+    switch (idx->hdr.kind * 2 + idx->hdr.layout) {
+        case 0: f(integral_constant<int, 0>{}, integral_constant<int, 0>{}); break;
+        case 1: f(integral_constant<int, 0>{}, integral_constant<int, 1>{}); break;
+        case 2: f(integral_constant<int, 1>{}, integral_constant<int, 0>{}); break;
+        case 3: f(integral_constant<int, 1>{}, integral_constant<int, 1>{}); break;
+        case 4: f(integral_constant<int, 2>{}, integral_constant<int, 0>{}); break;
+        default: f(integral_constant<int, 2>{}, integral_constant<int, 1>{}); break;
+    }
+}
 
 extern "C" {
 
@@ -169,6 +195,9 @@ static int upload(std::vector<uint8_t> &&blob, int device, fmx_index **out) {
     d.rl_bp = static_cast<const uint4 *>(sec(SEC_RL_BP));
     d.rl_bsel = static_cast<const uint32_t *>(sec(SEC_RL_BSEL));
     d.rl_bpsel = static_cast<const uint32_t *>(sec(SEC_RL_BPSEL));
+    d.exc = static_cast<const uint32_t *>(sec(SEC_EXC));
+    d.layout = hdr.layout;
+    d.nexc = hdr.nexc;
     d.n = (uint32_t)hdr.n;
     d.seq_len = (uint32_t)hdr.seq_len;
     d.levels = hdr.levels;
@@ -181,6 +210,16 @@ static int upload(std::vector<uint8_t> &&blob, int device, fmx_index **out) {
     d.first_row = (uint32_t)hdr.first_row;
     d.runs = (uint32_t)hdr.runs;
     idx->host_blob = std::move(blob);
+    cudaDeviceGetAttribute(&idx->sms, cudaDevAttrMultiProcessorCount, device);
+    dispatch(idx, [&](auto K, auto LY) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&idx->persist_blocks_per_sm, k_search_steps<K(), LY()>, 256, 0);
+    });
+    if (idx->persist_blocks_per_sm < 1) idx->persist_blocks_per_sm = 1;
+    rc = build_kmer_table(idx);
+    if (rc) {
+        fmx_index_free(idx);
+        return rc;
+    }
     *out = idx;
     return FMX_OK;
 }
@@ -231,12 +270,26 @@ void fmx_index_free(fmx_index *idx) {
     for (auto &b : idx->buf) b.release();
     if (idx->d_blob) cudaFree(idx->d_blob);
     if (idx->d_err) cudaFree(idx->d_err);
+    if (idx->d_kmer_tab) cudaFree(idx->d_kmer_tab);
+    if (idx->d_kmer_steps) cudaFree(idx->d_kmer_steps);
     if (idx->stream) cudaStreamDestroy(idx->stream);
     delete idx;
 }
 
+int fmx_index_set_option(fmx_index *idx, const char *key, int64_t value) {
+    if (!idx || !key) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    std::string k(key);
+    if (k == "search_persistent") idx->opt_persistent = value != 0;
+    else if (k == "kmer") idx->opt_kmer = value != 0;
+    else if (k == "persist_blocks_per_sm") {
+        if (value < 1 || value > 32) return fail(FMX_ERR_INVALID_ARG, "persist_blocks_per_sm out of range");
+        idx->persist_blocks_per_sm = (int)value;
+    } else return fail(FMX_ERR_INVALID_ARG, "unknown option: " + k);
+    return FMX_OK;
+}
+
 uint64_t fmx_index_len(const fmx_index *idx) { return idx ? idx->hdr.n : 0; }
-uint64_t fmx_index_device_bytes(const fmx_index *idx) { return idx ? idx->hdr.total_bytes : 0; }
+uint64_t fmx_index_device_bytes(const fmx_index *idx) { return idx ? idx->hdr.total_bytes + idx->kmer_entries * 9 : 0; }
 uint64_t fmx_index_pieces_count(const fmx_index *idx) { return idx ? idx->hdr.ndoc : 0; }
 int fmx_index_kind(const fmx_index *idx) { return idx ? (int)idx->hdr.kind : -1; }
 int fmx_index_has_locate(const fmx_index *idx) { return idx ? (int)idx->hdr.has_locate : 0; }
@@ -298,16 +351,88 @@ static int device_scan(const Tin *in, uint64_t n, Tout *out, Op op, bool write_t
 
 // ------------------------------------------------------------------ search
 
-template <int KIND>
-static int launch_search(const fmx_index *idx, const SearchArgs &a, cudaStream_t st) {
+static bool env_flag(const char *name) {
+    const char *v = std::getenv(name);
+    return v && v[0] && v[0] != '0';
+}
+
+static int dispatch_search(const fmx_index *idx, const SearchArgs &a, cudaStream_t st, bool force_simple = false) {
     if (a.npat == 0) return 0;
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, idx->device);
+    if (force_simple || !idx->opt_persistent) {
+        uint64_t blocks = (a.npat + 255) / 256;
+        uint64_t cap = (uint64_t)idx->sms * 8 * 8;  // grid-stride beyond 8 waves of 8 CTAs/SM
+        if (blocks > cap) blocks = cap;
+        dispatch(idx, [&](auto K, auto LY) { k_search<K(), LY()><<<(unsigned)blocks, 256, 0, st>>>(idx->dev, a); });
+        LAUNCH_CHECK();
+        return 0;
+    }
+    if (a.npat >= 0xFFFFFFFFull) return fail(FMX_ERR_UNSUPPORTED, "at most 2^32 - 2 patterns per search call");
+    int rc = idx->buf[B_QUEUE].ensure(a.npat * 16);
+    if (rc) return rc;
+    SearchArgs b = a;
+    b.queue = idx->buf[B_QUEUE].as<uint4>();
+    b.qcount = idx->d_work + 4;
+    b.qcursor = idx->d_work + 5;
+    CUDA_TRY(cudaMemsetAsync(b.qcount, 0, 2 * sizeof(unsigned long long), st));
+    // phase A: one pattern per thread
     uint64_t blocks = (a.npat + 255) / 256;
-    uint64_t cap = (uint64_t)sms * 8 * 8;  // grid-stride beyond 8 waves of 8 CTAs/SM
+    uint64_t cap = (uint64_t)idx->sms * 8 * 4;
     if (blocks > cap) blocks = cap;
-    k_search<KIND><<<(unsigned)blocks, 256, 0, st>>>(idx->dev, a);
+    dispatch(idx, [&](auto K, auto LY) { k_search_init<K(), LY()><<<(unsigned)blocks, 256, 0, st>>>(idx->dev, b); });
     LAUNCH_CHECK();
+    // phase B: persistent, one resident wave of CTAs (a multiple of the SM count) drains the queue
+    uint64_t pblocks = (uint64_t)idx->sms * idx->persist_blocks_per_sm;
+    uint64_t need = (a.npat + 255) / 256;
+    if (pblocks > need) pblocks = need;
+    dispatch(idx, [&](auto K, auto LY) { k_search_steps<K(), LY()><<<(unsigned)pblocks, 256, 0, st>>>(idx->dev, b); });
+    LAUNCH_CHECK();
+    return 0;
+}
+
+// Memoise the first k iterations of every fresh search: run the search kernel itself over all
+// sigma^k k-mers once, at index upload (sigma = max_character + 1).
+static int build_kmer_table(fmx_index *idx) {
+    if (env_flag("FMX_NO_KMER")) return 0;
+    const uint64_t sigma = idx->hdr.cs_len;
+    const uint64_t budget = idx->hdr.n >= (1ull << 22) ? (1ull << 21) : (1ull << 12);
+    uint32_t k = 0;
+    uint64_t entries = 1;
+    while (entries * sigma <= budget && k < 16) {
+        entries *= sigma;
+        k++;
+    }
+    if (k < 2 || idx->hdr.n < 2) return 0;
+    cudaStream_t st = idx->stream;
+    uint8_t *d_pat = nullptr;
+    uint64_t *d_s = nullptr, *d_e = nullptr;
+    CUDA_TRY(cudaMalloc(&d_pat, entries * k));
+    CUDA_TRY(cudaMalloc(&d_s, entries * 8));
+    CUDA_TRY(cudaMalloc(&d_e, entries * 8));
+    CUDA_TRY(cudaMalloc(&idx->d_kmer_tab, entries * sizeof(uint2)));
+    CUDA_TRY(cudaMalloc(&idx->d_kmer_steps, entries));
+    k_kmer_patterns<<<grid_for(entries, 256), 256, 0, st>>>(k, (uint32_t)sigma, entries, d_pat);
+    LAUNCH_CHECK();
+    SearchArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.pat = d_pat;
+    a.fixed_len = k;
+    a.npat = entries;
+    a.s0 = 0;
+    a.e0 = (uint32_t)idx->hdr.n;
+    a.out_s = d_s;
+    a.out_e = d_e;
+    a.err = idx->d_err;
+    a.steps_out = idx->d_kmer_steps;
+    int rc = dispatch_search(idx, a, st, true);
+    if (rc) return rc;
+    k_kmer_pack<<<grid_for(entries, 256), 256, 0, st>>>(d_s, d_e, entries, idx->d_kmer_tab);
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaStreamSynchronize(st));
+    cudaFree(d_pat);
+    cudaFree(d_s);
+    cudaFree(d_e);
+    idx->kmer_k = k;
+    idx->kmer_entries = entries;
     return 0;
 }
 
@@ -319,6 +444,7 @@ static int search_device(const fmx_index *idx, int mode, const uint8_t *d_pat, c
         return fail(FMX_ERR_UNSUPPORTED, "search_prefix/suffix/exact need a MultiPieces index (frontend.rs:369-390)");
     if ((d_is == nullptr) != (d_ie == nullptr)) return fail(FMX_ERR_INVALID_ARG, "init_s and init_e must both be given");
     SearchArgs a;
+    std::memset(&a, 0, sizeof(a));
     a.pat = d_pat;
     a.pat_off = d_pat_off;
     a.fixed_len = fixed_len;
@@ -331,12 +457,14 @@ static int search_device(const fmx_index *idx, int mode, const uint8_t *d_pat, c
     a.out_e = d_oe;
     a.err = idx->d_err;
     a.work = idx->d_work;
+    a.steps_out = nullptr;
+    // the table memoises searches that start from (0, n): fresh search / search_prefix
+    const bool tab_ok = idx->d_kmer_tab && idx->opt_kmer && !d_is && (mode == FMX_SEARCH || mode == FMX_SEARCH_PREFIX);
+    a.kmer_tab = tab_ok ? idx->d_kmer_tab : nullptr;
+    a.kmer_steps = tab_ok ? idx->d_kmer_steps : nullptr;
+    a.kmer_k = tab_ok ? idx->kmer_k : 0;
     CUDA_TRY(cudaMemsetAsync(idx->d_work, 0, sizeof(unsigned long long), st));
-    switch (idx->hdr.kind) {
-        case FMX_KIND_FM: return launch_search<FMX_KIND_FM_>(idx, a, st);
-        case FMX_KIND_RLFM: return launch_search<FMX_KIND_RLFM_>(idx, a, st);
-        default: return launch_search<FMX_KIND_MULTI_>(idx, a, st);
-    }
+    return dispatch_search(idx, a, st);
 }
 
 static int check_err_flag(const fmx_index *idx, cudaStream_t st) {
@@ -459,11 +587,7 @@ static int locate_prepare(const fmx_index *idx, int prefix_only, const uint64_t 
     if ((rc = idx->buf[B_FPOS].ensure((total + 1) * 8))) return rc;
     uint32_t *d_flag = idx->buf[B_FLAG].as<uint32_t>();
     uint64_t *d_fpos = idx->buf[B_FPOS].as<uint64_t>();
-    switch (idx->hdr.kind) {
-        case FMX_KIND_FM: k_flag_prefix<FMX_KIND_FM_><<<grid_for(total, 256), 256, 0, st>>>(idx->dev, d_rows, total, d_flag); break;
-        case FMX_KIND_RLFM: k_flag_prefix<FMX_KIND_RLFM_><<<grid_for(total, 256), 256, 0, st>>>(idx->dev, d_rows, total, d_flag); break;
-        default: k_flag_prefix<FMX_KIND_MULTI_><<<grid_for(total, 256), 256, 0, st>>>(idx->dev, d_rows, total, d_flag); break;
-    }
+    dispatch(idx, [&](auto K, auto LY) { k_flag_prefix<K(), LY()><<<grid_for(total, 256), 256, 0, st>>>(idx->dev, d_rows, total, d_flag); });
     LAUNCH_CHECK();
     if ((rc = device_scan<uint32_t, uint64_t, OpSum, true>(d_flag, total, d_fpos, OpSum(), true, idx->buf[B_TILES], st))) return rc;
     uint64_t kept = 0;
@@ -496,11 +620,7 @@ static int locate_fill(const fmx_index *idx, const uint32_t *d_rows, uint64_t to
     uint64_t blocks = (total + 255) / 256;
     uint64_t cap = (uint64_t)sms * 8 * 8;
     if (blocks > cap) blocks = cap;
-    switch (idx->hdr.kind) {
-        case FMX_KIND_FM: k_locate<FMX_KIND_FM_><<<(unsigned)blocks, 256, 0, st>>>(idx->dev, a); break;
-        case FMX_KIND_RLFM: k_locate<FMX_KIND_RLFM_><<<(unsigned)blocks, 256, 0, st>>>(idx->dev, a); break;
-        default: k_locate<FMX_KIND_MULTI_><<<(unsigned)blocks, 256, 0, st>>>(idx->dev, a); break;
-    }
+    dispatch(idx, [&](auto K, auto LY) { k_locate<K(), LY()><<<(unsigned)blocks, 256, 0, st>>>(idx->dev, a); });
     LAUNCH_CHECK();
     return 0;
 }
@@ -601,11 +721,7 @@ static int extract_device(const fmx_index *idx, const uint64_t *d_rows, uint64_t
                           uint8_t *d_out, uint32_t *d_len, cudaStream_t st) {
     if (nrows == 0 || k == 0) return 0;
     unsigned g = grid_for(nrows, 256);
-    switch (idx->hdr.kind) {
-        case FMX_KIND_FM: k_extract<FMX_KIND_FM_><<<g, 256, 0, st>>>(idx->dev, d_rows, nrows, k, forward, d_out, d_len); break;
-        case FMX_KIND_RLFM: k_extract<FMX_KIND_RLFM_><<<g, 256, 0, st>>>(idx->dev, d_rows, nrows, k, forward, d_out, d_len); break;
-        default: k_extract<FMX_KIND_MULTI_><<<g, 256, 0, st>>>(idx->dev, d_rows, nrows, k, forward, d_out, d_len); break;
-    }
+    dispatch(idx, [&](auto K, auto LY) { k_extract<K(), LY()><<<g, 256, 0, st>>>(idx->dev, d_rows, nrows, k, forward, d_out, d_len); });
     LAUNCH_CHECK();
     return 0;
 }
@@ -661,11 +777,7 @@ extern "C" int fmx_rows_op(const fmx_index *idx, int op, const uint64_t *rows, u
     unsigned g = grid_for(nrows, 256);
     const uint64_t *d_rows = idx->buf[B_S].as<uint64_t>();
     uint64_t *d_out = idx->buf[B_E].as<uint64_t>();
-    switch (idx->hdr.kind) {
-        case FMX_KIND_FM: k_rows_op<FMX_KIND_FM_><<<g, 256, 0, st>>>(idx->dev, op, d_rows, nrows, d_out); break;
-        case FMX_KIND_RLFM: k_rows_op<FMX_KIND_RLFM_><<<g, 256, 0, st>>>(idx->dev, op, d_rows, nrows, d_out); break;
-        default: k_rows_op<FMX_KIND_MULTI_><<<g, 256, 0, st>>>(idx->dev, op, d_rows, nrows, d_out); break;
-    }
+    dispatch(idx, [&](auto K, auto LY) { k_rows_op<K(), LY()><<<g, 256, 0, st>>>(idx->dev, op, d_rows, nrows, d_out); });
     LAUNCH_CHECK();
     CUDA_TRY(cudaMemcpyAsync(out, d_out, nrows * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -692,11 +804,7 @@ extern "C" int fmx_lf_map2_batch(const fmx_index *idx, const uint8_t *c, const u
     const uint8_t *d_c = idx->buf[B_PAT].as<uint8_t>();
     const uint64_t *d_i = idx->buf[B_S].as<uint64_t>();
     uint64_t *d_out = idx->buf[B_E].as<uint64_t>();
-    switch (idx->hdr.kind) {
-        case FMX_KIND_FM: k_lf_map2<FMX_KIND_FM_><<<g, 256, 0, st>>>(idx->dev, d_c, d_i, nrows, d_out); break;
-        case FMX_KIND_RLFM: k_lf_map2<FMX_KIND_RLFM_><<<g, 256, 0, st>>>(idx->dev, d_c, d_i, nrows, d_out); break;
-        default: k_lf_map2<FMX_KIND_MULTI_><<<g, 256, 0, st>>>(idx->dev, d_c, d_i, nrows, d_out); break;
-    }
+    dispatch(idx, [&](auto K, auto LY) { k_lf_map2<K(), LY()><<<g, 256, 0, st>>>(idx->dev, d_c, d_i, nrows, d_out); });
     LAUNCH_CHECK();
     CUDA_TRY(cudaMemcpyAsync(out, d_out, nrows * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));

@@ -2,43 +2,63 @@
 //
 // One contiguous allocation in HBM: BlobHeader followed by 256-byte aligned sections.
 //
-// RANK BLOCKS ("RB32").  Every rank-able bit vector (each wavelet-matrix level, and the
+// RANK BLOCKS ("RB192").  Every rank-able bit vector (each wavelet-matrix level, and the
 // RLFM run-start vectors b / bp) is an array of 32-byte blocks
 //       word 0    : u32  number of 1-bits in all preceding blocks of this vector
-//       word 1..7 : 224 payload bits, LSB first
-// so rank1(pos) -- and the bit at pos, for access -- costs exactly ONE 32-byte HBM
-// sector plus an in-register popcount.  The reference's dependency (vers-vecs RsVec)
-// keeps bits, 512-bit block counts and 8192-bit super-block counts in three separate
-// arrays, i.e. up to three cache lines per rank.  u32 counts bound the text length to
-// n < 2^32 (every BASELINE config; the largest is 3*10^9).
+//       word 1    : byte 1 = popcount(P0), byte 2 = popcount(P0) + popcount(P1)  (bytes 0, 3 = 0)
+//       word 2..7 : three 64-bit payload words P0, P1, P2 (192 payload bits, LSB first)
+// so rank1(pos) -- and the bit at pos, for access -- costs exactly ONE 32-byte HBM sector
+// (one 256-bit load) plus ONE masked 64-bit popcount: the in-block sub-counts replace the
+// up-to-seven masked popcounts a flat payload needs (the first kernels were ALU-bound on
+// exactly that when the index fits L2).  The reference's dependency (vers-vecs RsVec) keeps
+// bits, 512-bit block counts and 8192-bit super-block counts in three separate arrays, i.e.
+// up to three cache lines per rank.  u32 counts bound the text length to n < 2^32 (every
+// BASELINE config; the largest is 3*10^9).
 //
 // WAVELET MATRIX.  L = Text::max_bits() levels (text.rs:61-63), level 0 = most significant
 // bit, zeros stably partitioned before ones -- the structure of vers' WaveletMatrix, which
 // the reference stores its BWT in (fm_index.rs:44-58).  rank(i, c) walks ONE position down
 // the levels (the walk of position 0 is a per-symbol constant, folded into `adj`):
 //       lf_map2(c, i) = adj[c] + walk_c(i),   adj[c] = cs[c] - walk_c(0)      (mod 2^32)
+//
+// QUATERNARY LEVEL ("Q4").  When max_character <= 4 (DNA coded 0..4: every DNA config of
+// BASELINE.json) and the sequence holds at most FMX_MAX_EXC zeros, the L = 3 binary levels
+// collapse into ONE level of arity 4: 32-byte blocks
+//       word 0..3 : u32 occurrences of the 2-bit codes 0..3 in all preceding blocks
+//       word 4..7 : 64 two-bit codes (code = symbol - 1)
+// so lf_map2(c, i) = cs[c] + rank(i, c) costs ONE sector instead of three.  The rare symbol 0
+// (the \0 terminators: 1 for a single text, one per piece for MultiPieces) is stored as code 0
+// and its positions are listed in SEC_EXC (sorted; staged in shared memory), which corrects
+// rank(., 1) and answers rank(., 0) / access exactly.  Results are identical to the wavelet
+// matrix; only the number of sectors per probe changes (profiles/: search is bound by the
+// count of lane-sector requests in L1TEX when the index fits L2 and by the random-sector rate
+// of HBM when it does not -- both scale with probes per step).
 #pragma once
 #include <stdint.h>
 #include <vector_types.h>  // uint4 (CUDA toolkit header, host-safe)
 
 #define FMX_BLOB_MAGIC 0x3030324258584d46ull /* "FMXXB200" little endian-ish tag */
-#define FMX_BLOB_VERSION 1u
+#define FMX_BLOB_VERSION 3u
 #define FMX_MAX_LEVELS 8
-#define FMX_RB_BITS 224u
+#define FMX_RB_BITS 192u
+#define FMX_MAX_EXC 1024u   /* Q4 layout: at most this many \0 symbols in the sequence */
+#define FMX_LAYOUT_WAVELET 0u
+#define FMX_LAYOUT_QUAT 1u
 #define FMX_SECTION_ALIGN 256u
 
 enum FmxSection : uint32_t {
-    SEC_LEVEL0 = 0,  // .. SEC_LEVEL0 + 7 : wavelet levels (RB32)
+    SEC_LEVEL0 = 0,  // .. SEC_LEVEL0 + 7 : wavelet levels (RB192); Q4 layout: SEC_LEVEL0 = the Q4 blocks
     SEC_ADJ = 8,     // u32[cs_len]   adj[c] = cs[c] - walk_c(0)
     SEC_CS = 9,      // u32[cs_len+1] cs[c] (sais.rs:21-32), cs[cs_len] = n (FM/MULTI) or runs (RLFM)
     SEC_SA = 10,     // u32[((n-1)>>level)+1]  sampled suffix array, sa[i << level]  (sample.rs:33-37)
     SEC_DOC = 11,    // u32[ndoc]     multi_pieces.rs:53-79
     SEC_PIECE_END = 12,  // u32[ndoc]  text position of the k-th \0 (piece k is [end[k-1]+1, end[k]])
-    SEC_RL_B = 13,   // RB32 over n bits: run starts in L order  (rlfmi.rs:40-67)
-    SEC_RL_BP = 14,  // RB32 over n bits: run starts in F order  (rlfmi.rs:70-83)
+    SEC_RL_B = 13,   // RB192 over n bits: run starts in L order  (rlfmi.rs:40-67)
+    SEC_RL_BP = 14,  // RB192 over n bits: run starts in F order  (rlfmi.rs:70-83)
     SEC_RL_BSEL = 15,   // u32[runs+1]  select1(b, j), [runs] = n
     SEC_RL_BPSEL = 16,  // u32[runs+1]  select1(bp, j), [runs] = n
-    SEC_COUNT = 17
+    SEC_EXC = 17,       // u32[nexc]  Q4 layout: sorted positions whose symbol is 0
+    SEC_COUNT = 18
 };
 
 struct FmxSectionEntry {
@@ -65,7 +85,9 @@ struct FmxBlobHeader {
     uint64_t zeros[FMX_MAX_LEVELS];  // zeros per level
     uint64_t total_bytes;
     FmxSectionEntry sec[SEC_COUNT];
-    uint64_t reserved[8];
+    uint32_t layout;  // FMX_LAYOUT_WAVELET | FMX_LAYOUT_QUAT
+    uint32_t nexc;    // Q4: number of zeros in the sequence
+    uint64_t reserved[7];
 };
 
 // What the kernels see (passed by value as a __grid_constant__ parameter).
@@ -81,6 +103,7 @@ struct FmxDev {
     const uint4 *rl_bp;
     const uint32_t *rl_bsel;
     const uint32_t *rl_bpsel;
+    const uint32_t *exc;
     uint32_t n;
     uint32_t seq_len;
     uint32_t levels;
@@ -92,5 +115,7 @@ struct FmxDev {
     uint32_t ndoc;
     uint32_t first_row;
     uint32_t runs;
+    uint32_t layout;
+    uint32_t nexc;
     uint32_t pad;
 };

@@ -1,7 +1,7 @@
 // kernels.cuh -- hand-written sm_100a kernels for the FM-index query path.
 //
 // Everything here is HBM-latency / sector-rate bound integer work: no tensor cores.
-// One rank probe = one 32-byte sector (one 256-bit LDG) + an in-register popcount.
+// One rank probe = one 32-byte sector (one 256-bit LDG) + one masked 64-bit popcount.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -18,7 +18,7 @@ namespace fmx {
 // ------------------------------------------------------------------ rank blocks
 
 struct RB {
-    uint32_t w[8];  // w[0] = ones before the block, w[1..7] = 224 payload bits
+    uint32_t w[8];  // w[0] = ones before the block, w[1] = in-block sub-counts, w[2..7] = 3 x 64 payload bits
 };
 
 // one 32-byte sector, one instruction (sm_100: LDG.E.256), read-only path
@@ -26,29 +26,9 @@ __device__ __forceinline__ RB rb_load(const uint4 *__restrict__ v, uint32_t blk)
     RB b;
     const uint4 *p = v + 2ull * blk;
     asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(b.w[0]), "=r"(b.w[1]), "=r"(b.w[2]), "=r"(b.w[3]), "=r"(b.w[4]), "=r"(b.w[5]),
-                   "=r"(b.w[6]), "=r"(b.w[7])
-                 : "l"(p));
+        : "=r"(b.w[0]), "=r"(b.w[1]), "=r"(b.w[2]), "=r"(b.w[3]), "=r"(b.w[4]), "=r"(b.w[5]), "=r"(b.w[6]), "=r"(b.w[7])
+        : "l"(p));
     return b;
-}
-
-// ones in [0, blk*224 + r), r in [0, 224)
-__device__ __forceinline__ uint32_t rb_rank(const RB &b, uint32_t r) {
-    uint32_t full = r >> 5, rem = r & 31u, c = b.w[0];
-    uint32_t part = (1u << rem) - 1u;
-#pragma unroll
-    for (uint32_t k = 0; k < 7; k++) {
-        uint32_t m = k < full ? 0xFFFFFFFFu : (k == full ? part : 0u);
-        c += __popc(b.w[k + 1] & m);
-    }
-    return c;
-}
-
-__device__ __forceinline__ uint32_t rb_bit(const RB &b, uint32_t r) {
-    uint32_t full = r >> 5, word = b.w[1];
-#pragma unroll
-    for (uint32_t k = 1; k < 7; k++) word = (full == k) ? b.w[k + 1] : word;
-    return (word >> (r & 31u)) & 1u;
 }
 
 __device__ __forceinline__ void rb_split(uint32_t pos, uint32_t &blk, uint32_t &r) {
@@ -56,7 +36,41 @@ __device__ __forceinline__ void rb_split(uint32_t pos, uint32_t &blk, uint32_t &
     r = pos - blk * FMX_RB_BITS;
 }
 
-// rank1 of a stand-alone RB32 vector
+// the 64-bit payload word holding in-block bit r
+__device__ __forceinline__ void rb_word(const RB &b, uint32_t r, uint32_t &lo, uint32_t &hi) {
+    uint32_t j = r >> 6;
+    lo = j == 0 ? b.w[2] : (j == 1 ? b.w[4] : b.w[6]);
+    hi = j == 0 ? b.w[3] : (j == 1 ? b.w[5] : b.w[7]);
+}
+
+// ones in [0, blk*192 + r), r in [0, 192): block count + stored sub-count + one masked 64-bit popcount
+__device__ __forceinline__ uint32_t rb_rank(const RB &b, uint32_t r) {
+    uint32_t lo, hi;
+    rb_word(b, r, lo, hi);
+    uint32_t sub = __byte_perm(b.w[1], 0, 0x4440u | (r >> 6));
+    uint64_t keep = ~(~0ull << (r & 63u));  // low (r mod 64) bits
+    return b.w[0] + sub + __popc(lo & (uint32_t)keep) + __popc(hi & (uint32_t)(keep >> 32));
+}
+
+__device__ __forceinline__ uint32_t rb_bit(const RB &b, uint32_t r) {
+    uint32_t lo, hi;
+    rb_word(b, r, lo, hi);
+    uint32_t x = r & 63u;
+    return ((x & 32u ? hi : lo) >> (x & 31u)) & 1u;
+}
+
+// rank and bit together (access + rank share the selected word)
+__device__ __forceinline__ uint32_t rb_rank_bit(const RB &b, uint32_t r, uint32_t &bit) {
+    uint32_t lo, hi;
+    rb_word(b, r, lo, hi);
+    uint32_t x = r & 63u;
+    uint32_t sub = __byte_perm(b.w[1], 0, 0x4440u | (r >> 6));
+    uint64_t keep = ~(~0ull << x);
+    bit = ((x & 32u ? hi : lo) >> (x & 31u)) & 1u;
+    return b.w[0] + sub + __popc(lo & (uint32_t)keep) + __popc(hi & (uint32_t)(keep >> 32));
+}
+
+// rank1 of a stand-alone RB192 vector
 __device__ __forceinline__ uint32_t rbv_rank1(const uint4 *__restrict__ v, uint32_t pos) {
     uint32_t blk, r;
     rb_split(pos, blk, r);
@@ -64,7 +78,13 @@ __device__ __forceinline__ uint32_t rbv_rank1(const uint4 *__restrict__ v, uint3
     return rb_rank(b, r);
 }
 
-// select1: position of the k-th (0-based) one of an RB32 vector with nblk blocks.  k must exist.
+// position of the k-th (0-based) set bit of a 64-bit word given as (lo, hi)
+__device__ __forceinline__ uint32_t select_in_word64(uint32_t lo, uint32_t hi, uint32_t k) {
+    uint32_t c = __popc(lo);
+    return k < c ? __fns(lo, 0, k + 1) : 32u + __fns(hi, 0, k - c + 1);
+}
+
+// select1: position of the k-th (0-based) one of an RB192 vector with nblk blocks.  k must exist.
 __device__ __forceinline__ uint32_t rbv_select1(const uint4 *__restrict__ v, uint32_t nblk, uint32_t k) {
     const uint32_t *cw = reinterpret_cast<const uint32_t *>(v);
     uint32_t lo = 0, hi = nblk;  // last block with count <= k
@@ -73,15 +93,13 @@ __device__ __forceinline__ uint32_t rbv_select1(const uint4 *__restrict__ v, uin
         if (__ldg(cw + 8ull * mid) <= k) lo = mid; else hi = mid;
     }
     RB b = rb_load(v, lo);
-    uint32_t rem = k - b.w[0], pos = lo * FMX_RB_BITS;
-#pragma unroll
-    for (uint32_t j = 1; j < 8; j++) {
-        uint32_t c = __popc(b.w[j]);
-        if (rem < c) return pos + __fns(b.w[j], 0, rem + 1);
-        rem -= c;
-        pos += 32;
-    }
-    return pos;  // unreachable for valid k
+    uint32_t rem = k - b.w[0];
+    uint32_t s1 = (b.w[1] >> 8) & 0xFFu, s2 = (b.w[1] >> 16) & 0xFFu;
+    uint32_t j = rem >= s2 ? 2u : (rem >= s1 ? 1u : 0u);
+    rem -= j == 2 ? s2 : (j == 1 ? s1 : 0u);
+    uint32_t wl, wh;
+    rb_word(b, j << 6, wl, wh);
+    return lo * FMX_RB_BITS + (j << 6) + select_in_word64(wl, wh, rem);
 }
 __device__ __forceinline__ uint32_t rbv_select0(const uint4 *__restrict__ v, uint32_t nblk, uint32_t k) {
     const uint32_t *cw = reinterpret_cast<const uint32_t *>(v);
@@ -91,19 +109,37 @@ __device__ __forceinline__ uint32_t rbv_select0(const uint4 *__restrict__ v, uin
         if (mid * FMX_RB_BITS - __ldg(cw + 8ull * mid) <= k) lo = mid; else hi = mid;
     }
     RB b = rb_load(v, lo);
-    uint32_t rem = k - (lo * FMX_RB_BITS - b.w[0]), pos = lo * FMX_RB_BITS;
-#pragma unroll
-    for (uint32_t j = 1; j < 8; j++) {
-        uint32_t z = ~b.w[j];
-        uint32_t c = __popc(z);
-        if (rem < c) return pos + __fns(z, 0, rem + 1);
-        rem -= c;
-        pos += 32;
-    }
-    return pos;
+    uint32_t rem = k - (lo * FMX_RB_BITS - b.w[0]);
+    uint32_t z1 = 64u - ((b.w[1] >> 8) & 0xFFu), z2 = 128u - ((b.w[1] >> 16) & 0xFFu);
+    uint32_t j = rem >= z2 ? 2u : (rem >= z1 ? 1u : 0u);
+    rem -= j == 2 ? z2 : (j == 1 ? z1 : 0u);
+    uint32_t wl, wh;
+    rb_word(b, j << 6, wl, wh);
+    return lo * FMX_RB_BITS + (j << 6) + select_in_word64(~wl, ~wh, rem);
 }
 
-// ------------------------------------------------------------------ wavelet matrix
+// ------------------------------------------------------------------ shared-memory tables
+
+#define FMX_LAYOUT_WM 0  // binary wavelet matrix, L levels (any alphabet)
+#define FMX_LAYOUT_Q4 1  // one quaternary level (max_character <= 4, few \0): ONE sector per lf_map2
+
+template <int LAYOUT>
+struct Tabs {
+    uint32_t adj[256];  // WM: cs[c] - walk_c(0)
+    uint32_t cs[257];   // cs[c], cs[cs_len] = sequence length
+    uint32_t exc[LAYOUT == FMX_LAYOUT_Q4 ? FMX_MAX_EXC : 1];  // Q4: sorted positions whose symbol is 0
+};
+
+template <int LAYOUT>
+__device__ __forceinline__ void load_tables(const FmxDev &ix, Tabs<LAYOUT> &t) {
+    for (uint32_t k = threadIdx.x; k < ix.cs_len; k += blockDim.x) t.adj[k] = __ldg(ix.adj + k);
+    for (uint32_t k = threadIdx.x; k <= ix.cs_len; k += blockDim.x) t.cs[k] = __ldg(ix.cs + k);
+    if (LAYOUT == FMX_LAYOUT_Q4)
+        for (uint32_t k = threadIdx.x; k < ix.nexc; k += blockDim.x) t.exc[k] = __ldg(ix.exc + k);
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------ wavelet matrix (LAYOUT_WM)
 
 // position of `pos` after walking symbol c's path down all levels (rank(i,c) = walk - walk_c(0))
 __device__ __forceinline__ uint32_t wm_walk(const FmxDev &ix, uint32_t c, uint32_t pos) {
@@ -153,7 +189,8 @@ __device__ __forceinline__ uint32_t wm_access_walk(const FmxDev &ix, uint32_t po
         uint32_t blk, r;
         rb_split(pos, blk, r);
         RB b = rb_load(ix.lv[l], blk);
-        uint32_t ones = rb_rank(b, r), bit = rb_bit(b, r);
+        uint32_t bit;
+        uint32_t ones = rb_rank_bit(b, r, bit);
         c = (c << 1) | bit;
         pos = bit ? ix.zeros[l] + ones : pos - ones;
     }
@@ -174,6 +211,162 @@ __device__ __forceinline__ uint32_t wm_select(const FmxDev &ix, uint32_t c, uint
     return pos;
 }
 
+// ------------------------------------------------------------------ quaternary level (LAYOUT_Q4)
+// block = u32 cnt[4] (occurrences of codes 0..3 before the block) + 64 two-bit codes.
+// code = symbol - 1; the rare symbol 0 (the \0 terminators) is stored as code 0 and listed in `exc`.
+
+__device__ __forceinline__ uint32_t q4_lower_bound(const uint32_t *exc, uint32_t n, uint32_t i) {
+    uint32_t lo = 0, hi = n;  // number of exceptions < i
+    while (lo < hi) {
+        uint32_t m = lo + ((hi - lo) >> 1);
+        if (exc[m] < i) lo = m + 1; else hi = m;
+    }
+    return lo;
+}
+__device__ __forceinline__ uint32_t q4_exc_before(const FmxDev &ix, const uint32_t *exc, uint32_t i) {
+    if (ix.nexc == 1) return exc[0] < i ? 1u : 0u;
+    return q4_lower_bound(exc, ix.nexc, i);
+}
+__device__ __forceinline__ bool q4_is_exc(const FmxDev &ix, const uint32_t *exc, uint32_t i) {
+    if (ix.nexc == 1) return exc[0] == i;
+    uint32_t lb = q4_lower_bound(exc, ix.nexc, i);
+    return lb < ix.nexc && exc[lb] == i;
+}
+// one bit per code field (at the even bit positions) where the field equals `code`
+__device__ __forceinline__ uint32_t q4_eq(uint32_t word, uint32_t code) {
+    uint32_t y = ~(word ^ (code * 0x55555555u));
+    return y & (y >> 1) & 0x55555555u;
+}
+// occurrences of `code` among the first r codes of the block, r in [0, 64)
+__device__ __forceinline__ uint32_t q4_count(const RB &b, uint32_t r, uint32_t code) {
+    uint32_t total = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int d = (int)r - 16 * k;
+        uint32_t n = d <= 0 ? 0u : (d >= 16 ? 16u : (uint32_t)d);
+        uint32_t keep = (uint32_t)((1ull << (2u * n)) - 1ull);
+        total += __popc(q4_eq(b.w[4 + k], code) & keep);
+    }
+    return total;
+}
+__device__ __forceinline__ uint32_t q4_code(const RB &b, uint32_t r) {
+    uint32_t k = r >> 4;
+    uint32_t word = k == 0 ? b.w[4] : (k == 1 ? b.w[5] : (k == 2 ? b.w[6] : b.w[7]));
+    return (word >> (2u * (r & 15u))) & 3u;
+}
+__device__ __forceinline__ uint32_t q4_cnt(const RB &b, uint32_t code) {
+    return code == 0 ? b.w[0] : (code == 1 ? b.w[1] : (code == 2 ? b.w[2] : b.w[3]));
+}
+// rank(i, c) given the block of i
+__device__ __forceinline__ uint32_t q4_rank_in(const FmxDev &ix, const uint32_t *exc, const RB &b, uint32_t i,
+                                               uint32_t c) {
+    uint32_t x = q4_exc_before(ix, exc, i);
+    if (c == 0) return x;
+    uint32_t code = c - 1u;
+    uint32_t v = q4_cnt(b, code) + q4_count(b, i & 63u, code);
+    return code == 0 ? v - x : v;
+}
+// select(k, c)
+__device__ __forceinline__ uint32_t q4_select(const FmxDev &ix, const uint32_t *exc, uint32_t c, uint32_t k) {
+    if (c == 0) return exc[k];
+    const uint32_t code = c - 1u;
+    const uint32_t nblk = (ix.seq_len >> 6) + 1u;
+    const uint32_t *cw = reinterpret_cast<const uint32_t *>(ix.lv[0]);
+    uint32_t lo = 0, hi = nblk;  // last block with (occurrences of c before it) <= k
+    while (hi - lo > 1) {
+        uint32_t mid = lo + ((hi - lo) >> 1);
+        uint32_t before = __ldg(cw + 8ull * mid + code);
+        if (code == 0) before -= q4_exc_before(ix, exc, mid << 6);
+        if (before <= k) lo = mid; else hi = mid;
+    }
+    RB b = rb_load(ix.lv[0], lo);
+    uint32_t before = q4_cnt(b, code);
+    if (code == 0) before -= q4_exc_before(ix, exc, lo << 6);
+    uint32_t rem = k - before, pos = lo << 6;
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        uint32_t m = q4_eq(b.w[4 + w], code);
+        if (code == 0) {  // positions holding \0 are stored as code 0: drop them
+            uint32_t x0 = q4_exc_before(ix, exc, pos), x1 = q4_exc_before(ix, exc, pos + 16u);
+            for (uint32_t x = x0; x < x1; x++) m &= ~(1u << (2u * (exc[x] - pos)));
+        }
+        uint32_t cnt = __popc(m);
+        if (rem < cnt) return pos + (__fns(m, 0, rem + 1) >> 1);
+        rem -= cnt;
+        pos += 16u;
+    }
+    return pos;  // unreachable for a valid k
+}
+
+// ------------------------------------------------------------------ sequence primitives, both layouts
+// The "sequence" is the BWT (FM, MultiPieces) or the run heads (RLFM); cs is the matching C array.
+
+// cs[c] + rank(i, c)
+template <int LAYOUT>
+__device__ __forceinline__ uint32_t seq_lf(const FmxDev &ix, const Tabs<LAYOUT> &t, uint32_t c, uint32_t i) {
+    if (LAYOUT == FMX_LAYOUT_Q4) {
+        RB b = rb_load(ix.lv[0], i >> 6);
+        return t.cs[c] + q4_rank_in(ix, t.exc, b, i, c);
+    } else {
+        return t.adj[c] + wm_walk(ix, c, i);
+    }
+}
+
+// (s, e) <- (cs[c] + rank(s, c), cs[c] + rank(e, c)); one sector when both ends share a block
+template <int LAYOUT>
+__device__ __forceinline__ void seq_lf2(const FmxDev &ix, const Tabs<LAYOUT> &t, uint32_t c, uint32_t &s, uint32_t &e) {
+    if (LAYOUT == FMX_LAYOUT_Q4) {
+        uint32_t bs = s >> 6, be = e >> 6;
+        RB a = rb_load(ix.lv[0], bs);
+        RB b = a;
+        if (be != bs) b = rb_load(ix.lv[0], be);
+        uint32_t base = t.cs[c];
+        s = base + q4_rank_in(ix, t.exc, a, s, c);
+        e = base + q4_rank_in(ix, t.exc, b, e, c);
+    } else {
+        wm_walk2(ix, c, s, e);
+        uint32_t a = t.adj[c];
+        s += a;
+        e += a;
+    }
+}
+
+// sym = seq[i]; returns cs[sym] + rank(i, sym)   (access + rank fused: same sector(s))
+template <int LAYOUT>
+__device__ __forceinline__ uint32_t seq_access_lf(const FmxDev &ix, const Tabs<LAYOUT> &t, uint32_t i, uint32_t &sym) {
+    if (LAYOUT == FMX_LAYOUT_Q4) {
+        RB b = rb_load(ix.lv[0], i >> 6);
+        uint32_t c = q4_is_exc(ix, t.exc, i) ? 0u : q4_code(b, i & 63u) + 1u;
+        sym = c;
+        return t.cs[c] + q4_rank_in(ix, t.exc, b, i, c);
+    } else {
+        uint32_t c;
+        uint32_t w = wm_access_walk(ix, i, c);
+        sym = c;
+        return w + t.adj[c];
+    }
+}
+
+template <int LAYOUT>
+__device__ __forceinline__ uint32_t seq_access(const FmxDev &ix, const Tabs<LAYOUT> &t, uint32_t i) {
+    if (LAYOUT == FMX_LAYOUT_Q4) {
+        if (q4_is_exc(ix, t.exc, i)) return 0u;
+        RB b = rb_load(ix.lv[0], i >> 6);
+        return q4_code(b, i & 63u) + 1u;
+    } else {
+        uint32_t c;
+        wm_access_walk(ix, i, c);
+        return c;
+    }
+}
+
+// select(k, c): position of the k-th (0-based) c
+template <int LAYOUT>
+__device__ __forceinline__ uint32_t seq_select(const FmxDev &ix, const Tabs<LAYOUT> &t, uint32_t c, uint32_t k) {
+    if (LAYOUT == FMX_LAYOUT_Q4) return q4_select(ix, t.exc, c, k);
+    return wm_select(ix, c, k, t.cs[c] - t.adj[c]);
+}
+
 // ------------------------------------------------------------------ backend primitives
 // (crate-private seam src/backend.rs:5-40)
 
@@ -183,75 +376,84 @@ __device__ __forceinline__ uint32_t multi_zero_rule(const FmxDev &ix, uint32_t i
 }
 
 // ---- RLFM pieces (rlfmi.rs:118-170)
-// run index holding row i and whether that run's head is c, fused with rank(s, j, c):
+// for row i and symbol c:
 //   j   = rank1(b, i)
 //   h   = index of the run containing row i  (= rank1(b, i+1) - 1, clamped at i == n)
-//   nr  = rank(s, j, c)
+//   nrc = cs[c] + rank(s, j, c)
 //   hit = (s[h] == c)
-// The access of s[h] is done along c's path (h is j or j-1, so it shares sectors with the rank walk).
-__device__ __forceinline__ void rl_probe(const FmxDev &ix, uint32_t c, uint32_t i, uint32_t &j, uint32_t &nr,
-                                         bool &hit) {
+// h is j or j-1, so the access of s[h] shares its sector(s) with the rank of j.
+template <int LAYOUT>
+__device__ __forceinline__ void rl_probe(const FmxDev &ix, const Tabs<LAYOUT> &t, uint32_t c, uint32_t i, uint32_t &j,
+                                         uint32_t &nrc, bool &hit) {
     uint32_t blk, r;
     rb_split(i, blk, r);
     RB bb = rb_load(ix.rl_b, blk);
     j = rb_rank(bb, r);
     uint32_t starts_here = (i < ix.n) ? rb_bit(bb, r) : 0u;
     uint32_t h = starts_here ? j : j - 1u;  // b[0] == 1 so j >= 1 whenever !starts_here
-    const uint32_t L = ix.levels;
-    uint32_t p = j, q = h;
-    bool alive = true;
+    if (LAYOUT == FMX_LAYOUT_Q4) {
+        uint32_t bj = j >> 6, bh = h >> 6;
+        RB a = rb_load(ix.lv[0], bj);
+        RB d = a;
+        if (bh != bj) d = rb_load(ix.lv[0], bh);
+        uint32_t sh = q4_is_exc(ix, t.exc, h) ? 0u : q4_code(d, h & 63u) + 1u;
+        hit = sh == c;
+        nrc = t.cs[c] + q4_rank_in(ix, t.exc, a, j, c);
+    } else {
+        const uint32_t L = ix.levels;
+        uint32_t p = j, q = h;
+        bool alive = true;
 #pragma unroll 1
-    for (uint32_t l = 0; l < L; l++) {
-        uint32_t bit = (c >> (L - 1 - l)) & 1u;
-        uint32_t bp_, rp, bq, rq;
-        rb_split(p, bp_, rp);
-        rb_split(q, bq, rq);
-        const uint4 *v = ix.lv[l];
-        RB a = rb_load(v, bp_);
-        uint32_t op = rb_rank(a, rp);
-        if (alive) {
-            RB d = a;
-            if (bq != bp_) d = rb_load(v, bq);
-            uint32_t oq = rb_rank(d, rq);
-            alive = rb_bit(d, rq) == bit;
-            q = bit ? ix.zeros[l] + oq : q - oq;
+        for (uint32_t l = 0; l < L; l++) {
+            uint32_t bit = (c >> (L - 1 - l)) & 1u;
+            uint32_t bp_, rp, bq, rq;
+            rb_split(p, bp_, rp);
+            rb_split(q, bq, rq);
+            const uint4 *v = ix.lv[l];
+            RB a = rb_load(v, bp_);
+            uint32_t op = rb_rank(a, rp);
+            if (alive) {
+                RB d = a;
+                if (bq != bp_) d = rb_load(v, bq);
+                uint32_t qbit;
+                uint32_t oq = rb_rank_bit(d, rq, qbit);
+                alive = qbit == bit;
+                q = bit ? ix.zeros[l] + oq : q - oq;
+            }
+            p = bit ? ix.zeros[l] + op : p - op;
         }
-        p = bit ? ix.zeros[l] + op : p - op;
+        nrc = t.adj[c] + p;
+        hit = alive;
     }
-    nr = p;  // still offset by walk_c(0); the caller adds adj[c] = cs[c] - walk_c(0)
-    hit = alive;
 }
 
-// lf_map2 for every kind; s_adj = shared-memory copy of adj[]
-template <int KIND>
-__device__ __forceinline__ uint32_t lf_map2_dev(const FmxDev &ix, const uint32_t *s_adj, uint32_t c, uint32_t i) {
+// lf_map2 for every kind (fm_index.rs:93-95, multi_pieces.rs:140-153, rlfmi.rs:135-143)
+template <int KIND, int LAYOUT>
+__device__ __forceinline__ uint32_t lf_map2_dev(const FmxDev &ix, const Tabs<LAYOUT> &t, uint32_t c, uint32_t i) {
     if (KIND == FMX_KIND_RLFM_) {
-        uint32_t j, nr;
+        uint32_t j, nrc;
         bool hit;
-        rl_probe(ix, c, i, j, nr, hit);
-        uint32_t t = __ldg(ix.rl_bpsel + (s_adj[c] + nr));
-        if (!hit) return t;
-        return t + i - __ldg(ix.rl_bsel + j);
+        rl_probe<LAYOUT>(ix, t, c, i, j, nrc, hit);
+        uint32_t v = __ldg(ix.rl_bpsel + nrc);
+        if (!hit) return v;
+        return v + i - __ldg(ix.rl_bsel + j);
     } else {
-        uint32_t w = s_adj[c] + wm_walk(ix, c, i);
+        uint32_t w = seq_lf<LAYOUT>(ix, t, c, i);
         if (KIND == FMX_KIND_MULTI_ && c == 0) return multi_zero_rule(ix, i, w);
         return w;
     }
 }
 
 // (s, e) <- (lf_map2(c, s), lf_map2(c, e))   (wrapper.rs:109-110)
-template <int KIND>
-__device__ __forceinline__ void lf_map2_pair(const FmxDev &ix, const uint32_t *s_adj, uint32_t c, uint32_t &s,
+template <int KIND, int LAYOUT>
+__device__ __forceinline__ void lf_map2_pair(const FmxDev &ix, const Tabs<LAYOUT> &t, uint32_t c, uint32_t &s,
                                              uint32_t &e) {
     if (KIND == FMX_KIND_RLFM_) {
-        s = lf_map2_dev<KIND>(ix, s_adj, c, s);
-        e = lf_map2_dev<KIND>(ix, s_adj, c, e);
+        s = lf_map2_dev<KIND, LAYOUT>(ix, t, c, s);
+        e = lf_map2_dev<KIND, LAYOUT>(ix, t, c, e);
     } else {
         uint32_t s0 = s, e0 = e;
-        wm_walk2(ix, c, s, e);
-        uint32_t a = s_adj[c];
-        s += a;
-        e += a;
+        seq_lf2<LAYOUT>(ix, t, c, s, e);
         if (KIND == FMX_KIND_MULTI_ && c == 0) {
             s = multi_zero_rule(ix, s0, s);
             e = multi_zero_rule(ix, e0, e);
@@ -260,40 +462,36 @@ __device__ __forceinline__ void lf_map2_pair(const FmxDev &ix, const uint32_t *s
 }
 
 // get_l + lf_map fused: returns lf_map(i), sym = get_l(i)
-template <int KIND>
-__device__ __forceinline__ uint32_t lf_step(const FmxDev &ix, const uint32_t *s_adj, uint32_t i, uint32_t &sym) {
+template <int KIND, int LAYOUT>
+__device__ __forceinline__ uint32_t lf_step(const FmxDev &ix, const Tabs<LAYOUT> &t, uint32_t i, uint32_t &sym) {
     if (KIND == FMX_KIND_RLFM_) {
         // rlfmi.rs:127-133: c = get_l(i); j = rank1(b,i); nr = rank(s,j,c); select1(bp, cs[c]+nr) + i - select1(b, j)
         uint32_t blk, r;
         rb_split(i, blk, r);
         RB bb = rb_load(ix.rl_b, blk);
-        uint32_t j = rb_rank(bb, r);
-        uint32_t h = rb_bit(bb, r) ? j : j - 1u;
+        uint32_t bit;
+        uint32_t j = rb_rank_bit(bb, r, bit);
+        uint32_t h = bit ? j : j - 1u;
         uint32_t c;
-        uint32_t q = wm_access_walk(ix, h, c);  // q = walk_c(h); rank(s, j, c) = rank(s, h, c) + (j > h)
-        uint32_t nr = q + (j - h);
+        uint32_t q = seq_access_lf<LAYOUT>(ix, t, h, c);  // cs[c] + rank(s, h, c); rank(s, j, c) adds (j > h)
         sym = c;
-        return __ldg(ix.rl_bpsel + (s_adj[c] + nr)) + i - __ldg(ix.rl_bsel + j);
+        return __ldg(ix.rl_bpsel + (q + (j - h))) + i - __ldg(ix.rl_bsel + j);
     } else {
         uint32_t c;
-        uint32_t w = wm_access_walk(ix, i, c);
+        uint32_t w = seq_access_lf<LAYOUT>(ix, t, i, c);
         sym = c;
-        w += s_adj[c];
         if (KIND == FMX_KIND_MULTI_ && c == 0) return multi_zero_rule(ix, i, w);
         return w;
     }
 }
 
-template <int KIND>
-__device__ __forceinline__ uint32_t get_l_dev(const FmxDev &ix, uint32_t i) {
-    uint32_t c;
+template <int KIND, int LAYOUT>
+__device__ __forceinline__ uint32_t get_l_dev(const FmxDev &ix, const Tabs<LAYOUT> &t, uint32_t i) {
     if (KIND == FMX_KIND_RLFM_) {
         uint32_t h = rbv_rank1(ix.rl_b, i + 1 > ix.n ? ix.n : i + 1) - 1u;  // rank1 clamps past the end
-        wm_access_walk(ix, h, c);
-    } else {
-        wm_access_walk(ix, i, c);
+        return seq_access<LAYOUT>(ix, t, h);
     }
-    return c;
+    return seq_access<LAYOUT>(ix, t, i);
 }
 
 // greatest c with cs[c] <= key  (fm_index.rs:97-112)
@@ -308,33 +506,24 @@ __device__ __forceinline__ uint32_t cs_search(const uint32_t *s_cs, uint32_t cs_
 
 // get_f + fl_map fused (fm_index.rs:97-120, multi_pieces.rs:155-181, rlfmi.rs:145-169).
 // returns false when fl_map is None (MultiPieces, F[i] == 0).
-template <int KIND>
-__device__ __forceinline__ bool fl_step(const FmxDev &ix, const uint32_t *s_adj, const uint32_t *s_cs, uint32_t i,
-                                        uint32_t &sym, uint32_t &next) {
+template <int KIND, int LAYOUT>
+__device__ __forceinline__ bool fl_step(const FmxDev &ix, const Tabs<LAYOUT> &t, uint32_t i, uint32_t &sym,
+                                        uint32_t &next) {
     if (KIND == FMX_KIND_RLFM_) {
         uint32_t jr = rbv_rank1(ix.rl_bp, i + 1) - 1u;
-        uint32_t c = cs_search(s_cs, ix.cs_len, jr);
+        uint32_t c = cs_search(t.cs, ix.cs_len, jr);
         uint32_t p = __ldg(ix.rl_bpsel + jr);
-        uint32_t base = s_cs[c] - s_adj[c];
-        uint32_t m = wm_select(ix, c, jr - s_cs[c], base);
+        uint32_t m = seq_select<LAYOUT>(ix, t, c, jr - t.cs[c]);
         sym = c;
         next = __ldg(ix.rl_bsel + m) + i - p;
         return true;
     } else {
-        uint32_t c = cs_search(s_cs, ix.cs_len, i);
+        uint32_t c = cs_search(t.cs, ix.cs_len, i);
         sym = c;
         if (KIND == FMX_KIND_MULTI_ && c == 0) return false;
-        uint32_t base = s_cs[c] - s_adj[c];
-        next = wm_select(ix, c, i - s_cs[c], base);
+        next = seq_select<LAYOUT>(ix, t, c, i - t.cs[c]);
         return true;
     }
-}
-
-__device__ __forceinline__ void load_tables(const FmxDev &ix, uint32_t *s_adj, uint32_t *s_cs) {
-    for (uint32_t k = threadIdx.x; k < ix.cs_len; k += blockDim.x) s_adj[k] = __ldg(ix.adj + k);
-    if (s_cs)
-        for (uint32_t k = threadIdx.x; k <= ix.cs_len; k += blockDim.x) s_cs[k] = __ldg(ix.cs + k);
-    __syncthreads();
 }
 
 // ------------------------------------------------------------------ kernels
@@ -351,43 +540,246 @@ struct SearchArgs {
     uint64_t *out_e;
     uint32_t *err;                  // set to 1 if a processed char > max_character
     unsigned long long *work;       // [0] += executed search iterations
+    // memoised top of the search: (s, e) after the reference loop has consumed the LAST kmer_k
+    // characters of a pattern starting from (0, n) -- including its early break -- for every
+    // k-mer over 0..=max_character.  NULL => not used.
+    const uint2 *kmer_tab;
+    const uint8_t *kmer_steps;      // iterations the reference executes for that k-mer (<= kmer_k)
+    uint32_t kmer_k;
+    uint8_t *steps_out;             // nullable: per-pattern executed iterations (table build)
+    // v2 work queue: unfinished patterns after phase A, entry = {pattern id, remaining chars, s, e}
+    uint4 *queue;
+    unsigned long long *qcount;
+    unsigned long long *qcursor;
 };
 
-// Backward search (wrapper.rs:103-124), one pattern per thread.
-template <int KIND>
+__device__ __forceinline__ void pattern_span(const SearchArgs &a, uint64_t p, uint64_t &beg, uint32_t &len) {
+    if (a.pat_off) {
+        beg = a.pat_off[p];
+        len = (uint32_t)(a.pat_off[p + 1] - beg);
+    } else {
+        beg = p * a.fixed_len;
+        len = (uint32_t)a.fixed_len;
+    }
+}
+
+// Backward search (wrapper.rs:103-124): one pattern per thread, grid-stride; the first kmer_k
+// iterations of a fresh search are one table lookup.  This simple shape won the A/B against the
+// persistent refill kernels below: once the index sits in L2 the kernel is bound by the number of
+// lane-sector requests through L1TEX, which idle (diverged) lanes do not consume
+// (profiles/r01_cfg2_search_variants_ncu.txt).
+template <int KIND, int LAYOUT>
 __global__ void __launch_bounds__(256) k_search(const __grid_constant__ FmxDev ix, const __grid_constant__ SearchArgs a) {
-    __shared__ uint32_t s_adj[256];
-    load_tables(ix, s_adj, nullptr);
+    __shared__ Tabs<LAYOUT> tb;
+    load_tables<LAYOUT>(ix, tb);
     unsigned long long steps = 0;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < a.npat; p += stride) {
-        uint64_t beg, len;
-        if (a.pat_off) {
-            beg = a.pat_off[p];
-            len = a.pat_off[p + 1] - beg;
-        } else {
-            beg = p * a.fixed_len;
-            len = a.fixed_len;
-        }
+        uint64_t beg;
+        uint32_t len;
+        pattern_span(a, p, beg, len);
         uint32_t s = a.init_s ? (uint32_t)a.init_s[p] : a.s0;
         uint32_t e = a.init_e ? (uint32_t)a.init_e[p] : a.e0;
         const uint8_t *q = a.pat + beg;
-        for (uint64_t k = len; k-- > 0;) {
+        uint32_t it = 0;
+        if (a.kmer_tab != nullptr && a.init_s == nullptr && len >= a.kmer_k) {
+            // the first kmer_k iterations of a fresh search are one table lookup
+            const uint32_t K = a.kmer_k;
+            uint32_t idx = 0;
+            bool valid = true;
+            for (uint32_t j = 0; j < K; j++) {
+                uint32_t c = __ldg(q + len - 1 - j);
+                valid = valid && c <= ix.max_character;
+                idx = idx * ix.cs_len + c;
+            }
+            if (valid) {  // else: walk the slow path so the error shows up (or not) exactly as in the reference
+                uint2 t = __ldg(a.kmer_tab + idx);
+                s = t.x;
+                e = t.y;
+                it = K;
+                len -= K;
+                if (s == e) {
+                    it = __ldg(a.kmer_steps + idx);
+                    len = 0;
+                }
+            }
+        }
+        for (uint32_t k = len; k-- > 0;) {
             uint32_t c = __ldg(q + k);
             if (c > ix.max_character) {  // the reference panics here (cs[c] out of bounds, fm_index.rs:94)
                 atomicOr(a.err, 1u);
                 break;
             }
-            lf_map2_pair<KIND>(ix, s_adj, c, s, e);
-            steps++;
+            lf_map2_pair<KIND, LAYOUT>(ix, tb, c, s, e);
+            it++;
             if (s == e) break;
         }
+        steps += it;
         a.out_s[p] = s;
         a.out_e[p] = e;
+        if (a.steps_out) a.steps_out[p] = (uint8_t)it;
     }
     if (a.work) {
         for (int o = 16; o > 0; o >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, o);
         if ((threadIdx.x & 31) == 0 && steps) atomicAdd(a.work, steps);
+    }
+}
+
+// patterns for the k-mer table: entry t is the k-mer whose LAST character is the most significant
+// base-sigma digit of t
+__global__ void k_kmer_patterns(uint32_t k, uint32_t sigma, uint64_t entries, uint8_t *pat) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= entries) return;
+    uint64_t v = t;
+    for (uint32_t j = 0; j < k; j++) {  // least significant digit = first character of the k-mer
+        pat[t * k + j] = (uint8_t)(v % sigma);
+        v /= sigma;
+    }
+}
+__global__ void k_kmer_pack(const uint64_t *s, const uint64_t *e, uint64_t entries, uint2 *tab) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < entries) tab[t] = make_uint2((uint32_t)s[t], (uint32_t)e[t]);
+}
+
+// Backward search, persistent variant (option "search_persistent"), phase A: one pattern per thread, fully converged.
+// Sets up (s, e) and the number of characters still to consume; the first kmer_k iterations of a
+// fresh search are ONE table lookup.  Patterns the table already finishes (their range emptied
+// within kmer_k characters, or nothing is left) are final here; the rest go to a work queue.
+template <int KIND, int LAYOUT>
+__global__ void __launch_bounds__(256) k_search_init(const __grid_constant__ FmxDev ix, const __grid_constant__ SearchArgs a) {
+    const uint32_t lane = threadIdx.x & 31;
+    const bool use_tab = a.kmer_tab != nullptr && a.init_s == nullptr;
+    const uint32_t K = a.kmer_k, sigma = ix.cs_len;
+    unsigned long long steps = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t rounds = (a.npat + stride - 1) / stride;
+    for (uint64_t rd = 0; rd < rounds; rd++) {
+        uint64_t p = rd * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        bool todo = false;
+        uint32_t k = 0;
+        uint4 ent = make_uint4(0, 0, 0, 0);
+        if (p < a.npat) {
+            uint64_t beg;
+            pattern_span(a, p, beg, k);
+            const uint8_t *q = a.pat + beg;
+            uint32_t s = a.init_s ? (uint32_t)a.init_s[p] : a.s0;
+            uint32_t e = a.init_e ? (uint32_t)a.init_e[p] : a.e0;
+            bool done = k == 0;
+            if (use_tab && k >= K) {
+                uint32_t idx = 0;
+                bool valid = true;
+                for (uint32_t j = 0; j < K; j++) {
+                    uint32_t c = __ldg(q + k - 1 - j);
+                    valid = valid && c <= ix.max_character;
+                    idx = idx * sigma + c;
+                }
+                if (valid) {  // else: walk the slow path so the error shows up (or not) exactly as in the reference
+                    uint2 t = __ldg(a.kmer_tab + idx);
+                    s = t.x;
+                    e = t.y;
+                    k -= K;
+                    if (s == e) {
+                        steps += __ldg(a.kmer_steps + idx);
+                        done = true;
+                    } else {
+                        steps += K;
+                        done = k == 0;
+                    }
+                }
+            }
+            todo = !done;
+            if (done) {
+                a.out_s[p] = s;
+                a.out_e[p] = e;
+            }
+            ent = make_uint4((uint32_t)p, k, s, e);
+        }
+        unsigned m = __ballot_sync(0xffffffffu, todo);
+        if (m) {
+            unsigned long long base = 0;
+            if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(a.qcount, (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+            if (todo) a.queue[base + __popc(m & ((1u << lane) - 1u))] = ent;
+        }
+    }
+    if (a.work) {
+        for (int o = 16; o > 0; o >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, o);
+        if (lane == 0 && steps) atomicAdd(a.work, steps);
+    }
+}
+
+// phase B: persistent warps drain the work queue.  Every lane owns one pattern at a time and takes
+// its next queue entry the moment it finishes (s == e breaks make run lengths very uneven: the
+// one-pattern-per-thread kernel kept 23 of 32 lanes busy).  The next entry of every lane is
+// already in registers (loaded one refill ahead), so taking it costs no memory round trip.  Warps
+// grab 64-entry chunks from one global cursor, so SMs stay balanced to the end.
+#define FMX_QCHUNK 64u
+template <int KIND, int LAYOUT>
+__global__ void __launch_bounds__(256) k_search_steps(const __grid_constant__ FmxDev ix, const __grid_constant__ SearchArgs a) {
+    __shared__ Tabs<LAYOUT> tb;
+    load_tables<LAYOUT>(ix, tb);
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    const unsigned long long qn = *a.qcount;
+    unsigned long long w_next = 0, w_end = 0;  // this warp's current chunk of the queue
+    bool active = false, has_nxt = false, exhausted = qn == 0;
+    uint4 nxt = make_uint4(0, 0, 0, 0);
+    uint32_t p = 0, k = 0, s = 0, e = 0;
+    const uint8_t *q = nullptr;
+    unsigned long long steps = 0;
+    for (;;) {
+        unsigned idle = __ballot_sync(0xffffffffu, !active);
+        if (idle) {
+            if (!active && has_nxt) {
+                p = nxt.x;
+                k = nxt.y;
+                s = nxt.z;
+                e = nxt.w;
+                q = a.pat + (a.pat_off ? a.pat_off[p] : (uint64_t)p * a.fixed_len);
+                active = true;
+                has_nxt = false;
+            }
+            unsigned want = __ballot_sync(0xffffffffu, !has_nxt);
+            if (want && !exhausted) {
+                if (w_next >= w_end) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(a.qcursor, (unsigned long long)FMX_QCHUNK);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    w_next = base;
+                    w_end = base + FMX_QCHUNK < qn ? base + FMX_QCHUNK : qn;
+                    exhausted = base >= qn;
+                }
+                if (!exhausted) {
+                    unsigned long long mine = w_next + __popc(want & lt);
+                    if (!has_nxt && mine < w_end) {
+                        nxt = __ldg(a.queue + mine);
+                        has_nxt = true;
+                    }
+                    w_next += __popc(want);
+                }
+            }
+            if (exhausted && __ballot_sync(0xffffffffu, active || has_nxt) == 0) break;
+        }
+        if (active) {
+            uint32_t c = __ldg(q + --k);
+            if (c > ix.max_character) {  // the reference panics here (cs[c] out of bounds, fm_index.rs:94)
+                atomicOr(a.err, 1u);
+                k = 0;
+            } else {
+                lf_map2_pair<KIND, LAYOUT>(ix, tb, c, s, e);
+                steps++;
+                if (s == e) k = 0;
+            }
+            if (k == 0) {
+                a.out_s[p] = s;
+                a.out_e[p] = e;
+                active = false;
+            }
+        }
+    }
+    if (a.work) {
+        for (int o = 16; o > 0; o >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, o);
+        if (lane == 0 && steps) atomicAdd(a.work, steps);
     }
 }
 
@@ -415,11 +807,13 @@ __global__ void k_expand_rows(const uint64_t *s, const uint64_t *off, const uint
 }
 
 // prefix filter (wrapper.rs:208): flag[h] = (get_l(rows[h]) == 0)
-template <int KIND>
+template <int KIND, int LAYOUT>
 __global__ void __launch_bounds__(256) k_flag_prefix(const __grid_constant__ FmxDev ix, const uint32_t *rows,
                                                      uint64_t total, uint32_t *flag) {
+    __shared__ Tabs<LAYOUT> tb;
+    load_tables<LAYOUT>(ix, tb);
     uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (h < total) flag[h] = get_l_dev<KIND>(ix, rows[h]) == 0u ? 1u : 0u;
+    if (h < total) flag[h] = get_l_dev<KIND, LAYOUT>(ix, tb, rows[h]) == 0u ? 1u : 0u;
 }
 
 // stream compaction of the kept rows; fpos = exclusive scan of flag
@@ -447,10 +841,10 @@ struct LocateArgs {
 // sampled row, one hit per thread.  piece id (multi_pieces.rs:208-218) is derived from the located
 // position and the piece boundary table: it equals the number of \0 before the position, which is
 // what the reference's walk to the piece start computes (pinned by multi_pieces.rs:287-296).
-template <int KIND>
+template <int KIND, int LAYOUT>
 __global__ void __launch_bounds__(256) k_locate(const __grid_constant__ FmxDev ix, const __grid_constant__ LocateArgs a) {
-    __shared__ uint32_t s_adj[256];
-    load_tables(ix, s_adj, nullptr);
+    __shared__ Tabs<LAYOUT> tb;
+    load_tables<LAYOUT>(ix, tb);
     unsigned long long steps = 0;
     const uint32_t mask = (1u << ix.sa_level) - 1u;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -458,7 +852,7 @@ __global__ void __launch_bounds__(256) k_locate(const __grid_constant__ FmxDev i
         uint32_t row = a.rows[h];
         uint32_t st = 0, sym;
         while (row & mask) {
-            row = lf_step<KIND>(ix, s_adj, row, sym);
+            row = lf_step<KIND, LAYOUT>(ix, tb, row, sym);
             st++;
         }
         uint64_t v = (uint64_t)__ldg(ix.sa + (row >> ix.sa_level)) + st;
@@ -481,13 +875,12 @@ __global__ void __launch_bounds__(256) k_locate(const __grid_constant__ FmxDev i
 }
 
 // iter_chars_backward / iter_chars_forward, k characters per row (wrapper.rs:143-183)
-template <int KIND>
+template <int KIND, int LAYOUT>
 __global__ void __launch_bounds__(256) k_extract(const __grid_constant__ FmxDev ix, const uint64_t *rows,
                                                  uint64_t nrows, uint32_t k, int forward, uint8_t *out,
                                                  uint32_t *out_len) {
-    __shared__ uint32_t s_adj[256];
-    __shared__ uint32_t s_cs[257];
-    load_tables(ix, s_adj, s_cs);
+    __shared__ Tabs<LAYOUT> tb;
+    load_tables<LAYOUT>(ix, tb);
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nrows) return;
     uint32_t i = (uint32_t)rows[r], got = 0;
@@ -495,8 +888,8 @@ __global__ void __launch_bounds__(256) k_extract(const __grid_constant__ FmxDev 
     for (uint32_t t = 0; t < k; t++) {
         uint32_t c, nx;
         if (!forward) {
-            nx = lf_step<KIND>(ix, s_adj, i, c);
-        } else if (!fl_step<KIND>(ix, s_adj, s_cs, i, c, nx)) {
+            nx = lf_step<KIND, LAYOUT>(ix, tb, i, c);
+        } else if (!fl_step<KIND, LAYOUT>(ix, tb, i, c, nx)) {
             break;
         }
         o[t] = (uint8_t)c;
@@ -508,29 +901,28 @@ __global__ void __launch_bounds__(256) k_extract(const __grid_constant__ FmxDev 
 }
 
 // backend primitives over a batch of rows, for parity tests (src/backend.rs:5-40)
-template <int KIND>
+template <int KIND, int LAYOUT>
 __global__ void __launch_bounds__(256) k_rows_op(const __grid_constant__ FmxDev ix, int op, const uint64_t *rows,
                                                  uint64_t nrows, uint64_t *out) {
-    __shared__ uint32_t s_adj[256];
-    __shared__ uint32_t s_cs[257];
-    load_tables(ix, s_adj, s_cs);
+    __shared__ Tabs<LAYOUT> tb;
+    load_tables<LAYOUT>(ix, tb);
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nrows) return;
     uint32_t i = (uint32_t)rows[r], c, nx;
     uint64_t res = 0;
     switch (op) {
-        case 0: res = get_l_dev<KIND>(ix, i); break;
-        case 1: res = lf_step<KIND>(ix, s_adj, i, c); break;
+        case 0: res = get_l_dev<KIND, LAYOUT>(ix, tb, i); break;
+        case 1: res = lf_step<KIND, LAYOUT>(ix, tb, i, c); break;
         case 2:
-            if (KIND == FMX_KIND_RLFM_) res = cs_search(s_cs, ix.cs_len, rbv_rank1(ix.rl_bp, i + 1) - 1u);
-            else res = cs_search(s_cs, ix.cs_len, i);
+            if (KIND == FMX_KIND_RLFM_) res = cs_search(tb.cs, ix.cs_len, rbv_rank1(ix.rl_bp, i + 1) - 1u);
+            else res = cs_search(tb.cs, ix.cs_len, i);
             break;
-        case 3: res = fl_step<KIND>(ix, s_adj, s_cs, i, c, nx) ? (uint64_t)nx : FMX_NONE; break;
+        case 3: res = fl_step<KIND, LAYOUT>(ix, tb, i, c, nx) ? (uint64_t)nx : FMX_NONE; break;
         case 4: {
             const uint32_t mask = (1u << ix.sa_level) - 1u;
             uint32_t st = 0;
             while (i & mask) {
-                i = lf_step<KIND>(ix, s_adj, i, c);
+                i = lf_step<KIND, LAYOUT>(ix, tb, i, c);
                 st++;
             }
             uint64_t v = (uint64_t)__ldg(ix.sa + (i >> ix.sa_level)) + st;
@@ -539,9 +931,9 @@ __global__ void __launch_bounds__(256) k_rows_op(const __grid_constant__ FmxDev 
         }
         case 5: {  // the reference's literal piece_id walk (multi_pieces.rs:208-218)
             for (;;) {
-                uint32_t nxt = lf_step<KIND>(ix, s_adj, i, c);
+                uint32_t nxt = lf_step<KIND, LAYOUT>(ix, tb, i, c);
                 if (c == 0) {
-                    uint32_t rank0 = wm_walk(ix, 0, i) + s_adj[0];  // rank(bw, i, 0); cs[0] == 0
+                    uint32_t rank0 = seq_lf<LAYOUT>(ix, tb, 0, i);  // rank(bw, i, 0); cs[0] == 0
                     res = (uint64_t)((__ldg(ix.doc + rank0) + 1u) % ix.ndoc);
                     break;
                 }
@@ -553,14 +945,14 @@ __global__ void __launch_bounds__(256) k_rows_op(const __grid_constant__ FmxDev 
     out[r] = res;
 }
 
-template <int KIND>
+template <int KIND, int LAYOUT>
 __global__ void __launch_bounds__(256) k_lf_map2(const __grid_constant__ FmxDev ix, const uint8_t *c, const uint64_t *i,
                                                  uint64_t nrows, uint64_t *out) {
-    __shared__ uint32_t s_adj[256];
-    load_tables(ix, s_adj, nullptr);
+    __shared__ Tabs<LAYOUT> tb;
+    load_tables<LAYOUT>(ix, tb);
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nrows) return;
-    out[r] = lf_map2_dev<KIND>(ix, s_adj, c[r], (uint32_t)i[r]);
+    out[r] = lf_map2_dev<KIND, LAYOUT>(ix, tb, c[r], (uint32_t)i[r]);
 }
 
 // ------------------------------------------------------------------ scans (3-phase, hand written)

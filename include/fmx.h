@@ -91,6 +91,12 @@ void fmx_index_free(fmx_index *idx);
 /* Suffix array of a text exactly as sais::build_suffix_array (sais.rs:115-144) returns it. */
 int fmx_build_suffix_array(const void *text, uint64_t n, uint32_t char_width, uint64_t *sa_out);
 
+/* Tuning knobs (A/B measurement; results never change): "search_persistent" 0|1 (persistent
+ * per-lane-refill search kernels instead of one pattern per thread), "kmer" 0|1 (memoised first
+ * search iterations), "persist_blocks_per_sm" 1..32.  The environment variable
+ * FMX_FORCE_WAVELET=1 makes construction keep the binary wavelet matrix for small alphabets. */
+int fmx_index_set_option(fmx_index *idx, const char *key, int64_t value);
+
 /* SearchIndex::len (frontend.rs:35-39), heap_size (:41-44, here: device bytes),
  * HasMultiPieces::pieces_count (multi_pieces.rs:220-222) */
 uint64_t fmx_index_len(const fmx_index *idx);

@@ -4,9 +4,9 @@ import struct
 
 import numpy as np
 
-SEC_LEVEL0, SEC_ADJ, SEC_CS, SEC_SA, SEC_DOC, SEC_PIECE_END, SEC_RL_B, SEC_RL_BP, SEC_RL_BSEL, SEC_RL_BPSEL, SEC_COUNT = \
-    0, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17
-RB_BITS = 224
+SEC_LEVEL0, SEC_ADJ, SEC_CS, SEC_SA, SEC_DOC, SEC_PIECE_END, SEC_RL_B, SEC_RL_BP, SEC_RL_BSEL, SEC_RL_BPSEL, SEC_EXC, SEC_COUNT = \
+    0, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18
+RB_BITS = 192
 M32 = 0xFFFFFFFF
 
 
@@ -16,17 +16,13 @@ class RBVec:
 
     def rank1(self, pos):
         b, r = divmod(pos, RB_BITS)
-        c = int(self.w[b, 0])
-        for k in range(7):
-            if r >= 32 * (k + 1):
-                c += bin(int(self.w[b, 1 + k])).count("1")
-            elif r > 32 * k:
-                c += bin(int(self.w[b, 1 + k]) & ((1 << (r - 32 * k)) - 1)).count("1")
-        return c
+        j, x = r >> 6, r & 63
+        word = int(self.w[b, 2 + 2 * j]) | (int(self.w[b, 3 + 2 * j]) << 32)
+        return int(self.w[b, 0]) + ((int(self.w[b, 1]) >> (8 * j)) & 0xFF) + bin(word & ((1 << x) - 1)).count("1")
 
     def bit(self, pos):
         b, r = divmod(pos, RB_BITS)
-        return (int(self.w[b, 1 + (r >> 5)]) >> (r & 31)) & 1
+        return (int(self.w[b, 2 + (r >> 5)]) >> (r & 31)) & 1
 
 
 class Blob:
@@ -42,8 +38,16 @@ class Blob:
         (self.total_bytes,) = struct.unpack_from("<Q", raw, o)
         o += 8
         self.sec = [struct.unpack_from("<QQ", raw, o + 16 * k) for k in range(SEC_COUNT)]
+        o += 16 * SEC_COUNT
+        self.layout, self.nexc = struct.unpack_from("<II", raw, o)
         assert self.total_bytes == len(raw)
-        self.lv = [RBVec(self._sec(SEC_LEVEL0 + l)) for l in range(self.levels)]
+        if self.layout == 1:
+            self.q4 = np.frombuffer(self._sec(SEC_LEVEL0), dtype=np.uint32).reshape(-1, 8)
+            self.exc = [int(v) for v in np.frombuffer(self._sec(SEC_EXC), dtype=np.uint32)]
+            assert len(self.exc) == self.nexc
+            self.lv = []
+        else:
+            self.lv = [RBVec(self._sec(SEC_LEVEL0 + l)) for l in range(self.levels)]
         self.adj = np.frombuffer(self._sec(SEC_ADJ), dtype=np.uint32)
         self.cs = np.frombuffer(self._sec(SEC_CS), dtype=np.uint32)
         self.sa = np.frombuffer(self._sec(SEC_SA), dtype=np.uint32)
@@ -59,6 +63,41 @@ class Blob:
         off, nb = self.sec[k]
         assert off % 256 == 0
         return self.raw[off:off + nb]
+
+    # ---- Q4 layout
+    def q4_code(self, i):
+        b, t = divmod(i, 64)
+        return (int(self.q4[b, 4 + (t >> 4)]) >> (2 * (t & 15))) & 3
+
+    def q4_rank(self, i, c):
+        import bisect
+        x = bisect.bisect_left(self.exc, i)
+        if c == 0:
+            return x
+        code = c - 1
+        b, r = divmod(i, 64)
+        v = int(self.q4[b, code]) + sum(1 for t in range(r) if self.q4_code(b * 64 + t) == code)
+        return v - x if code == 0 else v
+
+    def q4_access(self, i):
+        import bisect
+        k = bisect.bisect_left(self.exc, i)
+        if k < len(self.exc) and self.exc[k] == i:
+            return 0
+        return self.q4_code(i) + 1
+
+    # cs[c] + rank(i, c) and (seq[i], cs + rank) for either layout
+    def seq_lf(self, c, i):
+        if self.layout == 1:
+            return int(self.cs[c]) + self.q4_rank(i, c)
+        return (int(self.adj[c]) + self.walk(c, i)) & M32
+
+    def seq_access_lf(self, i):
+        if self.layout == 1:
+            c = self.q4_access(i)
+            return c, int(self.cs[c]) + self.q4_rank(i, c)
+        c, w = self.access_walk(i)
+        return c, (w + int(self.adj[c])) & M32
 
     # the same arithmetic the kernels do (kernels.cuh), in Python
     def walk(self, c, pos):
@@ -84,11 +123,10 @@ class Blob:
             j = self.b.rank1(i)
             starts = self.b.bit(i) if i < self.n else 0
             h = j if starts else j - 1
-            hc, _ = self.access_walk(h)
-            nr = (int(self.adj[c]) + self.walk(c, j)) & M32
-            t = int(self.bpsel[nr])
+            hc, _ = self.seq_access_lf(h)
+            t = int(self.bpsel[self.seq_lf(c, j)])
             return t if hc != c else t + i - int(self.bsel[j])
-        w = (int(self.adj[c]) + self.walk(c, i)) & M32
+        w = self.seq_lf(c, i)
         if self.kind == 2 and c == 0:
             return self._zero_rule(i, w)
         return w
@@ -97,11 +135,9 @@ class Blob:
         if self.kind == 1:
             j = self.b.rank1(i)
             h = j if self.b.bit(i) else j - 1
-            c, q = self.access_walk(h)
-            nr = (int(self.adj[c]) + q + (j - h)) & M32
-            return c, int(self.bpsel[nr]) + i - int(self.bsel[j])
-        c, w = self.access_walk(i)
-        w = (w + int(self.adj[c])) & M32
+            c, q = self.seq_access_lf(h)
+            return c, int(self.bpsel[q + (j - h)]) + i - int(self.bsel[j])
+        c, w = self.seq_access_lf(i)
         if self.kind == 2 and c == 0:
             return c, self._zero_rule(i, w)
         return c, w

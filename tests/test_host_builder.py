@@ -75,7 +75,7 @@ def test_blob_reader_matches_oracle(kind):
     cases = list(CASES)
     for _ in range(6):
         mc = int(rng.choice([4, 7, 255]))
-        text = build_text(rng, int(rng.integers(2, 700)), min(mc, 8) if kind == 2 else min(mc, 7), kind == 2)
+        text = build_text(rng, int(rng.integers(2, 700)), min(mc + 1, 8) if kind == 2 else min(mc, 7), kind == 2)
         cases.append((text, mc, int(rng.integers(0, 4))))
     for text, mc, level in cases:
         if kind != 2 and 0 in text[:-1]:
@@ -84,6 +84,8 @@ def test_blob_reader_matches_oracle(kind):
         b = Blob(fmx.blob_build(fmx.Text.with_max_character(text, mc), kind, level))
         n = len(text)
         assert (b.n, b.kind, b.levels, b.cs_len) == (n, kind, int(mc).bit_length(), mc + 1)
+        zeros = text.count(0) if kind != 1 else 1
+        assert b.layout == (1 if mc <= 4 and zeros <= 1024 else 0)
         assert b.sa_level == orc.lib().orc_sample_level(o._h)
         assert b.sa_word_size == orc.lib().orc_sample_word_size(o._h)
         rows = range(n) if n < 300 else [int(v) for v in rng.integers(0, n, 200)]
@@ -106,3 +108,18 @@ def test_blob_reader_matches_oracle(kind):
         if kind == 2:
             assert b.ndoc == o.pieces_count() and b.first_row == orc.lib().orc_first_row(o._h)
             assert [int(v) for v in b.doc] == [orc.lib().orc_doc(o._h, k) for k in range(b.ndoc)]
+
+
+def test_q4_falls_back_to_wavelet_with_many_zeros(monkeypatch):
+    rng = np.random.default_rng(77)
+    text = build_text(rng, 9000, 5, True)          # ~17 % zeros > FMX_MAX_EXC
+    assert text.count(0) > 1024
+    b = Blob(fmx.blob_build(fmx.Text.with_max_character(text, 4), 2, 1))
+    assert b.layout == 0
+    o = orc.OracleIndex(text, 2, level=1, max_character=4)
+    for i in rng.integers(0, len(text), 100):
+        c, nx = b.lf_step(int(i))
+        assert c == o.get_l(int(i)) and nx == o.lf_map(int(i))
+    monkeypatch.setenv("FMX_FORCE_WAVELET", "1")
+    small = build_text(rng, 500, 4, False)
+    assert Blob(fmx.blob_build(fmx.Text.with_max_character(small, 4), 0, 1)).layout == 0

@@ -200,6 +200,28 @@ class _Index:
                                         _ptr(s), _ptr(e)))
         return SearchBatch(self, mode, s, e)
 
+    def search_locate_batch(self, patterns, mode=SEARCH, piece_ids=False, capacity=None):
+        """Fused, pipelined batched search + locate (fmx_search_locate_batch): the batched form of
+        `index.search(p).iter_matches().map(|m| m.locate())`.
+        -> (SearchBatch, hit_off[npat+1], positions[, piece_ids])"""
+        flat, off, fixed, npat = _pack(patterns)
+        s = np.zeros(npat, dtype=np.uint64)
+        e = np.zeros(npat, dtype=np.uint64)
+        hit_off = np.zeros(npat + 1, dtype=np.uint64)
+        cap = int(capacity) if capacity is not None else max(1024, 2 * npat)
+        pos = np.zeros(cap, dtype=np.uint64)
+        pid = np.zeros(cap, dtype=np.uint64) if piece_ids else None
+        total = C.c_uint64(0)
+        rc = self._L.fmx_search_locate_batch(self._h, mode, _ptr(flat), _ptr(off), fixed, npat, _ptr(s), _ptr(e),
+                                             _ptr(hit_off), _ptr(pos), _ptr(pid), cap, C.byref(total))
+        batch = SearchBatch(self, mode, s, e)
+        if rc == -9:  # FMX_ERR_CAPACITY: hit_off and total are valid; fetch the hits with exact-size buffers
+            res = batch.locate(piece_ids)
+            return (batch,) + tuple(res)
+        _check(rc)
+        t = int(total.value)
+        return (batch, hit_off, pos[:t].copy(), pid[:t].copy()) if piece_ids else (batch, hit_off, pos[:t].copy())
+
     def locate_batch(self, s, e, prefix_only=False, piece_ids=False):
         s = np.ascontiguousarray(s, dtype=np.uint64)
         e = np.ascontiguousarray(e, dtype=np.uint64)
@@ -239,6 +261,10 @@ class _Index:
         out = np.zeros(i.size, dtype=np.uint64)
         _check(self._L.fmx_lf_map2_batch(self._h, _ptr(c), _ptr(i), i.size, _ptr(out)))
         return out
+
+    def sectors_per_rank(self):
+        """32-byte sectors per rank/access probe in this index's device layout (L, or 1 for Q4)."""
+        return int(self._L.fmx_index_sectors_per_rank(self._h))
 
     def set_option(self, key, value):
         """tuning knobs for A/B measurements; results never change"""

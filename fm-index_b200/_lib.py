@@ -32,10 +32,12 @@ SIGNATURES = {
     "fmx_index_device": (_int, [_vp]),
     "fmx_index_wavelet_levels": (_u32, [_vp]),
     "fmx_index_sample_level": (_u32, [_vp]),
+    "fmx_index_sectors_per_rank": (_u32, [_vp]),
     "fmx_search_batch": (_int, [_vp, _int, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp]),
     "fmx_search_batch_device": (_int, [_vp, _int, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp]),
     "fmx_search_check": (_int, [_vp, _vp]),
     "fmx_locate_batch": (_int, [_vp, _int, _vp, _vp, _u64, _vp, _pp, _pp]),
+    "fmx_search_locate_batch": (_int, [_vp, _int, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _u64, _u64p]),
     "fmx_locate_count_device": (_int, [_vp, _int, _vp, _vp, _u64, _vp, _u64p, _vp]),
     "fmx_locate_fill_device": (_int, [_vp, _int, _vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp]),
     "fmx_extract_batch": (_int, [_vp, _vp, _u64, _u32, _int, _vp, _vp]),

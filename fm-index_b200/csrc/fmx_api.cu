@@ -65,6 +65,14 @@ struct DevBuf {
 enum { B_QUEUE, B_PAT, B_OFF, B_S, B_E, B_INS, B_INE, B_CNT, B_HOFF, B_OWNER, B_ROWS, B_ROWS2, B_FLAG, B_FPOS, B_TILES, B_POS, B_PID,
        B_OUT8, B_OUT32, B_COUNT };
 
+// one lane of the chunked H2D / kernels / D2H pipeline (fmx_search_locate_batch)
+struct Lane {
+    DevBuf buf[B_COUNT];
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev = nullptr;
+    uint64_t *h_total = nullptr;  // pinned
+};
+
 struct fmx_index {
     FmxBlobHeader hdr;
     FmxDev dev;
@@ -83,7 +91,10 @@ struct fmx_index {
     // tuning knobs (fmx_index_set_option)
     int opt_persistent = 0;  // 1: persistent refill search kernels instead of one pattern per thread
     int opt_kmer = 1;
+    uint64_t opt_pipeline_chunk = 0;  // patterns per pipeline chunk (0 = automatic)
     mutable DevBuf buf[B_COUNT];
+    mutable Lane lane[2];
+    mutable bool lanes_ready = false;
     mutable std::mutex mu;
 };
 
@@ -268,6 +279,12 @@ void fmx_index_free(fmx_index *idx) {
     if (!idx) return;
     cudaSetDevice(idx->device);
     for (auto &b : idx->buf) b.release();
+    for (auto &l : idx->lane) {
+        for (auto &b : l.buf) b.release();
+        if (l.st) cudaStreamDestroy(l.st);
+        if (l.ev) cudaEventDestroy(l.ev);
+        if (l.h_total) cudaFreeHost(l.h_total);
+    }
     if (idx->d_blob) cudaFree(idx->d_blob);
     if (idx->d_err) cudaFree(idx->d_err);
     if (idx->d_kmer_tab) cudaFree(idx->d_kmer_tab);
@@ -281,6 +298,7 @@ int fmx_index_set_option(fmx_index *idx, const char *key, int64_t value) {
     std::string k(key);
     if (k == "search_persistent") idx->opt_persistent = value != 0;
     else if (k == "kmer") idx->opt_kmer = value != 0;
+    else if (k == "pipeline_chunk") idx->opt_pipeline_chunk = value > 0 ? (uint64_t)value : 0;
     else if (k == "persist_blocks_per_sm") {
         if (value < 1 || value > 32) return fail(FMX_ERR_INVALID_ARG, "persist_blocks_per_sm out of range");
         idx->persist_blocks_per_sm = (int)value;
@@ -296,6 +314,9 @@ int fmx_index_has_locate(const fmx_index *idx) { return idx ? (int)idx->hdr.has_
 int fmx_index_device(const fmx_index *idx) { return idx ? idx->device : -1; }
 uint32_t fmx_index_wavelet_levels(const fmx_index *idx) { return idx ? idx->hdr.levels : 0; }
 uint32_t fmx_index_sample_level(const fmx_index *idx) { return idx ? idx->hdr.sa_level : 0; }
+uint32_t fmx_index_sectors_per_rank(const fmx_index *idx) {
+    return idx ? (idx->hdr.layout == FMX_LAYOUT_QUAT ? 1u : idx->hdr.levels) : 0;
+}
 
 }  // extern "C"
 
@@ -438,7 +459,8 @@ static int build_kmer_table(fmx_index *idx) {
 
 static int search_device(const fmx_index *idx, int mode, const uint8_t *d_pat, const uint64_t *d_pat_off,
                          uint64_t fixed_len, uint64_t npat, const uint64_t *d_is, const uint64_t *d_ie,
-                         uint64_t *d_os, uint64_t *d_oe, cudaStream_t st) {
+                         uint64_t *d_os, uint64_t *d_oe, cudaStream_t st, bool count_work = true,
+                         bool force_simple = false) {
     if (mode < FMX_SEARCH || mode > FMX_SEARCH_EXACT) return fail(FMX_ERR_INVALID_ARG, "bad search mode");
     if (mode != FMX_SEARCH && idx->hdr.kind != FMX_KIND_MULTI)
         return fail(FMX_ERR_UNSUPPORTED, "search_prefix/suffix/exact need a MultiPieces index (frontend.rs:369-390)");
@@ -456,15 +478,15 @@ static int search_device(const fmx_index *idx, int mode, const uint8_t *d_pat, c
     a.out_s = d_os;
     a.out_e = d_oe;
     a.err = idx->d_err;
-    a.work = idx->d_work;
+    a.work = count_work ? idx->d_work : nullptr;
     a.steps_out = nullptr;
     // the table memoises searches that start from (0, n): fresh search / search_prefix
     const bool tab_ok = idx->d_kmer_tab && idx->opt_kmer && !d_is && (mode == FMX_SEARCH || mode == FMX_SEARCH_PREFIX);
     a.kmer_tab = tab_ok ? idx->d_kmer_tab : nullptr;
     a.kmer_steps = tab_ok ? idx->d_kmer_steps : nullptr;
     a.kmer_k = tab_ok ? idx->kmer_k : 0;
-    CUDA_TRY(cudaMemsetAsync(idx->d_work, 0, sizeof(unsigned long long), st));
-    return dispatch_search(idx, a, st);
+    if (count_work) CUDA_TRY(cudaMemsetAsync(idx->d_work, 0, sizeof(unsigned long long), st));
+    return dispatch_search(idx, a, st, force_simple);
 }
 
 static int check_err_flag(const fmx_index *idx, cudaStream_t st) {
@@ -536,89 +558,104 @@ extern "C" int fmx_search_batch(const fmx_index *idx, int mode, const uint8_t *p
 
 // ------------------------------------------------------------------ locate
 
-// candidate rows of every range, in pattern order then ascending row order; applies the L == 0
-// filter by flag / scan / compaction.  On return d_hit_off holds the final offsets and
-// buf[B_ROWS] (or B_ROWS2 when filtered) the hit rows.  *rows_out points at them.
-static int locate_prepare(const fmx_index *idx, int prefix_only, const uint64_t *d_s, const uint64_t *d_e,
-                          uint64_t npat, uint64_t *d_hit_off, uint64_t *total_out, const uint32_t **rows_out,
-                          cudaStream_t st) {
+// ---- locate, stage 1 (asynchronous): candidate-row counts of every range and their exclusive
+// prefix sum.  d_off gets npat+1 entries; d_off[npat] is the number of candidate rows.
+static int locate_counts(const fmx_index *idx, DevBuf *buf, const uint64_t *d_s, const uint64_t *d_e, uint64_t npat,
+                         uint64_t *d_off, cudaStream_t st) {
     int rc;
-    *rows_out = nullptr;
     if (npat >= 0xFFFFFFFFull) return fail(FMX_ERR_UNSUPPORTED, "at most 2^32 - 2 patterns per locate call");
-    if ((rc = idx->buf[B_CNT].ensure((npat + 1) * 8))) return rc;
-    uint64_t *d_cnt = idx->buf[B_CNT].as<uint64_t>();
-    // unfiltered offsets go to d_hit_off directly when there is no filter
-    uint64_t *d_off = d_hit_off;
-    if (prefix_only) {
-        if ((rc = idx->buf[B_HOFF].ensure((npat + 1) * 8))) return rc;
-        d_off = idx->buf[B_HOFF].as<uint64_t>();
-    }
+    if ((rc = buf[B_CNT].ensure((npat + 1) * 8))) return rc;
+    uint64_t *d_cnt = buf[B_CNT].as<uint64_t>();
     if (npat) {
         k_range_counts<<<grid_for(npat, 256), 256, 0, st>>>(d_s, d_e, npat, d_cnt);
         LAUNCH_CHECK();
     }
-    if ((rc = device_scan<uint64_t, uint64_t, OpSum, true>(d_cnt, npat, d_off, OpSum(), true, idx->buf[B_TILES], st))) return rc;
-    uint64_t total = 0;
-    CUDA_TRY(cudaMemcpyAsync(&total, d_off + npat, 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    return device_scan<uint64_t, uint64_t, OpSum, true>(d_cnt, npat, d_off, OpSum(), true, buf[B_TILES], st);
+}
+
+// ---- locate, stage 2: the candidate rows themselves, in pattern order then ascending row order
+// (wrapper.rs:206-216), given their count `total` (= d_off[npat], already read back by the caller).
+// With prefix_only the L == 0 filter (wrapper.rs:208) is applied by flag / scan / compaction and
+// d_hit_off receives the filtered offsets (one stream synchronisation to learn the kept count).
+// Without it d_hit_off must be d_off.  *rows_out points at the hit rows in scratch.
+static int locate_rows(const fmx_index *idx, DevBuf *buf, int prefix_only, const uint64_t *d_s, uint64_t npat,
+                       const uint64_t *d_off, uint64_t total, uint64_t *d_hit_off, uint64_t *hits_out,
+                       const uint32_t **rows_out, cudaStream_t st) {
+    int rc;
+    *rows_out = nullptr;
     if (total >= 0xFFFFFFFFull * 4) return fail(FMX_ERR_UNSUPPORTED, "too many candidate rows in one locate call");
     if (total == 0) {
         if (prefix_only) CUDA_TRY(cudaMemsetAsync(d_hit_off, 0, (npat + 1) * 8, st));
-        *total_out = 0;
+        *hits_out = 0;
         return 0;
     }
-    if ((rc = idx->buf[B_OWNER].ensure(total * 4))) return rc;
-    if ((rc = idx->buf[B_ROWS].ensure(total * 4))) return rc;
-    uint32_t *d_owner = idx->buf[B_OWNER].as<uint32_t>();
-    uint32_t *d_rows = idx->buf[B_ROWS].as<uint32_t>();
+    if ((rc = buf[B_OWNER].ensure(total * 4))) return rc;
+    if ((rc = buf[B_ROWS].ensure(total * 4))) return rc;
+    uint32_t *d_owner = buf[B_OWNER].as<uint32_t>();
+    uint32_t *d_rows = buf[B_ROWS].as<uint32_t>();
     CUDA_TRY(cudaMemsetAsync(d_owner, 0, total * 4, st));
     k_mark_owners<<<grid_for(npat, 256), 256, 0, st>>>(d_off, npat, d_owner);
     LAUNCH_CHECK();
-    if ((rc = device_scan<uint32_t, uint32_t, OpMax, false>(d_owner, total, d_owner, OpMax(), false, idx->buf[B_TILES], st))) return rc;
+    if ((rc = device_scan<uint32_t, uint32_t, OpMax, false>(d_owner, total, d_owner, OpMax(), false, buf[B_TILES], st))) return rc;
     k_expand_rows<<<grid_for(total, 256), 256, 0, st>>>(d_s, d_off, d_owner, total, d_rows);
     LAUNCH_CHECK();
     if (!prefix_only) {
-        *total_out = total;
+        *hits_out = total;
         *rows_out = d_rows;
         return 0;
     }
-    // wrapper.rs:208: keep rows whose L is \0
-    if ((rc = idx->buf[B_FLAG].ensure(total * 4))) return rc;
-    if ((rc = idx->buf[B_FPOS].ensure((total + 1) * 8))) return rc;
-    uint32_t *d_flag = idx->buf[B_FLAG].as<uint32_t>();
-    uint64_t *d_fpos = idx->buf[B_FPOS].as<uint64_t>();
+    if ((rc = buf[B_FLAG].ensure(total * 4))) return rc;
+    if ((rc = buf[B_FPOS].ensure((total + 1) * 8))) return rc;
+    uint32_t *d_flag = buf[B_FLAG].as<uint32_t>();
+    uint64_t *d_fpos = buf[B_FPOS].as<uint64_t>();
     dispatch(idx, [&](auto K, auto LY) { k_flag_prefix<K(), LY()><<<grid_for(total, 256), 256, 0, st>>>(idx->dev, d_rows, total, d_flag); });
     LAUNCH_CHECK();
-    if ((rc = device_scan<uint32_t, uint64_t, OpSum, true>(d_flag, total, d_fpos, OpSum(), true, idx->buf[B_TILES], st))) return rc;
+    if ((rc = device_scan<uint32_t, uint64_t, OpSum, true>(d_flag, total, d_fpos, OpSum(), true, buf[B_TILES], st))) return rc;
     uint64_t kept = 0;
     CUDA_TRY(cudaMemcpyAsync(&kept, d_fpos + total, 8, cudaMemcpyDeviceToHost, st));
     k_filtered_offsets<<<grid_for(npat + 1, 256), 256, 0, st>>>(d_off, d_fpos, npat, d_hit_off);
     LAUNCH_CHECK();
     CUDA_TRY(cudaStreamSynchronize(st));
     if (kept) {
-        if ((rc = idx->buf[B_ROWS2].ensure(kept * 4))) return rc;
-        k_compact_rows<<<grid_for(total, 256), 256, 0, st>>>(d_rows, d_flag, d_fpos, total, idx->buf[B_ROWS2].as<uint32_t>());
+        if ((rc = buf[B_ROWS2].ensure(kept * 4))) return rc;
+        k_compact_rows<<<grid_for(total, 256), 256, 0, st>>>(d_rows, d_flag, d_fpos, total, buf[B_ROWS2].as<uint32_t>());
         LAUNCH_CHECK();
-        *rows_out = idx->buf[B_ROWS2].as<uint32_t>();
+        *rows_out = buf[B_ROWS2].as<uint32_t>();
     }
-    *total_out = kept;
+    *hits_out = kept;
     return 0;
 }
 
+// both stages with a synchronisation in between (the two-phase device API and fmx_locate_batch)
+static int locate_prepare(const fmx_index *idx, int prefix_only, const uint64_t *d_s, const uint64_t *d_e,
+                          uint64_t npat, uint64_t *d_hit_off, uint64_t *total_out, const uint32_t **rows_out,
+                          cudaStream_t st) {
+    int rc;
+    DevBuf *buf = idx->buf;
+    uint64_t *d_off = d_hit_off;  // unfiltered offsets go to d_hit_off directly when there is no filter
+    if (prefix_only) {
+        if ((rc = buf[B_HOFF].ensure((npat + 1) * 8))) return rc;
+        d_off = buf[B_HOFF].as<uint64_t>();
+    }
+    if ((rc = locate_counts(idx, buf, d_s, d_e, npat, d_off, st))) return rc;
+    uint64_t total = 0;
+    CUDA_TRY(cudaMemcpyAsync(&total, d_off + npat, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return locate_rows(idx, buf, prefix_only, d_s, npat, d_off, total, d_hit_off, total_out, rows_out, st);
+}
+
 static int locate_fill(const fmx_index *idx, const uint32_t *d_rows, uint64_t total, uint64_t *d_pos, uint64_t *d_pid,
-                       cudaStream_t st) {
-    CUDA_TRY(cudaMemsetAsync(idx->d_work + 1, 0, sizeof(unsigned long long), st));
+                       cudaStream_t st, bool count_work = true) {
+    if (count_work) CUDA_TRY(cudaMemsetAsync(idx->d_work + 1, 0, sizeof(unsigned long long), st));
     if (total == 0) return 0;
     LocateArgs a;
     a.rows = d_rows;
     a.total = total;
     a.positions = d_pos;
     a.piece_ids = d_pid;
-    a.work = idx->d_work;
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, idx->device);
+    a.work = count_work ? idx->d_work : nullptr;
     uint64_t blocks = (total + 255) / 256;
-    uint64_t cap = (uint64_t)sms * 8 * 8;
+    uint64_t cap = (uint64_t)idx->sms * 8 * 8;
     if (blocks > cap) blocks = cap;
     dispatch(idx, [&](auto K, auto LY) { k_locate<K(), LY()><<<(unsigned)blocks, 256, 0, st>>>(idx->dev, a); });
     LAUNCH_CHECK();
@@ -712,6 +749,131 @@ extern "C" int fmx_locate_batch(const fmx_index *idx, int prefix_only, const uin
     CUDA_TRY(cudaStreamSynchronize(st));
     if (positions) *positions = h_pos;
     if (piece_ids) *piece_ids = h_pid;
+    return FMX_OK;
+}
+
+// ------------------------------------------------------------------ fused, pipelined search + locate
+
+static int ensure_lanes(const fmx_index *idx) {
+    if (idx->lanes_ready) return 0;
+    for (auto &l : idx->lane) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&l.st, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&l.ev, cudaEventDisableTiming));
+        CUDA_TRY(cudaMallocHost(reinterpret_cast<void **>(&l.h_total), 64));
+    }
+    idx->lanes_ready = true;
+    return 0;
+}
+
+extern "C" int fmx_search_locate_batch(const fmx_index *idx, int mode, const uint8_t *pat, const uint64_t *pat_off,
+                                       uint64_t fixed_len, uint64_t npat, uint64_t *out_s, uint64_t *out_e,
+                                       uint64_t *hit_off, uint64_t *positions, uint64_t *piece_ids, uint64_t capacity,
+                                       uint64_t *total_hits) {
+    if (!idx || !hit_off || !total_hits) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    const bool want_hits = positions != nullptr || piece_ids != nullptr;
+    int rc;
+    if (want_hits && (rc = locate_args_ok(idx, piece_ids != nullptr))) return rc;
+    *total_hits = 0;
+    hit_off[0] = 0;
+    if (npat == 0) return FMX_OK;
+    uint64_t pat_bytes = pat_off ? pat_off[npat] : npat * fixed_len;
+    if (pat_bytes && !pat) return fail(FMX_ERR_INVALID_ARG, "null pattern buffer");
+    std::lock_guard<std::mutex> lk(idx->mu);
+    CUDA_TRY(cudaSetDevice(idx->device));
+    if ((rc = ensure_lanes(idx))) return rc;
+    const int prefix_only = (mode == FMX_SEARCH_PREFIX || mode == FMX_SEARCH_EXACT) ? 1 : 0;
+    // chunks: enough of them to overlap copies with kernels, big enough to fill the GPU
+    uint64_t chunk = (npat + 3) / 4;
+    if (chunk < (1ull << 16)) chunk = 1ull << 16;
+    if (chunk > (1ull << 23)) chunk = 1ull << 23;
+    if (idx->opt_pipeline_chunk) chunk = idx->opt_pipeline_chunk;
+    const uint64_t nchunks = (npat + chunk - 1) / chunk;
+    uint64_t running = 0;
+    bool overflow = false;
+
+    auto stage1 = [&](uint64_t c) -> int {  // H2D patterns, search, candidate counts (all asynchronous)
+        Lane &L = idx->lane[c & 1];
+        const uint64_t lo = c * chunk, n = (lo + chunk < npat ? chunk : npat - lo);
+        const uint64_t off0 = pat_off ? pat_off[lo] : lo * fixed_len;
+        const uint64_t nbytes = (pat_off ? pat_off[lo + n] : (lo + n) * fixed_len) - off0;
+        int r;
+        if ((r = L.buf[B_PAT].ensure(nbytes + 16))) return r;
+        if ((r = L.buf[B_S].ensure(n * 8))) return r;
+        if ((r = L.buf[B_E].ensure(n * 8))) return r;
+        if ((r = L.buf[B_HOFF].ensure((n + 1) * 8))) return r;
+        if (nbytes) CUDA_TRY(cudaMemcpyAsync(L.buf[B_PAT].p, pat + off0, nbytes, cudaMemcpyHostToDevice, L.st));
+        const uint8_t *d_pat = L.buf[B_PAT].as<uint8_t>();
+        const uint64_t *d_off = nullptr;
+        if (pat_off) {
+            if ((r = L.buf[B_OFF].ensure((n + 1) * 8))) return r;
+            CUDA_TRY(cudaMemcpyAsync(L.buf[B_OFF].p, pat_off + lo, (n + 1) * 8, cudaMemcpyHostToDevice, L.st));
+            d_off = L.buf[B_OFF].as<uint64_t>();
+            d_pat -= off0;  // the kernel adds the batch-global byte offsets
+        }
+        uint64_t *d_s = L.buf[B_S].as<uint64_t>(), *d_e = L.buf[B_E].as<uint64_t>();
+        if ((r = search_device(idx, mode, d_pat, d_off, fixed_len, n, nullptr, nullptr, d_s, d_e, L.st, false, true))) return r;
+        if (out_s) CUDA_TRY(cudaMemcpyAsync(out_s + lo, d_s, n * 8, cudaMemcpyDeviceToHost, L.st));
+        if (out_e) CUDA_TRY(cudaMemcpyAsync(out_e + lo, d_e, n * 8, cudaMemcpyDeviceToHost, L.st));
+        uint64_t *d_unf = L.buf[B_HOFF].as<uint64_t>();
+        if ((r = locate_counts(idx, L.buf, d_s, d_e, n, d_unf, L.st))) return r;
+        CUDA_TRY(cudaMemcpyAsync(L.h_total, d_unf + n, 8, cudaMemcpyDeviceToHost, L.st));
+        CUDA_TRY(cudaEventRecord(L.ev, L.st));
+        return 0;
+    };
+    auto stage2 = [&](uint64_t c) -> int {  // rows, LF walks, D2H of offsets and positions
+        Lane &L = idx->lane[c & 1];
+        const uint64_t lo = c * chunk, n = (lo + chunk < npat ? chunk : npat - lo);
+        CUDA_TRY(cudaEventSynchronize(L.ev));
+        const uint64_t cand = *L.h_total;
+        int r;
+        uint64_t *d_s = L.buf[B_S].as<uint64_t>();
+        uint64_t *d_unf = L.buf[B_HOFF].as<uint64_t>();
+        uint64_t *d_src = d_unf;
+        uint64_t hits = cand;
+        const uint32_t *rows = nullptr;
+        if (want_hits || prefix_only) {
+            if (prefix_only) {
+                if ((r = L.buf[B_INE].ensure((n + 1) * 8))) return r;
+                d_src = L.buf[B_INE].as<uint64_t>();
+            }
+            if ((r = locate_rows(idx, L.buf, prefix_only, d_s, n, d_unf, cand, d_src, &hits, &rows, L.st))) return r;
+        }
+        if ((r = L.buf[B_INS].ensure((n + 1) * 8))) return r;
+        uint64_t *d_final = L.buf[B_INS].as<uint64_t>();
+        k_add_base<<<grid_for(n + 1, 256), 256, 0, L.st>>>(d_src, n + 1, running, d_final);
+        LAUNCH_CHECK();
+        CUDA_TRY(cudaMemcpyAsync(hit_off + lo, d_final, (n + 1) * 8, cudaMemcpyDeviceToHost, L.st));
+        if (want_hits && hits) {
+            if (running + hits > capacity) {
+                overflow = true;
+            } else if (!overflow) {
+                uint64_t *d_pos = nullptr, *d_pid = nullptr;
+                if (positions) {
+                    if ((r = L.buf[B_POS].ensure(hits * 8))) return r;
+                    d_pos = L.buf[B_POS].as<uint64_t>();
+                }
+                if (piece_ids) {
+                    if ((r = L.buf[B_PID].ensure(hits * 8))) return r;
+                    d_pid = L.buf[B_PID].as<uint64_t>();
+                }
+                if ((r = locate_fill(idx, rows, hits, d_pos, d_pid, L.st, false))) return r;
+                if (positions) CUDA_TRY(cudaMemcpyAsync(positions + running, d_pos, hits * 8, cudaMemcpyDeviceToHost, L.st));
+                if (piece_ids) CUDA_TRY(cudaMemcpyAsync(piece_ids + running, d_pid, hits * 8, cudaMemcpyDeviceToHost, L.st));
+            }
+        }
+        running += hits;
+        return 0;
+    };
+    rc = 0;
+    for (uint64_t c = 0; c <= nchunks && rc == 0; c++) {
+        if (c < nchunks) rc = stage1(c);
+        if (rc == 0 && c >= 1) rc = stage2(c - 1);
+    }
+    for (auto &l : idx->lane) cudaStreamSynchronize(l.st);
+    if (rc) return rc;
+    *total_hits = running;
+    if ((rc = check_err_flag(idx, idx->lane[0].st))) return rc;
+    if (overflow) return fail(FMX_ERR_CAPACITY, "positions buffer too small: total_hits holds the size needed");
     return FMX_OK;
 }
 

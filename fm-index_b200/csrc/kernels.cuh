@@ -823,6 +823,12 @@ __global__ void k_compact_rows(const uint32_t *rows, const uint32_t *flag, const
     if (h < total && flag[h]) out_rows[fpos[h]] = rows[h];
 }
 
+// out[i] = in[i] + base (chunked pipelines: chunk-local hit offsets -> batch-global ones)
+__global__ void k_add_base(const uint64_t *in, uint64_t n, uint64_t base, uint64_t *out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] + base;
+}
+
 // filtered hit offsets: hit_off[p] = fpos[off[p]]  (fpos has total+1 entries)
 __global__ void k_filtered_offsets(const uint64_t *off, const uint64_t *fpos, uint64_t npat, uint64_t *hit_off) {
     uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -43,7 +43,8 @@ typedef enum fmx_status {
     FMX_ERR_PATTERN_CHAR = -5,  /* a processed pattern char > max_character: the reference panics (fm_index.rs:94) */
     FMX_ERR_OOM = -6,
     FMX_ERR_UNSUPPORTED = -7,
-    FMX_ERR_IO = -8
+    FMX_ERR_IO = -8,
+    FMX_ERR_CAPACITY = -9       /* caller-provided output buffer too small */
 } fmx_status;
 
 /* src/frontend.rs:110-193: the three backends; locate support is chosen by `level` */
@@ -93,7 +94,8 @@ int fmx_build_suffix_array(const void *text, uint64_t n, uint32_t char_width, ui
 
 /* Tuning knobs (A/B measurement; results never change): "search_persistent" 0|1 (persistent
  * per-lane-refill search kernels instead of one pattern per thread), "kmer" 0|1 (memoised first
- * search iterations), "persist_blocks_per_sm" 1..32.  The environment variable
+ * search iterations), "persist_blocks_per_sm" 1..32, "pipeline_chunk" (patterns per chunk of
+ * fmx_search_locate_batch's copy/compute pipeline, 0 = automatic).  The environment variable
  * FMX_FORCE_WAVELET=1 makes construction keep the binary wavelet matrix for small alphabets. */
 int fmx_index_set_option(fmx_index *idx, const char *key, int64_t value);
 
@@ -107,6 +109,9 @@ int fmx_index_has_locate(const fmx_index *idx);
 int fmx_index_device(const fmx_index *idx);
 uint32_t fmx_index_wavelet_levels(const fmx_index *idx); /* Text::max_bits, text.rs:61-63 */
 uint32_t fmx_index_sample_level(const fmx_index *idx);
+/* 32-byte sectors one rank/access probe of the BWT touches in this index's device layout:
+ * L for the binary wavelet matrix, 1 for the quaternary level used when max_character <= 4. */
+uint32_t fmx_index_sectors_per_rank(const fmx_index *idx);
 
 /* ---------------------------------------------------------------- search / count
  * Batched SearchIndex::search / search_prefix / search_suffix / search_exact and
@@ -139,6 +144,20 @@ int fmx_search_check(const fmx_index *idx, void *stream);
  * receive hit_off[npat] values each and are released with fmx_free(). */
 int fmx_locate_batch(const fmx_index *idx, int prefix_only, const uint64_t *s, const uint64_t *e,
                      uint64_t npat, uint64_t *hit_off, uint64_t **positions, uint64_t **piece_ids);
+/* Fused search + locate for host buffers: the batched form of
+ *     index.search(p).iter_matches().map(|m| m.locate())           (README.md:49-64)
+ * in ONE call.  The batch is cut into chunks that flow through a two-lane pipeline (H2D copy of
+ * chunk k+1 overlaps the kernels of chunk k and the D2H copy of chunk k-1); SA ranges never make
+ * the round trip to the host in between.  out_s / out_e (nullable) receive the SA ranges,
+ * hit_off (npat+1) the exclusive prefix sum of hit counts, positions / piece_ids (nullable,
+ * caller-owned, `capacity` entries each) the matches in the reference's iteration order.
+ * If the batch has more hits than `capacity`, returns FMX_ERR_CAPACITY with hit_off and
+ * *total_hits filled so the caller can size the buffers and use fmx_locate_batch.
+ * Pinned (page-locked) host buffers make the copies asynchronous; pageable ones work too. */
+int fmx_search_locate_batch(const fmx_index *idx, int mode, const uint8_t *pat, const uint64_t *pat_off,
+                            uint64_t fixed_len, uint64_t npat, uint64_t *out_s, uint64_t *out_e,
+                            uint64_t *hit_off, uint64_t *positions, uint64_t *piece_ids,
+                            uint64_t capacity, uint64_t *total_hits);
 /* two-phase device form: count (synchronous, returns the total), then fill (async). */
 int fmx_locate_count_device(const fmx_index *idx, int prefix_only, const uint64_t *d_s,
                             const uint64_t *d_e, uint64_t npat, uint64_t *d_hit_off,

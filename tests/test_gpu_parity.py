@@ -364,3 +364,41 @@ def test_config2_full_size_properties():
     # checksum of checksums: the batch split in two halves gives the same answers
     b1, b2 = index.search_batch(pats[: npat // 2]), index.search_batch(pats[npat // 2:])
     assert np.array_equal(np.concatenate([b1.s, b2.s]), b.s) and np.array_equal(np.concatenate([b1.e, b2.e]), b.e)
+
+
+# ---- the fused, pipelined entry (fmx_search_locate_batch) must agree with the two-call path
+@pytest.mark.parametrize("kind", [orc.FM, orc.RLFM, orc.MULTI])
+def test_fused_search_locate_matches_two_phase(kind):
+    rng = np.random.default_rng(300 + kind)
+    if kind == orc.MULTI:
+        text = np.concatenate([np.append(rng.integers(1, 5, int(l), dtype=np.uint8), np.uint8(0))
+                               for l in rng.integers(10_000, 30_000, 12)])
+    else:
+        text = dna(300_000, 31 + kind)
+    npat = 50_000
+    pats, _ = mixed_patterns(text, npat, 24, 9)
+    index = KINDS[kind][1].new(fmx.Text.with_max_character(text, 4), 2)
+    index.set_option("pipeline_chunk", 7_001)    # 8 ragged chunks: exercises both pipeline lanes
+    modes = [fmx.SEARCH] + ([fmx.SEARCH_PREFIX, fmx.SEARCH_SUFFIX, fmx.SEARCH_EXACT] if kind == orc.MULTI else [])
+    for mode in modes:
+        ref = index.search_batch(pats, mode)
+        if kind == orc.MULTI:
+            rh, rp, rd = ref.locate(piece_ids=True)
+            b, h, p, d = index.search_locate_batch(pats, mode, piece_ids=True)
+            assert np.array_equal(d, rd)
+        else:
+            rh, rp = ref.locate()
+            b, h, p = index.search_locate_batch(pats, mode)
+        assert np.array_equal(b.s, ref.s) and np.array_equal(b.e, ref.e)
+        assert np.array_equal(h, rh) and np.array_equal(p, rp)
+    # ragged patterns + a capacity that is too small (falls back to exact-size buffers)
+    lens = rng.integers(1, 40, 40_000)
+    flat = rng.integers(1, 5, int(lens.sum()), dtype=np.uint8)
+    off = np.zeros(lens.size + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(lens)
+    ref = index.search_batch((flat, off))
+    rh, rp = ref.locate()
+    b, h, p = index.search_locate_batch((flat, off), capacity=1000)
+    assert np.array_equal(b.s, ref.s) and np.array_equal(h, rh) and np.array_equal(p, rp)
+    b, h, p = index.search_locate_batch((flat, off), capacity=int(rh[-1]) + 5)
+    assert np.array_equal(b.e, ref.e) and np.array_equal(h, rh) and np.array_equal(p, rp)

@@ -458,6 +458,16 @@ def suffix_array(text) -> np.ndarray:
     return sa[: t.size]
 
 
+def suffix_array_device(text, max_character=255, device=0):
+    """The same suffix array built on the GPU (gpu_sa.cu). -> (sa, doubling rounds)"""
+    t = _as_u8(text)
+    sa = np.zeros(max(t.size, 1), dtype=np.uint64)
+    rounds = C.c_int(0)
+    _check(load_library().fmx_build_suffix_array_device(_ptr(t), t.size, 1, max_character, device, _ptr(sa),
+                                                        C.byref(rounds)))
+    return sa[: t.size], rounds.value
+
+
 def blob_build(text: Text, kind, level=None) -> np.ndarray:
     """Host-only half of construction: the device-layout blob as bytes."""
     L = load_library()

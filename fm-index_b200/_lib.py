@@ -23,6 +23,7 @@ SIGNATURES = {
     "fmx_index_load": (_int, [C.c_char_p, _int, _pp]),
     "fmx_index_free": (None, [_vp]),
     "fmx_build_suffix_array": (_int, [_vp, _u64, _u32, _vp]),
+    "fmx_build_suffix_array_device": (_int, [_vp, _u64, _u32, _u64, _int, _vp, C.POINTER(C.c_int)]),
     "fmx_index_set_option": (_int, [_vp, C.c_char_p, C.c_int64]),
     "fmx_index_len": (_u64, [_vp]),
     "fmx_index_device_bytes": (_u64, [_vp]),

@@ -117,20 +117,35 @@ static void build_wavelet(const uint8_t *seq, uint64_t n, uint32_t L, WMat &m) {
     m.lv.clear();
     m.zeros.assign(L, 0);
     std::vector<uint8_t> cur(seq, seq + n), nxt(n);
+    // chunks of whole rank blocks so that threads never share a payload word
+    const uint64_t chunk = (uint64_t)FMX_RB_BITS * 4096;
+    const int64_t nchunks = (int64_t)((n + chunk - 1) / chunk);
+    std::vector<uint64_t> zc((size_t)nchunks + 1, 0);
     for (uint32_t l = 0; l < L; l++) {
         uint32_t sh = L - 1 - l;
         m.lv.emplace_back(n);
         RBVec &v = m.lv.back();
-        uint64_t z = 0;
-        for (uint64_t i = 0; i < n; i++) {
-            if ((cur[i] >> sh) & 1) v.set(i); else z++;
+#pragma omp parallel for schedule(static)
+        for (int64_t c = 0; c < nchunks; c++) {
+            uint64_t lo = (uint64_t)c * chunk, hi = lo + chunk < n ? lo + chunk : n, z = 0;
+            for (uint64_t i = lo; i < hi; i++) {
+                if ((cur[i] >> sh) & 1) v.set(i); else z++;
+            }
+            zc[(size_t)c + 1] = z;
         }
         v.finish();
+        zc[0] = 0;
+        for (int64_t c = 0; c < nchunks; c++) zc[(size_t)c + 1] += zc[(size_t)c];
+        uint64_t z = zc[(size_t)nchunks];
         m.zeros[l] = z;
         if (l + 1 < L) {
-            uint64_t p0 = 0, p1 = z;
-            for (uint64_t i = 0; i < n; i++) {
-                if ((cur[i] >> sh) & 1) nxt[p1++] = cur[i]; else nxt[p0++] = cur[i];
+#pragma omp parallel for schedule(static)
+            for (int64_t c = 0; c < nchunks; c++) {
+                uint64_t lo = (uint64_t)c * chunk, hi = lo + chunk < n ? lo + chunk : n;
+                uint64_t p0 = zc[(size_t)c], p1 = z + (lo - zc[(size_t)c]);
+                for (uint64_t i = lo; i < hi; i++) {
+                    if ((cur[i] >> sh) & 1) nxt[p1++] = cur[i]; else nxt[p0++] = cur[i];
+                }
             }
             cur.swap(nxt);
         }
@@ -142,23 +157,36 @@ struct Q4Vec {
     std::vector<uint32_t> w;
     std::vector<uint32_t> exc;
     void build(const uint8_t *seq, uint64_t n) {
-        uint64_t nblk = n / 64 + 1;
+        const uint64_t nblk = n / 64 + 1;
         w.assign(nblk * 8, 0);
         exc.clear();
-        uint32_t cnt[4] = {0, 0, 0, 0};
-        for (uint64_t b = 0; b < nblk; b++) {
-            uint32_t *blk = &w[b * 8];
-            for (int c = 0; c < 4; c++) blk[c] = cnt[c];
-            uint64_t lo = b * 64, hi = lo + 64 < n ? lo + 64 : n;
+        // pass 1: payload + per-block code counts (independent per block)
+#pragma omp parallel for schedule(static)
+        for (int64_t b = 0; b < (int64_t)nblk; b++) {
+            uint32_t *blk = &w[(uint64_t)b * 8];
+            uint32_t cnt[4] = {0, 0, 0, 0};
+            uint64_t lo = (uint64_t)b * 64, hi = lo + 64 < n ? lo + 64 : n;
             for (uint64_t i = lo; i < hi; i++) {
                 uint32_t sym = seq[i];
-                if (sym == 0) exc.push_back((uint32_t)i);
                 uint32_t code = sym ? sym - 1 : 0;
                 uint32_t t = (uint32_t)(i - lo);
                 blk[4 + (t >> 4)] |= code << (2 * (t & 15));
                 cnt[code]++;
             }
+            for (int c = 0; c < 4; c++) blk[c] = cnt[c];
         }
+        // pass 2: exclusive prefix of the counts
+        uint32_t acc[4] = {0, 0, 0, 0};
+        for (uint64_t b = 0; b < nblk; b++) {
+            uint32_t *blk = &w[b * 8];
+            for (int c = 0; c < 4; c++) {
+                uint32_t v = blk[c];
+                blk[c] = acc[c];
+                acc[c] += v;
+            }
+        }
+        for (uint64_t i = 0; i < n; i++)
+            if (seq[i] == 0) exc.push_back((uint32_t)i);
     }
 };
 
@@ -177,7 +205,7 @@ struct SectionData {
 };
 
 int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level,
-               std::vector<uint8_t> &blob, std::string &err) {
+               std::vector<uint8_t> &blob, std::string &err, int sa_device) {
     if (mc == 0 || mc > 255) {
         err = "max_character must be in 1..=255 for u8 texts";
         return FMX_ERR_INVALID_ARG;
@@ -190,8 +218,11 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
         err = "text length must be below 2^32 - 1 (u32 rank counts in the device layout)";
         return FMX_ERR_UNSUPPORTED;
     }
-    for (uint64_t i = 0; i < n; i++) {
-        if (text[i] > mc) {  // sais.rs:16-18 would index occs out of bounds (panic)
+    {
+        int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+        for (int64_t i = 0; i < (int64_t)n; i++) bad |= text[i] > mc;
+        if (bad) {  // sais.rs:16-18 would index occs out of bounds (panic)
             err = "text contains a character larger than max_character";
             return FMX_ERR_INVALID_ARG;
         }
@@ -203,7 +234,21 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
     const uint32_t cs_len = (uint32_t)mc + 1;
 
     std::vector<uint32_t> sa;
-    suffix_array_u32(text, n, sa);
+    {
+        const char *host_only = std::getenv("FMX_HOST_SA");
+        bool use_gpu = sa_device >= 0 && n >= (1u << 16) && !(host_only && host_only[0] && host_only[0] != '0');
+        if (use_gpu) {
+            sa.resize(n);
+            std::string gerr;
+            int grc = gpu_suffix_array(text, n, L, sa_device, sa.data(), nullptr, gerr);
+            if (grc) {
+                err = "GPU suffix array construction failed: " + gerr;
+                return grc;
+            }
+        } else {
+            suffix_array_u32(text, n, sa);
+        }
+    }
 
     // BWT: bw[i] = text[sa[i]-1], 0 when sa[i] == 0 (fm_index.rs:48-55; rlfmi.rs:49-53 uses
     // text[n-1] there, which is the same \0 for every text that passes validation with n >= 2)

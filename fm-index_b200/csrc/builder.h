@@ -10,8 +10,14 @@ namespace fmx {
 
 // Returns 0 or a negative fmx_status; on failure `err` holds the message
 // (for invalid texts: the reference's Error::InvalidText strings, sais.rs:128-139).
+// sa_device >= 0: build the suffix array on that GPU (gpu_sa.cu) when the text is large enough,
+// otherwise with the host SA-IS.  The blob is byte-identical either way.
 int build_blob(const uint8_t *text, uint64_t n, uint64_t max_character, int kind, int level,
-               std::vector<uint8_t> &blob, std::string &err);
+               std::vector<uint8_t> &blob, std::string &err, int sa_device = -1);
+
+// gpu_sa.cu
+int gpu_suffix_array(const uint8_t *text, uint64_t n, uint32_t bits, int device, uint32_t *sa_out, int *rounds_out,
+                     std::string &err);
 
 // sais.rs:115-144 (validation + suffix array)
 int build_suffix_array(const uint8_t *text, uint64_t n, uint64_t *sa_out, std::string &err);

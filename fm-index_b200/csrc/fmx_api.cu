@@ -142,6 +142,23 @@ int fmx_build_suffix_array(const void *text, uint64_t n, uint32_t char_width, ui
     return rc ? fail(rc, err) : FMX_OK;
 }
 
+int fmx_build_suffix_array_device(const void *text, uint64_t n, uint32_t char_width, uint64_t max_character, int device,
+                                  uint64_t *sa_out, int *rounds) {
+    if (char_width != 1) return fail(FMX_ERR_UNSUPPORTED, "only u8 texts (char_width == 1) are supported");
+    if (max_character == 0 || max_character > 255) return fail(FMX_ERR_INVALID_ARG, "max_character must be in 1..=255");
+    if ((!text || !sa_out) && n) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    const uint8_t *t = static_cast<const uint8_t *>(text);
+    for (uint64_t i = 0; i < n; i++)
+        if (t[i] > max_character) return fail(FMX_ERR_INVALID_ARG, "text contains a character larger than max_character");
+    uint32_t bits = 64 - (uint32_t)__builtin_clzll(max_character);
+    std::vector<uint32_t> sa(n);
+    std::string err;
+    int rc = gpu_suffix_array(t, n, bits, device, sa.data(), rounds, err);
+    if (rc) return fail(rc, err);
+    for (uint64_t i = 0; i < n; i++) sa_out[i] = sa[i];
+    return FMX_OK;
+}
+
 int fmx_blob_build(const void *text, uint64_t n, uint32_t char_width, uint64_t max_character, int kind, int level,
                    void **blob, uint64_t *blob_bytes) {
     if (!blob || !blob_bytes || (!text && n)) return fail(FMX_ERR_INVALID_ARG, "null argument");
@@ -245,9 +262,15 @@ int fmx_index_build(const void *text, uint64_t n, uint32_t char_width, uint64_t 
                     int device, fmx_index **out) {
     if (!out || (!text && n)) return fail(FMX_ERR_INVALID_ARG, "null argument");
     if (char_width != 1) return fail(FMX_ERR_UNSUPPORTED, "only u8 texts (char_width == 1) are supported");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(FMX_ERR_CUDA, "no CUDA device available (the engine has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(FMX_ERR_INVALID_ARG, "device ordinal out of range");
     std::vector<uint8_t> b;
     std::string err;
-    int rc = build_blob(static_cast<const uint8_t *>(text), n, max_character, kind, level, b, err);
+    int rc = build_blob(static_cast<const uint8_t *>(text), n, max_character, kind, level, b, err, device);
     if (rc) return fail(rc, err);
     return upload(std::move(b), device, out);
 }

@@ -91,6 +91,11 @@ void fmx_index_free(fmx_index *idx);
 
 /* Suffix array of a text exactly as sais::build_suffix_array (sais.rs:115-144) returns it. */
 int fmx_build_suffix_array(const void *text, uint64_t n, uint32_t char_width, uint64_t *sa_out);
+/* The same suffix array built on the GPU (prefix doubling over radix sorts; what fmx_index_build
+ * uses for texts of 2^16 symbols and more, FMX_HOST_SA=1 disables).  No text validation.
+ * *rounds (nullable) receives the number of doubling rounds. */
+int fmx_build_suffix_array_device(const void *text, uint64_t n, uint32_t char_width, uint64_t max_character,
+                                  int device, uint64_t *sa_out, int *rounds);
 
 /* Tuning knobs (A/B measurement; results never change): "search_persistent" 0|1 (persistent
  * per-lane-refill search kernels instead of one pattern per thread), "kmer" 0|1 (memoised first

@@ -402,3 +402,39 @@ def test_fused_search_locate_matches_two_phase(kind):
     assert np.array_equal(b.s, ref.s) and np.array_equal(h, rh) and np.array_equal(p, rp)
     b, h, p = index.search_locate_batch((flat, off), capacity=int(rh[-1]) + 5)
     assert np.array_equal(b.e, ref.e) and np.array_equal(h, rh) and np.array_equal(p, rp)
+
+
+# ---- index construction on the GPU (gpu_sa.cu): same suffix array, byte-identical blob
+def test_gpu_suffix_array_matches_oracle():
+    rng = np.random.default_rng(404)
+    cases = []
+    for t in range(12):
+        n = int(rng.integers(2, 5000))
+        mc = int(rng.choice([1, 4, 7, 255]))
+        cases.append((build_text(rng, n, min(mc + 1, 256) if t & 1 else max(2, min(mc, 255)), bool(t & 1)), mc))
+    cases.append((bytes([3, 0, 0, 0, 2, 0, 0, 1, 0]), 3))                        # runs of \0 inside the text
+    cases.append((bytes([1] * 3000 + [0]), 1))                                     # one long run: many doubling rounds
+    rep = build_text(rng, 4000, 4, False)[:-1]
+    cases.append((rep * 50 + b"\0", 4))                                            # highly repetitive
+    cases.append((dna(400_000, 8).tobytes(), 4))
+    cases.append((np.append(rng.integers(1, 256, 300_000, dtype=np.uint8), np.uint8(0)).tobytes(), 255))
+    for text, mc in cases:
+        mc = max(mc, max(text))
+        sa, rounds = fmx.suffix_array_device(text, mc)
+        assert np.array_equal(sa, orc.suffix_array(text)), (len(text), mc, rounds)
+
+
+@pytest.mark.parametrize("kind", [orc.FM, orc.RLFM, orc.MULTI])
+def test_gpu_built_blob_identical_to_host_built(kind, tmp_path):
+    rng = np.random.default_rng(500 + kind)
+    if kind == orc.MULTI:
+        text = np.concatenate([np.append(rng.integers(1, 5, int(l), dtype=np.uint8), np.uint8(0))
+                               for l in rng.integers(5_000, 40_000, 9)])
+    else:
+        text = dna(200_000, 60 + kind)
+    t = fmx.Text.with_max_character(text, 4)
+    index = KINDS[kind][1].new(t, 2)                 # >= 2^16 symbols: suffix array built on the GPU
+    p = tmp_path / "gpu_built.fmx"
+    index.save(p)
+    host = fmx.blob_build(t, kind, 2)                # host SA-IS
+    assert np.array_equal(np.fromfile(p, dtype=np.uint8), host)

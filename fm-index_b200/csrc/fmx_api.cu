@@ -62,7 +62,7 @@ struct DevBuf {
     T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-enum { B_QUEUE, B_PAT, B_OFF, B_S, B_E, B_INS, B_INE, B_CNT, B_HOFF, B_OWNER, B_ROWS, B_ROWS2, B_FLAG, B_FPOS, B_TILES, B_POS, B_PID,
+enum { B_QUEUE, B_BUCKET, B_BHIST, B_ORDER, B_PAT, B_OFF, B_S, B_E, B_INS, B_INE, B_CNT, B_HOFF, B_OWNER, B_ROWS, B_ROWS2, B_FLAG, B_FPOS, B_TILES, B_POS, B_PID,
        B_OUT8, B_OUT32, B_COUNT };
 
 // one lane of the chunked H2D / kernels / D2H pipeline (fmx_search_locate_batch)
@@ -92,6 +92,7 @@ struct fmx_index {
     int opt_persistent = 0;  // 1: persistent refill search kernels instead of one pattern per thread
     int opt_kmer = 1;
     uint64_t opt_pipeline_chunk = 0;  // patterns per pipeline chunk (0 = automatic)
+    int opt_bucket = 0;               // 1: visit the batch in k-mer bucket order (lost the A/B, kept for experiments); -1 auto
     mutable DevBuf buf[B_COUNT];
     mutable Lane lane[2];
     mutable bool lanes_ready = false;
@@ -321,7 +322,13 @@ int fmx_index_set_option(fmx_index *idx, const char *key, int64_t value) {
     std::string k(key);
     if (k == "search_persistent") idx->opt_persistent = value != 0;
     else if (k == "kmer") idx->opt_kmer = value != 0;
+    else if (k == "bucket") idx->opt_bucket = value < 0 ? -1 : (value != 0);
     else if (k == "pipeline_chunk") idx->opt_pipeline_chunk = value > 0 ? (uint64_t)value : 0;
+    else if (k == "l2_fetch_granularity") {
+        if (value != 32 && value != 64 && value != 128) return fail(FMX_ERR_INVALID_ARG, "l2_fetch_granularity must be 32, 64 or 128");
+        CUDA_TRY(cudaSetDevice(idx->device));
+        CUDA_TRY(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
+    }
     else if (k == "persist_blocks_per_sm") {
         if (value < 1 || value > 32) return fail(FMX_ERR_INVALID_ARG, "persist_blocks_per_sm out of range");
         idx->persist_blocks_per_sm = (int)value;
@@ -400,9 +407,37 @@ static bool env_flag(const char *name) {
     return v && v[0] && v[0] != '0';
 }
 
-static int dispatch_search(const fmx_index *idx, const SearchArgs &a, cudaStream_t st, bool force_simple = false) {
-    if (a.npat == 0) return 0;
+// k-mer bucketing of the batch (see SearchArgs::order): histogram, exclusive scan, scatter
+static int bucket_patterns(const fmx_index *idx, DevBuf *buf, SearchArgs &a, cudaStream_t st) {
+    const uint64_t nb = idx->kmer_entries + 1;
+    int rc;
+    if ((rc = buf[B_BUCKET].ensure(a.npat * 4))) return rc;
+    if ((rc = buf[B_BHIST].ensure((nb + 1) * 4))) return rc;
+    if ((rc = buf[B_ORDER].ensure(a.npat * 4))) return rc;
+    uint32_t *d_bucket = buf[B_BUCKET].as<uint32_t>(), *d_hist = buf[B_BHIST].as<uint32_t>();
+    CUDA_TRY(cudaMemsetAsync(d_hist, 0, (nb + 1) * 4, st));
+    k_bucket_count<<<grid_for(a.npat, 256), 256, 0, st>>>(a, idx->hdr.cs_len, idx->hdr.max_character,
+                                                          (uint32_t)idx->kmer_entries, d_bucket, d_hist);
+    LAUNCH_CHECK();
+    if ((rc = device_scan<uint32_t, uint32_t, OpSum, true>(d_hist, nb, d_hist, OpSum(), false, buf[B_TILES], st))) return rc;
+    k_bucket_scatter<<<grid_for(a.npat, 256), 256, 0, st>>>(d_bucket, a.npat, d_hist, buf[B_ORDER].as<uint32_t>());
+    LAUNCH_CHECK();
+    a.order = buf[B_ORDER].as<uint32_t>();
+    return 0;
+}
+
+static int dispatch_search(const fmx_index *idx, const SearchArgs &a_in, cudaStream_t st, bool force_simple = false,
+                           DevBuf *buf = nullptr) {
+    if (a_in.npat == 0) return 0;
+    SearchArgs a = a_in;
+    if (!buf) buf = idx->buf;
     if (force_simple || !idx->opt_persistent) {
+        // big batches over an index that does not fit L2: visit the index in SA order
+        const bool big = idx->hdr.total_bytes > (96ull << 20) && a.npat >= (1ull << 18);
+        if (a.kmer_tab && a.npat < 0xFFFFFFFFull && !a.steps_out && (idx->opt_bucket == 1 || (idx->opt_bucket < 0 && big))) {
+            int rc = bucket_patterns(idx, buf, a, st);
+            if (rc) return rc;
+        }
         uint64_t blocks = (a.npat + 255) / 256;
         uint64_t cap = (uint64_t)idx->sms * 8 * 8;  // grid-stride beyond 8 waves of 8 CTAs/SM
         if (blocks > cap) blocks = cap;
@@ -483,7 +518,7 @@ static int build_kmer_table(fmx_index *idx) {
 static int search_device(const fmx_index *idx, int mode, const uint8_t *d_pat, const uint64_t *d_pat_off,
                          uint64_t fixed_len, uint64_t npat, const uint64_t *d_is, const uint64_t *d_ie,
                          uint64_t *d_os, uint64_t *d_oe, cudaStream_t st, bool count_work = true,
-                         bool force_simple = false) {
+                         bool force_simple = false, DevBuf *buf = nullptr) {
     if (mode < FMX_SEARCH || mode > FMX_SEARCH_EXACT) return fail(FMX_ERR_INVALID_ARG, "bad search mode");
     if (mode != FMX_SEARCH && idx->hdr.kind != FMX_KIND_MULTI)
         return fail(FMX_ERR_UNSUPPORTED, "search_prefix/suffix/exact need a MultiPieces index (frontend.rs:369-390)");
@@ -509,7 +544,7 @@ static int search_device(const fmx_index *idx, int mode, const uint8_t *d_pat, c
     a.kmer_steps = tab_ok ? idx->d_kmer_steps : nullptr;
     a.kmer_k = tab_ok ? idx->kmer_k : 0;
     if (count_work) CUDA_TRY(cudaMemsetAsync(idx->d_work, 0, sizeof(unsigned long long), st));
-    return dispatch_search(idx, a, st, force_simple);
+    return dispatch_search(idx, a, st, force_simple, buf);
 }
 
 static int check_err_flag(const fmx_index *idx, cudaStream_t st) {
@@ -834,7 +869,7 @@ extern "C" int fmx_search_locate_batch(const fmx_index *idx, int mode, const uin
             d_pat -= off0;  // the kernel adds the batch-global byte offsets
         }
         uint64_t *d_s = L.buf[B_S].as<uint64_t>(), *d_e = L.buf[B_E].as<uint64_t>();
-        if ((r = search_device(idx, mode, d_pat, d_off, fixed_len, n, nullptr, nullptr, d_s, d_e, L.st, false, true))) return r;
+        if ((r = search_device(idx, mode, d_pat, d_off, fixed_len, n, nullptr, nullptr, d_s, d_e, L.st, false, true, L.buf))) return r;
         if (out_s) CUDA_TRY(cudaMemcpyAsync(out_s + lo, d_s, n * 8, cudaMemcpyDeviceToHost, L.st));
         if (out_e) CUDA_TRY(cudaMemcpyAsync(out_e + lo, d_e, n * 8, cudaMemcpyDeviceToHost, L.st));
         uint64_t *d_unf = L.buf[B_HOFF].as<uint64_t>();

@@ -547,6 +547,10 @@ struct SearchArgs {
     const uint8_t *kmer_steps;      // iterations the reference executes for that k-mer (<= kmer_k)
     uint32_t kmer_k;
     uint8_t *steps_out;             // nullable: per-pattern executed iterations (table build)
+    // nullable: order[t] = pattern handled by thread t.  Patterns bucketed by their k-mer table index
+    // (= sorted by SA range start to within one k-mer range) touch the index quasi-sequentially, so
+    // concurrently running threads share sectors in L2 and DRAM rows instead of hitting random ones.
+    const uint32_t *order;
     // v2 work queue: unfinished patterns after phase A, entry = {pattern id, remaining chars, s, e}
     uint4 *queue;
     unsigned long long *qcount;
@@ -563,6 +567,19 @@ __device__ __forceinline__ void pattern_span(const SearchArgs &a, uint64_t p, ui
     }
 }
 
+// table index of the last K characters of a pattern; false if one of them exceeds max_character
+__device__ __forceinline__ bool kmer_index(const uint8_t *q, uint32_t len, uint32_t K, uint32_t sigma, uint32_t maxc,
+                                           uint32_t &idx) {
+    uint32_t v = 0;
+    bool valid = true;
+    for (uint32_t j = 0; j < K; j++) {
+        uint32_t c = __ldg(q + len - K + j);
+        valid = valid && c <= maxc;
+        v = v * sigma + c;
+    }
+    idx = v;
+    return valid;
+}
 // Backward search (wrapper.rs:103-124): one pattern per thread, grid-stride; the first kmer_k
 // iterations of a fresh search are one table lookup.  This simple shape won the A/B against the
 // persistent refill kernels below: once the index sits in L2 the kernel is bound by the number of
@@ -574,7 +591,8 @@ __global__ void __launch_bounds__(256) k_search(const __grid_constant__ FmxDev i
     load_tables<LAYOUT>(ix, tb);
     unsigned long long steps = 0;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < a.npat; p += stride) {
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < a.npat; t += stride) {
+        const uint64_t p = a.order ? (uint64_t)a.order[t] : t;
         uint64_t beg;
         uint32_t len;
         pattern_span(a, p, beg, len);
@@ -585,14 +603,8 @@ __global__ void __launch_bounds__(256) k_search(const __grid_constant__ FmxDev i
         if (a.kmer_tab != nullptr && a.init_s == nullptr && len >= a.kmer_k) {
             // the first kmer_k iterations of a fresh search are one table lookup
             const uint32_t K = a.kmer_k;
-            uint32_t idx = 0;
-            bool valid = true;
-            for (uint32_t j = 0; j < K; j++) {
-                uint32_t c = __ldg(q + len - 1 - j);
-                valid = valid && c <= ix.max_character;
-                idx = idx * ix.cs_len + c;
-            }
-            if (valid) {  // else: walk the slow path so the error shows up (or not) exactly as in the reference
+            uint32_t idx;
+            if (kmer_index(q, len, K, ix.cs_len, ix.max_character, idx)) {  // else: walk the slow path so the error shows up (or not) exactly as in the reference
                 uint2 t = __ldg(a.kmer_tab + idx);
                 s = t.x;
                 e = t.y;
@@ -625,20 +637,44 @@ __global__ void __launch_bounds__(256) k_search(const __grid_constant__ FmxDev i
     }
 }
 
-// patterns for the k-mer table: entry t is the k-mer whose LAST character is the most significant
-// base-sigma digit of t
+// patterns for the k-mer table: entry t is the k-mer whose FIRST character is the most significant
+// base-sigma digit of t, so table order = lexicographic order = order of the SA ranges
 __global__ void k_kmer_patterns(uint32_t k, uint32_t sigma, uint64_t entries, uint8_t *pat) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= entries) return;
     uint64_t v = t;
-    for (uint32_t j = 0; j < k; j++) {  // least significant digit = first character of the k-mer
+    for (uint32_t j = k; j-- > 0;) {
         pat[t * k + j] = (uint8_t)(v % sigma);
         v /= sigma;
     }
 }
+
 __global__ void k_kmer_pack(const uint64_t *s, const uint64_t *e, uint64_t entries, uint2 *tab) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < entries) tab[t] = make_uint2((uint32_t)s[t], (uint32_t)e[t]);
+}
+
+// bucketing pass 1: bucket[p] = k-mer table index of pattern p (the extra bucket `entries` takes
+// patterns the table cannot serve); hist[bucket]++
+__global__ void __launch_bounds__(256) k_bucket_count(const __grid_constant__ SearchArgs a, uint32_t sigma, uint32_t maxc,
+                                                       uint32_t entries, uint32_t *bucket, uint32_t *hist) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.npat) return;
+    uint64_t beg;
+    uint32_t len, idx = entries;
+    pattern_span(a, p, beg, len);
+    if (len >= a.kmer_k) {
+        uint32_t v;
+        if (kmer_index(a.pat + beg, len, a.kmer_k, sigma, maxc, v)) idx = v;
+    }
+    bucket[p] = idx;
+    atomicAdd(hist + idx, 1u);
+}
+// bucketing pass 2: cursor[] holds the exclusive prefix sum of hist; order[slot] = p
+__global__ void __launch_bounds__(256) k_bucket_scatter(const uint32_t *bucket, uint64_t npat, uint32_t *cursor,
+                                                         uint32_t *order) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < npat) order[atomicAdd(cursor + bucket[p], 1u)] = (uint32_t)p;
 }
 
 // Backward search, persistent variant (option "search_persistent"), phase A: one pattern per thread, fully converged.
@@ -666,14 +702,8 @@ __global__ void __launch_bounds__(256) k_search_init(const __grid_constant__ Fmx
             uint32_t e = a.init_e ? (uint32_t)a.init_e[p] : a.e0;
             bool done = k == 0;
             if (use_tab && k >= K) {
-                uint32_t idx = 0;
-                bool valid = true;
-                for (uint32_t j = 0; j < K; j++) {
-                    uint32_t c = __ldg(q + k - 1 - j);
-                    valid = valid && c <= ix.max_character;
-                    idx = idx * sigma + c;
-                }
-                if (valid) {  // else: walk the slow path so the error shows up (or not) exactly as in the reference
+                uint32_t idx;
+                if (kmer_index(q, k, K, sigma, ix.max_character, idx)) {  // else: walk the slow path so the error shows up (or not) exactly as in the reference
                     uint2 t = __ldg(a.kmer_tab + idx);
                     s = t.x;
                     e = t.y;
@@ -1063,7 +1093,7 @@ __global__ void __launch_bounds__(256) k_random_gather(const uint4 *buf, uint64_
         z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
         z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
         z ^= z >> 31;
-        uint64_t unit = z % nunits;
+        uint64_t unit = __umul64hi(z, nunits);  // uniform in [0, nunits) without a 64-bit division
 #pragma unroll
         for (int q = 0; q < WIDTH / 32; q++) {
             RB b = rb_load(buf, (uint32_t)(unit * (WIDTH / 32) + q));

@@ -99,7 +99,8 @@ int fmx_build_suffix_array_device(const void *text, uint64_t n, uint32_t char_wi
 
 /* Tuning knobs (A/B measurement; results never change): "search_persistent" 0|1 (persistent
  * per-lane-refill search kernels instead of one pattern per thread), "kmer" 0|1 (memoised first
- * search iterations), "persist_blocks_per_sm" 1..32, "pipeline_chunk" (patterns per chunk of
+ * search iterations), "bucket" -1|0|1 (visit the batch in k-mer bucket order: auto / never / always),
+ * "l2_fetch_granularity" 32|64|128, "persist_blocks_per_sm" 1..32, "pipeline_chunk" (patterns per chunk of
  * fmx_search_locate_batch's copy/compute pipeline, 0 = automatic).  The environment variable
  * FMX_FORCE_WAVELET=1 makes construction keep the binary wavelet matrix for small alphabets. */
 int fmx_index_set_option(fmx_index *idx, const char *key, int64_t value);

@@ -438,3 +438,19 @@ def test_gpu_built_blob_identical_to_host_built(kind, tmp_path):
     index.save(p)
     host = fmx.blob_build(t, kind, 2)                # host SA-IS
     assert np.array_equal(np.fromfile(p, dtype=np.uint8), host)
+
+
+def test_search_options_do_not_change_results():
+    """the tuning knobs (persistent kernels, k-mer table off, bucketed order) are result-neutral"""
+    text = dna(500_000, 91)
+    pats, _ = mixed_patterns(text, 60_000, 28, 92)
+    index = fmx.FMIndexWithLocate.new(fmx.Text.with_max_character(text, 4), 1)
+    ref = index.search_batch(pats)
+    steps = index.last_work()[0]
+    for key, val in (("search_persistent", 1), ("kmer", 0), ("search_persistent", 0), ("kmer", 1), ("bucket", 1)):
+        index.set_option(key, val)
+        b = index.search_batch(pats)
+        assert np.array_equal(b.s, ref.s) and np.array_equal(b.e, ref.e), (key, val)
+        assert index.last_work()[0] == steps
+    with pytest.raises(fmx.Error):
+        index.set_option("no_such_option", 1)

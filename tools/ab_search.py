@@ -9,8 +9,9 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="cfg2_dna100m")
 ap.add_argument("--npat", type=int, default=0)
 ap.add_argument("--reps", type=int, default=5)
-ap.add_argument("--variants", default="v1,v1k,v2k")
+ap.add_argument("--variants", default="v1,v1k,v1kb,v2k")
 ap.add_argument("--bps", default="")
+ap.add_argument("--gran", default="")
 args = ap.parse_args()
 fmx = fmx_pkg.load(); L = fmx.load_library()
 n, npat, m, sigma, mc, level, desc = bench.WORKLOADS[args.workload]
@@ -28,11 +29,15 @@ flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 ref = None
 rows = []
 variants = [(v, None) for v in args.variants.split(",")]
+grans = [int(g) for g in args.gran.split(",")] if args.gran else [None]
 if args.bps:
     variants += [("v2k", int(b)) for b in args.bps.split(",")]
-for name, bps in variants:
+for name, bps, gran in [(n_, b_, g_) for g_ in grans for (n_, b_) in variants]:
+    if gran:
+        index.set_option("l2_fetch_granularity", gran)
     index.set_option("search_persistent", name.startswith("v2"))
-    index.set_option("kmer", name.endswith("k"))
+    index.set_option("kmer", "k" in name)
+    index.set_option("bucket", 1 if name.endswith("b") else 0)
     if bps:
         index.set_option("persist_blocks_per_sm", bps)
     ts = []
@@ -48,7 +53,7 @@ for name, bps in variants:
     cur = (d_s.clone(), d_e.clone())
     same = True if ref is None else bool(torch.equal(cur[0], ref[0]) and torch.equal(cur[1], ref[1]))
     if ref is None: ref = cur
-    row = {"variant": name, "blocks_per_sm": bps, "ms_best": min(ts), "ms_mean": float(np.mean(ts)),
+    row = {"variant": name, "blocks_per_sm": bps, "l2_fetch_granularity": gran, "ms_best": min(ts), "ms_mean": float(np.mean(ts)),
            "Gq_per_s": npat / min(ts) / 1e6, "steps": steps, "identical_to_first": same}
     rows.append(row); print(row, flush=True)
 os.makedirs("gpurun_out", exist_ok=True)

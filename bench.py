@@ -7,6 +7,10 @@ FMIndexWithLocate, sampling level 2, 1M 32-mers (50 % sampled from the text, 50 
 over 100 MB synthetic DNA.  Prints ONE JSON line (see the contract in the task description).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+                    [--npat P] [--by-piece]
+
+Other workloads (the remaining BASELINE configs and the north-star target) are selected with
+--workload; `--by-piece` runs the MultiPieces workload piece-partitioned with the NCCL gather.
 """
 from __future__ import annotations
 
@@ -23,15 +27,29 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+FM, RLFM, MULTI = 0, 1, 2
+# name: dict(kind, n, npat, m (0 = ragged 8..64), sigma, mc, level, desc)
 WORKLOADS = {
-    # name: (text_len, npat, pattern_len, sigma, max_character, level, description)
-    "cfg2_dna100m": (100_000_000, 1_000_000, 32, 4, 4, 2,
-                     "BASELINE configs[1]: FMIndexWithLocate level 2, 1M 32-mers over 100 MB synthetic DNA"),
-    "target_dna1g": (1_000_000_000, 100_000_000, 32, 4, 4, 2,
-                     "north-star target: 100M 32-mers over 1 GB synthetic DNA, level 2"),
-    "cfg1_dna1m": (1_000_000, 10_000, 20, 4, 4, 2, "BASELINE configs[0] shape (CPU-runnable)"),
-    "dna16m": (16_000_000, 1_000_000, 32, 4, 4, 2, "small smoke workload"),
+    "cfg2_dna100m": dict(kind=FM, n=100_000_000, npat=1_000_000, m=32, sigma=4, mc=4, level=2,
+                         desc="BASELINE configs[1]: FMIndexWithLocate level 2, 1M 32-mers over 100 MB synthetic DNA"),
+    "target_dna1g": dict(kind=FM, n=1_000_000_000, npat=100_000_000, m=32, sigma=4, mc=4, level=2,
+                         desc="north-star target: 100M 32-mers over 1 GB synthetic DNA, level 2"),
+    "cfg1_dna1m": dict(kind=FM, n=1_000_000, npat=10_000, m=20, sigma=4, mc=4, level=2,
+                       desc="BASELINE configs[0] shape (CPU-runnable): 10k 20-mers over 1 MB DNA"),
+    "dna16m": dict(kind=FM, n=16_000_000, npat=1_000_000, m=32, sigma=4, mc=4, level=2, desc="small smoke workload"),
+    "cfg3_rlfm": dict(kind=RLFM, n=64 * (16 << 20), npat=10_000_000, m=32, sigma=4, mc=4, level=2, copies=64,
+                      desc="BASELINE configs[2]: RLFMIndexWithLocate, 64 mutated copies (0.1% SNPs) of a 16 Mi haplotype, "
+                           "10M 32-mers sampled from the text"),
+    "cfg3_rlfm_256m": dict(kind=RLFM, n=16 * (16 << 20), npat=2_000_000, m=32, sigma=4, mc=4, level=2, copies=16,
+                           desc="BASELINE configs[2] scaled: 16 mutated copies of a 16 Mi haplotype, 2M 32-mers"),
+    "cfg4_multi": dict(kind=MULTI, n=3_000_000_000, npat=10_000_000, m=32, sigma=4, mc=4, level=2, pieces=24,
+                       desc="BASELINE configs[3]: FMIndexMultiPiecesWithLocate over 24 chromosome-like pieces, 3 GB"),
+    "cfg4_multi_480m": dict(kind=MULTI, n=480_000_000, npat=4_000_000, m=32, sigma=4, mc=4, level=2, pieces=24,
+                            desc="BASELINE configs[3] scaled: 24 chromosome-like pieces, 480 MB total"),
+    "cfg5_bytes1g": dict(kind=FM, n=1_000_000_000, npat=100_000_000, m=0, sigma=255, mc=255, level=2,
+                         desc="BASELINE configs[4]: byte alphabet, FMIndexWithLocate over 1 GB, 100M patterns of length 8-64"),
 }
+CHROM = [248, 242, 198, 190, 181, 171, 159, 145, 138, 133, 135, 133, 114, 107, 102, 90, 83, 80, 58, 64, 46, 50, 156, 57]
 
 
 def _s64(c: int) -> int:
@@ -52,6 +70,13 @@ def mix64(x):
     return x ^ _lsr(x, 31)
 
 
+def gen_symbols(lo: int, hi: int, sigma: int, seed: int, device):
+    import torch
+
+    r = mix64(torch.arange(lo, hi, dtype=torch.int64, device=device) + seed * 0x1000000000)
+    return (_lsr(r, 33) % sigma + 1).to(torch.uint8)
+
+
 def gen_text(n: int, sigma: int, seed: int, device="cpu"):
     """n symbols uniform over 1..=sigma followed by the \\0 terminator (torch uint8 tensor on `device`)."""
     import torch
@@ -60,13 +85,42 @@ def gen_text(n: int, sigma: int, seed: int, device="cpu"):
     chunk = 1 << 26
     for lo in range(0, n, chunk):
         hi = min(n, lo + chunk)
-        r = mix64(torch.arange(lo, hi, dtype=torch.int64, device=device) + seed * 0x1000000000)
-        out[lo:hi] = (_lsr(r, 33) % sigma + 1).to(torch.uint8)
+        out[lo:hi] = gen_symbols(lo, hi, sigma, seed, device)
     out[n] = 0
     return out
 
 
-def gen_patterns(text, npat: int, m: int, sigma: int, seed: int):
+def gen_text_for(w: dict, device="cpu"):
+    """the text of a workload (torch uint8 on `device`)"""
+    import torch
+
+    n, sigma = w["n"], w["sigma"]
+    if w["kind"] == RLFM:  # mutated copies of one haplotype (config 3): seeds 5 (base), 6.. (copies)
+        copies = w["copies"]
+        base_len = n // copies
+        base = gen_symbols(0, base_len, sigma, 5, device)
+        out = torch.empty(n + 1, dtype=torch.uint8, device=device)
+        for c in range(copies):
+            r = mix64(torch.arange(0, base_len, dtype=torch.int64, device=device) + (6 + c) * 0x1000000000)
+            mut = (_lsr(r, 20) % 1000) == 0                       # 0.1 % substitutions
+            sub = (_lsr(r, 40) % sigma + 1).to(torch.uint8)
+            out[c * base_len:(c + 1) * base_len] = torch.where(mut, sub, base)
+        out[n] = 0
+        return out
+    if w["kind"] == MULTI:  # chromosome-like pieces, each followed by \0 (config 4)
+        total = sum(CHROM[: w["pieces"]])
+        lens = [max(1000, int(n * c / total)) for c in CHROM[: w["pieces"]]]
+        out = torch.empty(sum(lens) + len(lens), dtype=torch.uint8, device=device)
+        pos = 0
+        for k, ln in enumerate(lens):
+            out[pos:pos + ln] = gen_symbols(0, ln, sigma, 100 + k, device)
+            out[pos + ln] = 0
+            pos += ln + 1
+        return out
+    return gen_text(n, sigma, 3, device)
+
+
+def gen_patterns(text, npat: int, m: int, sigma: int, seed: int, all_sampled=False):
     """even patterns: substrings at uniform random offsets (>= 1 hit); odd: uniform random.
     `text` is a torch uint8 tensor; returns (patterns [npat, m] uint8, starts [npat] int64) on its device."""
     import torch
@@ -81,20 +135,49 @@ def gen_patterns(text, npat: int, m: int, sigma: int, seed: int):
         hi = min(npat, lo + chunk)
         k = torch.arange(lo, hi, dtype=torch.int64, device=device)
         st = _lsr(mix64(k + seed * 0x1000000000), 1) % (n - m)
-        rnd = mix64(k[:, None] * 64 + cols + (seed + 1) * 0x1000000000)
-        blk = (_lsr(rnd, 33) % sigma + 1).to(torch.uint8)
         samp = text[st[:, None] + cols]
-        pats[lo:hi] = torch.where((k % 2 == 0)[:, None], samp, blk)
+        if all_sampled:
+            pats[lo:hi] = samp
+        else:
+            rnd = mix64(k[:, None] * 64 + cols + (seed + 1) * 0x1000000000)
+            blk = (_lsr(rnd, 33) % sigma + 1).to(torch.uint8)
+            pats[lo:hi] = torch.where((k % 2 == 0)[:, None], samp, blk)
         starts[lo:hi] = st
     return pats, starts
 
 
+def gen_ragged_patterns(text, npat: int, sigma: int, seed: int, lo_len=8, hi_len=64):
+    """lengths uniform in lo_len..=hi_len; even patterns sampled from the text, odd uniform random.
+    returns (flat uint8, offsets int64[npat+1])"""
+    import torch
+
+    device = text.device
+    n = text.numel() - 1
+    k = torch.arange(npat, dtype=torch.int64, device=device)
+    lens = _lsr(mix64(k + (seed + 7) * 0x1000000000), 8) % (hi_len - lo_len + 1) + lo_len
+    off = torch.zeros(npat + 1, dtype=torch.int64, device=device)
+    off[1:] = torch.cumsum(lens, dim=0)
+    total = int(off[-1].item())
+    flat = torch.empty(total, dtype=torch.uint8, device=device)
+    st = _lsr(mix64(k + seed * 0x1000000000), 1) % (n - hi_len)
+    chunk = 1 << 20
+    for a in range(0, npat, chunk):
+        b = min(npat, a + chunk)
+        lo_b, hi_b = int(off[a].item()), int(off[b].item())
+        owner = torch.repeat_interleave(torch.arange(a, b, device=device), lens[a:b])
+        within = torch.arange(lo_b, hi_b, device=device) - off[owner]
+        samp = text[st[owner] + within]
+        rnd = mix64(torch.arange(lo_b, hi_b, dtype=torch.int64, device=device) + (seed + 1) * 0x1000000000)
+        blk = (_lsr(rnd, 33) % sigma + 1).to(torch.uint8)
+        flat[lo_b:hi_b] = torch.where(owner % 2 == 0, samp, blk)
+    return flat, off
+
+
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons during the timed region (NVML)."""
+    """Samples SM clock and throttle reasons while the measured section runs (NVML)."""
 
     def __init__(self, dev_index: int):
         super().__init__(daemon=True)
-        self.dev_index = dev_index
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop_evt = threading.Event()
         self.ok = False
@@ -138,7 +221,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.004)
+            time.sleep(0.002)
 
     def stop(self):
         self._stop_evt.set()
@@ -161,6 +244,15 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(workload: str, npat: int):
+    """DRAM bytes per k_search launch measured under ncu (profiles/ncu_traffic.json), scaled by batch size."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[workload]
+        return t["k_search_dram_bytes"] * npat / t["npat"], t
+    except Exception:
+        return None, None
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -178,10 +270,8 @@ def cpu_model():
     return "unknown"
 
 
-def run_cpu_path(oracle_index, pats, nthreads, locate=True):
+def run_cpu_path(oracle_index, flat, off, nthreads):
     """the restated CPU path (oracle, OpenMP over patterns): returns (seconds, s, e, hit_off, pos)"""
-    npat, m = pats.shape
-    flat, off = pats.reshape(-1), np.arange(npat + 1, dtype=np.uint64) * np.uint64(m)
     t0 = time.perf_counter()
     s, e = oracle_index.search_batch(flat, off, nthreads=nthreads)
     hit_off, pos, _ = oracle_index.locate_batch(s, e, nthreads=nthreads)
@@ -189,7 +279,27 @@ def run_cpu_path(oracle_index, pats, nthreads, locate=True):
     return dt, s, e, hit_off, pos
 
 
-def reference_arm(args, wl_name, wl):
+def host_patterns(w, text_t, npat, seed):
+    """(flat uint8 ndarray, offsets uint64 ndarray) of the first npat patterns of the workload, on the host"""
+    if w["m"]:
+        p = gen_patterns(text_t, npat, w["m"], w["sigma"], seed, all_sampled=w["kind"] == RLFM)[0].cpu().numpy()
+        return p.reshape(-1), np.arange(npat + 1, dtype=np.uint64) * np.uint64(w["m"])
+    flat, off = gen_ragged_patterns(text_t, npat, w["sigma"], seed)
+    return flat.cpu().numpy(), off.cpu().numpy().astype(np.uint64)
+
+
+def config_of(name, w, text_len, npat, extra=None):
+    cfg = {"workload": name, "description": w["desc"], "text_len": text_len, "patterns_per_step_per_gpu": npat,
+           "pattern_len": w["m"] if w["m"] else "8..64 (ragged)",
+           "pattern_mix": "all sampled from the text" if w["kind"] == RLFM else "50% sampled from text / 50% uniform random",
+           "index": ["FMIndexWithLocate", "RLFMIndexWithLocate", "FMIndexMultiPiecesWithLocate"][w["kind"]],
+           "sampling_level": w["level"], "wavelet_levels": int(w["mc"]).bit_length()}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def reference_arm(args, name, w):
     """--impl reference: the reference's CPU implementation of the path.  The crate cannot be built
     here (no Rust toolchain, vers-vecs un-vendored), so this is the oracle port of it, run on all
     host threads over a bounded sample of the same workload."""
@@ -198,19 +308,18 @@ def reference_arm(args, wl_name, wl):
         return 0
     from oracle import oracle as orc
 
-    n, npat, m, sigma, mc, level, desc = wl
     nthreads = host_threads()
-    text_t = gen_text(n, sigma, 3)
+    text_t = gen_text_for(w)
+    npat = args.npat or w["npat"]
     sample = min(npat, args.cpu_sample)
-    pats = gen_patterns(text_t, sample, m, sigma, 4)[0].numpy()
+    flat, off = host_patterns(w, text_t, sample, 4)
     text = text_t.numpy()
     t0 = time.perf_counter()
-    oracle_index = orc.OracleIndex(text, orc.FM, level=level, max_character=mc)
+    oracle_index = orc.OracleIndex(text, w["kind"], level=w["level"], max_character=w["mc"])
     build_s = time.perf_counter() - t0
-    times = []
-    hits = 0
+    times, hits = [], 0
     for it in range(args.warmup + args.steps):
-        dt, s, e, hit_off, pos = run_cpu_path(oracle_index, pats, nthreads)
+        dt, s, e, hit_off, pos = run_cpu_path(oracle_index, flat, off, nthreads)
         hits = int(hit_off[-1])
         if it >= args.warmup:
             times.append(dt)
@@ -220,10 +329,7 @@ def reference_arm(args, wl_name, wl):
         "impl": "reference", "metric": "count+locate queries/s", "value": value, "unit": "queries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32/u64 integer",
-        "data": "synthetic",
-        "config": {"workload": wl_name, "description": desc, "text_len": n + 1, "patterns_per_step": sample,
-                   "pattern_len": m, "pattern_mix": "50% sampled from text / 50% uniform random",
-                   "index": "FMIndexWithLocate", "sampling_level": level, "wavelet_levels": int(mc).bit_length()},
+        "data": "synthetic", "config": config_of(name, w, int(text.size), sample),
         "located_hits_per_s": hits / (ms * 1e-3),
         "cpu_baseline": {"value": value, "unit": "queries/s", "cores": nthreads, "kind": "port",
                          "sample": f"first {sample} patterns of the workload, count+locate, {args.steps} passes",
@@ -241,16 +347,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2_dna100m", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-sample", type=int, default=200_000, help="patterns in the CPU baseline sample")
     ap.add_argument("--npat", type=int, default=0, help="override the workload's patterns per step")
+    ap.add_argument("--cpu-sample", type=int, default=200_000, help="patterns in the CPU baseline sample")
+    ap.add_argument("--by-piece", action="store_true", help="MultiPieces workloads: partition the pieces over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gather-peak", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    wl = WORKLOADS[args.workload]
+    w = WORKLOADS[args.workload]
     if args.impl == "reference":
-        return reference_arm(args, args.workload, wl)
+        return reference_arm(args, args.workload, w)
 
     import torch
     import torch.distributed as dist
@@ -268,20 +375,27 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.by_piece:
+        return by_piece_bench(args, w, fmx, rank, world, local)
 
-    n, npat, m, sigma, mc, level, desc = wl
-    if args.npat:
-        npat = args.npat
+    npat = args.npat or w["npat"]
+    kind, mc, level, m = w["kind"], w["mc"], w["level"], w["m"]
     # synthetic text and patterns are generated on the GPU (same integer arithmetic as on the CPU)
-    d_text = gen_text(n, sigma, 3, device="cuda")
+    d_text = gen_text_for(w, device="cuda")
     # index replicated on every GPU; each rank answers its own batch (weak scaling, no collective
     # on the query path)
-    d_pat, _ = gen_patterns(d_text, npat, m, sigma, 4 + 1000 * rank)
+    seed = 4 + 1000 * rank
+    if m:
+        d_pat, _ = gen_patterns(d_text, npat, m, w["sigma"], seed, all_sampled=kind == RLFM)
+        d_off = None
+    else:
+        d_pat, d_off = gen_ragged_patterns(d_text, npat, w["sigma"], seed)
     text = d_text.cpu().numpy()
     del d_text
     torch.cuda.empty_cache()
+    cls = [fmx.FMIndexWithLocate, fmx.RLFMIndexWithLocate, fmx.FMIndexMultiPiecesWithLocate][kind]
     t0 = time.perf_counter()
-    index = fmx.FMIndexWithLocate.new(fmx.Text.with_max_character(text, mc), level, device=local)
+    index = cls.new(fmx.Text.with_max_character(text, mc), level, device=local)
     build_s = time.perf_counter() - t0
     h = index._h
     # a real (non-default) stream: the library launches on the stream it is handed, and the CUDA
@@ -295,6 +409,7 @@ def main():
     d_e = torch.empty(npat, dtype=torch.int64, device="cuda")
     d_hoff = torch.empty(npat + 1, dtype=torch.int64, device="cuda")
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    p_off = d_off.data_ptr() if d_off is not None else None
 
     def chk(rc):
         if rc != 0:
@@ -304,7 +419,7 @@ def main():
     total = C.c_uint64(0)
 
     def search():
-        chk(L.fmx_search_batch_device(h, 0, d_pat.data_ptr(), None, m, npat, None, None, d_s.data_ptr(),
+        chk(L.fmx_search_batch_device(h, 0, d_pat.data_ptr(), p_off, m, npat, None, None, d_s.data_ptr(),
                                       d_e.data_ptr(), sp))
 
     def locate():
@@ -341,7 +456,6 @@ def main():
         ev[k][2].record(stream)
     torch.cuda.synchronize()
     wall = time.perf_counter() - wall0
-    clocks = sampler.stop()
     launches = L.fmx_launch_count() - launches0
     if world > 1:
         dist.barrier()
@@ -363,8 +477,12 @@ def main():
     value = world * npat / (ms_per_step * 1e-3)
 
     # ---- end to end through the host-buffer C ABI: pinned host inputs, H2D + D2H inside the timed region
-    h_pat = torch.empty((npat, m), dtype=torch.uint8).pin_memory()
+    h_pat = torch.empty(d_pat.shape, dtype=torch.uint8).pin_memory()
     h_pat.copy_(d_pat)
+    h_off = None
+    if d_off is not None:
+        h_off = torch.empty(npat + 1, dtype=torch.int64).pin_memory()
+        h_off.copy_(d_off)
     h_s = torch.empty(npat, dtype=torch.int64).pin_memory()
     h_e = torch.empty(npat, dtype=torch.int64).pin_memory()
     h_hoff = torch.empty(npat + 1, dtype=torch.int64).pin_memory()
@@ -374,8 +492,9 @@ def main():
 
     def e2e_step():
         # the call a user makes: host patterns in, SA ranges + CSR hit lists out (one fused C-ABI call)
-        chk(L.fmx_search_locate_batch(h, 0, h_pat.data_ptr(), None, m, npat, h_s.data_ptr(), h_e.data_ptr(),
-                                      h_hoff.data_ptr(), h_pos.data_ptr(), None, cap, C.byref(nhits)))
+        chk(L.fmx_search_locate_batch(h, 0, h_pat.data_ptr(), None if h_off is None else h_off.data_ptr(), m, npat,
+                                      h_s.data_ptr(), h_e.data_ptr(), h_hoff.data_ptr(), h_pos.data_ptr(), None, cap,
+                                      C.byref(nhits)))
         return int(nhits.value)
 
     for _ in range(2):
@@ -389,11 +508,12 @@ def main():
         nh = e2e_step()
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
+    clocks = sampler.stop()
     if world > 1:
         tt = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
-    h2d = npat * m
+    h2d = int(h_pat.numel()) + (8 * (npat + 1) if h_off is not None else 0)
     d2h = 2 * 8 * npat + 8 * (npat + 1) + 8 * nh
 
     if rank != 0:
@@ -403,31 +523,39 @@ def main():
 
     # ---- roofline of the dominant kernel (k_search).  Algorithmic bytes = one 32-byte sector per
     # rank probe the device layout needs: 32 B x 2 bounds x P x executed steps, P = sectors per rank
-    # (L for the binary wavelet matrix, 1 for the quaternary level DNA alphabets get).  The same
-    # count for the reference's L-level wavelet matrix is reported beside it.
+    # (L for the binary wavelet matrix, 1 for the quaternary level DNA alphabets get; RLFM adds the
+    # run-start vector and the two select tables).  The same count for the reference's L-level
+    # wavelet matrix is reported beside it.
     Lw = int(mc).bit_length()
     P = index.sectors_per_rank()
+    per_lf2 = P + (3 if kind == RLFM else 0)
     peak, peak_src = measured_peaks()
     ms_search = ms_search_total / args.steps
-    alg_bytes_search = 32.0 * 2 * P * search_steps
-    alg_bytes_locate = 32.0 * (P * lf_steps + hits)
+    alg_bytes_search = 32.0 * 2 * per_lf2 * search_steps
+    alg_bytes_locate = 32.0 * (per_lf2 * lf_steps + hits)
     achieved = alg_bytes_search / (ms_search * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(args.workload, npat)
+    beyond_l2 = index.heap_size() > (400 << 20)
     roofline = {"bound": "hbm", "kernel": "k_search", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes_search, "kernel_ms": ms_search,
-                "sectors_per_rank": P, "reference_layout_algorithmic_bytes": 32.0 * 2 * Lw * search_steps,
-                "note": ("index larger than L2: HBM random-sector bound" if index.heap_size() > (400 << 20) else
-                         "index fits the 126 MB L2: bound by L2 latency / L1TEX request rate, not HBM; see traffic"),
+                "sectors_per_lf_map2": per_lf2,
+                "reference_layout_algorithmic_bytes": 32.0 * 2 * (Lw if kind != RLFM else 2 * Lw + 3) * search_steps,
+                "note": ("index larger than L2: HBM bound" if beyond_l2 else
+                         "index fits the 126 MB L2: bound by L2 latency / L1TEX request rate, not HBM (see traffic)"),
                 "executed_search_steps": int(search_steps), "executed_lf_steps": int(lf_steps),
                 "locate_kernel": {"achieved": alg_bytes_locate / (max(ms_locate_total / args.steps, 1e-9) * 1e-3) / 1e9,
                                   "phase_ms": ms_locate_total / args.steps}}
+    if traffic:
+        roofline["traffic_frac_of_peak"] = traffic / (ms_search * 1e-3) / 1e9 / peak
+        roofline["traffic_source"] = traffic_src.get("source")
     if not args.no_gather_peak:
         try:
             gp = fmx.random_gather_peak(local, nbytes=4 << 30, nloads=1 << 28, iters=3)
             sect = alg_bytes_search / 32.0 / (ms_search * 1e-3)
             roofline["random_access"] = {"peak_sectors_per_s": gp, "peak_GBps": gp * 32 / 1e9,
                                          "achieved_sectors_per_s": sect, "frac": sect / gp,
-                                         "how": "independent random 32 B gathers over a 4 GiB buffer, best of 3"}
+                                         "how": "independent uniform-random 32 B gathers over a 4 GiB buffer, best of 3"}
         except Exception as ex:  # pragma: no cover
             roofline["random_access"] = {"error": str(ex)}
 
@@ -439,11 +567,17 @@ def main():
         nthreads = host_threads()
         sample = min(npat, args.cpu_sample)
         tb = time.perf_counter()
-        oracle_index = orc.OracleIndex(text, orc.FM, level=level, max_character=mc)
+        oracle_index = orc.OracleIndex(text, kind, level=level, max_character=mc)
         obuild = time.perf_counter() - tb
+        if m:
+            s_flat = h_pat[:sample].numpy().reshape(-1)
+            s_off = np.arange(sample + 1, dtype=np.uint64) * np.uint64(m)
+        else:
+            s_off = h_off[: sample + 1].numpy().astype(np.uint64)
+            s_flat = h_pat.numpy()[: int(s_off[-1])]
         best = None
         for _ in range(2):
-            dt, s, e, ohoff, opos = run_cpu_path(oracle_index, h_pat[:sample].numpy(), nthreads)
+            dt, s, e, ohoff, opos = run_cpu_path(oracle_index, s_flat, s_off, nthreads)
             best = dt if best is None else min(best, dt)
         g_s = d_s[:sample].cpu().numpy().view(np.uint64)
         g_e = d_e[:sample].cpu().numpy().view(np.uint64)
@@ -462,11 +596,11 @@ def main():
         "metric": "count+locate queries/s", "value": value, "unit": "queries/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32/u64 integer", "data": "synthetic",
-        "config": {"workload": args.workload, "description": desc, "text_len": n + 1, "patterns_per_step_per_gpu": npat,
-                   "pattern_len": m, "pattern_mix": "50% sampled from text / 50% uniform random",
-                   "index": "FMIndexWithLocate", "sampling_level": level, "wavelet_levels": Lw,
-                   "index_device_bytes": index.heap_size(), "l2": "flushed between timed iterations (512 MiB memset)",
-                   "parallelism": f"index replicated x{world}, query batches sharded", "index_build_s": round(build_s, 1)},
+        "config": config_of(args.workload, w, int(text.size), npat, {
+            "index_device_bytes": index.heap_size(), "device_layout": "quaternary (1 sector per rank)" if P == 1 else
+            f"binary wavelet matrix ({P} sectors per rank)",
+            "l2": "flushed between timed iterations (512 MiB memset)",
+            "parallelism": f"index replicated x{world}, query batches sharded", "index_build_s": round(build_s, 1)}),
         "count_queries_per_s": world * npat / (ms_search_total / args.steps * 1e-3),
         "located_hits_per_s": hits_all / (ms_per_step * 1e-3),
         "hits_per_step": hits_all,
@@ -480,6 +614,79 @@ def main():
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def by_piece_bench(args, w, fmx, rank, world, local):
+    """MultiPieces partitioned by piece: every rank indexes its pieces, answers every pattern, and the
+    per-pattern counts and hit lists are combined with NCCL all_gathers (fm-index_b200/partitioned.py)."""
+    import torch
+    import torch.distributed as dist
+
+    from fm_index_b200 import partitioned as part
+
+    if w["kind"] != MULTI:
+        raise SystemExit("--by-piece needs a MultiPieces workload (cfg4_multi*)")
+    npat = args.npat or w["npat"]
+    d_text = gen_text_for(w, device="cuda")
+    d_pat, _ = gen_patterns(d_text, npat, w["m"], w["sigma"], 4)          # the SAME batch on every rank
+    keep = (d_pat != 0).all(dim=1)                                          # \0 cannot cross the partition
+    d_pat = d_pat[keep].contiguous()
+    npat = int(d_pat.shape[0])
+    text = d_text.cpu().numpy()
+    del d_text
+    torch.cuda.empty_cache()
+    t0 = time.perf_counter()
+    idx = part.PartitionedMultiPieces(text, w["level"], w["mc"], device=local)
+    build_s = time.perf_counter() - t0
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    L = fmx.load_library()
+    for _ in range(args.warmup):
+        counts, hoff, pos, pid = idx.search_locate(d_pat)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = L.fmx_launch_count()
+    sampler.start()
+    for k in range(args.steps):
+        ev[k][0].record(stream)
+        counts, hoff, pos, pid = idx.search_locate(d_pat)
+        ev[k][1].record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    launches = L.fmx_launch_count() - launches0
+    ms_total = float(sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps)))
+    if world > 1:
+        tt = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt.item())
+    ms = ms_total / args.steps
+    hits = int(hoff[-1].item())
+    # property check: every gathered hit really holds its pattern, in the right piece
+    ends = np.flatnonzero(text == 0)
+    p_h, o_h = pos.cpu().numpy(), np.repeat(np.arange(npat), np.diff(hoff.cpu().numpy()))
+    pats_h = d_pat.cpu().numpy()
+    sel = np.random.default_rng(0).integers(0, max(hits, 1), min(hits, 200_000))
+    got = text[p_h[sel][:, None] + np.arange(w["m"])[None, :]]
+    ok = bool(np.array_equal(got, pats_h[o_h[sel]]) and
+              np.array_equal(pid.cpu().numpy()[sel], np.searchsorted(ends, p_h[sel], side="left")))
+    if rank == 0:
+        line = {"metric": "count+locate queries/s", "value": npat / (ms * 1e-3), "unit": "queries/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "u32/u64 integer", "data": "synthetic",
+                "config": config_of(args.workload, w, int(text.size), npat, {
+                    "parallelism": f"pieces partitioned over {world} GPUs {idx.ranges}; every pattern answered by every "
+                                   "rank; counts + hit lists combined by NCCL all_gather",
+                    "index_build_s": round(build_s, 1)}),
+                "located_hits_per_s": hits / (ms * 1e-3), "hits_per_step": hits, "gpu_launches": int(launches),
+                "clocks": clocks, "gathered_hits_verified_against_text": ok}
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -14,10 +14,11 @@ ap.add_argument("--bps", default="")
 ap.add_argument("--gran", default="")
 args = ap.parse_args()
 fmx = fmx_pkg.load(); L = fmx.load_library()
-n, npat, m, sigma, mc, level, desc = bench.WORKLOADS[args.workload]
-npat = args.npat or npat
+w = bench.WORKLOADS[args.workload]
+n, m, sigma, mc, level = w["n"], w["m"], w["sigma"], w["mc"], w["level"]
+npat = args.npat or w["npat"]
 torch.cuda.set_device(0)
-d_text = bench.gen_text(n, sigma, 3, device="cuda")
+d_text = bench.gen_text_for(w, device="cuda")
 d_pat, _ = bench.gen_patterns(d_text, npat, m, sigma, 4)
 text = d_text.cpu().numpy(); del d_text
 t0 = time.time()

@@ -454,3 +454,17 @@ def test_search_options_do_not_change_results():
         assert index.last_work()[0] == steps
     with pytest.raises(fmx.Error):
         index.set_option("no_such_option", 1)
+
+
+def test_cpp_facade(tmp_path):
+    """include/fmx.hpp (the compiled host-side mirror of the crate's API) against the reference's
+    README doctest and multi_pieces example, as a C++ program linked to libfmx_b200.so"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "test_api"
+    libdir = os.path.join(root, "fm-index_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "test_api.cpp"), "-o", str(exe),
+                           "-L", libdir, "-lfmx_b200", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and "cpp facade ok" in out.stdout, out.stdout + out.stderr

@@ -266,6 +266,10 @@ class _Index:
         """32-byte sectors per rank/access probe in this index's device layout (L, or 1 for Q4)."""
         return int(self._L.fmx_index_sectors_per_rank(self._h))
 
+    def kmer_k(self, big=False):
+        """characters memoised by the small / large k-mer table (0 = none)"""
+        return int(self._L.fmx_index_kmer_k(self._h, int(big)))
+
     def set_option(self, key, value):
         """tuning knobs for A/B measurements; results never change"""
         _check(self._L.fmx_index_set_option(self._h, key.encode(), int(value)))

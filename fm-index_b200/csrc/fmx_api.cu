@@ -86,6 +86,11 @@ struct fmx_index {
     uint8_t *d_kmer_steps = nullptr;
     uint32_t kmer_k = 0;
     uint64_t kmer_entries = 0;
+    uint2 *d_big_tab = nullptr;            // the large (HBM-resident) table
+    uint8_t *d_big_steps = nullptr;
+    uint32_t big_k = 0;
+    uint64_t big_entries = 0;
+    int opt_kmer_big = 1;
     int sms = 148;
     int persist_blocks_per_sm = 4;
     // tuning knobs (fmx_index_set_option)
@@ -100,6 +105,7 @@ struct fmx_index {
 };
 
 static int build_kmer_table(fmx_index *idx);
+static int build_big_table(fmx_index *idx, uint64_t budget_bytes);
 
 static inline cudaStream_t pick_stream(const fmx_index *idx, void *stream) {
     return stream ? reinterpret_cast<cudaStream_t>(stream) : idx->stream;
@@ -313,6 +319,8 @@ void fmx_index_free(fmx_index *idx) {
     if (idx->d_err) cudaFree(idx->d_err);
     if (idx->d_kmer_tab) cudaFree(idx->d_kmer_tab);
     if (idx->d_kmer_steps) cudaFree(idx->d_kmer_steps);
+    if (idx->d_big_tab) cudaFree(idx->d_big_tab);
+    if (idx->d_big_steps) cudaFree(idx->d_big_steps);
     if (idx->stream) cudaStreamDestroy(idx->stream);
     delete idx;
 }
@@ -322,6 +330,12 @@ int fmx_index_set_option(fmx_index *idx, const char *key, int64_t value) {
     std::string k(key);
     if (k == "search_persistent") idx->opt_persistent = value != 0;
     else if (k == "kmer") idx->opt_kmer = value != 0;
+    else if (k == "kmer_big") idx->opt_kmer_big = value != 0;
+    else if (k == "kmer_budget_mb") {  // rebuild the large table with another HBM budget
+        CUDA_TRY(cudaSetDevice(idx->device));
+        int rc = build_big_table(idx, (uint64_t)(value < 0 ? 0 : value) << 20);
+        if (rc) return rc;
+    }
     else if (k == "bucket") idx->opt_bucket = value < 0 ? -1 : (value != 0);
     else if (k == "pipeline_chunk") idx->opt_pipeline_chunk = value > 0 ? (uint64_t)value : 0;
     else if (k == "l2_fetch_granularity") {
@@ -337,7 +351,10 @@ int fmx_index_set_option(fmx_index *idx, const char *key, int64_t value) {
 }
 
 uint64_t fmx_index_len(const fmx_index *idx) { return idx ? idx->hdr.n : 0; }
-uint64_t fmx_index_device_bytes(const fmx_index *idx) { return idx ? idx->hdr.total_bytes + idx->kmer_entries * 9 : 0; }
+uint64_t fmx_index_device_bytes(const fmx_index *idx) {
+    return idx ? idx->hdr.total_bytes + (idx->kmer_entries + idx->big_entries) * 9 : 0;
+}
+uint32_t fmx_index_kmer_k(const fmx_index *idx, int big) { return idx ? (big ? idx->big_k : idx->kmer_k) : 0; }
 uint64_t fmx_index_pieces_count(const fmx_index *idx) { return idx ? idx->hdr.ndoc : 0; }
 int fmx_index_kind(const fmx_index *idx) { return idx ? (int)idx->hdr.kind : -1; }
 int fmx_index_has_locate(const fmx_index *idx) { return idx ? (int)idx->hdr.has_locate : 0; }
@@ -416,8 +433,8 @@ static int bucket_patterns(const fmx_index *idx, DevBuf *buf, SearchArgs &a, cud
     if ((rc = buf[B_ORDER].ensure(a.npat * 4))) return rc;
     uint32_t *d_bucket = buf[B_BUCKET].as<uint32_t>(), *d_hist = buf[B_BHIST].as<uint32_t>();
     CUDA_TRY(cudaMemsetAsync(d_hist, 0, (nb + 1) * 4, st));
-    k_bucket_count<<<grid_for(a.npat, 256), 256, 0, st>>>(a, idx->hdr.cs_len, idx->hdr.max_character,
-                                                          (uint32_t)idx->kmer_entries, d_bucket, d_hist);
+    k_bucket_count<<<grid_for(a.npat, 256), 256, 0, st>>>(a, idx->hdr.max_character, (uint32_t)idx->kmer_entries, d_bucket,
+                                                          d_hist);
     LAUNCH_CHECK();
     if ((rc = device_scan<uint32_t, uint32_t, OpSum, true>(d_hist, nb, d_hist, OpSum(), false, buf[B_TILES], st))) return rc;
     k_bucket_scatter<<<grid_for(a.npat, 256), 256, 0, st>>>(d_bucket, a.npat, d_hist, buf[B_ORDER].as<uint32_t>());
@@ -469,50 +486,112 @@ static int dispatch_search(const fmx_index *idx, const SearchArgs &a_in, cudaStr
 }
 
 // Memoise the first k iterations of every fresh search: run the search kernel itself over all
-// sigma^k k-mers once, at index upload (sigma = max_character + 1).
-static int build_kmer_table(fmx_index *idx) {
-    if (env_flag("FMX_NO_KMER")) return 0;
-    const uint64_t sigma = idx->hdr.cs_len;
-    const uint64_t budget = idx->hdr.n >= (1ull << 22) ? (1ull << 21) : (1ull << 12);
-    uint32_t k = 0;
-    uint64_t entries = 1;
-    while (entries * sigma <= budget && k < 16) {
-        entries *= sigma;
-        k++;
-    }
-    if (k < 2 || idx->hdr.n < 2) return 0;
+// base^k k-mers (base = max_character: the non-zero symbols), at index upload.  `accel` lets the
+// build of the large table start from the small one.
+static int build_one_table(fmx_index *idx, uint32_t k, uint64_t entries, bool accel, uint2 **tab_out, uint8_t **steps_out) {
     cudaStream_t st = idx->stream;
-    uint8_t *d_pat = nullptr;
+    const uint64_t chunk = entries < (1ull << 26) ? entries : (1ull << 26);
+    uint8_t *d_pat = nullptr, *d_steps = nullptr;
     uint64_t *d_s = nullptr, *d_e = nullptr;
-    CUDA_TRY(cudaMalloc(&d_pat, entries * k));
-    CUDA_TRY(cudaMalloc(&d_s, entries * 8));
-    CUDA_TRY(cudaMalloc(&d_e, entries * 8));
-    CUDA_TRY(cudaMalloc(&idx->d_kmer_tab, entries * sizeof(uint2)));
-    CUDA_TRY(cudaMalloc(&idx->d_kmer_steps, entries));
-    k_kmer_patterns<<<grid_for(entries, 256), 256, 0, st>>>(k, (uint32_t)sigma, entries, d_pat);
-    LAUNCH_CHECK();
-    SearchArgs a;
-    std::memset(&a, 0, sizeof(a));
-    a.pat = d_pat;
-    a.fixed_len = k;
-    a.npat = entries;
-    a.s0 = 0;
-    a.e0 = (uint32_t)idx->hdr.n;
-    a.out_s = d_s;
-    a.out_e = d_e;
-    a.err = idx->d_err;
-    a.steps_out = idx->d_kmer_steps;
-    int rc = dispatch_search(idx, a, st, true);
-    if (rc) return rc;
-    k_kmer_pack<<<grid_for(entries, 256), 256, 0, st>>>(d_s, d_e, entries, idx->d_kmer_tab);
-    LAUNCH_CHECK();
-    CUDA_TRY(cudaStreamSynchronize(st));
+    uint2 *d_tab = nullptr;
+    cudaError_t e = cudaMalloc(&d_tab, entries * sizeof(uint2));
+    if (e == cudaSuccess) e = cudaMalloc(&d_steps, entries);
+    if (e == cudaSuccess) e = cudaMalloc(&d_pat, chunk * k);
+    if (e == cudaSuccess) e = cudaMalloc(&d_s, chunk * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&d_e, chunk * 8);
+    int rc = 0;
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        rc = fail(FMX_ERR_OOM, std::string("k-mer table: ") + cudaGetErrorString(e));
+    }
+    for (uint64_t first = 0; rc == 0 && first < entries; first += chunk) {
+        const uint64_t m = entries - first < chunk ? entries - first : chunk;
+        k_kmer_patterns<<<grid_for(m, 256), 256, 0, st>>>(k, idx->hdr.max_character, first, m, d_pat);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        SearchArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.pat = d_pat;
+        a.fixed_len = k;
+        a.npat = m;
+        a.s0 = 0;
+        a.e0 = (uint32_t)idx->hdr.n;
+        a.out_s = d_s;
+        a.out_e = d_e;
+        a.err = idx->d_err;
+        a.steps_out = d_steps + first;
+        if (accel) {
+            a.kmer_tab = idx->d_kmer_tab;
+            a.kmer_steps = idx->d_kmer_steps;
+            a.kmer_k = idx->kmer_k;
+        }
+        rc = dispatch_search(idx, a, st, true);
+        if (rc) break;
+        k_kmer_pack<<<grid_for(m, 256), 256, 0, st>>>(d_s, d_e, m, d_tab + first);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (cudaStreamSynchronize(st) != cudaSuccess) rc = fail(FMX_ERR_CUDA, "k-mer table build failed");
+    }
     cudaFree(d_pat);
     cudaFree(d_s);
     cudaFree(d_e);
+    if (rc) {
+        cudaFree(d_tab);
+        cudaFree(d_steps);
+        return rc;
+    }
+    *tab_out = d_tab;
+    *steps_out = d_steps;
+    return 0;
+}
+
+static void pick_k(uint64_t base, uint64_t max_entries, uint32_t &k, uint64_t &entries) {
+    k = 0;
+    entries = 1;
+    while (base > 1 && entries * base <= max_entries && k < 32) {
+        entries *= base;
+        k++;
+    }
+}
+
+// the large table: as many characters as `budget_bytes` of HBM buy (9 bytes per entry)
+static int build_big_table(fmx_index *idx, uint64_t budget_bytes) {
+    if (idx->d_big_tab) cudaFree(idx->d_big_tab);
+    if (idx->d_big_steps) cudaFree(idx->d_big_steps);
+    idx->d_big_tab = nullptr;
+    idx->d_big_steps = nullptr;
+    idx->big_k = 0;
+    idx->big_entries = 0;
+    if (!idx->d_kmer_tab || budget_bytes == 0) return 0;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && budget_bytes > free_b / 3) budget_bytes = free_b / 3;
+    uint64_t max_entries = budget_bytes / 9;
+    if (max_entries > (1ull << 32)) max_entries = 1ull << 32;
+    uint32_t k;
+    uint64_t entries;
+    pick_k(idx->hdr.max_character, max_entries, k, entries);
+    if (k <= idx->kmer_k) return 0;
+    int rc = build_one_table(idx, k, entries, true, &idx->d_big_tab, &idx->d_big_steps);
+    if (rc) return rc;
+    idx->big_k = k;
+    idx->big_entries = entries;
+    return 0;
+}
+
+static int build_kmer_table(fmx_index *idx) {
+    if (env_flag("FMX_NO_KMER") || idx->hdr.n < 2) return 0;
+    const bool large_text = idx->hdr.n >= (1ull << 22);
+    uint32_t k;
+    uint64_t entries;
+    pick_k(idx->hdr.max_character, large_text ? (1ull << 21) : (1ull << 12), k, entries);
+    if (k < 1) return 0;
+    int rc = build_one_table(idx, k, entries, false, &idx->d_kmer_tab, &idx->d_kmer_steps);
+    if (rc) return rc;
     idx->kmer_k = k;
     idx->kmer_entries = entries;
-    return 0;
+    if (!large_text) return 0;
+    // default HBM budget of the large table: twice the index itself (FMX_KMER_BUDGET_MB overrides)
+    uint64_t budget = 2 * idx->hdr.total_bytes;
+    if (const char *v = std::getenv("FMX_KMER_BUDGET_MB")) budget = std::strtoull(v, nullptr, 10) << 20;
+    return build_big_table(idx, budget);
 }
 
 static int search_device(const fmx_index *idx, int mode, const uint8_t *d_pat, const uint64_t *d_pat_off,
@@ -543,6 +622,10 @@ static int search_device(const fmx_index *idx, int mode, const uint8_t *d_pat, c
     a.kmer_tab = tab_ok ? idx->d_kmer_tab : nullptr;
     a.kmer_steps = tab_ok ? idx->d_kmer_steps : nullptr;
     a.kmer_k = tab_ok ? idx->kmer_k : 0;
+    const bool big_ok = tab_ok && idx->d_big_tab && idx->opt_kmer_big;
+    a.big_tab = big_ok ? idx->d_big_tab : nullptr;
+    a.big_steps = big_ok ? idx->d_big_steps : nullptr;
+    a.big_k = big_ok ? idx->big_k : 0;
     if (count_work) CUDA_TRY(cudaMemsetAsync(idx->d_work, 0, sizeof(unsigned long long), st));
     return dispatch_search(idx, a, st, force_simple, buf);
 }

@@ -543,9 +543,16 @@ struct SearchArgs {
     // memoised top of the search: (s, e) after the reference loop has consumed the LAST kmer_k
     // characters of a pattern starting from (0, n) -- including its early break -- for every
     // k-mer over 0..=max_character.  NULL => not used.
+    // Table indices are base-max_character numbers over the digits c-1 (patterns with a \0 or an
+    // out-of-range character among those k take the ordinary path).  Two tables: a small L2-resident
+    // one (kmer_k) and, HBM permitting, a large one (big_k > kmer_k) that replaces big_k iterations
+    // -- and usually the whole search of an absent pattern -- by one DRAM access.
     const uint2 *kmer_tab;
     const uint8_t *kmer_steps;      // iterations the reference executes for that k-mer (<= kmer_k)
     uint32_t kmer_k;
+    const uint2 *big_tab;
+    const uint8_t *big_steps;
+    uint32_t big_k;
     uint8_t *steps_out;             // nullable: per-pattern executed iterations (table build)
     // nullable: order[t] = pattern handled by thread t.  Patterns bucketed by their k-mer table index
     // (= sorted by SA range start to within one k-mer range) touch the index quasi-sequentially, so
@@ -567,19 +574,52 @@ __device__ __forceinline__ void pattern_span(const SearchArgs &a, uint64_t p, ui
     }
 }
 
-// table index of the last K characters of a pattern; false if one of them exceeds max_character
-__device__ __forceinline__ bool kmer_index(const uint8_t *q, uint32_t len, uint32_t K, uint32_t sigma, uint32_t maxc,
-                                           uint32_t &idx) {
+// table index of the last K characters of a pattern (base max_character, digit = c - 1);
+// false if one of them is \0 or exceeds max_character
+__device__ __forceinline__ bool kmer_index(const uint8_t *q, uint32_t len, uint32_t K, uint32_t maxc, uint32_t &idx) {
     uint32_t v = 0;
     bool valid = true;
     for (uint32_t j = 0; j < K; j++) {
         uint32_t c = __ldg(q + len - K + j);
-        valid = valid && c <= maxc;
-        v = v * sigma + c;
+        valid = valid && (c - 1u) < maxc;
+        v = v * maxc + (c - 1u);
     }
     idx = v;
     return valid;
 }
+
+// memoised start of a fresh search: returns true and sets (s, e, it, len) when a table serves the
+// pattern; otherwise the caller walks from (s0, e0) so errors show up (or not) exactly as in the reference
+__device__ __forceinline__ bool kmer_lookup(const SearchArgs &a, uint32_t maxc, const uint8_t *q, uint32_t &len,
+                                            uint32_t &s, uint32_t &e, uint32_t &it) {
+    const uint2 *tab = nullptr;
+    const uint8_t *stp = nullptr;
+    uint32_t K = 0;
+    if (a.big_tab != nullptr && len >= a.big_k) {
+        tab = a.big_tab;
+        stp = a.big_steps;
+        K = a.big_k;
+    } else if (a.kmer_tab != nullptr && len >= a.kmer_k) {
+        tab = a.kmer_tab;
+        stp = a.kmer_steps;
+        K = a.kmer_k;
+    } else {
+        return false;
+    }
+    uint32_t idx;
+    if (!kmer_index(q, len, K, maxc, idx)) return false;
+    uint2 t = __ldg(tab + idx);
+    s = t.x;
+    e = t.y;
+    it = K;
+    len -= K;
+    if (s == e) {
+        it = __ldg(stp + idx);
+        len = 0;
+    }
+    return true;
+}
+
 // Backward search (wrapper.rs:103-124): one pattern per thread, grid-stride; the first kmer_k
 // iterations of a fresh search are one table lookup.  This simple shape won the A/B against the
 // persistent refill kernels below: once the index sits in L2 the kernel is bound by the number of
@@ -600,22 +640,7 @@ __global__ void __launch_bounds__(256) k_search(const __grid_constant__ FmxDev i
         uint32_t e = a.init_e ? (uint32_t)a.init_e[p] : a.e0;
         const uint8_t *q = a.pat + beg;
         uint32_t it = 0;
-        if (a.kmer_tab != nullptr && a.init_s == nullptr && len >= a.kmer_k) {
-            // the first kmer_k iterations of a fresh search are one table lookup
-            const uint32_t K = a.kmer_k;
-            uint32_t idx;
-            if (kmer_index(q, len, K, ix.cs_len, ix.max_character, idx)) {  // else: walk the slow path so the error shows up (or not) exactly as in the reference
-                uint2 t = __ldg(a.kmer_tab + idx);
-                s = t.x;
-                e = t.y;
-                it = K;
-                len -= K;
-                if (s == e) {
-                    it = __ldg(a.kmer_steps + idx);
-                    len = 0;
-                }
-            }
-        }
+        if (a.init_s == nullptr) kmer_lookup(a, ix.max_character, q, len, s, e, it);
         for (uint32_t k = len; k-- > 0;) {
             uint32_t c = __ldg(q + k);
             if (c > ix.max_character) {  // the reference panics here (cs[c] out of bounds, fm_index.rs:94)
@@ -639,12 +664,12 @@ __global__ void __launch_bounds__(256) k_search(const __grid_constant__ FmxDev i
 
 // patterns for the k-mer table: entry t is the k-mer whose FIRST character is the most significant
 // base-sigma digit of t, so table order = lexicographic order = order of the SA ranges
-__global__ void k_kmer_patterns(uint32_t k, uint32_t sigma, uint64_t entries, uint8_t *pat) {
+__global__ void k_kmer_patterns(uint32_t k, uint32_t sigma, uint64_t first, uint64_t entries, uint8_t *pat) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= entries) return;
-    uint64_t v = t;
+    uint64_t v = first + t;
     for (uint32_t j = k; j-- > 0;) {
-        pat[t * k + j] = (uint8_t)(v % sigma);
+        pat[t * k + j] = (uint8_t)(v % sigma + 1);  // digit d stands for the character d + 1
         v /= sigma;
     }
 }
@@ -656,7 +681,7 @@ __global__ void k_kmer_pack(const uint64_t *s, const uint64_t *e, uint64_t entri
 
 // bucketing pass 1: bucket[p] = k-mer table index of pattern p (the extra bucket `entries` takes
 // patterns the table cannot serve); hist[bucket]++
-__global__ void __launch_bounds__(256) k_bucket_count(const __grid_constant__ SearchArgs a, uint32_t sigma, uint32_t maxc,
+__global__ void __launch_bounds__(256) k_bucket_count(const __grid_constant__ SearchArgs a, uint32_t maxc,
                                                        uint32_t entries, uint32_t *bucket, uint32_t *hist) {
     uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.npat) return;
@@ -665,7 +690,7 @@ __global__ void __launch_bounds__(256) k_bucket_count(const __grid_constant__ Se
     pattern_span(a, p, beg, len);
     if (len >= a.kmer_k) {
         uint32_t v;
-        if (kmer_index(a.pat + beg, len, a.kmer_k, sigma, maxc, v)) idx = v;
+        if (kmer_index(a.pat + beg, len, a.kmer_k, maxc, v)) idx = v;
     }
     bucket[p] = idx;
     atomicAdd(hist + idx, 1u);
@@ -684,8 +709,7 @@ __global__ void __launch_bounds__(256) k_bucket_scatter(const uint32_t *bucket, 
 template <int KIND, int LAYOUT>
 __global__ void __launch_bounds__(256) k_search_init(const __grid_constant__ FmxDev ix, const __grid_constant__ SearchArgs a) {
     const uint32_t lane = threadIdx.x & 31;
-    const bool use_tab = a.kmer_tab != nullptr && a.init_s == nullptr;
-    const uint32_t K = a.kmer_k, sigma = ix.cs_len;
+    const bool use_tab = a.init_s == nullptr;
     unsigned long long steps = 0;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t rounds = (a.npat + stride - 1) / stride;
@@ -701,20 +725,11 @@ __global__ void __launch_bounds__(256) k_search_init(const __grid_constant__ Fmx
             uint32_t s = a.init_s ? (uint32_t)a.init_s[p] : a.s0;
             uint32_t e = a.init_e ? (uint32_t)a.init_e[p] : a.e0;
             bool done = k == 0;
-            if (use_tab && k >= K) {
-                uint32_t idx;
-                if (kmer_index(q, k, K, sigma, ix.max_character, idx)) {  // else: walk the slow path so the error shows up (or not) exactly as in the reference
-                    uint2 t = __ldg(a.kmer_tab + idx);
-                    s = t.x;
-                    e = t.y;
-                    k -= K;
-                    if (s == e) {
-                        steps += __ldg(a.kmer_steps + idx);
-                        done = true;
-                    } else {
-                        steps += K;
-                        done = k == 0;
-                    }
+            if (use_tab) {
+                uint32_t it = 0;
+                if (kmer_lookup(a, ix.max_character, q, k, s, e, it)) {
+                    steps += it;
+                    done = k == 0;
                 }
             }
             todo = !done;

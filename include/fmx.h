@@ -99,7 +99,9 @@ int fmx_build_suffix_array_device(const void *text, uint64_t n, uint32_t char_wi
 
 /* Tuning knobs (A/B measurement; results never change): "search_persistent" 0|1 (persistent
  * per-lane-refill search kernels instead of one pattern per thread), "kmer" 0|1 (memoised first
- * search iterations), "bucket" -1|0|1 (visit the batch in k-mer bucket order: auto / never / always),
+ * search iterations), "kmer_big" 0|1 (the large HBM-resident table), "kmer_budget_mb" (rebuild the
+ * large table with that many MiB of HBM; default = twice the index size, FMX_KMER_BUDGET_MB at
+ * build time), "bucket" -1|0|1 (visit the batch in k-mer bucket order: auto / never / always),
  * "l2_fetch_granularity" 32|64|128, "persist_blocks_per_sm" 1..32, "pipeline_chunk" (patterns per chunk of
  * fmx_search_locate_batch's copy/compute pipeline, 0 = automatic).  The environment variable
  * FMX_FORCE_WAVELET=1 makes construction keep the binary wavelet matrix for small alphabets. */
@@ -118,6 +120,8 @@ uint32_t fmx_index_sample_level(const fmx_index *idx);
 /* 32-byte sectors one rank/access probe of the BWT touches in this index's device layout:
  * L for the binary wavelet matrix, 1 for the quaternary level used when max_character <= 4. */
 uint32_t fmx_index_sectors_per_rank(const fmx_index *idx);
+/* characters memoised by the small (big = 0) / large (big = 1) k-mer table of fresh searches; 0 = none */
+uint32_t fmx_index_kmer_k(const fmx_index *idx, int big);
 
 /* ---------------------------------------------------------------- search / count
  * Batched SearchIndex::search / search_prefix / search_suffix / search_exact and

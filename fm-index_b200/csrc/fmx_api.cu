@@ -738,7 +738,7 @@ static int locate_rows(const fmx_index *idx, DevBuf *buf, int prefix_only, const
     k_mark_owners<<<grid_for(npat, 256), 256, 0, st>>>(d_off, npat, d_owner);
     LAUNCH_CHECK();
     if ((rc = device_scan<uint32_t, uint32_t, OpMax, false>(d_owner, total, d_owner, OpMax(), false, buf[B_TILES], st))) return rc;
-    k_expand_rows<<<grid_for(total, 256), 256, 0, st>>>(d_s, d_off, d_owner, total, d_rows);
+    k_expand_rows<<<grid_for(total, 256), 256, 0, st>>>(d_s, d_off, d_owner, total, nullptr, d_rows);
     LAUNCH_CHECK();
     if (!prefix_only) {
         *hits_out = total;
@@ -786,12 +786,13 @@ static int locate_prepare(const fmx_index *idx, int prefix_only, const uint64_t 
 }
 
 static int locate_fill(const fmx_index *idx, const uint32_t *d_rows, uint64_t total, uint64_t *d_pos, uint64_t *d_pid,
-                       cudaStream_t st, bool count_work = true) {
+                       cudaStream_t st, bool count_work = true, const uint64_t *total_dev = nullptr) {
     if (count_work) CUDA_TRY(cudaMemsetAsync(idx->d_work + 1, 0, sizeof(unsigned long long), st));
     if (total == 0) return 0;
     LocateArgs a;
     a.rows = d_rows;
     a.total = total;
+    a.total_dev = total_dev;
     a.positions = d_pos;
     a.piece_ids = d_pid;
     a.work = count_work ? idx->d_work : nullptr;
@@ -835,6 +836,41 @@ extern "C" int fmx_locate_fill_device(const fmx_index *idx, int prefix_only, con
     // the rows prepared by the matching fmx_locate_count_device call are still in scratch
     const uint32_t *rows = prefix_only ? idx->buf[B_ROWS2].as<uint32_t>() : idx->buf[B_ROWS].as<uint32_t>();
     return locate_fill(idx, rows, total_hits, d_positions, d_piece_ids, pick_stream(idx, stream));
+}
+
+// Fully asynchronous locate on device buffers (no host synchronisation, graph-capturable): the hit
+// total stays on the device (d_hit_off[npat]); launches are sized by `capacity`.
+extern "C" int fmx_locate_batch_device(const fmx_index *idx, int prefix_only, const uint64_t *d_s, const uint64_t *d_e,
+                                       uint64_t npat, uint64_t *d_hit_off, uint64_t *d_positions, uint64_t *d_piece_ids,
+                                       uint64_t capacity, void *stream) {
+    if (!idx || !d_hit_off || (!d_positions && !d_piece_ids)) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    int rc = locate_args_ok(idx, d_piece_ids != nullptr);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(idx->device));
+    cudaStream_t st = pick_stream(idx, stream);
+    if (prefix_only) {  // the L == 0 filter needs the kept count on the host: synchronous path
+        uint64_t total = 0;
+        const uint32_t *rows = nullptr;
+        if ((rc = locate_prepare(idx, prefix_only, d_s, d_e, npat, d_hit_off, &total, &rows, st))) return rc;
+        if (total > capacity) total = capacity;
+        return locate_fill(idx, rows, total, d_positions, d_piece_ids, st);
+    }
+    DevBuf *buf = idx->buf;
+    if ((rc = locate_counts(idx, buf, d_s, d_e, npat, d_hit_off, st))) return rc;
+    if (capacity == 0 || npat == 0) return FMX_OK;
+    if (capacity >= 0xFFFFFFFFull * 4) return fail(FMX_ERR_UNSUPPORTED, "capacity too large");
+    if ((rc = buf[B_OWNER].ensure(capacity * 4))) return rc;
+    if ((rc = buf[B_ROWS].ensure(capacity * 4))) return rc;
+    uint32_t *d_owner = buf[B_OWNER].as<uint32_t>();
+    uint32_t *d_rows = buf[B_ROWS].as<uint32_t>();
+    const uint64_t *d_total = d_hit_off + npat;
+    CUDA_TRY(cudaMemsetAsync(d_owner, 0, capacity * 4, st));
+    k_mark_owners_capped<<<grid_for(npat, 256), 256, 0, st>>>(d_hit_off, npat, capacity, d_owner);
+    LAUNCH_CHECK();
+    if ((rc = device_scan<uint32_t, uint32_t, OpMax, false>(d_owner, capacity, d_owner, OpMax(), false, buf[B_TILES], st))) return rc;
+    k_expand_rows<<<grid_for(capacity, 256), 256, 0, st>>>(d_s, d_hit_off, d_owner, capacity, d_total, d_rows);
+    LAUNCH_CHECK();
+    return locate_fill(idx, d_rows, capacity, d_positions, d_piece_ids, st, true, d_total);
 }
 
 extern "C" int fmx_locate_batch(const fmx_index *idx, int prefix_only, const uint64_t *s, const uint64_t *e, uint64_t npat,

@@ -841,10 +841,18 @@ __global__ void k_mark_owners(const uint64_t *off, uint64_t npat, uint32_t *owne
     if (p < npat && off[p + 1] > off[p]) owner[off[p]] = (uint32_t)p + 1u;
 }
 
+// the same when only the first `cap` rows have room
+__global__ void k_mark_owners_capped(const uint64_t *off, uint64_t npat, uint64_t cap, uint32_t *owner) {
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < npat && off[p + 1] > off[p] && off[p] < cap) owner[off[p]] = (uint32_t)p + 1u;
+}
+
 // rows[h] = s[p] + (h - off[p]) with p = owner[h] - 1 (after the max-scan of owner)
+// total_dev (nullable): the real number of rows, on the device (fully asynchronous locate)
 __global__ void k_expand_rows(const uint64_t *s, const uint64_t *off, const uint32_t *owner, uint64_t total,
-                              uint32_t *rows) {
+                              const uint64_t *total_dev, uint32_t *rows) {
     uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (total_dev && *total_dev < total) total = *total_dev;
     if (h < total) {
         uint32_t p = owner[h] - 1u;
         rows[h] = (uint32_t)(s[p] + (h - off[p]));
@@ -882,7 +890,8 @@ __global__ void k_filtered_offsets(const uint64_t *off, const uint64_t *fpos, ui
 
 struct LocateArgs {
     const uint32_t *rows;
-    uint64_t total;
+    uint64_t total;             // number of hits, or the capacity when total_dev is given
+    const uint64_t *total_dev;  // nullable: the real number of hits, on the device
     uint64_t *positions;  // nullable
     uint64_t *piece_ids;  // nullable (MultiPieces)
     unsigned long long *work;  // [1] += executed LF steps
@@ -899,7 +908,9 @@ __global__ void __launch_bounds__(256) k_locate(const __grid_constant__ FmxDev i
     unsigned long long steps = 0;
     const uint32_t mask = (1u << ix.sa_level) - 1u;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < a.total; h += stride) {
+    uint64_t total = a.total;
+    if (a.total_dev && *a.total_dev < total) total = *a.total_dev;
+    for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < total; h += stride) {
         uint32_t row = a.rows[h];
         uint32_t st = 0, sym;
         while (row & mask) {

@@ -177,6 +177,15 @@ int fmx_locate_fill_device(const fmx_index *idx, int prefix_only, const uint64_t
                            uint64_t total_hits, uint64_t *d_positions, uint64_t *d_piece_ids,
                            void *stream);
 
+/* Fully asynchronous form (no host synchronisation, CUDA-graph capturable when prefix_only == 0):
+ * launches are sized by `capacity` (entries of d_positions / d_piece_ids); the real number of hits
+ * stays on the device in d_hit_off[npat]; if it exceeds `capacity` only the first `capacity` hits are
+ * written.  Scratch must have been sized by an earlier identical call before a graph capture. */
+int fmx_locate_batch_device(const fmx_index *idx, int prefix_only, const uint64_t *d_s,
+                            const uint64_t *d_e, uint64_t npat, uint64_t *d_hit_off,
+                            uint64_t *d_positions, uint64_t *d_piece_ids, uint64_t capacity,
+                            void *stream);
+
 /* ---------------------------------------------------------------- extraction
  * Batched Match::iter_chars_backward / iter_chars_forward taken k characters deep
  * -- src/wrapper.rs:143-183, 229-235.  rows are SA rows (the `i` of a Match).

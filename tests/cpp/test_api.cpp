@@ -41,7 +41,7 @@ int main() {
         auto b = index.search_batch({"dolor", "ipsum", "zzz", ""}, true);
         CHECK(b.count(0) == 4 && b.count(1) == 1 && b.count(2) == 0 && b.count(3) == raw.size());
         CHECK((std::vector<uint64_t>(b.positions.begin(), b.positions.begin() + 4) == std::vector<uint64_t>{246, 12, 300, 103}));
-        CHECK(search.search("m ").count() == 1 && index.search("or").search("dol").count() == 4);  // "ipsum dolor"
+        CHECK(search.search("m ").count() == 2 && index.search("or").search("dol").count() == 4);  // "ipsum dolor", "cillum dolore"
     }
     {
         std::string raw = std::string("mississippi") + '\0';

@@ -468,3 +468,35 @@ def test_cpp_facade(tmp_path):
                            "-L", libdir, "-lfmx_b200", f"-Wl,-rpath,{libdir}"])
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and "cpp facade ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_async_device_locate_matches_host_api():
+    """fmx_locate_batch_device (no host synchronisation; the total stays on the device) against the
+    host-buffer API, for an exact, a generous and a too-small capacity"""
+    import ctypes as C
+    import torch
+    text = dna(400_000, 17)
+    pats, _ = mixed_patterns(text, 30_000, 20, 18)
+    index = fmx.FMIndexWithLocate.new(fmx.Text.with_max_character(text, 4), 2)
+    ref = index.search_batch(pats)
+    rh, rp = ref.locate()
+    total = int(rh[-1])
+    L, h = index._L, index._h
+    d_pat = torch.from_numpy(pats).cuda()
+    npat, m = pats.shape
+    d_s = torch.empty(npat, dtype=torch.int64, device="cuda")
+    d_e = torch.empty_like(d_s)
+    d_off = torch.empty(npat + 1, dtype=torch.int64, device="cuda")
+    st = torch.cuda.Stream()
+    sp = C.c_void_p(st.cuda_stream)
+    assert L.fmx_search_batch_device(h, 0, d_pat.data_ptr(), None, m, npat, None, None, d_s.data_ptr(), d_e.data_ptr(), sp) == 0
+    for cap in (total, total + 5000, total // 2):
+        d_pos = torch.full((max(cap, 1),), -1, dtype=torch.int64, device="cuda")
+        assert L.fmx_locate_batch_device(h, 0, d_s.data_ptr(), d_e.data_ptr(), npat, d_off.data_ptr(), d_pos.data_ptr(),
+                                         None, cap, sp) == 0, L.fmx_last_error()
+        st.synchronize()
+        assert np.array_equal(d_off.cpu().numpy().view(np.uint64), rh)
+        k = min(cap, total)
+        assert np.array_equal(d_pos[:k].cpu().numpy().view(np.uint64), rp[:k])
+        if cap > total:
+            assert bool((d_pos[total:] == -1).all())

@@ -529,9 +529,10 @@ def main():
 
     def e2e_step():
         # the call a user makes: host patterns in, SA ranges + CSR hit lists out (one fused C-ABI call)
+        # (SA ranges are internal state of the crate's Search object -- get_range is test-only,
+        # wrapper.rs:126-129 -- so the user-visible result is counts = diff(hit_off) and the positions)
         chk(L.fmx_search_locate_batch(h, 0, h_pat.data_ptr(), None if h_off is None else h_off.data_ptr(), m, npat,
-                                      h_s.data_ptr(), h_e.data_ptr(), h_hoff.data_ptr(), h_pos.data_ptr(), None, cap,
-                                      C.byref(nhits)))
+                                      None, None, h_hoff.data_ptr(), h_pos.data_ptr(), None, cap, C.byref(nhits)))
         return int(nhits.value)
 
     for _ in range(2):
@@ -551,7 +552,7 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
     h2d = int(h_pat.numel()) + (8 * (npat + 1) if h_off is not None else 0)
-    d2h = 2 * 8 * npat + 8 * (npat + 1) + 8 * nh
+    d2h = 8 * (npat + 1) + 8 * nh
 
     if rank != 0:
         if world > 1:
@@ -643,7 +644,7 @@ def main():
         "located_hits_per_s": hits_all / (ms_per_step * 1e-3),
         "hits_per_step": hits_all,
         "e2e": {"value": world * npat / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_s * 1e3, "api": "fmx_search_locate_batch (host buffers, pinned; chunked H2D/kernel/D2H pipeline)"},
+                "ms_per_step": e2e_s * 1e3, "api": "fmx_search_locate_batch: host patterns in, CSR hit offsets (counts) + positions out (pinned buffers; chunked H2D/kernel/D2H pipeline)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,

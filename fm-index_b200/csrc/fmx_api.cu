@@ -66,6 +66,7 @@ enum { B_QUEUE, B_BUCKET, B_BHIST, B_ORDER, B_PAT, B_OFF, B_S, B_E, B_INS, B_INE
        B_OUT8, B_OUT32, B_COUNT };
 
 // one lane of the chunked H2D / kernels / D2H pipeline (fmx_search_locate_batch)
+#define FMX_LANES 4
 struct Lane {
     DevBuf buf[B_COUNT];
     cudaStream_t st = nullptr;
@@ -99,7 +100,7 @@ struct fmx_index {
     uint64_t opt_pipeline_chunk = 0;  // patterns per pipeline chunk (0 = automatic)
     int opt_bucket = 0;               // 1: visit the batch in k-mer bucket order (lost the A/B, kept for experiments); -1 auto
     mutable DevBuf buf[B_COUNT];
-    mutable Lane lane[2];
+    mutable Lane lane[FMX_LANES];
     mutable bool lanes_ready = false;
     mutable std::mutex mu;
 };
@@ -969,7 +970,7 @@ extern "C" int fmx_search_locate_batch(const fmx_index *idx, int mode, const uin
     bool overflow = false;
 
     auto stage1 = [&](uint64_t c) -> int {  // H2D patterns, search, candidate counts (all asynchronous)
-        Lane &L = idx->lane[c & 1];
+        Lane &L = idx->lane[c % FMX_LANES];
         const uint64_t lo = c * chunk, n = (lo + chunk < npat ? chunk : npat - lo);
         const uint64_t off0 = pat_off ? pat_off[lo] : lo * fixed_len;
         const uint64_t nbytes = (pat_off ? pat_off[lo + n] : (lo + n) * fixed_len) - off0;
@@ -998,7 +999,7 @@ extern "C" int fmx_search_locate_batch(const fmx_index *idx, int mode, const uin
         return 0;
     };
     auto stage2 = [&](uint64_t c) -> int {  // rows, LF walks, D2H of offsets and positions
-        Lane &L = idx->lane[c & 1];
+        Lane &L = idx->lane[c % FMX_LANES];
         const uint64_t lo = c * chunk, n = (lo + chunk < npat ? chunk : npat - lo);
         CUDA_TRY(cudaEventSynchronize(L.ev));
         const uint64_t cand = *L.h_total;
@@ -1042,9 +1043,11 @@ extern "C" int fmx_search_locate_batch(const fmx_index *idx, int mode, const uin
         return 0;
     };
     rc = 0;
-    for (uint64_t c = 0; c <= nchunks && rc == 0; c++) {
+    // stage 1 runs FMX_LANES - 1 chunks ahead of stage 2: the H2D copies queue back to back on the
+    // copy engine while the host waits for hit totals of earlier chunks
+    for (uint64_t c = 0; c < nchunks + FMX_LANES - 1 && rc == 0; c++) {
         if (c < nchunks) rc = stage1(c);
-        if (rc == 0 && c >= 1) rc = stage2(c - 1);
+        if (rc == 0 && c >= FMX_LANES - 1 && c - (FMX_LANES - 1) < nchunks) rc = stage2(c - (FMX_LANES - 1));
     }
     for (auto &l : idx->lane) cudaStreamSynchronize(l.st);
     if (rc) return rc;

@@ -156,7 +156,7 @@ int fmx_locate_batch(const fmx_index *idx, int prefix_only, const uint64_t *s, c
                      uint64_t npat, uint64_t *hit_off, uint64_t **positions, uint64_t **piece_ids);
 /* Fused search + locate for host buffers: the batched form of
  *     index.search(p).iter_matches().map(|m| m.locate())           (README.md:49-64)
- * in ONE call.  The batch is cut into chunks that flow through a two-lane pipeline (H2D copy of
+ * in ONE call.  The batch is cut into chunks that flow through a four-lane pipeline (H2D copy of
  * chunk k+1 overlaps the kernels of chunk k and the D2H copy of chunk k-1); SA ranges never make
  * the round trip to the host in between.  out_s / out_e (nullable) receive the SA ranges,
  * hit_off (npat+1) the exclusive prefix sum of hit counts, positions / piece_ids (nullable,

@@ -190,9 +190,92 @@ struct Q4Vec {
     }
 };
 
-static bool want_q4(uint64_t mc, const uint8_t *seq, uint64_t n) {
+// Quaternary wavelet matrix (fmx_layout.h): one Q4-style level per two bits of the symbol.
+struct WM4 {
+    uint32_t Lq = 0;
+    std::vector<std::vector<uint32_t>> lv;  // blocks per level
+    uint64_t qoff[FMX_MAX_QLEVELS][4] = {};
+    static inline uint32_t digit(uint32_t c, uint32_t Lq, uint32_t l) { return (c >> (2 * (Lq - 1 - l))) & 3u; }
+    void build(const uint8_t *seq, uint64_t n, uint32_t L) {
+        Lq = (L + 1) / 2;
+        lv.assign(Lq, {});
+        std::vector<uint8_t> cur(seq, seq + n), nxt(n);
+        const uint64_t nblk = n / 64 + 1;
+        const uint64_t chunk = 64ull * 8192;
+        const int64_t nchunks = (int64_t)((n + chunk - 1) / chunk);
+        std::vector<uint64_t> cc((size_t)(nchunks + 1) * 4, 0);
+        for (uint32_t l = 0; l < Lq; l++) {
+            std::vector<uint32_t> &w = lv[l];
+            w.assign(nblk * 8, 0);
+#pragma omp parallel for schedule(static)
+            for (int64_t b = 0; b < (int64_t)nblk; b++) {
+                uint32_t *blk = &w[(uint64_t)b * 8];
+                uint32_t cnt[4] = {0, 0, 0, 0};
+                uint64_t lo = (uint64_t)b * 64, hi = lo + 64 < n ? lo + 64 : n;
+                for (uint64_t i = lo; i < hi; i++) {
+                    uint32_t d = digit(cur[i], Lq, l), t = (uint32_t)(i - lo);
+                    blk[4 + (t >> 4)] |= d << (2 * (t & 15));
+                    cnt[d]++;
+                }
+                for (int c = 0; c < 4; c++) blk[c] = cnt[c];
+            }
+            uint32_t acc[4] = {0, 0, 0, 0};
+            for (uint64_t b = 0; b < nblk; b++) {
+                uint32_t *blk = &w[b * 8];
+                for (int c = 0; c < 4; c++) {
+                    uint32_t v = blk[c];
+                    blk[c] = acc[c];
+                    acc[c] += v;
+                }
+            }
+            uint64_t o = 0;
+            for (int d = 0; d < 4; d++) {
+                qoff[l][d] = o;
+                o += acc[d];
+            }
+            if (l + 1 < Lq) {  // stable partition by digit
+#pragma omp parallel for schedule(static)
+                for (int64_t c = 0; c < nchunks; c++) {
+                    uint64_t lo = (uint64_t)c * chunk, hi = lo + chunk < n ? lo + chunk : n, k[4] = {0, 0, 0, 0};
+                    for (uint64_t i = lo; i < hi; i++) k[digit(cur[i], Lq, l)]++;
+                    for (int d = 0; d < 4; d++) cc[(size_t)(c + 1) * 4 + d] = k[d];
+                }
+                for (int d = 0; d < 4; d++) cc[d] = qoff[l][d];
+                for (int64_t c = 0; c < nchunks; c++)
+                    for (int d = 0; d < 4; d++) cc[(size_t)(c + 1) * 4 + d] += cc[(size_t)c * 4 + d];
+#pragma omp parallel for schedule(static)
+                for (int64_t c = 0; c < nchunks; c++) {
+                    uint64_t lo = (uint64_t)c * chunk, hi = lo + chunk < n ? lo + chunk : n;
+                    uint64_t p[4] = {cc[(size_t)c * 4], cc[(size_t)c * 4 + 1], cc[(size_t)c * 4 + 2], cc[(size_t)c * 4 + 3]};
+                    for (uint64_t i = lo; i < hi; i++) nxt[p[digit(cur[i], Lq, l)]++] = cur[i];
+                }
+                cur.swap(nxt);
+            }
+        }
+    }
+    // occurrences of digit d among the first pos entries of level l
+    uint64_t rank(uint32_t l, uint64_t pos, uint32_t d) const {
+        const uint32_t *blk = &lv[l][(pos / 64) * 8];
+        uint64_t c = blk[d];
+        for (uint32_t t = 0; t < pos % 64; t++) c += ((blk[4 + (t >> 4)] >> (2 * (t & 15))) & 3u) == d;
+        return c;
+    }
+    uint64_t walk(uint64_t pos, uint32_t c) const {
+        for (uint32_t l = 0; l < Lq; l++) {
+            uint32_t d = digit(c, Lq, l);
+            pos = qoff[l][d] + rank(l, pos, d);
+        }
+        return pos;
+    }
+};
+
+static bool force_binary_wavelet() {
     const char *force = std::getenv("FMX_FORCE_WAVELET");
-    if (force && force[0] && force[0] != '0') return false;
+    return force && force[0] && force[0] != '0';
+}
+
+static bool want_q4(uint64_t mc, const uint8_t *seq, uint64_t n) {
+    if (force_binary_wavelet()) return false;
     if (mc > 4) return false;
     uint64_t zeros = 0;
     for (uint64_t i = 0; i < n; i++) zeros += seq[i] == 0;
@@ -268,7 +351,9 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
 
     WMat wm;
     Q4Vec q4;
+    WM4 wm4;
     bool use_q4 = false;
+    const bool use_wm4_else = !force_binary_wavelet();  // every alphabet Q4 does not take
     std::vector<uint32_t> cs(cs_len + 1, 0), adj(cs_len, 0);
     std::vector<uint32_t> doc, piece_end, bsel, bpsel;
     RBVec rb_b(0), rb_bp(0);
@@ -284,6 +369,7 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
         cs[cs_len] = (uint32_t)n;
         use_q4 = want_q4(mc, bwt.data(), n);
         if (use_q4) q4.build(bwt.data(), n);
+        else if (use_wm4_else) wm4.build(bwt.data(), n, L);
         else build_wavelet(bwt.data(), n, L, wm);
         hdr.seq_len = n;
         if (kind == FMX_KIND_MULTI) {
@@ -331,6 +417,7 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
         hdr.seq_len = r;
         use_q4 = want_q4(mc, heads.data(), r);
         if (use_q4) q4.build(heads.data(), r);
+        else if (use_wm4_else) wm4.build(heads.data(), r, L);
         else build_wavelet(heads.data(), r, L, wm);
         bsel.assign(r + 1, (uint32_t)n);
         for (uint64_t j = 0; j < r; j++) bsel[j] = starts[j];
@@ -362,6 +449,12 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
     if (use_q4) {
         hdr.layout = FMX_LAYOUT_QUAT;
         hdr.nexc = (uint32_t)q4.exc.size();
+    } else if (use_wm4_else) {
+        hdr.layout = FMX_LAYOUT_WM4;
+        hdr.qlevels = wm4.Lq;
+        for (uint32_t l = 0; l < wm4.Lq; l++)
+            for (int d = 0; d < 4; d++) hdr.qoff[l][d] = wm4.qoff[l][d];
+        for (uint32_t c = 0; c < cs_len; c++) adj[c] = cs[c] - (uint32_t)wm4.walk(0, c);
     } else {
         hdr.layout = FMX_LAYOUT_WAVELET;
         for (uint32_t l = 0; l < L; l++) hdr.zeros[l] = wm.zeros[l];
@@ -390,6 +483,8 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
     if (use_q4) {
         sec[SEC_LEVEL0] = {q4.w.data(), q4.w.size() * 4};
         if (!q4.exc.empty()) sec[SEC_EXC] = {q4.exc.data(), q4.exc.size() * 4};
+    } else if (use_wm4_else) {
+        for (uint32_t l = 0; l < wm4.Lq; l++) sec[SEC_LEVEL0 + l] = {wm4.lv[l].data(), wm4.lv[l].size() * 4};
     } else {
         for (uint32_t l = 0; l < L; l++) sec[SEC_LEVEL0 + l] = {wm.lv[l].w.data(), wm.lv[l].bytes()};
     }
@@ -428,7 +523,7 @@ int check_blob(const void *blob, uint64_t bytes, FmxBlobHeader &hdr, std::string
         err = "not an fmx blob (bad magic or version)";
         return FMX_ERR_INVALID_ARG;
     }
-    if (hdr.total_bytes != bytes || hdr.levels == 0 || hdr.levels > FMX_MAX_LEVELS || hdr.kind > 2 || hdr.layout > 1 ||
+    if (hdr.total_bytes != bytes || hdr.levels == 0 || hdr.levels > FMX_MAX_LEVELS || hdr.kind > 2 || hdr.layout > 2 || hdr.qlevels > FMX_MAX_QLEVELS ||
         hdr.nexc > FMX_MAX_EXC) {
         err = "corrupt fmx blob header";
         return FMX_ERR_INVALID_ARG;

@@ -117,13 +117,16 @@ static inline unsigned grid_for(uint64_t n, unsigned threads) { return (unsigned
 template <class F>
 static void dispatch(const fmx_index *idx, F &&f) {
     using std::integral_constant;
-    switch (idx->hdr.kind * 2 + idx->hdr.layout) {
+    switch (idx->hdr.kind * 3 + idx->hdr.layout) {
         case 0: f(integral_constant<int, 0>{}, integral_constant<int, 0>{}); break;
         case 1: f(integral_constant<int, 0>{}, integral_constant<int, 1>{}); break;
-        case 2: f(integral_constant<int, 1>{}, integral_constant<int, 0>{}); break;
-        case 3: f(integral_constant<int, 1>{}, integral_constant<int, 1>{}); break;
-        case 4: f(integral_constant<int, 2>{}, integral_constant<int, 0>{}); break;
-        default: f(integral_constant<int, 2>{}, integral_constant<int, 1>{}); break;
+        case 2: f(integral_constant<int, 0>{}, integral_constant<int, 2>{}); break;
+        case 3: f(integral_constant<int, 1>{}, integral_constant<int, 0>{}); break;
+        case 4: f(integral_constant<int, 1>{}, integral_constant<int, 1>{}); break;
+        case 5: f(integral_constant<int, 1>{}, integral_constant<int, 2>{}); break;
+        case 6: f(integral_constant<int, 2>{}, integral_constant<int, 0>{}); break;
+        case 7: f(integral_constant<int, 2>{}, integral_constant<int, 1>{}); break;
+        default: f(integral_constant<int, 2>{}, integral_constant<int, 2>{}); break;
     }
 }
 
@@ -222,6 +225,9 @@ static int upload(std::vector<uint8_t> &&blob, int device, fmx_index **out) {
         d.lv[l] = static_cast<const uint4 *>(sec(SEC_LEVEL0 + l));
         d.zeros[l] = (uint32_t)hdr.zeros[l];
     }
+    d.qlevels = hdr.qlevels;
+    for (uint32_t l = 0; l < hdr.qlevels; l++)
+        for (int g = 0; g < 4; g++) d.qoff[l * 4 + g] = (uint32_t)hdr.qoff[l][g];
     d.adj = static_cast<const uint32_t *>(sec(SEC_ADJ));
     d.cs = static_cast<const uint32_t *>(sec(SEC_CS));
     d.sa = static_cast<const uint32_t *>(sec(SEC_SA));
@@ -363,7 +369,8 @@ int fmx_index_device(const fmx_index *idx) { return idx ? idx->device : -1; }
 uint32_t fmx_index_wavelet_levels(const fmx_index *idx) { return idx ? idx->hdr.levels : 0; }
 uint32_t fmx_index_sample_level(const fmx_index *idx) { return idx ? idx->hdr.sa_level : 0; }
 uint32_t fmx_index_sectors_per_rank(const fmx_index *idx) {
-    return idx ? (idx->hdr.layout == FMX_LAYOUT_QUAT ? 1u : idx->hdr.levels) : 0;
+    if (!idx) return 0;
+    return idx->hdr.layout == FMX_LAYOUT_QUAT ? 1u : (idx->hdr.layout == FMX_LAYOUT_WM4 ? idx->hdr.qlevels : idx->hdr.levels);
 }
 
 }  // extern "C"

@@ -26,7 +26,13 @@
 // collapse into ONE level of arity 4: 32-byte blocks
 //       word 0..3 : u32 occurrences of the 2-bit codes 0..3 in all preceding blocks
 //       word 4..7 : 64 two-bit codes (code = symbol - 1)
-// so lf_map2(c, i) = cs[c] + rank(i, c) costs ONE sector instead of three.  The rare symbol 0
+// so lf_map2(c, i) = cs[c] + rank(i, c) costs ONE sector instead of three.
+//
+// QUATERNARY WAVELET MATRIX ("WM4", the default for every other alphabet).  The same 32-byte
+// blocks, one level per TWO bits of the symbol (ceil(L/2) levels, most significant digit first),
+// symbols stably partitioned by digit into four groups starting at qoff[l][0..3].  A walk is
+//       pos <- qoff[l][d] + rank_d(level l, pos),   d = digit l of c
+// i.e. HALF the sectors of the binary matrix (4 instead of 8 for bytes).  adj[] as above.  The rare symbol 0
 // (the \0 terminators: 1 for a single text, one per piece for MultiPieces) is stored as code 0
 // and its positions are listed in SEC_EXC (sorted; staged in shared memory), which corrects
 // rank(., 1) and answers rank(., 0) / access exactly.  Results are identical to the wavelet
@@ -38,12 +44,14 @@
 #include <vector_types.h>  // uint4 (CUDA toolkit header, host-safe)
 
 #define FMX_BLOB_MAGIC 0x3030324258584d46ull /* "FMXXB200" little endian-ish tag */
-#define FMX_BLOB_VERSION 3u
+#define FMX_BLOB_VERSION 4u
 #define FMX_MAX_LEVELS 8
 #define FMX_RB_BITS 192u
 #define FMX_MAX_EXC 1024u   /* Q4 layout: at most this many \0 symbols in the sequence */
 #define FMX_LAYOUT_WAVELET 0u
 #define FMX_LAYOUT_QUAT 1u
+#define FMX_LAYOUT_WM4 2u
+#define FMX_MAX_QLEVELS 4
 #define FMX_SECTION_ALIGN 256u
 
 enum FmxSection : uint32_t {
@@ -85,9 +93,12 @@ struct FmxBlobHeader {
     uint64_t zeros[FMX_MAX_LEVELS];  // zeros per level
     uint64_t total_bytes;
     FmxSectionEntry sec[SEC_COUNT];
-    uint32_t layout;  // FMX_LAYOUT_WAVELET | FMX_LAYOUT_QUAT
+    uint32_t layout;  // FMX_LAYOUT_WAVELET | FMX_LAYOUT_QUAT | FMX_LAYOUT_WM4
     uint32_t nexc;    // Q4: number of zeros in the sequence
-    uint64_t reserved[7];
+    uint32_t qlevels; // WM4: ceil(levels / 2)
+    uint32_t pad0;
+    uint64_t qoff[FMX_MAX_QLEVELS][4];  // WM4: start of digit group d at level l
+    uint64_t reserved[6];
 };
 
 // What the kernels see (passed by value as a __grid_constant__ parameter).
@@ -117,5 +128,6 @@ struct FmxDev {
     uint32_t runs;
     uint32_t layout;
     uint32_t nexc;
-    uint32_t pad;
+    uint32_t qlevels;
+    uint32_t qoff[FMX_MAX_QLEVELS * 4];
 };

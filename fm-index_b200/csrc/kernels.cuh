@@ -122,6 +122,7 @@ __device__ __forceinline__ uint32_t rbv_select0(const uint4 *__restrict__ v, uin
 
 #define FMX_LAYOUT_WM 0  // binary wavelet matrix, L levels (any alphabet)
 #define FMX_LAYOUT_Q4 1  // one quaternary level (max_character <= 4, few \0): ONE sector per lf_map2
+#define FMX_LAYOUT_W4 2  // quaternary wavelet matrix, ceil(L/2) levels (every other alphabet)
 
 template <int LAYOUT>
 struct Tabs {
@@ -298,7 +299,92 @@ __device__ __forceinline__ uint32_t q4_select(const FmxDev &ix, const uint32_t *
     return pos;  // unreachable for a valid k
 }
 
-// ------------------------------------------------------------------ sequence primitives, both layouts
+// ------------------------------------------------------------------ quaternary wavelet matrix (LAYOUT_W4)
+// Q4-style blocks (u32 cnt[4] + 64 two-bit codes), one level per two bits of the symbol, most
+// significant digit first; the codes are plain digits (no exception list).  Symbols are stably
+// partitioned by digit: group d of level l starts at qoff[l][d].
+
+__device__ __forceinline__ uint32_t w4_digit(const FmxDev &ix, uint32_t c, uint32_t l) {
+    return (c >> (2u * (ix.qlevels - 1u - l))) & 3u;
+}
+// position after descending one level along digit d, given the block of pos
+__device__ __forceinline__ uint32_t w4_down(const FmxDev &ix, const RB &b, uint32_t l, uint32_t d, uint32_t pos) {
+    return ix.qoff[l * 4u + d] + q4_cnt(b, d) + q4_count(b, pos & 63u, d);
+}
+
+__device__ __forceinline__ uint32_t w4_walk(const FmxDev &ix, uint32_t c, uint32_t pos) {
+    const uint32_t Lq = ix.qlevels;
+#pragma unroll 1
+    for (uint32_t l = 0; l < Lq; l++) {
+        RB b = rb_load(ix.lv[l], pos >> 6);
+        pos = w4_down(ix, b, l, w4_digit(ix, c, l), pos);
+    }
+    return pos;
+}
+
+__device__ __forceinline__ void w4_walk2(const FmxDev &ix, uint32_t c, uint32_t &s, uint32_t &e) {
+    const uint32_t Lq = ix.qlevels;
+#pragma unroll 1
+    for (uint32_t l = 0; l < Lq; l++) {
+        const uint4 *v = ix.lv[l];
+        uint32_t bs = s >> 6, be = e >> 6;
+        RB a = rb_load(v, bs);
+        RB b = a;
+        if (be != bs) b = rb_load(v, be);
+        uint32_t d = w4_digit(ix, c, l);
+        s = w4_down(ix, a, l, d, s);
+        e = w4_down(ix, b, l, d, e);
+    }
+}
+
+__device__ __forceinline__ uint32_t w4_access_walk(const FmxDev &ix, uint32_t pos, uint32_t &sym) {
+    const uint32_t Lq = ix.qlevels;
+    uint32_t c = 0;
+#pragma unroll 1
+    for (uint32_t l = 0; l < Lq; l++) {
+        RB b = rb_load(ix.lv[l], pos >> 6);
+        uint32_t d = q4_code(b, pos & 63u);
+        c = (c << 2) | d;
+        pos = w4_down(ix, b, l, d, pos);
+    }
+    sym = c;
+    return pos;
+}
+
+// position of the k-th (0-based) digit d in level l
+__device__ __forceinline__ uint32_t w4_select_level(const FmxDev &ix, uint32_t l, uint32_t d, uint32_t k) {
+    const uint32_t nblk = (ix.seq_len >> 6) + 1u;
+    const uint32_t *cw = reinterpret_cast<const uint32_t *>(ix.lv[l]);
+    uint32_t lo = 0, hi = nblk;  // last block with (digits d before it) <= k
+    while (hi - lo > 1) {
+        uint32_t mid = lo + ((hi - lo) >> 1);
+        if (__ldg(cw + 8ull * mid + d) <= k) lo = mid; else hi = mid;
+    }
+    RB b = rb_load(ix.lv[l], lo);
+    uint32_t rem = k - q4_cnt(b, d), pos = lo << 6;
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        uint32_t m = q4_eq(b.w[4 + w], d);
+        uint32_t cnt = __popc(m);
+        if (rem < cnt) return pos + (__fns(m, 0, rem + 1) >> 1);
+        rem -= cnt;
+        pos += 16u;
+    }
+    return pos;  // unreachable for a valid k
+}
+
+// select(k, c); base = walk_c(0)
+__device__ __forceinline__ uint32_t w4_select(const FmxDev &ix, uint32_t c, uint32_t k, uint32_t base) {
+    uint32_t pos = base + k;
+#pragma unroll 1
+    for (uint32_t l = ix.qlevels; l-- > 0;) {
+        uint32_t d = w4_digit(ix, c, l);
+        pos = w4_select_level(ix, l, d, pos - ix.qoff[l * 4u + d]);
+    }
+    return pos;
+}
+
+// ------------------------------------------------------------------ sequence primitives, all layouts
 // The "sequence" is the BWT (FM, MultiPieces) or the run heads (RLFM); cs is the matching C array.
 
 // cs[c] + rank(i, c)
@@ -307,6 +393,8 @@ __device__ __forceinline__ uint32_t seq_lf(const FmxDev &ix, const Tabs<LAYOUT> 
     if (LAYOUT == FMX_LAYOUT_Q4) {
         RB b = rb_load(ix.lv[0], i >> 6);
         return t.cs[c] + q4_rank_in(ix, t.exc, b, i, c);
+    } else if (LAYOUT == FMX_LAYOUT_W4) {
+        return t.adj[c] + w4_walk(ix, c, i);
     } else {
         return t.adj[c] + wm_walk(ix, c, i);
     }
@@ -324,7 +412,8 @@ __device__ __forceinline__ void seq_lf2(const FmxDev &ix, const Tabs<LAYOUT> &t,
         s = base + q4_rank_in(ix, t.exc, a, s, c);
         e = base + q4_rank_in(ix, t.exc, b, e, c);
     } else {
-        wm_walk2(ix, c, s, e);
+        if (LAYOUT == FMX_LAYOUT_W4) w4_walk2(ix, c, s, e);
+        else wm_walk2(ix, c, s, e);
         uint32_t a = t.adj[c];
         s += a;
         e += a;
@@ -341,7 +430,7 @@ __device__ __forceinline__ uint32_t seq_access_lf(const FmxDev &ix, const Tabs<L
         return t.cs[c] + q4_rank_in(ix, t.exc, b, i, c);
     } else {
         uint32_t c;
-        uint32_t w = wm_access_walk(ix, i, c);
+        uint32_t w = LAYOUT == FMX_LAYOUT_W4 ? w4_access_walk(ix, i, c) : wm_access_walk(ix, i, c);
         sym = c;
         return w + t.adj[c];
     }
@@ -355,7 +444,8 @@ __device__ __forceinline__ uint32_t seq_access(const FmxDev &ix, const Tabs<LAYO
         return q4_code(b, i & 63u) + 1u;
     } else {
         uint32_t c;
-        wm_access_walk(ix, i, c);
+        if (LAYOUT == FMX_LAYOUT_W4) w4_access_walk(ix, i, c);
+        else wm_access_walk(ix, i, c);
         return c;
     }
 }
@@ -364,6 +454,7 @@ __device__ __forceinline__ uint32_t seq_access(const FmxDev &ix, const Tabs<LAYO
 template <int LAYOUT>
 __device__ __forceinline__ uint32_t seq_select(const FmxDev &ix, const Tabs<LAYOUT> &t, uint32_t c, uint32_t k) {
     if (LAYOUT == FMX_LAYOUT_Q4) return q4_select(ix, t.exc, c, k);
+    if (LAYOUT == FMX_LAYOUT_W4) return w4_select(ix, c, k, t.cs[c] - t.adj[c]);
     return wm_select(ix, c, k, t.cs[c] - t.adj[c]);
 }
 
@@ -399,6 +490,26 @@ __device__ __forceinline__ void rl_probe(const FmxDev &ix, const Tabs<LAYOUT> &t
         uint32_t sh = q4_is_exc(ix, t.exc, h) ? 0u : q4_code(d, h & 63u) + 1u;
         hit = sh == c;
         nrc = t.cs[c] + q4_rank_in(ix, t.exc, a, j, c);
+    } else if (LAYOUT == FMX_LAYOUT_W4) {
+        const uint32_t Lq = ix.qlevels;
+        uint32_t p = j, q = h;
+        bool alive = true;
+#pragma unroll 1
+        for (uint32_t l = 0; l < Lq; l++) {
+            const uint4 *v = ix.lv[l];
+            uint32_t d = w4_digit(ix, c, l);
+            uint32_t bp_ = p >> 6, bq = q >> 6;
+            RB a = rb_load(v, bp_);
+            if (alive) {
+                RB g = a;
+                if (bq != bp_) g = rb_load(v, bq);
+                alive = q4_code(g, q & 63u) == d;
+                q = w4_down(ix, g, l, d, q);
+            }
+            p = w4_down(ix, a, l, d, p);
+        }
+        nrc = t.adj[c] + p;
+        hit = alive;
     } else {
         const uint32_t L = ix.levels;
         uint32_t p = j, q = h;

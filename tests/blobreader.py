@@ -39,9 +39,15 @@ class Blob:
         o += 8
         self.sec = [struct.unpack_from("<QQ", raw, o + 16 * k) for k in range(SEC_COUNT)]
         o += 16 * SEC_COUNT
-        self.layout, self.nexc = struct.unpack_from("<II", raw, o)
+        self.layout, self.nexc, self.qlevels, _ = struct.unpack_from("<IIII", raw, o)
+        o += 16
+        self.qoff = [struct.unpack_from("<4Q", raw, o + 32 * l) for l in range(4)]
         assert self.total_bytes == len(raw)
-        if self.layout == 1:
+        if self.layout == 2:
+            assert self.qlevels == (self.levels + 1) // 2
+            self.q4l = [np.frombuffer(self._sec(SEC_LEVEL0 + l), dtype=np.uint32).reshape(-1, 8) for l in range(self.qlevels)]
+            self.lv = []
+        elif self.layout == 1:
             self.q4 = np.frombuffer(self._sec(SEC_LEVEL0), dtype=np.uint32).reshape(-1, 8)
             self.exc = [int(v) for v in np.frombuffer(self._sec(SEC_EXC), dtype=np.uint32)]
             assert len(self.exc) == self.nexc
@@ -99,8 +105,21 @@ class Blob:
         c, w = self.access_walk(i)
         return c, (w + int(self.adj[c])) & M32
 
+    # ---- WM4 layout: quaternary wavelet matrix
+    def w4_code(self, l, i):
+        b, t = divmod(i, 64)
+        return (int(self.q4l[l][b, 4 + (t >> 4)]) >> (2 * (t & 15))) & 3
+
+    def w4_down(self, l, d, pos):
+        b, r = divmod(pos, 64)
+        return self.qoff[l][d] + int(self.q4l[l][b, d]) + sum(1 for t in range(r) if self.w4_code(l, b * 64 + t) == d)
+
     # the same arithmetic the kernels do (kernels.cuh), in Python
     def walk(self, c, pos):
+        if self.layout == 2:
+            for l in range(self.qlevels):
+                pos = self.w4_down(l, (c >> (2 * (self.qlevels - 1 - l))) & 3, pos)
+            return pos
         L = self.levels
         for l in range(L):
             ones = self.lv[l].rank1(pos)
@@ -108,6 +127,13 @@ class Blob:
         return pos
 
     def access_walk(self, pos):
+        if self.layout == 2:
+            c = 0
+            for l in range(self.qlevels):
+                d = self.w4_code(l, pos)
+                c = (c << 2) | d
+                pos = self.w4_down(l, d, pos)
+            return c, pos
         L, c = self.levels, 0
         for l in range(L):
             ones, bit = self.lv[l].rank1(pos), self.lv[l].bit(pos)

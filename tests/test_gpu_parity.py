@@ -166,6 +166,47 @@ def test_extraction_vs_oracle(kind):
         assert np.array_equal(ln, oln) and np.array_equal(out, oout)
 
 
+
+# ---- the three device layouts (fmx_layout.h) answer identically: the builder picks Q4 for DNA-coded
+# texts and the quaternary wavelet matrix otherwise; FMX_FORCE_WAVELET=1 keeps the binary matrix
+@pytest.mark.parametrize("kind", [orc.FM, orc.RLFM, orc.MULTI])
+def test_binary_wavelet_layout_parity(kind, monkeypatch):
+    monkeypatch.setenv("FMX_FORCE_WAVELET", "1")
+    rng = np.random.default_rng(300 + kind)
+    multi = kind == orc.MULTI
+    for mc in (4, 37, 255):
+        text = build_text(rng, 4000, min(mc, 20), multi)
+        index = KINDS[kind][1].new(fmx.Text.with_max_character(text, mc), 2)
+        assert index.sectors_per_rank() == int(mc).bit_length()
+        oracle = orc.OracleIndex(text, kind, level=2, max_character=mc)
+        n = len(text)
+        rows = np.arange(n, dtype=np.uint64)
+        assert list(index.rows_op(0, rows)) == [oracle.get_l(i) for i in range(n)]
+        assert list(index.rows_op(1, rows)) == [oracle.lf_map(i) for i in range(n)]
+        exp_fl = [oracle.fl_map(i) for i in range(n)]
+        assert list(index.rows_op(3, rows)) == [(1 << 64) - 1 if v is None else v for v in exp_fl]
+        pats = [bytes(text[p:p + m]) if k & 1 else bytes(int(x) for x in rng.integers(1, min(mc, 20) + 1, m))
+                for k, (p, m) in enumerate(zip(rng.integers(0, n - 12, 400), rng.integers(1, 12, 400)))]
+        pats = [p for p in pats if multi or 0 not in p]
+        flat, off = orc.pack_patterns(pats)
+        b = index.search_batch(pats)
+        s, e = oracle.search_batch(flat, off)
+        assert np.array_equal(b.s, s) and np.array_equal(b.e, e)
+        hoff, pos = b.locate()
+        ooff, opos, _ = oracle.locate_batch(s, e)
+        assert np.array_equal(hoff, ooff) and np.array_equal(pos, opos)
+
+
+def test_quaternary_wavelet_matrix_is_the_default_for_wide_alphabets():
+    rng = np.random.default_rng(310)
+    for mc, lq in ((5, 2), (37, 3), (255, 4)):
+        text = build_text(rng, 2000, min(mc, 30), False)
+        index = fmx.FMIndex.new(fmx.Text.with_max_character(text, mc))
+        assert index.sectors_per_rank() == lq
+    dna_like = build_text(rng, 2000, 4, False)
+    assert fmx.FMIndex.new(fmx.Text.with_max_character(dna_like, 4)).sectors_per_rank() == 1
+
+
 def test_refinement_and_empty_pattern():
     index = fmx.FMIndexWithLocate.new(fmx.Text.new(MISS), 0)
     assert index.search(b"").get_range() == (0, 12)

@@ -462,6 +462,43 @@ void orc_free(orc_index *x) {
     free(x);
 }
 
+/* Linear-time check that `sa` is THE suffix array of `text` (plain lexicographic suffix order,
+ * a proper prefix sorts first -- the order sais.rs:115-307 produces, pinned by sais.rs:546-557):
+ * (1) sa is a permutation of 0..n; (2) for neighbours a = sa[i], b = sa[i+1]: text[a] < text[b], or
+ * text[a] == text[b] and suffix a+1 sorts before suffix b+1 (by its rank; the empty suffix first).
+ * (1) + (2) for all i imply the order is the suffix order by induction on the suffix length.
+ * returns 0 when it is.  Lets bench.py hand a GPU-built SA to the oracle without trusting it. */
+int orc_check_suffix_array(const uint8_t *text, uint64_t n, const uint64_t *sa) {
+    if (n == 0) return 0;
+    uint64_t *isa = (uint64_t *)malloc(n * 8);
+    if (!isa) return -2;
+    memset(isa, 0xFF, n * 8);
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        if (sa[i] >= n) bad |= 1;
+        else isa[sa[i]] = (uint64_t)i; /* a duplicate leaves some slot at UINT64_MAX */
+    }
+    if (!bad) {
+#pragma omp parallel for schedule(static) reduction(| : bad)
+        for (int64_t i = 0; i < (int64_t)n; i++)
+            if (isa[i] == UINT64_MAX || sa[isa[i]] != (uint64_t)i) bad |= 1;
+    }
+    if (!bad) {
+#pragma omp parallel for schedule(static) reduction(| : bad)
+        for (int64_t i = 0; i < (int64_t)n - 1; i++) {
+            uint64_t a = sa[i], b = sa[i + 1];
+            if (text[a] < text[b]) continue;
+            if (text[a] > text[b]) { bad |= 1; continue; }
+            if (a + 1 == n) continue;            /* suffix a is a proper prefix of suffix b */
+            if (b + 1 == n) { bad |= 1; continue; }
+            if (isa[a + 1] > isa[b + 1]) bad |= 1;
+        }
+    }
+    free(isa);
+    return bad ? -1 : 0;
+}
+
 static orc_index *build_impl(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level,
                              const uint64_t *sa_in, char *err, size_t errlen) {
     if (mc == 0 || mc > 255) {
@@ -488,6 +525,11 @@ static orc_index *build_impl(const uint8_t *text, uint64_t n, uint64_t mc, int k
                 free(sa);
                 return NULL;
             }
+        }
+        if (orc_check_suffix_array(text, n, sa_in) != 0) {
+            set_err(err, errlen, "the supplied array is not the suffix array of the text");
+            free(sa);
+            return NULL;
         }
         memcpy(sa, sa_in, n * 8);
     } else if (orc_suffix_array(text, n, sa, err, errlen) != 0) {

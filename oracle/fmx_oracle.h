@@ -40,12 +40,16 @@ enum { ORC_SEARCH = 0, ORC_SEARCH_PREFIX = 1, ORC_SEARCH_SUFFIX = 2, ORC_SEARCH_
  * sais.rs:128-139) when the text is rejected. */
 orc_index *orc_build(const uint8_t *text, uint64_t n, uint64_t max_character, int kind,
                      int level, char *err, size_t errlen);
-/* Same, but the suffix array is supplied by the caller (bench-only speed path
- * for GB-scale texts; the SA of a text is unique so results are unchanged). */
+/* Same, but the suffix array is supplied by the caller (bench-only speed path for GB-scale
+ * texts).  The array is VERIFIED first (orc_check_suffix_array, linear time): the suffix array
+ * of a text is unique, so a verified one gives exactly the index orc_build would. */
 orc_index *orc_build_from_sa(const uint8_t *text, uint64_t n, uint64_t max_character,
                              int kind, int level, const uint64_t *sa, char *err,
                              size_t errlen);
 void orc_free(orc_index *idx);
+
+/* 0 iff sa is the suffix array of text (independent linear-time checker). */
+int orc_check_suffix_array(const uint8_t *text, uint64_t n, const uint64_t *sa);
 
 /* Suffix array alone (sais.rs:115-144 incl. validation). returns 0 ok, -1 invalid text. */
 int orc_suffix_array(const uint8_t *text, uint64_t n, uint64_t *sa, char *err, size_t errlen);

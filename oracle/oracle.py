@@ -51,6 +51,8 @@ def lib():
     L.orc_build_from_sa.restype = vp
     L.orc_build_from_sa.argtypes = [vp, u64, u64, C.c_int, C.c_int, vp, C.c_char_p, C.c_size_t]
     L.orc_free.argtypes = [vp]
+    L.orc_check_suffix_array.restype = C.c_int
+    L.orc_check_suffix_array.argtypes = [vp, u64, vp]
     L.orc_suffix_array.restype = C.c_int
     L.orc_suffix_array.argtypes = [vp, u64, vp, C.c_char_p, C.c_size_t]
     for name in ("orc_len", "orc_pieces_count", "orc_heap_bits", "orc_cs_len", "orc_rlfm_runs", "orc_first_row"):
@@ -113,6 +115,15 @@ def suffix_array(text) -> np.ndarray:
     if rc != 0:
         raise InvalidText(err.value.decode())
     return sa[: t.size]
+
+
+def check_suffix_array(text, sa) -> bool:
+    """independent linear-time check that `sa` is the suffix array of `text`"""
+    t = _as_u8(text)
+    sa = np.ascontiguousarray(sa, dtype=np.uint64)
+    if sa.size != t.size:
+        return False
+    return lib().orc_check_suffix_array(t.ctypes.data, t.size, sa.ctypes.data) == 0
 
 
 class OracleIndex:

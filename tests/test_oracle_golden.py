@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as orc
-from refutil import (TEXT_README, TEXT_TWINKLE, naive_search, naive_suffix_array, random_cases)
+from refutil import (TEXT_README, TEXT_TWINKLE, build_text, naive_search, naive_suffix_array, random_cases)
 
 MISS = b"mississippi\0"
 
@@ -215,3 +215,33 @@ def test_pattern_char_above_max_character():
         idx.search(bytes([1, 5]))
     # the reference breaks out before reaching the bad char when the range empties first
     assert idx.search(bytes([5, 4, 4]))[0] == idx.search(bytes([5, 4, 4]))[1]
+
+
+def test_suffix_array_checker_and_build_from_sa():
+    """orc_check_suffix_array accepts exactly the suffix array; orc_build_from_sa refuses anything else
+    (bench.py hands the oracle a GPU-built SA for GB-scale texts: it is verified, not trusted)"""
+    rng = np.random.default_rng(9)
+    for multi in (False, True):
+        for n in (2, 3, 50, 3000):
+            text = build_text(rng, n, 4, multi)
+            sa = orc.suffix_array(text)
+            assert orc.check_suffix_array(text, sa)
+            if n > 3:
+                bad = sa.copy()
+                i = int(rng.integers(0, n - 1))
+                bad[i], bad[i + 1] = bad[i + 1], bad[i]
+                assert not orc.check_suffix_array(text, bad)
+                dup = sa.copy()
+                dup[1] = dup[2]
+                assert not orc.check_suffix_array(text, dup)
+                oob = sa.copy()
+                oob[0] = n
+                assert not orc.check_suffix_array(text, oob)
+                with pytest.raises(orc.InvalidText, match="not the suffix array"):
+                    orc.OracleIndex(text, orc.MULTI if multi else orc.FM, level=1, sa=bad)
+            a = orc.OracleIndex(text, orc.MULTI if multi else orc.FM, level=1, sa=sa)
+            b = orc.OracleIndex(text, orc.MULTI if multi else orc.FM, level=1)
+            assert [a.lf_map(i) for i in range(n)] == [b.lf_map(i) for i in range(n)]
+            assert [a.get_sa(i) for i in range(n)] == [b.get_sa(i) for i in range(n)]
+    rep = (build_text(rng, 700, 3, False)[:-1] * 30) + b"\0"      # repetitive: long equal prefixes
+    assert orc.check_suffix_array(rep, orc.suffix_array(rep))

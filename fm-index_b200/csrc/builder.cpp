@@ -274,6 +274,41 @@ static bool force_binary_wavelet() {
     return force && force[0] && force[0] != '0';
 }
 
+// Per-symbol RB192 bit vectors (fmx_layout.h "SYM"), built in place inside the blob.
+static uint64_t sym_budget_bytes() {
+    const char *e = std::getenv("FMX_SYM_BUDGET_MB");
+    if (e && e[0]) return (uint64_t)std::strtoull(e, nullptr, 10) << 20;
+    return 49152ull << 20;
+}
+static uint64_t sym_bytes(uint64_t cs_len, uint64_t n) { return cs_len * (n / FMX_RB_BITS + 1) * 32; }
+static void sym_build(const uint8_t *seq, uint64_t n, uint32_t cs_len, uint32_t *dst) {
+    const uint64_t nblk = n / FMX_RB_BITS + 1;
+    const uint64_t chunk_blocks = 2048;
+    const int64_t nchunks = (int64_t)((nblk + chunk_blocks - 1) / chunk_blocks);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t ch = 0; ch < nchunks; ch++) {  // a thread owns whole blocks (of every symbol): no shared words
+        uint64_t lo = (uint64_t)ch * chunk_blocks * FMX_RB_BITS, hi = lo + chunk_blocks * FMX_RB_BITS;
+        if (hi > n) hi = n;
+        for (uint64_t i = lo; i < hi; i++) {
+            uint64_t b = i / FMX_RB_BITS;
+            uint32_t r = (uint32_t)(i - b * FMX_RB_BITS);
+            dst[((uint64_t)seq[i] * nblk + b) * 8 + 2 + (r >> 5)] |= 1u << (r & 31);
+        }
+    }
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t c = 0; c < (int64_t)cs_len; c++) {
+        uint32_t *v = dst + (uint64_t)c * nblk * 8;
+        uint64_t acc = 0;
+        for (uint64_t b = 0; b < nblk; b++) {
+            uint32_t *blk = v + b * 8;
+            uint32_t p0 = RBVec::pop64(blk + 2), p1 = RBVec::pop64(blk + 4), p2 = RBVec::pop64(blk + 6);
+            blk[0] = (uint32_t)acc;
+            blk[1] = (p0 << 8) | ((p0 + p1) << 16);
+            acc += p0 + p1 + p2;
+        }
+    }
+}
+
 static bool want_q4(uint64_t mc, const uint8_t *seq, uint64_t n) {
     if (force_binary_wavelet()) return false;
     if (mc > 4) return false;
@@ -352,8 +387,11 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
     WMat wm;
     Q4Vec q4;
     WM4 wm4;
-    bool use_q4 = false;
-    const bool use_wm4_else = !force_binary_wavelet();  // every alphabet Q4 does not take
+    bool use_q4 = false, use_sym = false;
+    const bool use_wm4_else = !force_binary_wavelet();  // every alphabet Q4 / SYM do not take
+    std::vector<uint8_t> heads;                          // RLFM: the run heads
+    const uint8_t *seq_ptr = bwt.data();                 // the sequence the rank structure is over
+    auto pick_sym = [&](uint64_t len) { return !use_q4 && use_wm4_else && sym_bytes(cs_len, len) + len <= sym_budget_bytes(); };
     std::vector<uint32_t> cs(cs_len + 1, 0), adj(cs_len, 0);
     std::vector<uint32_t> doc, piece_end, bsel, bpsel;
     RBVec rb_b(0), rb_bp(0);
@@ -368,7 +406,9 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
         }
         cs[cs_len] = (uint32_t)n;
         use_q4 = want_q4(mc, bwt.data(), n);
+        use_sym = pick_sym(n);
         if (use_q4) q4.build(bwt.data(), n);
+        else if (use_sym) {}  // built in place once the blob is allocated
         else if (use_wm4_else) wm4.build(bwt.data(), n, L);
         else build_wavelet(bwt.data(), n, L, wm);
         hdr.seq_len = n;
@@ -394,7 +434,6 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
         }
     } else {
         // rlfmi.rs:37-96
-        std::vector<uint8_t> heads;
         std::vector<uint32_t> starts;
         rb_b = RBVec(n);
         rb_bp = RBVec(n);
@@ -415,8 +454,11 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
         uint64_t r = heads.size();
         hdr.runs = r;
         hdr.seq_len = r;
+        seq_ptr = heads.data();
         use_q4 = want_q4(mc, heads.data(), r);
+        use_sym = pick_sym(r);
         if (use_q4) q4.build(heads.data(), r);
+        else if (use_sym) {}
         else if (use_wm4_else) wm4.build(heads.data(), r, L);
         else build_wavelet(heads.data(), r, L, wm);
         bsel.assign(r + 1, (uint32_t)n);
@@ -449,6 +491,9 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
     if (use_q4) {
         hdr.layout = FMX_LAYOUT_QUAT;
         hdr.nexc = (uint32_t)q4.exc.size();
+    } else if (use_sym) {
+        hdr.layout = FMX_LAYOUT_SYM;
+        hdr.sym_nblk = (uint32_t)(hdr.seq_len / FMX_RB_BITS + 1);
     } else if (use_wm4_else) {
         hdr.layout = FMX_LAYOUT_WM4;
         hdr.qlevels = wm4.Lq;
@@ -483,6 +528,9 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
     if (use_q4) {
         sec[SEC_LEVEL0] = {q4.w.data(), q4.w.size() * 4};
         if (!q4.exc.empty()) sec[SEC_EXC] = {q4.exc.data(), q4.exc.size() * 4};
+    } else if (use_sym) {
+        sec[SEC_LEVEL0] = {nullptr, sym_bytes(cs_len, hdr.seq_len)};  // filled in place below
+        sec[SEC_LEVEL0 + 1] = {seq_ptr, hdr.seq_len ? hdr.seq_len : 1};
     } else if (use_wm4_else) {
         for (uint32_t l = 0; l < wm4.Lq; l++) sec[SEC_LEVEL0 + l] = {wm4.lv[l].data(), wm4.lv[l].size() * 4};
     } else {
@@ -508,8 +556,17 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
     hdr.total_bytes = off;
     blob.assign(off, 0);
     std::memcpy(blob.data(), &hdr, sizeof(hdr));
-    for (int k = 0; k < (int)SEC_COUNT; k++)
-        if (sec[k].bytes) std::memcpy(blob.data() + hdr.sec[k].offset, sec[k].ptr, sec[k].bytes);
+    for (int k = 0; k < (int)SEC_COUNT; k++) {
+        if (!sec[k].bytes || !sec[k].ptr) continue;
+        const uint64_t piece = 64ull << 20;  // large sections: copy in parallel
+        const int64_t np = (int64_t)((sec[k].bytes + piece - 1) / piece);
+#pragma omp parallel for schedule(static) if (np > 1)
+        for (int64_t q = 0; q < np; q++) {
+            uint64_t lo = (uint64_t)q * piece, len = sec[k].bytes - lo < piece ? sec[k].bytes - lo : piece;
+            std::memcpy(blob.data() + hdr.sec[k].offset + lo, static_cast<const uint8_t *>(sec[k].ptr) + lo, len);
+        }
+    }
+    if (use_sym) sym_build(seq_ptr, hdr.seq_len, cs_len, reinterpret_cast<uint32_t *>(blob.data() + hdr.sec[SEC_LEVEL0].offset));
     return 0;
 }
 
@@ -523,7 +580,7 @@ int check_blob(const void *blob, uint64_t bytes, FmxBlobHeader &hdr, std::string
         err = "not an fmx blob (bad magic or version)";
         return FMX_ERR_INVALID_ARG;
     }
-    if (hdr.total_bytes != bytes || hdr.levels == 0 || hdr.levels > FMX_MAX_LEVELS || hdr.kind > 2 || hdr.layout > 2 || hdr.qlevels > FMX_MAX_QLEVELS ||
+    if (hdr.total_bytes != bytes || hdr.levels == 0 || hdr.levels > FMX_MAX_LEVELS || hdr.kind > 2 || hdr.layout > 3 || hdr.qlevels > FMX_MAX_QLEVELS ||
         hdr.nexc > FMX_MAX_EXC) {
         err = "corrupt fmx blob header";
         return FMX_ERR_INVALID_ARG;

@@ -117,16 +117,19 @@ static inline unsigned grid_for(uint64_t n, unsigned threads) { return (unsigned
 template <class F>
 static void dispatch(const fmx_index *idx, F &&f) {
     using std::integral_constant;
-    switch (idx->hdr.kind * 3 + idx->hdr.layout) {
+    switch (idx->hdr.kind * 4 + idx->hdr.layout) {
         case 0: f(integral_constant<int, 0>{}, integral_constant<int, 0>{}); break;
         case 1: f(integral_constant<int, 0>{}, integral_constant<int, 1>{}); break;
         case 2: f(integral_constant<int, 0>{}, integral_constant<int, 2>{}); break;
-        case 3: f(integral_constant<int, 1>{}, integral_constant<int, 0>{}); break;
-        case 4: f(integral_constant<int, 1>{}, integral_constant<int, 1>{}); break;
-        case 5: f(integral_constant<int, 1>{}, integral_constant<int, 2>{}); break;
-        case 6: f(integral_constant<int, 2>{}, integral_constant<int, 0>{}); break;
-        case 7: f(integral_constant<int, 2>{}, integral_constant<int, 1>{}); break;
-        default: f(integral_constant<int, 2>{}, integral_constant<int, 2>{}); break;
+        case 3: f(integral_constant<int, 0>{}, integral_constant<int, 3>{}); break;
+        case 4: f(integral_constant<int, 1>{}, integral_constant<int, 0>{}); break;
+        case 5: f(integral_constant<int, 1>{}, integral_constant<int, 1>{}); break;
+        case 6: f(integral_constant<int, 1>{}, integral_constant<int, 2>{}); break;
+        case 7: f(integral_constant<int, 1>{}, integral_constant<int, 3>{}); break;
+        case 8: f(integral_constant<int, 2>{}, integral_constant<int, 0>{}); break;
+        case 9: f(integral_constant<int, 2>{}, integral_constant<int, 1>{}); break;
+        case 10: f(integral_constant<int, 2>{}, integral_constant<int, 2>{}); break;
+        default: f(integral_constant<int, 2>{}, integral_constant<int, 3>{}); break;
     }
 }
 
@@ -224,6 +227,11 @@ static int upload(std::vector<uint8_t> &&blob, int device, fmx_index **out) {
     for (uint32_t l = 0; l < hdr.levels; l++) {
         d.lv[l] = static_cast<const uint4 *>(sec(SEC_LEVEL0 + l));
         d.zeros[l] = (uint32_t)hdr.zeros[l];
+    }
+    if (hdr.layout == FMX_LAYOUT_SYM) {
+        d.lv[0] = static_cast<const uint4 *>(sec(SEC_LEVEL0));
+        d.raw = static_cast<const uint8_t *>(sec(SEC_LEVEL0 + 1));
+        d.sym_nblk = hdr.sym_nblk;
     }
     d.qlevels = hdr.qlevels;
     for (uint32_t l = 0; l < hdr.qlevels; l++)
@@ -370,7 +378,8 @@ uint32_t fmx_index_wavelet_levels(const fmx_index *idx) { return idx ? idx->hdr.
 uint32_t fmx_index_sample_level(const fmx_index *idx) { return idx ? idx->hdr.sa_level : 0; }
 uint32_t fmx_index_sectors_per_rank(const fmx_index *idx) {
     if (!idx) return 0;
-    return idx->hdr.layout == FMX_LAYOUT_QUAT ? 1u : (idx->hdr.layout == FMX_LAYOUT_WM4 ? idx->hdr.qlevels : idx->hdr.levels);
+    if (idx->hdr.layout == FMX_LAYOUT_QUAT || idx->hdr.layout == FMX_LAYOUT_SYM) return 1u;
+    return idx->hdr.layout == FMX_LAYOUT_WM4 ? idx->hdr.qlevels : idx->hdr.levels;
 }
 
 }  // extern "C"
@@ -598,6 +607,7 @@ static int build_kmer_table(fmx_index *idx) {
     if (!large_text) return 0;
     // default HBM budget of the large table: twice the index itself (FMX_KMER_BUDGET_MB overrides)
     uint64_t budget = 2 * idx->hdr.total_bytes;
+    if (budget > (8ull << 30)) budget = 8ull << 30;  // the SYM layout is large by design; the table need not follow it
     if (const char *v = std::getenv("FMX_KMER_BUDGET_MB")) budget = std::strtoull(v, nullptr, 10) << 20;
     return build_big_table(idx, budget);
 }

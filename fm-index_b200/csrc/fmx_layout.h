@@ -32,7 +32,19 @@
 // blocks, one level per TWO bits of the symbol (ceil(L/2) levels, most significant digit first),
 // symbols stably partitioned by digit into four groups starting at qoff[l][0..3].  A walk is
 //       pos <- qoff[l][d] + rank_d(level l, pos),   d = digit l of c
-// i.e. HALF the sectors of the binary matrix (4 instead of 8 for bytes).  adj[] as above.  The rare symbol 0
+// i.e. HALF the sectors of the binary matrix (4 instead of 8 for bytes).  adj[] as above.
+//
+// PER-SYMBOL BIT VECTORS ("SYM", the default for every non-DNA alphabet while it fits the HBM
+// budget).  One RB192 bit vector PER SYMBOL (bit i of vector c = [seq[i] == c]), concatenated in
+// SEC_LEVEL0 (vector c starts at block c * sym_nblk), plus the raw sequence bytes in SEC_LEVEL0+1:
+//       lf_map2(c, i) = cs[c] + rank1(vec_c, i)          ONE sector, like Q4
+//       access(i)     = raw[i]                           ONE request
+// Space is cs_len * n / 6 bytes (43 GB for a 1 GB byte text): a deliberate trade of the B200's
+// 180 GB of HBM for requests, because the random-request rate -- not bandwidth, not capacity -- is
+// what bounds this workload (profiles/r01b_random_access_study.md: ~45 G DRAM-missing requests/s
+// whatever their size).  Above the budget (FMX_SYM_BUDGET_MB, default 49152) the builder falls back to WM4.
+//
+// Q4 DETAILS.  The rare symbol 0
 // (the \0 terminators: 1 for a single text, one per piece for MultiPieces) is stored as code 0
 // and its positions are listed in SEC_EXC (sorted; staged in shared memory), which corrects
 // rank(., 1) and answers rank(., 0) / access exactly.  Results are identical to the wavelet
@@ -51,11 +63,12 @@
 #define FMX_LAYOUT_WAVELET 0u
 #define FMX_LAYOUT_QUAT 1u
 #define FMX_LAYOUT_WM4 2u
+#define FMX_LAYOUT_SYM 3u
 #define FMX_MAX_QLEVELS 4
 #define FMX_SECTION_ALIGN 256u
 
 enum FmxSection : uint32_t {
-    SEC_LEVEL0 = 0,  // .. SEC_LEVEL0 + 7 : wavelet levels (RB192); Q4 layout: SEC_LEVEL0 = the Q4 blocks
+    SEC_LEVEL0 = 0,  // .. SEC_LEVEL0 + 7 : wavelet levels (RB192); Q4: SEC_LEVEL0 = the Q4 blocks; SYM: vectors, +1 = raw bytes
     SEC_ADJ = 8,     // u32[cs_len]   adj[c] = cs[c] - walk_c(0)
     SEC_CS = 9,      // u32[cs_len+1] cs[c] (sais.rs:21-32), cs[cs_len] = n (FM/MULTI) or runs (RLFM)
     SEC_SA = 10,     // u32[((n-1)>>level)+1]  sampled suffix array, sa[i << level]  (sample.rs:33-37)
@@ -96,7 +109,7 @@ struct FmxBlobHeader {
     uint32_t layout;  // FMX_LAYOUT_WAVELET | FMX_LAYOUT_QUAT | FMX_LAYOUT_WM4
     uint32_t nexc;    // Q4: number of zeros in the sequence
     uint32_t qlevels; // WM4: ceil(levels / 2)
-    uint32_t pad0;
+    uint32_t sym_nblk; // SYM: RB192 blocks per symbol vector (seq_len / 192 + 1)
     uint64_t qoff[FMX_MAX_QLEVELS][4];  // WM4: start of digit group d at level l
     uint64_t reserved[6];
 };
@@ -130,4 +143,6 @@ struct FmxDev {
     uint32_t nexc;
     uint32_t qlevels;
     uint32_t qoff[FMX_MAX_QLEVELS * 4];
+    uint32_t sym_nblk;
+    const uint8_t *raw;  // SYM: the sequence itself
 };

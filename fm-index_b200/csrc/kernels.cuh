@@ -25,7 +25,14 @@ struct RB {
 __device__ __forceinline__ RB rb_load(const uint4 *__restrict__ v, uint32_t blk) {
     RB b;
     const uint4 *p = v + 2ull * blk;
+    // .L2::64B: on sm_100 a plain LDG makes L2 fill the whole 128-byte line from DRAM (125 B of DRAM
+    // traffic per random 32 B read); this qualifier caps the fill at 64 B (63 B measured) --
+    // tools/fetch_gran.cu, profiles/r01b_random_access_study.md
+#ifndef FMX_NO_L2_64B
+    asm("ld.global.nc.L2::64B.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#else
     asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#endif
         : "=r"(b.w[0]), "=r"(b.w[1]), "=r"(b.w[2]), "=r"(b.w[3]), "=r"(b.w[4]), "=r"(b.w[5]), "=r"(b.w[6]), "=r"(b.w[7])
         : "l"(p));
     return b;
@@ -122,7 +129,8 @@ __device__ __forceinline__ uint32_t rbv_select0(const uint4 *__restrict__ v, uin
 
 #define FMX_LAYOUT_WM 0  // binary wavelet matrix, L levels (any alphabet)
 #define FMX_LAYOUT_Q4 1  // one quaternary level (max_character <= 4, few \0): ONE sector per lf_map2
-#define FMX_LAYOUT_W4 2  // quaternary wavelet matrix, ceil(L/2) levels (every other alphabet)
+#define FMX_LAYOUT_W4 2  // quaternary wavelet matrix, ceil(L/2) levels (alphabets too large for SYM's budget)
+#define FMX_LAYOUT_SY 3  // one RB192 bit vector per symbol + the raw sequence: ONE sector per lf_map2
 
 template <int LAYOUT>
 struct Tabs {
@@ -384,6 +392,13 @@ __device__ __forceinline__ uint32_t w4_select(const FmxDev &ix, uint32_t c, uint
     return pos;
 }
 
+// ------------------------------------------------------------------ per-symbol bit vectors (LAYOUT_SY)
+// vector c = RB192 over [seq[i] == c], starting at block c * sym_nblk of lv[0]; raw = the sequence bytes
+
+__device__ __forceinline__ const uint4 *sy_vec(const FmxDev &ix, uint32_t c) {
+    return ix.lv[0] + 2ull * (uint64_t)c * ix.sym_nblk;
+}
+
 // ------------------------------------------------------------------ sequence primitives, all layouts
 // The "sequence" is the BWT (FM, MultiPieces) or the run heads (RLFM); cs is the matching C array.
 
@@ -393,6 +408,8 @@ __device__ __forceinline__ uint32_t seq_lf(const FmxDev &ix, const Tabs<LAYOUT> 
     if (LAYOUT == FMX_LAYOUT_Q4) {
         RB b = rb_load(ix.lv[0], i >> 6);
         return t.cs[c] + q4_rank_in(ix, t.exc, b, i, c);
+    } else if (LAYOUT == FMX_LAYOUT_SY) {
+        return t.cs[c] + rbv_rank1(sy_vec(ix, c), i);
     } else if (LAYOUT == FMX_LAYOUT_W4) {
         return t.adj[c] + w4_walk(ix, c, i);
     } else {
@@ -411,6 +428,17 @@ __device__ __forceinline__ void seq_lf2(const FmxDev &ix, const Tabs<LAYOUT> &t,
         uint32_t base = t.cs[c];
         s = base + q4_rank_in(ix, t.exc, a, s, c);
         e = base + q4_rank_in(ix, t.exc, b, e, c);
+    } else if (LAYOUT == FMX_LAYOUT_SY) {
+        const uint4 *v = sy_vec(ix, c);
+        uint32_t bs, rs, be, re;
+        rb_split(s, bs, rs);
+        rb_split(e, be, re);
+        RB a = rb_load(v, bs);
+        RB b = a;
+        if (be != bs) b = rb_load(v, be);
+        uint32_t base = t.cs[c];
+        s = base + rb_rank(a, rs);
+        e = base + rb_rank(b, re);
     } else {
         if (LAYOUT == FMX_LAYOUT_W4) w4_walk2(ix, c, s, e);
         else wm_walk2(ix, c, s, e);
@@ -428,6 +456,10 @@ __device__ __forceinline__ uint32_t seq_access_lf(const FmxDev &ix, const Tabs<L
         uint32_t c = q4_is_exc(ix, t.exc, i) ? 0u : q4_code(b, i & 63u) + 1u;
         sym = c;
         return t.cs[c] + q4_rank_in(ix, t.exc, b, i, c);
+    } else if (LAYOUT == FMX_LAYOUT_SY) {
+        uint32_t c = __ldg(ix.raw + i);
+        sym = c;
+        return t.cs[c] + rbv_rank1(sy_vec(ix, c), i);
     } else {
         uint32_t c;
         uint32_t w = LAYOUT == FMX_LAYOUT_W4 ? w4_access_walk(ix, i, c) : wm_access_walk(ix, i, c);
@@ -442,6 +474,8 @@ __device__ __forceinline__ uint32_t seq_access(const FmxDev &ix, const Tabs<LAYO
         if (q4_is_exc(ix, t.exc, i)) return 0u;
         RB b = rb_load(ix.lv[0], i >> 6);
         return q4_code(b, i & 63u) + 1u;
+    } else if (LAYOUT == FMX_LAYOUT_SY) {
+        return __ldg(ix.raw + i);
     } else {
         uint32_t c;
         if (LAYOUT == FMX_LAYOUT_W4) w4_access_walk(ix, i, c);
@@ -454,6 +488,7 @@ __device__ __forceinline__ uint32_t seq_access(const FmxDev &ix, const Tabs<LAYO
 template <int LAYOUT>
 __device__ __forceinline__ uint32_t seq_select(const FmxDev &ix, const Tabs<LAYOUT> &t, uint32_t c, uint32_t k) {
     if (LAYOUT == FMX_LAYOUT_Q4) return q4_select(ix, t.exc, c, k);
+    if (LAYOUT == FMX_LAYOUT_SY) return rbv_select1(sy_vec(ix, c), ix.sym_nblk, k);
     if (LAYOUT == FMX_LAYOUT_W4) return w4_select(ix, c, k, t.cs[c] - t.adj[c]);
     return wm_select(ix, c, k, t.cs[c] - t.adj[c]);
 }
@@ -490,6 +525,9 @@ __device__ __forceinline__ void rl_probe(const FmxDev &ix, const Tabs<LAYOUT> &t
         uint32_t sh = q4_is_exc(ix, t.exc, h) ? 0u : q4_code(d, h & 63u) + 1u;
         hit = sh == c;
         nrc = t.cs[c] + q4_rank_in(ix, t.exc, a, j, c);
+    } else if (LAYOUT == FMX_LAYOUT_SY) {
+        hit = __ldg(ix.raw + h) == c;
+        nrc = t.cs[c] + rbv_rank1(sy_vec(ix, c), j);
     } else if (LAYOUT == FMX_LAYOUT_W4) {
         const uint32_t Lq = ix.qlevels;
         uint32_t p = j, q = h;

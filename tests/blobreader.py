@@ -39,11 +39,17 @@ class Blob:
         o += 8
         self.sec = [struct.unpack_from("<QQ", raw, o + 16 * k) for k in range(SEC_COUNT)]
         o += 16 * SEC_COUNT
-        self.layout, self.nexc, self.qlevels, _ = struct.unpack_from("<IIII", raw, o)
+        self.layout, self.nexc, self.qlevels, self.sym_nblk = struct.unpack_from("<IIII", raw, o)
         o += 16
         self.qoff = [struct.unpack_from("<4Q", raw, o + 32 * l) for l in range(4)]
         assert self.total_bytes == len(raw)
-        if self.layout == 2:
+        if self.layout == 3:
+            assert self.sym_nblk == self.seq_len // RB_BITS + 1
+            allv = np.frombuffer(self._sec(SEC_LEVEL0), dtype=np.uint32).reshape(self.cs_len, self.sym_nblk, 8)
+            self.symv = [RBVec(allv[c].tobytes()) for c in range(self.cs_len)]
+            self.rawseq = np.frombuffer(self._sec(SEC_LEVEL0 + 1), dtype=np.uint8)
+            self.lv = []
+        elif self.layout == 2:
             assert self.qlevels == (self.levels + 1) // 2
             self.q4l = [np.frombuffer(self._sec(SEC_LEVEL0 + l), dtype=np.uint32).reshape(-1, 8) for l in range(self.qlevels)]
             self.lv = []
@@ -94,11 +100,16 @@ class Blob:
 
     # cs[c] + rank(i, c) and (seq[i], cs + rank) for either layout
     def seq_lf(self, c, i):
+        if self.layout == 3:
+            return int(self.cs[c]) + self.symv[c].rank1(i)
         if self.layout == 1:
             return int(self.cs[c]) + self.q4_rank(i, c)
         return (int(self.adj[c]) + self.walk(c, i)) & M32
 
     def seq_access_lf(self, i):
+        if self.layout == 3:
+            c = int(self.rawseq[i])
+            return c, int(self.cs[c]) + self.symv[c].rank1(i)
         if self.layout == 1:
             c = self.q4_access(i)
             return c, int(self.cs[c]) + self.q4_rank(i, c)

@@ -167,17 +167,24 @@ def test_extraction_vs_oracle(kind):
 
 
 
-# ---- the three device layouts (fmx_layout.h) answer identically: the builder picks Q4 for DNA-coded
-# texts and the quaternary wavelet matrix otherwise; FMX_FORCE_WAVELET=1 keeps the binary matrix
+# ---- the four device layouts (fmx_layout.h) answer identically: the builder picks Q4 for DNA-coded
+# texts and per-symbol bit vectors (SYM) otherwise; a zero SYM budget gives the quaternary wavelet
+# matrix (what alphabets too large for the budget get); FMX_FORCE_WAVELET=1 keeps the binary matrix
 @pytest.mark.parametrize("kind", [orc.FM, orc.RLFM, orc.MULTI])
-def test_binary_wavelet_layout_parity(kind, monkeypatch):
-    monkeypatch.setenv("FMX_FORCE_WAVELET", "1")
+@pytest.mark.parametrize("env", [("FMX_FORCE_WAVELET", "1"), ("FMX_SYM_BUDGET_MB", "0")])
+def test_fallback_layouts_parity(kind, env, monkeypatch):
+    monkeypatch.setenv(*env)
     rng = np.random.default_rng(300 + kind)
     multi = kind == orc.MULTI
     for mc in (4, 37, 255):
         text = build_text(rng, 4000, min(mc, 20), multi)
         index = KINDS[kind][1].new(fmx.Text.with_max_character(text, mc), 2)
-        assert index.sectors_per_rank() == int(mc).bit_length()
+        bits = int(mc).bit_length()
+        if env[0] == "FMX_FORCE_WAVELET":
+            assert index.sectors_per_rank() == bits
+        else:
+            q4 = mc <= 4 and (text.count(0) if kind != orc.RLFM else 1) <= 1024
+            assert index.sectors_per_rank() == (1 if q4 else (bits + 1) // 2)
         oracle = orc.OracleIndex(text, kind, level=2, max_character=mc)
         n = len(text)
         rows = np.arange(n, dtype=np.uint64)
@@ -197,12 +204,12 @@ def test_binary_wavelet_layout_parity(kind, monkeypatch):
         assert np.array_equal(hoff, ooff) and np.array_equal(pos, opos)
 
 
-def test_quaternary_wavelet_matrix_is_the_default_for_wide_alphabets():
+def test_one_sector_per_rank_is_the_default():
     rng = np.random.default_rng(310)
-    for mc, lq in ((5, 2), (37, 3), (255, 4)):
+    for mc in (5, 37, 255):
         text = build_text(rng, 2000, min(mc, 30), False)
         index = fmx.FMIndex.new(fmx.Text.with_max_character(text, mc))
-        assert index.sectors_per_rank() == lq
+        assert index.sectors_per_rank() == 1           # per-symbol bit vectors
     dna_like = build_text(rng, 2000, 4, False)
     assert fmx.FMIndex.new(fmx.Text.with_max_character(dna_like, 4)).sectors_per_rank() == 1
 

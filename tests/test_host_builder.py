@@ -85,7 +85,7 @@ def test_blob_reader_matches_oracle(kind):
         n = len(text)
         assert (b.n, b.kind, b.levels, b.cs_len) == (n, kind, int(mc).bit_length(), mc + 1)
         zeros = text.count(0) if kind != 1 else 1
-        assert b.layout == (1 if mc <= 4 and zeros <= 1024 else 2)
+        assert b.layout == (1 if mc <= 4 and zeros <= 1024 else 3)
         assert b.sa_level == orc.lib().orc_sample_level(o._h)
         assert b.sa_word_size == orc.lib().orc_sample_word_size(o._h)
         rows = range(n) if n < 300 else [int(v) for v in rng.integers(0, n, 200)]
@@ -115,7 +115,7 @@ def test_q4_falls_back_to_wavelet_with_many_zeros(monkeypatch):
     text = build_text(rng, 9000, 5, True)          # ~17 % zeros > FMX_MAX_EXC
     assert text.count(0) > 1024
     b = Blob(fmx.blob_build(fmx.Text.with_max_character(text, 4), 2, 1))
-    assert b.layout == 2                           # the quaternary wavelet matrix takes every other case
+    assert b.layout == 3                           # per-symbol bit vectors take every other case within the budget
     o = orc.OracleIndex(text, 2, level=1, max_character=4)
     for i in rng.integers(0, len(text), 100):
         c, nx = b.lf_step(int(i))
@@ -126,15 +126,18 @@ def test_q4_falls_back_to_wavelet_with_many_zeros(monkeypatch):
 
 
 @pytest.mark.parametrize("kind", [0, 1, 2])
-def test_binary_wavelet_blob_matches_oracle(kind, monkeypatch):
-    """FMX_FORCE_WAVELET=1 keeps the binary wavelet matrix (layout 0): same answers"""
-    monkeypatch.setenv("FMX_FORCE_WAVELET", "1")
+@pytest.mark.parametrize("env,layout", [(("FMX_FORCE_WAVELET", "1"), 0), (("FMX_SYM_BUDGET_MB", "0"), 2)])
+def test_fallback_layout_blobs_match_oracle(kind, env, layout, monkeypatch):
+    """FMX_FORCE_WAVELET=1 keeps the binary wavelet matrix (layout 0); a zero SYM budget gives the quaternary
+    wavelet matrix (layout 2, what alphabets too large for the per-symbol vectors get): same answers"""
+    monkeypatch.setenv(*env)
     rng = np.random.default_rng(kind + 400)
     for mc in (4, 37, 255):
         text = build_text(rng, 500, min(mc, 8), kind == 2)
         o = orc.OracleIndex(text, kind, level=1, max_character=mc)
         b = Blob(fmx.blob_build(fmx.Text.with_max_character(text, mc), kind, 1))
-        assert b.layout == 0
+        zeros = text.count(0) if kind != 1 else 1
+        assert b.layout == (1 if layout == 2 and mc <= 4 and zeros <= 1024 else layout)
         n = len(text)
         for i in range(0, n, 3):
             c, nx = b.lf_step(i)

@@ -98,6 +98,7 @@ struct fmx_index {
     int opt_persistent = 0;  // 1: persistent refill search kernels instead of one pattern per thread
     int opt_kmer = 1;
     uint64_t opt_pipeline_chunk = 0;  // patterns per pipeline chunk (0 = automatic)
+    int opt_locate_refill = 0;        // 1: per-lane refill k_locate (lost the A/B: it breaks the coalescing of adjacent rows)
     int opt_bucket = 0;               // 1: visit the batch in k-mer bucket order (lost the A/B, kept for experiments); -1 auto
     mutable DevBuf buf[B_COUNT];
     mutable Lane lane[FMX_LANES];
@@ -351,6 +352,7 @@ int fmx_index_set_option(fmx_index *idx, const char *key, int64_t value) {
         int rc = build_big_table(idx, (uint64_t)(value < 0 ? 0 : value) << 20);
         if (rc) return rc;
     }
+    else if (k == "locate_refill") idx->opt_locate_refill = value != 0;
     else if (k == "bucket") idx->opt_bucket = value < 0 ? -1 : (value != 0);
     else if (k == "pipeline_chunk") idx->opt_pipeline_chunk = value > 0 ? (uint64_t)value : 0;
     else if (k == "l2_fetch_granularity") {
@@ -814,9 +816,23 @@ static int locate_fill(const fmx_index *idx, const uint32_t *d_rows, uint64_t to
     a.positions = d_pos;
     a.piece_ids = d_pid;
     a.work = count_work ? idx->d_work : nullptr;
-    uint64_t blocks = (total + 255) / 256;
-    uint64_t cap = (uint64_t)idx->sms * 8 * 8;
-    if (blocks > cap) blocks = cap;
+    if (!idx->opt_locate_refill) {
+        uint64_t blocks = (total + 255) / 256;
+        uint64_t cap = (uint64_t)idx->sms * 8 * 8;
+        if (blocks > cap) blocks = cap;
+        dispatch(idx, [&](auto K, auto LY) { k_locate_simple<K(), LY()><<<(unsigned)blocks, 256, 0, st>>>(idx->dev, a); });
+        LAUNCH_CHECK();
+        return 0;
+    }
+    // per-lane refill: a warp works through chunks of consecutive hits; enough chunks per warp to keep
+    // its lanes fed, enough warps to fill the GPU (8 CTAs of 8 warps per SM)
+    const uint64_t max_warps = (uint64_t)idx->sms * 8 * 8;
+    uint64_t chunk = 64;
+    while (chunk < 1024 && (total + chunk - 1) / chunk > 4 * max_warps) chunk *= 2;
+    uint64_t warps = (total + chunk - 1) / chunk;
+    if (warps > max_warps) warps = max_warps;
+    a.chunk = chunk;
+    const uint64_t blocks = (warps + 7) / 8;
     dispatch(idx, [&](auto K, auto LY) { k_locate<K(), LY()><<<(unsigned)blocks, 256, 0, st>>>(idx->dev, a); });
     LAUNCH_CHECK();
     return 0;

@@ -1044,6 +1044,7 @@ struct LocateArgs {
     uint64_t *positions;  // nullable
     uint64_t *piece_ids;  // nullable (MultiPieces)
     unsigned long long *work;  // [1] += executed LF steps
+    uint64_t chunk;            // k_locate: consecutive hits per warp chunk
 };
 
 // get_sa (fm_index.rs:127-140 / rlfmi.rs:176-189 / multi_pieces.rs:188-201): LF-walk each row to a
@@ -1051,7 +1052,7 @@ struct LocateArgs {
 // position and the piece boundary table: it equals the number of \0 before the position, which is
 // what the reference's walk to the piece start computes (pinned by multi_pieces.rs:287-296).
 template <int KIND, int LAYOUT>
-__global__ void __launch_bounds__(256) k_locate(const __grid_constant__ FmxDev ix, const __grid_constant__ LocateArgs a) {
+__global__ void __launch_bounds__(256) k_locate_simple(const __grid_constant__ FmxDev ix, const __grid_constant__ LocateArgs a) {
     __shared__ Tabs<LAYOUT> tb;
     load_tables<LAYOUT>(ix, tb);
     unsigned long long steps = 0;
@@ -1082,6 +1083,83 @@ __global__ void __launch_bounds__(256) k_locate(const __grid_constant__ FmxDev i
     if (a.work) {
         for (int o = 16; o > 0; o >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, o);
         if ((threadIdx.x & 31) == 0 && steps) atomicAdd(a.work + 1, steps);
+    }
+}
+
+// The same, with per-lane refill (option "locate_refill"; NOT the default -- it lost the A/B).  Walk
+// lengths are geometric (mean 2^level - 1, long tail), so with one hit per thread a warp waits for its
+// slowest lane: ncu showed 8-12 of 32 lanes active and the kernel issue-bound on the RLFM config
+// (profiles/r01b_cfg3_ncu.txt: ALU pipe 75 %, 11.7 active threads per instruction).  Here a warp owns
+// chunks of `chunk` consecutive hits and a lane takes the next hit the moment its own walk ends, so
+// nearly every issued LF step serves 32 lanes.  Measured: 15-20 % SLOWER on every workload
+// (profiles/r01b_locate_refill_ab.json).  With one hit per thread the 32 lanes walk ADJACENT rows in
+// lockstep, and LF keeps adjacent rows with equal symbols adjacent, so their probes share sectors;
+// refilled lanes hold unrelated rows and every probe becomes its own memory request.
+template <int KIND, int LAYOUT>
+__global__ void __launch_bounds__(256) k_locate(const __grid_constant__ FmxDev ix, const __grid_constant__ LocateArgs a) {
+    __shared__ Tabs<LAYOUT> tb;
+    load_tables<LAYOUT>(ix, tb);
+    unsigned long long steps = 0;
+    const uint32_t mask = (1u << ix.sa_level) - 1u;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    uint64_t total = a.total;
+    if (a.total_dev && *a.total_dev < total) total = *a.total_dev;
+    const uint64_t C = a.chunk;
+    uint64_t chunk = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint64_t next = chunk * C < total ? chunk * C : total;
+    uint64_t end = next + C < total ? next + C : total;
+    bool active = false;
+    uint32_t row = 0, st = 0;
+    uint64_t h = 0;
+    for (;;) {
+        if (active && !(row & mask)) {  // sampled row reached: (sa + steps) % n, both terms < n
+            uint64_t v = (uint64_t)__ldg(ix.sa + (row >> ix.sa_level)) + st;
+            if (v >= ix.n) v -= ix.n;
+            if (a.positions) a.positions[h] = v;
+            if (KIND == FMX_KIND_MULTI_ && a.piece_ids) {
+                uint32_t lo = 0, hi = ix.ndoc;  // number of piece ends strictly before v
+                while (lo < hi) {
+                    uint32_t m = lo + ((hi - lo) >> 1);
+                    if (__ldg(ix.piece_end + m) < v) lo = m + 1; else hi = m;
+                }
+                a.piece_ids[h] = lo;
+            }
+            steps += st;
+            active = false;
+        }
+        const unsigned idle = __ballot_sync(0xffffffffu, !active);
+        if (idle) {
+            if (next == end && next < total) {  // this warp's next chunk
+                chunk += nwarps;
+                next = chunk * C < total ? chunk * C : total;
+                end = next + C < total ? next + C : total;
+            }
+            const uint64_t avail = end - next;
+            if (avail) {
+                const uint32_t r = __popc(idle & lt);
+                if (!active && r < avail) {
+                    h = next + r;
+                    row = a.rows[h];
+                    st = 0;
+                    active = true;
+                }
+                const uint32_t want = __popc(idle);
+                next += want < avail ? want : avail;
+            } else if (idle == 0xffffffffu) {
+                break;
+            }
+        }
+        if (active && (row & mask)) {
+            uint32_t sym;
+            row = lf_step<KIND, LAYOUT>(ix, tb, row, sym);
+            st++;
+        }
+    }
+    if (a.work) {
+        for (int o = 16; o > 0; o >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, o);
+        if (lane == 0 && steps) atomicAdd(a.work + 1, steps);
     }
 }
 

@@ -500,6 +500,14 @@ def test_search_options_do_not_change_results():
         b = index.search_batch(pats)
         assert np.array_equal(b.s, ref.s) and np.array_equal(b.e, ref.e), (key, val)
         assert index.last_work()[0] == steps
+    hoff, pos = ref.locate()
+    index.set_option("locate_refill", 0)                  # one hit per thread instead of per-lane refill
+    hoff2, pos2 = index.search_batch(pats).locate()
+    lf_simple = index.last_work()[1]
+    index.set_option("locate_refill", 1)
+    hoff3, pos3 = index.search_batch(pats).locate()
+    assert np.array_equal(hoff, hoff2) and np.array_equal(pos, pos2) and np.array_equal(pos, pos3)
+    assert index.last_work()[1] == lf_simple
     with pytest.raises(fmx.Error):
         index.set_option("no_such_option", 1)
 

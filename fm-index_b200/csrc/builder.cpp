@@ -152,7 +152,7 @@ static void build_wavelet(const uint8_t *seq, uint64_t n, uint32_t L, WMat &m) {
     }
 }
 
-// One quaternary level (fmx_layout.h): cnt[4] + 64 two-bit codes per 32-byte block.
+// One quaternary level (fmx_layout.h): cnt[4] + 64 two-bit codes (as two 64-bit planes) per 32-byte block.
 struct Q4Vec {
     std::vector<uint32_t> w;
     std::vector<uint32_t> exc;
@@ -170,7 +170,8 @@ struct Q4Vec {
                 uint32_t sym = seq[i];
                 uint32_t code = sym ? sym - 1 : 0;
                 uint32_t t = (uint32_t)(i - lo);
-                blk[4 + (t >> 4)] |= code << (2 * (t & 15));
+                blk[4 + (t >> 5)] |= (code & 1u) << (t & 31);  // bit planes: words 4,5 = low bits, 6,7 = high bits
+                blk[6 + (t >> 5)] |= (code >> 1) << (t & 31);
                 cnt[code]++;
             }
             for (int c = 0; c < 4; c++) blk[c] = cnt[c];
@@ -214,7 +215,8 @@ struct WM4 {
                 uint64_t lo = (uint64_t)b * 64, hi = lo + 64 < n ? lo + 64 : n;
                 for (uint64_t i = lo; i < hi; i++) {
                     uint32_t d = digit(cur[i], Lq, l), t = (uint32_t)(i - lo);
-                    blk[4 + (t >> 4)] |= d << (2 * (t & 15));
+                    blk[4 + (t >> 5)] |= (d & 1u) << (t & 31);
+                    blk[6 + (t >> 5)] |= (d >> 1) << (t & 31);
                     cnt[d]++;
                 }
                 for (int c = 0; c < 4; c++) blk[c] = cnt[c];
@@ -257,7 +259,8 @@ struct WM4 {
     uint64_t rank(uint32_t l, uint64_t pos, uint32_t d) const {
         const uint32_t *blk = &lv[l][(pos / 64) * 8];
         uint64_t c = blk[d];
-        for (uint32_t t = 0; t < pos % 64; t++) c += ((blk[4 + (t >> 4)] >> (2 * (t & 15))) & 3u) == d;
+        for (uint32_t t = 0; t < pos % 64; t++)
+            c += ((((blk[4 + (t >> 5)] >> (t & 31)) & 1u) | (((blk[6 + (t >> 5)] >> (t & 31)) & 1u) << 1)) == d);
         return c;
     }
     uint64_t walk(uint64_t pos, uint32_t c) const {

@@ -98,6 +98,7 @@ struct fmx_index {
     int opt_persistent = 0;  // 1: persistent refill search kernels instead of one pattern per thread
     int opt_kmer = 1;
     uint64_t opt_pipeline_chunk = 0;  // patterns per pipeline chunk (0 = automatic)
+    int opt_locate_expand = 0;        // 0 auto, 1 always expand the rows first, 2 always binary-search in k_locate
     int opt_locate_refill = 0;        // 1: per-lane refill k_locate (lost the A/B: it breaks the coalescing of adjacent rows)
     int opt_bucket = 0;               // 1: visit the batch in k-mer bucket order (lost the A/B, kept for experiments); -1 auto
     mutable DevBuf buf[B_COUNT];
@@ -353,6 +354,7 @@ int fmx_index_set_option(fmx_index *idx, const char *key, int64_t value) {
         if (rc) return rc;
     }
     else if (k == "locate_refill") idx->opt_locate_refill = value != 0;
+    else if (k == "locate_expand") idx->opt_locate_expand = (int)value;
     else if (k == "bucket") idx->opt_bucket = value < 0 ? -1 : (value != 0);
     else if (k == "pipeline_chunk") idx->opt_pipeline_chunk = value > 0 ? (uint64_t)value : 0;
     else if (k == "l2_fetch_granularity") {
@@ -388,15 +390,18 @@ uint32_t fmx_index_sectors_per_rank(const fmx_index *idx) {
 
 // ------------------------------------------------------------------ scans
 
-template <class Tin, class Tout, class Op, bool EXCL>
-static int device_scan(const Tin *in, uint64_t n, Tout *out, Op op, bool write_total, DevBuf &tiles, cudaStream_t st) {
+// tiles below this count: each block of the last phase reduces the preceding tile sums itself
+#define FMX_SCAN_SELF_CARRY_TILES 4096
+
+template <class Load, class Tout, class Op, bool EXCL>
+static int device_scan_load(Load in, uint64_t n, Tout *out, Op op, bool write_total, DevBuf &tiles, cudaStream_t st) {
     if (n == 0) {
         if (EXCL && write_total) CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(Tout), st));
         return 0;
     }
     uint64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     if (ntiles == 1) {
-        k_scan_apply<Tin, Tout, Op, EXCL><<<1, SCAN_THREADS, 0, st>>>(in, n, nullptr, out, op, write_total ? 1 : 0);
+        k_scan_apply<Load, Tout, Op, EXCL><<<1, SCAN_THREADS, 0, st>>>(in, n, nullptr, nullptr, out, op, write_total ? 1 : 0);
         LAUNCH_CHECK();
         return 0;
     }
@@ -408,8 +413,13 @@ static int device_scan(const Tin *in, uint64_t n, Tout *out, Op op, bool write_t
     if (rc) return rc;
     uint64_t *sum0 = tiles.as<uint64_t>();
     uint64_t *pre0 = sum0 + ntiles;
-    k_scan_reduce<Tin, Op><<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(in, n, sum0, op);
+    k_scan_reduce<Load, Op><<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(in, n, sum0, op);
     LAUNCH_CHECK();
+    if (ntiles <= FMX_SCAN_SELF_CARRY_TILES) {
+        k_scan_apply<Load, Tout, Op, EXCL><<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(in, n, nullptr, sum0, out, op, write_total ? 1 : 0);
+        LAUNCH_CHECK();
+        return 0;
+    }
     // exclusive scan of the tile sums (recursive on the same buffer tail)
     struct Level {
         uint64_t *sum, *pre, n;
@@ -417,23 +427,29 @@ static int device_scan(const Tin *in, uint64_t n, Tout *out, Op op, bool write_t
     std::vector<Level> lv;
     lv.push_back({sum0, pre0, ntiles});
     uint64_t *cursor = pre0 + ntiles;
+    using L64 = LoadPtr<uint64_t>;
     while (lv.back().n > SCAN_TILE) {
         uint64_t m = (lv.back().n + SCAN_TILE - 1) / SCAN_TILE;
         Level nx{cursor, cursor + m, m};
         cursor += 2 * m;
-        k_scan_reduce<uint64_t, Op><<<(unsigned)m, SCAN_THREADS, 0, st>>>(lv.back().sum, lv.back().n, nx.sum, op);
+        k_scan_reduce<L64, Op><<<(unsigned)m, SCAN_THREADS, 0, st>>>(L64{lv.back().sum}, lv.back().n, nx.sum, op);
         LAUNCH_CHECK();
         lv.push_back(nx);
     }
     for (size_t k = lv.size(); k-- > 0;) {
         const uint64_t *carry = (k + 1 < lv.size()) ? lv[k + 1].pre : nullptr;
         unsigned g = (unsigned)((lv[k].n + SCAN_TILE - 1) / SCAN_TILE);
-        k_scan_apply<uint64_t, uint64_t, Op, true><<<g, SCAN_THREADS, 0, st>>>(lv[k].sum, lv[k].n, carry, lv[k].pre, op, 0);
+        k_scan_apply<L64, uint64_t, Op, true><<<g, SCAN_THREADS, 0, st>>>(L64{lv[k].sum}, lv[k].n, carry, nullptr, lv[k].pre, op, 0);
         LAUNCH_CHECK();
     }
-    k_scan_apply<Tin, Tout, Op, EXCL><<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(in, n, pre0, out, op, write_total ? 1 : 0);
+    k_scan_apply<Load, Tout, Op, EXCL><<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(in, n, pre0, nullptr, out, op, write_total ? 1 : 0);
     LAUNCH_CHECK();
     return 0;
+}
+
+template <class Tin, class Tout, class Op, bool EXCL>
+static int device_scan(const Tin *in, uint64_t n, Tout *out, Op op, bool write_total, DevBuf &tiles, cudaStream_t st) {
+    return device_scan_load<LoadPtr<Tin>, Tout, Op, EXCL>(LoadPtr<Tin>{in}, n, out, op, write_total, tiles, st);
 }
 
 // ------------------------------------------------------------------ search
@@ -719,19 +735,33 @@ extern "C" int fmx_search_batch(const fmx_index *idx, int mode, const uint8_t *p
 
 // ------------------------------------------------------------------ locate
 
+// where the rows of the hits come from: the expanded list, or (rows == NULL) the ranges themselves
+struct RowSource {
+    const uint32_t *rows = nullptr;
+    const uint64_t *hoff = nullptr;
+    const uint64_t *s = nullptr;
+    uint64_t npat = 0;
+};
+
+// small batches skip the row expansion (memset + mark + 2-3 scan launches + expand): k_locate finds its row
+// by binary search over the hit offsets instead
+static bool expand_by_search(const fmx_index *idx, uint64_t total) {
+    if (idx->opt_locate_expand == 1) return false;
+    if (idx->opt_locate_expand == 2) return true;
+    return total <= (1ull << 22);
+}
+
+
 // ---- locate, stage 1 (asynchronous): candidate-row counts of every range and their exclusive
 // prefix sum.  d_off gets npat+1 entries; d_off[npat] is the number of candidate rows.
 static int locate_counts(const fmx_index *idx, DevBuf *buf, const uint64_t *d_s, const uint64_t *d_e, uint64_t npat,
                          uint64_t *d_off, cudaStream_t st) {
     int rc;
     if (npat >= 0xFFFFFFFFull) return fail(FMX_ERR_UNSUPPORTED, "at most 2^32 - 2 patterns per locate call");
-    if ((rc = buf[B_CNT].ensure((npat + 1) * 8))) return rc;
-    uint64_t *d_cnt = buf[B_CNT].as<uint64_t>();
-    if (npat) {
-        k_range_counts<<<grid_for(npat, 256), 256, 0, st>>>(d_s, d_e, npat, d_cnt);
-        LAUNCH_CHECK();
-    }
-    return device_scan<uint64_t, uint64_t, OpSum, true>(d_cnt, npat, d_off, OpSum(), true, buf[B_TILES], st);
+    (void)rc;
+    // candidate rows per range (e - s) are computed inside the scan's loads
+    return device_scan_load<LoadRangeCount, uint64_t, OpSum, true>(LoadRangeCount{d_s, d_e}, npat, d_off, OpSum(), true,
+                                                                   buf[B_TILES], st);
 }
 
 // ---- locate, stage 2: the candidate rows themselves, in pattern order then ascending row order
@@ -741,13 +771,20 @@ static int locate_counts(const fmx_index *idx, DevBuf *buf, const uint64_t *d_s,
 // Without it d_hit_off must be d_off.  *rows_out points at the hit rows in scratch.
 static int locate_rows(const fmx_index *idx, DevBuf *buf, int prefix_only, const uint64_t *d_s, uint64_t npat,
                        const uint64_t *d_off, uint64_t total, uint64_t *d_hit_off, uint64_t *hits_out,
-                       const uint32_t **rows_out, cudaStream_t st) {
+                       RowSource *rows_out, cudaStream_t st) {
     int rc;
-    *rows_out = nullptr;
+    *rows_out = RowSource();
     if (total >= 0xFFFFFFFFull * 4) return fail(FMX_ERR_UNSUPPORTED, "too many candidate rows in one locate call");
     if (total == 0) {
         if (prefix_only) CUDA_TRY(cudaMemsetAsync(d_hit_off, 0, (npat + 1) * 8, st));
         *hits_out = 0;
+        return 0;
+    }
+    if (!prefix_only && expand_by_search(idx, total)) {
+        *hits_out = total;
+        rows_out->hoff = d_off;
+        rows_out->s = d_s;
+        rows_out->npat = npat;
         return 0;
     }
     if ((rc = buf[B_OWNER].ensure(total * 4))) return rc;
@@ -762,7 +799,7 @@ static int locate_rows(const fmx_index *idx, DevBuf *buf, int prefix_only, const
     LAUNCH_CHECK();
     if (!prefix_only) {
         *hits_out = total;
-        *rows_out = d_rows;
+        rows_out->rows = d_rows;
         return 0;
     }
     if ((rc = buf[B_FLAG].ensure(total * 4))) return rc;
@@ -781,7 +818,7 @@ static int locate_rows(const fmx_index *idx, DevBuf *buf, int prefix_only, const
         if ((rc = buf[B_ROWS2].ensure(kept * 4))) return rc;
         k_compact_rows<<<grid_for(total, 256), 256, 0, st>>>(d_rows, d_flag, d_fpos, total, buf[B_ROWS2].as<uint32_t>());
         LAUNCH_CHECK();
-        *rows_out = buf[B_ROWS2].as<uint32_t>();
+        rows_out->rows = buf[B_ROWS2].as<uint32_t>();
     }
     *hits_out = kept;
     return 0;
@@ -789,7 +826,7 @@ static int locate_rows(const fmx_index *idx, DevBuf *buf, int prefix_only, const
 
 // both stages with a synchronisation in between (the two-phase device API and fmx_locate_batch)
 static int locate_prepare(const fmx_index *idx, int prefix_only, const uint64_t *d_s, const uint64_t *d_e,
-                          uint64_t npat, uint64_t *d_hit_off, uint64_t *total_out, const uint32_t **rows_out,
+                          uint64_t npat, uint64_t *d_hit_off, uint64_t *total_out, RowSource *rows_out,
                           cudaStream_t st) {
     int rc;
     DevBuf *buf = idx->buf;
@@ -805,12 +842,15 @@ static int locate_prepare(const fmx_index *idx, int prefix_only, const uint64_t 
     return locate_rows(idx, buf, prefix_only, d_s, npat, d_off, total, d_hit_off, total_out, rows_out, st);
 }
 
-static int locate_fill(const fmx_index *idx, const uint32_t *d_rows, uint64_t total, uint64_t *d_pos, uint64_t *d_pid,
+static int locate_fill(const fmx_index *idx, const RowSource &src, uint64_t total, uint64_t *d_pos, uint64_t *d_pid,
                        cudaStream_t st, bool count_work = true, const uint64_t *total_dev = nullptr) {
     if (count_work) CUDA_TRY(cudaMemsetAsync(idx->d_work + 1, 0, sizeof(unsigned long long), st));
     if (total == 0) return 0;
     LocateArgs a;
-    a.rows = d_rows;
+    a.rows = src.rows;
+    a.hoff = src.hoff;
+    a.s = src.s;
+    a.npat = src.npat;
     a.total = total;
     a.total_dev = total_dev;
     a.positions = d_pos;
@@ -852,7 +892,7 @@ extern "C" int fmx_locate_count_device(const fmx_index *idx, int prefix_only, co
     int rc = locate_args_ok(idx, false);
     if (rc) return rc;
     CUDA_TRY(cudaSetDevice(idx->device));
-    const uint32_t *rows;
+    RowSource rows;
     return locate_prepare(idx, prefix_only, d_s, d_e, npat, d_hit_off, total_hits, &rows, pick_stream(idx, stream));
 }
 
@@ -868,7 +908,14 @@ extern "C" int fmx_locate_fill_device(const fmx_index *idx, int prefix_only, con
     (void)npat;
     (void)d_hit_off;
     // the rows prepared by the matching fmx_locate_count_device call are still in scratch
-    const uint32_t *rows = prefix_only ? idx->buf[B_ROWS2].as<uint32_t>() : idx->buf[B_ROWS].as<uint32_t>();
+    RowSource rows;  // what fmx_locate_count_device left behind for these ranges
+    if (!prefix_only && expand_by_search(idx, total_hits)) {
+        rows.hoff = d_hit_off;
+        rows.s = d_s;
+        rows.npat = npat;
+    } else {
+        rows.rows = prefix_only ? idx->buf[B_ROWS2].as<uint32_t>() : idx->buf[B_ROWS].as<uint32_t>();
+    }
     return locate_fill(idx, rows, total_hits, d_positions, d_piece_ids, pick_stream(idx, stream));
 }
 
@@ -884,7 +931,7 @@ extern "C" int fmx_locate_batch_device(const fmx_index *idx, int prefix_only, co
     cudaStream_t st = pick_stream(idx, stream);
     if (prefix_only) {  // the L == 0 filter needs the kept count on the host: synchronous path
         uint64_t total = 0;
-        const uint32_t *rows = nullptr;
+        RowSource rows;
         if ((rc = locate_prepare(idx, prefix_only, d_s, d_e, npat, d_hit_off, &total, &rows, st))) return rc;
         if (total > capacity) total = capacity;
         return locate_fill(idx, rows, total, d_positions, d_piece_ids, st);
@@ -893,6 +940,14 @@ extern "C" int fmx_locate_batch_device(const fmx_index *idx, int prefix_only, co
     if ((rc = locate_counts(idx, buf, d_s, d_e, npat, d_hit_off, st))) return rc;
     if (capacity == 0 || npat == 0) return FMX_OK;
     if (capacity >= 0xFFFFFFFFull * 4) return fail(FMX_ERR_UNSUPPORTED, "capacity too large");
+    const uint64_t *d_total0 = d_hit_off + npat;
+    if (expand_by_search(idx, capacity)) {
+        RowSource src;
+        src.hoff = d_hit_off;
+        src.s = d_s;
+        src.npat = npat;
+        return locate_fill(idx, src, capacity, d_positions, d_piece_ids, st, true, d_total0);
+    }
     if ((rc = buf[B_OWNER].ensure(capacity * 4))) return rc;
     if ((rc = buf[B_ROWS].ensure(capacity * 4))) return rc;
     uint32_t *d_owner = buf[B_OWNER].as<uint32_t>();
@@ -904,7 +959,9 @@ extern "C" int fmx_locate_batch_device(const fmx_index *idx, int prefix_only, co
     if ((rc = device_scan<uint32_t, uint32_t, OpMax, false>(d_owner, capacity, d_owner, OpMax(), false, buf[B_TILES], st))) return rc;
     k_expand_rows<<<grid_for(capacity, 256), 256, 0, st>>>(d_s, d_hit_off, d_owner, capacity, d_total, d_rows);
     LAUNCH_CHECK();
-    return locate_fill(idx, d_rows, capacity, d_positions, d_piece_ids, st, true, d_total);
+    RowSource src;
+    src.rows = d_rows;
+    return locate_fill(idx, src, capacity, d_positions, d_piece_ids, st, true, d_total);
 }
 
 extern "C" int fmx_locate_batch(const fmx_index *idx, int prefix_only, const uint64_t *s, const uint64_t *e, uint64_t npat,
@@ -925,7 +982,7 @@ extern "C" int fmx_locate_batch(const fmx_index *idx, int prefix_only, const uin
         CUDA_TRY(cudaMemcpyAsync(idx->buf[B_E].p, e, npat * 8, cudaMemcpyHostToDevice, st));
     }
     uint64_t total = 0;
-    const uint32_t *rows = nullptr;
+    RowSource rows;
     uint64_t *d_hoff = idx->buf[B_OFF].as<uint64_t>();
     if ((rc = locate_prepare(idx, prefix_only, idx->buf[B_S].as<uint64_t>(), idx->buf[B_E].as<uint64_t>(), npat, d_hoff,
                              &total, &rows, st)))
@@ -1041,7 +1098,7 @@ extern "C" int fmx_search_locate_batch(const fmx_index *idx, int mode, const uin
         uint64_t *d_unf = L.buf[B_HOFF].as<uint64_t>();
         uint64_t *d_src = d_unf;
         uint64_t hits = cand;
-        const uint32_t *rows = nullptr;
+        RowSource rows;
         if (want_hits || prefix_only) {
             if (prefix_only) {
                 if ((r = L.buf[B_INE].ensure((n + 1) * 8))) return r;

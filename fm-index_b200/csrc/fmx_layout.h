@@ -25,7 +25,11 @@
 // BASELINE.json) and the sequence holds at most FMX_MAX_EXC zeros, the L = 3 binary levels
 // collapse into ONE level of arity 4: 32-byte blocks
 //       word 0..3 : u32 occurrences of the 2-bit codes 0..3 in all preceding blocks
-//       word 4..7 : 64 two-bit codes (code = symbol - 1)
+//       word 4..7 : 64 two-bit codes (code = symbol - 1) as two 64-bit PLANES: words 4,5 hold the low
+//                   bit of codes 0..63, words 6,7 the high bit.  "positions holding code c" is then
+//                   (p0 ^ a) & (p1 ^ b) with a, b in {0, ~0}: one masked 64-bit popcount per rank
+//                   (interleaved 2-bit fields needed four; k_search was issue-bound on them when the
+//                   index fits L2)
 // so lf_map2(c, i) = cs[c] + rank(i, c) costs ONE sector instead of three.
 //
 // QUATERNARY WAVELET MATRIX ("WM4", the default for every other alphabet).  The same 32-byte
@@ -56,7 +60,7 @@
 #include <vector_types.h>  // uint4 (CUDA toolkit header, host-safe)
 
 #define FMX_BLOB_MAGIC 0x3030324258584d46ull /* "FMXXB200" little endian-ish tag */
-#define FMX_BLOB_VERSION 4u
+#define FMX_BLOB_VERSION 5u
 #define FMX_MAX_LEVELS 8
 #define FMX_RB_BITS 192u
 #define FMX_MAX_EXC 1024u   /* Q4 layout: at most this many \0 symbols in the sequence */

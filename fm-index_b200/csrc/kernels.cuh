@@ -241,39 +241,68 @@ __device__ __forceinline__ bool q4_is_exc(const FmxDev &ix, const uint32_t *exc,
     uint32_t lb = q4_lower_bound(exc, ix.nexc, i);
     return lb < ix.nexc && exc[lb] == i;
 }
-// one bit per code field (at the even bit positions) where the field equals `code`
-__device__ __forceinline__ uint32_t q4_eq(uint32_t word, uint32_t code) {
-    uint32_t y = ~(word ^ (code * 0x55555555u));
-    return y & (y >> 1) & 0x55555555u;
+// the block's payload is two 64-bit planes (w[4..5] = low bits, w[6..7] = high bits of the 64 codes):
+// bit t of (lo, hi) is set where code t equals `code`
+__device__ __forceinline__ void q4_match(const RB &b, uint32_t code, uint32_t &lo, uint32_t &hi) {
+    const uint32_t a0 = (code & 1u) ? 0u : 0xFFFFFFFFu, a1 = (code & 2u) ? 0u : 0xFFFFFFFFu;
+    lo = (b.w[4] ^ a0) & (b.w[6] ^ a1);
+    hi = (b.w[5] ^ a0) & (b.w[7] ^ a1);
 }
 // occurrences of `code` among the first r codes of the block, r in [0, 64)
 __device__ __forceinline__ uint32_t q4_count(const RB &b, uint32_t r, uint32_t code) {
-    uint32_t total = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        int d = (int)r - 16 * k;
-        uint32_t n = d <= 0 ? 0u : (d >= 16 ? 16u : (uint32_t)d);
-        uint32_t keep = (uint32_t)((1ull << (2u * n)) - 1ull);
-        total += __popc(q4_eq(b.w[4 + k], code) & keep);
-    }
-    return total;
+    uint32_t lo, hi;
+    q4_match(b, code, lo, hi);
+    const uint64_t keep = ~(~0ull << r);
+    return __popc(lo & (uint32_t)keep) + __popc(hi & (uint32_t)(keep >> 32));
 }
 __device__ __forceinline__ uint32_t q4_code(const RB &b, uint32_t r) {
-    uint32_t k = r >> 4;
-    uint32_t word = k == 0 ? b.w[4] : (k == 1 ? b.w[5] : (k == 2 ? b.w[6] : b.w[7]));
-    return (word >> (2u * (r & 15u))) & 3u;
+    const uint32_t p0 = (r & 32u) ? b.w[5] : b.w[4], p1 = (r & 32u) ? b.w[7] : b.w[6];
+    return ((p0 >> (r & 31u)) & 1u) | (((p1 >> (r & 31u)) & 1u) << 1);
 }
 __device__ __forceinline__ uint32_t q4_cnt(const RB &b, uint32_t code) {
-    return code == 0 ? b.w[0] : (code == 1 ? b.w[1] : (code == 2 ? b.w[2] : b.w[3]));
+    const uint32_t lo = (code & 1u) ? b.w[1] : b.w[0], hi = (code & 1u) ? b.w[3] : b.w[2];  // selects, no branches
+    return (code & 2u) ? hi : lo;
+}
+// exceptions before i, counted only when `on` (lane-uniform control flow: the common single-\0 case is
+// two predicated instructions instead of a divergent branch)
+__device__ __forceinline__ uint32_t q4_exc_before_if(const FmxDev &ix, const uint32_t *exc, uint32_t i, bool on) {
+    if (ix.nexc == 1) return (on && exc[0] < i) ? 1u : 0u;
+    return on ? q4_lower_bound(exc, ix.nexc, i) : 0u;
 }
 // rank(i, c) given the block of i
 __device__ __forceinline__ uint32_t q4_rank_in(const FmxDev &ix, const uint32_t *exc, const RB &b, uint32_t i,
                                                uint32_t c) {
-    uint32_t x = q4_exc_before(ix, exc, i);
-    if (c == 0) return x;
+    if (c == 0) return q4_exc_before(ix, exc, i);
     uint32_t code = c - 1u;
     uint32_t v = q4_cnt(b, code) + q4_count(b, i & 63u, code);
-    return code == 0 ? v - x : v;
+    return v - q4_exc_before_if(ix, exc, i, code == 0);
+}
+// the same for both ends of an SA range; bs / be = their blocks, b2 = the block of e when it differs.
+// When both ends share the block (the usual case once the range is narrow) the match mask and the
+// block counter are computed once.
+__device__ __forceinline__ void q4_rank2_in(const FmxDev &ix, const uint32_t *exc, const uint4 *v, uint32_t c, uint32_t &s,
+                                            uint32_t &e) {
+    const uint32_t bs = s >> 6, be = e >> 6;
+    RB a = rb_load(v, bs);
+    if (c == 0) {
+        s = q4_exc_before(ix, exc, s);
+        e = q4_exc_before(ix, exc, e);
+        return;
+    }
+    const uint32_t code = c - 1u;
+    const uint32_t xs = q4_exc_before_if(ix, exc, s, code == 0), xe = q4_exc_before_if(ix, exc, e, code == 0);
+    uint32_t ml, mh;
+    q4_match(a, code, ml, mh);
+    const uint32_t base = q4_cnt(a, code);
+    const uint64_t ks = ~(~0ull << (s & 63u));
+    s = base + __popc(ml & (uint32_t)ks) + __popc(mh & (uint32_t)(ks >> 32)) - xs;
+    if (be == bs) {
+        const uint64_t ke = ~(~0ull << (e & 63u));
+        e = base + __popc(ml & (uint32_t)ke) + __popc(mh & (uint32_t)(ke >> 32)) - xe;
+    } else {
+        RB b = rb_load(v, be);
+        e = q4_cnt(b, code) + q4_count(b, e & 63u, code) - xe;
+    }
 }
 // select(k, c)
 __device__ __forceinline__ uint32_t q4_select(const FmxDev &ix, const uint32_t *exc, uint32_t c, uint32_t k) {
@@ -292,19 +321,16 @@ __device__ __forceinline__ uint32_t q4_select(const FmxDev &ix, const uint32_t *
     uint32_t before = q4_cnt(b, code);
     if (code == 0) before -= q4_exc_before(ix, exc, lo << 6);
     uint32_t rem = k - before, pos = lo << 6;
-#pragma unroll
-    for (int w = 0; w < 4; w++) {
-        uint32_t m = q4_eq(b.w[4 + w], code);
-        if (code == 0) {  // positions holding \0 are stored as code 0: drop them
-            uint32_t x0 = q4_exc_before(ix, exc, pos), x1 = q4_exc_before(ix, exc, pos + 16u);
-            for (uint32_t x = x0; x < x1; x++) m &= ~(1u << (2u * (exc[x] - pos)));
+    uint32_t ml, mh;
+    q4_match(b, code, ml, mh);
+    if (code == 0) {  // positions holding \0 are stored as code 0: drop them
+        uint32_t x0 = q4_exc_before(ix, exc, pos), x1 = q4_exc_before(ix, exc, pos + 64u);
+        for (uint32_t x = x0; x < x1; x++) {
+            uint32_t t = exc[x] - pos;
+            if (t & 32u) mh &= ~(1u << (t & 31u)); else ml &= ~(1u << t);
         }
-        uint32_t cnt = __popc(m);
-        if (rem < cnt) return pos + (__fns(m, 0, rem + 1) >> 1);
-        rem -= cnt;
-        pos += 16u;
     }
-    return pos;  // unreachable for a valid k
+    return pos + select_in_word64(ml, mh, rem);
 }
 
 // ------------------------------------------------------------------ quaternary wavelet matrix (LAYOUT_W4)
@@ -369,16 +395,10 @@ __device__ __forceinline__ uint32_t w4_select_level(const FmxDev &ix, uint32_t l
         if (__ldg(cw + 8ull * mid + d) <= k) lo = mid; else hi = mid;
     }
     RB b = rb_load(ix.lv[l], lo);
-    uint32_t rem = k - q4_cnt(b, d), pos = lo << 6;
-#pragma unroll
-    for (int w = 0; w < 4; w++) {
-        uint32_t m = q4_eq(b.w[4 + w], d);
-        uint32_t cnt = __popc(m);
-        if (rem < cnt) return pos + (__fns(m, 0, rem + 1) >> 1);
-        rem -= cnt;
-        pos += 16u;
-    }
-    return pos;  // unreachable for a valid k
+    uint32_t rem = k - q4_cnt(b, d);
+    uint32_t ml, mh;
+    q4_match(b, d, ml, mh);
+    return (lo << 6) + select_in_word64(ml, mh, rem);
 }
 
 // select(k, c); base = walk_c(0)
@@ -421,13 +441,10 @@ __device__ __forceinline__ uint32_t seq_lf(const FmxDev &ix, const Tabs<LAYOUT> 
 template <int LAYOUT>
 __device__ __forceinline__ void seq_lf2(const FmxDev &ix, const Tabs<LAYOUT> &t, uint32_t c, uint32_t &s, uint32_t &e) {
     if (LAYOUT == FMX_LAYOUT_Q4) {
-        uint32_t bs = s >> 6, be = e >> 6;
-        RB a = rb_load(ix.lv[0], bs);
-        RB b = a;
-        if (be != bs) b = rb_load(ix.lv[0], be);
-        uint32_t base = t.cs[c];
-        s = base + q4_rank_in(ix, t.exc, a, s, c);
-        e = base + q4_rank_in(ix, t.exc, b, e, c);
+        q4_rank2_in(ix, t.exc, ix.lv[0], c, s, e);
+        const uint32_t base = t.cs[c];
+        s += base;
+        e += base;
     } else if (LAYOUT == FMX_LAYOUT_SY) {
         const uint4 *v = sy_vec(ix, c);
         uint32_t bs, rs, be, re;
@@ -723,13 +740,38 @@ __device__ __forceinline__ void pattern_span(const SearchArgs &a, uint64_t p, ui
     }
 }
 
+// Pattern bytes through a one-word register cache: consecutive characters of a pattern come from the
+// same aligned 32-bit word, so a 32-mer costs 8-9 load instructions instead of 32 (the byte loads were
+// ~20 % of the L1TEX wavefronts of k_search and, once index blocks had evicted the pattern lines from
+// L1, extra L2 requests: profiles/r01b_target_ncu.txt)
+struct PatReader {
+    const uint32_t *words;  // the aligned word holding the pattern's first byte
+    uint32_t off;           // byte offset of the pattern inside that word
+    uint32_t cur = 0xFFFFFFFFu, w = 0;
+    __device__ __forceinline__ explicit PatReader(const uint8_t *q) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(q);
+        words = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+        off = (uint32_t)(a & 3u);
+    }
+    // character k of the pattern
+    __device__ __forceinline__ uint32_t get(uint32_t k) {
+        const uint32_t idx = k + off, wi = idx >> 2;
+        if (wi != cur) {
+            cur = wi;
+            w = __ldg(words + wi);
+        }
+        return (w >> (8u * (idx & 3u))) & 0xFFu;
+    }
+};
+
 // table index of the last K characters of a pattern (base max_character, digit = c - 1);
 // false if one of them is \0 or exceeds max_character
 __device__ __forceinline__ bool kmer_index(const uint8_t *q, uint32_t len, uint32_t K, uint32_t maxc, uint32_t &idx) {
     uint32_t v = 0;
     bool valid = true;
+    PatReader pr(q);
     for (uint32_t j = 0; j < K; j++) {
-        uint32_t c = __ldg(q + len - K + j);
+        uint32_t c = pr.get(len - K + j);
         valid = valid && (c - 1u) < maxc;
         v = v * maxc + (c - 1u);
     }
@@ -790,8 +832,9 @@ __global__ void __launch_bounds__(256) k_search(const __grid_constant__ FmxDev i
         const uint8_t *q = a.pat + beg;
         uint32_t it = 0;
         if (a.init_s == nullptr) kmer_lookup(a, ix.max_character, q, len, s, e, it);
+        PatReader pr(q);
         for (uint32_t k = len; k-- > 0;) {
-            uint32_t c = __ldg(q + k);
+            uint32_t c = pr.get(k);
             if (c > ix.max_character) {  // the reference panics here (cs[c] out of bounds, fm_index.rs:94)
                 atomicOr(a.err, 1u);
                 break;
@@ -977,13 +1020,6 @@ __global__ void __launch_bounds__(256) k_search_steps(const __grid_constant__ Fm
     }
 }
 
-// hit counts per pattern (wrapper.rs:132-139, 203-217): e - s, unfiltered (the L == 0 filter is
-// applied on the expanded candidate rows)
-__global__ void k_range_counts(const uint64_t *s, const uint64_t *e, uint64_t npat, uint64_t *cnt) {
-    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < npat) cnt[p] = e[p] > s[p] ? e[p] - s[p] : 0;
-}
-
 // owner[off[p]] = p + 1 for every pattern with at least one candidate row
 __global__ void k_mark_owners(const uint64_t *off, uint64_t npat, uint32_t *owner) {
     uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1038,7 +1074,10 @@ __global__ void k_filtered_offsets(const uint64_t *off, const uint64_t *fpos, ui
 }
 
 struct LocateArgs {
-    const uint32_t *rows;
+    const uint32_t *rows;       // the hit rows; NULL => row h = s[p] + (h - hoff[p]) with p found by binary search
+    const uint64_t *hoff;       // (rows == NULL) npat + 1 hit offsets
+    const uint64_t *s;          // (rows == NULL) SA range starts
+    uint64_t npat;
     uint64_t total;             // number of hits, or the capacity when total_dev is given
     const uint64_t *total_dev;  // nullable: the real number of hits, on the device
     uint64_t *positions;  // nullable
@@ -1046,6 +1085,19 @@ struct LocateArgs {
     unsigned long long *work;  // [1] += executed LF steps
     uint64_t chunk;            // k_locate: consecutive hits per warp chunk
 };
+
+// row of hit h (wrapper.rs:206-216: rows s..e of pattern p, patterns in order): from the expanded row
+// list, or -- small batches, where the five expansion launches cost more than they save -- by binary
+// search of the hit offsets (neighbouring hits take the same path, so the probes hit L1)
+__device__ __forceinline__ uint32_t locate_row(const LocateArgs &a, uint64_t h) {
+    if (a.rows) return a.rows[h];
+    uint64_t lo = 0, hi = a.npat;  // last p with hoff[p] <= h
+    while (hi - lo > 1) {
+        uint64_t mid = lo + ((hi - lo) >> 1);
+        if (__ldg(a.hoff + mid) <= h) lo = mid; else hi = mid;
+    }
+    return (uint32_t)(__ldg(a.s + lo) + (h - __ldg(a.hoff + lo)));
+}
 
 // get_sa (fm_index.rs:127-140 / rlfmi.rs:176-189 / multi_pieces.rs:188-201): LF-walk each row to a
 // sampled row, one hit per thread.  piece id (multi_pieces.rs:208-218) is derived from the located
@@ -1061,7 +1113,7 @@ __global__ void __launch_bounds__(256) k_locate_simple(const __grid_constant__ F
     uint64_t total = a.total;
     if (a.total_dev && *a.total_dev < total) total = *a.total_dev;
     for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < total; h += stride) {
-        uint32_t row = a.rows[h];
+        uint32_t row = locate_row(a, h);
         uint32_t st = 0, sym;
         while (row & mask) {
             row = lf_step<KIND, LAYOUT>(ix, tb, row, sym);
@@ -1141,7 +1193,7 @@ __global__ void __launch_bounds__(256) k_locate(const __grid_constant__ FmxDev i
                 const uint32_t r = __popc(idle & lt);
                 if (!active && r < avail) {
                     h = next + r;
-                    row = a.rows[h];
+                    row = locate_row(a, h);
                     st = 0;
                     active = true;
                 }
@@ -1291,37 +1343,62 @@ __device__ __forceinline__ uint64_t block_scan_excl(uint64_t v, Op op, uint64_t 
     return op(warp_prefix, excl);
 }
 
+// scan inputs: a plain array, or the candidate-row count e - s of every SA range computed on the fly
+// (wrapper.rs:132-139; saves the k_range_counts pass and its array)
+template <class T>
+struct LoadPtr {
+    const T *p;
+    __device__ __forceinline__ uint64_t operator()(uint64_t i) const { return (uint64_t)p[i]; }
+};
+struct LoadRangeCount {
+    const uint64_t *s, *e;
+    __device__ __forceinline__ uint64_t operator()(uint64_t i) const {
+        uint64_t a = s[i], b = e[i];
+        return b > a ? b - a : 0;
+    }
+};
+
 // phase 1: per-tile reduction
-template <class Tin, class Op>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const Tin *in, uint64_t n, uint64_t *tile_sum, Op op) {
+template <class Load, class Op>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(Load in, uint64_t n, uint64_t *tile_sum, Op op) {
     __shared__ uint64_t s_warp[SCAN_THREADS / 32];
     uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
     uint64_t acc = op.identity();
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++)
-        if (base + k < n) acc = op(acc, (uint64_t)in[base + k]);
+        if (base + k < n) acc = op(acc, in(base + k));
     uint64_t total;
     block_scan_excl(acc, op, total, s_warp);
     if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
 }
 
 // phase 3: per-tile scan with the carry of the preceding tiles.  EXCL: exclusive (out[i] excludes in[i]).
-// When `out_total` is set and EXCL, out[n] receives the grand total (out has n+1 entries).
-template <class Tin, class Tout, class Op, bool EXCL>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const Tin *in, uint64_t n, const uint64_t *tile_prefix,
-                                                             Tout *out, Op op, int write_total) {
+// The carry is tile_prefix[blockIdx.x] when a scanned prefix array is given; otherwise, when tile_sums is
+// given, the block reduces the sums of the tiles before it itself (small inputs: no middle kernel).
+// When `write_total` is set and EXCL, out[n] receives the grand total (out has n+1 entries).
+template <class Load, class Tout, class Op, bool EXCL>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(Load in, uint64_t n, const uint64_t *tile_prefix,
+                                                             const uint64_t *tile_sums, Tout *out, Op op, int write_total) {
     __shared__ uint64_t s_warp[SCAN_THREADS / 32];
+    uint64_t tile_carry = op.identity();
+    if (tile_prefix) {
+        tile_carry = tile_prefix[blockIdx.x];
+    } else if (tile_sums) {
+        uint64_t part = op.identity();
+        for (uint32_t i = threadIdx.x; i < blockIdx.x; i += SCAN_THREADS) part = op(part, tile_sums[i]);
+        block_scan_excl(part, op, tile_carry, s_warp);
+    }
     uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
     uint64_t v[SCAN_ITEMS];
     uint64_t acc = op.identity();
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
-        v[k] = base + k < n ? (uint64_t)in[base + k] : op.identity();
+        v[k] = base + k < n ? in(base + k) : op.identity();
         acc = op(acc, v[k]);
     }
     uint64_t total;
     uint64_t pre = block_scan_excl(acc, op, total, s_warp);
-    uint64_t carry = op(tile_prefix ? tile_prefix[blockIdx.x] : op.identity(), pre);
+    uint64_t carry = op(tile_carry, pre);
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
         uint64_t inc = op(carry, v[k]);

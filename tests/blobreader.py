@@ -79,7 +79,7 @@ class Blob:
     # ---- Q4 layout
     def q4_code(self, i):
         b, t = divmod(i, 64)
-        return (int(self.q4[b, 4 + (t >> 4)]) >> (2 * (t & 15))) & 3
+        return ((int(self.q4[b, 4 + (t >> 5)]) >> (t & 31)) & 1) | (((int(self.q4[b, 6 + (t >> 5)]) >> (t & 31)) & 1) << 1)
 
     def q4_rank(self, i, c):
         import bisect
@@ -119,7 +119,7 @@ class Blob:
     # ---- WM4 layout: quaternary wavelet matrix
     def w4_code(self, l, i):
         b, t = divmod(i, 64)
-        return (int(self.q4l[l][b, 4 + (t >> 4)]) >> (2 * (t & 15))) & 3
+        return ((int(self.q4l[l][b, 4 + (t >> 5)]) >> (t & 31)) & 1) | (((int(self.q4l[l][b, 6 + (t >> 5)]) >> (t & 31)) & 1) << 1)
 
     def w4_down(self, l, d, pos):
         b, r = divmod(pos, 64)

@@ -508,6 +508,13 @@ def test_search_options_do_not_change_results():
     hoff3, pos3 = index.search_batch(pats).locate()
     assert np.array_equal(hoff, hoff2) and np.array_equal(pos, pos2) and np.array_equal(pos, pos3)
     assert index.last_work()[1] == lf_simple
+    for mode in (1, 2, 0):                                # rows expanded by scans / found by binary search / auto
+        index.set_option("locate_expand", mode)
+        b = index.search_batch(pats)
+        h4, p4 = b.locate()
+        assert np.array_equal(hoff, h4) and np.array_equal(pos, p4), mode
+        h5, p5 = index.search_locate_batch(pats)[1:3]
+        assert np.array_equal(hoff, h5) and np.array_equal(pos, p5), mode
     with pytest.raises(fmx.Error):
         index.set_option("no_such_option", 1)
 

@@ -561,43 +561,61 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (k_search).  Algorithmic bytes = one 32-byte sector per
-    # rank probe the device layout needs: 32 B x 2 bounds x P x executed steps, P = sectors per rank
-    # (L for the binary wavelet matrix, 1 for the quaternary level DNA alphabets get; RLFM adds the
-    # run-start vector and the two select tables).  The same count for the reference's L-level
-    # wavelet matrix is reported beside it.
+    # ---- roofline of the dominant kernel (k_search).
+    # `achieved` follows SURVEY.md 8(d): algorithmic bytes = one 32-byte sector per wavelet-level rank probe of
+    # the REFERENCE's structure -- 32 B x 2 range ends x L levels x executed search iterations (RLFM: 2L + 3
+    # probes per lf_map2) -- divided by the kernel's measured duration.  The device layout needs fewer sectors
+    # (1 per rank for Q4 / SYM) and the k-mer tables memoise the first iterations, so this can exceed the
+    # streaming peak; the same count for the device layout, the DRAM bytes ncu measured (`traffic`) and the
+    # L2-request rate against the measured random-request peak are reported beside it.
     Lw = int(mc).bit_length()
     P = index.sectors_per_rank()
-    per_lf2 = P + (3 if kind == RLFM else 0)
+    ref_per_lf2 = Lw if kind != RLFM else 2 * Lw + 3
+    dev_per_lf2 = P + (3 if kind == RLFM else 0)
     peak, peak_src = measured_peaks()
     ms_search = ms_search_total / args.steps
-    alg_bytes_search = 32.0 * 2 * per_lf2 * search_steps
-    alg_bytes_locate = 32.0 * (per_lf2 * lf_steps + hits)
+    ms_locate = max(ms_locate_total / args.steps, 1e-9)
+    alg_bytes_search = 32.0 * 2 * ref_per_lf2 * search_steps
+    dev_bytes_search = 32.0 * 2 * dev_per_lf2 * search_steps
+    alg_bytes_locate = 32.0 * ((Lw if kind != RLFM else Lw + 3) * lf_steps + hits)
     achieved = alg_bytes_search / (ms_search * 1e-3) / 1e9
-    traffic, traffic_src = ncu_traffic(args.workload, npat)
+    traffic, tsrc = ncu_traffic(args.workload, npat)
     beyond_l2 = index.heap_size() > (400 << 20)
     roofline = {"bound": "hbm", "kernel": "k_search", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes_search, "kernel_ms": ms_search,
-                "sectors_per_lf_map2": per_lf2,
-                "reference_layout_algorithmic_bytes": 32.0 * 2 * (Lw if kind != RLFM else 2 * Lw + 3) * search_steps,
-                "note": ("index larger than L2: HBM bound" if beyond_l2 else
-                         "index fits the 126 MB L2: bound by L2 latency / L1TEX request rate, not HBM (see traffic)"),
+                "definition": "SURVEY.md 8(d): 32 B x 2 range ends x L wavelet levels x executed search iterations "
+                              "(RLFM: 2L+3 probes per lf_map2) / kernel duration (CUDA events on the launch stream)",
+                "reference_sectors_per_lf_map2": ref_per_lf2,
+                "device_layout": {"sectors_per_lf_map2": dev_per_lf2, "bytes_per_launch": dev_bytes_search,
+                                  "achieved": dev_bytes_search / (ms_search * 1e-3) / 1e9,
+                                  "frac": dev_bytes_search / (ms_search * 1e-3) / 1e9 / peak},
+                "note": ("index larger than L2: bound by the rate of DRAM-missing L2 requests (see random_access), "
+                         "not by bandwidth" if beyond_l2 else
+                         "index fits the 126 MB L2: bound by instruction issue / L1TEX request rate, not HBM (see traffic)")
+                        + "; frac > 1 means fewer bytes moved than the reference structure's sector model needs",
                 "executed_search_steps": int(search_steps), "executed_lf_steps": int(lf_steps),
-                "locate_kernel": {"achieved": alg_bytes_locate / (max(ms_locate_total / args.steps, 1e-9) * 1e-3) / 1e9,
-                                  "phase_ms": ms_locate_total / args.steps}}
+                "locate_kernel": {"achieved": alg_bytes_locate / (ms_locate * 1e-3) / 1e9, "phase_ms": ms_locate,
+                                  "frac": alg_bytes_locate / (ms_locate * 1e-3) / 1e9 / peak}}
     if traffic:
         roofline["traffic_frac_of_peak"] = traffic / (ms_search * 1e-3) / 1e9 / peak
-        roofline["traffic_source"] = traffic_src.get("source")
+        roofline["traffic_source"] = tsrc.get("source")
+    gp = None
     if not args.no_gather_peak:
         try:
             gp = fmx.random_gather_peak(local, nbytes=4 << 30, nloads=1 << 28, iters=3)
-            sect = alg_bytes_search / 32.0 / (ms_search * 1e-3)
-            roofline["random_access"] = {"peak_sectors_per_s": gp, "peak_GBps": gp * 32 / 1e9,
-                                         "achieved_sectors_per_s": sect, "frac": sect / gp,
-                                         "how": "independent uniform-random 32 B gathers over a 4 GiB buffer, best of 3"}
         except Exception as ex:  # pragma: no cover
             roofline["random_access"] = {"error": str(ex)}
+    if gp:
+        ra = {"peak_requests_per_s": gp,
+              "how": "independent uniform-random 32 B loads over a 4 GiB buffer, best of 3 (every load is one "
+                     "DRAM-missing L2 request; profiles/r01b_random_access_study.md)"}
+        if tsrc and tsrc.get("k_search", {}).get("l2_read_requests"):
+            req = tsrc["k_search"]["l2_read_requests"] * npat / tsrc["npat"]
+            ra.update({"l2_read_requests_per_launch": req, "achieved_requests_per_s": req / (ms_search * 1e-3),
+                       "frac": req / (ms_search * 1e-3) / gp,
+                       "requests_source": "lts__t_requests_srcunit_tex_op_read.sum of the ncu capture, scaled by batch size"})
+        roofline["random_access"] = ra
 
     # ---- CPU baseline beside it: the oracle port on all host threads, bounded sample; also the parity check
     cpu = None
@@ -648,8 +666,7 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32/u64 integer", "data": "synthetic",
         "config": config_of(args.workload, w, int(text.size), npat, {
-            "index_device_bytes": index.heap_size(), "device_layout": "quaternary (1 sector per rank)" if P == 1 else
-            f"binary wavelet matrix ({P} sectors per rank)",
+            "index_device_bytes": index.heap_size(), "device_layout": index.layout_name(),
             "l2": "flushed between timed iterations (512 MiB memset)",
             "step": "fmx_search_batch_device + fmx_locate_batch_device" + (" replayed as one CUDA graph" if graph is not None else ""),
             "parallelism": f"index replicated x{world}, query batches sharded", "index_build_s": round(build_s, 1)}),

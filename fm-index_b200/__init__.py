@@ -266,6 +266,12 @@ class _Index:
         """32-byte sectors per rank/access probe in this index's device layout (L, or 1 for Q4)."""
         return int(self._L.fmx_index_sectors_per_rank(self._h))
 
+    def layout_name(self):
+        """which device layout the builder chose (fmx_layout.h)"""
+        return ["binary wavelet matrix (L sectors per rank)", "Q4: one quaternary level (1 sector per rank)",
+                "WM4: quaternary wavelet matrix (ceil(L/2) sectors per rank)",
+                "SYM: one bit vector per symbol (1 sector per rank)"][int(self._L.fmx_index_layout(self._h))]
+
     def kmer_k(self, big=False):
         """characters memoised by the small / large k-mer table (0 = none)"""
         return int(self._L.fmx_index_kmer_k(self._h, int(big)))

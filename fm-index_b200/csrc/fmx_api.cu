@@ -380,6 +380,7 @@ int fmx_index_has_locate(const fmx_index *idx) { return idx ? (int)idx->hdr.has_
 int fmx_index_device(const fmx_index *idx) { return idx ? idx->device : -1; }
 uint32_t fmx_index_wavelet_levels(const fmx_index *idx) { return idx ? idx->hdr.levels : 0; }
 uint32_t fmx_index_sample_level(const fmx_index *idx) { return idx ? idx->hdr.sa_level : 0; }
+uint32_t fmx_index_layout(const fmx_index *idx) { return idx ? idx->hdr.layout : 0; }
 uint32_t fmx_index_sectors_per_rank(const fmx_index *idx) {
     if (!idx) return 0;
     if (idx->hdr.layout == FMX_LAYOUT_QUAT || idx->hdr.layout == FMX_LAYOUT_SYM) return 1u;

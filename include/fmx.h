@@ -103,8 +103,11 @@ int fmx_build_suffix_array_device(const void *text, uint64_t n, uint32_t char_wi
  * large table with that many MiB of HBM; default = twice the index size, FMX_KMER_BUDGET_MB at
  * build time), "bucket" -1|0|1 (visit the batch in k-mer bucket order: auto / never / always),
  * "l2_fetch_granularity" 32|64|128, "persist_blocks_per_sm" 1..32, "pipeline_chunk" (patterns per chunk of
- * fmx_search_locate_batch's copy/compute pipeline, 0 = automatic).  The environment variable
- * FMX_FORCE_WAVELET=1 makes construction keep the binary wavelet matrix for small alphabets. */
+ * fmx_search_locate_batch's copy/compute pipeline, 0 = automatic), "locate_refill" 0|1 (per-lane refill
+ * locate kernel), "locate_expand" 0|1|2 (hit rows: auto / always expanded by scans / always found by
+ * binary search inside the locate kernel).  Environment at construction time: FMX_FORCE_WAVELET=1
+ * keeps the binary wavelet matrix; FMX_SYM_BUDGET_MB caps the per-symbol bit-vector layout (default
+ * 49152; 0 = use the quaternary wavelet matrix instead). */
 int fmx_index_set_option(fmx_index *idx, const char *key, int64_t value);
 
 /* SearchIndex::len (frontend.rs:35-39), heap_size (:41-44, here: device bytes),
@@ -118,8 +121,11 @@ int fmx_index_device(const fmx_index *idx);
 uint32_t fmx_index_wavelet_levels(const fmx_index *idx); /* Text::max_bits, text.rs:61-63 */
 uint32_t fmx_index_sample_level(const fmx_index *idx);
 /* 32-byte sectors one rank/access probe of the BWT touches in this index's device layout:
- * L for the binary wavelet matrix, 1 for the quaternary level used when max_character <= 4. */
+ * 1 for Q4 (max_character <= 4) and SYM (per-symbol bit vectors), ceil(L/2) for the quaternary
+ * wavelet matrix, L for the binary one. */
 uint32_t fmx_index_sectors_per_rank(const fmx_index *idx);
+/* the device layout the builder chose: 0 binary wavelet matrix, 1 Q4, 2 WM4, 3 SYM (csrc/fmx_layout.h) */
+uint32_t fmx_index_layout(const fmx_index *idx);
 /* characters memoised by the small (big = 0) / large (big = 1) k-mer table of fresh searches; 0 = none */
 uint32_t fmx_index_kmer_k(const fmx_index *idx, int big);
 

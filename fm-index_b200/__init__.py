@@ -222,6 +222,19 @@ class _Index:
         t = int(total.value)
         return (batch, hit_off, pos[:t].copy(), pid[:t].copy()) if piece_ids else (batch, hit_off, pos[:t].copy())
 
+    def locate_page(self, s, e, first_hit, nhits, piece_ids=False):
+        """One page of the hit list of the ranges (s, e): hits [first_hit, first_hit + nhits) in the reference's
+        iteration order (fmx_locate_page).  -> (positions[, piece_ids], total_hits)"""
+        s = np.ascontiguousarray(s, dtype=np.uint64)
+        e = np.ascontiguousarray(e, dtype=np.uint64)
+        pos = np.zeros(max(int(nhits), 1), dtype=np.uint64)
+        pid = np.zeros(max(int(nhits), 1), dtype=np.uint64) if piece_ids else None
+        total = C.c_uint64(0)
+        _check(self._L.fmx_locate_page(self._h, _ptr(s), _ptr(e), s.size, int(first_hit), int(nhits), _ptr(pos), _ptr(pid),
+                                       C.byref(total)))
+        got = max(0, min(int(nhits), int(total.value) - int(first_hit)))
+        return (pos[:got], pid[:got], int(total.value)) if piece_ids else (pos[:got], int(total.value))
+
     def locate_batch(self, s, e, prefix_only=False, piece_ids=False):
         s = np.ascontiguousarray(s, dtype=np.uint64)
         e = np.ascontiguousarray(e, dtype=np.uint64)
@@ -458,6 +471,20 @@ class SearchBatch:
         """-> (hit_off[npat+1], positions[, piece_ids]); matches of pattern p are
         positions[hit_off[p]:hit_off[p+1]] in the reference's iteration order."""
         return self._index.locate_batch(self.s, self.e, self._mode in (SEARCH_PREFIX, SEARCH_EXACT), piece_ids)
+
+    def iter_locate_pages(self, page_hits):
+        """Lazily yields (first_hit, positions) pages of at most `page_hits` matches, in the reference's
+        iteration order: bounded memory for match sets too large to hold at once."""
+        if self._mode in (SEARCH_PREFIX, SEARCH_EXACT):
+            raise Error("paged locate supports the unfiltered modes (search, search_suffix)")
+        first = 0
+        while True:
+            pos, total = self._index.locate_page(self.s, self.e, first, page_hits)
+            if pos.size:
+                yield first, pos
+            first += int(page_hits)
+            if first >= total:
+                return
 
 
 def suffix_array(text) -> np.ndarray:

@@ -43,6 +43,8 @@ SIGNATURES = {
     "fmx_search_locate_batch": (_int, [_vp, _int, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _u64, _u64p]),
     "fmx_locate_count_device": (_int, [_vp, _int, _vp, _vp, _u64, _vp, _u64p, _vp]),
     "fmx_locate_fill_device": (_int, [_vp, _int, _vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp]),
+    "fmx_locate_page": (_int, [_vp, _vp, _vp, _u64, _u64, _u64, _vp, _vp, _u64p]),
+    "fmx_locate_page_device": (_int, [_vp, _vp, _vp, _u64, _u64, _u64, _vp, _vp, _vp]),
     "fmx_locate_batch_device": (_int, [_vp, _int, _vp, _vp, _u64, _vp, _vp, _vp, _u64, _vp]),
     "fmx_extract_batch": (_int, [_vp, _vp, _u64, _u32, _int, _vp, _vp]),
     "fmx_extract_batch_device": (_int, [_vp, _vp, _u64, _u32, _int, _vp, _vp, _vp]),

@@ -98,6 +98,7 @@ struct fmx_index {
     int opt_persistent = 0;  // 1: persistent refill search kernels instead of one pattern per thread
     int opt_kmer = 1;
     uint64_t opt_pipeline_chunk = 0;  // patterns per pipeline chunk (0 = automatic)
+    int opt_locate_ranges = -1;       // -1 auto (RLFM with >= 8 matches per pattern), 0 never, 1 always: k_locate_ranges
     int opt_locate_expand = 0;        // 0 auto, 1 always expand the rows first, 2 always binary-search in k_locate
     int opt_locate_refill = 0;        // 1: per-lane refill k_locate (lost the A/B: it breaks the coalescing of adjacent rows)
     int opt_bucket = 0;               // 1: visit the batch in k-mer bucket order (lost the A/B, kept for experiments); -1 auto
@@ -355,6 +356,7 @@ int fmx_index_set_option(fmx_index *idx, const char *key, int64_t value) {
     }
     else if (k == "locate_refill") idx->opt_locate_refill = value != 0;
     else if (k == "locate_expand") idx->opt_locate_expand = (int)value;
+    else if (k == "locate_ranges") idx->opt_locate_ranges = value < 0 ? -1 : (value != 0);
     else if (k == "bucket") idx->opt_bucket = value < 0 ? -1 : (value != 0);
     else if (k == "pipeline_chunk") idx->opt_pipeline_chunk = value > 0 ? (uint64_t)value : 0;
     else if (k == "l2_fetch_granularity") {
@@ -742,6 +744,8 @@ struct RowSource {
     const uint64_t *hoff = nullptr;
     const uint64_t *s = nullptr;
     uint64_t npat = 0;
+    uint64_t first = 0;
+    bool ranges = false;  // walk sub-ranges (k_locate_ranges) instead of rows
 };
 
 // small batches skip the row expansion (memset + mark + 2-3 scan launches + expand): k_locate finds its row
@@ -750,6 +754,13 @@ static bool expand_by_search(const fmx_index *idx, uint64_t total) {
     if (idx->opt_locate_expand == 1) return false;
     if (idx->opt_locate_expand == 2) return true;
     return total <= (1ull << 22);
+}
+
+// many matches per pattern (repetitive texts): walk whole sub-ranges instead of single rows (k_locate_ranges)
+static bool locate_by_ranges(const fmx_index *idx, uint64_t total, uint64_t npat) {
+    if (idx->hdr.sa_level > 6 || idx->opt_locate_ranges == 0 || idx->opt_locate_refill) return false;
+    if (idx->opt_locate_ranges == 1) return true;
+    return idx->hdr.kind == FMX_KIND_RLFM && npat > 0 && total >= 8 * npat;
 }
 
 
@@ -781,11 +792,12 @@ static int locate_rows(const fmx_index *idx, DevBuf *buf, int prefix_only, const
         *hits_out = 0;
         return 0;
     }
-    if (!prefix_only && expand_by_search(idx, total)) {
+    if (!prefix_only && (locate_by_ranges(idx, total, npat) || expand_by_search(idx, total))) {
         *hits_out = total;
         rows_out->hoff = d_off;
         rows_out->s = d_s;
         rows_out->npat = npat;
+        rows_out->ranges = locate_by_ranges(idx, total, npat);
         return 0;
     }
     if ((rc = buf[B_OWNER].ensure(total * 4))) return rc;
@@ -852,11 +864,21 @@ static int locate_fill(const fmx_index *idx, const RowSource &src, uint64_t tota
     a.hoff = src.hoff;
     a.s = src.s;
     a.npat = src.npat;
+    a.first = src.first;
     a.total = total;
     a.total_dev = total_dev;
     a.positions = d_pos;
     a.piece_ids = d_pid;
     a.work = count_work ? idx->d_work : nullptr;
+    if (src.ranges && !src.rows) {
+        const uint64_t threads = (total + LOCATE_GROUP - 1) / LOCATE_GROUP;
+        dispatch(idx, [&](auto K, auto LY) {
+            k_locate_ranges<K(), LY()><<<(unsigned)((threads + LOCATE_RANGE_THREADS - 1) / LOCATE_RANGE_THREADS),
+                                         LOCATE_RANGE_THREADS, 0, st>>>(idx->dev, a);
+        });
+        LAUNCH_CHECK();
+        return 0;
+    }
     if (!idx->opt_locate_refill) {
         uint64_t blocks = (total + 255) / 256;
         uint64_t cap = (uint64_t)idx->sms * 8 * 8;
@@ -910,10 +932,11 @@ extern "C" int fmx_locate_fill_device(const fmx_index *idx, int prefix_only, con
     (void)d_hit_off;
     // the rows prepared by the matching fmx_locate_count_device call are still in scratch
     RowSource rows;  // what fmx_locate_count_device left behind for these ranges
-    if (!prefix_only && expand_by_search(idx, total_hits)) {
+    if (!prefix_only && (locate_by_ranges(idx, total_hits, npat) || expand_by_search(idx, total_hits))) {
         rows.hoff = d_hit_off;
         rows.s = d_s;
         rows.npat = npat;
+        rows.ranges = locate_by_ranges(idx, total_hits, npat);
     } else {
         rows.rows = prefix_only ? idx->buf[B_ROWS2].as<uint32_t>() : idx->buf[B_ROWS].as<uint32_t>();
     }
@@ -942,11 +965,12 @@ extern "C" int fmx_locate_batch_device(const fmx_index *idx, int prefix_only, co
     if (capacity == 0 || npat == 0) return FMX_OK;
     if (capacity >= 0xFFFFFFFFull * 4) return fail(FMX_ERR_UNSUPPORTED, "capacity too large");
     const uint64_t *d_total0 = d_hit_off + npat;
-    if (expand_by_search(idx, capacity)) {
+    if (locate_by_ranges(idx, capacity, npat) || expand_by_search(idx, capacity)) {
         RowSource src;
         src.hoff = d_hit_off;
         src.s = d_s;
         src.npat = npat;
+        src.ranges = locate_by_ranges(idx, capacity, npat);
         return locate_fill(idx, src, capacity, d_positions, d_piece_ids, st, true, d_total0);
     }
     if ((rc = buf[B_OWNER].ensure(capacity * 4))) return rc;
@@ -963,6 +987,73 @@ extern "C" int fmx_locate_batch_device(const fmx_index *idx, int prefix_only, co
     RowSource src;
     src.rows = d_rows;
     return locate_fill(idx, src, capacity, d_positions, d_piece_ids, st, true, d_total);
+}
+
+// One page of the hit list: hits [first_hit, first_hit + nhits) of the CSR that fmx_locate_count_device
+// (prefix_only == 0) left in d_hit_off, written to d_positions[0 .. nhits).  Bounded-memory iteration over
+// huge match sets (lazy iter_matches, wrapper.rs:137-139, 203-217): asynchronous, no scratch.
+extern "C" int fmx_locate_page_device(const fmx_index *idx, const uint64_t *d_s, const uint64_t *d_hit_off, uint64_t npat,
+                                      uint64_t first_hit, uint64_t nhits, uint64_t *d_positions, uint64_t *d_piece_ids,
+                                      void *stream) {
+    if (!idx || !d_s || !d_hit_off || (!d_positions && !d_piece_ids)) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    int rc = locate_args_ok(idx, d_piece_ids != nullptr);
+    if (rc) return rc;
+    if (nhits == 0 || npat == 0) return FMX_OK;
+    CUDA_TRY(cudaSetDevice(idx->device));
+    RowSource src;
+    src.hoff = d_hit_off;
+    src.s = d_s;
+    src.npat = npat;
+    src.first = first_hit;
+    src.ranges = locate_by_ranges(idx, nhits, npat);
+    return locate_fill(idx, src, nhits, d_positions, d_piece_ids, pick_stream(idx, stream));
+}
+
+// host-buffer form: SA ranges in, one page of positions out; *total_hits = size of the whole hit list
+extern "C" int fmx_locate_page(const fmx_index *idx, const uint64_t *s, const uint64_t *e, uint64_t npat, uint64_t first_hit,
+                               uint64_t nhits, uint64_t *positions, uint64_t *piece_ids, uint64_t *total_hits) {
+    if (!idx || !total_hits || (!s && npat) || (!e && npat)) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    int rc = locate_args_ok(idx, piece_ids != nullptr);
+    if (rc) return rc;
+    *total_hits = 0;
+    if (npat == 0) return FMX_OK;
+    std::lock_guard<std::mutex> lk(idx->mu);
+    CUDA_TRY(cudaSetDevice(idx->device));
+    cudaStream_t st = idx->stream;
+    if ((rc = idx->buf[B_S].ensure(npat * 8 + 8))) return rc;
+    if ((rc = idx->buf[B_E].ensure(npat * 8 + 8))) return rc;
+    if ((rc = idx->buf[B_OFF].ensure((npat + 1) * 8))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(idx->buf[B_S].p, s, npat * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(idx->buf[B_E].p, e, npat * 8, cudaMemcpyHostToDevice, st));
+    uint64_t *d_hoff = idx->buf[B_OFF].as<uint64_t>();
+    if ((rc = locate_counts(idx, idx->buf, idx->buf[B_S].as<uint64_t>(), idx->buf[B_E].as<uint64_t>(), npat, d_hoff, st))) return rc;
+    uint64_t total = 0;
+    CUDA_TRY(cudaMemcpyAsync(&total, d_hoff + npat, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *total_hits = total;
+    if (first_hit >= total || nhits == 0) return FMX_OK;
+    if (nhits > total - first_hit) nhits = total - first_hit;
+    uint64_t *d_pos = nullptr, *d_pid = nullptr;
+    if (positions) {
+        if ((rc = idx->buf[B_POS].ensure(nhits * 8))) return rc;
+        d_pos = idx->buf[B_POS].as<uint64_t>();
+    }
+    if (piece_ids) {
+        if ((rc = idx->buf[B_PID].ensure(nhits * 8))) return rc;
+        d_pid = idx->buf[B_PID].as<uint64_t>();
+    }
+    if (!d_pos && !d_pid) return FMX_OK;
+    RowSource src;
+    src.hoff = d_hoff;
+    src.s = idx->buf[B_S].as<uint64_t>();
+    src.npat = npat;
+    src.first = first_hit;
+    src.ranges = locate_by_ranges(idx, total, npat);
+    if ((rc = locate_fill(idx, src, nhits, d_pos, d_pid, st))) return rc;
+    if (positions) CUDA_TRY(cudaMemcpyAsync(positions, d_pos, nhits * 8, cudaMemcpyDeviceToHost, st));
+    if (piece_ids) CUDA_TRY(cudaMemcpyAsync(piece_ids, d_pid, nhits * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return FMX_OK;
 }
 
 extern "C" int fmx_locate_batch(const fmx_index *idx, int prefix_only, const uint64_t *s, const uint64_t *e, uint64_t npat,

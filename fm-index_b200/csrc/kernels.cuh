@@ -1078,6 +1078,7 @@ struct LocateArgs {
     const uint64_t *hoff;       // (rows == NULL) npat + 1 hit offsets
     const uint64_t *s;          // (rows == NULL) SA range starts
     uint64_t npat;
+    uint64_t first;             // (rows == NULL) index of the first hit to produce: output slot h holds hit first + h
     uint64_t total;             // number of hits, or the capacity when total_dev is given
     const uint64_t *total_dev;  // nullable: the real number of hits, on the device
     uint64_t *positions;  // nullable
@@ -1091,6 +1092,7 @@ struct LocateArgs {
 // search of the hit offsets (neighbouring hits take the same path, so the probes hit L1)
 __device__ __forceinline__ uint32_t locate_row(const LocateArgs &a, uint64_t h) {
     if (a.rows) return a.rows[h];
+    h += a.first;
     uint64_t lo = 0, hi = a.npat;  // last p with hoff[p] <= h
     while (hi - lo > 1) {
         uint64_t mid = lo + ((hi - lo) >> 1);
@@ -1212,6 +1214,132 @@ __global__ void __launch_bounds__(256) k_locate(const __grid_constant__ FmxDev i
     if (a.work) {
         for (int o = 16; o > 0; o >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, o);
         if (lane == 0 && steps) atomicAdd(a.work + 1, steps);
+    }
+}
+
+// get_sa for whole SA ranges (option "locate_ranges"; automatic when patterns have many matches each).
+// The rows of one pattern are ADJACENT (s .. e-1).  While all rows of a sub-range [a, a+len) carry the same
+// BWT symbol c -- the normal case on repetitive texts, which is what RLFMIndex is for -- LF maps them to
+// the adjacent rows lf_map2(c, a) .. +len, so ONE lf_map2 pair steps the whole sub-range: the check is
+// lf_map2(c, a + len) - lf_map2(c, a) == len.  At every step the members whose current row is sampled
+// (row % 2^level == 0) take their position sa[row >> level] + t and leave; a sub-range that is not uniform
+// is split in halves.  Size-1 sub-ranges are the reference's per-row walk, so the result (and the count of
+// executed LF steps) is identical by construction; the per-row kernel above walks 64 copies of the same
+// path, this one walks it once.  One thread handles LOCATE_GROUP consecutive hits of the hit list.
+// Measured on BASELINE config 3 (6.1e8 hits, 64 copies): 31.0 ms against 35.1 ms for the per-row kernel --
+// it executes ~10x fewer instructions but its loads and stores are one memory request per thread, where
+// the per-row kernel's 32 adjacent rows share theirs (1.25 requests per hit), so it trades the issue
+// bound for the request-rate bound.  Staging the positions in shared memory for a coalesced store was
+// slower still (53 ms: occupancy).  Automatic for RLFM indexes only (a user picks those for repetitive
+// texts); on non-repetitive texts every sub-range splits at once and this degenerates to row walks
+// with overhead.
+#define LOCATE_GROUP 64
+#define LOCATE_STACK 8
+#define LOCATE_RANGE_THREADS 256
+template <int KIND, int LAYOUT>
+__global__ void __launch_bounds__(LOCATE_RANGE_THREADS) k_locate_ranges(const __grid_constant__ FmxDev ix,
+                                                                        const __grid_constant__ LocateArgs a) {
+    __shared__ Tabs<LAYOUT> tb;
+    load_tables<LAYOUT>(ix, tb);
+    unsigned long long steps = 0;
+    uint64_t total = a.total;
+    if (a.total_dev && *a.total_dev < total) total = *a.total_dev;
+    const uint32_t M = 1u << ix.sa_level;  // host guarantees sa_level <= 6
+    uint64_t cm = 0;                       // bit j set for j = 0, M, 2M, .. < 64
+    for (uint32_t j = 0; j < 64; j += M) cm |= 1ull << j;
+    const uint64_t H0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * LOCATE_GROUP;
+    if (H0 < total) {
+        const uint64_t H1 = H0 + LOCATE_GROUP < total ? H0 + LOCATE_GROUP : total;
+        uint64_t p = 0;
+        {
+            uint64_t lo = 0, hi = a.npat;  // last p with hoff[p] <= first + H0
+            while (hi - lo > 1) {
+                uint64_t mid = lo + ((hi - lo) >> 1);
+                if (__ldg(a.hoff + mid) <= a.first + H0) lo = mid; else hi = mid;
+            }
+            p = lo;
+        }
+        uint64_t h = H0;
+        while (h < H1) {
+            const uint64_t g = a.first + h;  // global hit number
+            while (__ldg(a.hoff + p + 1) <= g) p++;
+            const uint64_t pend = __ldg(a.hoff + p + 1) - a.first;  // this pattern's hits end here (local numbering)
+            const uint64_t seg_end = pend < H1 ? pend : H1;
+            // sub-range stack: rows [row, row + 64 - clz(pending)), output slot of member 0, steps so far, unresolved members
+            uint32_t st_row[LOCATE_STACK], st_t[LOCATE_STACK];
+            uint64_t st_out[LOCATE_STACK], st_pend[LOCATE_STACK];
+            int sp = 0;
+            {
+                const uint32_t len = (uint32_t)(seg_end - h);
+                st_row[0] = (uint32_t)(__ldg(a.s + p) + (g - __ldg(a.hoff + p)));
+                st_out[0] = h;
+                st_t[0] = 0;
+                st_pend[0] = len >= 64 ? ~0ull : ((1ull << len) - 1ull);
+                sp = 1;
+            }
+            while (sp > 0) {
+                sp--;
+                uint32_t row = st_row[sp], t = st_t[sp];
+                uint64_t out = st_out[sp], pending = st_pend[sp];
+                for (;;) {
+                    // members on sampled rows leave with their position
+                    const uint32_t r = (0u - row) & (M - 1u);
+                    uint64_t hit = r < 64 ? (pending & (cm << r)) : 0ull;
+                    pending &= ~hit;
+                    while (hit) {
+                        const uint32_t j = (uint32_t)__ffsll((long long)hit) - 1u;
+                        hit &= hit - 1;
+                        uint64_t v = (uint64_t)__ldg(ix.sa + ((row + j) >> ix.sa_level)) + t;
+                        if (v >= ix.n) v -= ix.n;  // (sa + steps) % n; both terms are < n
+                        if (a.positions) a.positions[out + j] = v;
+                        if (KIND == FMX_KIND_MULTI_ && a.piece_ids) {
+                            uint32_t lo = 0, hi = ix.ndoc;  // number of piece ends strictly before v
+                            while (lo < hi) {
+                                uint32_t m = lo + ((hi - lo) >> 1);
+                                if (__ldg(ix.piece_end + m) < v) lo = m + 1; else hi = m;
+                            }
+                            a.piece_ids[out + j] = lo;
+                        }
+                        steps += t;
+                    }
+                    if (!pending) break;
+                    // drop resolved members at both ends
+                    const uint32_t tz = (uint32_t)__ffsll((long long)pending) - 1u;
+                    pending >>= tz;
+                    row += tz;
+                    out += tz;
+                    const uint32_t len = 64u - (uint32_t)__clzll((long long)pending);
+                    uint32_t sym;
+                    const uint32_t nrow = lf_step<KIND, LAYOUT>(ix, tb, row, sym);
+                    bool uniform = len == 1;
+                    if (!uniform && !(KIND == FMX_KIND_MULTI_ && sym == 0))
+                        uniform = lf_map2_dev<KIND, LAYOUT>(ix, tb, sym, row + len) - nrow == len;
+                    if (uniform) {
+                        row = nrow;
+                        t++;
+                        continue;
+                    }
+                    // split in halves; the upper half waits on the stack (it cannot overflow: every split
+                    // halves the length, 64 -> 1 in 6 splits, and a popped entry frees its slot first)
+                    const uint32_t half = len >> 1;
+                    const uint64_t up = pending >> half;
+                    if (up) {
+                        st_row[sp] = row + half;
+                        st_out[sp] = out + half;
+                        st_t[sp] = t;
+                        st_pend[sp] = up;
+                        sp++;
+                    }
+                    pending &= (1ull << half) - 1ull;
+                    if (!pending) break;
+                }
+            }
+            h = seg_end;
+        }
+    }
+    if (a.work) {
+        for (int o = 16; o > 0; o >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, o);
+        if ((threadIdx.x & 31) == 0 && steps) atomicAdd(a.work + 1, steps);
     }
 }
 

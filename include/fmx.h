@@ -105,7 +105,8 @@ int fmx_build_suffix_array_device(const void *text, uint64_t n, uint32_t char_wi
  * "l2_fetch_granularity" 32|64|128, "persist_blocks_per_sm" 1..32, "pipeline_chunk" (patterns per chunk of
  * fmx_search_locate_batch's copy/compute pipeline, 0 = automatic), "locate_refill" 0|1 (per-lane refill
  * locate kernel), "locate_expand" 0|1|2 (hit rows: auto / always expanded by scans / always found by
- * binary search inside the locate kernel).  Environment at construction time: FMX_FORCE_WAVELET=1
+ * binary search inside the locate kernel), "locate_ranges" -1|0|1 (walk whole SA sub-ranges instead of
+ * single rows: auto = RLFM indexes whose patterns average >= 8 matches / never / always).  Environment at construction time: FMX_FORCE_WAVELET=1
  * keeps the binary wavelet matrix; FMX_SYM_BUDGET_MB caps the per-symbol bit-vector layout (default
  * 49152; 0 = use the quaternary wavelet matrix instead). */
 int fmx_index_set_option(fmx_index *idx, const char *key, int64_t value);
@@ -182,6 +183,19 @@ int fmx_locate_fill_device(const fmx_index *idx, int prefix_only, const uint64_t
                            const uint64_t *d_e, uint64_t npat, const uint64_t *d_hit_off,
                            uint64_t total_hits, uint64_t *d_positions, uint64_t *d_piece_ids,
                            void *stream);
+
+/* Paged hit list -- the bounded-memory form of the lazy iter_matches (wrapper.rs:137-139, 203-217)
+ * for match sets too large to hold at once (BASELINE config 3: ~6e8 hits).  Hits are numbered in the
+ * reference's iteration order (pattern by pattern, rows ascending); a page is hits
+ * [first_hit, first_hit + nhits).  Unfiltered modes only (search / search_suffix).
+ * Host form: SA ranges in, one page out (fewer if the list ends), *total_hits = size of the whole list.
+ * Device form: d_hit_off is what fmx_locate_count_device(prefix_only = 0) produced; asynchronous. */
+int fmx_locate_page(const fmx_index *idx, const uint64_t *s, const uint64_t *e, uint64_t npat,
+                    uint64_t first_hit, uint64_t nhits, uint64_t *positions, uint64_t *piece_ids,
+                    uint64_t *total_hits);
+int fmx_locate_page_device(const fmx_index *idx, const uint64_t *d_s, const uint64_t *d_hit_off,
+                           uint64_t npat, uint64_t first_hit, uint64_t nhits, uint64_t *d_positions,
+                           uint64_t *d_piece_ids, void *stream);
 
 /* Fully asynchronous form (no host synchronisation, CUDA-graph capturable when prefix_only == 0):
  * launches are sized by `capacity` (entries of d_positions / d_piece_ids); the real number of hits

@@ -385,6 +385,65 @@ def test_byte_alphabet_ragged():
     assert np.array_equal(hoff, ooff) and np.array_equal(pos, opos)
 
 
+@pytest.mark.parametrize("kind", [orc.FM, orc.RLFM, orc.MULTI])
+@pytest.mark.parametrize("level", [0, 2, 5])
+def test_range_walk_locate_on_repetitive_text(kind, level):
+    """k_locate_ranges (whole SA sub-ranges stepped by one lf_map2 pair while their BWT symbols agree) against
+    the oracle's per-row walks: positions in the reference's order, piece ids, and the executed LF steps"""
+    rng = np.random.default_rng(900 + kind + level)
+    base = rng.integers(1, 5, 3000, dtype=np.uint8)
+    copies = []
+    for c in range(40):                                    # 40 mutated copies: every 12-mer has ~40 matches
+        x = base.copy()
+        mut = rng.random(x.size) < 0.01
+        x[mut] = rng.integers(1, 5, int(mut.sum()), dtype=np.uint8)
+        copies.append(x)
+        if kind == orc.MULTI:
+            copies.append(np.zeros(1, dtype=np.uint8))
+    text = np.concatenate(copies + ([] if kind == orc.MULTI else [np.zeros(1, dtype=np.uint8)]))
+    index = KINDS[kind][1].new(fmx.Text.with_max_character(text, 4), level)
+    oracle = orc.OracleIndex(text, kind, level=level, max_character=4)
+    starts = rng.integers(0, base.size - 12, 300)
+    pats = [bytes(base[p:p + int(m)]) for p, m in zip(starts, rng.integers(1, 13, 300))] + [b"", bytes([3])]
+    flat, off = orc.pack_patterns(pats)
+    s, e = oracle.search_batch(flat, off)
+    want = oracle.locate_batch(s, e, want_piece_ids=kind == orc.MULTI)
+    for mode in (1, 0):
+        index.set_option("locate_ranges", mode)
+        b = index.search_batch(pats)
+        got = b.locate(piece_ids=kind == orc.MULTI)
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), mode
+        if kind == orc.MULTI:
+            assert np.array_equal(got[2], want[2])
+        if mode == 1:
+            lf_ranges = index.last_work()[1]
+        else:
+            assert index.last_work()[1] == lf_ranges
+        fused = index.search_locate_batch(pats, capacity=int(want[0][-1]) + 8)
+        assert np.array_equal(fused[1], want[0]) and np.array_equal(fused[2], want[1])
+        page, total = index.locate_page(b.s, b.e, 1000, 5000)
+        assert total == int(want[0][-1]) and np.array_equal(page, want[1][1000:6000])
+
+
+def test_paged_locate_equals_full_locate():
+    """fmx_locate_page: the hit list in pages (bounded memory) equals the one-shot list, order included"""
+    text = dna(200_000, 55)
+    index = fmx.FMIndexMultiPiecesWithLocate.new(fmx.Text.with_max_character(text, 4), 2)
+    pats = [bytes([1]), bytes([2, 3]), bytes([4, 4, 1]), bytes([1, 2, 3, 4, 1, 2, 3]), b""]
+    b = index.search_batch(pats)
+    hoff, pos, pid = b.locate(piece_ids=True)
+    total = int(hoff[-1])
+    assert total > 250_000
+    got = np.concatenate([p for _, p in b.iter_locate_pages(30_011)])
+    assert np.array_equal(got, pos)
+    ppos, ppid, t = index.locate_page(b.s, b.e, 123_456, 1000, piece_ids=True)
+    assert t == total and np.array_equal(ppos, pos[123_456:124_456]) and np.array_equal(ppid, pid[123_456:124_456])
+    tail, t = index.locate_page(b.s, b.e, total - 5, 100)
+    assert np.array_equal(tail, pos[-5:])
+    none, t = index.locate_page(b.s, b.e, total + 7, 100)
+    assert none.size == 0 and t == total
+
+
 def test_huge_range_locate():
     """A pattern matching a large share of the text: one pattern, many hits (load balance path)."""
     text = dna(300_000, 77)
@@ -515,6 +574,11 @@ def test_search_options_do_not_change_results():
         assert np.array_equal(hoff, h4) and np.array_equal(pos, p4), mode
         h5, p5 = index.search_locate_batch(pats)[1:3]
         assert np.array_equal(hoff, h5) and np.array_equal(pos, p5), mode
+    for mode in (1, 0, -1):                               # sub-range walks instead of row walks / rows / auto
+        index.set_option("locate_ranges", mode)
+        h6, p6 = index.search_batch(pats).locate()
+        assert np.array_equal(hoff, h6) and np.array_equal(pos, p6), mode
+        assert index.last_work()[1] == lf_simple
     with pytest.raises(fmx.Error):
         index.set_option("no_such_option", 1)
 

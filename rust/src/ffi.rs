@@ -31,6 +31,9 @@ extern "C" {
                             npat: u64, init_s: *const u64, init_e: *const u64, out_s: *mut u64, out_e: *mut u64) -> c_int;
     pub fn fmx_locate_batch(idx: *const fmx_index, prefix_only: c_int, s: *const u64, e: *const u64, npat: u64,
                             hit_off: *mut u64, positions: *mut *mut u64, piece_ids: *mut *mut u64) -> c_int;
+    // one page of the hit list: the bounded-memory form of the lazy iter_matches (wrapper.rs:137-139, 203-217)
+    pub fn fmx_locate_page(idx: *const fmx_index, s: *const u64, e: *const u64, npat: u64, first_hit: u64, nhits: u64,
+                           positions: *mut u64, piece_ids: *mut u64, total_hits: *mut u64) -> c_int;
     pub fn fmx_search_locate_batch(idx: *const fmx_index, mode: c_int, pat: *const u8, pat_off: *const u64,
                                    fixed_len: u64, npat: u64, out_s: *mut u64, out_e: *mut u64, hit_off: *mut u64,
                                    positions: *mut u64, piece_ids: *mut u64, capacity: u64, total_hits: *mut u64) -> c_int;

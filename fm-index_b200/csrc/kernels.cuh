@@ -745,20 +745,32 @@ __device__ __forceinline__ void pattern_span(const SearchArgs &a, uint64_t p, ui
 // ~20 % of the L1TEX wavefronts of k_search and, once index blocks had evicted the pattern lines from
 // L1, extra L2 requests: profiles/r01b_target_ncu.txt)
 struct PatReader {
+    const uint8_t *q;
     const uint32_t *words;  // the aligned word holding the pattern's first byte
     uint32_t off;           // byte offset of the pattern inside that word
+    uint32_t len;
     uint32_t cur = 0xFFFFFFFFu, w = 0;
-    __device__ __forceinline__ explicit PatReader(const uint8_t *q) {
-        const uintptr_t a = reinterpret_cast<uintptr_t>(q);
+    __device__ __forceinline__ PatReader(const uint8_t *q_, uint32_t len_) : q(q_), len(len_) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(q_);
         words = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
         off = (uint32_t)(a & 3u);
     }
-    // character k of the pattern
+    // character k of the pattern, k < len
     __device__ __forceinline__ uint32_t get(uint32_t k) {
         const uint32_t idx = k + off, wi = idx >> 2;
         if (wi != cur) {
             cur = wi;
-            w = __ldg(words + wi);
+            const uint32_t first = wi << 2;  // the word covers pattern bytes [first - off, first - off + 4)
+            if (first >= off && first + 4u <= off + len) {
+                w = __ldg(words + wi);
+            } else {  // a word that sticks out of the pattern is never read as a whole: no byte outside the
+                      // caller's buffer is touched, whatever its alignment and size
+                w = 0;
+                for (uint32_t b = 0; b < 4; b++) {
+                    const uint32_t pi = first + b;
+                    if (pi >= off && pi < off + len) w |= (uint32_t)__ldg(q + (pi - off)) << (8u * b);
+                }
+            }
         }
         return (w >> (8u * (idx & 3u))) & 0xFFu;
     }
@@ -769,7 +781,7 @@ struct PatReader {
 __device__ __forceinline__ bool kmer_index(const uint8_t *q, uint32_t len, uint32_t K, uint32_t maxc, uint32_t &idx) {
     uint32_t v = 0;
     bool valid = true;
-    PatReader pr(q);
+    PatReader pr(q, len);
     for (uint32_t j = 0; j < K; j++) {
         uint32_t c = pr.get(len - K + j);
         valid = valid && (c - 1u) < maxc;
@@ -831,8 +843,8 @@ __global__ void __launch_bounds__(256) k_search(const __grid_constant__ FmxDev i
         uint32_t e = a.init_e ? (uint32_t)a.init_e[p] : a.e0;
         const uint8_t *q = a.pat + beg;
         uint32_t it = 0;
+        PatReader pr(q, len);  // bounds = the whole pattern (the table lookup below shortens len)
         if (a.init_s == nullptr) kmer_lookup(a, ix.max_character, q, len, s, e, it);
-        PatReader pr(q);
         for (uint32_t k = len; k-- > 0;) {
             uint32_t c = pr.get(k);
             if (c > ix.max_character) {  // the reference panics here (cs[c] out of bounds, fm_index.rs:94)

@@ -350,6 +350,7 @@ def main():
     ap.add_argument("--npat", type=int, default=0, help="override the workload's patterns per step")
     ap.add_argument("--cpu-sample", type=int, default=200_000, help="patterns in the CPU baseline sample")
     ap.add_argument("--by-piece", action="store_true", help="MultiPieces workloads: partition the pieces over the GPUs")
+    ap.add_argument("--option", action="append", default=[], help="key=value tuning option (fmx_index_set_option), for A/B runs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gather-peak", action="store_true")
     ap.add_argument("--oracle-own-sa", action="store_true",
@@ -399,6 +400,9 @@ def main():
     t0 = time.perf_counter()
     index = cls.new(fmx.Text.with_max_character(text, mc), level, device=local)
     build_s = time.perf_counter() - t0
+    for kv in args.option:
+        k_, v_ = kv.split("=")
+        index.set_option(k_, int(v_))
     h = index._h
     # a real (non-default) stream: the library launches on the stream it is handed, and the CUDA
     # events below must sit on that same stream
@@ -669,7 +673,8 @@ def main():
             "index_device_bytes": index.heap_size(), "device_layout": index.layout_name(),
             "l2": "flushed between timed iterations (512 MiB memset)",
             "step": "fmx_search_batch_device + fmx_locate_batch_device" + (" replayed as one CUDA graph" if graph is not None else ""),
-            "parallelism": f"index replicated x{world}, query batches sharded", "index_build_s": round(build_s, 1)}),
+            "parallelism": f"index replicated x{world}, query batches sharded", "index_build_s": round(build_s, 1),
+            **({"options": args.option} if args.option else {})}),
         "count_queries_per_s": world * npat / (ms_search_total / args.steps * 1e-3),
         "located_hits_per_s": hits_all / (ms_per_step * 1e-3),
         "hits_per_step": hits_all,

@@ -354,7 +354,7 @@ int fmx_index_set_option(fmx_index *idx, const char *key, int64_t value) {
         int rc = build_big_table(idx, (uint64_t)(value < 0 ? 0 : value) << 20);
         if (rc) return rc;
     }
-    else if (k == "locate_refill") idx->opt_locate_refill = value != 0;
+    else if (k == "locate_refill") idx->opt_locate_refill = value < 0 || value > 2 ? 0 : (int)value;
     else if (k == "locate_expand") idx->opt_locate_expand = (int)value;
     else if (k == "locate_ranges") idx->opt_locate_ranges = value < 0 ? -1 : (value != 0);
     else if (k == "bucket") idx->opt_bucket = value < 0 ? -1 : (value != 0);
@@ -896,7 +896,10 @@ static int locate_fill(const fmx_index *idx, const RowSource &src, uint64_t tota
     if (warps > max_warps) warps = max_warps;
     a.chunk = chunk;
     const uint64_t blocks = (warps + 7) / 8;
-    dispatch(idx, [&](auto K, auto LY) { k_locate<K(), LY()><<<(unsigned)blocks, 256, 0, st>>>(idx->dev, a); });
+    if (idx->opt_locate_refill == 2)
+        dispatch(idx, [&](auto K, auto LY) { k_locate_stable<K(), LY()><<<(unsigned)blocks, 256, 0, st>>>(idx->dev, a); });
+    else
+        dispatch(idx, [&](auto K, auto LY) { k_locate<K(), LY()><<<(unsigned)blocks, 256, 0, st>>>(idx->dev, a); });
     LAUNCH_CHECK();
     return 0;
 }

@@ -1229,6 +1229,91 @@ __global__ void __launch_bounds__(256) k_locate(const __grid_constant__ FmxDev i
     }
 }
 
+// get_sa with STABLE warp-level compaction (option "locate_refill" = 2).  The refill kernel above lost
+// because it drops new hits into whichever lanes are idle, so neighbouring lanes stop holding neighbouring
+// rows and their probes stop sharing sectors.  Here a warp owns chunks of consecutive hits and keeps its
+// live walks in HIT ORDER: when fewer than FMX_COMPACT_BELOW lanes are busy the survivors are shifted down
+// (order preserved, three shuffles) and the free lanes on top take the next hits of the chunk, in order.
+// Survivors of a run are its unsampled rows -- still near-adjacent -- so coalescing mostly survives while
+// nearly every issued LF step serves a full warp.
+#define FMX_COMPACT_BELOW 25
+template <int KIND, int LAYOUT>
+__global__ void __launch_bounds__(256) k_locate_stable(const __grid_constant__ FmxDev ix, const __grid_constant__ LocateArgs a) {
+    __shared__ Tabs<LAYOUT> tb;
+    __shared__ uint32_t xch[8][3][32];
+    const uint32_t warp = threadIdx.x >> 5;
+    load_tables<LAYOUT>(ix, tb);
+    unsigned long long steps = 0;
+    const uint32_t mask = (1u << ix.sa_level) - 1u;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    uint64_t total = a.total;
+    if (a.total_dev && *a.total_dev < total) total = *a.total_dev;
+    const uint64_t C = a.chunk;
+    for (uint64_t chunk = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk * C < total; chunk += nwarps) {
+        const uint64_t base = chunk * C;
+        const uint32_t cnt = (uint32_t)(base + C < total ? C : total - base);
+        uint32_t next = 0;  // hits of the chunk handed out so far
+        bool active = false;
+        uint32_t row = 0, st = 0, hl = 0;  // hl = hit index inside the chunk
+        for (;;) {
+            if (active && !(row & mask)) {  // sampled row reached: (sa + steps) % n, both terms < n
+                uint64_t v = (uint64_t)__ldg(ix.sa + (row >> ix.sa_level)) + st;
+                if (v >= ix.n) v -= ix.n;
+                if (a.positions) a.positions[base + hl] = v;
+                if (KIND == FMX_KIND_MULTI_ && a.piece_ids) {
+                    uint32_t lo = 0, hi = ix.ndoc;  // number of piece ends strictly before v
+                    while (lo < hi) {
+                        uint32_t m = lo + ((hi - lo) >> 1);
+                        if (__ldg(ix.piece_end + m) < v) lo = m + 1; else hi = m;
+                    }
+                    a.piece_ids[base + hl] = lo;
+                }
+                steps += st;
+                active = false;
+            }
+            const unsigned live = __ballot_sync(0xffffffffu, active);
+            const uint32_t nlive = __popc(live);
+            if (nlive < FMX_COMPACT_BELOW && next < cnt) {
+                // stable compaction through shared memory: live lane -> slot popc(live lanes below it)
+                // (a pull by shuffle needs __fns, which is a software loop)
+                if (active) {
+                    const uint32_t d = __popc(live & lt);
+                    xch[warp][0][d] = row;
+                    xch[warp][1][d] = st;
+                    xch[warp][2][d] = hl;
+                }
+                __syncwarp();
+                active = lane < nlive;
+                row = xch[warp][0][lane];
+                st = xch[warp][1][lane];
+                hl = xch[warp][2][lane];
+                __syncwarp();
+                if (!active && next + (lane - nlive) < cnt) {  // the next hits of the chunk, in order
+                    hl = next + (lane - nlive);
+                    row = locate_row(a, base + hl);
+                    st = 0;
+                    active = true;
+                }
+                const uint32_t room = 32u - nlive, left = cnt - next;
+                next += room < left ? room : left;
+            } else if (live == 0) {
+                break;
+            }
+            if (active && (row & mask)) {
+                uint32_t sym;
+                row = lf_step<KIND, LAYOUT>(ix, tb, row, sym);
+                st++;
+            }
+        }
+    }
+    if (a.work) {
+        for (int o = 16; o > 0; o >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, o);
+        if (lane == 0 && steps) atomicAdd(a.work + 1, steps);
+    }
+}
+
 // get_sa for whole SA ranges (option "locate_ranges"; automatic when patterns have many matches each).
 // The rows of one pattern are ADJACENT (s .. e-1).  While all rows of a sub-range [a, a+len) carry the same
 // BWT symbol c -- the normal case on repetitive texts, which is what RLFMIndex is for -- LF maps them to

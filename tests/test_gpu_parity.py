@@ -563,10 +563,12 @@ def test_search_options_do_not_change_results():
     index.set_option("locate_refill", 0)                  # one hit per thread instead of per-lane refill
     hoff2, pos2 = index.search_batch(pats).locate()
     lf_simple = index.last_work()[1]
-    index.set_option("locate_refill", 1)
-    hoff3, pos3 = index.search_batch(pats).locate()
-    assert np.array_equal(hoff, hoff2) and np.array_equal(pos, pos2) and np.array_equal(pos, pos3)
-    assert index.last_work()[1] == lf_simple
+    for mode in (1, 2):                                   # unstable refill / stable warp-level compaction
+        index.set_option("locate_refill", mode)
+        hoff3, pos3 = index.search_batch(pats).locate()
+        assert np.array_equal(hoff, hoff2) and np.array_equal(pos, pos2) and np.array_equal(pos, pos3), mode
+        assert index.last_work()[1] == lf_simple
+    index.set_option("locate_refill", 0)
     for mode in (1, 2, 0):                                # rows expanded by scans / found by binary search / auto
         index.set_option("locate_expand", mode)
         b = index.search_batch(pats)

@@ -98,6 +98,7 @@ struct fmx_index {
     int opt_persistent = 0;  // 1: persistent refill search kernels instead of one pattern per thread
     int opt_kmer = 1;
     uint64_t opt_pipeline_chunk = 0;  // patterns per pipeline chunk (0 = automatic)
+    int opt_stage_patterns = 1;       // 0: never stage pattern bytes in shared memory (A/B)
     int opt_locate_ranges = -1;       // -1 auto (RLFM with >= 8 matches per pattern), 0 never, 1 always: k_locate_ranges
     int opt_locate_expand = 0;        // 0 auto, 1 always expand the rows first, 2 always binary-search in k_locate
     int opt_locate_refill = 0;        // 1: per-lane refill k_locate (lost the A/B: it breaks the coalescing of adjacent rows)
@@ -356,6 +357,7 @@ int fmx_index_set_option(fmx_index *idx, const char *key, int64_t value) {
     }
     else if (k == "locate_refill") idx->opt_locate_refill = value < 0 || value > 2 ? 0 : (int)value;
     else if (k == "locate_expand") idx->opt_locate_expand = (int)value;
+    else if (k == "stage_patterns") idx->opt_stage_patterns = value != 0;
     else if (k == "locate_ranges") idx->opt_locate_ranges = value < 0 ? -1 : (value != 0);
     else if (k == "bucket") idx->opt_bucket = value < 0 ? -1 : (value != 0);
     else if (k == "pipeline_chunk") idx->opt_pipeline_chunk = value > 0 ? (uint64_t)value : 0;
@@ -656,6 +658,8 @@ static int search_device(const fmx_index *idx, int mode, const uint8_t *d_pat, c
     a.err = idx->d_err;
     a.work = count_work ? idx->d_work : nullptr;
     a.steps_out = nullptr;
+    a.staged = (!d_pat_off && fixed_len > 0 && fixed_len % 16 == 0 && reinterpret_cast<uintptr_t>(d_pat) % 16 == 0 &&
+                idx->opt_stage_patterns) ? 1u : 0u;
     // the table memoises searches that start from (0, n): fresh search / search_prefix
     const bool tab_ok = idx->d_kmer_tab && idx->opt_kmer && !d_is && (mode == FMX_SEARCH || mode == FMX_SEARCH_PREFIX);
     a.kmer_tab = tab_ok ? idx->d_kmer_tab : nullptr;

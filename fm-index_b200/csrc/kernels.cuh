@@ -724,6 +724,8 @@ struct SearchArgs {
     // (= sorted by SA range start to within one k-mer range) touch the index quasi-sequentially, so
     // concurrently running threads share sectors in L2 and DRAM rows instead of hitting random ones.
     const uint32_t *order;
+    // fixed_len is a positive multiple of 16 and pat is 16-byte aligned: stage pattern bytes in shared memory
+    uint32_t staged;
     // v2 work queue: unfinished patterns after phase A, entry = {pattern id, remaining chars, s, e}
     uint4 *queue;
     unsigned long long *qcount;
@@ -778,10 +780,10 @@ struct PatReader {
 
 // table index of the last K characters of a pattern (base max_character, digit = c - 1);
 // false if one of them is \0 or exceeds max_character
-__device__ __forceinline__ bool kmer_index(const uint8_t *q, uint32_t len, uint32_t K, uint32_t maxc, uint32_t &idx) {
+template <class Reader>
+__device__ __forceinline__ bool kmer_index(Reader &pr, uint32_t len, uint32_t K, uint32_t maxc, uint32_t &idx) {
     uint32_t v = 0;
     bool valid = true;
-    PatReader pr(q, len);
     for (uint32_t j = 0; j < K; j++) {
         uint32_t c = pr.get(len - K + j);
         valid = valid && (c - 1u) < maxc;
@@ -793,7 +795,8 @@ __device__ __forceinline__ bool kmer_index(const uint8_t *q, uint32_t len, uint3
 
 // memoised start of a fresh search: returns true and sets (s, e, it, len) when a table serves the
 // pattern; otherwise the caller walks from (s0, e0) so errors show up (or not) exactly as in the reference
-__device__ __forceinline__ bool kmer_lookup(const SearchArgs &a, uint32_t maxc, const uint8_t *q, uint32_t &len,
+template <class Reader>
+__device__ __forceinline__ bool kmer_lookup(const SearchArgs &a, uint32_t maxc, Reader &q, uint32_t &len,
                                             uint32_t &s, uint32_t &e, uint32_t &it) {
     const uint2 *tab = nullptr;
     const uint8_t *stp = nullptr;
@@ -823,6 +826,58 @@ __device__ __forceinline__ bool kmer_lookup(const SearchArgs &a, uint32_t maxc, 
     return true;
 }
 
+// Fixed-length patterns whose bytes are 16-byte aligned (the batched entry points' usual input): the thread
+// pulls 32 characters of ITS pattern with two 128-bit loads into its own column of a shared-memory tile
+// and reads characters from there.  The warp's loads are one request per 128-byte line (0.25 per
+// pattern); word-by-word reads through L1 cost up to two L2 requests per pattern once index blocks had
+// evicted the lines -- of the twelve a 32-mer search on the 1 GB index makes in total.
+struct StagedReader {
+    uint32_t (*sp)[256];
+    const uint8_t *q;
+    uint32_t len, wb;  // the tile holds characters [wb, wb + 32)
+    __device__ __forceinline__ StagedReader(uint32_t (*sp_)[256], const uint8_t *q_, uint32_t len_) : sp(sp_), q(q_), len(len_) {
+        load(len_ > 32u ? len_ - 32u : 0u);
+    }
+    __device__ __forceinline__ void load(uint32_t w0) {
+        wb = w0;
+        const uint4 *g = reinterpret_cast<const uint4 *>(q + w0);
+        const uint4 v0 = __ldg(g);
+        sp[0][threadIdx.x] = v0.x;
+        sp[1][threadIdx.x] = v0.y;
+        sp[2][threadIdx.x] = v0.z;
+        sp[3][threadIdx.x] = v0.w;
+        if (w0 + 16u < len) {
+            const uint4 v1 = __ldg(g + 1);
+            sp[4][threadIdx.x] = v1.x;
+            sp[5][threadIdx.x] = v1.y;
+            sp[6][threadIdx.x] = v1.z;
+            sp[7][threadIdx.x] = v1.w;
+        }
+    }
+    __device__ __forceinline__ uint32_t get(uint32_t k) {
+        if (k < wb) load(wb >= 32u ? wb - 32u : 0u);
+        const uint32_t idx = k - wb;
+        return (sp[idx >> 2][threadIdx.x] >> (8u * (idx & 3u))) & 0xFFu;
+    }
+};
+
+// the reference loop for one pattern (wrapper.rs:103-124), characters through `rd`
+template <int KIND, int LAYOUT, class Reader>
+__device__ __forceinline__ void search_one(const FmxDev &ix, const Tabs<LAYOUT> &tb, const SearchArgs &a, Reader &rd,
+                                           uint32_t len, uint32_t &s, uint32_t &e, uint32_t &it) {
+    if (a.init_s == nullptr) kmer_lookup(a, ix.max_character, rd, len, s, e, it);
+    for (uint32_t k = len; k-- > 0;) {
+        uint32_t c = rd.get(k);
+        if (c > ix.max_character) {  // the reference panics here (cs[c] out of bounds, fm_index.rs:94)
+            atomicOr(a.err, 1u);
+            break;
+        }
+        lf_map2_pair<KIND, LAYOUT>(ix, tb, c, s, e);
+        it++;
+        if (s == e) break;
+    }
+}
+
 // Backward search (wrapper.rs:103-124): one pattern per thread, grid-stride; the first kmer_k
 // iterations of a fresh search are one table lookup.  This simple shape won the A/B against the
 // persistent refill kernels below: once the index sits in L2 the kernel is bound by the number of
@@ -831,6 +886,7 @@ __device__ __forceinline__ bool kmer_lookup(const SearchArgs &a, uint32_t maxc, 
 template <int KIND, int LAYOUT>
 __global__ void __launch_bounds__(256) k_search(const __grid_constant__ FmxDev ix, const __grid_constant__ SearchArgs a) {
     __shared__ Tabs<LAYOUT> tb;
+    __shared__ uint32_t spat[8][256];
     load_tables<LAYOUT>(ix, tb);
     unsigned long long steps = 0;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -843,17 +899,12 @@ __global__ void __launch_bounds__(256) k_search(const __grid_constant__ FmxDev i
         uint32_t e = a.init_e ? (uint32_t)a.init_e[p] : a.e0;
         const uint8_t *q = a.pat + beg;
         uint32_t it = 0;
-        PatReader pr(q, len);  // bounds = the whole pattern (the table lookup below shortens len)
-        if (a.init_s == nullptr) kmer_lookup(a, ix.max_character, q, len, s, e, it);
-        for (uint32_t k = len; k-- > 0;) {
-            uint32_t c = pr.get(k);
-            if (c > ix.max_character) {  // the reference panics here (cs[c] out of bounds, fm_index.rs:94)
-                atomicOr(a.err, 1u);
-                break;
-            }
-            lf_map2_pair<KIND, LAYOUT>(ix, tb, c, s, e);
-            it++;
-            if (s == e) break;
+        if (a.staged) {
+            StagedReader rd(spat, q, len);
+            search_one<KIND, LAYOUT>(ix, tb, a, rd, len, s, e, it);
+        } else {
+            PatReader rd(q, len);  // bounds = the whole pattern
+            search_one<KIND, LAYOUT>(ix, tb, a, rd, len, s, e, it);
         }
         steps += it;
         a.out_s[p] = s;
@@ -894,7 +945,8 @@ __global__ void __launch_bounds__(256) k_bucket_count(const __grid_constant__ Se
     pattern_span(a, p, beg, len);
     if (len >= a.kmer_k) {
         uint32_t v;
-        if (kmer_index(a.pat + beg, len, a.kmer_k, maxc, v)) idx = v;
+        PatReader rd(a.pat + beg, len);
+        if (kmer_index(rd, len, a.kmer_k, maxc, v)) idx = v;
     }
     bucket[p] = idx;
     atomicAdd(hist + idx, 1u);
@@ -931,7 +983,8 @@ __global__ void __launch_bounds__(256) k_search_init(const __grid_constant__ Fmx
             bool done = k == 0;
             if (use_tab) {
                 uint32_t it = 0;
-                if (kmer_lookup(a, ix.max_character, q, k, s, e, it)) {
+                PatReader rd(q, k);
+                if (kmer_lookup(a, ix.max_character, rd, k, s, e, it)) {
                     steps += it;
                     done = k == 0;
                 }

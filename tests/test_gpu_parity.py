@@ -425,6 +425,23 @@ def test_range_walk_locate_on_repetitive_text(kind, level):
         assert total == int(want[0][-1]) and np.array_equal(page, want[1][1000:6000])
 
 
+@pytest.mark.parametrize("m", [16, 32, 48, 64, 80, 20])
+def test_fixed_length_patterns_staged_in_shared_memory(m):
+    """fixed-length batches whose length is a multiple of 16 read their characters through a shared-memory
+    tile (32-character windows, refilled for longer patterns); everything else through the word reader"""
+    text = dna(300_000, 61)
+    pats, _ = mixed_patterns(text, 20_000, m, 62)
+    index = fmx.FMIndexWithLocate.new(fmx.Text.with_max_character(text, 4), 2)
+    oracle = orc.OracleIndex(text, orc.FM, level=2, max_character=4)
+    s, e = oracle.search_batch(pats.reshape(-1), np.arange(pats.shape[0] + 1, dtype=np.uint64) * m)
+    for stage in (1, 0):
+        index.set_option("stage_patterns", stage)
+        for kmer in (1, 0):
+            index.set_option("kmer", kmer)
+            b = index.search_batch(pats)
+            assert np.array_equal(b.s, s) and np.array_equal(b.e, e), (stage, kmer)
+
+
 def test_paged_locate_equals_full_locate():
     """fmx_locate_page: the hit list in pages (bounded memory) equals the one-shot list, order included"""
     text = dna(200_000, 55)

@@ -509,11 +509,40 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
         for (uint32_t c = 0; c < cs_len; c++) adj[c] = cs[c] - (uint32_t)wm.walk(0, c);
     }
 
+    // seed-and-verify structures (fmx_layout.h): dense (full SA + full ISA) within the budget, else sampled
+    // for the SYM layout (text, ISA every 4 positions, SA samples of level <= 3), else none
+    std::vector<uint32_t> isa_s;
+    bool verify = kind == FMX_KIND_FM && n >= 4096, verify_dense = false;
+    {
+        const char *nv = std::getenv("FMX_NO_VERIFY");
+        if (nv && nv[0] && nv[0] != '0') verify = false;
+        uint64_t budget = 24576ull << 20;
+        if (const char *vb = std::getenv("FMX_VERIFY_BUDGET_MB")) budget = std::strtoull(vb, nullptr, 10) << 20;
+        // an index whose rank structure sits in the 126 MB L2 answers a step from L2; the tail's three or four
+        // DRAM reads are slower than that (measured on the 100 MB DNA config), so it is not built there
+        uint64_t min_rank = 192ull << 20;
+        if (const char *mr = std::getenv("FMX_VERIFY_MIN_RANK_MB")) min_rank = std::strtoull(mr, nullptr, 10) << 20;
+        const uint64_t rank_bytes = use_q4 ? (n / 64 + 1) * 32 : (use_sym ? sym_bytes(cs_len, n) : (uint64_t)L * (n / FMX_RB_BITS + 1) * 32);
+        if (rank_bytes < min_rank) verify = false;
+        verify_dense = verify && 9 * n <= budget;
+        if (verify && !verify_dense) verify = use_sym && (level < 0 || level <= 3);
+    }
+    const uint32_t isa_level = verify_dense ? 0u : 2u;
+    if (verify) {
+        isa_s.assign(((n - 1) >> isa_level) + 1, 0);
+#pragma omp parallel for schedule(static)
+        for (int64_t r = 0; r < (int64_t)n; r++)
+            if ((sa[r] & ((1u << isa_level) - 1u)) == 0) isa_s[sa[r] >> isa_level] = (uint32_t)r;
+        hdr.verify = 1;
+        hdr.isa_level = isa_level;
+    }
+    const bool need_samples_for_verify = verify && !verify_dense;
+
     // sample.rs:21-44
     std::vector<uint32_t> samples;
-    if (level >= 0) {
-        hdr.has_locate = 1;
-        uint32_t lvl = (uint32_t)level;
+    if (level >= 0 || need_samples_for_verify) {
+        hdr.has_locate = level >= 0 ? 1 : 0;  // count-only indexes keep level-2 samples for the sampled verify path only
+        uint32_t lvl = level >= 0 ? (uint32_t)level : 2u;
         if (n > 0) {
             hdr.sa_word_size = log2_u64(n) + 1;
             if (lvl >= 63 || n <= (1ull << lvl)) lvl = 0;  // sample.rs:28-31
@@ -524,7 +553,8 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
             for (int64_t i = 0; i < (int64_t)hdr.sa_count; i++) samples[i] = sa[(uint64_t)i << lvl];
         }
     }
-    std::vector<uint32_t>().swap(sa);
+    hdr.vsa_level = verify_dense ? 0u : hdr.sa_level;
+    if (!verify_dense) std::vector<uint32_t>().swap(sa);  // the dense verify path keeps the full array (SEC_VSA)
 
     // ---- assemble
     SectionData sec[SEC_COUNT];
@@ -542,6 +572,11 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
     sec[SEC_ADJ] = {adj.data(), adj.size() * 4};
     sec[SEC_CS] = {cs.data(), cs.size() * 4};
     if (!samples.empty()) sec[SEC_SA] = {samples.data(), samples.size() * 4};
+    if (verify) {
+        sec[SEC_TEXT] = {text, n};
+        sec[SEC_ISA] = {isa_s.data(), isa_s.size() * 4};
+        if (verify_dense) sec[SEC_VSA] = {sa.data(), sa.size() * 4};
+    }
     if (!doc.empty()) sec[SEC_DOC] = {doc.data(), doc.size() * 4};
     if (!piece_end.empty()) sec[SEC_PIECE_END] = {piece_end.data(), piece_end.size() * 4};
     if (kind == FMX_KIND_RLFM) {

@@ -98,6 +98,7 @@ struct fmx_index {
     int opt_persistent = 0;  // 1: persistent refill search kernels instead of one pattern per thread
     int opt_kmer = 1;
     uint64_t opt_pipeline_chunk = 0;  // patterns per pipeline chunk (0 = automatic)
+    int opt_verify = 1;               // 0: never take the seed-and-verify tail (A/B)
     int opt_stage_patterns = 1;       // 0: never stage pattern bytes in shared memory (A/B)
     int opt_locate_ranges = -1;       // -1 auto (RLFM with >= 8 matches per pattern), 0 never, 1 always: k_locate_ranges
     int opt_locate_expand = 0;        // 0 auto, 1 always expand the rows first, 2 always binary-search in k_locate
@@ -250,6 +251,12 @@ static int upload(std::vector<uint8_t> &&blob, int device, fmx_index **out) {
     d.rl_bsel = static_cast<const uint32_t *>(sec(SEC_RL_BSEL));
     d.rl_bpsel = static_cast<const uint32_t *>(sec(SEC_RL_BPSEL));
     d.exc = static_cast<const uint32_t *>(sec(SEC_EXC));
+    d.text = static_cast<const uint8_t *>(sec(SEC_TEXT));
+    d.isa = static_cast<const uint32_t *>(sec(SEC_ISA));
+    d.vsa = hdr.sec[SEC_VSA].bytes ? static_cast<const uint32_t *>(sec(SEC_VSA)) : d.sa;
+    d.vsa_level = hdr.vsa_level;
+    d.verify = hdr.verify && d.text && d.isa && d.vsa ? 1u : 0u;
+    d.isa_level = hdr.isa_level;
     d.layout = hdr.layout;
     d.nexc = hdr.nexc;
     d.n = (uint32_t)hdr.n;
@@ -358,6 +365,7 @@ int fmx_index_set_option(fmx_index *idx, const char *key, int64_t value) {
     else if (k == "locate_refill") idx->opt_locate_refill = value < 0 || value > 2 ? 0 : (int)value;
     else if (k == "locate_expand") idx->opt_locate_expand = (int)value;
     else if (k == "stage_patterns") idx->opt_stage_patterns = value != 0;
+    else if (k == "verify") idx->opt_verify = value != 0;
     else if (k == "locate_ranges") idx->opt_locate_ranges = value < 0 ? -1 : (value != 0);
     else if (k == "bucket") idx->opt_bucket = value < 0 ? -1 : (value != 0);
     else if (k == "pipeline_chunk") idx->opt_pipeline_chunk = value > 0 ? (uint64_t)value : 0;
@@ -383,7 +391,7 @@ int fmx_index_kind(const fmx_index *idx) { return idx ? (int)idx->hdr.kind : -1;
 int fmx_index_has_locate(const fmx_index *idx) { return idx ? (int)idx->hdr.has_locate : 0; }
 int fmx_index_device(const fmx_index *idx) { return idx ? idx->device : -1; }
 uint32_t fmx_index_wavelet_levels(const fmx_index *idx) { return idx ? idx->hdr.levels : 0; }
-uint32_t fmx_index_sample_level(const fmx_index *idx) { return idx ? idx->hdr.sa_level : 0; }
+uint32_t fmx_index_sample_level(const fmx_index *idx) { return idx && idx->hdr.has_locate ? idx->hdr.sa_level : 0; }
 uint32_t fmx_index_layout(const fmx_index *idx) { return idx ? idx->hdr.layout : 0; }
 uint32_t fmx_index_sectors_per_rank(const fmx_index *idx) {
     if (!idx) return 0;
@@ -660,6 +668,7 @@ static int search_device(const fmx_index *idx, int mode, const uint8_t *d_pat, c
     a.steps_out = nullptr;
     a.staged = (!d_pat_off && fixed_len > 0 && fixed_len % 16 == 0 && reinterpret_cast<uintptr_t>(d_pat) % 16 == 0 &&
                 idx->opt_stage_patterns) ? 1u : 0u;
+    a.verify = (idx->dev.verify && idx->opt_verify) ? 1u : 0u;
     // the table memoises searches that start from (0, n): fresh search / search_prefix
     const bool tab_ok = idx->d_kmer_tab && idx->opt_kmer && !d_is && (mode == FMX_SEARCH || mode == FMX_SEARCH_PREFIX);
     a.kmer_tab = tab_ok ? idx->d_kmer_tab : nullptr;

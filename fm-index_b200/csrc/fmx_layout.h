@@ -48,6 +48,19 @@
 // what bounds this workload (profiles/r01b_random_access_study.md: ~45 G DRAM-missing requests/s
 // whatever their size).  Above the budget (FMX_SYM_BUDGET_MB, default 49152) the builder falls back to WM4.
 //
+// SEED-AND-VERIFY TAIL (FM kind; SEC_TEXT, SEC_ISA, SEC_VSA).  Once backward search has narrowed the range
+// to ONE row, the remaining characters can only match one place: the row is located, the rest of the
+// pattern is compared with the text directly, and the row the reference's loop would end in is
+// ISA[pos - matched].  DENSE form (default while 9 n bytes fit FMX_VERIFY_BUDGET_MB, 24 GiB): the full
+// suffix array and its inverse, so the tail costs three or four memory requests -- SA[s], one or two text
+// lines, ISA[q] -- instead of one per remaining character, with no data-dependent loop.  SAMPLED form
+// (larger texts with the SYM layout): the caller's suffix-array samples (level <= 3) and an ISA sampled
+// every 4 positions, each followed by a short LF walk; it pays only where an LF step is expensive.
+// Either way the result is exactly the (s, e) and step count of the reference loop, including the emptied
+// range when the comparison fails (one more lf_map2 pair with the mismatching character).  These are
+// acceleration structures of the SEARCH, like the k-mer tables: locate still walks to the samples of the
+// level the caller asked for.
+//
 // Q4 DETAILS.  The rare symbol 0
 // (the \0 terminators: 1 for a single text, one per piece for MultiPieces) is stored as code 0
 // and its positions are listed in SEC_EXC (sorted; staged in shared memory), which corrects
@@ -60,7 +73,7 @@
 #include <vector_types.h>  // uint4 (CUDA toolkit header, host-safe)
 
 #define FMX_BLOB_MAGIC 0x3030324258584d46ull /* "FMXXB200" little endian-ish tag */
-#define FMX_BLOB_VERSION 5u
+#define FMX_BLOB_VERSION 6u
 #define FMX_MAX_LEVELS 8
 #define FMX_RB_BITS 192u
 #define FMX_MAX_EXC 1024u   /* Q4 layout: at most this many \0 symbols in the sequence */
@@ -83,7 +96,10 @@ enum FmxSection : uint32_t {
     SEC_RL_BSEL = 15,   // u32[runs+1]  select1(b, j), [runs] = n
     SEC_RL_BPSEL = 16,  // u32[runs+1]  select1(bp, j), [runs] = n
     SEC_EXC = 17,       // u32[nexc]  Q4 layout: sorted positions whose symbol is 0
-    SEC_COUNT = 18
+    SEC_TEXT = 18,      // u8[n]      the text itself (verify path, FM kind)
+    SEC_ISA = 19,       // u32[ceil(n / 2^isa_level)]  row of the suffix starting at text position k << isa_level
+    SEC_VSA = 20,       // u32[n]     the FULL suffix array, for the verify path only (locate keeps the caller's level)
+    SEC_COUNT = 21
 };
 
 struct FmxSectionEntry {
@@ -114,8 +130,12 @@ struct FmxBlobHeader {
     uint32_t nexc;    // Q4: number of zeros in the sequence
     uint32_t qlevels; // WM4: ceil(levels / 2)
     uint32_t sym_nblk; // SYM: RB192 blocks per symbol vector (seq_len / 192 + 1)
+    uint32_t verify;     // 1: SEC_TEXT / SEC_ISA / SEC_SA present for the seed-and-verify tail of k_search
+    uint32_t isa_level;  // ISA sampling: every 2^isa_level-th text position (0 with the dense structures)
+    uint32_t vsa_level;  // sampling level of the suffix-array samples the verify path walks to (0 = SEC_VSA / dense)
+    uint32_t pad1;
     uint64_t qoff[FMX_MAX_QLEVELS][4];  // WM4: start of digit group d at level l
-    uint64_t reserved[6];
+    uint64_t reserved[4];
 };
 
 // What the kernels see (passed by value as a __grid_constant__ parameter).
@@ -149,4 +169,10 @@ struct FmxDev {
     uint32_t qoff[FMX_MAX_QLEVELS * 4];
     uint32_t sym_nblk;
     const uint8_t *raw;  // SYM: the sequence itself
+    const uint8_t *text; // verify path: the text
+    const uint32_t *isa; // verify path: sampled inverse suffix array
+    uint32_t verify;
+    uint32_t isa_level;
+    const uint32_t *vsa;  // verify path: suffix-array samples of level vsa_level (the full array when dense)
+    uint32_t vsa_level;
 };

@@ -726,6 +726,8 @@ struct SearchArgs {
     const uint32_t *order;
     // fixed_len is a positive multiple of 16 and pat is 16-byte aligned: stage pattern bytes in shared memory
     uint32_t staged;
+    // the index carries the verify structures and the option is on: seed-and-verify tail for one-row ranges
+    uint32_t verify;
     // v2 work queue: unfinished patterns after phase A, entry = {pattern id, remaining chars, s, e}
     uint4 *queue;
     unsigned long long *qcount;
@@ -861,12 +863,65 @@ struct StagedReader {
     }
 };
 
+// Seed-and-verify tail (fmx_layout.h): the range is the single row s and `rem` characters rd[0 .. rem) are
+// still to be consumed.  Locates the row, compares the characters with the text, and jumps to the row the
+// reference loop ends in through the sampled inverse suffix array.  Returns false (nothing changed) when
+// the pattern would run off the start of the text.  Arithmetic mirrored in tests/blobreader.py.
+#define FMX_VERIFY_MIN_DENSE 6u     /* fewest remaining characters worth the tail: dense structures (3-4 requests) */
+#define FMX_VERIFY_MIN_SAMPLED 10u  /* sampled structures (two short LF walks on top) */
+template <int KIND, int LAYOUT, class Reader>
+__device__ __forceinline__ bool verify_tail(const FmxDev &ix, const Tabs<LAYOUT> &tb, const SearchArgs &a, Reader &rd,
+                                            uint32_t rem, uint32_t &s, uint32_t &e, uint32_t &it) {
+    const uint32_t mask = (1u << ix.vsa_level) - 1u;  // 0 with the dense structures: no walk
+    uint32_t row = s, st = 0, sym;
+    while (row & mask) {
+        row = lf_step<KIND, LAYOUT>(ix, tb, row, sym);
+        st++;
+    }
+    uint32_t pos = __ldg(ix.vsa + (row >> ix.vsa_level)) + st;  // < 2n < 2^32
+    if (pos >= ix.n) pos -= ix.n;
+    if (pos < rem) return false;
+    // characters rd[rem-1], rd[rem-2], .. against text[pos-1], text[pos-2], ..
+    PatReader tr(ix.text + (pos - rem), rem);
+    uint32_t matched = 0;
+    while (matched < rem && rd.get(rem - 1u - matched) == tr.get(rem - 1u - matched)) matched++;
+    uint32_t r = s;
+    if (matched) {
+        const uint32_t q = pos - matched, step = 1u << ix.isa_level;
+        uint32_t q4 = (q + step - 1u) & ~(step - 1u);
+        if (q4 >= ix.n) {  // past the last sample: walk from the final suffix "\0", which is row 0
+            q4 = ix.n - 1u;
+            r = 0;
+        } else {
+            r = __ldg(ix.isa + (q4 >> ix.isa_level));
+        }
+        for (uint32_t d = q4 - q; d > 0; d--) r = lf_step<KIND, LAYOUT>(ix, tb, r, sym);
+    }
+    it += matched;
+    s = r;
+    e = r + 1u;
+    if (matched < rem) {  // the reference's next iteration empties the range -- or hits an invalid character
+        const uint32_t c = rd.get(rem - 1u - matched);
+        if (c > ix.max_character) {
+            atomicOr(a.err, 1u);
+            return true;
+        }
+        lf_map2_pair<KIND, LAYOUT>(ix, tb, c, s, e);
+        it++;
+    }
+    return true;
+}
+
 // the reference loop for one pattern (wrapper.rs:103-124), characters through `rd`
 template <int KIND, int LAYOUT, class Reader>
 __device__ __forceinline__ void search_one(const FmxDev &ix, const Tabs<LAYOUT> &tb, const SearchArgs &a, Reader &rd,
                                            uint32_t len, uint32_t &s, uint32_t &e, uint32_t &it) {
     if (a.init_s == nullptr) kmer_lookup(a, ix.max_character, rd, len, s, e, it);
     for (uint32_t k = len; k-- > 0;) {
+        if (KIND == FMX_KIND_FM_ && a.verify && e - s == 1u &&
+            k + 1u >= (ix.isa_level == 0 ? FMX_VERIFY_MIN_DENSE : FMX_VERIFY_MIN_SAMPLED)) {
+            if (verify_tail<KIND, LAYOUT>(ix, tb, a, rd, k + 1u, s, e, it)) break;
+        }
         uint32_t c = rd.get(k);
         if (c > ix.max_character) {  // the reference panics here (cs[c] out of bounds, fm_index.rs:94)
             atomicOr(a.err, 1u);

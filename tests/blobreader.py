@@ -4,8 +4,8 @@ import struct
 
 import numpy as np
 
-SEC_LEVEL0, SEC_ADJ, SEC_CS, SEC_SA, SEC_DOC, SEC_PIECE_END, SEC_RL_B, SEC_RL_BP, SEC_RL_BSEL, SEC_RL_BPSEL, SEC_EXC, SEC_COUNT = \
-    0, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18
+SEC_LEVEL0, SEC_ADJ, SEC_CS, SEC_SA, SEC_DOC, SEC_PIECE_END, SEC_RL_B, SEC_RL_BP, SEC_RL_BSEL, SEC_RL_BPSEL, SEC_EXC, SEC_TEXT, SEC_ISA, \
+    SEC_VSA, SEC_COUNT = 0, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21
 RB_BITS = 192
 M32 = 0xFFFFFFFF
 
@@ -41,6 +41,8 @@ class Blob:
         o += 16 * SEC_COUNT
         self.layout, self.nexc, self.qlevels, self.sym_nblk = struct.unpack_from("<IIII", raw, o)
         o += 16
+        self.verify, self.isa_level, self.vsa_level, _ = struct.unpack_from("<IIII", raw, o)
+        o += 16
         self.qoff = [struct.unpack_from("<4Q", raw, o + 32 * l) for l in range(4)]
         assert self.total_bytes == len(raw)
         if self.layout == 3:
@@ -65,6 +67,10 @@ class Blob:
         self.sa = np.frombuffer(self._sec(SEC_SA), dtype=np.uint32)
         self.doc = np.frombuffer(self._sec(SEC_DOC), dtype=np.uint32)
         self.piece_end = np.frombuffer(self._sec(SEC_PIECE_END), dtype=np.uint32)
+        if self.verify:
+            self.text = np.frombuffer(self._sec(SEC_TEXT), dtype=np.uint8)
+            self.isa = np.frombuffer(self._sec(SEC_ISA), dtype=np.uint32)
+            self.vsa = np.frombuffer(self._sec(SEC_VSA), dtype=np.uint32) if self.sec[SEC_VSA][1] else self.sa
         if self.kind == 1:
             self.b = RBVec(self._sec(SEC_RL_B))
             self.bp = RBVec(self._sec(SEC_RL_BP))
@@ -193,3 +199,55 @@ class Blob:
             if s == e:
                 break
         return s, e
+
+
+    # ---- the seed-and-verify tail of k_search (kernels.cuh: verify_tail), in Python
+    @property
+    def VERIFY_MIN(self):
+        return 6 if self.isa_level == 0 else 10
+
+    def _verify_tail(self, pat, k, s):
+        """range [s, s+1), characters pat[0:k] still to consume -> (s, e, steps executed) or None"""
+        row, st, mask = s, 0, (1 << self.vsa_level) - 1
+        while row & mask:
+            _, row = self.lf_step(row)
+            st += 1
+        pos = (int(self.vsa[row >> self.vsa_level]) + st) % self.n
+        if pos < k:
+            return None
+        matched = 0
+        while matched < k and pat[k - 1 - matched] == int(self.text[pos - 1 - matched]):
+            matched += 1
+        q = pos - matched
+        if matched == 0:
+            r = s
+        else:
+            step = 1 << self.isa_level
+            q4 = (q + step - 1) // step * step
+            if q4 >= self.n:
+                r, q4 = 0, self.n - 1          # the suffix "\0" is row 0
+            else:
+                r = int(self.isa[q4 >> self.isa_level])
+            for _ in range(q4 - q):
+                _, r = self.lf_step(r)
+        s, e, it = r, r + 1, matched
+        if matched < k:
+            c = pat[k - 1 - matched]
+            s, e = self.lf_map2(c, s), self.lf_map2(c, e)
+            it += 1
+        return s, e, it
+
+    def search_verify(self, pat):
+        """SearchWrapper::search with the verify tail; -> (s, e, steps executed)"""
+        s, e, it, k = 0, self.n, 0, len(pat)
+        while k > 0:
+            if self.verify and e - s == 1 and k >= self.VERIFY_MIN:
+                res = self._verify_tail(pat, k, s)
+                if res is not None:
+                    return res[0], res[1], it + res[2]
+            s, e = self.lf_map2(pat[k - 1], s), self.lf_map2(pat[k - 1], e)
+            it += 1
+            k -= 1
+            if s == e:
+                break
+        return s, e, it

@@ -442,6 +442,56 @@ def test_fixed_length_patterns_staged_in_shared_memory(m):
             assert np.array_equal(b.s, s) and np.array_equal(b.e, e), (stage, kmer)
 
 
+@pytest.mark.parametrize("mc,level,dense", [(4, 2, True), (4, None, True), (255, 1, True), (255, 3, False), (255, None, False)])
+def test_seed_and_verify_tail(mc, level, dense, monkeypatch):
+    """one-row ranges finish by locate + text comparison + sampled-ISA jump (verify_tail): SA ranges and
+    executed step counts equal the oracle's plain loop -- matches, mismatches anywhere in the tail, patterns
+    running off the start of the text, invalid characters inside the compared region"""
+    monkeypatch.setenv("FMX_VERIFY_MIN_RANK_MB", "0")    # by default only indexes beyond the L2 carry the structures
+    if not dense:
+        monkeypatch.setenv("FMX_VERIFY_BUDGET_MB", "0")   # sampled structures (texts beyond the dense budget, SYM layout)
+    rng = np.random.default_rng(700 + mc + (level or 0))
+    n = 50_000
+    sigma = min(mc, 4)
+    text = np.append(rng.integers(1, sigma + 1, n, dtype=np.uint8), np.uint8(0))
+    cls = fmx.FMIndex if level is None else fmx.FMIndexWithLocate
+    index = cls.new(fmx.Text.with_max_character(text, mc)) if level is None else cls.new(fmx.Text.with_max_character(text, mc), level)
+    oracle = orc.OracleIndex(text, orc.FM, level=level, max_character=mc)
+    pats = []
+    for t in range(6000):
+        m = int(rng.integers(10, 70)) if t % 7 else int(rng.integers(6, 14))
+        p0 = int(rng.integers(0, n - m))
+        pat = text[p0:p0 + m].copy()
+        kind = t % 5
+        if kind == 1:
+            j = int(rng.integers(0, m))
+            pat[j] = pat[j] % sigma + 1
+        elif kind == 2:
+            pat = np.concatenate([rng.integers(1, sigma + 1, 25, dtype=np.uint8), text[:m]])
+        elif kind == 3:
+            for j in rng.integers(0, m, 3):
+                pat[int(j)] = rng.integers(1, sigma + 1)
+        elif kind == 4 and mc == 255:
+            pat[int(rng.integers(0, m))] = 0          # a \0 inside the pattern: valid character, never matches here
+        pats.append(pat.tobytes())
+    flat, off = orc.pack_patterns(pats)
+    s, e, steps = oracle.search_batch(flat, off, want_steps=True)
+    for verify in (1, 0):
+        index.set_option("verify", verify)
+        b = index.search_batch(pats)
+        assert np.array_equal(b.s, s) and np.array_equal(b.e, e), verify
+        assert index.last_work()[0] == int(steps.sum()), verify
+    if mc == 4:                                       # invalid character deep inside an otherwise unique match
+        bad = bytearray(text[1000:1040].tobytes())
+        bad[5] = 9
+        with pytest.raises(IndexError):
+            index.search_batch([bytes(bad)])
+        bad2 = bytearray(text[1000:1040].tobytes())
+        bad2[5] = 9
+        bad2[30] = bad2[30] % 4 + 1                   # ... but the range empties first: no error, as in the reference
+        assert index.search_batch([bytes(bad2)]).count()[0] == 0
+
+
 def test_paged_locate_equals_full_locate():
     """fmx_locate_page: the hit list in pages (bounded memory) equals the one-shot list, order included"""
     text = dna(200_000, 55)

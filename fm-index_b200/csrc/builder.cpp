@@ -512,11 +512,11 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
     // seed-and-verify structures (fmx_layout.h): dense (full SA + full ISA) within the budget, else sampled
     // for the SYM layout (text, ISA every 4 positions, SA samples of level <= 3), else none
     std::vector<uint32_t> isa_s;
-    bool verify = kind == FMX_KIND_FM && n >= 4096, verify_dense = false;
+    bool verify = (kind == FMX_KIND_FM || kind == FMX_KIND_MULTI) && n >= 4096, verify_dense = false;
     {
         const char *nv = std::getenv("FMX_NO_VERIFY");
         if (nv && nv[0] && nv[0] != '0') verify = false;
-        uint64_t budget = 24576ull << 20;
+        uint64_t budget = 32768ull << 20;
         if (const char *vb = std::getenv("FMX_VERIFY_BUDGET_MB")) budget = std::strtoull(vb, nullptr, 10) << 20;
         // an index whose rank structure sits in the 126 MB L2 answers a step from L2; the tail's three or four
         // DRAM reads are slower than that (measured on the 100 MB DNA config), so it is not built there
@@ -525,7 +525,7 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
         const uint64_t rank_bytes = use_q4 ? (n / 64 + 1) * 32 : (use_sym ? sym_bytes(cs_len, n) : (uint64_t)L * (n / FMX_RB_BITS + 1) * 32);
         if (rank_bytes < min_rank) verify = false;
         verify_dense = verify && 9 * n <= budget;
-        if (verify && !verify_dense) verify = use_sym && (level < 0 || level <= 3);
+        if (verify && !verify_dense) verify = kind == FMX_KIND_FM && use_sym && (level < 0 || level <= 3);
     }
     const uint32_t isa_level = verify_dense ? 0u : 2u;
     if (verify) {

@@ -48,16 +48,17 @@
 // what bounds this workload (profiles/r01b_random_access_study.md: ~45 G DRAM-missing requests/s
 // whatever their size).  Above the budget (FMX_SYM_BUDGET_MB, default 49152) the builder falls back to WM4.
 //
-// SEED-AND-VERIFY TAIL (FM kind; SEC_TEXT, SEC_ISA, SEC_VSA).  Once backward search has narrowed the range
+// SEED-AND-VERIFY TAIL (FM and MultiPieces kinds; SEC_TEXT, SEC_ISA, SEC_VSA).  Once backward search has narrowed the range
 // to ONE row, the remaining characters can only match one place: the row is located, the rest of the
 // pattern is compared with the text directly, and the row the reference's loop would end in is
-// ISA[pos - matched].  DENSE form (default while 9 n bytes fit FMX_VERIFY_BUDGET_MB, 24 GiB): the full
+// ISA[pos - matched].  DENSE form (default while 9 n bytes fit FMX_VERIFY_BUDGET_MB, 32 GiB): the full
 // suffix array and its inverse, so the tail costs three or four memory requests -- SA[s], one or two text
 // lines, ISA[q] -- instead of one per remaining character, with no data-dependent loop.  SAMPLED form
 // (larger texts with the SYM layout): the caller's suffix-array samples (level <= 3) and an ISA sampled
 // every 4 positions, each followed by a short LF walk; it pays only where an LF step is expensive.
-// Either way the result is exactly the (s, e) and step count of the reference loop, including the emptied
-// range when the comparison fails (one more lf_map2 pair with the mismatching character).  These are
+// The tail consumes exactly the characters that match; the ordinary loop then takes the next one, so a
+// mismatch empties the range -- and an invalid character raises the error -- exactly as in the reference,
+// with the same (s, e) and step count.  MultiPieces: the comparison stops in front of a \0 of the text.  These are
 // acceleration structures of the SEARCH, like the k-mer tables: locate still walks to the samples of the
 // level the caller asked for.
 //

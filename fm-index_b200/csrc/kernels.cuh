@@ -865,13 +865,16 @@ struct StagedReader {
 
 // Seed-and-verify tail (fmx_layout.h): the range is the single row s and `rem` characters rd[0 .. rem) are
 // still to be consumed.  Locates the row, compares the characters with the text, and jumps to the row the
-// reference loop ends in through the sampled inverse suffix array.  Returns false (nothing changed) when
-// the pattern would run off the start of the text.  Arithmetic mirrored in tests/blobreader.py.
+// reference loop reaches after the characters that match, through the inverse suffix array.  Returns how
+// many characters it consumed (s updated; the range is [s, s + 1)); 0 = nothing done (immediate mismatch,
+// or the pattern would run off the start of the text).  The caller's ordinary loop takes the next
+// character -- the mismatching one empties the range there exactly as in the reference, an invalid one
+// raises the error there.  MultiPieces: the comparison stops in front of a \0 of the text, whose LF rule
+// (multi_pieces.rs:140-153) is not a plain rank.  Arithmetic mirrored in tests/blobreader.py.
 #define FMX_VERIFY_MIN_DENSE 6u     /* fewest remaining characters worth the tail: dense structures (3-4 requests) */
 #define FMX_VERIFY_MIN_SAMPLED 10u  /* sampled structures (two short LF walks on top) */
 template <int KIND, int LAYOUT, class Reader>
-__device__ __forceinline__ bool verify_tail(const FmxDev &ix, const Tabs<LAYOUT> &tb, const SearchArgs &a, Reader &rd,
-                                            uint32_t rem, uint32_t &s, uint32_t &e, uint32_t &it) {
+__device__ __forceinline__ uint32_t verify_tail(const FmxDev &ix, const Tabs<LAYOUT> &tb, Reader &rd, uint32_t rem, uint32_t &s) {
     const uint32_t mask = (1u << ix.vsa_level) - 1u;  // 0 with the dense structures: no walk
     uint32_t row = s, st = 0, sym;
     while (row & mask) {
@@ -880,36 +883,27 @@ __device__ __forceinline__ bool verify_tail(const FmxDev &ix, const Tabs<LAYOUT>
     }
     uint32_t pos = __ldg(ix.vsa + (row >> ix.vsa_level)) + st;  // < 2n < 2^32
     if (pos >= ix.n) pos -= ix.n;
-    if (pos < rem) return false;
+    if (pos < rem) return 0;
     // characters rd[rem-1], rd[rem-2], .. against text[pos-1], text[pos-2], ..
     PatReader tr(ix.text + (pos - rem), rem);
     uint32_t matched = 0;
-    while (matched < rem && rd.get(rem - 1u - matched) == tr.get(rem - 1u - matched)) matched++;
-    uint32_t r = s;
-    if (matched) {
-        const uint32_t q = pos - matched, step = 1u << ix.isa_level;
-        uint32_t q4 = (q + step - 1u) & ~(step - 1u);
-        if (q4 >= ix.n) {  // past the last sample: walk from the final suffix "\0", which is row 0
-            q4 = ix.n - 1u;
-            r = 0;
-        } else {
-            r = __ldg(ix.isa + (q4 >> ix.isa_level));
-        }
-        for (uint32_t d = q4 - q; d > 0; d--) r = lf_step<KIND, LAYOUT>(ix, tb, r, sym);
+    while (matched < rem) {
+        const uint32_t t = tr.get(rem - 1u - matched);
+        if ((KIND == FMX_KIND_MULTI_ && t == 0u) || rd.get(rem - 1u - matched) != t) break;
+        matched++;
     }
-    it += matched;
+    if (!matched) return 0;
+    const uint32_t q = pos - matched, step = 1u << ix.isa_level;
+    uint32_t q4 = (q + step - 1u) & ~(step - 1u), r;
+    if (q4 >= ix.n) {  // past the last sample: walk from the final suffix "\0", which is row 0
+        q4 = ix.n - 1u;
+        r = 0;
+    } else {
+        r = __ldg(ix.isa + (q4 >> ix.isa_level));
+    }
+    for (uint32_t d = q4 - q; d > 0; d--) r = lf_step<KIND, LAYOUT>(ix, tb, r, sym);
     s = r;
-    e = r + 1u;
-    if (matched < rem) {  // the reference's next iteration empties the range -- or hits an invalid character
-        const uint32_t c = rd.get(rem - 1u - matched);
-        if (c > ix.max_character) {
-            atomicOr(a.err, 1u);
-            return true;
-        }
-        lf_map2_pair<KIND, LAYOUT>(ix, tb, c, s, e);
-        it++;
-    }
-    return true;
+    return matched;
 }
 
 // the reference loop for one pattern (wrapper.rs:103-124), characters through `rd`
@@ -917,18 +911,28 @@ template <int KIND, int LAYOUT, class Reader>
 __device__ __forceinline__ void search_one(const FmxDev &ix, const Tabs<LAYOUT> &tb, const SearchArgs &a, Reader &rd,
                                            uint32_t len, uint32_t &s, uint32_t &e, uint32_t &it) {
     if (a.init_s == nullptr) kmer_lookup(a, ix.max_character, rd, len, s, e, it);
-    for (uint32_t k = len; k-- > 0;) {
-        if (KIND == FMX_KIND_FM_ && a.verify && e - s == 1u &&
-            k + 1u >= (ix.isa_level == 0 ? FMX_VERIFY_MIN_DENSE : FMX_VERIFY_MIN_SAMPLED)) {
-            if (verify_tail<KIND, LAYOUT>(ix, tb, a, rd, k + 1u, s, e, it)) break;
+    const uint32_t vmin = ix.isa_level == 0 ? FMX_VERIFY_MIN_DENSE : FMX_VERIFY_MIN_SAMPLED;
+    bool armed = KIND != FMX_KIND_RLFM_ && a.verify != 0;
+    uint32_t k = len;
+    while (k > 0) {
+        if (armed && e - s == 1u && k >= vmin) {
+            const uint32_t got = verify_tail<KIND, LAYOUT>(ix, tb, rd, k, s);
+            armed = got != 0;  // try again after the next ordinary step only if this attempt got somewhere
+            if (got) {
+                e = s + 1u;
+                it += got;
+                k -= got;
+                continue;
+            }
         }
-        uint32_t c = rd.get(k);
+        const uint32_t c = rd.get(k - 1u);
         if (c > ix.max_character) {  // the reference panics here (cs[c] out of bounds, fm_index.rs:94)
             atomicOr(a.err, 1u);
             break;
         }
         lf_map2_pair<KIND, LAYOUT>(ix, tb, c, s, e);
         it++;
+        k--;
         if (s == e) break;
     }
 }

@@ -207,44 +207,44 @@ class Blob:
         return 6 if self.isa_level == 0 else 10
 
     def _verify_tail(self, pat, k, s):
-        """range [s, s+1), characters pat[0:k] still to consume -> (s, e, steps executed) or None"""
+        """range [s, s+1), characters pat[0:k] still to consume -> (row, characters consumed); consumed 0 = nothing done"""
         row, st, mask = s, 0, (1 << self.vsa_level) - 1
         while row & mask:
             _, row = self.lf_step(row)
             st += 1
         pos = (int(self.vsa[row >> self.vsa_level]) + st) % self.n
         if pos < k:
-            return None
+            return s, 0
         matched = 0
-        while matched < k and pat[k - 1 - matched] == int(self.text[pos - 1 - matched]):
+        while matched < k:
+            t = int(self.text[pos - 1 - matched])
+            if (self.kind == 2 and t == 0) or pat[k - 1 - matched] != t:
+                break
             matched += 1
-        q = pos - matched
         if matched == 0:
-            r = s
+            return s, 0
+        q = pos - matched
+        step = 1 << self.isa_level
+        q4 = (q + step - 1) // step * step
+        if q4 >= self.n:
+            r, q4 = 0, self.n - 1          # the suffix "\0" is row 0
         else:
-            step = 1 << self.isa_level
-            q4 = (q + step - 1) // step * step
-            if q4 >= self.n:
-                r, q4 = 0, self.n - 1          # the suffix "\0" is row 0
-            else:
-                r = int(self.isa[q4 >> self.isa_level])
-            for _ in range(q4 - q):
-                _, r = self.lf_step(r)
-        s, e, it = r, r + 1, matched
-        if matched < k:
-            c = pat[k - 1 - matched]
-            s, e = self.lf_map2(c, s), self.lf_map2(c, e)
-            it += 1
-        return s, e, it
+            r = int(self.isa[q4 >> self.isa_level])
+        for _ in range(q4 - q):
+            _, r = self.lf_step(r)
+        return r, matched
 
-    def search_verify(self, pat):
-        """SearchWrapper::search with the verify tail; -> (s, e, steps executed)"""
-        s, e, it, k = 0, self.n, 0, len(pat)
+    def search_verify(self, pat, mode=0):
+        """SearchWrapper::search with the verify tail (search_one in kernels.cuh); -> (s, e, steps executed)"""
+        s, e, it, k = 0, (self.ndoc if mode in (2, 3) else self.n), 0, len(pat)
+        armed = bool(self.verify) and self.kind != 1
         while k > 0:
-            if self.verify and e - s == 1 and k >= self.VERIFY_MIN:
-                res = self._verify_tail(pat, k, s)
-                if res is not None:
-                    return res[0], res[1], it + res[2]
+            if armed and e - s == 1 and k >= self.VERIFY_MIN:
+                s, got = self._verify_tail(pat, k, s)
+                armed = got != 0
+                if got:
+                    e, it, k = s + 1, it + got, k - got
+                    continue
             s, e = self.lf_map2(pat[k - 1], s), self.lf_map2(pat[k - 1], e)
             it += 1
             k -= 1

@@ -442,8 +442,10 @@ def test_fixed_length_patterns_staged_in_shared_memory(m):
             assert np.array_equal(b.s, s) and np.array_equal(b.e, e), (stage, kmer)
 
 
-@pytest.mark.parametrize("mc,level,dense", [(4, 2, True), (4, None, True), (255, 1, True), (255, 3, False), (255, None, False)])
-def test_seed_and_verify_tail(mc, level, dense, monkeypatch):
+@pytest.mark.parametrize("mc,level,dense,kind", [(4, 2, True, orc.FM), (4, None, True, orc.FM), (255, 1, True, orc.FM),
+                                                 (255, 3, False, orc.FM), (255, None, False, orc.FM),
+                                                 (4, 2, True, orc.MULTI), (255, None, True, orc.MULTI)])
+def test_seed_and_verify_tail(mc, level, dense, kind, monkeypatch):
     """one-row ranges finish by locate + text comparison + sampled-ISA jump (verify_tail): SA ranges and
     executed step counts equal the oracle's plain loop -- matches, mismatches anywhere in the tail, patterns
     running off the start of the text, invalid characters inside the compared region"""
@@ -454,9 +456,11 @@ def test_seed_and_verify_tail(mc, level, dense, monkeypatch):
     n = 50_000
     sigma = min(mc, 4)
     text = np.append(rng.integers(1, sigma + 1, n, dtype=np.uint8), np.uint8(0))
-    cls = fmx.FMIndex if level is None else fmx.FMIndexWithLocate
+    if kind == orc.MULTI:
+        text[rng.integers(5, n - 5, 40) // 2 * 2] = 0     # pieces: never two \0 in a row, none at either end
+    cls = KINDS[kind][0 if level is None else 1]
     index = cls.new(fmx.Text.with_max_character(text, mc)) if level is None else cls.new(fmx.Text.with_max_character(text, mc), level)
-    oracle = orc.OracleIndex(text, orc.FM, level=level, max_character=mc)
+    oracle = orc.OracleIndex(text, kind, level=level, max_character=mc)
     pats = []
     for t in range(6000):
         m = int(rng.integers(10, 70)) if t % 7 else int(rng.integers(6, 14))
@@ -475,13 +479,14 @@ def test_seed_and_verify_tail(mc, level, dense, monkeypatch):
             pat[int(rng.integers(0, m))] = 0          # a \0 inside the pattern: valid character, never matches here
         pats.append(pat.tobytes())
     flat, off = orc.pack_patterns(pats)
-    s, e, steps = oracle.search_batch(flat, off, want_steps=True)
-    for verify in (1, 0):
-        index.set_option("verify", verify)
-        b = index.search_batch(pats)
-        assert np.array_equal(b.s, s) and np.array_equal(b.e, e), verify
-        assert index.last_work()[0] == int(steps.sum()), verify
-    if mc == 4:                                       # invalid character deep inside an otherwise unique match
+    for mode in ((fmx.SEARCH, fmx.SEARCH_PREFIX, fmx.SEARCH_SUFFIX, fmx.SEARCH_EXACT) if kind == orc.MULTI else (fmx.SEARCH,)):
+        s, e, steps = oracle.search_batch(flat, off, mode, want_steps=True)
+        for verify in (1, 0):
+            index.set_option("verify", verify)
+            b = index.search_batch(pats, mode)
+            assert np.array_equal(b.s, s) and np.array_equal(b.e, e), (mode, verify)
+            assert index.last_work()[0] == int(steps.sum()), (mode, verify)
+    if mc == 4 and kind == orc.FM:                                     # invalid character deep inside an otherwise unique match
         bad = bytearray(text[1000:1040].tobytes())
         bad[5] = 9
         with pytest.raises(IndexError):

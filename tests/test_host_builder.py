@@ -148,8 +148,8 @@ def test_fallback_layout_blobs_match_oracle(kind, env, layout, monkeypatch):
 
 
 @pytest.mark.parametrize("dense", [True, False])
-@pytest.mark.parametrize("mc,level", [(4, 2), (4, None), (255, 1), (255, 5)])
-def test_verify_structures_and_tail_logic(mc, level, dense, monkeypatch):
+@pytest.mark.parametrize("mc,level,kind", [(4, 2, 0), (4, None, 0), (255, 1, 0), (255, 5, 0), (4, 2, 2), (255, None, 2)])
+def test_verify_structures_and_tail_logic(mc, level, kind, dense, monkeypatch):
     """SEC_TEXT / SEC_ISA / verify samples of the blob, and the seed-and-verify tail arithmetic (mirrored in
     blobreader.search_verify) against the oracle's plain loop: same (s, e), same executed step count"""
     monkeypatch.setenv("FMX_VERIFY_MIN_RANK_MB", "0")    # by default only indexes beyond the L2 carry the structures
@@ -157,11 +157,14 @@ def test_verify_structures_and_tail_logic(mc, level, dense, monkeypatch):
         monkeypatch.setenv("FMX_VERIFY_BUDGET_MB", "0")   # the sampled form (what texts beyond the budget get)
     rng = np.random.default_rng(500 + mc + (level or 0))
     n = 6000
-    text = bytes(int(x) for x in rng.integers(1, min(mc, 4) + 1, n)) + b"\0"
-    b = Blob(fmx.blob_build(fmx.Text.with_max_character(text, mc), 0, level))
-    o = orc.OracleIndex(text, 0, level=level, max_character=mc)
+    body = rng.integers(1, min(mc, 4) + 1, n)
+    if kind == 2:
+        body[rng.integers(5, n - 5, 12) // 2 * 2] = 0     # pieces (never two \0 in a row, none at either end)
+    text = bytes(int(x) for x in body) + b"\0"
+    b = Blob(fmx.blob_build(fmx.Text.with_max_character(text, mc), kind, level))
+    o = orc.OracleIndex(text, kind, level=level, max_character=mc)
     sa = orc.suffix_array(text)
-    if not dense and (mc <= 4 or (level is not None and level > 3)):
+    if not dense and (kind == 2 or mc <= 4 or (level is not None and level > 3)):
         assert not b.verify                       # sampled form: only where an LF step is expensive and walks are short
         return
     assert b.verify and bytes(b.text) == text
@@ -179,16 +182,17 @@ def test_verify_structures_and_tail_logic(mc, level, dense, monkeypatch):
         if t % 7 == 0:
             m = int(rng.integers(6, 12))               # around the shortest tail the path takes
         pat = list(text[p0:p0 + m])
-        kind = t % 4
-        if kind == 1:                              # a mismatch somewhere in the tail
+        variant = t % 4
+        if variant == 1:                           # a mismatch somewhere in the tail
             j = int(rng.integers(0, m))
             pat[j] = pat[j] % min(mc, 4) + 1
-        elif kind == 2 and p0 < 40:                # runs off the start of the text
+        elif variant == 2 and t % 8 == 2:          # runs off the start of the text
             pat = [1] * 30 + list(text[:m])
-        elif kind == 3:                            # several mismatches
+        elif variant == 3:                         # several mismatches
             for j in rng.integers(0, m, 3):
                 pat[int(j)] = int(rng.integers(1, min(mc, 4) + 1))
-        s, e, it = b.search_verify(pat)
-        os_, oe, osteps = o.search_batch(*orc.pack_patterns([bytes(pat)]), want_steps=True)
-        assert (s, e) == (int(os_[0]), int(oe[0])), (t, kind)
-        assert it == int(osteps[0]), (t, kind)
+        for mode in ((0, 1, 2, 3) if kind == 2 else (0,)):
+            s, e, it = b.search_verify(pat, mode)
+            os_, oe, osteps = o.search_batch(*orc.pack_patterns([bytes(pat)]), mode, want_steps=True)
+            assert (s, e) == (int(os_[0]), int(oe[0])), (t, variant, mode)
+            assert it == int(osteps[0]), (t, variant, mode)

@@ -78,7 +78,6 @@ struct fmx_index {
     FmxBlobHeader hdr;
     FmxDev dev;
     void *d_blob = nullptr;
-    std::vector<uint8_t> host_blob;  // kept for save()
     int device = 0;
     cudaStream_t stream = nullptr;
     uint32_t *d_err = nullptr;             // [0] pattern-char error flag
@@ -270,7 +269,8 @@ static int upload(std::vector<uint8_t> &&blob, int device, fmx_index **out) {
     d.ndoc = (uint32_t)hdr.ndoc;
     d.first_row = (uint32_t)hdr.first_row;
     d.runs = (uint32_t)hdr.runs;
-    idx->host_blob = std::move(blob);
+    // the host copy of the blob is dropped here (tens of GB for the SYM / verify layouts): save() reads it back
+    std::vector<uint8_t>().swap(blob);
     cudaDeviceGetAttribute(&idx->sms, cudaDevAttrMultiProcessorCount, device);
     dispatch(idx, [&](auto K, auto LY) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&idx->persist_blocks_per_sm, k_search_steps<K(), LY()>, 256, 0);
@@ -310,11 +310,24 @@ int fmx_index_build(const void *text, uint64_t n, uint32_t char_width, uint64_t 
 
 int fmx_index_save(const fmx_index *idx, const char *path) {
     if (!idx || !path) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(idx->device));
     FILE *f = std::fopen(path, "wb");
     if (!f) return fail(FMX_ERR_IO, std::string("cannot open ") + path);
-    size_t w = std::fwrite(idx->host_blob.data(), 1, idx->host_blob.size(), f);
+    // the blob lives on the device only: stream it back through a bounded staging buffer
+    const uint64_t total = idx->hdr.total_bytes, piece = 256ull << 20;
+    std::vector<uint8_t> stage((size_t)(total < piece ? total : piece));
+    bool ok = true;
+    for (uint64_t off = 0; off < total && ok; off += piece) {
+        const uint64_t len = total - off < piece ? total - off : piece;
+        if (cudaMemcpy(stage.data(), static_cast<const uint8_t *>(idx->d_blob) + off, len, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            std::fclose(f);
+            cudaGetLastError();
+            return fail(FMX_ERR_CUDA, "index save: device to host copy failed");
+        }
+        ok = std::fwrite(stage.data(), 1, len, f) == len;
+    }
     std::fclose(f);
-    return w == idx->host_blob.size() ? FMX_OK : fail(FMX_ERR_IO, "short write");
+    return ok ? FMX_OK : fail(FMX_ERR_IO, "short write");
 }
 
 int fmx_index_load(const char *path, int device, fmx_index **out) {

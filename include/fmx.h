@@ -104,11 +104,15 @@ int fmx_build_suffix_array_device(const void *text, uint64_t n, uint32_t char_wi
  * build time), "bucket" -1|0|1 (visit the batch in k-mer bucket order: auto / never / always),
  * "l2_fetch_granularity" 32|64|128, "persist_blocks_per_sm" 1..32, "pipeline_chunk" (patterns per chunk of
  * fmx_search_locate_batch's copy/compute pipeline, 0 = automatic), "locate_refill" 0|1 (per-lane refill
- * locate kernel), "locate_expand" 0|1|2 (hit rows: auto / always expanded by scans / always found by
+ * locate kernel; 2 = stable warp-level compaction), "verify" 0|1 (seed-and-verify tail of the search),
+ * "stage_patterns" 0|1 (fixed-length pattern bytes through shared memory), "locate_expand" 0|1|2 (hit rows: auto / always expanded by scans / always found by
  * binary search inside the locate kernel), "locate_ranges" -1|0|1 (walk whole SA sub-ranges instead of
  * single rows: auto = RLFM indexes whose patterns average >= 8 matches / never / always).  Environment at construction time: FMX_FORCE_WAVELET=1
  * keeps the binary wavelet matrix; FMX_SYM_BUDGET_MB caps the per-symbol bit-vector layout (default
- * 49152; 0 = use the quaternary wavelet matrix instead). */
+ * 49152; 0 = use the quaternary wavelet matrix instead); FMX_VERIFY_BUDGET_MB caps the dense
+ * seed-and-verify structures (text + full suffix array + inverse, 9 bytes per symbol; default 32768),
+ * FMX_VERIFY_MIN_RANK_MB is the smallest rank structure they are built for (default 192: smaller ones
+ * sit in L2), FMX_NO_VERIFY=1 never builds them.  csrc/fmx_layout.h describes every structure. */
 int fmx_index_set_option(fmx_index *idx, const char *key, int64_t value);
 
 /* SearchIndex::len (frontend.rs:35-39), heap_size (:41-44, here: device bytes),

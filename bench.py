@@ -657,11 +657,16 @@ def main():
         g_pos = d_pos[0][: int(g_hoff[-1])].cpu().numpy().view(np.uint64)
         parity = bool(np.array_equal(g_s, s) and np.array_equal(g_e, e) and np.array_equal(g_hoff, ohoff)
                       and np.array_equal(g_pos, opos))
+        # the end-to-end (host-buffer) call must agree too: its CSR offsets and positions for the same sample
+        e_hoff = h_hoff[: sample + 1].numpy().view(np.uint64)
+        e_pos = h_pos[: int(e_hoff[-1])].numpy().view(np.uint64)
+        e2e_parity = bool(np.array_equal(e_hoff, ohoff) and np.array_equal(e_pos, opos))
+        parity = parity and e2e_parity
         cpu = {"value": sample / best, "unit": "queries/s", "cores": nthreads, "kind": "port",
                "sample": f"first {sample} patterns of the workload, count+locate, best of 2",
                "located_hits_per_s": int(ohoff[-1]) / best, "cpu_model": cpu_model(),
                "index_build_s": round(obuild, 1), "index_suffix_array": sa_src,
-               "gpu_matches_oracle_on_sample": parity}
+               "gpu_matches_oracle_on_sample": parity, "e2e_call_matches_oracle_on_sample": e2e_parity}
         if not parity:
             print("PARITY FAILURE: GPU results differ from the oracle on the sample", file=sys.stderr)
 

@@ -649,9 +649,23 @@ static int build_kmer_table(fmx_index *idx) {
     idx->kmer_k = k;
     idx->kmer_entries = entries;
     if (!large_text) return 0;
-    // default HBM budget of the large table: twice the index itself (FMX_KMER_BUDGET_MB overrides)
+    // default HBM budget of the large table (FMX_KMER_BUDGET_MB overrides): twice the index itself, at most
+    // 8 GiB, while the rank structure sits in L2.  Beyond L2 every step of a search is a DRAM request, and
+    // the table is sized to END the search of an absent pattern: the smallest k with sigma^k >= 4 n leaves
+    // n / sigma^k <= 1/4 expected occurrences of a random k-mer (1 GB of DNA: k = 16, 38.7 GB; measured
+    // 17.0 -> 11.6 ms per 100 M 32-mers against k = 14; the 3 GB MultiPieces config 2.03 -> 1.62 ms per 10 M).
+    // At most 40 GiB, never more than a third of the free HBM (build_big_table), and only for small alphabets:
+    // with 255 symbols one more character multiplies the table by 255 and bought 2.5 % on the byte config.
     uint64_t budget = 2 * idx->hdr.total_bytes;
-    if (budget > (8ull << 30)) budget = 8ull << 30;  // the SYM layout is large by design; the table need not follow it
+    if (budget > (8ull << 30)) budget = 8ull << 30;
+    if (idx->hdr.sec[SEC_LEVEL0].bytes >= (192ull << 20) && idx->hdr.max_character <= 16) {
+        const uint64_t base = idx->hdr.max_character, want = 4 * idx->hdr.n;
+        uint64_t entries_k = 1;
+        while (entries_k < want && entries_k <= (1ull << 32) / base) entries_k *= base;
+        uint64_t b2 = entries_k * 9;
+        if (b2 > (40ull << 30)) b2 = 40ull << 30;
+        if (b2 > budget) budget = b2;
+    }
     if (const char *v = std::getenv("FMX_KMER_BUDGET_MB")) budget = std::strtoull(v, nullptr, 10) << 20;
     return build_big_table(idx, budget);
 }

@@ -132,6 +132,28 @@ impl<'a> Search<'a> {
             piece: pid.get(k).map(|v| PieceId(*v as usize)),
         })
     }
+    /// Text positions of the matches in pages of at most `page` entries, in `iter_matches()` order, without
+    /// ever holding the whole list (fmx_locate_page): the bounded-memory form of the lazy iterator for
+    /// searches with very many matches.  Unfiltered searches only (search / search_suffix).
+    pub fn locate_pages(&'a self, page: usize) -> impl Iterator<Item = Vec<u64>> + 'a {
+        assert!(self.locate, "locate_pages() needs a ...WithLocate index");
+        assert!(self.mode == ffi::FMX_SEARCH || self.mode == ffi::FMX_SEARCH_SUFFIX, "paged locate is unfiltered");
+        let (s, e, dev) = (self.s as u64, self.e as u64, self.dev);
+        let mut first = 0u64;
+        let mut done = page == 0;
+        std::iter::from_fn(move || {
+            if done { return None; }
+            let mut buf = vec![0u64; page];
+            let mut total = 0u64;
+            check(unsafe { ffi::fmx_locate_page(dev.0, &s, &e, 1, first, page as u64, buf.as_mut_ptr(), std::ptr::null_mut(), &mut total) });
+            let got = total.saturating_sub(first).min(page as u64) as usize;
+            first += page as u64;
+            done = first >= total;
+            if got == 0 { return None; }
+            buf.truncate(got);
+            Some(buf)
+        })
+    }
 }
 
 /// Match / MatchWithLocate / MatchWithPieceId (frontend.rs:85-104 over wrapper.rs:219-248).

@@ -1,0 +1,66 @@
+"""Property tests (hypothesis) of the host builder through the CPU blob reader: whatever the alphabet, kind, sampling
+level and layout knobs, the blob's own arithmetic -- plain loop and seed-and-verify tail -- answers like the oracle.
+No GPU involved."""
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings
+from hypothesis import strategies as st
+
+import fmx_pkg
+from blobreader import Blob
+from oracle import oracle as orc
+from refutil import build_text
+
+fmx = fmx_pkg.load()
+
+ENVS = [{}, {"FMX_SYM_BUDGET_MB": "0"}, {"FMX_FORCE_WAVELET": "1"}, {"FMX_VERIFY_BUDGET_MB": "0"}]
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(seed=st.integers(0, 2**31 - 1), kind=st.sampled_from([0, 1, 2]), mc=st.sampled_from([1, 2, 4, 5, 9, 37, 255]),
+       level=st.sampled_from([None, 0, 1, 2, 3, 6]), env=st.sampled_from(ENVS), n=st.integers(2, 5000))
+def test_blob_answers_like_the_oracle(seed, kind, mc, level, env, n, monkeypatch):
+    for k in ("FMX_SYM_BUDGET_MB", "FMX_FORCE_WAVELET", "FMX_VERIFY_BUDGET_MB", "FMX_NO_VERIFY"):
+        monkeypatch.delenv(k, raising=False)
+    monkeypatch.setenv("FMX_VERIFY_MIN_RANK_MB", "0")
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(seed)
+    multi = kind == 2
+    alpha = min(mc + 1, 9) if multi else min(mc, 8)
+    if multi and alpha < 2:
+        alpha = 2
+    text = build_text(rng, n, alpha, multi)
+    if max(text) > mc:
+        return
+    try:
+        o = orc.OracleIndex(text, kind, level=level, max_character=mc)
+    except orc.InvalidText:
+        with pytest.raises(fmx.InvalidText):
+            fmx.blob_build(fmx.Text.with_max_character(text, mc), kind, level)
+        return
+    b = Blob(fmx.blob_build(fmx.Text.with_max_character(text, mc), kind, level))
+    assert (b.n, b.kind, b.cs_len) == (len(text), kind, mc + 1)
+    rows = [int(v) for v in rng.integers(0, len(text), 25)]
+    for i in rows:
+        c, nx = b.lf_step(i)
+        assert c == o.get_l(i) and nx == o.lf_map(i)
+        if level is not None:
+            assert b.get_sa(i) == o.get_sa(i)
+    pats = []
+    for _ in range(25):
+        m = int(rng.integers(1, 40))
+        p0 = int(rng.integers(0, max(1, len(text) - m)))
+        pat = bytearray(text[p0:p0 + m])
+        if rng.random() < 0.4 and len(pat):
+            pat[int(rng.integers(0, len(pat)))] = int(rng.integers(0 if multi else 1, min(mc, alpha) + 1))
+        if not multi and 0 in pat:
+            continue
+        pats.append(bytes(pat))
+    for pat in pats:
+        flat, off = orc.pack_patterns([pat])
+        for mode in ((0, 1, 2, 3) if multi else (0,)):
+            s, e, steps = o.search_batch(flat, off, mode, want_steps=True)
+            assert b.search(list(pat), mode) == (int(s[0]), int(e[0]))
+            if kind != 1:
+                assert b.search_verify(list(pat), mode) == (int(s[0]), int(e[0]), int(steps[0]))

@@ -8,6 +8,8 @@
 #include "builder.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -325,8 +327,44 @@ struct SectionData {
     uint64_t bytes = 0;
 };
 
+HostBlob::~HostBlob() { std::free(p); }
+
+int HostBlob::alloc(uint64_t bytes, bool zero) {
+    std::free(p);
+    p = static_cast<uint8_t *>(std::malloc(bytes ? bytes : 1));
+    n = p ? bytes : 0;
+    if (!p) return FMX_ERR_OOM;
+    if (zero) {
+        const uint64_t piece = 32ull << 20;
+        const int64_t np = (int64_t)((bytes + piece - 1) / piece);
+#pragma omp parallel for schedule(static)
+        for (int64_t q = 0; q < np; q++) {
+            const uint64_t lo = (uint64_t)q * piece;
+            std::memset(p + lo, 0, bytes - lo < piece ? bytes - lo : piece);
+        }
+    }
+    return 0;
+}
+
+// FMX_BUILD_TIMING=1: phase times of build_blob on stderr
+struct PhaseTimer {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    PhaseTimer() : on(false), t0(std::chrono::steady_clock::now()) {
+        const char *e = std::getenv("FMX_BUILD_TIMING");
+        on = e && e[0] && e[0] != '0';
+    }
+    void mark(const char *what) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[fmx build] %-28s %8.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level,
-               std::vector<uint8_t> &blob, std::string &err, int sa_device) {
+               HostBlob &blob, std::string &err, int sa_device) {
+    PhaseTimer tm;
     if (mc == 0 || mc > 255) {
         err = "max_character must be in 1..=255 for u8 texts";
         return FMX_ERR_INVALID_ARG;
@@ -350,6 +388,7 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
     }
     int rc = validate_text(text, n, err);
     if (rc) return rc;
+    tm.mark("validate");
 
     const uint32_t L = log2_u64(mc) + 1;  // text.rs:61-63
     const uint32_t cs_len = (uint32_t)mc + 1;
@@ -371,12 +410,14 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
         }
     }
 
+    tm.mark("suffix array");
     // BWT: bw[i] = text[sa[i]-1], 0 when sa[i] == 0 (fm_index.rs:48-55; rlfmi.rs:49-53 uses
     // text[n-1] there, which is the same \0 for every text that passes validation with n >= 2)
     std::vector<uint8_t> bwt(n);
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < (int64_t)n; i++) bwt[i] = sa[i] ? text[sa[i] - 1] : (kind == FMX_KIND_RLFM && n ? text[n - 1] : 0);
 
+    tm.mark("bwt");
     FmxBlobHeader hdr;
     std::memset(&hdr, 0, sizeof(hdr));
     hdr.magic = FMX_BLOB_MAGIC;
@@ -491,6 +532,7 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
         }
         rb_bp.finish();
     }
+    tm.mark("rank structure / runs / doc");
     if (use_q4) {
         hdr.layout = FMX_LAYOUT_QUAT;
         hdr.nexc = (uint32_t)q4.exc.size();
@@ -537,6 +579,7 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
         hdr.isa_level = isa_level;
     }
     const bool need_samples_for_verify = verify && !verify_dense;
+    tm.mark("adj / inverse suffix array");
 
     // sample.rs:21-44
     std::vector<uint32_t> samples;
@@ -556,6 +599,7 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
     hdr.vsa_level = verify_dense ? 0u : hdr.sa_level;
     if (!verify_dense) std::vector<uint32_t>().swap(sa);  // the dense verify path keeps the full array (SEC_VSA)
 
+    tm.mark("samples");
     // ---- assemble
     SectionData sec[SEC_COUNT];
     if (use_q4) {
@@ -592,8 +636,12 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
         off += (sec[k].bytes + FMX_SECTION_ALIGN - 1) / FMX_SECTION_ALIGN * FMX_SECTION_ALIGN;
     }
     hdr.total_bytes = off;
-    blob.assign(off, 0);
-    std::memcpy(blob.data(), &hdr, sizeof(hdr));
+    if (blob.alloc(off, true)) {
+        err = "out of host memory for the index blob";
+        return FMX_ERR_OOM;
+    }
+    tm.mark("allocate blob");
+    std::memcpy(blob.p, &hdr, sizeof(hdr));
     for (int k = 0; k < (int)SEC_COUNT; k++) {
         if (!sec[k].bytes || !sec[k].ptr) continue;
         const uint64_t piece = 64ull << 20;  // large sections: copy in parallel
@@ -601,10 +649,12 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
 #pragma omp parallel for schedule(static) if (np > 1)
         for (int64_t q = 0; q < np; q++) {
             uint64_t lo = (uint64_t)q * piece, len = sec[k].bytes - lo < piece ? sec[k].bytes - lo : piece;
-            std::memcpy(blob.data() + hdr.sec[k].offset + lo, static_cast<const uint8_t *>(sec[k].ptr) + lo, len);
+            std::memcpy(blob.p + hdr.sec[k].offset + lo, static_cast<const uint8_t *>(sec[k].ptr) + lo, len);
         }
     }
-    if (use_sym) sym_build(seq_ptr, hdr.seq_len, cs_len, reinterpret_cast<uint32_t *>(blob.data() + hdr.sec[SEC_LEVEL0].offset));
+    tm.mark("copy sections");
+    if (use_sym) sym_build(seq_ptr, hdr.seq_len, cs_len, reinterpret_cast<uint32_t *>(blob.p + hdr.sec[SEC_LEVEL0].offset));
+    tm.mark("per-symbol vectors");
     return 0;
 }
 

@@ -8,12 +8,30 @@
 
 namespace fmx {
 
+// The blob on the host: one malloc'd buffer (tens of GB for the SYM / verify layouts).  Zeroed by all cores at
+// once -- first touch by one thread was the largest single cost of building the byte-alphabet index.
+struct HostBlob {
+    uint8_t *p = nullptr;
+    uint64_t n = 0;
+    HostBlob() = default;
+    HostBlob(const HostBlob &) = delete;
+    HostBlob &operator=(const HostBlob &) = delete;
+    ~HostBlob();
+    int alloc(uint64_t bytes, bool zero);  // 0 or FMX_ERR_OOM
+    uint8_t *release() {
+        uint8_t *q = p;
+        p = nullptr;
+        n = 0;
+        return q;
+    }
+};
+
 // Returns 0 or a negative fmx_status; on failure `err` holds the message
 // (for invalid texts: the reference's Error::InvalidText strings, sais.rs:128-139).
 // sa_device >= 0: build the suffix array on that GPU (gpu_sa.cu) when the text is large enough,
 // otherwise with the host SA-IS.  The blob is byte-identical either way.
 int build_blob(const uint8_t *text, uint64_t n, uint64_t max_character, int kind, int level,
-               std::vector<uint8_t> &blob, std::string &err, int sa_device = -1);
+               HostBlob &blob, std::string &err, int sa_device = -1);
 
 // gpu_sa.cu
 int gpu_suffix_array(const uint8_t *text, uint64_t n, uint32_t bits, int device, uint32_t *sa_out, int *rounds_out,

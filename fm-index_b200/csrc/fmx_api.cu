@@ -181,22 +181,20 @@ int fmx_blob_build(const void *text, uint64_t n, uint32_t char_width, uint64_t m
                    void **blob, uint64_t *blob_bytes) {
     if (!blob || !blob_bytes || (!text && n)) return fail(FMX_ERR_INVALID_ARG, "null argument");
     if (char_width != 1) return fail(FMX_ERR_UNSUPPORTED, "only u8 texts (char_width == 1) are supported");
-    std::vector<uint8_t> b;
+    HostBlob b;
     std::string err;
     int rc = build_blob(static_cast<const uint8_t *>(text), n, max_character, kind, level, b, err);
     if (rc) return fail(rc, err);
-    void *p = std::malloc(b.size());
-    if (!p) return fail(FMX_ERR_OOM, "malloc blob");
-    std::memcpy(p, b.data(), b.size());
-    *blob = p;
-    *blob_bytes = b.size();
+    *blob_bytes = b.n;
+    *blob = b.release();  // malloc'd: the caller frees it with fmx_free
     return FMX_OK;
 }
 
-static int upload(std::vector<uint8_t> &&blob, int device, fmx_index **out) {
+// uploads a blob the caller owns (nothing of it is kept on the host: save() reads the device copy back)
+static int upload(const uint8_t *blob, uint64_t blob_bytes, int device, fmx_index **out) {
     FmxBlobHeader hdr;
     std::string err;
-    int rc = check_blob(blob.data(), blob.size(), hdr, err);
+    int rc = check_blob(blob, blob_bytes, hdr, err);
     if (rc) return fail(rc, err);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -208,13 +206,13 @@ static int upload(std::vector<uint8_t> &&blob, int device, fmx_index **out) {
     fmx_index *idx = new fmx_index();
     idx->hdr = hdr;
     idx->device = device;
-    cudaError_t e = cudaMalloc(&idx->d_blob, blob.size());
+    cudaError_t e = cudaMalloc(&idx->d_blob, blob_bytes);
     if (e != cudaSuccess) {
         delete idx;
         cudaGetLastError();
         return fail(FMX_ERR_OOM, std::string("cudaMalloc index: ") + cudaGetErrorString(e));
     }
-    e = cudaMemcpy(idx->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice);
+    e = cudaMemcpy(idx->d_blob, blob, blob_bytes, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&idx->d_err, 256);
     if (e == cudaSuccess) e = cudaMemset(idx->d_err, 0, 256);
@@ -269,8 +267,6 @@ static int upload(std::vector<uint8_t> &&blob, int device, fmx_index **out) {
     d.ndoc = (uint32_t)hdr.ndoc;
     d.first_row = (uint32_t)hdr.first_row;
     d.runs = (uint32_t)hdr.runs;
-    // the host copy of the blob is dropped here (tens of GB for the SYM / verify layouts): save() reads it back
-    std::vector<uint8_t>().swap(blob);
     cudaDeviceGetAttribute(&idx->sms, cudaDevAttrMultiProcessorCount, device);
     dispatch(idx, [&](auto K, auto LY) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&idx->persist_blocks_per_sm, k_search_steps<K(), LY()>, 256, 0);
@@ -287,8 +283,7 @@ static int upload(std::vector<uint8_t> &&blob, int device, fmx_index **out) {
 
 int fmx_index_from_blob(const void *blob, uint64_t blob_bytes, int device, fmx_index **out) {
     if (!blob || !out) return fail(FMX_ERR_INVALID_ARG, "null argument");
-    std::vector<uint8_t> b(static_cast<const uint8_t *>(blob), static_cast<const uint8_t *>(blob) + blob_bytes);
-    return upload(std::move(b), device, out);
+    return upload(static_cast<const uint8_t *>(blob), blob_bytes, device, out);
 }
 
 int fmx_index_build(const void *text, uint64_t n, uint32_t char_width, uint64_t max_character, int kind, int level,
@@ -301,11 +296,11 @@ int fmx_index_build(const void *text, uint64_t n, uint32_t char_width, uint64_t 
         return fail(FMX_ERR_CUDA, "no CUDA device available (the engine has no CPU fallback)");
     }
     if (device < 0 || device >= ndev) return fail(FMX_ERR_INVALID_ARG, "device ordinal out of range");
-    std::vector<uint8_t> b;
+    HostBlob b;
     std::string err;
     int rc = build_blob(static_cast<const uint8_t *>(text), n, max_character, kind, level, b, err, device);
     if (rc) return fail(rc, err);
-    return upload(std::move(b), device, out);
+    return upload(b.p, b.n, device, out);
 }
 
 int fmx_index_save(const fmx_index *idx, const char *path) {
@@ -337,11 +332,15 @@ int fmx_index_load(const char *path, int device, fmx_index **out) {
     std::fseek(f, 0, SEEK_END);
     long sz = std::ftell(f);
     std::fseek(f, 0, SEEK_SET);
-    std::vector<uint8_t> b((size_t)(sz > 0 ? sz : 0));
-    size_t r = std::fread(b.data(), 1, b.size(), f);
+    HostBlob b;
+    if (b.alloc((uint64_t)(sz > 0 ? sz : 0), false)) {
+        std::fclose(f);
+        return fail(FMX_ERR_OOM, "out of host memory reading the index file");
+    }
+    size_t r = std::fread(b.p, 1, b.n, f);
     std::fclose(f);
-    if (r != b.size()) return fail(FMX_ERR_IO, "short read");
-    return upload(std::move(b), device, out);
+    if (r != b.n) return fail(FMX_ERR_IO, "short read");
+    return upload(b.p, b.n, device, out);
 }
 
 void fmx_index_free(fmx_index *idx) {

@@ -62,6 +62,29 @@ int build_suffix_array(const uint8_t *text, uint64_t n, uint64_t *sa_out, std::s
     return 0;
 }
 
+// ascending positions i with seq[i] == 0 (the \0 terminators: few), found by all cores
+static std::vector<uint32_t> zero_positions(const uint8_t *seq, uint64_t n) {
+    const uint64_t chunk = 1ull << 22;
+    const int64_t nchunks = (int64_t)((n + chunk - 1) / chunk);
+    std::vector<std::vector<uint32_t>> part((size_t)nchunks);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t c = 0; c < nchunks; c++) {
+        const uint64_t lo = (uint64_t)c * chunk, hi = lo + chunk < n ? lo + chunk : n;
+        const uint8_t *q = seq + lo;
+        uint64_t len = hi - lo, off = 0;
+        while (off < len) {
+            const void *hit = std::memchr(q + off, 0, len - off);
+            if (!hit) break;
+            off = (uint64_t)(static_cast<const uint8_t *>(hit) - q);
+            part[(size_t)c].push_back((uint32_t)(lo + off));
+            off++;
+        }
+    }
+    std::vector<uint32_t> out;
+    for (auto &v : part) out.insert(out.end(), v.begin(), v.end());
+    return out;
+}
+
 // One rank-able bit vector in RB192 form (fmx_layout.h).
 struct RBVec {
     uint64_t nbits, nblk;
@@ -188,8 +211,7 @@ struct Q4Vec {
                 acc[c] += v;
             }
         }
-        for (uint64_t i = 0; i < n; i++)
-            if (seq[i] == 0) exc.push_back((uint32_t)i);
+        exc = zero_positions(seq, n);
     }
 };
 
@@ -318,7 +340,8 @@ static bool want_q4(uint64_t mc, const uint8_t *seq, uint64_t n) {
     if (force_binary_wavelet()) return false;
     if (mc > 4) return false;
     uint64_t zeros = 0;
-    for (uint64_t i = 0; i < n; i++) zeros += seq[i] == 0;
+#pragma omp parallel for schedule(static) reduction(+ : zeros)
+    for (int64_t i = 0; i < (int64_t)n; i++) zeros += seq[i] == 0;
     return zeros <= FMX_MAX_EXC;
 }
 
@@ -442,7 +465,14 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
 
     if (kind == FMX_KIND_FM || kind == FMX_KIND_MULTI) {
         std::vector<uint64_t> occ(cs_len, 0);
-        for (uint64_t i = 0; i < n; i++) occ[text[i]]++;
+#pragma omp parallel
+        {
+            std::vector<uint64_t> mine(cs_len, 0);
+#pragma omp for schedule(static) nowait
+            for (int64_t i = 0; i < (int64_t)n; i++) mine[text[i]]++;
+#pragma omp critical
+            for (uint32_t c = 0; c < cs_len; c++) occ[c] += mine[c];
+        }
         uint64_t sum = 0;
         for (uint32_t c = 0; c < cs_len; c++) {  // sais.rs:21-32
             cs[c] = (uint32_t)sum;
@@ -458,13 +488,11 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
         hdr.seq_len = n;
         if (kind == FMX_KIND_MULTI) {
             // multi_pieces.rs:53-79
-            for (uint64_t i = 0; i < n; i++)
-                if (text[i] == 0) piece_end.push_back((uint32_t)i);
+            piece_end = zero_positions(text, n);
             uint64_t zc = piece_end.size();
             doc.assign(zc, 0);
             uint64_t k = 0;
-            for (uint64_t p = 0; p < n; p++) {
-                if (bwt[p] != 0) continue;  // p = select(bw, k, 0)
+            for (uint32_t p : zero_positions(bwt.data(), n)) {  // p = select(bw, k, 0)
                 if (k >= zc) {               // the reference would index doc out of bounds (panic)
                     err = "text without a \\0 terminator cannot be indexed as multi-pieces";
                     return FMX_ERR_INVALID_TEXT;

@@ -2,9 +2,9 @@
 """bench.py -- count + locate throughput of the B200 FM-index query engine.
 
 One "step" = one pass of the hot path (backward search of every pattern, then locate of every
-match) over one batch of synthetic patterns.  Default workload = BASELINE.json configs[1]:
-FMIndexWithLocate, sampling level 2, 1M 32-mers (50 % sampled from the text, 50 % uniform random)
-over 100 MB synthetic DNA.  Prints ONE JSON line (see the contract in the task description).
+match) over one batch of synthetic patterns.  Default workload = the north-star target of
+BASELINE.json: FMIndexWithLocate, sampling level 2, 100M 32-mers (50 % sampled from the text, 50 %
+uniform random) over 1 GB synthetic DNA.  Prints ONE JSON line (see the contract in the task description).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
                     [--npat P] [--by-piece]
@@ -244,13 +244,30 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(workload: str, npat: int):
-    """DRAM bytes per k_search launch measured under ncu (profiles/ncu_traffic.json), scaled by batch size."""
+def source_hash():
+    """sha256 over the kernel and API sources: ties an ncu capture to the code it measured"""
+    import hashlib
+
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "fm-index_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh", ".h", ".hpp", ".cpp")):
+            h.update(name.encode())
+            h.update(open(os.path.join(d, name), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def ncu_capture(workload: str, npat: int, mode: str):
+    """Per-step DRAM bytes and L2 read requests measured under ncu (profiles/ncu_traffic.json), used ONLY when the
+    capture was taken from exactly these sources, this workload, this batch size and this index mode.
+    Nothing is scaled: a stale or mismatching capture gives None."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[workload]
-        return t["k_search_dram_bytes"] * npat / t["npat"], t
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[f"{workload}:{mode}"]
+        if t.get("source_hash") != source_hash() or int(t.get("npat", -1)) != int(npat):
+            return None
+        return t
     except Exception:
-        return None, None
+        return None
 
 
 def host_threads():
@@ -268,6 +285,48 @@ def cpu_model():
     except Exception:
         pass
     return "unknown"
+
+
+def _gpu_numa_node(torch, dev: int):
+    try:
+        pr = torch.cuda.get_device_properties(dev)
+        path = f"/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0/numa_node"
+        return int(open(path).read().strip())
+    except Exception:
+        return -1
+
+
+def _node_cores(node: int):
+    out = []
+    for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+        a, _, b = part.partition("-")
+        out += list(range(int(a), int(b or a) + 1))
+    return out
+
+
+def pin_rank_to_numa(local: int, world: int):
+    """One rank per GPU: keep the rank's threads (and the pinned buffers it first-touches) on the cores of its GPU's
+    NUMA node when the box says which that is; the ranks that share a node split its cores evenly.
+    -> number of cores this rank may use (None: affinity left alone)."""
+    try:
+        import torch
+
+        cores = sorted(os.sched_getaffinity(0))
+        nodes = [_gpu_numa_node(torch, d) for d in range(world)]
+        mine = nodes[local]
+        pool = cores
+        if mine >= 0:
+            nc = [c for c in _node_cores(mine) if c in cores]
+            if nc:
+                pool = nc
+        peers = [d for d in range(world) if nodes[d] == mine] if mine >= 0 else list(range(world))
+        share = max(1, len(pool) // max(1, len(peers)))
+        k = peers.index(local)
+        sel = pool[k * share:(k + 1) * share] or pool
+        os.sched_setaffinity(0, sel)
+        return len(sel)
+    except Exception:
+        return None
 
 
 def run_cpu_path(oracle_index, flat, off, nthreads):
@@ -299,6 +358,27 @@ def config_of(name, w, text_len, npat, extra=None):
     return cfg
 
 
+def oracle_for(w, text, device=None):
+    """The oracle's index of the workload's text.  GB-scale texts: its single-threaded SA-IS takes ~5 min per GB,
+    so -- when a GPU is there -- it is handed the GPU-built suffix array, which it VERIFIES with its own
+    linear-time checker (orc_check_suffix_array) before building everything else itself.  Construction is not the
+    measured path."""
+    from oracle import oracle as orc
+
+    sa_src = "oracle SA-IS"
+    if text.size >= (1 << 27) and device is not None:
+        import fmx_pkg
+
+        fmx = fmx_pkg.load()
+        sa, _ = fmx.suffix_array_device(text, w["mc"], device)
+        oi = orc.OracleIndex(text, w["kind"], level=w["level"], max_character=w["mc"], sa=sa)
+        del sa
+        sa_src = "GPU-built SA, verified by the oracle's linear-time checker"
+    else:
+        oi = orc.OracleIndex(text, w["kind"], level=w["level"], max_character=w["mc"])
+    return oi, sa_src
+
+
 def reference_arm(args, name, w):
     """--impl reference: the reference's CPU implementation of the path.  The crate cannot be built
     here (no Rust toolchain, vers-vecs un-vendored), so this is the oracle port of it, run on all
@@ -306,8 +386,6 @@ def reference_arm(args, name, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from oracle import oracle as orc
-
     nthreads = host_threads()
     text_t = gen_text_for(w)
     npat = args.npat or w["npat"]
@@ -315,7 +393,17 @@ def reference_arm(args, name, w):
     flat, off = host_patterns(w, text_t, sample, 4)
     text = text_t.numpy()
     t0 = time.perf_counter()
-    oracle_index = orc.OracleIndex(text, w["kind"], level=w["level"], max_character=w["mc"])
+    device = None
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            device = 0
+    except Exception:
+        device = None
+    if args.oracle_own_sa:
+        device = None
+    oracle_index, sa_src = oracle_for(w, text, device)
     build_s = time.perf_counter() - t0
     times, hits = [], 0
     for it in range(args.warmup + args.steps):
@@ -328,16 +416,124 @@ def reference_arm(args, name, w):
     line = {
         "impl": "reference", "metric": "count+locate queries/s", "value": value, "unit": "queries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32/u64 integer",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
         "data": "synthetic", "config": config_of(name, w, int(text.size), sample),
         "located_hits_per_s": hits / (ms * 1e-3),
         "cpu_baseline": {"value": value, "unit": "queries/s", "cores": nthreads, "kind": "port",
                          "sample": f"first {sample} patterns of the workload, count+locate, {args.steps} passes",
-                         "cpu_model": cpu_model(), "index_build_s": round(build_s, 1)},
+                         "cpu_model": cpu_model(), "index_build_s": round(build_s, 1), "index_suffix_array": sa_src},
         "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+PHASES = ["seed (k-mer table lookup; the whole k_search on indexes without the phased kernels)", "steps (k_ph_steps)",
+          "verify (k_ph_verify)", "steps, second pass (+ widen)", "counts + offsets scan", "emit / locate"]
+
+
+class DeviceRun:
+    """One index + one device-resident batch: the timed step and its variants, through fmx_query_batch_device."""
+
+    def __init__(self, fmx, L, index, d_pat, d_off, m, npat, stream):
+        import torch
+
+        from fm_index_b200 import _lib
+
+        self.torch, self.L, self.index, self.h = torch, L, index, index._h
+        self.d_pat, self.d_off, self.m, self.npat, self.stream = d_pat, d_off, m, npat, stream
+        self.sp = C.c_void_p(stream.cuda_stream)
+        self.Q = _lib.Query
+        self.d_cnt = torch.empty(npat, dtype=torch.int64, device="cuda")
+        self.d_hoff = torch.empty(npat + 1, dtype=torch.int64, device="cuda")
+        self.d_pos = torch.empty(1024, dtype=torch.int64, device="cuda")
+        self.cap = 1024
+        self.hits = 0
+
+    def chk(self, rc):
+        if rc != 0:
+            raise RuntimeError(self.L.fmx_last_error().decode())
+
+    def query(self, counts=False, locate=True, rows=None):
+        q = self.Q()
+        q.mode, q.packed_bits, q.patterns = 0, 0, self.d_pat.data_ptr()
+        q.pat_off = self.d_off.data_ptr() if self.d_off is not None else None
+        q.fixed_len, q.npat, q.out_width = self.m, self.npat, 8
+        if rows is not None:
+            q.out_s, q.out_e = rows[0].data_ptr(), rows[1].data_ptr()
+        if counts:
+            q.counts = self.d_cnt.data_ptr()
+        if locate:
+            q.hit_off, q.positions, q.capacity = self.d_hoff.data_ptr(), self.d_pos.data_ptr(), self.cap
+        self.chk(self.L.fmx_query_batch_device(self.h, C.byref(q), self.sp))
+
+    def size_outputs(self):
+        """first pass: learn the hit count, size the position buffer, run once more with room for every hit"""
+        torch = self.torch
+        self.query()
+        self.chk(self.L.fmx_search_check(self.h, self.sp))
+        self.hits = int(self.d_hoff[-1].item())
+        self.cap = self.hits + 1024
+        self.d_pos = torch.empty(self.cap, dtype=torch.int64, device="cuda")
+        self.query()
+        torch.cuda.synchronize()
+
+    def timed(self, fn, steps, flush, graph=True):
+        """-> (per-step ms list, launches per step, replayed as a graph?)"""
+        torch, L, stream = self.torch, self.L, self.stream
+        g, per = None, None
+        fn()
+        torch.cuda.synchronize()
+        if graph:
+            try:
+                l0 = L.fmx_launch_count()
+                gg = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gg, stream=stream):
+                    fn()
+                per = L.fmx_launch_count() - l0
+                gg.replay()
+                torch.cuda.synchronize()
+                g = gg
+            except Exception as ex:  # pragma: no cover
+                print(f"CUDA graph capture failed ({ex}); timing plain launches", file=sys.stderr)
+                torch.cuda.synchronize()
+            torch.cuda.set_stream(stream)
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(steps)]
+        l0 = L.fmx_launch_count()
+        for k in range(steps):
+            flush.zero_()  # L2 flush between timed iterations
+            ev[k][0].record(stream)
+            if g is not None:
+                g.replay()
+            else:
+                fn()
+            ev[k][1].record(stream)
+        torch.cuda.synchronize()
+        launches = (L.fmx_launch_count() - l0) / steps if g is None else per
+        return [ev[k][0].elapsed_time(ev[k][1]) for k in range(steps)], int(launches), g is not None
+
+    def phases(self, fn, flush, passes=3):
+        """live per-phase durations: CUDA events the library records between its own launches (option phase_timing)"""
+        acc = np.zeros(len(PHASES))
+        self.index.set_option("phase_timing", 1)
+        buf = (C.c_float * len(PHASES))()
+        for _ in range(passes):
+            flush.zero_()
+            fn()
+            self.chk(self.L.fmx_last_phase_ms(self.h, self.sp, buf, len(PHASES)))
+            acc += np.array(list(buf))
+        self.index.set_option("phase_timing", 0)
+        return acc / passes
+
+    def work(self, fn):
+        """one counting pass: executed search iterations, LF steps, index requests issued"""
+        self.index.set_option("count_work", 1)
+        fn()
+        a, b = self.index.last_work(self.sp)
+        r0, r1 = C.c_uint64(0), C.c_uint64(0)
+        self.chk(self.L.fmx_last_requests(self.h, self.sp, C.byref(r0), C.byref(r1)))
+        self.index.set_option("count_work", 0)
+        return a, b, r0.value, r1.value
 
 
 def main():
@@ -346,13 +542,16 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2_dna100m", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="target_dna1g", choices=sorted(WORKLOADS))
     ap.add_argument("--npat", type=int, default=0, help="override the workload's patterns per step")
     ap.add_argument("--cpu-sample", type=int, default=200_000, help="patterns in the CPU baseline sample")
     ap.add_argument("--by-piece", action="store_true", help="MultiPieces workloads: partition the pieces over the GPUs")
+    ap.add_argument("--mode", default="auto", choices=["auto", "rich", "compact"], help="index mode of the headline run")
     ap.add_argument("--option", action="append", default=[], help="key=value tuning option (fmx_index_set_option), for A/B runs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gather-peak", action="store_true")
+    ap.add_argument("--no-compact", action="store_true", help="skip the compact-mode index measured beside the headline one")
+    ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--oracle-own-sa", action="store_true",
                     help="CPU baseline: build the suffix array with the oracle's own SA-IS even for GB-scale texts")
     args = ap.parse_args()
@@ -380,6 +579,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if args.by_piece:
         return by_piece_bench(args, w, fmx, rank, world, local)
+    ncores = pin_rank_to_numa(local, world)
+    if ncores:
+        os.environ["OMP_NUM_THREADS"] = str(ncores)   # the host builder's OpenMP passes (torchrun forces 1)
 
     npat = args.npat or w["npat"]
     kind, mc, level, m = w["kind"], w["mc"], w["level"], w["m"]
@@ -397,305 +599,387 @@ def main():
     del d_text
     torch.cuda.empty_cache()
     cls = [fmx.FMIndexWithLocate, fmx.RLFMIndexWithLocate, fmx.FMIndexMultiPiecesWithLocate][kind]
+    mode_id = {"auto": fmx.MODE_AUTO, "rich": fmx.MODE_RICH, "compact": fmx.MODE_COMPACT}[args.mode]
     t0 = time.perf_counter()
-    index = cls.new(fmx.Text.with_max_character(text, mc), level, device=local)
+    index = cls.new(fmx.Text.with_max_character(text, mc), level, device=local, mode=mode_id)
     build_s = time.perf_counter() - t0
     for kv in args.option:
         k_, v_ = kv.split("=")
         index.set_option(k_, int(v_))
-    h = index._h
+    mode_name = {fmx.MODE_RICH: "rich", fmx.MODE_COMPACT: "compact"}[index.mode()]
     # a real (non-default) stream: the library launches on the stream it is handed, and the CUDA
     # events below must sit on that same stream
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-    sp = C.c_void_p(stream.cuda_stream)
     assert stream.cuda_stream != 0
-
-    d_s = torch.empty(npat, dtype=torch.int64, device="cuda")
-    d_e = torch.empty(npat, dtype=torch.int64, device="cuda")
-    d_hoff = torch.empty(npat + 1, dtype=torch.int64, device="cuda")
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-    p_off = d_off.data_ptr() if d_off is not None else None
 
-    def chk(rc):
-        if rc != 0:
-            raise RuntimeError(L.fmx_last_error().decode())
-
-    d_pos = [torch.empty(1, dtype=torch.int64, device="cuda")]
-    total = C.c_uint64(0)
-
-    def search():
-        chk(L.fmx_search_batch_device(h, 0, d_pat.data_ptr(), p_off, m, npat, None, None, d_s.data_ptr(),
-                                      d_e.data_ptr(), sp))
-
-    def locate():
-        chk(L.fmx_locate_count_device(h, 0, d_s.data_ptr(), d_e.data_ptr(), npat, d_hoff.data_ptr(), C.byref(total), sp))
-        if d_pos[0].numel() < total.value:
-            d_pos[0] = torch.empty(total.value + 1024, dtype=torch.int64, device="cuda")
-        chk(L.fmx_locate_fill_device(h, 0, d_s.data_ptr(), d_e.data_ptr(), npat, d_hoff.data_ptr(), total.value,
-                                     d_pos[0].data_ptr(), None, sp))
-
-    # first pass through the two-phase API learns the hit count (sizes the position buffer)
-    search()
-    locate()
-    chk(L.fmx_search_check(h, sp))
-    hits = total.value
-    cap_dev = int(hits) + 1024
-    if d_pos[0].numel() < cap_dev:
-        d_pos[0] = torch.empty(cap_dev, dtype=torch.int64, device="cuda")
+    run = DeviceRun(fmx, L, index, d_pat, d_off, m, npat, stream)
+    run.size_outputs()
+    hits = run.hits
 
     def step():
-        # the timed step: backward search of every pattern, then locate of every match; both calls
-        # are asynchronous (the hit total never leaves the device), so the host only enqueues
-        search()
-        chk(L.fmx_locate_batch_device(h, 0, d_s.data_ptr(), d_e.data_ptr(), npat, d_hoff.data_ptr(),
-                                      d_pos[0].data_ptr(), None, cap_dev, sp))
+        # the timed step: count + locate of every pattern, one asynchronous call (the hit total never leaves the device)
+        run.query(counts=False, locate=True)
+
+    def count_step():
+        run.query(counts=True, locate=False)
 
     for _ in range(args.warmup):
         flush.zero_()
         step()
-    search_steps, lf_steps = index.last_work(sp)
     torch.cuda.synchronize()
-    # the step is a fixed launch sequence: replay it as a CUDA graph when capture works
-    graph, launches_per_step = None, None
-    try:
-        l0 = L.fmx_launch_count()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=stream):
-            step()
-        launches_per_step = L.fmx_launch_count() - l0
-        g.replay()
-        torch.cuda.synchronize()
-        graph = g
-    except Exception as ex:  # pragma: no cover
-        print(f"CUDA graph capture failed ({ex}); timing plain launches", file=sys.stderr)
-        torch.cuda.synchronize()
-    torch.cuda.set_stream(stream)
 
     # ---- timed region (device-resident inputs)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
-    ev_s = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
     sampler = ClockSampler(local)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    launches0 = L.fmx_launch_count()
     sampler.start()
     wall0 = time.perf_counter()
-    for k in range(args.steps):
-        flush.zero_()  # L2 flush between timed iterations
-        ev[k][0].record(stream)
-        if graph is not None:
-            graph.replay()
-        else:
-            step()
-        ev[k][1].record(stream)
-    torch.cuda.synchronize()
+    t_step, launches_per_step, graphed = run.timed(step, args.steps, flush)
     wall = time.perf_counter() - wall0
-    launches = L.fmx_launch_count() - launches0 if graph is None else launches_per_step * args.steps
-    # the dominant kernel on its own (same flush, same stream): its launch duration for the roofline
-    for k in range(args.steps):
-        flush.zero_()
-        ev_s[k][0].record(stream)
-        search()
-        ev_s[k][1].record(stream)
+    t_count, _, _ = run.timed(count_step, args.steps, flush)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    t_step = np.array([ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps)])
-    t_search = np.array([ev_s[k][0].elapsed_time(ev_s[k][1]) for k in range(args.steps)])
-    ms_total = float(t_step.sum())
+    ms_total, ms_count_total = float(np.sum(t_step)), float(np.sum(t_count))
     if world > 1:
-        tt = torch.tensor([ms_total, float(t_search.sum())], device="cuda", dtype=torch.float64)
+        tt = torch.tensor([ms_total, ms_count_total], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_total, ms_search_total = [float(v) for v in tt.tolist()]
+        ms_total, ms_count_total = [float(v) for v in tt.tolist()]
         hh = torch.tensor([hits], device="cuda", dtype=torch.int64)
         dist.all_reduce(hh, op=dist.ReduceOp.SUM)
         hits_all = int(hh.item())
     else:
-        ms_search_total = float(t_search.sum())
         hits_all = hits
-    ms_locate_total = max(ms_total - ms_search_total, 0.0)
     ms_per_step = ms_total / args.steps
+    ms_count = ms_count_total / args.steps
     value = world * npat / (ms_per_step * 1e-3)
 
     # ---- end to end through the host-buffer C ABI: pinned host inputs, H2D + D2H inside the timed region
-    h_pat = torch.empty(d_pat.shape, dtype=torch.uint8).pin_memory()
-    h_pat.copy_(d_pat)
-    h_off = None
-    if d_off is not None:
-        h_off = torch.empty(npat + 1, dtype=torch.int64).pin_memory()
-        h_off.copy_(d_off)
-    h_s = torch.empty(npat, dtype=torch.int64).pin_memory()
-    h_e = torch.empty(npat, dtype=torch.int64).pin_memory()
-    h_hoff = torch.empty(npat + 1, dtype=torch.int64).pin_memory()
-    cap = int(hits) + 1024
-    h_pos = torch.empty(cap, dtype=torch.int64).pin_memory()
-    nhits = C.c_uint64(0)
-
-    def e2e_step():
-        # the call a user makes: host patterns in, SA ranges + CSR hit lists out (one fused C-ABI call)
-        # (SA ranges are internal state of the crate's Search object -- get_range is test-only,
-        # wrapper.rs:126-129 -- so the user-visible result is counts = diff(hit_off) and the positions)
-        chk(L.fmx_search_locate_batch(h, 0, h_pat.data_ptr(), None if h_off is None else h_off.data_ptr(), m, npat,
-                                      None, None, h_hoff.data_ptr(), h_pos.data_ptr(), None, cap, C.byref(nhits)))
-        return int(nhits.value)
-
-    for _ in range(2):
-        e2e_step()
-    e2e_steps = max(3, min(args.steps, 10))
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        nh = e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e = None
+    if not args.no_e2e:
+        e2e = e2e_measure(args, fmx, L, index, d_pat, d_off, m, npat, hits, mc, world, dist, torch)
     clocks = sampler.stop()
-    if world > 1:
-        tt = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_s = float(tt.item())
-    h2d = int(h_pat.numel()) + (8 * (npat + 1) if h_off is not None else 0)
-    d2h = 8 * (npat + 1) + 8 * nh
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (k_search).
-    # `achieved` follows SURVEY.md 8(d): algorithmic bytes = one 32-byte sector per wavelet-level rank probe of
-    # the REFERENCE's structure -- 32 B x 2 range ends x L levels x executed search iterations (RLFM: 2L + 3
-    # probes per lf_map2) -- divided by the kernel's measured duration.  The device layout needs fewer sectors
-    # (1 per rank for Q4 / SYM) and the k-mer tables memoise the first iterations, so this can exceed the
-    # streaming peak; the same count for the device layout, the DRAM bytes ncu measured (`traffic`) and the
-    # L2-request rate against the measured random-request peak are reported beside it.
-    Lw = int(mc).bit_length()
-    P = index.sectors_per_rank()
-    ref_per_lf2 = Lw if kind != RLFM else 2 * Lw + 3
-    dev_per_lf2 = P + (3 if kind == RLFM else 0)
+    # ---- what the step is made of, live: per-phase durations, executed work, requests issued
+    phase_ms = run.phases(step, flush)
+    search_steps, lf_steps, req_search, req_emit = run.work(step)
+    dominant = int(np.argmax(phase_ms))
     peak, peak_src = measured_peaks()
-    ms_search = ms_search_total / args.steps
-    ms_locate = max(ms_locate_total / args.steps, 1e-9)
-    alg_bytes_search = 32.0 * 2 * ref_per_lf2 * search_steps
-    dev_bytes_search = 32.0 * 2 * dev_per_lf2 * search_steps
-    alg_bytes_locate = 32.0 * ((Lw if kind != RLFM else Lw + 3) * lf_steps + hits)
-    achieved = alg_bytes_search / (ms_search * 1e-3) / 1e9
-    traffic, tsrc = ncu_traffic(args.workload, npat)
-    beyond_l2 = index.heap_size() > (400 << 20)
-    roofline = {"bound": "hbm", "kernel": "k_search", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes_search, "kernel_ms": ms_search,
-                "definition": "SURVEY.md 8(d): 32 B x 2 range ends x L wavelet levels x executed search iterations "
-                              "(RLFM: 2L+3 probes per lf_map2) / kernel duration (CUDA events on the launch stream)",
-                "reference_sectors_per_lf_map2": ref_per_lf2,
-                "device_layout": {"sectors_per_lf_map2": dev_per_lf2, "bytes_per_launch": dev_bytes_search,
-                                  "achieved": dev_bytes_search / (ms_search * 1e-3) / 1e9,
-                                  "frac": dev_bytes_search / (ms_search * 1e-3) / 1e9 / peak},
-                "note": ("index larger than L2: bound by the rate of DRAM-missing L2 requests (see random_access), "
-                         "not by bandwidth" if beyond_l2 else
-                         "index fits the 126 MB L2: bound by instruction issue / L1TEX request rate, not HBM (see traffic)")
-                        + "; frac > 1 means fewer bytes moved than the reference structure's sector model needs",
-                "executed_search_steps": int(search_steps), "executed_lf_steps": int(lf_steps),
-                "locate_kernel": {"achieved": alg_bytes_locate / (ms_locate * 1e-3) / 1e9, "phase_ms": ms_locate,
-                                  "frac": alg_bytes_locate / (ms_locate * 1e-3) / 1e9 / peak}}
-    if traffic:
-        roofline["traffic_frac_of_peak"] = traffic / (ms_search * 1e-3) / 1e9 / peak
-        roofline["traffic_source"] = tsrc.get("source")
     gp = None
     if not args.no_gather_peak:
         try:
             gp = fmx.random_gather_peak(local, nbytes=4 << 30, nloads=1 << 28, iters=3)
         except Exception as ex:  # pragma: no cover
-            roofline["random_access"] = {"error": str(ex)}
-    if gp:
-        ra = {"peak_requests_per_s": gp,
-              "how": "independent uniform-random 32 B loads over a 4 GiB buffer, best of 3 (every load is one "
-                     "DRAM-missing L2 request; profiles/r01b_random_access_study.md)"}
-        if tsrc and tsrc.get("k_search", {}).get("l2_read_requests"):
-            req = tsrc["k_search"]["l2_read_requests"] * npat / tsrc["npat"]
-            ra.update({"l2_read_requests_per_launch": req, "achieved_requests_per_s": req / (ms_search * 1e-3),
-                       "frac": req / (ms_search * 1e-3) / gp,
-                       "requests_source": "lts__t_requests_srcunit_tex_op_read.sum of the ncu capture, scaled by batch size"})
-        roofline["random_access"] = ra
+            print(f"random gather peak failed: {ex}", file=sys.stderr)
+    roofline = roofline_block(args, w, index, mode_name, npat, hits, ms_per_step, ms_count, phase_ms, dominant, search_steps,
+                              lf_steps, req_search, req_emit, peak, peak_src, gp)
+
+    # ---- the same batch on a COMPACT index (reference-sized: rank structure + samples + L2-resident table)
+    compact = None
+    if not args.no_compact and mode_name == "rich" and world == 1:
+        try:
+            compact = compact_measure(args, fmx, L, cls, text, mc, level, local, d_pat, d_off, m, npat, stream, flush, run, gp)
+        except Exception as ex:  # pragma: no cover
+            compact = {"error": str(ex)}
 
     # ---- CPU baseline beside it: the oracle port on all host threads, bounded sample; also the parity check
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        from oracle import oracle as orc
+        cpu = cpu_baseline_and_parity(args, w, text, local, run, d_pat, d_off, m, npat, e2e)
 
-        nthreads = host_threads()
-        sample = min(npat, args.cpu_sample)
-        tb = time.perf_counter()
-        sa_src = "oracle SA-IS"
-        if text.size >= (1 << 27) and not args.oracle_own_sa:
-            # GB-scale texts: the oracle's single-threaded SA-IS takes ~5 min per GB of box time.  Hand it
-            # the GPU-built suffix array instead; the oracle VERIFIES it with its own linear-time checker
-            # (orc_check_suffix_array) before using it, and builds everything else itself.
-            sa, _ = fmx.suffix_array_device(text, mc, local)
-            oracle_index = orc.OracleIndex(text, kind, level=level, max_character=mc, sa=sa)
-            del sa
-            sa_src = "GPU-built SA, verified by the oracle's linear-time checker"
-        else:
-            oracle_index = orc.OracleIndex(text, kind, level=level, max_character=mc)
-        obuild = time.perf_counter() - tb
-        if m:
-            s_flat = h_pat[:sample].numpy().reshape(-1)
-            s_off = np.arange(sample + 1, dtype=np.uint64) * np.uint64(m)
-        else:
-            s_off = h_off[: sample + 1].numpy().astype(np.uint64)
-            s_flat = h_pat.numpy()[: int(s_off[-1])]
-        best = None
-        for _ in range(2):
-            dt, s, e, ohoff, opos = run_cpu_path(oracle_index, s_flat, s_off, nthreads)
-            best = dt if best is None else min(best, dt)
-        g_s = d_s[:sample].cpu().numpy().view(np.uint64)
-        g_e = d_e[:sample].cpu().numpy().view(np.uint64)
-        g_hoff = d_hoff[: sample + 1].cpu().numpy().view(np.uint64)
-        g_pos = d_pos[0][: int(g_hoff[-1])].cpu().numpy().view(np.uint64)
-        parity = bool(np.array_equal(g_s, s) and np.array_equal(g_e, e) and np.array_equal(g_hoff, ohoff)
-                      and np.array_equal(g_pos, opos))
-        # the end-to-end (host-buffer) call must agree too: its CSR offsets and positions for the same sample
-        e_hoff = h_hoff[: sample + 1].numpy().view(np.uint64)
-        e_pos = h_pos[: int(e_hoff[-1])].numpy().view(np.uint64)
-        e2e_parity = bool(np.array_equal(e_hoff, ohoff) and np.array_equal(e_pos, opos))
-        parity = parity and e2e_parity
-        cpu = {"value": sample / best, "unit": "queries/s", "cores": nthreads, "kind": "port",
-               "sample": f"first {sample} patterns of the workload, count+locate, best of 2",
-               "located_hits_per_s": int(ohoff[-1]) / best, "cpu_model": cpu_model(),
-               "index_build_s": round(obuild, 1), "index_suffix_array": sa_src,
-               "gpu_matches_oracle_on_sample": parity, "e2e_call_matches_oracle_on_sample": e2e_parity}
-        if not parity:
-            print("PARITY FAILURE: GPU results differ from the oracle on the sample", file=sys.stderr)
-
+    if e2e is not None:
+        e2e.pop("_bytes_form_results", None)
     line = {
         "metric": "count+locate queries/s", "value": value, "unit": "queries/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u32/u64 integer", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": config_of(args.workload, w, int(text.size), npat, {
-            "index_device_bytes": index.heap_size(), "device_layout": index.layout_name(),
+            "index_mode": mode_name, "index_device_bytes": index.heap_size(), "device_layout": index.layout_name(),
+            "index_bytes_per_text_symbol": round(index.heap_size() / max(1, int(text.size)), 2),
+            "kmer_table_k": [index.kmer_k(False), index.kmer_k(True)],
             "l2": "flushed between timed iterations (512 MiB memset)",
-            "step": "fmx_search_batch_device + fmx_locate_batch_device" + (" replayed as one CUDA graph" if graph is not None else ""),
+            "step": "fmx_query_batch_device (hit offsets + positions)" + (" replayed as one CUDA graph" if graphed else ""),
             "parallelism": f"index replicated x{world}, query batches sharded", "index_build_s": round(build_s, 1),
             **({"options": args.option} if args.option else {})}),
-        "count_queries_per_s": world * npat / (ms_search_total / args.steps * 1e-3),
+        "count_queries_per_s": world * npat / (ms_count * 1e-3),
         "located_hits_per_s": hits_all / (ms_per_step * 1e-3),
         "hits_per_step": hits_all,
-        "e2e": {"value": world * npat / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_s * 1e3, "api": "fmx_search_locate_batch: host patterns in, CSR hit offsets (counts) + positions out (pinned buffers; chunked H2D/kernel/D2H pipeline)"},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches_per_step * args.steps),
         "clocks": clocks,
         "roofline": roofline,
         "wall_ms_per_step_incl_flush": wall / args.steps * 1e3,
     }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if compact is not None:
+        line["compact_mode"] = compact
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def roofline_block(args, w, index, mode_name, npat, hits, ms_step, ms_count, phase_ms, dominant, search_steps, lf_steps,
+                   req_search, req_emit, peak, peak_src, gp):
+    """What the hardware did (frac) and, separately, how much less it had to do than the reference's structure
+    (algorithmic_gain).
+
+    frac = max(DRAM bytes moved / step time / HBM peak, L2 read requests / step time / measured random-request peak).
+    DRAM bytes and L2 requests are per-step sums over the step's kernels from an ncu capture of exactly these
+    sources, this workload, batch size and index mode (profiles/ncu_traffic.json, keyed by a source hash; nothing is
+    scaled).  When no such capture exists, `traffic` is null and frac falls back to the requests the kernels counted
+    themselves (lane-level index loads, an upper bound on their L2 requests), said so in `frac_source`."""
+    kind, mc = w["kind"], w["mc"]
+    Lw = int(mc).bit_length()
+    P = index.sectors_per_rank()
+    ref_per_lf2 = Lw if kind != RLFM else 2 * Lw + 3
+    dev_per_lf2 = P + (3 if kind == RLFM else 0)
+    alg_bytes_search = 32.0 * 2 * ref_per_lf2 * search_steps
+    # locate: the reference walks to a sample (mean 2^level - 1 steps of L probes) + the sample itself
+    mean_walk = (1 << w["level"]) - 1
+    alg_bytes_locate = 32.0 * hits * ((Lw if kind != RLFM else Lw + 3) * (lf_steps / hits if lf_steps and hits else mean_walk) + 1)
+    cap = ncu_capture(args.workload, npat, mode_name)
+    t = ms_step * 1e-3
+    names = ["k_ph_seed", "k_ph_steps", "k_ph_verify", "k_ph_steps (second pass)", "scan", "k_emit_small + k_emit_big / k_locate_*"]
+    if not req_search:
+        names[0] = "k_search"
+    r = {"bound": "hbm", "kernel": names[dominant], "peak": peak, "unit": "GB/s", "peak_source": peak_src,
+         "step_ms": ms_step, "phase_ms": {PHASES[k]: round(float(phase_ms[k]), 4) for k in range(len(PHASES))},
+         "phase_ms_note": "CUDA events the library records between its own launches, separate untimed-region passes with the same L2 flush",
+         "kernel_share_of_step": float(phase_ms[dominant] / max(1e-9, float(np.sum(phase_ms))))}
+    fr_req = None
+    if gp:
+        r["random_access"] = {"peak_requests_per_s": gp,
+                              "how": "independent uniform-random 32 B loads over a 4 GiB buffer, best of 3, measured in this run "
+                                     "(every load is one DRAM- and TLB-missing L2 request; profiles/r02_random_access_study.md)"}
+    if cap:
+        traffic = float(cap["dram_bytes_per_step"])
+        reqs = float(cap["l2_read_requests_per_step"])
+        r["traffic"] = traffic
+        r["achieved"] = traffic / t / 1e9
+        fr_bw = r["achieved"] / peak
+        r["traffic_source"] = cap.get("source")
+        r["l2_read_requests_per_step"] = reqs
+        r["requests_per_pattern"] = reqs / npat
+        r["dram_bytes_per_pattern"] = traffic / npat
+        if gp:
+            fr_req = reqs / t / gp
+            r["random_access"].update({"achieved_requests_per_s": reqs / t, "frac": fr_req})
+        r["frac"] = max(fr_bw, fr_req or 0.0)
+        r["frac_source"] = "max(DRAM bytes / time / HBM peak = %.3f, L2 read requests / time / random-request peak = %s); ncu capture of these sources" % (
+            fr_bw, "%.3f" % fr_req if fr_req is not None else "n/a")
+    else:
+        r["traffic"] = None
+        issued = float(req_search + req_emit)
+        r["issued_index_requests_per_step"] = issued
+        r["requests_per_pattern"] = issued / npat if issued else None
+        est_bytes = issued * 64.0   # every index load carries .L2::64B: a miss fills 64 bytes
+        r["achieved"] = est_bytes / t / 1e9 if issued else alg_bytes_search / (ms_count * 1e-3) / 1e9
+        if issued and gp:
+            fr_req = issued / t / gp
+            r["random_access"].update({"achieved_requests_per_s": issued / t, "frac": fr_req})
+        r["frac"] = max(r["achieved"] / peak, fr_req or 0.0) if issued else None
+        r["frac_source"] = ("no ncu capture of these exact sources / batch: requests counted by the kernels themselves (lane-level index "
+                            "loads, an upper bound on L2 requests) x 64 B fills" if issued else
+                            "no ncu capture and no request counters on this path")
+    r["algorithmic_gain"] = {
+        "definition": "SURVEY.md 8(d): bytes the REFERENCE's structure would touch for the same answers -- 32 B x 2 range ends x L "
+                      "wavelet levels x executed search iterations (RLFM: 2L+3 probes per lf_map2), locate 32 B x (L x walk + 1) per "
+                      "hit -- over the step time; far above the HBM peak because the tables, the one-sector layout and the "
+                      "suffix-array structures remove most of those probes.  Not a utilisation figure.",
+        "reference_sectors_per_lf_map2": ref_per_lf2, "device_sectors_per_lf_map2": dev_per_lf2,
+        "executed_search_steps": int(search_steps), "executed_lf_steps": int(lf_steps),
+        "search_bytes": alg_bytes_search, "locate_bytes": alg_bytes_locate,
+        "GBps": (alg_bytes_search + alg_bytes_locate) / t / 1e9,
+        "x_hbm_peak": (alg_bytes_search + alg_bytes_locate) / t / 1e9 / peak}
+    return r
+
+
+def e2e_measure(args, fmx, L, index, d_pat, d_off, m, npat, hits, mc, world, dist, torch):
+    """fmx_query_batch with pinned HOST buffers: H2D of the step's patterns and D2H of its results inside the timed
+    region.  Two forms: byte patterns with 64-bit outputs (what a caller holding the crate's &[u8] patterns passes)
+    and, for alphabets of <= 4 symbols, 2-bit packed patterns with 32-bit outputs (8 B per 32-mer over PCIe)."""
+    from fm_index_b200 import _lib
+
+    h = index._h
+    out = {}
+
+    def run_form(packed):
+        W = 4 if packed else 8
+        dt = torch.int32 if packed else torch.int64
+        if packed:
+            # pack on the GPU (fmx_query's layout: character k of a pattern in bits [2k, 2k+2) of its words, as c - 1)
+            wpp = (2 * m + 63) // 64
+            shifts = (torch.arange(32, device="cuda", dtype=torch.int64) * 2)
+            h_in = torch.empty((npat, wpp), dtype=torch.int64).pin_memory()
+            chunk = 1 << 21
+            for lo in range(0, npat, chunk):
+                hi = min(npat, lo + chunk)
+                codes = torch.zeros((hi - lo, wpp * 32), dtype=torch.int64, device="cuda")
+                codes[:, :m] = d_pat[lo:hi].to(torch.int64) - 1
+                h_in[lo:hi].copy_((codes.view(hi - lo, wpp, 32) << shifts[None, None, :]).sum(dim=2))  # disjoint fields: sum == or
+                del codes
+        else:
+            h_in = torch.empty(d_pat.shape, dtype=torch.uint8).pin_memory()
+            h_in.copy_(d_pat)
+        h_off_in = None
+        if d_off is not None:
+            h_off_in = torch.empty(npat + 1, dtype=torch.int64).pin_memory()
+            h_off_in.copy_(d_off)
+        h_hoff = torch.empty(npat + 1, dtype=dt).pin_memory()
+        cap = int(hits) + 1024
+        h_pos = torch.empty(cap, dtype=dt).pin_memory()
+        q = _lib.Query()
+        q.mode, q.packed_bits, q.patterns = 0, 2 if packed else 0, h_in.data_ptr()
+        q.pat_off = h_off_in.data_ptr() if h_off_in is not None else None
+        q.fixed_len, q.npat, q.out_width = m, npat, W
+        q.hit_off, q.positions, q.capacity = h_hoff.data_ptr(), h_pos.data_ptr(), cap
+        total = C.c_uint64(0)
+
+        def call():
+            rc = L.fmx_query_batch(h, C.byref(q), C.byref(total))
+            if rc != 0:
+                raise RuntimeError(L.fmx_last_error().decode())
+            return int(total.value)
+
+        for _ in range(2):
+            call()
+        steps = max(3, min(args.steps, 10))
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            nh = call()
+        torch.cuda.synchronize()
+        sec = (time.perf_counter() - t0) / steps
+        if world > 1:
+            tt = torch.tensor([sec], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            sec = float(tt.item())
+        h2d = int(h_in.numel() * h_in.element_size()) + (8 * (npat + 1) if h_off_in is not None else 0)
+        d2h = W * (npat + 1) + W * nh
+        return {"value": world * npat / sec, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": sec * 1e3, "pcie_GBps_in": h2d / sec / 1e9, "pcie_GBps_out": d2h / sec / 1e9,
+                "_keep": (h_hoff, h_pos)}
+
+    bytes_form = run_form(False)
+    best = bytes_form
+    best_api = "fmx_query_batch: byte patterns in (1 B per character), uint64 CSR hit offsets + positions out"
+    if m and mc <= 4 and m <= 4096:
+        packed_form = run_form(True)
+        out["packed_vs_bytes"] = {"bytes_form_queries_per_s": bytes_form["value"], "bytes_form_ms": bytes_form["ms_per_step"],
+                                  "bytes_form_h2d": bytes_form["h2d_bytes_per_step"], "bytes_form_d2h": bytes_form["d2h_bytes_per_step"]}
+        best = packed_form
+        best_api = ("fmx_query_batch: 2-bit packed patterns in (fmx_query.packed_bits = 2: 8 B per 32-mer), uint32 CSR hit offsets + "
+                    "positions out")
+    keep = bytes_form.pop("_keep")
+    if best is not bytes_form:
+        best.pop("_keep")
+    out.update(best)
+    out["api"] = best_api + " (pinned buffers; chunked H2D / kernels / D2H pipeline, one host wait per chunk)"
+    out["_bytes_form_results"] = keep
+    return out
+
+
+def compact_measure(args, fmx, L, cls, text, mc, level, local, d_pat, d_off, m, npat, stream, flush, rich_run, gp):
+    """the same batch, same call, on an index built with FMX_MODE_COMPACT"""
+    import torch
+
+    t0 = time.perf_counter()
+    cidx = cls.new(fmx.Text.with_max_character(text, mc), level, device=local, mode=fmx.MODE_COMPACT)
+    build_s = time.perf_counter() - t0
+    run = DeviceRun(fmx, L, cidx, d_pat, d_off, m, npat, stream)
+    run.size_outputs()
+    same = bool(run.hits == rich_run.hits and torch.equal(run.d_hoff, rich_run.d_hoff) and
+                torch.equal(run.d_pos[: run.hits], rich_run.d_pos[: run.hits]))
+    steps = max(3, min(args.steps, 10))
+
+    def step():
+        run.query(counts=False, locate=True)
+
+    def count_step():
+        run.query(counts=True, locate=False)
+
+    t_step, launches, _ = run.timed(step, steps, flush)
+    t_count, _, _ = run.timed(count_step, steps, flush)
+    ms, msc = float(np.mean(t_step)), float(np.mean(t_count))
+    search_steps, lf_steps, _, _ = run.work(step)
+    out = {"value": npat / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms, "count_queries_per_s": npat / (msc * 1e-3),
+           "located_hits_per_s": run.hits / (ms * 1e-3), "index_device_bytes": cidx.heap_size(),
+           "index_bytes_per_text_symbol": round(cidx.heap_size() / max(1, int(text.size)), 2),
+           "kmer_table_k": [cidx.kmer_k(False), cidx.kmer_k(True)], "index_build_s": round(build_s, 1),
+           "executed_search_steps": int(search_steps), "executed_lf_steps": int(lf_steps),
+           "same_results_as_rich_index": same,
+           "what": "FMX_MODE_COMPACT: rank structure + the caller's SA samples + an L2-resident k-mer table; k_search + LF-walk locate"}
+    cap = ncu_capture(args.workload, npat, "compact")
+    if cap:
+        out["traffic"] = cap["dram_bytes_per_step"]
+        out["l2_read_requests_per_step"] = cap["l2_read_requests_per_step"]
+        out["dram_frac_of_hbm_peak"] = cap["dram_bytes_per_step"] / (ms * 1e-3) / 1e9 / measured_peaks()[0]
+        if gp:
+            out["request_frac_of_random_peak"] = cap["l2_read_requests_per_step"] / (ms * 1e-3) / gp
+    del run, cidx
+    torch.cuda.empty_cache()
+    return out
+
+
+def cpu_baseline_and_parity(args, w, text, local, run, d_pat, d_off, m, npat, e2e):
+    import torch
+
+    kind = w["kind"]
+    nthreads = host_threads()
+    sample = min(npat, args.cpu_sample)
+    tb = time.perf_counter()
+    oracle_index, sa_src = oracle_for(w, text, None if args.oracle_own_sa else local)
+    obuild = time.perf_counter() - tb
+    if m:
+        s_flat = d_pat[:sample].cpu().numpy().reshape(-1)
+        s_off = np.arange(sample + 1, dtype=np.uint64) * np.uint64(m)
+    else:
+        s_off = d_off[: sample + 1].cpu().numpy().astype(np.uint64)
+        s_flat = d_pat[: int(s_off[-1])].cpu().numpy()
+    best = None
+    for _ in range(2):
+        dt, s, e, ohoff, opos = run_cpu_path(oracle_index, s_flat, s_off, nthreads)
+        best = dt if best is None else min(best, dt)
+    # the device step's results for the sample, plus the exact SA ranges from a rows-wanted query
+    d_s = torch.empty(npat, dtype=torch.int64, device="cuda")
+    d_e = torch.empty(npat, dtype=torch.int64, device="cuda")
+    run.query(counts=True, locate=True, rows=(d_s, d_e))
+    torch.cuda.synchronize()
+    g_s = d_s[:sample].cpu().numpy().view(np.uint64)
+    g_e = d_e[:sample].cpu().numpy().view(np.uint64)
+    g_cnt = run.d_cnt[:sample].cpu().numpy().view(np.uint64)
+    g_hoff = run.d_hoff[: sample + 1].cpu().numpy().view(np.uint64)
+    g_pos = run.d_pos[: int(g_hoff[-1])].cpu().numpy().view(np.uint64)
+    parity = bool(np.array_equal(g_s, s) and np.array_equal(g_e, e) and np.array_equal(g_hoff, ohoff) and
+                  np.array_equal(g_pos, opos) and np.array_equal(g_cnt, np.where(e > s, e - s, 0)))
+    e2e_parity = None
+    if e2e is not None and "_bytes_form_results" in e2e:
+        h_hoff, h_pos = e2e.pop("_bytes_form_results")
+        e_hoff = h_hoff[: sample + 1].numpy().view(np.uint64)
+        e_pos = h_pos[: int(e_hoff[-1])].numpy().view(np.uint64)
+        e2e_parity = bool(np.array_equal(e_hoff, ohoff) and np.array_equal(e_pos, opos))
+        parity = parity and e2e_parity
+    cpu = {"value": sample / best, "unit": "queries/s", "cores": nthreads, "kind": "port",
+           "sample": f"first {sample} patterns of the workload, count+locate, best of 2",
+           "located_hits_per_s": int(ohoff[-1]) / best, "cpu_model": cpu_model(),
+           "index_build_s": round(obuild, 1), "index_suffix_array": sa_src,
+           "gpu_matches_oracle_on_sample": parity, "e2e_call_matches_oracle_on_sample": e2e_parity}
+    if not parity:
+        print("PARITY FAILURE: GPU results differ from the oracle on the sample", file=sys.stderr)
+    return cpu
 
 
 def by_piece_bench(args, w, fmx, rank, world, local):

@@ -24,10 +24,12 @@ from ._lib import load as load_library
 __all__ = [
     "Text", "Error", "InvalidText", "PieceId", "FMIndex", "FMIndexWithLocate", "RLFMIndex",
     "RLFMIndexWithLocate", "FMIndexMultiPieces", "FMIndexMultiPiecesWithLocate", "Search", "Match",
-    "SearchBatch", "load_library", "suffix_array", "random_gather_peak",
+    "SearchBatch", "load_library", "suffix_array", "random_gather_peak", "pack_patterns", "MODE_AUTO", "MODE_COMPACT",
+    "MODE_RICH",
 ]
 
 KIND_FM, KIND_RLFM, KIND_MULTI = 0, 1, 2
+MODE_AUTO, MODE_COMPACT, MODE_RICH = 0, 1, 2
 SEARCH, SEARCH_PREFIX, SEARCH_SUFFIX, SEARCH_EXACT = 0, 1, 2, 3
 _NONE = (1 << 64) - 1
 
@@ -130,7 +132,7 @@ class _Index:
     _kind = KIND_FM
     _locate = False
 
-    def __init__(self, text: Text, level=None, device=0, _handle=None):
+    def __init__(self, text: Text, level=None, device=0, _handle=None, mode=MODE_AUTO):
         L = load_library()
         self._L = L
         if _handle is not None:
@@ -145,7 +147,7 @@ class _Index:
             lvl = int(level)
         t = text.text()
         h = C.c_void_p()
-        _check(L.fmx_index_build(_ptr(t), t.size, 1, text.max_character(), self._kind, lvl, device, C.byref(h)))
+        _check(L.fmx_index_build_ex(_ptr(t), t.size, 1, text.max_character(), self._kind, lvl, device, int(mode), C.byref(h)))
         self._h = h
 
     @classmethod
@@ -221,6 +223,56 @@ class _Index:
         _check(rc)
         t = int(total.value)
         return (batch, hit_off, pos[:t].copy(), pid[:t].copy()) if piece_ids else (batch, hit_off, pos[:t].copy())
+
+    def query_batch(self, patterns, mode=SEARCH, rows=False, counts=False, locate=True, piece_ids=False, width=8,
+                    packed_bits=0, fixed_len=None, capacity=None):
+        """fmx_query_batch: count + locate of a batch in one call, byte or packed patterns, 64- or 32-bit outputs.
+        `patterns`: as for search_batch, or (packed_bits != 0) a uint64 array of packed words with `fixed_len`
+        characters per pattern (see pack_patterns).  -> dict with the requested arrays + "total"."""
+        dt = np.uint64 if width == 8 else np.uint32
+        if packed_bits:
+            words = np.ascontiguousarray(patterns, dtype=np.uint64).reshape(-1)
+            wpp = (int(fixed_len) * packed_bits + 63) // 64
+            npat, flat, off, fixed = words.size // wpp, words, None, int(fixed_len)
+        else:
+            flat, off, fixed, npat = _pack(patterns)
+        q = _lib.Query()
+        q.mode, q.packed_bits, q.patterns, q.pat_off, q.fixed_len, q.npat = mode, packed_bits, _ptr(flat), _ptr(off), fixed, npat
+        q.out_width = width
+        out = {}
+        if rows:
+            out["s"], out["e"] = np.zeros(npat, dtype=np.uint64), np.zeros(npat, dtype=np.uint64)
+            q.out_s, q.out_e = _ptr(out["s"]), _ptr(out["e"])
+        if counts:
+            out["counts"] = np.zeros(npat, dtype=dt)
+            q.counts = _ptr(out["counts"])
+        cap = 0
+        if locate or piece_ids:
+            out["hit_off"] = np.zeros(npat + 1, dtype=dt)
+            q.hit_off = _ptr(out["hit_off"])
+            cap = int(capacity) if capacity is not None else max(1024, 2 * npat)
+            if locate:
+                out["positions"] = np.zeros(cap, dtype=dt)
+                q.positions = _ptr(out["positions"])
+            if piece_ids:
+                out["piece_ids"] = np.zeros(cap, dtype=dt)
+                q.piece_ids = _ptr(out["piece_ids"])
+        q.capacity = cap
+        total = C.c_uint64(0)
+        rc = self._L.fmx_query_batch(self._h, C.byref(q), C.byref(total))
+        t = int(total.value)
+        if rc == -9 and capacity is None and t < (1 << 32 if width == 4 else 1 << 62):  # retry with exact-size buffers
+            return self.query_batch(patterns, mode, rows, counts, locate, piece_ids, width, packed_bits, fixed_len, capacity=t)
+        _check(rc)
+        for k in ("positions", "piece_ids"):
+            if k in out:
+                out[k] = out[k][:t]
+        out["total"] = t
+        return out
+
+    def mode(self):
+        """MODE_COMPACT or MODE_RICH: what the index holds (fmx_index_mode_of)"""
+        return int(self._L.fmx_index_mode_of(self._h))
 
     def locate_page(self, s, e, first_hit, nhits, piece_ids=False):
         """One page of the hit list of the ranges (s, e): hits [first_hit, first_hit + nhits) in the reference's
@@ -505,13 +557,26 @@ def suffix_array_device(text, max_character=255, device=0):
     return sa[: t.size], rounds.value
 
 
-def blob_build(text: Text, kind, level=None) -> np.ndarray:
+def pack_patterns(patterns, bits=2) -> np.ndarray:
+    """[npat, m] characters 1..2^bits -> packed words as fmx_query wants them: pattern p occupies
+    ceil(m * bits / 64) uint64 words, character k in bits [k*bits, (k+1)*bits) of that stream, stored as c - 1."""
+    p = np.ascontiguousarray(patterns, dtype=np.uint8)
+    npat, m = p.shape
+    per = 64 // bits
+    wpp = (m + per - 1) // per
+    codes = np.zeros((npat, wpp * per), dtype=np.uint64)
+    codes[:, :m] = p.astype(np.uint64) - 1
+    shifts = (np.arange(per, dtype=np.uint64) * np.uint64(bits))[None, None, :]
+    return np.bitwise_or.reduce(codes.reshape(npat, wpp, per) << shifts, axis=2).reshape(-1)
+
+
+def blob_build(text: Text, kind, level=None, mode=MODE_AUTO) -> np.ndarray:
     """Host-only half of construction: the device-layout blob as bytes."""
     L = load_library()
     t = text.text()
     p, nb = C.c_void_p(), C.c_uint64(0)
-    _check(L.fmx_blob_build(_ptr(t), t.size, 1, text.max_character(), kind, -1 if level is None else level,
-                            C.byref(p), C.byref(nb)))
+    _check(L.fmx_blob_build_ex(_ptr(t), t.size, 1, text.max_character(), kind, -1 if level is None else level, int(mode),
+                               C.byref(p), C.byref(nb)))
     a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(nb.value,)).copy()
     L.fmx_free(p)
     return a

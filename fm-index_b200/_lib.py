@@ -17,7 +17,10 @@ SIGNATURES = {
     "fmx_device_count": (_int, []),
     "fmx_free": (None, [_vp]),
     "fmx_index_build": (_int, [_vp, _u64, _u32, _u64, _int, _int, _int, _pp]),
+    "fmx_index_build_ex": (_int, [_vp, _u64, _u32, _u64, _int, _int, _int, _int, _pp]),
+    "fmx_index_mode_of": (_int, [_vp]),
     "fmx_blob_build": (_int, [_vp, _u64, _u32, _u64, _int, _int, _pp, _u64p]),
+    "fmx_blob_build_ex": (_int, [_vp, _u64, _u32, _u64, _int, _int, _int, _pp, _u64p]),
     "fmx_index_from_blob": (_int, [_vp, _u64, _int, _pp]),
     "fmx_index_save": (_int, [_vp, C.c_char_p]),
     "fmx_index_load": (_int, [C.c_char_p, _int, _pp]),
@@ -41,6 +44,8 @@ SIGNATURES = {
     "fmx_search_check": (_int, [_vp, _vp]),
     "fmx_locate_batch": (_int, [_vp, _int, _vp, _vp, _u64, _vp, _pp, _pp]),
     "fmx_search_locate_batch": (_int, [_vp, _int, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _u64, _u64p]),
+    "fmx_query_batch": (_int, [_vp, _vp, _u64p]),
+    "fmx_query_batch_device": (_int, [_vp, _vp, _vp]),
     "fmx_locate_count_device": (_int, [_vp, _int, _vp, _vp, _u64, _vp, _u64p, _vp]),
     "fmx_locate_fill_device": (_int, [_vp, _int, _vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp]),
     "fmx_locate_page": (_int, [_vp, _vp, _vp, _u64, _u64, _u64, _vp, _vp, _u64p]),
@@ -51,9 +56,21 @@ SIGNATURES = {
     "fmx_rows_op": (_int, [_vp, _int, _vp, _u64, _vp]),
     "fmx_lf_map2_batch": (_int, [_vp, _vp, _vp, _u64, _vp]),
     "fmx_last_work": (_int, [_vp, _vp, _u64p, _u64p]),
+    "fmx_last_requests": (_int, [_vp, _vp, _u64p, _u64p]),
+    "fmx_last_phase_ms": (_int, [_vp, _vp, C.POINTER(C.c_float), _int]),
     "fmx_random_gather_bench": (_int, [_int, _u64, _u64, _int, _u32, C.POINTER(C.c_double)]),
     "fmx_launch_count": (_u64, []),
 }
+
+
+
+class Query(C.Structure):
+    """struct fmx_query (include/fmx.h)"""
+    _fields_ = [("mode", C.c_int), ("packed_bits", C.c_uint32), ("patterns", C.c_void_p), ("pat_off", C.c_void_p),
+                ("fixed_len", C.c_uint64), ("npat", C.c_uint64), ("out_width", C.c_uint32), ("reserved", C.c_uint32),
+                ("out_s", C.c_void_p), ("out_e", C.c_void_p), ("counts", C.c_void_p), ("hit_off", C.c_void_p),
+                ("positions", C.c_void_p), ("piece_ids", C.c_void_p), ("capacity", C.c_uint64)]
+
 
 _lib = None
 

@@ -386,8 +386,17 @@ struct PhaseTimer {
 };
 
 int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level,
-               HostBlob &blob, std::string &err, int sa_device) {
+               HostBlob &blob, std::string &err, int sa_device, int mode) {
     PhaseTimer tm;
+    if (mode == FMX_MODE_AUTO) {
+        const char *m = std::getenv("FMX_MODE");
+        if (m && !std::strcmp(m, "compact")) mode = FMX_MODE_COMPACT;
+        else if (m && !std::strcmp(m, "rich")) mode = FMX_MODE_RICH;
+    }
+    if (mode < FMX_MODE_AUTO || mode > FMX_MODE_RICH) {
+        err = "unknown index mode";
+        return FMX_ERR_INVALID_ARG;
+    }
     if (mc == 0 || mc > 255) {
         err = "max_character must be in 1..=255 for u8 texts";
         return FMX_ERR_INVALID_ARG;
@@ -582,10 +591,17 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
     // seed-and-verify structures (fmx_layout.h): dense (full SA + full ISA) within the budget, else sampled
     // for the SYM layout (text, ISA every 4 positions, SA samples of level <= 3), else none
     std::vector<uint32_t> isa_s;
-    bool verify = (kind == FMX_KIND_FM || kind == FMX_KIND_MULTI) && n >= 4096, verify_dense = false;
+    bool verify = (kind == FMX_KIND_FM || kind == FMX_KIND_MULTI) && n >= (mode == FMX_MODE_RICH ? 64u : 4096u), verify_dense = false;
+    // A single-text index (FM, RLFM) over a text with INTERIOR zeros: the reference's lf_map2(0, i) = cs[0] + rank(i, 0)
+    // (fm_index.rs:93-95) is not the true LF row there, so neither its walks nor its searches agree with the
+    // suffix array; the structures that answer from the suffix array are not built for such texts.
+    bool interior_zero = false;
+    if (kind != FMX_KIND_MULTI && n >= 2) interior_zero = std::memchr(text, 0, n - 1) != nullptr;
+    bool dense_sa = false;  // SEC_VSA: the full suffix array (verify path; HBM-rich locate)
     {
         const char *nv = std::getenv("FMX_NO_VERIFY");
         if (nv && nv[0] && nv[0] != '0') verify = false;
+        if (mode == FMX_MODE_COMPACT || interior_zero) verify = false;
         uint64_t budget = 32768ull << 20;
         if (const char *vb = std::getenv("FMX_VERIFY_BUDGET_MB")) budget = std::strtoull(vb, nullptr, 10) << 20;
         // an index whose rank structure sits in the 126 MB L2 answers a step from L2; the tail's three or four
@@ -593,9 +609,13 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
         uint64_t min_rank = 192ull << 20;
         if (const char *mr = std::getenv("FMX_VERIFY_MIN_RANK_MB")) min_rank = std::strtoull(mr, nullptr, 10) << 20;
         const uint64_t rank_bytes = use_q4 ? (n / 64 + 1) * 32 : (use_sym ? sym_bytes(cs_len, n) : (uint64_t)L * (n / FMX_RB_BITS + 1) * 32);
-        if (rank_bytes < min_rank) verify = false;
+        if (rank_bytes < min_rank && mode != FMX_MODE_RICH) verify = false;
         verify_dense = verify && 9 * n <= budget;
         if (verify && !verify_dense) verify = kind == FMX_KIND_FM && use_sym && (level < 0 || level <= 3);
+        dense_sa = verify_dense;
+        // RLFM in the HBM-rich mode: no verify tail (its ranges rarely narrow to one row), but locate by the
+        // resident suffix array
+        if (kind == FMX_KIND_RLFM && mode == FMX_MODE_RICH && level >= 0 && !interior_zero && n >= 64 && 4 * n <= budget) dense_sa = true;
     }
     const uint32_t isa_level = verify_dense ? 0u : 2u;
     if (verify) {
@@ -625,7 +645,8 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
         }
     }
     hdr.vsa_level = verify_dense ? 0u : hdr.sa_level;
-    if (!verify_dense) std::vector<uint32_t>().swap(sa);  // the dense verify path keeps the full array (SEC_VSA)
+    hdr.reserved[0] = (uint64_t)mode;
+    if (!dense_sa) std::vector<uint32_t>().swap(sa);  // the dense paths keep the full array (SEC_VSA)
 
     tm.mark("samples");
     // ---- assemble
@@ -647,8 +668,8 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
     if (verify) {
         sec[SEC_TEXT] = {text, n};
         sec[SEC_ISA] = {isa_s.data(), isa_s.size() * 4};
-        if (verify_dense) sec[SEC_VSA] = {sa.data(), sa.size() * 4};
     }
+    if (dense_sa) sec[SEC_VSA] = {sa.data(), sa.size() * 4};
     if (!doc.empty()) sec[SEC_DOC] = {doc.data(), doc.size() * 4};
     if (!piece_end.empty()) sec[SEC_PIECE_END] = {piece_end.data(), piece_end.size() * 4};
     if (kind == FMX_KIND_RLFM) {
@@ -696,17 +717,58 @@ int check_blob(const void *blob, uint64_t bytes, FmxBlobHeader &hdr, std::string
         err = "not an fmx blob (bad magic or version)";
         return FMX_ERR_INVALID_ARG;
     }
-    if (hdr.total_bytes != bytes || hdr.levels == 0 || hdr.levels > FMX_MAX_LEVELS || hdr.kind > 2 || hdr.layout > 3 || hdr.qlevels > FMX_MAX_QLEVELS ||
-        hdr.nexc > FMX_MAX_EXC) {
-        err = "corrupt fmx blob header";
+    auto bad = [&](const char *what) {
+        err = std::string("corrupt fmx blob: ") + what;
         return FMX_ERR_INVALID_ARG;
-    }
+    };
+    if (hdr.total_bytes != bytes) return bad("total size");
+    if (hdr.levels == 0 || hdr.levels > FMX_MAX_LEVELS || hdr.kind > 2 || hdr.layout > 3 || hdr.qlevels > FMX_MAX_QLEVELS ||
+        hdr.nexc > FMX_MAX_EXC)
+        return bad("header");
+    // the kernels copy cs_len + 1 words into shared tables of 256 / 257 entries and index rows with u32
+    if (hdr.max_character == 0 || hdr.max_character > 255 || hdr.cs_len != hdr.max_character + 1) return bad("alphabet");
+    if (hdr.levels != 64u - (uint32_t)__builtin_clzll((uint64_t)hdr.max_character)) return bad("levels");
+    if (hdr.n >= 0xFFFFFFFFull || hdr.seq_len > hdr.n || hdr.runs > hdr.n || hdr.ndoc > hdr.n) return bad("lengths");
+    if (hdr.sa_level >= 32 || hdr.isa_level >= 32 || hdr.vsa_level >= 32) return bad("sampling levels");
+    if (hdr.kind == FMX_KIND_RLFM ? hdr.seq_len != hdr.runs : hdr.seq_len != hdr.n) return bad("sequence length");
+    if (hdr.reserved[0] > FMX_MODE_RICH) return bad("mode");
     for (int k = 0; k < (int)SEC_COUNT; k++) {
-        if (hdr.sec[k].bytes && (hdr.sec[k].offset % FMX_SECTION_ALIGN || hdr.sec[k].offset + hdr.sec[k].bytes > bytes)) {
-            err = "corrupt fmx blob section table";
-            return FMX_ERR_INVALID_ARG;
-        }
+        const uint64_t o = hdr.sec[k].offset, b = hdr.sec[k].bytes;
+        if (b && (o % FMX_SECTION_ALIGN || o < sizeof(FmxBlobHeader) || b > bytes || o > bytes - b)) return bad("section table");
     }
+    auto need = [&](int k, uint64_t min_bytes) { return hdr.sec[k].bytes >= min_bytes; };
+    const uint64_t n = hdr.n, len = hdr.seq_len;
+    if (!need(SEC_CS, (uint64_t)(hdr.cs_len + 1) * 4) || !need(SEC_ADJ, (uint64_t)hdr.cs_len * 4)) return bad("cs / adj");
+    if (hdr.layout == FMX_LAYOUT_QUAT) {
+        if (hdr.max_character > 4 || !need(SEC_LEVEL0, (len / 64 + 1) * 32) || (hdr.nexc && !need(SEC_EXC, (uint64_t)hdr.nexc * 4))) return bad("Q4 level");
+    } else if (hdr.layout == FMX_LAYOUT_SYM) {
+        if (hdr.sym_nblk != len / FMX_RB_BITS + 1 || !need(SEC_LEVEL0, (uint64_t)hdr.cs_len * hdr.sym_nblk * 32) || !need(SEC_LEVEL0 + 1, len))
+            return bad("SYM vectors");
+    } else if (hdr.layout == FMX_LAYOUT_WM4) {
+        if (hdr.qlevels != (hdr.levels + 1) / 2) return bad("WM4 levels");
+        for (uint32_t l = 0; l < hdr.qlevels; l++) {
+            if (!need(SEC_LEVEL0 + l, (len / 64 + 1) * 32)) return bad("WM4 level");
+            for (int d = 0; d < 4; d++)
+                if (hdr.qoff[l][d] > len) return bad("WM4 offsets");
+        }
+    } else {
+        for (uint32_t l = 0; l < hdr.levels; l++)
+            if (!need(SEC_LEVEL0 + l, (len / FMX_RB_BITS + 1) * 32) || hdr.zeros[l] > len) return bad("wavelet level");
+    }
+    if (hdr.has_locate || hdr.sec[SEC_SA].bytes) {
+        if (n && (hdr.sa_count != ((n - 1) >> hdr.sa_level) + 1 || !need(SEC_SA, hdr.sa_count * 4))) return bad("suffix-array samples");
+    }
+    if (hdr.kind == FMX_KIND_MULTI && (!need(SEC_DOC, hdr.ndoc * 4) || !need(SEC_PIECE_END, hdr.ndoc * 4) || hdr.first_row >= (n ? n : 1)))
+        return bad("pieces");
+    if (hdr.kind == FMX_KIND_RLFM && (!need(SEC_RL_B, (n / FMX_RB_BITS + 1) * 32) || !need(SEC_RL_BP, (n / FMX_RB_BITS + 1) * 32) ||
+                                      !need(SEC_RL_BSEL, (hdr.runs + 1) * 4) || !need(SEC_RL_BPSEL, (hdr.runs + 1) * 4)))
+        return bad("run-length sections");
+    if (hdr.verify) {
+        if (!n || !need(SEC_TEXT, n) || !need(SEC_ISA, (((n - 1) >> hdr.isa_level) + 1) * 4)) return bad("verify sections");
+        if (hdr.vsa_level == 0 && !need(SEC_VSA, n * 4)) return bad("verify suffix array");
+        if (hdr.vsa_level != 0 && !hdr.sec[SEC_SA].bytes) return bad("verify samples");
+    }
+    if (hdr.sec[SEC_VSA].bytes && !need(SEC_VSA, n * 4)) return bad("dense suffix array");
     return 0;
 }
 

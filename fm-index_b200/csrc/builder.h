@@ -30,8 +30,9 @@ struct HostBlob {
 // (for invalid texts: the reference's Error::InvalidText strings, sais.rs:128-139).
 // sa_device >= 0: build the suffix array on that GPU (gpu_sa.cu) when the text is large enough,
 // otherwise with the host SA-IS.  The blob is byte-identical either way.
+// mode: FMX_MODE_AUTO / _COMPACT / _RICH (include/fmx.h)
 int build_blob(const uint8_t *text, uint64_t n, uint64_t max_character, int kind, int level,
-               HostBlob &blob, std::string &err, int sa_device = -1);
+               HostBlob &blob, std::string &err, int sa_device = -1, int mode = 0);
 
 // gpu_sa.cu
 int gpu_suffix_array(const uint8_t *text, uint64_t n, uint32_t bits, int device, uint32_t *sa_out, int *rounds_out,

@@ -12,6 +12,7 @@
 #include "../../include/fmx.h"
 #include "builder.h"
 #include "kernels.cuh"
+#include "phased.cuh"
 
 using namespace fmx;
 
@@ -63,7 +64,7 @@ struct DevBuf {
 };
 
 enum { B_QUEUE, B_BUCKET, B_BHIST, B_ORDER, B_PAT, B_OFF, B_S, B_E, B_INS, B_INE, B_CNT, B_HOFF, B_OWNER, B_ROWS, B_ROWS2, B_FLAG, B_FPOS, B_TILES, B_POS, B_PID,
-       B_OUT8, B_OUT32, B_COUNT };
+       B_OUT8, B_OUT32, B_RS, B_RE, B_HINT, B_QS, B_QV, B_QN, B_BIGQ, B_W64, B_COUNT };
 
 // one lane of the chunked H2D / kernels / D2H pipeline (fmx_search_locate_batch)
 #define FMX_LANES 4
@@ -72,6 +73,19 @@ struct Lane {
     cudaStream_t st = nullptr;
     cudaEvent_t ev = nullptr;
     uint64_t *h_total = nullptr;  // pinned
+    uint64_t pos_cap = 0;         // entries the lane's position buffers were sized for when the chunk was emitted
+};
+
+#define FMX_NPHASE 6  /* seed, steps, verify, steps2 (+ widen), offsets (counts + scan), emit / locate */
+
+// what fmx_locate_count_device left behind for the fmx_locate_fill_device call that completes it
+struct CountToken {
+    bool valid = false;
+    int prefix_only = 0;
+    uint64_t npat = 0, total = 0;
+    const uint64_t *d_s = nullptr, *d_hit_off = nullptr;
+    const uint32_t *rows = nullptr;
+    bool ranges = false;
 };
 
 struct fmx_index {
@@ -103,10 +117,19 @@ struct fmx_index {
     int opt_locate_expand = 0;        // 0 auto, 1 always expand the rows first, 2 always binary-search in k_locate
     int opt_locate_refill = 0;        // 1: per-lane refill k_locate (lost the A/B: it breaks the coalescing of adjacent rows)
     int opt_bucket = 0;               // 1: visit the batch in k-mer bucket order (lost the A/B, kept for experiments); -1 auto
+    int opt_count_work = 0;           // 1: kernels count executed search iterations / LF steps (fmx_last_work)
+    int opt_phased = 1;               // 0: one-kernel k_search even when the dense verify structures exist (A/B)
+    int opt_locate_dense = 1;         // 0: LF walks to the samples even when the full suffix array is resident (A/B)
+    uint32_t tab_embed = 0;           // one-row k-mer table entries carry the row's text position (SearchArgs::tab_embed)
     mutable DevBuf buf[B_COUNT];
     mutable Lane lane[FMX_LANES];
     mutable bool lanes_ready = false;
     mutable std::mutex mu;
+    mutable CountToken count_token;
+    // option "phase_timing": CUDA events between the phases of a query (fmx_last_phase_ms)
+    int opt_phase_timing = 0;
+    mutable cudaEvent_t pev[FMX_NPHASE + 1] = {};
+    mutable uint32_t pev_mask = 0;
 };
 
 static int build_kmer_table(fmx_index *idx);
@@ -116,6 +139,20 @@ static inline cudaStream_t pick_stream(const fmx_index *idx, void *stream) {
     return stream ? reinterpret_cast<cudaStream_t>(stream) : idx->stream;
 }
 static inline unsigned grid_for(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+// phase boundary k (0 = start of the query) on the query's stream; only with option "phase_timing"
+static void phase_mark(const fmx_index *idx, int k, cudaStream_t st) {
+    if (!idx->opt_phase_timing) return;
+    if (!idx->pev[k] && cudaEventCreate(&idx->pev[k]) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    if (k == 0) idx->pev_mask = 0;
+    if (cudaEventRecord(idx->pev[k], st) == cudaSuccess) idx->pev_mask |= 1u << k;
+    else cudaGetLastError();
+}
+// the full suffix array is resident (SEC_VSA): HBM-rich locate, position = SA[row]
+static inline bool has_dense_sa(const fmx_index *idx) { return idx->hdr.sec[SEC_VSA].bytes != 0 && idx->dev.vsa != nullptr; }
+static inline bool locate_dense(const fmx_index *idx) { return has_dense_sa(idx) && idx->opt_locate_dense && idx->hdr.has_locate; }
 
 // run f(K, LY) with the index's (kind, layout) as compile-time constants
 template <class F>
@@ -177,17 +214,22 @@ int fmx_build_suffix_array_device(const void *text, uint64_t n, uint32_t char_wi
     return FMX_OK;
 }
 
-int fmx_blob_build(const void *text, uint64_t n, uint32_t char_width, uint64_t max_character, int kind, int level,
-                   void **blob, uint64_t *blob_bytes) {
+int fmx_blob_build_ex(const void *text, uint64_t n, uint32_t char_width, uint64_t max_character, int kind, int level,
+                      int mode, void **blob, uint64_t *blob_bytes) {
     if (!blob || !blob_bytes || (!text && n)) return fail(FMX_ERR_INVALID_ARG, "null argument");
     if (char_width != 1) return fail(FMX_ERR_UNSUPPORTED, "only u8 texts (char_width == 1) are supported");
     HostBlob b;
     std::string err;
-    int rc = build_blob(static_cast<const uint8_t *>(text), n, max_character, kind, level, b, err);
+    int rc = build_blob(static_cast<const uint8_t *>(text), n, max_character, kind, level, b, err, -1, mode);
     if (rc) return fail(rc, err);
     *blob_bytes = b.n;
     *blob = b.release();  // malloc'd: the caller frees it with fmx_free
     return FMX_OK;
+}
+
+int fmx_blob_build(const void *text, uint64_t n, uint32_t char_width, uint64_t max_character, int kind, int level,
+                   void **blob, uint64_t *blob_bytes) {
+    return fmx_blob_build_ex(text, n, char_width, max_character, kind, level, FMX_MODE_AUTO, blob, blob_bytes);
 }
 
 // uploads a blob the caller owns (nothing of it is kept on the host: save() reads the device copy back)
@@ -251,8 +293,9 @@ static int upload(const uint8_t *blob, uint64_t blob_bytes, int device, fmx_inde
     d.text = static_cast<const uint8_t *>(sec(SEC_TEXT));
     d.isa = static_cast<const uint32_t *>(sec(SEC_ISA));
     d.vsa = hdr.sec[SEC_VSA].bytes ? static_cast<const uint32_t *>(sec(SEC_VSA)) : d.sa;
-    d.vsa_level = hdr.vsa_level;
+    d.vsa_level = hdr.sec[SEC_VSA].bytes ? 0u : hdr.vsa_level;
     d.verify = hdr.verify && d.text && d.isa && d.vsa ? 1u : 0u;
+    idx->tab_embed = (d.verify && hdr.sec[SEC_VSA].bytes && hdr.isa_level == 0 && hdr.n < (1ull << 31)) ? 1u : 0u;
     d.isa_level = hdr.isa_level;
     d.layout = hdr.layout;
     d.nexc = hdr.nexc;
@@ -288,6 +331,16 @@ int fmx_index_from_blob(const void *blob, uint64_t blob_bytes, int device, fmx_i
 
 int fmx_index_build(const void *text, uint64_t n, uint32_t char_width, uint64_t max_character, int kind, int level,
                     int device, fmx_index **out) {
+    return fmx_index_build_ex(text, n, char_width, max_character, kind, level, device, FMX_MODE_AUTO, out);
+}
+
+int fmx_index_mode_of(const fmx_index *idx) {
+    if (!idx) return -1;
+    return (idx->hdr.verify || idx->hdr.sec[SEC_VSA].bytes) ? FMX_MODE_RICH : FMX_MODE_COMPACT;
+}
+
+int fmx_index_build_ex(const void *text, uint64_t n, uint32_t char_width, uint64_t max_character, int kind, int level,
+                       int device, int mode, fmx_index **out) {
     if (!out || (!text && n)) return fail(FMX_ERR_INVALID_ARG, "null argument");
     if (char_width != 1) return fail(FMX_ERR_UNSUPPORTED, "only u8 texts (char_width == 1) are supported");
     int ndev = 0;
@@ -298,7 +351,7 @@ int fmx_index_build(const void *text, uint64_t n, uint32_t char_width, uint64_t 
     if (device < 0 || device >= ndev) return fail(FMX_ERR_INVALID_ARG, "device ordinal out of range");
     HostBlob b;
     std::string err;
-    int rc = build_blob(static_cast<const uint8_t *>(text), n, max_character, kind, level, b, err, device);
+    int rc = build_blob(static_cast<const uint8_t *>(text), n, max_character, kind, level, b, err, device, mode);
     if (rc) return fail(rc, err);
     return upload(b.p, b.n, device, out);
 }
@@ -360,6 +413,8 @@ void fmx_index_free(fmx_index *idx) {
     if (idx->d_big_tab) cudaFree(idx->d_big_tab);
     if (idx->d_big_steps) cudaFree(idx->d_big_steps);
     if (idx->stream) cudaStreamDestroy(idx->stream);
+    for (auto &e : idx->pev)
+        if (e) cudaEventDestroy(e);
     delete idx;
 }
 
@@ -380,6 +435,10 @@ int fmx_index_set_option(fmx_index *idx, const char *key, int64_t value) {
     else if (k == "verify") idx->opt_verify = value != 0;
     else if (k == "locate_ranges") idx->opt_locate_ranges = value < 0 ? -1 : (value != 0);
     else if (k == "bucket") idx->opt_bucket = value < 0 ? -1 : (value != 0);
+    else if (k == "count_work") idx->opt_count_work = value != 0;
+    else if (k == "search_phased") idx->opt_phased = value != 0;
+    else if (k == "locate_dense") idx->opt_locate_dense = value != 0;
+    else if (k == "phase_timing") idx->opt_phase_timing = value != 0;
     else if (k == "pipeline_chunk") idx->opt_pipeline_chunk = value > 0 ? (uint64_t)value : 0;
     else if (k == "l2_fetch_granularity") {
         if (value != 32 && value != 64 && value != 128) return fail(FMX_ERR_INVALID_ARG, "l2_fetch_granularity must be 32, 64 or 128");
@@ -583,6 +642,7 @@ static int build_one_table(fmx_index *idx, uint32_t k, uint64_t entries, bool ac
             a.kmer_tab = idx->d_kmer_tab;
             a.kmer_steps = idx->d_kmer_steps;
             a.kmer_k = idx->kmer_k;
+            a.tab_embed = idx->tab_embed;  // the small table was embedded when it was built
         }
         rc = dispatch_search(idx, a, st, true);
         if (rc) break;
@@ -593,6 +653,11 @@ static int build_one_table(fmx_index *idx, uint32_t k, uint64_t entries, bool ac
     cudaFree(d_pat);
     cudaFree(d_s);
     cudaFree(d_e);
+    if (rc == 0 && idx->tab_embed) {  // one-row entries: y = FLAG | SA[s] (phased.cuh)
+        k_table_embed<<<grid_for(entries, 256), 256, 0, st>>>(d_tab, entries, idx->dev.vsa);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (cudaStreamSynchronize(st) != cudaSuccess) rc = fail(FMX_ERR_CUDA, "k-mer table embedding failed");
+    }
     if (rc) {
         cudaFree(d_tab);
         cudaFree(d_steps);
@@ -647,7 +712,7 @@ static int build_kmer_table(fmx_index *idx) {
     if (rc) return rc;
     idx->kmer_k = k;
     idx->kmer_entries = entries;
-    if (!large_text) return 0;
+    if (!large_text || idx->hdr.reserved[0] == FMX_MODE_COMPACT) return 0;  // COMPACT: the L2-resident table only
     // default HBM budget of the large table (FMX_KMER_BUDGET_MB overrides): twice the index itself, at most
     // 8 GiB, while the rank structure sits in L2.  Beyond L2 every step of a search is a DRAM request, and
     // the table is sized to END the search of an absent pattern: the smallest k with sigma^k >= 4 n leaves
@@ -669,31 +734,44 @@ static int build_kmer_table(fmx_index *idx) {
     return build_big_table(idx, budget);
 }
 
-static int search_device(const fmx_index *idx, int mode, const uint8_t *d_pat, const uint64_t *d_pat_off,
-                         uint64_t fixed_len, uint64_t npat, const uint64_t *d_is, const uint64_t *d_ie,
-                         uint64_t *d_os, uint64_t *d_oe, cudaStream_t st, bool count_work = true,
-                         bool force_simple = false, DevBuf *buf = nullptr) {
+// where the patterns of a batch live on the device: bytes (+ offsets or a fixed length) or packed words
+struct PatSrc {
+    const uint8_t *pat = nullptr;
+    const uint64_t *pat_off = nullptr;
+    uint64_t fixed_len = 0;
+    const uint64_t *packed = nullptr;
+    uint32_t packed_bits = 0;
+};
+
+static int make_search_args(const fmx_index *idx, int mode, const PatSrc &ps, uint64_t npat, const uint64_t *d_is,
+                            const uint64_t *d_ie, bool count_work, SearchArgs &a) {
     if (mode < FMX_SEARCH || mode > FMX_SEARCH_EXACT) return fail(FMX_ERR_INVALID_ARG, "bad search mode");
     if (mode != FMX_SEARCH && idx->hdr.kind != FMX_KIND_MULTI)
         return fail(FMX_ERR_UNSUPPORTED, "search_prefix/suffix/exact need a MultiPieces index (frontend.rs:369-390)");
     if ((d_is == nullptr) != (d_ie == nullptr)) return fail(FMX_ERR_INVALID_ARG, "init_s and init_e must both be given");
-    SearchArgs a;
     std::memset(&a, 0, sizeof(a));
-    a.pat = d_pat;
-    a.pat_off = d_pat_off;
-    a.fixed_len = fixed_len;
+    a.pat = ps.pat;
+    a.pat_off = ps.pat_off;
+    a.fixed_len = ps.fixed_len;
+    if (ps.packed_bits) {
+        if (ps.packed_bits != 2 && ps.packed_bits != 4) return fail(FMX_ERR_INVALID_ARG, "packed_bits must be 0, 2 or 4");
+        if (idx->hdr.max_character > (1u << ps.packed_bits))
+            return fail(FMX_ERR_UNSUPPORTED, "packed patterns need max_character <= 2^packed_bits");
+        if (ps.pat_off || ps.fixed_len == 0) return fail(FMX_ERR_INVALID_ARG, "packed patterns need a fixed length");
+        if (ps.fixed_len > 0xFFFFFFFFull / ps.packed_bits) return fail(FMX_ERR_INVALID_ARG, "packed pattern too long");
+        a.packed = ps.packed;
+        a.packed_bits = ps.packed_bits;
+        a.packed_wpp = (uint32_t)((ps.fixed_len * ps.packed_bits + 63) / 64);
+    }
     a.npat = npat;
     a.init_s = d_is;
     a.init_e = d_ie;
     a.s0 = 0;  // wrapper.rs:41, 65, 73, 81
     a.e0 = (mode == FMX_SEARCH_SUFFIX || mode == FMX_SEARCH_EXACT) ? (uint32_t)idx->hdr.ndoc : (uint32_t)idx->hdr.n;
-    a.out_s = d_os;
-    a.out_e = d_oe;
     a.err = idx->d_err;
-    a.work = count_work ? idx->d_work : nullptr;
-    a.steps_out = nullptr;
-    a.staged = (!d_pat_off && fixed_len > 0 && fixed_len % 16 == 0 && reinterpret_cast<uintptr_t>(d_pat) % 16 == 0 &&
-                idx->opt_stage_patterns) ? 1u : 0u;
+    a.work = (count_work && idx->opt_count_work) ? idx->d_work : nullptr;
+    a.staged = (!ps.packed_bits && !ps.pat_off && ps.fixed_len > 0 && ps.fixed_len % 16 == 0 &&
+                reinterpret_cast<uintptr_t>(ps.pat) % 16 == 0 && idx->opt_stage_patterns) ? 1u : 0u;
     a.verify = (idx->dev.verify && idx->opt_verify) ? 1u : 0u;
     // the table memoises searches that start from (0, n): fresh search / search_prefix
     const bool tab_ok = idx->d_kmer_tab && idx->opt_kmer && !d_is && (mode == FMX_SEARCH || mode == FMX_SEARCH_PREFIX);
@@ -704,8 +782,81 @@ static int search_device(const fmx_index *idx, int mode, const uint8_t *d_pat, c
     a.big_tab = big_ok ? idx->d_big_tab : nullptr;
     a.big_steps = big_ok ? idx->d_big_steps : nullptr;
     a.big_k = big_ok ? idx->big_k : 0;
-    if (count_work) CUDA_TRY(cudaMemsetAsync(idx->d_work, 0, sizeof(unsigned long long), st));
-    return dispatch_search(idx, a, st, force_simple, buf);
+    a.tab_embed = tab_ok ? idx->tab_embed : 0u;
+    return 0;
+}
+
+// the phased pipeline (phased.cuh) needs the DENSE verify structures and a fresh search
+static bool phased_ok(const fmx_index *idx, const SearchArgs &a) {
+    return idx->opt_phased && a.verify && idx->hdr.isa_level == 0 && has_dense_sa(idx) && idx->hdr.kind != FMX_KIND_RLFM &&
+           !a.init_s && !a.steps_out && a.npat < 0xFFFFFFFFull;
+}
+
+// Backward search of a batch by the phased kernels; leaves (rs, re, hint) in buf[B_RS / B_RE / B_HINT].
+static int search_phased(const fmx_index *idx, DevBuf *buf, const SearchArgs &a, bool want_rows, cudaStream_t st) {
+    int rc;
+    const uint64_t npat = a.npat;
+    if ((rc = buf[B_RS].ensure(npat * 4 + 16))) return rc;
+    if ((rc = buf[B_RE].ensure(npat * 4 + 16))) return rc;
+    if ((rc = buf[B_HINT].ensure(npat * 4 + 16))) return rc;
+    if ((rc = buf[B_QS].ensure(npat * 16 + 16))) return rc;
+    if ((rc = buf[B_QV].ensure(npat * 16 + 16))) return rc;
+    if ((rc = buf[B_QN].ensure(64))) return rc;
+    if (npat == 0) return 0;
+    PhasedArgs g;
+    g.a = a;
+    g.rs = buf[B_RS].as<uint32_t>();
+    g.re = buf[B_RE].as<uint32_t>();
+    g.hint = buf[B_HINT].as<uint32_t>();
+    g.want_rows = want_rows ? 1u : 0u;
+    g.q_steps = buf[B_QS].as<uint4>();
+    g.q_verify = buf[B_QV].as<uint4>();
+    g.qn = buf[B_QN].as<unsigned long long>();
+    CUDA_TRY(cudaMemsetAsync(g.qn, 0, 32, st));
+    uint64_t blocks = (npat + 255) / 256;
+    const uint64_t cap = (uint64_t)idx->sms * 8 * 4;
+    if (blocks > cap) blocks = cap;
+    // queue kernels: one resident wave (a multiple of the SM count); the queue lengths live on the device
+    uint64_t qblocks = (uint64_t)idx->sms * 8;
+    if (qblocks > (npat + 255) / 256) qblocks = (npat + 255) / 256;
+    dispatch(idx, [&](auto K, auto LY) {
+        if constexpr (K() != FMX_KIND_RLFM_) {
+            k_ph_seed<K(), LY()><<<(unsigned)blocks, 256, 0, st>>>(idx->dev, g);
+            phase_mark(idx, 1, st);
+            k_ph_steps<K(), LY()><<<(unsigned)qblocks, 256, 0, st>>>(idx->dev, g, 0);
+            phase_mark(idx, 2, st);
+            k_ph_verify<K(), LY()><<<(unsigned)qblocks, 256, 0, st>>>(idx->dev, g);
+            phase_mark(idx, 3, st);
+            k_ph_steps<K(), LY()><<<(unsigned)qblocks, 256, 0, st>>>(idx->dev, g, 1);
+        }
+    });
+    g_launches.fetch_add(3, std::memory_order_relaxed);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+static int search_device(const fmx_index *idx, int mode, const PatSrc &ps, uint64_t npat, const uint64_t *d_is,
+                         const uint64_t *d_ie, uint64_t *d_os, uint64_t *d_oe, cudaStream_t st, bool count_work = true,
+                         bool force_simple = false, DevBuf *buf = nullptr) {
+    SearchArgs a;
+    int rc = make_search_args(idx, mode, ps, npat, d_is, d_ie, count_work, a);
+    if (rc) return rc;
+    a.out_s = d_os;
+    a.out_e = d_oe;
+    if (a.work) {
+        CUDA_TRY(cudaMemsetAsync(idx->d_work, 0, sizeof(unsigned long long), st));
+        CUDA_TRY(cudaMemsetAsync(idx->d_work + 2, 0, sizeof(unsigned long long), st));
+    }
+    if (!buf) buf = idx->buf;
+    if (phased_ok(idx, a)) {
+        if ((rc = search_phased(idx, buf, a, true, st))) return rc;
+        if (npat) {
+            k_ph_widen<<<grid_for(npat, 256), 256, 0, st>>>(buf[B_RS].as<uint32_t>(), buf[B_RE].as<uint32_t>(), npat, d_os, d_oe);
+            LAUNCH_CHECK();
+        }
+        return 0;
+    }
+    return dispatch_search(idx, a, st, force_simple || a.packed_bits != 0, buf);
 }
 
 static int check_err_flag(const fmx_index *idx, cudaStream_t st) {
@@ -724,9 +875,13 @@ extern "C" int fmx_search_batch_device(const fmx_index *idx, int mode, const uin
                                        uint64_t fixed_len, uint64_t npat, const uint64_t *d_init_s,
                                        const uint64_t *d_init_e, uint64_t *d_out_s, uint64_t *d_out_e, void *stream) {
     if (!idx || !d_out_s || !d_out_e) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(idx->mu);
     CUDA_TRY(cudaSetDevice(idx->device));
-    return search_device(idx, mode, d_pat, d_pat_off, fixed_len, npat, d_init_s, d_init_e, d_out_s, d_out_e,
-                         pick_stream(idx, stream));
+    PatSrc ps;
+    ps.pat = d_pat;
+    ps.pat_off = d_pat_off;
+    ps.fixed_len = fixed_len;
+    return search_device(idx, mode, ps, npat, d_init_s, d_init_e, d_out_s, d_out_e, pick_stream(idx, stream));
 }
 
 extern "C" int fmx_search_check(const fmx_index *idx, void *stream) {
@@ -767,8 +922,11 @@ extern "C" int fmx_search_batch(const fmx_index *idx, int mode, const uint8_t *p
     } else if (init_s || init_e) {
         return fail(FMX_ERR_INVALID_ARG, "init_s and init_e must both be given");
     }
-    rc = search_device(idx, mode, idx->buf[B_PAT].as<uint8_t>(), d_off, fixed_len, npat, d_is, d_ie,
-                       idx->buf[B_S].as<uint64_t>(), idx->buf[B_E].as<uint64_t>(), st);
+    PatSrc ps;
+    ps.pat = idx->buf[B_PAT].as<uint8_t>();
+    ps.pat_off = d_off;
+    ps.fixed_len = fixed_len;
+    rc = search_device(idx, mode, ps, npat, d_is, d_ie, idx->buf[B_S].as<uint64_t>(), idx->buf[B_E].as<uint64_t>(), st);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(out_s, idx->buf[B_S].p, npat * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(out_e, idx->buf[B_E].p, npat * 8, cudaMemcpyDeviceToHost, st));
@@ -896,9 +1054,11 @@ static int locate_prepare(const fmx_index *idx, int prefix_only, const uint64_t 
 
 static int locate_fill(const fmx_index *idx, const RowSource &src, uint64_t total, uint64_t *d_pos, uint64_t *d_pid,
                        cudaStream_t st, bool count_work = true, const uint64_t *total_dev = nullptr) {
+    count_work = count_work && idx->opt_count_work;
     if (count_work) CUDA_TRY(cudaMemsetAsync(idx->d_work + 1, 0, sizeof(unsigned long long), st));
     if (total == 0) return 0;
     LocateArgs a;
+    a.dense = locate_dense(idx) ? 1u : 0u;
     a.rows = src.rows;
     a.hoff = src.hoff;
     a.s = src.s;
@@ -909,7 +1069,7 @@ static int locate_fill(const fmx_index *idx, const RowSource &src, uint64_t tota
     a.positions = d_pos;
     a.piece_ids = d_pid;
     a.work = count_work ? idx->d_work : nullptr;
-    if (src.ranges && !src.rows) {
+    if (src.ranges && !src.rows && !a.dense) {
         const uint64_t threads = (total + LOCATE_GROUP - 1) / LOCATE_GROUP;
         dispatch(idx, [&](auto K, auto LY) {
             k_locate_ranges<K(), LY()><<<(unsigned)((threads + LOCATE_RANGE_THREADS - 1) / LOCATE_RANGE_THREADS),
@@ -918,7 +1078,7 @@ static int locate_fill(const fmx_index *idx, const RowSource &src, uint64_t tota
         LAUNCH_CHECK();
         return 0;
     }
-    if (!idx->opt_locate_refill) {
+    if (!idx->opt_locate_refill || a.dense) {
         uint64_t blocks = (total + 255) / 256;
         uint64_t cap = (uint64_t)idx->sms * 8 * 8;
         if (blocks > cap) blocks = cap;
@@ -956,9 +1116,22 @@ extern "C" int fmx_locate_count_device(const fmx_index *idx, int prefix_only, co
     if (!idx || !d_hit_off || !total_hits) return fail(FMX_ERR_INVALID_ARG, "null argument");
     int rc = locate_args_ok(idx, false);
     if (rc) return rc;
+    std::lock_guard<std::mutex> lk(idx->mu);
     CUDA_TRY(cudaSetDevice(idx->device));
     RowSource rows;
-    return locate_prepare(idx, prefix_only, d_s, d_e, npat, d_hit_off, total_hits, &rows, pick_stream(idx, stream));
+    idx->count_token = CountToken();
+    rc = locate_prepare(idx, prefix_only, d_s, d_e, npat, d_hit_off, total_hits, &rows, pick_stream(idx, stream));
+    if (rc) return rc;
+    // what the matching fmx_locate_fill_device call must present again (the rows may sit in scratch)
+    idx->count_token.valid = true;
+    idx->count_token.prefix_only = prefix_only;
+    idx->count_token.npat = npat;
+    idx->count_token.total = *total_hits;
+    idx->count_token.d_s = d_s;
+    idx->count_token.d_hit_off = d_hit_off;
+    idx->count_token.rows = rows.rows;
+    idx->count_token.ranges = rows.ranges;
+    return FMX_OK;
 }
 
 extern "C" int fmx_locate_fill_device(const fmx_index *idx, int prefix_only, const uint64_t *d_s, const uint64_t *d_e,
@@ -967,44 +1140,50 @@ extern "C" int fmx_locate_fill_device(const fmx_index *idx, int prefix_only, con
     if (!idx) return fail(FMX_ERR_INVALID_ARG, "null argument");
     int rc = locate_args_ok(idx, d_piece_ids != nullptr);
     if (rc) return rc;
+    std::lock_guard<std::mutex> lk(idx->mu);
     CUDA_TRY(cudaSetDevice(idx->device));
-    (void)d_s;
     (void)d_e;
-    (void)npat;
-    (void)d_hit_off;
-    // the rows prepared by the matching fmx_locate_count_device call are still in scratch
-    RowSource rows;  // what fmx_locate_count_device left behind for these ranges
-    if (!prefix_only && (locate_by_ranges(idx, total_hits, npat) || expand_by_search(idx, total_hits))) {
+    // the rows prepared by the matching fmx_locate_count_device call may still sit in scratch: the call must be
+    // the continuation of exactly that count
+    const CountToken &tk = idx->count_token;
+    if (!tk.valid || tk.prefix_only != prefix_only || tk.npat != npat || tk.total != total_hits || tk.d_s != d_s ||
+        tk.d_hit_off != d_hit_off)
+        return fail(FMX_ERR_INVALID_ARG, "fmx_locate_fill_device must follow the fmx_locate_count_device call for the same ranges");
+    RowSource rows;
+    if (tk.rows) {
+        rows.rows = tk.rows;
+    } else {
         rows.hoff = d_hit_off;
         rows.s = d_s;
         rows.npat = npat;
-        rows.ranges = locate_by_ranges(idx, total_hits, npat);
-    } else {
-        rows.rows = prefix_only ? idx->buf[B_ROWS2].as<uint32_t>() : idx->buf[B_ROWS].as<uint32_t>();
+        rows.ranges = tk.ranges;
     }
     return locate_fill(idx, rows, total_hits, d_positions, d_piece_ids, pick_stream(idx, stream));
 }
 
 // Fully asynchronous locate on device buffers (no host synchronisation, graph-capturable): the hit
 // total stays on the device (d_hit_off[npat]); launches are sized by `capacity`.
-extern "C" int fmx_locate_batch_device(const fmx_index *idx, int prefix_only, const uint64_t *d_s, const uint64_t *d_e,
-                                       uint64_t npat, uint64_t *d_hit_off, uint64_t *d_positions, uint64_t *d_piece_ids,
-                                       uint64_t capacity, void *stream) {
-    if (!idx || !d_hit_off || (!d_positions && !d_piece_ids)) return fail(FMX_ERR_INVALID_ARG, "null argument");
-    int rc = locate_args_ok(idx, d_piece_ids != nullptr);
-    if (rc) return rc;
-    CUDA_TRY(cudaSetDevice(idx->device));
-    cudaStream_t st = pick_stream(idx, stream);
+static int locate_async(const fmx_index *idx, DevBuf *buf, int prefix_only, const uint64_t *d_s, const uint64_t *d_e,
+                        uint64_t npat, uint64_t *d_hit_off, uint64_t *d_positions, uint64_t *d_piece_ids, uint64_t capacity,
+                        cudaStream_t st, bool count_work) {
+    int rc;
     if (prefix_only) {  // the L == 0 filter needs the kept count on the host: synchronous path
         uint64_t total = 0;
         RowSource rows;
-        if ((rc = locate_prepare(idx, prefix_only, d_s, d_e, npat, d_hit_off, &total, &rows, st))) return rc;
+        uint64_t *d_off = d_hit_off;
+        if ((rc = buf[B_HOFF].ensure((npat + 1) * 8))) return rc;
+        d_off = buf[B_HOFF].as<uint64_t>();
+        if ((rc = locate_counts(idx, buf, d_s, d_e, npat, d_off, st))) return rc;
+        uint64_t cand = 0;
+        CUDA_TRY(cudaMemcpyAsync(&cand, d_off + npat, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if ((rc = locate_rows(idx, buf, prefix_only, d_s, npat, d_off, cand, d_hit_off, &total, &rows, st))) return rc;
         if (total > capacity) total = capacity;
-        return locate_fill(idx, rows, total, d_positions, d_piece_ids, st);
+        if (!d_positions && !d_piece_ids) return 0;
+        return locate_fill(idx, rows, total, d_positions, d_piece_ids, st, count_work);
     }
-    DevBuf *buf = idx->buf;
     if ((rc = locate_counts(idx, buf, d_s, d_e, npat, d_hit_off, st))) return rc;
-    if (capacity == 0 || npat == 0) return FMX_OK;
+    if (capacity == 0 || npat == 0 || (!d_positions && !d_piece_ids)) return FMX_OK;
     if (capacity >= 0xFFFFFFFFull * 4) return fail(FMX_ERR_UNSUPPORTED, "capacity too large");
     const uint64_t *d_total0 = d_hit_off + npat;
     if (locate_by_ranges(idx, capacity, npat) || expand_by_search(idx, capacity)) {
@@ -1013,7 +1192,7 @@ extern "C" int fmx_locate_batch_device(const fmx_index *idx, int prefix_only, co
         src.s = d_s;
         src.npat = npat;
         src.ranges = locate_by_ranges(idx, capacity, npat);
-        return locate_fill(idx, src, capacity, d_positions, d_piece_ids, st, true, d_total0);
+        return locate_fill(idx, src, capacity, d_positions, d_piece_ids, st, count_work, d_total0);
     }
     if ((rc = buf[B_OWNER].ensure(capacity * 4))) return rc;
     if ((rc = buf[B_ROWS].ensure(capacity * 4))) return rc;
@@ -1028,7 +1207,19 @@ extern "C" int fmx_locate_batch_device(const fmx_index *idx, int prefix_only, co
     LAUNCH_CHECK();
     RowSource src;
     src.rows = d_rows;
-    return locate_fill(idx, src, capacity, d_positions, d_piece_ids, st, true, d_total);
+    return locate_fill(idx, src, capacity, d_positions, d_piece_ids, st, count_work, d_total);
+}
+
+extern "C" int fmx_locate_batch_device(const fmx_index *idx, int prefix_only, const uint64_t *d_s, const uint64_t *d_e,
+                                       uint64_t npat, uint64_t *d_hit_off, uint64_t *d_positions, uint64_t *d_piece_ids,
+                                       uint64_t capacity, void *stream) {
+    if (!idx || !d_hit_off || (!d_positions && !d_piece_ids)) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    int rc = locate_args_ok(idx, d_piece_ids != nullptr);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(idx->mu);
+    CUDA_TRY(cudaSetDevice(idx->device));
+    return locate_async(idx, idx->buf, prefix_only, d_s, d_e, npat, d_hit_off, d_positions, d_piece_ids, capacity,
+                        pick_stream(idx, stream), true);
 }
 
 // One page of the hit list: hits [first_hit, first_hit + nhits) of the CSR that fmx_locate_count_device
@@ -1041,6 +1232,7 @@ extern "C" int fmx_locate_page_device(const fmx_index *idx, const uint64_t *d_s,
     int rc = locate_args_ok(idx, d_piece_ids != nullptr);
     if (rc) return rc;
     if (nhits == 0 || npat == 0) return FMX_OK;
+    std::lock_guard<std::mutex> lk(idx->mu);
     CUDA_TRY(cudaSetDevice(idx->device));
     RowSource src;
     src.hoff = d_hit_off;
@@ -1154,7 +1346,209 @@ extern "C" int fmx_locate_batch(const fmx_index *idx, int prefix_only, const uin
     return FMX_OK;
 }
 
-// ------------------------------------------------------------------ fused, pipelined search + locate
+// ------------------------------------------------------------------ fused query: count + locate, any input form
+
+// out[i] = in[i] (+ base) in the caller's width
+template <class Tin, class Tout>
+__global__ void k_convert(const Tin *in, uint64_t n, uint64_t base, Tout *out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (Tout)((uint64_t)in[i] + base);
+}
+// counts[p] = e - s (wrapper.rs:132-134; an inverted range counts 0 here, the reference would underflow)
+template <class Tr, class Tout>
+__global__ void k_range_counts(const Tr *s, const Tr *e, uint64_t n, Tout *out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = e[i] > s[i] ? (Tout)(e[i] - s[i]) : (Tout)0;
+}
+
+struct QueryOut {           // device pointers, caller's width
+    uint32_t width = 8;
+    uint64_t *out_s = nullptr, *out_e = nullptr;
+    void *counts = nullptr, *hit_off = nullptr, *positions = nullptr, *piece_ids = nullptr;
+    uint64_t capacity = 0;
+};
+
+template <class Tw>
+static int emit_dense(const fmx_index *idx, DevBuf *buf, uint64_t npat, const uint32_t *hint, const QueryOut &o, cudaStream_t st,
+                      bool count_work) {
+    int rc;
+    if ((rc = buf[B_BIGQ].ensure(npat * 4 + 16))) return rc;
+    if ((rc = buf[B_QN].ensure(64))) return rc;
+    EmitArgs<Tw, Tw> g;
+    g.rs = buf[B_RS].as<uint32_t>();
+    g.re = buf[B_RE].as<uint32_t>();
+    g.hint = hint;
+    g.off = static_cast<const Tw *>(o.hit_off);
+    g.npat = npat;
+    g.capacity = o.capacity;
+    g.positions = static_cast<Tw *>(o.positions);
+    g.piece_ids = static_cast<Tw *>(o.piece_ids);
+    g.bigq = buf[B_BIGQ].as<uint32_t>();
+    g.bign = buf[B_QN].as<unsigned long long>() + 4;
+    g.req = count_work ? idx->d_work + 3 : nullptr;
+    CUDA_TRY(cudaMemsetAsync(g.bign, 0, 8, st));
+    uint64_t blocks = (npat + 255) / 256;
+    const uint64_t cap = (uint64_t)idx->sms * 8 * 4;
+    if (blocks > cap) blocks = cap;
+    uint64_t bblocks = (uint64_t)idx->sms * 8;
+    if (bblocks > (npat + 7) / 8) bblocks = (npat + 7) / 8;
+    if (idx->hdr.kind == FMX_KIND_MULTI) {
+        k_emit_small<FMX_KIND_MULTI_, Tw, Tw><<<(unsigned)blocks, 256, 0, st>>>(idx->dev, g);
+        k_emit_big<FMX_KIND_MULTI_, Tw, Tw><<<(unsigned)bblocks, 256, 0, st>>>(idx->dev, g);
+    } else {
+        k_emit_small<FMX_KIND_FM_, Tw, Tw><<<(unsigned)blocks, 256, 0, st>>>(idx->dev, g);
+        k_emit_big<FMX_KIND_FM_, Tw, Tw><<<(unsigned)bblocks, 256, 0, st>>>(idx->dev, g);
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+// The whole query on device buffers, asynchronous.  HBM-rich indexes: phased search (no inverse-suffix-array
+// request unless the caller wants the rows) + positions from the hints / the resident suffix array.  Every other
+// index: k_search + the LF-walk locate kernels.
+static int query_device(const fmx_index *idx, DevBuf *buf, int mode, const PatSrc &ps, uint64_t npat, const QueryOut &o,
+                        cudaStream_t st, bool count_work) {
+    int rc;
+    const bool want_hits = o.positions != nullptr || o.piece_ids != nullptr;
+    const bool want_off = o.hit_off != nullptr;
+    const bool want_rows = o.out_s != nullptr || o.out_e != nullptr;
+    const int prefix_only = (mode == FMX_SEARCH_PREFIX || mode == FMX_SEARCH_EXACT) ? 1 : 0;
+    if (o.width != 8 && o.width != 4) return fail(FMX_ERR_INVALID_ARG, "out_width must be 8 or 4");
+    if (want_hits && !want_off) return fail(FMX_ERR_INVALID_ARG, "positions / piece_ids need hit_off");
+    if (want_rows && (!o.out_s || !o.out_e)) return fail(FMX_ERR_INVALID_ARG, "out_s and out_e must both be given");
+    if (want_hits && (rc = locate_args_ok(idx, o.piece_ids != nullptr))) return rc;
+    if (npat >= 0xFFFFFFFFull) return fail(FMX_ERR_UNSUPPORTED, "at most 2^32 - 2 patterns per call");
+    SearchArgs a;
+    if ((rc = make_search_args(idx, mode, ps, npat, nullptr, nullptr, count_work, a))) return rc;
+    if (a.work) CUDA_TRY(cudaMemsetAsync(idx->d_work, 0, 4 * sizeof(unsigned long long), st));
+    if (npat == 0) {
+        if (want_off) CUDA_TRY(cudaMemsetAsync(o.hit_off, 0, o.width, st));
+        return 0;
+    }
+    phase_mark(idx, 0, st);
+    const bool dense = locate_dense(idx) || (!want_hits && has_dense_sa(idx));
+    const bool rich_out = dense && !prefix_only;   // counts / offsets / positions straight from (rs, re, hint)
+    const uint32_t *hint = nullptr;
+    uint64_t *d_s = o.out_s, *d_e = o.out_e;
+    if (phased_ok(idx, a)) {
+        const bool rows = want_rows || !rich_out;
+        if ((rc = search_phased(idx, buf, a, rows, st))) return rc;
+        hint = buf[B_HINT].as<uint32_t>();
+        if (rows) {
+            if (!d_s) {
+                if ((rc = buf[B_S].ensure(npat * 8))) return rc;
+                if ((rc = buf[B_E].ensure(npat * 8))) return rc;
+                d_s = buf[B_S].as<uint64_t>();
+                d_e = buf[B_E].as<uint64_t>();
+            }
+            k_ph_widen<<<grid_for(npat, 256), 256, 0, st>>>(buf[B_RS].as<uint32_t>(), buf[B_RE].as<uint32_t>(), npat, d_s, d_e);
+            LAUNCH_CHECK();
+        }
+    } else {
+        if (!d_s) {
+            if ((rc = buf[B_S].ensure(npat * 8))) return rc;
+            if ((rc = buf[B_E].ensure(npat * 8))) return rc;
+            d_s = buf[B_S].as<uint64_t>();
+            d_e = buf[B_E].as<uint64_t>();
+        }
+        a.out_s = d_s;
+        a.out_e = d_e;
+        if ((rc = dispatch_search(idx, a, st, true, buf))) return rc;
+        phase_mark(idx, 1, st);
+        if (rich_out) {  // (s, e) as u32 for the emit kernels
+            if ((rc = buf[B_RS].ensure(npat * 4 + 16))) return rc;
+            if ((rc = buf[B_RE].ensure(npat * 4 + 16))) return rc;
+            k_convert<uint64_t, uint32_t><<<grid_for(npat, 256), 256, 0, st>>>(d_s, npat, 0, buf[B_RS].as<uint32_t>());
+            k_convert<uint64_t, uint32_t><<<grid_for(npat, 256), 256, 0, st>>>(d_e, npat, 0, buf[B_RE].as<uint32_t>());
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            LAUNCH_CHECK();
+        }
+    }
+    phase_mark(idx, 4, st);
+    if (rich_out) {
+        const uint32_t *rs = buf[B_RS].as<uint32_t>(), *re = buf[B_RE].as<uint32_t>();
+        if (o.counts) {
+            if (o.width == 8) k_range_counts<uint32_t, uint64_t><<<grid_for(npat, 256), 256, 0, st>>>(rs, re, npat, static_cast<uint64_t *>(o.counts));
+            else k_range_counts<uint32_t, uint32_t><<<grid_for(npat, 256), 256, 0, st>>>(rs, re, npat, static_cast<uint32_t *>(o.counts));
+            LAUNCH_CHECK();
+        }
+        if (!want_off) return 0;
+        if (o.width == 8) rc = device_scan_load<LoadCount32, uint64_t, OpSum, true>(LoadCount32{rs, re}, npat, static_cast<uint64_t *>(o.hit_off), OpSum(), true, buf[B_TILES], st);
+        else rc = device_scan_load<LoadCount32, uint32_t, OpSum, true>(LoadCount32{rs, re}, npat, static_cast<uint32_t *>(o.hit_off), OpSum(), true, buf[B_TILES], st);
+        if (rc) return rc;
+        phase_mark(idx, 5, st);
+        if (!want_hits || o.capacity == 0) return 0;
+        if (a.work) CUDA_TRY(cudaMemsetAsync(idx->d_work + 1, 0, sizeof(unsigned long long), st));
+        rc = o.width == 8 ? emit_dense<uint64_t>(idx, buf, npat, hint, o, st, a.work != nullptr)
+                          : emit_dense<uint32_t>(idx, buf, npat, hint, o, st, a.work != nullptr);
+        phase_mark(idx, 6, st);
+        return rc;
+    }
+    // LF-walk locate (compact indexes, filtered modes): u64 internally, narrowed at the end for out_width 4
+    if (o.counts) {
+        if (o.width == 8) k_range_counts<uint64_t, uint64_t><<<grid_for(npat, 256), 256, 0, st>>>(d_s, d_e, npat, static_cast<uint64_t *>(o.counts));
+        else k_range_counts<uint64_t, uint32_t><<<grid_for(npat, 256), 256, 0, st>>>(d_s, d_e, npat, static_cast<uint32_t *>(o.counts));
+        LAUNCH_CHECK();
+    }
+    if (!want_off) return 0;
+    if (o.width == 8) {
+        rc = locate_async(idx, buf, prefix_only, d_s, d_e, npat, static_cast<uint64_t *>(o.hit_off),
+                          static_cast<uint64_t *>(o.positions), static_cast<uint64_t *>(o.piece_ids), o.capacity, st, count_work);
+        phase_mark(idx, 6, st);
+        return rc;
+    }
+    if ((rc = buf[B_W64].ensure((npat + 1) * 8))) return rc;
+    uint64_t *w_off = buf[B_W64].as<uint64_t>(), *w_pos = nullptr, *w_pid = nullptr;
+    if (o.positions) {
+        if ((rc = buf[B_POS].ensure(o.capacity * 8 + 8))) return rc;
+        w_pos = buf[B_POS].as<uint64_t>();
+    }
+    if (o.piece_ids) {
+        if ((rc = buf[B_PID].ensure(o.capacity * 8 + 8))) return rc;
+        w_pid = buf[B_PID].as<uint64_t>();
+    }
+    if ((rc = locate_async(idx, buf, prefix_only, d_s, d_e, npat, w_off, w_pos, w_pid, o.capacity, st, count_work))) return rc;
+    k_convert<uint64_t, uint32_t><<<grid_for(npat + 1, 256), 256, 0, st>>>(w_off, npat + 1, 0, static_cast<uint32_t *>(o.hit_off));
+    if (w_pos) k_convert<uint64_t, uint32_t><<<grid_for(o.capacity, 256), 256, 0, st>>>(w_pos, o.capacity, 0, static_cast<uint32_t *>(o.positions));
+    if (w_pid) k_convert<uint64_t, uint32_t><<<grid_for(o.capacity, 256), 256, 0, st>>>(w_pid, o.capacity, 0, static_cast<uint32_t *>(o.piece_ids));
+    LAUNCH_CHECK();
+    return 0;
+}
+
+static int query_args_ok(const fmx_index *idx, const fmx_query *q) {
+    if (!idx || !q) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    if (q->npat && !q->patterns && (q->pat_off ? true : q->fixed_len != 0)) return fail(FMX_ERR_INVALID_ARG, "null pattern buffer");
+    if (q->out_width != 8 && q->out_width != 4) return fail(FMX_ERR_INVALID_ARG, "out_width must be 8 or 4");
+    if ((q->positions || q->piece_ids) && !q->hit_off) return fail(FMX_ERR_INVALID_ARG, "positions / piece_ids need hit_off");
+    if (q->packed_bits && (q->pat_off || !q->fixed_len)) return fail(FMX_ERR_INVALID_ARG, "packed patterns need a fixed length");
+    return 0;
+}
+
+extern "C" int fmx_query_batch_device(const fmx_index *idx, const fmx_query *q, void *stream) {
+    int rc = query_args_ok(idx, q);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(idx->mu);
+    CUDA_TRY(cudaSetDevice(idx->device));
+    PatSrc ps;
+    if (q->packed_bits) ps.packed = static_cast<const uint64_t *>(q->patterns);
+    else ps.pat = static_cast<const uint8_t *>(q->patterns);
+    ps.packed_bits = q->packed_bits;
+    ps.pat_off = q->pat_off;
+    ps.fixed_len = q->fixed_len;
+    QueryOut o;
+    o.width = q->out_width;
+    o.out_s = q->out_s;
+    o.out_e = q->out_e;
+    o.counts = q->counts;
+    o.hit_off = q->hit_off;
+    o.positions = q->positions;
+    o.piece_ids = q->piece_ids;
+    o.capacity = q->capacity;
+    return query_device(idx, idx->buf, q->mode, ps, q->npat, o, pick_stream(idx, stream), true);
+}
+
+// ------------------------------------------------------------------ the same for host buffers: chunked pipeline
 
 static int ensure_lanes(const fmx_index *idx) {
     if (idx->lanes_ready) return 0;
@@ -1167,23 +1561,29 @@ static int ensure_lanes(const fmx_index *idx) {
     return 0;
 }
 
-extern "C" int fmx_search_locate_batch(const fmx_index *idx, int mode, const uint8_t *pat, const uint64_t *pat_off,
-                                       uint64_t fixed_len, uint64_t npat, uint64_t *out_s, uint64_t *out_e,
-                                       uint64_t *hit_off, uint64_t *positions, uint64_t *piece_ids, uint64_t capacity,
-                                       uint64_t *total_hits) {
-    if (!idx || !hit_off || !total_hits) return fail(FMX_ERR_INVALID_ARG, "null argument");
-    const bool want_hits = positions != nullptr || piece_ids != nullptr;
-    int rc;
-    if (want_hits && (rc = locate_args_ok(idx, piece_ids != nullptr))) return rc;
-    *total_hits = 0;
-    hit_off[0] = 0;
+// The batch is cut into chunks that flow through FMX_LANES lanes (stream + scratch each): stage 1 of a chunk
+// (H2D patterns, the whole query_device with a guessed position capacity, hit total -> pinned word, event) is
+// enqueued FMX_LANES - 1 chunks ahead of stage 2 (wait for the total, re-emit in the rare case the guess was too
+// small, rebase the offsets, D2H of exactly the bytes produced).  The host waits once per chunk, on an event
+// that is usually already complete.
+extern "C" int fmx_query_batch(const fmx_index *idx, const fmx_query *q, uint64_t *total_hits) {
+    int rc = query_args_ok(idx, q);
+    if (rc) return rc;
+    if (total_hits) *total_hits = 0;
+    const uint32_t W = q->out_width;
+    const uint64_t npat = q->npat;
+    auto put = [&](void *base, uint64_t i, uint64_t v) {
+        if (W == 8) static_cast<uint64_t *>(base)[i] = v; else static_cast<uint32_t *>(base)[i] = (uint32_t)v;
+    };
+    if (q->hit_off) put(q->hit_off, 0, 0);
+    const bool want_hits = q->positions != nullptr || q->piece_ids != nullptr;
+    if (want_hits && (rc = locate_args_ok(idx, q->piece_ids != nullptr))) return rc;
     if (npat == 0) return FMX_OK;
-    uint64_t pat_bytes = pat_off ? pat_off[npat] : npat * fixed_len;
-    if (pat_bytes && !pat) return fail(FMX_ERR_INVALID_ARG, "null pattern buffer");
+    const uint8_t *pat8 = static_cast<const uint8_t *>(q->patterns);
+    const uint64_t wpp = q->packed_bits ? (q->fixed_len * q->packed_bits + 63) / 64 : 0;
     std::lock_guard<std::mutex> lk(idx->mu);
     CUDA_TRY(cudaSetDevice(idx->device));
     if ((rc = ensure_lanes(idx))) return rc;
-    const int prefix_only = (mode == FMX_SEARCH_PREFIX || mode == FMX_SEARCH_EXACT) ? 1 : 0;
     // chunks: enough of them to overlap copies with kernels, big enough to fill the GPU
     uint64_t chunk = (npat + 3) / 4;
     if (chunk < (1ull << 16)) chunk = 1ull << 16;
@@ -1192,93 +1592,177 @@ extern "C" int fmx_search_locate_batch(const fmx_index *idx, int mode, const uin
     const uint64_t nchunks = (npat + chunk - 1) / chunk;
     uint64_t running = 0;
     bool overflow = false;
+    uint64_t guess_num = 2, guess_den = 1;  // position capacity of a chunk = n * num / den (refined from the chunks seen)
 
-    auto stage1 = [&](uint64_t c) -> int {  // H2D patterns, search, candidate counts (all asynchronous)
+    auto chunk_src = [&](uint64_t lo, uint64_t n, Lane &L, PatSrc &ps, int &r) {
+        r = 0;
+        if (q->packed_bits) {
+            const uint64_t nbytes = n * wpp * 8;
+            if ((r = L.buf[B_PAT].ensure(nbytes + 16))) return;
+            if (cudaMemcpyAsync(L.buf[B_PAT].p, pat8 + lo * wpp * 8, nbytes, cudaMemcpyHostToDevice, L.st) != cudaSuccess) {
+                r = fail(FMX_ERR_CUDA, "H2D copy of the patterns failed");
+                return;
+            }
+            ps.packed = L.buf[B_PAT].as<uint64_t>();
+            ps.packed_bits = q->packed_bits;
+            ps.fixed_len = q->fixed_len;
+            return;
+        }
+        const uint64_t off0 = q->pat_off ? q->pat_off[lo] : lo * q->fixed_len;
+        const uint64_t nbytes = (q->pat_off ? q->pat_off[lo + n] : (lo + n) * q->fixed_len) - off0;
+        if ((r = L.buf[B_PAT].ensure(nbytes + 16))) return;
+        if (nbytes && cudaMemcpyAsync(L.buf[B_PAT].p, pat8 + off0, nbytes, cudaMemcpyHostToDevice, L.st) != cudaSuccess) {
+            r = fail(FMX_ERR_CUDA, "H2D copy of the patterns failed");
+            return;
+        }
+        ps.pat = L.buf[B_PAT].as<uint8_t>();
+        ps.fixed_len = q->fixed_len;
+        if (q->pat_off) {
+            if ((r = L.buf[B_OFF].ensure((n + 1) * 8))) return;
+            if (cudaMemcpyAsync(L.buf[B_OFF].p, q->pat_off + lo, (n + 1) * 8, cudaMemcpyHostToDevice, L.st) != cudaSuccess) {
+                r = fail(FMX_ERR_CUDA, "H2D copy of the pattern offsets failed");
+                return;
+            }
+            ps.pat_off = L.buf[B_OFF].as<uint64_t>();
+            ps.pat -= off0;  // the kernel adds the batch-global byte offsets
+        }
+    };
+    auto lane_out = [&](Lane &L, uint64_t n, uint64_t cap, QueryOut &o) -> int {
+        int r;
+        o.width = W;
+        if (q->out_s) {
+            if ((r = L.buf[B_S].ensure(n * 8))) return r;
+            if ((r = L.buf[B_E].ensure(n * 8))) return r;
+            o.out_s = L.buf[B_S].as<uint64_t>();
+            o.out_e = L.buf[B_E].as<uint64_t>();
+        }
+        if (q->counts) {
+            if ((r = L.buf[B_CNT].ensure(n * 8))) return r;
+            o.counts = L.buf[B_CNT].p;
+        }
+        if (q->hit_off) {
+            if ((r = L.buf[B_HOFF].ensure((n + 1) * 8))) return r;
+            o.hit_off = L.buf[B_HOFF].p;
+        }
+        if (q->positions) {
+            if ((r = L.buf[B_OUT8].ensure(cap * W + 16))) return r;
+            o.positions = L.buf[B_OUT8].p;
+        }
+        if (q->piece_ids) {
+            if ((r = L.buf[B_OUT32].ensure(cap * W + 16))) return r;
+            o.piece_ids = L.buf[B_OUT32].p;
+        }
+        o.capacity = cap;
+        return 0;
+    };
+    auto stage1 = [&](uint64_t c) -> int {
         Lane &L = idx->lane[c % FMX_LANES];
         const uint64_t lo = c * chunk, n = (lo + chunk < npat ? chunk : npat - lo);
-        const uint64_t off0 = pat_off ? pat_off[lo] : lo * fixed_len;
-        const uint64_t nbytes = (pat_off ? pat_off[lo + n] : (lo + n) * fixed_len) - off0;
+        PatSrc ps;
         int r;
-        if ((r = L.buf[B_PAT].ensure(nbytes + 16))) return r;
-        if ((r = L.buf[B_S].ensure(n * 8))) return r;
-        if ((r = L.buf[B_E].ensure(n * 8))) return r;
-        if ((r = L.buf[B_HOFF].ensure((n + 1) * 8))) return r;
-        if (nbytes) CUDA_TRY(cudaMemcpyAsync(L.buf[B_PAT].p, pat + off0, nbytes, cudaMemcpyHostToDevice, L.st));
-        const uint8_t *d_pat = L.buf[B_PAT].as<uint8_t>();
-        const uint64_t *d_off = nullptr;
-        if (pat_off) {
-            if ((r = L.buf[B_OFF].ensure((n + 1) * 8))) return r;
-            CUDA_TRY(cudaMemcpyAsync(L.buf[B_OFF].p, pat_off + lo, (n + 1) * 8, cudaMemcpyHostToDevice, L.st));
-            d_off = L.buf[B_OFF].as<uint64_t>();
-            d_pat -= off0;  // the kernel adds the batch-global byte offsets
+        chunk_src(lo, n, L, ps, r);
+        if (r) return r;
+        uint64_t cap = want_hits ? n * guess_num / guess_den + 4096 : 0;
+        QueryOut o;
+        if ((r = lane_out(L, n, cap, o))) return r;
+        L.pos_cap = cap;
+        if ((r = query_device(idx, L.buf, q->mode, ps, n, o, L.st, false))) return r;
+        if (q->out_s) {
+            CUDA_TRY(cudaMemcpyAsync(q->out_s + lo, o.out_s, n * 8, cudaMemcpyDeviceToHost, L.st));
+            CUDA_TRY(cudaMemcpyAsync(q->out_e + lo, o.out_e, n * 8, cudaMemcpyDeviceToHost, L.st));
         }
-        uint64_t *d_s = L.buf[B_S].as<uint64_t>(), *d_e = L.buf[B_E].as<uint64_t>();
-        if ((r = search_device(idx, mode, d_pat, d_off, fixed_len, n, nullptr, nullptr, d_s, d_e, L.st, false, true, L.buf))) return r;
-        if (out_s) CUDA_TRY(cudaMemcpyAsync(out_s + lo, d_s, n * 8, cudaMemcpyDeviceToHost, L.st));
-        if (out_e) CUDA_TRY(cudaMemcpyAsync(out_e + lo, d_e, n * 8, cudaMemcpyDeviceToHost, L.st));
-        uint64_t *d_unf = L.buf[B_HOFF].as<uint64_t>();
-        if ((r = locate_counts(idx, L.buf, d_s, d_e, n, d_unf, L.st))) return r;
-        CUDA_TRY(cudaMemcpyAsync(L.h_total, d_unf + n, 8, cudaMemcpyDeviceToHost, L.st));
+        if (q->counts) CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(q->counts) + lo * W, o.counts, n * W, cudaMemcpyDeviceToHost, L.st));
+        if (q->hit_off) {
+            *L.h_total = 0;
+            CUDA_TRY(cudaMemcpyAsync(L.h_total, static_cast<uint8_t *>(o.hit_off) + n * W, W, cudaMemcpyDeviceToHost, L.st));
+        }
         CUDA_TRY(cudaEventRecord(L.ev, L.st));
         return 0;
     };
-    auto stage2 = [&](uint64_t c) -> int {  // rows, LF walks, D2H of offsets and positions
+    auto stage2 = [&](uint64_t c) -> int {
         Lane &L = idx->lane[c % FMX_LANES];
         const uint64_t lo = c * chunk, n = (lo + chunk < npat ? chunk : npat - lo);
+        if (!q->hit_off) return 0;
         CUDA_TRY(cudaEventSynchronize(L.ev));
-        const uint64_t cand = *L.h_total;
+        const uint64_t hits = *L.h_total;
         int r;
-        uint64_t *d_s = L.buf[B_S].as<uint64_t>();
-        uint64_t *d_unf = L.buf[B_HOFF].as<uint64_t>();
-        uint64_t *d_src = d_unf;
-        uint64_t hits = cand;
-        RowSource rows;
-        if (want_hits || prefix_only) {
-            if (prefix_only) {
-                if ((r = L.buf[B_INE].ensure((n + 1) * 8))) return r;
-                d_src = L.buf[B_INE].as<uint64_t>();
+        if (W == 4 && running + hits > 0xFFFFFFFFull) overflow = true;
+        if (want_hits && hits > L.pos_cap && running + hits <= q->capacity && !overflow) {
+            // the guess was too small for this chunk: emit again with room for every hit (the patterns and the
+            // search results of the chunk are still in the lane's buffers)
+            PatSrc ps;
+            QueryOut o;
+            if ((r = lane_out(L, n, hits, o))) return r;
+            L.pos_cap = hits;
+            if (q->packed_bits) {
+                ps.packed = L.buf[B_PAT].as<uint64_t>();
+                ps.packed_bits = q->packed_bits;
+            } else {
+                ps.pat = L.buf[B_PAT].as<uint8_t>();
+                if (q->pat_off) {
+                    ps.pat_off = L.buf[B_OFF].as<uint64_t>();
+                    ps.pat -= q->pat_off[lo];
+                }
             }
-            if ((r = locate_rows(idx, L.buf, prefix_only, d_s, n, d_unf, cand, d_src, &hits, &rows, L.st))) return r;
+            ps.fixed_len = q->fixed_len;
+            o.counts = nullptr;
+            if ((r = query_device(idx, L.buf, q->mode, ps, n, o, L.st, false))) return r;
         }
+        if (hits * 2 > n * guess_num / guess_den) {  // later chunks: twice what this one needed
+            guess_num = (hits * 2 + n - 1) / n + 1;
+            guess_den = 1;
+        }
+        // offsets of the chunk, rebased to the batch
         if ((r = L.buf[B_INS].ensure((n + 1) * 8))) return r;
-        uint64_t *d_final = L.buf[B_INS].as<uint64_t>();
-        k_add_base<<<grid_for(n + 1, 256), 256, 0, L.st>>>(d_src, n + 1, running, d_final);
+        if (W == 8) k_convert<uint64_t, uint64_t><<<grid_for(n + 1, 256), 256, 0, L.st>>>(L.buf[B_HOFF].as<uint64_t>(), n + 1, running, L.buf[B_INS].as<uint64_t>());
+        else k_convert<uint32_t, uint32_t><<<grid_for(n + 1, 256), 256, 0, L.st>>>(L.buf[B_HOFF].as<uint32_t>(), n + 1, running, L.buf[B_INS].as<uint32_t>());
         LAUNCH_CHECK();
-        CUDA_TRY(cudaMemcpyAsync(hit_off + lo, d_final, (n + 1) * 8, cudaMemcpyDeviceToHost, L.st));
+        CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(q->hit_off) + lo * W, L.buf[B_INS].p, (n + 1) * W, cudaMemcpyDeviceToHost, L.st));
         if (want_hits && hits) {
-            if (running + hits > capacity) {
+            if (running + hits > q->capacity) {
                 overflow = true;
             } else if (!overflow) {
-                uint64_t *d_pos = nullptr, *d_pid = nullptr;
-                if (positions) {
-                    if ((r = L.buf[B_POS].ensure(hits * 8))) return r;
-                    d_pos = L.buf[B_POS].as<uint64_t>();
-                }
-                if (piece_ids) {
-                    if ((r = L.buf[B_PID].ensure(hits * 8))) return r;
-                    d_pid = L.buf[B_PID].as<uint64_t>();
-                }
-                if ((r = locate_fill(idx, rows, hits, d_pos, d_pid, L.st, false))) return r;
-                if (positions) CUDA_TRY(cudaMemcpyAsync(positions + running, d_pos, hits * 8, cudaMemcpyDeviceToHost, L.st));
-                if (piece_ids) CUDA_TRY(cudaMemcpyAsync(piece_ids + running, d_pid, hits * 8, cudaMemcpyDeviceToHost, L.st));
+                if (q->positions) CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(q->positions) + running * W, L.buf[B_OUT8].p, hits * W, cudaMemcpyDeviceToHost, L.st));
+                if (q->piece_ids) CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(q->piece_ids) + running * W, L.buf[B_OUT32].p, hits * W, cudaMemcpyDeviceToHost, L.st));
             }
         }
         running += hits;
         return 0;
     };
     rc = 0;
-    // stage 1 runs FMX_LANES - 1 chunks ahead of stage 2: the H2D copies queue back to back on the
-    // copy engine while the host waits for hit totals of earlier chunks
     for (uint64_t c = 0; c < nchunks + FMX_LANES - 1 && rc == 0; c++) {
         if (c < nchunks) rc = stage1(c);
         if (rc == 0 && c >= FMX_LANES - 1 && c - (FMX_LANES - 1) < nchunks) rc = stage2(c - (FMX_LANES - 1));
     }
     for (auto &l : idx->lane) cudaStreamSynchronize(l.st);
     if (rc) return rc;
-    *total_hits = running;
+    if (total_hits) *total_hits = running;
     if ((rc = check_err_flag(idx, idx->lane[0].st))) return rc;
-    if (overflow) return fail(FMX_ERR_CAPACITY, "positions buffer too small: total_hits holds the size needed");
+    if (overflow) return fail(FMX_ERR_CAPACITY, "output buffer too small (or more than 2^32 - 1 hits with out_width 4): total_hits holds the size needed");
     return FMX_OK;
+}
+
+extern "C" int fmx_search_locate_batch(const fmx_index *idx, int mode, const uint8_t *pat, const uint64_t *pat_off,
+                                       uint64_t fixed_len, uint64_t npat, uint64_t *out_s, uint64_t *out_e,
+                                       uint64_t *hit_off, uint64_t *positions, uint64_t *piece_ids, uint64_t capacity,
+                                       uint64_t *total_hits) {
+    if (!idx || !hit_off || !total_hits) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    if ((out_s == nullptr) != (out_e == nullptr)) return fail(FMX_ERR_INVALID_ARG, "out_s and out_e must both be given");
+    fmx_query q;
+    std::memset(&q, 0, sizeof(q));
+    q.mode = mode;
+    q.patterns = pat;
+    q.pat_off = pat_off;
+    q.fixed_len = fixed_len;
+    q.npat = npat;
+    q.out_width = 8;
+    q.out_s = out_s;
+    q.out_e = out_e;
+    q.hit_off = hit_off;
+    q.positions = positions;
+    q.piece_ids = piece_ids;
+    q.capacity = capacity;
+    return fmx_query_batch(idx, &q, total_hits);
 }
 
 // ------------------------------------------------------------------ extraction / primitives
@@ -1379,6 +1863,28 @@ extern "C" int fmx_lf_map2_batch(const fmx_index *idx, const uint8_t *c, const u
 
 // ------------------------------------------------------------------ measurement helpers
 
+// Milliseconds of the phases of the last query with option "phase_timing" on: [0] seed (table lookups; the whole
+// k_search on indexes without the phased kernels), [1] steps, [2] verify, [3] second steps pass (+ row widening),
+// [4] counts + offsets scan, [5] emit / locate.  Phases that did not run are 0.  Synchronises the stream.
+extern "C" int fmx_last_phase_ms(const fmx_index *idx, void *stream, float *ms, int n) {
+    if (!idx || !ms) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(idx->device));
+    CUDA_TRY(cudaStreamSynchronize(pick_stream(idx, stream)));
+    for (int k = 0; k < n; k++) ms[k] = 0.f;
+    int prev = (idx->pev_mask & 1u) ? 0 : -1;
+    for (int k = 1; k <= FMX_NPHASE && prev >= 0; k++) {
+        if (!(idx->pev_mask & (1u << k))) continue;
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, idx->pev[prev], idx->pev[k]) != cudaSuccess) {
+            cudaGetLastError();
+            t = 0.f;
+        }
+        if (k - 1 < n) ms[k - 1] = t;
+        prev = k;
+    }
+    return FMX_OK;
+}
+
 extern "C" int fmx_last_work(const fmx_index *idx, void *stream, uint64_t *search_steps, uint64_t *lf_steps) {
     if (!idx) return fail(FMX_ERR_INVALID_ARG, "null argument");
     CUDA_TRY(cudaSetDevice(idx->device));
@@ -1388,6 +1894,22 @@ extern "C" int fmx_last_work(const fmx_index *idx, void *stream, uint64_t *searc
     CUDA_TRY(cudaStreamSynchronize(st));
     if (search_steps) *search_steps = w[0];
     if (lf_steps) *lf_steps = w[1];
+    return FMX_OK;
+}
+
+// Index requests the phased kernels of the last query issued (option "count_work"): lane-level loads of table
+// entries, rank blocks, suffix-array / inverse entries and text sectors by the search phases, and of suffix-array
+// entries by the emit kernels.  An upper bound on the L2 requests of those kernels (neighbouring lanes share
+// lines); 0 on indexes that do not run the phased kernels.  Synchronises the stream.
+extern "C" int fmx_last_requests(const fmx_index *idx, void *stream, uint64_t *search_requests, uint64_t *emit_requests) {
+    if (!idx) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(idx->device));
+    cudaStream_t st = pick_stream(idx, stream);
+    unsigned long long w[4] = {0, 0, 0, 0};
+    CUDA_TRY(cudaMemcpyAsync(w, idx->d_work, sizeof(w), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (search_requests) *search_requests = w[2];
+    if (emit_requests) *emit_requests = w[3];
     return FMX_OK;
 }
 

@@ -38,6 +38,29 @@ __device__ __forceinline__ RB rb_load(const uint4 *__restrict__ v, uint32_t blk)
     return b;
 }
 
+// Scalar loads of randomly addressed index data (table entries, suffix-array / inverse entries, text words):
+// the same .L2::64B qualifier, so a miss fills 64 bytes of the line from DRAM instead of all 128.
+#ifndef FMX_NO_L2_64B
+#define FMX_LD_S "ld.global.nc.L2::64B"
+#else
+#define FMX_LD_S "ld.global.nc"
+#endif
+__device__ __forceinline__ uint32_t ldg32_s(const uint32_t *p) {
+    uint32_t v;
+    asm(FMX_LD_S ".u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint2 ldg64_s(const uint2 *p) {
+    uint2 v;
+    asm(FMX_LD_S ".v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t ldg8_s(const uint8_t *p) {
+    uint32_t v;
+    asm(FMX_LD_S ".u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
 __device__ __forceinline__ void rb_split(uint32_t pos, uint32_t &blk, uint32_t &r) {
     blk = pos / FMX_RB_BITS;
     r = pos - blk * FMX_RB_BITS;
@@ -474,7 +497,7 @@ __device__ __forceinline__ uint32_t seq_access_lf(const FmxDev &ix, const Tabs<L
         sym = c;
         return t.cs[c] + q4_rank_in(ix, t.exc, b, i, c);
     } else if (LAYOUT == FMX_LAYOUT_SY) {
-        uint32_t c = __ldg(ix.raw + i);
+        uint32_t c = ldg8_s(ix.raw + i);
         sym = c;
         return t.cs[c] + rbv_rank1(sy_vec(ix, c), i);
     } else {
@@ -492,7 +515,7 @@ __device__ __forceinline__ uint32_t seq_access(const FmxDev &ix, const Tabs<LAYO
         RB b = rb_load(ix.lv[0], i >> 6);
         return q4_code(b, i & 63u) + 1u;
     } else if (LAYOUT == FMX_LAYOUT_SY) {
-        return __ldg(ix.raw + i);
+        return ldg8_s(ix.raw + i);
     } else {
         uint32_t c;
         if (LAYOUT == FMX_LAYOUT_W4) w4_access_walk(ix, i, c);
@@ -543,7 +566,7 @@ __device__ __forceinline__ void rl_probe(const FmxDev &ix, const Tabs<LAYOUT> &t
         hit = sh == c;
         nrc = t.cs[c] + q4_rank_in(ix, t.exc, a, j, c);
     } else if (LAYOUT == FMX_LAYOUT_SY) {
-        hit = __ldg(ix.raw + h) == c;
+        hit = ldg8_s(ix.raw + h) == c;
         nrc = t.cs[c] + rbv_rank1(sy_vec(ix, c), j);
     } else if (LAYOUT == FMX_LAYOUT_W4) {
         const uint32_t Lq = ix.qlevels;
@@ -600,9 +623,9 @@ __device__ __forceinline__ uint32_t lf_map2_dev(const FmxDev &ix, const Tabs<LAY
         uint32_t j, nrc;
         bool hit;
         rl_probe<LAYOUT>(ix, t, c, i, j, nrc, hit);
-        uint32_t v = __ldg(ix.rl_bpsel + nrc);
+        uint32_t v = ldg32_s(ix.rl_bpsel + nrc);
         if (!hit) return v;
-        return v + i - __ldg(ix.rl_bsel + j);
+        return v + i - ldg32_s(ix.rl_bsel + j);
     } else {
         uint32_t w = seq_lf<LAYOUT>(ix, t, c, i);
         if (KIND == FMX_KIND_MULTI_ && c == 0) return multi_zero_rule(ix, i, w);
@@ -641,7 +664,7 @@ __device__ __forceinline__ uint32_t lf_step(const FmxDev &ix, const Tabs<LAYOUT>
         uint32_t c;
         uint32_t q = seq_access_lf<LAYOUT>(ix, t, h, c);  // cs[c] + rank(s, h, c); rank(s, j, c) adds (j > h)
         sym = c;
-        return __ldg(ix.rl_bpsel + (q + (j - h))) + i - __ldg(ix.rl_bsel + j);
+        return ldg32_s(ix.rl_bpsel + (q + (j - h))) + i - ldg32_s(ix.rl_bsel + j);
     } else {
         uint32_t c;
         uint32_t w = seq_access_lf<LAYOUT>(ix, t, i, c);
@@ -678,10 +701,10 @@ __device__ __forceinline__ bool fl_step(const FmxDev &ix, const Tabs<LAYOUT> &t,
     if (KIND == FMX_KIND_RLFM_) {
         uint32_t jr = rbv_rank1(ix.rl_bp, i + 1) - 1u;
         uint32_t c = cs_search(t.cs, ix.cs_len, jr);
-        uint32_t p = __ldg(ix.rl_bpsel + jr);
+        uint32_t p = ldg32_s(ix.rl_bpsel + jr);
         uint32_t m = seq_select<LAYOUT>(ix, t, c, jr - t.cs[c]);
         sym = c;
-        next = __ldg(ix.rl_bsel + m) + i - p;
+        next = ldg32_s(ix.rl_bsel + m) + i - p;
         return true;
     } else {
         uint32_t c = cs_search(t.cs, ix.cs_len, i);
@@ -732,7 +755,17 @@ struct SearchArgs {
     uint4 *queue;
     unsigned long long *qcount;
     unsigned long long *qcursor;
+    // table entries of one-row ranges carry the row's text position instead of e (y = FMX_TAB_POS_FLAG | SA[s];
+    // only when n < 2^31 and the dense suffix array exists): the seed-and-verify path then skips the SA request
+    uint32_t tab_embed;
+    // packed patterns (fmx_query.packed_bits = 2 or 4): pattern p is the 64-bit words [p * packed_wpp, (p+1) * packed_wpp)
+    // of `packed`, character k in bits [k * bits, (k+1) * bits) of that stream, stored as character - 1
+    const uint64_t *packed;
+    uint32_t packed_bits;
+    uint32_t packed_wpp;
 };
+#define FMX_TAB_POS_FLAG 0x80000000u
+#define FMX_NOHINT 0xFFFFFFFFu
 
 __device__ __forceinline__ void pattern_span(const SearchArgs &a, uint64_t p, uint64_t &beg, uint32_t &len) {
     if (a.pat_off) {
@@ -748,13 +781,14 @@ __device__ __forceinline__ void pattern_span(const SearchArgs &a, uint64_t p, ui
 // same aligned 32-bit word, so a 32-mer costs 8-9 load instructions instead of 32 (the byte loads were
 // ~20 % of the L1TEX wavefronts of k_search and, once index blocks had evicted the pattern lines from
 // L1, extra L2 requests: profiles/r01b_target_ncu.txt)
-struct PatReader {
+template <bool SECT>
+struct ByteReader {
     const uint8_t *q;
     const uint32_t *words;  // the aligned word holding the pattern's first byte
     uint32_t off;           // byte offset of the pattern inside that word
     uint32_t len;
     uint32_t cur = 0xFFFFFFFFu, w = 0;
-    __device__ __forceinline__ PatReader(const uint8_t *q_, uint32_t len_) : q(q_), len(len_) {
+    __device__ __forceinline__ ByteReader(const uint8_t *q_, uint32_t len_) : q(q_), len(len_) {
         const uintptr_t a = reinterpret_cast<uintptr_t>(q_);
         words = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
         off = (uint32_t)(a & 3u);
@@ -766,17 +800,39 @@ struct PatReader {
             cur = wi;
             const uint32_t first = wi << 2;  // the word covers pattern bytes [first - off, first - off + 4)
             if (first >= off && first + 4u <= off + len) {
-                w = __ldg(words + wi);
+                w = SECT ? ldg32_s(words + wi) : __ldg(words + wi);
             } else {  // a word that sticks out of the pattern is never read as a whole: no byte outside the
                       // caller's buffer is touched, whatever its alignment and size
                 w = 0;
                 for (uint32_t b = 0; b < 4; b++) {
                     const uint32_t pi = first + b;
-                    if (pi >= off && pi < off + len) w |= (uint32_t)__ldg(q + (pi - off)) << (8u * b);
+                    if (pi >= off && pi < off + len) w |= (SECT ? ldg8_s(q + (pi - off)) : (uint32_t)__ldg(q + (pi - off))) << (8u * b);
                 }
             }
         }
         return (w >> (8u * (idx & 3u))) & 0xFFu;
+    }
+};
+typedef ByteReader<false> PatReader;   // pattern bytes: streamed, default fill
+typedef ByteReader<true> TextReader;   // text bytes at a random position: sector-granular fill
+
+// Patterns in either input form behind one get(k): bytes (PatReader) or packed codes (SearchArgs::packed)
+struct AnyReader {
+    PatReader pr;
+    const uint64_t *pw;
+    uint32_t bits, curw;
+    uint64_t w;
+    __device__ __forceinline__ AnyReader(const SearchArgs &a, uint64_t p, uint64_t beg, uint32_t len)
+        : pr(a.pat + (a.packed_bits ? 0 : beg), a.packed_bits ? 0u : len), pw(a.packed + p * a.packed_wpp), bits(a.packed_bits),
+          curw(0xFFFFFFFFu), w(0) {}
+    __device__ __forceinline__ uint32_t get(uint32_t k) {
+        if (bits == 0) return pr.get(k);
+        const uint32_t bit = k * bits, wi = bit >> 6;
+        if (wi != curw) {
+            curw = wi;
+            w = __ldg(pw + wi);
+        }
+        return ((uint32_t)(w >> (bit & 63u)) & ((1u << bits) - 1u)) + 1u;
     }
 };
 
@@ -799,7 +855,7 @@ __device__ __forceinline__ bool kmer_index(Reader &pr, uint32_t len, uint32_t K,
 // pattern; otherwise the caller walks from (s0, e0) so errors show up (or not) exactly as in the reference
 template <class Reader>
 __device__ __forceinline__ bool kmer_lookup(const SearchArgs &a, uint32_t maxc, Reader &q, uint32_t &len,
-                                            uint32_t &s, uint32_t &e, uint32_t &it) {
+                                            uint32_t &s, uint32_t &e, uint32_t &it, uint32_t *pos = nullptr) {
     const uint2 *tab = nullptr;
     const uint8_t *stp = nullptr;
     uint32_t K = 0;
@@ -816,13 +872,19 @@ __device__ __forceinline__ bool kmer_lookup(const SearchArgs &a, uint32_t maxc, 
     }
     uint32_t idx;
     if (!kmer_index(q, len, K, maxc, idx)) return false;
-    uint2 t = __ldg(tab + idx);
+    uint2 t = ldg64_s(tab + idx);
     s = t.x;
     e = t.y;
+    if (a.tab_embed && (e & FMX_TAB_POS_FLAG)) {  // one-row range: y carries SA[s]
+        if (pos) *pos = e & ~FMX_TAB_POS_FLAG;
+        e = s + 1u;
+    }
     it = K;
     len -= K;
     if (s == e) {
-        it = __ldg(stp + idx);
+        // the iterations the reference executed before the range emptied: a second random request, made only
+        // when the caller asked for work counters (option "count_work") or per-pattern steps (table build)
+        if (a.work || a.steps_out) it = ldg8_s(stp + idx);
         len = 0;
     }
     return true;
@@ -869,8 +931,10 @@ struct StagedReader {
 // many characters it consumed (s updated; the range is [s, s + 1)); 0 = nothing done (immediate mismatch,
 // or the pattern would run off the start of the text).  The caller's ordinary loop takes the next
 // character -- the mismatching one empties the range there exactly as in the reference, an invalid one
-// raises the error there.  MultiPieces: the comparison stops in front of a \0 of the text, whose LF rule
-// (multi_pieces.rs:140-153) is not a plain rank.  Arithmetic mirrored in tests/blobreader.py.
+// raises the error there.  The comparison stops in front of a \0 of the text for every kind: the LF rule of
+// MultiPieces for \0 (multi_pieces.rs:140-153) is not a plain rank, and the FM backend's plain rank for \0
+// (fm_index.rs:93-95) is not the true LF row when a text holds interior zeros -- the ordinary step reproduces
+// either.  Arithmetic mirrored in tests/blobreader.py.
 #define FMX_VERIFY_MIN_DENSE 6u     /* fewest remaining characters worth the tail: dense structures (3-4 requests) */
 #define FMX_VERIFY_MIN_SAMPLED 10u  /* sampled structures (two short LF walks on top) */
 template <int KIND, int LAYOUT, class Reader>
@@ -881,15 +945,15 @@ __device__ __forceinline__ uint32_t verify_tail(const FmxDev &ix, const Tabs<LAY
         row = lf_step<KIND, LAYOUT>(ix, tb, row, sym);
         st++;
     }
-    uint32_t pos = __ldg(ix.vsa + (row >> ix.vsa_level)) + st;  // < 2n < 2^32
+    uint32_t pos = ldg32_s(ix.vsa + (row >> ix.vsa_level)) + st;  // < 2n < 2^32
     if (pos >= ix.n) pos -= ix.n;
     if (pos < rem) return 0;
     // characters rd[rem-1], rd[rem-2], .. against text[pos-1], text[pos-2], ..
-    PatReader tr(ix.text + (pos - rem), rem);
+    TextReader tr(ix.text + (pos - rem), rem);
     uint32_t matched = 0;
     while (matched < rem) {
         const uint32_t t = tr.get(rem - 1u - matched);
-        if ((KIND == FMX_KIND_MULTI_ && t == 0u) || rd.get(rem - 1u - matched) != t) break;
+        if (t == 0u || rd.get(rem - 1u - matched) != t) break;
         matched++;
     }
     if (!matched) return 0;
@@ -899,7 +963,7 @@ __device__ __forceinline__ uint32_t verify_tail(const FmxDev &ix, const Tabs<LAY
         q4 = ix.n - 1u;
         r = 0;
     } else {
-        r = __ldg(ix.isa + (q4 >> ix.isa_level));
+        r = ldg32_s(ix.isa + (q4 >> ix.isa_level));
     }
     for (uint32_t d = q4 - q; d > 0; d--) r = lf_step<KIND, LAYOUT>(ix, tb, r, sym);
     s = r;
@@ -958,7 +1022,10 @@ __global__ void __launch_bounds__(256) k_search(const __grid_constant__ FmxDev i
         uint32_t e = a.init_e ? (uint32_t)a.init_e[p] : a.e0;
         const uint8_t *q = a.pat + beg;
         uint32_t it = 0;
-        if (a.staged) {
+        if (a.packed_bits) {
+            AnyReader rd(a, p, beg, len);
+            search_one<KIND, LAYOUT>(ix, tb, a, rd, len, s, e, it);
+        } else if (a.staged) {
             StagedReader rd(spat, q, len);
             search_one<KIND, LAYOUT>(ix, tb, a, rd, len, s, e, it);
         } else {
@@ -1209,7 +1276,18 @@ struct LocateArgs {
     uint64_t *piece_ids;  // nullable (MultiPieces)
     unsigned long long *work;  // [1] += executed LF steps
     uint64_t chunk;            // k_locate: consecutive hits per warp chunk
+    uint32_t dense;            // the full suffix array is resident (SEC_VSA) and may be used: position = SA[row]
 };
+
+// piece id of a text position (multi_pieces.rs:208-218): the number of piece ends strictly before it
+__device__ __forceinline__ uint32_t piece_of(const FmxDev &ix, uint64_t v) {
+    uint32_t lo = 0, hi = ix.ndoc;
+    while (lo < hi) {
+        uint32_t m = lo + ((hi - lo) >> 1);
+        if (__ldg(ix.piece_end + m) < v) lo = m + 1; else hi = m;
+    }
+    return lo;
+}
 
 // row of hit h (wrapper.rs:206-216: rows s..e of pattern p, patterns in order): from the expanded row
 // list, or -- small batches, where the five expansion launches cost more than they save -- by binary
@@ -1241,21 +1319,19 @@ __global__ void __launch_bounds__(256) k_locate_simple(const __grid_constant__ F
     for (uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; h < total; h += stride) {
         uint32_t row = locate_row(a, h);
         uint32_t st = 0, sym;
-        while (row & mask) {
-            row = lf_step<KIND, LAYOUT>(ix, tb, row, sym);
-            st++;
-        }
-        uint64_t v = (uint64_t)__ldg(ix.sa + (row >> ix.sa_level)) + st;
-        if (v >= ix.n) v -= ix.n;  // (sa + steps) % n; both terms are < n
-        if (a.positions) a.positions[h] = v;
-        if (KIND == FMX_KIND_MULTI_ && a.piece_ids) {
-            uint32_t lo = 0, hi = ix.ndoc;  // number of piece ends strictly before v
-            while (lo < hi) {
-                uint32_t m = lo + ((hi - lo) >> 1);
-                if (__ldg(ix.piece_end + m) < v) lo = m + 1; else hi = m;
+        uint64_t v;
+        if (a.dense) {  // HBM-rich mode: the walk's result is SA[row] by definition; one request, no walk
+            v = ldg32_s(ix.vsa + row);
+        } else {
+            while (row & mask) {
+                row = lf_step<KIND, LAYOUT>(ix, tb, row, sym);
+                st++;
             }
-            a.piece_ids[h] = lo;
+            v = (uint64_t)ldg32_s(ix.sa + (row >> ix.sa_level)) + st;
+            if (v >= ix.n) v -= ix.n;  // (sa + steps) % n; both terms are < n
         }
+        if (a.positions) a.positions[h] = v;
+        if (KIND == FMX_KIND_MULTI_ && a.piece_ids) a.piece_ids[h] = piece_of(ix, v);
         steps += st;
     }
     if (a.work) {
@@ -1293,7 +1369,7 @@ __global__ void __launch_bounds__(256) k_locate(const __grid_constant__ FmxDev i
     uint64_t h = 0;
     for (;;) {
         if (active && !(row & mask)) {  // sampled row reached: (sa + steps) % n, both terms < n
-            uint64_t v = (uint64_t)__ldg(ix.sa + (row >> ix.sa_level)) + st;
+            uint64_t v = (uint64_t)ldg32_s(ix.sa + (row >> ix.sa_level)) + st;
             if (v >= ix.n) v -= ix.n;
             if (a.positions) a.positions[h] = v;
             if (KIND == FMX_KIND_MULTI_ && a.piece_ids) {
@@ -1371,7 +1447,7 @@ __global__ void __launch_bounds__(256) k_locate_stable(const __grid_constant__ F
         uint32_t row = 0, st = 0, hl = 0;  // hl = hit index inside the chunk
         for (;;) {
             if (active && !(row & mask)) {  // sampled row reached: (sa + steps) % n, both terms < n
-                uint64_t v = (uint64_t)__ldg(ix.sa + (row >> ix.sa_level)) + st;
+                uint64_t v = (uint64_t)ldg32_s(ix.sa + (row >> ix.sa_level)) + st;
                 if (v >= ix.n) v -= ix.n;
                 if (a.positions) a.positions[base + hl] = v;
                 if (KIND == FMX_KIND_MULTI_ && a.piece_ids) {
@@ -1498,7 +1574,7 @@ __global__ void __launch_bounds__(LOCATE_RANGE_THREADS) k_locate_ranges(const __
                     while (hit) {
                         const uint32_t j = (uint32_t)__ffsll((long long)hit) - 1u;
                         hit &= hit - 1;
-                        uint64_t v = (uint64_t)__ldg(ix.sa + ((row + j) >> ix.sa_level)) + t;
+                        uint64_t v = (uint64_t)ldg32_s(ix.sa + ((row + j) >> ix.sa_level)) + t;
                         if (v >= ix.n) v -= ix.n;  // (sa + steps) % n; both terms are < n
                         if (a.positions) a.positions[out + j] = v;
                         if (KIND == FMX_KIND_MULTI_ && a.piece_ids) {
@@ -1603,7 +1679,7 @@ __global__ void __launch_bounds__(256) k_rows_op(const __grid_constant__ FmxDev 
                 i = lf_step<KIND, LAYOUT>(ix, tb, i, c);
                 st++;
             }
-            uint64_t v = (uint64_t)__ldg(ix.sa + (i >> ix.sa_level)) + st;
+            uint64_t v = (uint64_t)ldg32_s(ix.sa + (i >> ix.sa_level)) + st;
             res = v >= ix.n ? v - ix.n : v;
             break;
         }

@@ -1,0 +1,337 @@
+// phased.cuh -- the HBM-rich query pipeline: backward search split into converged phases, and locate by the
+// resident suffix array.
+//
+// k_search (kernels.cuh) runs the whole reference loop (wrapper.rs:103-124) of one pattern in one thread.  On
+// indexes that carry the dense seed-and-verify structures (fmx_layout.h: text, full suffix array, inverse) the
+// work of a pattern is three very different things -- one table lookup, a few rank steps, one verify tail --
+// and the patterns of a warp disagree about which of them they are in: ncu showed 6-10 of 32 lanes active
+// (profiles/r01b_*_ncu.txt).  Here every phase is its own kernel over a compacted queue, so a warp's lanes do
+// the same thing at the same time and every memory instruction serves 32 patterns:
+//
+//   k_ph_seed    one pattern per thread: the k-mer table lookup (ONE request).  Finished patterns (range
+//                emptied inside the table, or nothing left) are written out; one-row ranges with enough
+//                characters left go to the VERIFY queue; the rest to the STEPS queue.
+//   k_ph_steps   ordinary reference iterations (lf_map2 on both range ends) until the range empties, the pattern
+//                ends, or the range is one row with enough characters left (-> VERIFY queue).
+//   k_ph_verify  position of the row (from the table entry, else SA[s]), comparison of the remaining characters
+//                with the text, and -- only when the caller wants SA rows -- ISA[pos - matched].
+//   k_ph_steps   again, over the patterns whose comparison stopped early and whose exact (s, e) are wanted
+//                (second = 1: the verify tail is not tried again, as in search_one).
+//
+// Results are those of search_one, bit for bit: (s, e) when rows are wanted, e - s otherwise, plus a HINT: the
+// text position of the final row when the verify phase produced it, which is exactly what locate returns for
+// that row, so locate of a verified one-row range costs no memory request at all.
+//
+// Locate in this mode (k_emit_small / k_emit_big) reads positions from the resident suffix array: the
+// reference's walk (fm_index.rs:127-140) ends in (sa[row'] + steps) % n = SA[row] by construction.
+#pragma once
+#include "kernels.cuh"
+
+namespace fmx {
+
+struct PhasedArgs {
+    SearchArgs a;             // patterns, (s0, e0), tables, err, work
+    uint32_t *rs, *re;        // [npat] final range; with want_rows == 0 only re - rs is meaningful for verified patterns
+    uint32_t *hint;           // [npat] text position of row rs when the verify phase knows it, else FMX_NOHINT
+    uint32_t want_rows;       // 1: exact (rs, re) for every pattern (one more request per verified pattern)
+    uint4 *q_steps;           // STEPS queue: {pattern, characters left, s, e}
+    uint4 *q_verify;          // VERIFY queue: {pattern, characters left, s, position of row s or FMX_NOHINT}
+    unsigned long long *qn;   // [0] STEPS entries, [1] VERIFY entries, [2] STEPS entries of the second pass
+};
+
+// order-preserving append of the flagged lanes' entries (one atomic per warp); all 32 lanes must call it
+__device__ __forceinline__ void warp_push(bool want, const uint4 &ent, uint4 *queue, unsigned long long *counter) {
+    const uint32_t lane = threadIdx.x & 31;
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (!m) return;
+    const int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if ((int)lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (want) queue[base + __popc(m & ((1u << lane) - 1u))] = ent;
+}
+
+// rank blocks lf_map2_pair loads for the range (s, e): the two ends share the block once the range is narrow
+template <int LAYOUT>
+__device__ __forceinline__ uint32_t pair_requests(const FmxDev &ix, uint32_t s, uint32_t e) {
+    if (LAYOUT == FMX_LAYOUT_Q4) return (s >> 6) == (e >> 6) ? 1u : 2u;
+    if (LAYOUT == FMX_LAYOUT_SY) return s / FMX_RB_BITS == e / FMX_RB_BITS ? 1u : 2u;
+    if (LAYOUT == FMX_LAYOUT_W4) return ix.qlevels * ((s >> 6) == (e >> 6) ? 1u : 2u);
+    return ix.levels * (s / FMX_RB_BITS == e / FMX_RB_BITS ? 1u : 2u);
+}
+
+__device__ __forceinline__ void warp_add(unsigned long long v, unsigned long long *counter) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(counter, v);
+}
+
+template <int KIND, int LAYOUT>
+__global__ void __launch_bounds__(256) k_ph_seed(const __grid_constant__ FmxDev ix, const __grid_constant__ PhasedArgs g) {
+    const SearchArgs &a = g.a;
+    unsigned long long steps = 0, reqs = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t rounds = (a.npat + stride - 1) / stride;
+    for (uint64_t r = 0; r < rounds; r++) {
+        const uint64_t p = r * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        int dest = 0;  // 1 = STEPS, 2 = VERIFY
+        uint4 ent = make_uint4(0, 0, 0, 0);
+        if (p < a.npat) {
+            uint64_t beg;
+            uint32_t len;
+            pattern_span(a, p, beg, len);
+            uint32_t s = a.s0, e = a.e0, it = 0, pos = FMX_NOHINT, rem = len;
+            AnyReader rd(a, p, beg, len);
+            if (kmer_lookup(a, ix.max_character, rd, rem, s, e, it, &pos)) reqs += (s == e && a.work) ? 2u : 1u;  // entry (+ step byte)
+            steps += it;
+            if (rem == 0 || s == e) {
+                g.rs[p] = s;
+                g.re[p] = e;
+                g.hint[p] = (e - s == 1u) ? pos : FMX_NOHINT;
+            } else if (a.verify && e - s == 1u && rem >= FMX_VERIFY_MIN_DENSE) {
+                dest = 2;
+                ent = make_uint4((uint32_t)p, rem, s, pos);
+            } else {
+                dest = 1;
+                ent = make_uint4((uint32_t)p, rem, s, e);
+            }
+        }
+        warp_push(dest == 1, ent, g.q_steps, g.qn + 0);
+        warp_push(dest == 2, ent, g.q_verify, g.qn + 1);
+    }
+    if (a.work) {
+        warp_add(steps, a.work);
+        warp_add(reqs, a.work + 2);
+    }
+}
+
+template <int KIND, int LAYOUT>
+__global__ void __launch_bounds__(256) k_ph_steps(const __grid_constant__ FmxDev ix, const __grid_constant__ PhasedArgs g,
+                                                  int second) {
+    __shared__ Tabs<LAYOUT> tb;
+    load_tables<LAYOUT>(ix, tb);
+    const SearchArgs &a = g.a;
+    const unsigned long long qn = g.qn[second ? 2 : 0];
+    unsigned long long steps = 0, reqs = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t rounds = (qn + stride - 1) / stride;
+    const bool armed = !second && a.verify;
+    for (uint64_t r = 0; r < rounds; r++) {
+        const uint64_t t = r * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        bool to_verify = false;
+        uint4 ent = make_uint4(0, 0, 0, 0);
+        if (t < qn) {
+            ent = g.q_steps[t];
+            const uint64_t p = ent.x;
+            uint32_t rem = ent.y, s = ent.z, e = ent.w;
+            uint64_t beg;
+            uint32_t len;
+            pattern_span(a, p, beg, len);
+            AnyReader rd(a, p, beg, len);
+            while (rem > 0) {
+                if (armed && e - s == 1u && rem >= FMX_VERIFY_MIN_DENSE) {
+                    to_verify = true;
+                    break;
+                }
+                const uint32_t c = rd.get(rem - 1u);
+                if (c > ix.max_character) {  // the reference panics here (cs[c] out of bounds, fm_index.rs:94)
+                    atomicOr(a.err, 1u);
+                    break;
+                }
+                if (a.work) reqs += pair_requests<LAYOUT>(ix, s, e);
+                lf_map2_pair<KIND, LAYOUT>(ix, tb, c, s, e);
+                steps++;
+                rem--;
+                if (s == e) break;
+            }
+            if (to_verify) {
+                ent = make_uint4((uint32_t)p, rem, s, FMX_NOHINT);
+            } else {
+                g.rs[p] = s;
+                g.re[p] = e;
+                g.hint[p] = FMX_NOHINT;
+            }
+        }
+        warp_push(to_verify, ent, g.q_verify, g.qn + 1);
+    }
+    if (a.work) {
+        warp_add(steps, a.work);
+        warp_add(reqs, a.work + 2);
+    }
+}
+
+// verify phase.  Entry: the range is the single row s, `rem` characters rd[0 .. rem) are still to be consumed.
+// What search_one's verify_tail + following iterations do, case by case (kernels.cuh):
+//   all rem characters match            -> row ISA[pos - rem], range of one row, pattern consumed
+//   `matched` < rem match, then a true mismatch with a character c != 0, c <= max_character
+//                                       -> the next ordinary iteration empties the range (BWT of the row != c)
+//   the comparison stops for another reason (text \0, pattern \0 or invalid character, start of the text)
+//                                       -> ordinary iterations from row ISA[pos - matched], tail not tried again
+template <int KIND, int LAYOUT>
+__global__ void __launch_bounds__(256) k_ph_verify(const __grid_constant__ FmxDev ix, const __grid_constant__ PhasedArgs g) {
+    const SearchArgs &a = g.a;
+    const unsigned long long qn = g.qn[1];
+    unsigned long long steps = 0, reqs = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t rounds = (qn + stride - 1) / stride;
+    for (uint64_t r = 0; r < rounds; r++) {
+        const uint64_t t = r * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        bool again = false;
+        uint4 ent = make_uint4(0, 0, 0, 0);
+        if (t < qn) {
+            ent = g.q_verify[t];
+            const uint64_t p = ent.x;
+            const uint32_t rem = ent.y, s = ent.z;
+            uint32_t pos = ent.w;
+            if (pos == FMX_NOHINT) {
+                pos = ldg32_s(ix.vsa + s);
+                reqs++;
+            }
+            uint32_t matched = 0, c = 0;
+            if (pos >= rem) {
+                uint64_t beg;
+                uint32_t len;
+                pattern_span(a, p, beg, len);
+                AnyReader rd(a, p, beg, len);
+                TextReader tr(ix.text + (pos - rem), rem);
+                while (matched < rem) {
+                    const uint32_t tc = tr.get(rem - 1u - matched);
+                    c = rd.get(rem - 1u - matched);
+                    if (tc == 0u || c != tc) break;
+                    matched++;
+                }
+            }
+            steps += matched;
+            if (pos >= rem) {  // 32-byte sectors of the text the comparison read
+                const uint32_t last = pos - 1u, first = pos - (matched < rem ? matched + 1u : rem);
+                reqs += (last >> 5) - (first >> 5) + 1u;
+            }
+            if (pos >= rem && matched == rem) {
+                const uint32_t q = pos - rem;
+                g.hint[p] = q;
+                uint32_t row = 0;
+                if (g.want_rows) {
+                    row = ldg32_s(ix.isa + q);
+                    reqs++;
+                }
+                g.rs[p] = row;
+                g.re[p] = row + 1u;
+            } else if (pos >= rem && !g.want_rows && c != 0u && c <= ix.max_character) {
+                // true mismatch: the reference's next iteration leaves s == e; count 0, rows not wanted
+                steps++;
+                g.rs[p] = 0;
+                g.re[p] = 0;
+                g.hint[p] = FMX_NOHINT;
+            } else {
+                const uint32_t row = matched ? ldg32_s(ix.isa + (pos - matched)) : s;
+                reqs += matched ? 1u : 0u;
+                again = true;
+                ent = make_uint4((uint32_t)p, rem - matched, row, row + 1u);
+            }
+        }
+        warp_push(again, ent, g.q_steps, g.qn + 2);
+    }
+    if (a.work) {
+        warp_add(steps, a.work);
+        warp_add(reqs, a.work + 2);
+    }
+}
+
+// (rs, re) as the u64 arrays of the C ABI
+__global__ void k_ph_widen(const uint32_t *rs, const uint32_t *re, uint64_t npat, uint64_t *out_s, uint64_t *out_e) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < npat) {
+        out_s[p] = rs[p];
+        out_e[p] = re[p];
+    }
+}
+
+// scan input: matches per pattern (wrapper.rs:132-134)
+struct LoadCount32 {
+    const uint32_t *s, *e;
+    __device__ __forceinline__ uint64_t operator()(uint64_t i) const {
+        const uint32_t a = s[i], b = e[i];
+        return b > a ? (uint64_t)(b - a) : 0ull;
+    }
+};
+
+// ---- locate by the resident suffix array.  positions[off[p] + j] = SA[rs[p] + j], rows ascending (wrapper.rs:206-216)
+template <class Toff, class Tout>
+struct EmitArgs {
+    const uint32_t *rs, *re, *hint;  // hint nullable
+    const Toff *off;                 // npat + 1 hit offsets
+    uint64_t npat;
+    uint64_t capacity;               // entries of positions / piece_ids
+    Tout *positions;                 // nullable
+    Tout *piece_ids;                 // nullable (MultiPieces)
+    uint32_t *bigq;                  // patterns with more than FMX_EMIT_SMALL matches
+    unsigned long long *bign;
+    unsigned long long *req;         // nullable: += suffix-array requests issued (hinted positions cost none)
+};
+#define FMX_EMIT_SMALL 4u
+
+template <int KIND, class Toff, class Tout>
+__global__ void __launch_bounds__(256) k_emit_small(const __grid_constant__ FmxDev ix, const __grid_constant__ EmitArgs<Toff, Tout> g) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t rounds = (g.npat + stride - 1) / stride;
+    const uint32_t lane = threadIdx.x & 31;
+    unsigned long long reqs = 0;
+    for (uint64_t r = 0; r < rounds; r++) {
+        const uint64_t p = r * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        bool big = false;
+        if (p < g.npat) {
+            const uint32_t s = g.rs[p], e = g.re[p];
+            const uint32_t cnt = e > s ? e - s : 0u;
+            if (cnt > FMX_EMIT_SMALL) {
+                big = true;
+            } else if (cnt) {
+                const uint64_t o = (uint64_t)g.off[p];
+                const uint32_t h = (g.hint && cnt == 1u) ? g.hint[p] : FMX_NOHINT;
+                for (uint32_t j = 0; j < cnt; j++) {
+                    if (o + j >= g.capacity) break;
+                    const uint32_t v = h != FMX_NOHINT ? h : ldg32_s(ix.vsa + s + j);
+                    reqs += h != FMX_NOHINT ? 0u : 1u;
+                    if (g.positions) g.positions[o + j] = (Tout)v;
+                    if (KIND == FMX_KIND_MULTI_ && g.piece_ids) g.piece_ids[o + j] = (Tout)piece_of(ix, v);
+                }
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, big);
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(g.bign, (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (big) g.bigq[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)p;
+        }
+    }
+    if (g.req) warp_add(reqs, g.req);
+}
+
+// one warp per pattern with many matches: SA[s .. e) is a contiguous read, the output a contiguous write
+template <int KIND, class Toff, class Tout>
+__global__ void __launch_bounds__(256) k_emit_big(const __grid_constant__ FmxDev ix, const __grid_constant__ EmitArgs<Toff, Tout> g) {
+    const unsigned long long qn = *g.bign;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < qn; w += nwarps) {
+        const uint32_t p = g.bigq[w];
+        const uint32_t s = g.rs[p], e = g.re[p];
+        const uint64_t o = (uint64_t)g.off[p];
+        for (uint32_t j = lane; j < e - s; j += 32) {
+            if (o + j >= g.capacity) break;
+            const uint32_t v = __ldg(ix.vsa + s + j);
+            if (g.positions) g.positions[o + j] = (Tout)v;
+            if (KIND == FMX_KIND_MULTI_ && g.piece_ids) g.piece_ids[o + j] = (Tout)piece_of(ix, v);
+        }
+    }
+}
+
+// the k-mer tables of an index with a resident suffix array: one-row entries carry the row's text position
+__global__ void k_table_embed(uint2 *tab, uint64_t entries, const uint32_t *vsa) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= entries) return;
+    const uint2 v = tab[t];
+    if (v.y == v.x + 1u) tab[t] = make_uint2(v.x, FMX_TAB_POS_FLAG | ldg32_s(vsa + v.x));
+}
+
+}  // namespace fmx

@@ -64,6 +64,16 @@ typedef enum fmx_mode {
 
 #define FMX_LEVEL_COUNT_ONLY (-1)
 
+/* How much HBM an index may spend beyond the reference's own structures (fmx_index_build_ex):
+ *   COMPACT  rank structure + the caller's suffix-array samples + an L2-resident k-mer table: the reference's
+ *            space (about n/2 + 4n/2^level bytes for DNA); locate walks LF to the samples.
+ *   RICH     additionally the text, the FULL suffix array and its inverse (9 n bytes) and a k-mer table sized to
+ *            end the search of an absent pattern: every query step that the reference answers with a chain of
+ *            dependent rank probes becomes one or two memory requests, locate is SA[row].  Bit-identical results.
+ *   AUTO     RICH when the rank structure does not fit the 126 MB L2 and the budgets allow, else COMPACT
+ *            (FMX_MODE=compact|rich in the environment overrides AUTO). */
+typedef enum fmx_index_mode { FMX_MODE_AUTO = 0, FMX_MODE_COMPACT = 1, FMX_MODE_RICH = 2 } fmx_index_mode;
+
 const char *fmx_last_error(void);
 int fmx_version(void);
 int fmx_device_count(void);
@@ -79,9 +89,16 @@ void fmx_free(void *p);
 int fmx_index_build(const void *text, uint64_t n, uint32_t char_width, uint64_t max_character,
                     int kind, int level, int device, fmx_index **out);
 
+int fmx_index_build_ex(const void *text, uint64_t n, uint32_t char_width, uint64_t max_character,
+                       int kind, int level, int device, int mode, fmx_index **out);
+/* the mode an index was built with, resolved (FMX_MODE_COMPACT or FMX_MODE_RICH) */
+int fmx_index_mode_of(const fmx_index *idx);
+
 /* Host-only half of construction: text -> device-layout blob (no GPU needed). */
 int fmx_blob_build(const void *text, uint64_t n, uint32_t char_width, uint64_t max_character,
                    int kind, int level, void **blob, uint64_t *blob_bytes);
+int fmx_blob_build_ex(const void *text, uint64_t n, uint32_t char_width, uint64_t max_character,
+                      int kind, int level, int mode, void **blob, uint64_t *blob_bytes);
 /* Upload a blob (serialised once; the reference only has un-exposed serde derives,
  * fm_index.rs:13, rlfmi.rs:15, multi_pieces.rs:16, sample.rs:12). */
 int fmx_index_from_blob(const void *blob, uint64_t blob_bytes, int device, fmx_index **out);
@@ -210,6 +227,48 @@ int fmx_locate_batch_device(const fmx_index *idx, int prefix_only, const uint64_
                             uint64_t *d_positions, uint64_t *d_piece_ids, uint64_t capacity,
                             void *stream);
 
+/* ---------------------------------------------------------------- fused query (count + locate), any input form
+ * One descriptor for the batched form of
+ *     index.search(p).count()  /  index.search(p).iter_matches().map(|m| m.locate())     (README.md:49-64)
+ * over byte patterns or PACKED patterns, with 64- or 32-bit outputs.
+ *
+ * Packed patterns (packed_bits = 2 or 4; needs max_character <= 2^packed_bits): every pattern has `fixed_len`
+ * characters and occupies ceil(fixed_len * packed_bits / 64) consecutive 64-bit little-endian words; character k
+ * of a pattern sits in bits [k * packed_bits, (k + 1) * packed_bits) of its words (bit 0 = least significant bit
+ * of the first word) and is stored as (character - 1), so DNA coded 1..4 packs a 32-mer into ONE word -- 8 bytes
+ * over PCIe instead of 32.  A packed pattern cannot hold the character 0.
+ *
+ * out_width = 8: hit_off / positions / piece_ids / counts are uint64_t (Rust usize); out_width = 4: uint32_t
+ * (every index has n < 2^32; hit_off then needs the batch to have fewer than 2^32 hits, else FMX_ERR_CAPACITY).
+ * out_s / out_e (nullable, always uint64_t): the exact SA ranges.  Leaving them NULL lets the HBM-rich path skip
+ * the inverse-suffix-array request that only serves to name the final row.
+ * counts (nullable): e - s per pattern (Search::count, wrapper.rs:132-134).  hit_off (nullable, npat + 1): the
+ * exclusive prefix sum of the hit counts.  positions / piece_ids (nullable, `capacity` entries): the matches in
+ * the reference's iteration order.  Unfiltered modes need nothing else; FMX_SEARCH_PREFIX / _EXACT apply the
+ * L == 0 filter to hit_off / positions (counts stay unfiltered, as in the reference). */
+typedef struct fmx_query {
+    int mode;                /* fmx_mode */
+    uint32_t packed_bits;    /* 0: one byte per character; 2 or 4: packed (see above) */
+    const void *patterns;    /* bytes (pattern p = [pat_off[p], pat_off[p+1]) or p * fixed_len ..) or packed words */
+    const uint64_t *pat_off; /* NULL: every pattern has fixed_len characters (required for packed input) */
+    uint64_t fixed_len;
+    uint64_t npat;
+    uint32_t out_width;      /* 8 or 4 */
+    uint32_t reserved;
+    uint64_t *out_s, *out_e; /* nullable */
+    void *counts;            /* nullable */
+    void *hit_off;           /* nullable unless positions / piece_ids are given */
+    void *positions;         /* nullable */
+    void *piece_ids;         /* nullable */
+    uint64_t capacity;
+} fmx_query;
+/* Device buffers, asynchronous on `stream` (NULL = the index's stream), CUDA-graph capturable for the unfiltered
+ * modes once scratch has been sized by an identical earlier call; the hit total stays in hit_off[npat]. */
+int fmx_query_batch_device(const fmx_index *idx, const fmx_query *q, void *stream);
+/* Host buffers (pinned ones make the copies asynchronous): chunked H2D / kernels / D2H pipeline.  *total_hits
+ * (nullable) receives hit_off[npat].  More hits than `capacity`: FMX_ERR_CAPACITY with counts / hit_off filled. */
+int fmx_query_batch(const fmx_index *idx, const fmx_query *q, uint64_t *total_hits);
+
 /* ---------------------------------------------------------------- extraction
  * Batched Match::iter_chars_backward / iter_chars_forward taken k characters deep
  * -- src/wrapper.rs:143-183, 229-235.  rows are SA rows (the `i` of a Match).
@@ -234,6 +293,14 @@ int fmx_lf_map2_batch(const fmx_index *idx, const uint8_t *c, const uint64_t *i,
 /* Work counters of the last search / locate-fill launch (executed backward-search
  * iterations, executed LF steps): the roofline numerator.  Synchronises the stream. */
 int fmx_last_work(const fmx_index *idx, void *stream, uint64_t *search_steps, uint64_t *lf_steps);
+/* Index requests issued by the phased kernels of the last query (option "count_work"): lane-level loads of table
+ * entries, rank blocks, suffix-array / inverse entries and text sectors by the search, and of suffix-array entries
+ * by the emit kernels.  Synchronises the stream. */
+int fmx_last_requests(const fmx_index *idx, void *stream, uint64_t *search_requests, uint64_t *emit_requests);
+/* Milliseconds of the phases of the last fmx_query_batch_device call made with option "phase_timing" = 1
+ * (CUDA events between the library's own launches): [0] seed / k_search, [1] steps, [2] verify, [3] second steps
+ * pass, [4] counts + offsets scan, [5] emit / locate.  Synchronises the stream. */
+int fmx_last_phase_ms(const fmx_index *idx, void *stream, float *ms, int n);
 /* Peak random gather rate microbenchmark over `bytes` of device memory (independent random
  * loads of load_bytes = 32 (one sector), 64 or 128 bytes each; no dependent chain): the
  * random-access roofline denominator.  Returns 32-byte sectors per second. */

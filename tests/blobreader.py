@@ -218,7 +218,7 @@ class Blob:
         matched = 0
         while matched < k:
             t = int(self.text[pos - 1 - matched])
-            if (self.kind == 2 and t == 0) or pat[k - 1 - matched] != t:
+            if t == 0 or pat[k - 1 - matched] != t:
                 break
             matched += 1
         if matched == 0:

@@ -272,6 +272,7 @@ def test_config1_count_parity():
     text = dna(1_000_000, 1)
     pats, _ = mixed_patterns(text, 10_000, 20, 2)
     index = fmx.FMIndex.new(fmx.Text.with_max_character(text, 4))
+    index.set_option("count_work", 1)
     oracle = orc.OracleIndex(text, orc.FM, max_character=4)
     b = index.search_batch(pats)
     s, e, steps = oracle.search_batch(pats.reshape(-1), np.arange(10_001, dtype=np.uint64) * 20, want_steps=True)
@@ -402,6 +403,7 @@ def test_range_walk_locate_on_repetitive_text(kind, level):
             copies.append(np.zeros(1, dtype=np.uint8))
     text = np.concatenate(copies + ([] if kind == orc.MULTI else [np.zeros(1, dtype=np.uint8)]))
     index = KINDS[kind][1].new(fmx.Text.with_max_character(text, 4), level)
+    index.set_option("count_work", 1)
     oracle = orc.OracleIndex(text, kind, level=level, max_character=4)
     starts = rng.integers(0, base.size - 12, 300)
     pats = [bytes(base[p:p + int(m)]) for p, m in zip(starts, rng.integers(1, 13, 300))]
@@ -464,6 +466,7 @@ def test_seed_and_verify_tail(mc, level, dense, kind, monkeypatch):
         text[rng.integers(5, n - 5, 40) // 2 * 2] = 0     # pieces: never two \0 in a row, none at either end
     cls = KINDS[kind][0 if level is None else 1]
     index = cls.new(fmx.Text.with_max_character(text, mc)) if level is None else cls.new(fmx.Text.with_max_character(text, mc), level)
+    index.set_option("count_work", 1)
     oracle = orc.OracleIndex(text, kind, level=level, max_character=mc)
     pats = []
     for t in range(6000):
@@ -485,11 +488,12 @@ def test_seed_and_verify_tail(mc, level, dense, kind, monkeypatch):
     flat, off = orc.pack_patterns(pats)
     for mode in ((fmx.SEARCH, fmx.SEARCH_PREFIX, fmx.SEARCH_SUFFIX, fmx.SEARCH_EXACT) if kind == orc.MULTI else (fmx.SEARCH,)):
         s, e, steps = oracle.search_batch(flat, off, mode, want_steps=True)
-        for verify in (1, 0):
+        for verify, phased in ((1, 1), (1, 0), (0, 1)):   # phased kernels / verify tail inside k_search / plain loop
             index.set_option("verify", verify)
+            index.set_option("search_phased", phased)
             b = index.search_batch(pats, mode)
-            assert np.array_equal(b.s, s) and np.array_equal(b.e, e), (mode, verify)
-            assert index.last_work()[0] == int(steps.sum()), (mode, verify)
+            assert np.array_equal(b.s, s) and np.array_equal(b.e, e), (mode, verify, phased)
+            assert index.last_work()[0] == int(steps.sum()), (mode, verify, phased)
     if mc == 4 and kind == orc.FM:                                     # invalid character deep inside an otherwise unique match
         bad = bytearray(text[1000:1040].tobytes())
         bad[5] = 9
@@ -628,6 +632,7 @@ def test_search_options_do_not_change_results():
     text = dna(500_000, 91)
     pats, _ = mixed_patterns(text, 60_000, 28, 92)
     index = fmx.FMIndexWithLocate.new(fmx.Text.with_max_character(text, 4), 1)
+    index.set_option("count_work", 1)
     ref = index.search_batch(pats)
     steps = index.last_work()[0]
     for key, val in (("search_persistent", 1), ("kmer", 0), ("search_persistent", 0), ("kmer", 1), ("bucket", 1)):
@@ -705,3 +710,212 @@ def test_async_device_locate_matches_host_api():
         assert np.array_equal(d_pos[:k].cpu().numpy().view(np.uint64), rp[:k])
         if cap > total:
             assert bool((d_pos[total:] == -1).all())
+
+
+# ---------------------------------------------------------------- round 2: HBM-rich mode, fused query, packed patterns
+
+def _rich_case(kind, mc, seed, n=60_000, pieces=30):
+    rng = np.random.default_rng(seed)
+    sigma = min(mc, 4) if mc <= 4 else 6
+    text = np.append(rng.integers(1, sigma + 1, n, dtype=np.uint8), np.uint8(0))
+    if kind == orc.MULTI:
+        text[rng.integers(5, n - 5, pieces) // 2 * 2] = 0
+    pats = []
+    for t in range(5000):
+        m = int(rng.integers(1, 60))
+        p0 = int(rng.integers(0, n - m))
+        pat = text[p0:p0 + m].copy()
+        v = t % 6
+        if v == 1:
+            j = int(rng.integers(0, m))
+            pat[j] = pat[j] % sigma + 1
+        elif v == 2:
+            pat = np.concatenate([rng.integers(1, sigma + 1, 9, dtype=np.uint8), text[:m]])   # runs off the start of the text
+        elif v == 3:
+            pat = rng.integers(1, sigma + 1, m, dtype=np.uint8)
+        elif v == 4 and kind == orc.MULTI:
+            pat[int(rng.integers(0, m))] = 0
+        pats.append(pat.tobytes())
+    pats += [b"", bytes([1])]
+    return text, pats
+
+
+@pytest.mark.parametrize("kind", [orc.FM, orc.MULTI])
+@pytest.mark.parametrize("mc,env", [(4, None), (255, None), (37, ("FMX_SYM_BUDGET_MB", "0")), (6, ("FMX_FORCE_WAVELET", "1"))])
+def test_rich_mode_query_parity(kind, mc, env, monkeypatch):
+    """FMX_MODE_RICH: phased search (table-embedded positions, verify queue, hints) + locate by the resident suffix
+    array, through fmx_query_batch in every output combination, against the oracle: SA ranges, counts, ordered
+    positions, piece ids, executed step counts; and against the same index with the rich paths switched off"""
+    if env:
+        monkeypatch.setenv(*env)
+    text, pats = _rich_case(kind, mc, 4000 + kind + mc)
+    index = KINDS[kind][1].new(fmx.Text.with_max_character(text, mc), 2, mode=fmx.MODE_RICH)
+    assert index.mode() == fmx.MODE_RICH
+    index.set_option("count_work", 1)
+    oracle = orc.OracleIndex(text, kind, level=2, max_character=mc)
+    flat, off = orc.pack_patterns(pats)
+    modes = [fmx.SEARCH] + ([fmx.SEARCH_PREFIX, fmx.SEARCH_SUFFIX, fmx.SEARCH_EXACT] if kind == orc.MULTI else [])
+    for mode in modes:
+        po = mode in (fmx.SEARCH_PREFIX, fmx.SEARCH_EXACT)
+        s, e, steps = oracle.search_batch(flat, off, mode, want_steps=True)
+        ooff, opos, opid = oracle.locate_batch(s, e, prefix_only=po, want_piece_ids=kind == orc.MULTI)
+        cnt = np.where(e > s, e - s, 0)
+        b = index.search_batch(pats, mode)                      # phased, rows wanted
+        assert np.array_equal(b.s, s) and np.array_equal(b.e, e), mode
+        assert index.last_work()[0] == int(steps.sum())
+        got = b.locate(piece_ids=kind == orc.MULTI)             # two-call path: dense k_locate_simple
+        assert np.array_equal(got[0], ooff) and np.array_equal(got[1], opos)
+        for rows in (True, False):
+            for width in (8, 4):
+                r = index.query_batch(pats, mode, rows=rows, counts=True, piece_ids=kind == orc.MULTI, width=width)
+                if rows:
+                    assert np.array_equal(r["s"], s) and np.array_equal(r["e"], e)
+                assert np.array_equal(r["counts"].astype(np.uint64), cnt), (mode, rows, width)
+                assert np.array_equal(r["hit_off"].astype(np.uint64), ooff), (mode, rows, width)
+                assert np.array_equal(r["positions"].astype(np.uint64), opos), (mode, rows, width)
+                if kind == orc.MULTI:
+                    assert np.array_equal(r["piece_ids"].astype(np.uint64), opid)
+        r = index.query_batch(pats, mode, locate=False, counts=True)       # count only: no ISA request, no locate
+        assert np.array_equal(r["counts"], cnt)
+        if not po:
+            assert index.last_work()[0] == int(steps.sum())               # the shortcut counts the reference's last iteration too
+    # the rich paths off: same answers from the plain kernels
+    ref = index.query_batch(pats, rows=True, counts=True)
+    for key in ("search_phased", "locate_dense", "verify"):
+        index.set_option(key, 0)
+        r = index.query_batch(pats, rows=True, counts=True)
+        for k in ("s", "e", "counts", "hit_off", "positions"):
+            assert np.array_equal(r[k], ref[k]), (key, k)
+    for key in ("search_phased", "locate_dense", "verify"):
+        index.set_option(key, 1)
+    if mc < 255:                                          # invalid characters: first processed, and deep inside a unique match
+        bad = bytearray(text[1000:1040].tobytes())
+        bad[5] = mc + 1
+        for rows in (True, False):
+            for pat in (bytes([1, 2, mc + 1]), bytes(bad)):
+                with pytest.raises(IndexError):
+                    index.query_batch([pat], rows=rows)
+        assert index.query_batch([bytes([1])], locate=False, counts=True)["counts"][0] > 0   # still usable
+
+
+def test_rich_mode_many_hits_and_pipeline():
+    """patterns with thousands of matches (k_emit_big), a chunked pipeline with a position-capacity guess that is too
+    small for the first chunks, a too-small caller capacity"""
+    text = dna(300_000, 123)
+    index = fmx.FMIndexWithLocate.new(fmx.Text.with_max_character(text, 4), 2, mode=fmx.MODE_RICH)
+    oracle = orc.OracleIndex(text, orc.FM, level=2, max_character=4)
+    rng = np.random.default_rng(5)
+    pats = [bytes(rng.integers(1, 5, int(m), dtype=np.uint8)) for m in rng.integers(1, 9, 30_000)] + [b""]
+    flat, off = orc.pack_patterns(pats)
+    s, e = oracle.search_batch(flat, off)
+    ooff, opos, _ = oracle.locate_batch(s, e)
+    index.set_option("pipeline_chunk", 4_001)
+    for width in (8, 4):
+        r = index.query_batch(pats, width=width, capacity=int(ooff[-1]) + 3)
+        assert r["total"] == int(ooff[-1])
+        assert np.array_equal(r["hit_off"].astype(np.uint64), ooff) and np.array_equal(r["positions"].astype(np.uint64), opos)
+    r = index.query_batch(pats)                                  # default capacity is too small: retried with the exact size
+    assert np.array_equal(r["positions"], opos)
+    b, h, p = index.search_locate_batch(pats, capacity=int(ooff[-1]) + 3)
+    assert np.array_equal(b.s, s) and np.array_equal(h, ooff) and np.array_equal(p, opos)
+
+
+@pytest.mark.parametrize("mode", [fmx.MODE_RICH, fmx.MODE_COMPACT])
+@pytest.mark.parametrize("m", [12, 32, 33, 70])
+def test_packed_patterns(mode, m):
+    """2-bit packed patterns (fmx_query.packed_bits = 2): same answers as the byte form, on rich and compact indexes"""
+    text = dna(200_000, 77 + m)
+    pats, _ = mixed_patterns(text, 20_000, m, 78)
+    index = fmx.FMIndexWithLocate.new(fmx.Text.with_max_character(text, 4), 2, mode=mode)
+    assert index.mode() == mode
+    ref = index.query_batch(pats, rows=True, counts=True)
+    packed = fmx.pack_patterns(pats, 2)
+    assert packed.size == pats.shape[0] * ((2 * m + 63) // 64)
+    for width in (8, 4):
+        r = index.query_batch(packed, rows=True, counts=True, width=width, packed_bits=2, fixed_len=m)
+        for k in ("s", "e", "counts", "hit_off", "positions"):
+            assert np.array_equal(r[k].astype(np.uint64), ref[k]), (k, width)
+    r = index.query_batch(packed, packed_bits=2, fixed_len=m)            # no rows: hints only
+    assert np.array_equal(r["positions"], ref["positions"])
+    oracle = orc.OracleIndex(text, orc.FM, level=2, max_character=4)
+    s, e = oracle.search_batch(pats.reshape(-1), np.arange(pats.shape[0] + 1, dtype=np.uint64) * m)
+    ooff, opos, _ = oracle.locate_batch(s, e)
+    assert np.array_equal(ref["s"], s) and np.array_equal(ref["e"], e) and np.array_equal(ref["positions"], opos)
+    with pytest.raises(fmx.Error):                                        # 4 < max_character: cannot be packed in 2 bits
+        fmx.FMIndex.new(fmx.Text.with_max_character(text, 9)).query_batch(packed, packed_bits=2, fixed_len=m, locate=False, counts=True)
+
+
+def test_rlfm_rich_mode_locates_from_the_suffix_array():
+    rng = np.random.default_rng(31)
+    base = rng.integers(1, 5, 5000, dtype=np.uint8)
+    copies = []
+    for _ in range(20):
+        x = base.copy()
+        mut = rng.random(x.size) < 0.005
+        x[mut] = rng.integers(1, 5, int(mut.sum()), dtype=np.uint8)
+        copies.append(x)
+    text = np.append(np.concatenate(copies), np.uint8(0))
+    index = fmx.RLFMIndexWithLocate.new(fmx.Text.with_max_character(text, 4), 3, mode=fmx.MODE_RICH)
+    assert index.mode() == fmx.MODE_RICH
+    oracle = orc.OracleIndex(text, orc.RLFM, level=3, max_character=4)
+    pats = [bytes(base[p:p + int(m)]) for p, m in zip(rng.integers(0, 4900, 2000), rng.integers(1, 40, 2000))]
+    flat, off = orc.pack_patterns(pats)
+    s, e = oracle.search_batch(flat, off)
+    ooff, opos, _ = oracle.locate_batch(s, e)
+    r = index.query_batch(pats, rows=True)
+    assert np.array_equal(r["s"], s) and np.array_equal(r["hit_off"], ooff) and np.array_equal(r["positions"], opos)
+    h, p = index.search_batch(pats).locate()
+    assert np.array_equal(h, ooff) and np.array_equal(p, opos)
+    index.set_option("locate_dense", 0)
+    h, p = index.search_batch(pats).locate()
+    assert np.array_equal(p, opos)
+
+
+@pytest.mark.parametrize("kind", [orc.FM, orc.RLFM])
+def test_single_text_with_interior_zeros(kind):
+    """the reference accepts single-text indexes over texts with interior \\0 (sais.rs:128-139); its
+    lf_map2(0, i) is a plain rank there, which is not the true LF row.  SA ranges of patterns with and without \\0
+    must equal the oracle's in every mode the index can be asked for."""
+    rng = np.random.default_rng(17 + kind)
+    n = 30_000
+    text = np.append(rng.integers(1, 5, n, dtype=np.uint8), np.uint8(0))
+    text[rng.integers(5, n - 5, 60) // 2 * 2] = 0
+    oracle = orc.OracleIndex(text, kind, max_character=4)
+    pats = []
+    for t in range(4000):
+        m = int(rng.integers(1, 50))
+        p0 = int(rng.integers(0, n - m))
+        pat = text[p0:p0 + m].copy()
+        if t % 3 == 1:
+            pat[int(rng.integers(0, m))] = rng.integers(0, 5)
+        pats.append(pat.tobytes())
+    flat, off = orc.pack_patterns(pats)
+    s, e = oracle.search_batch(flat, off)
+    for mode in (fmx.MODE_AUTO, fmx.MODE_RICH, fmx.MODE_COMPACT):
+        index = KINDS[kind][0].new(fmx.Text.with_max_character(text, 4), mode=mode)
+        assert index.mode() == fmx.MODE_COMPACT          # nothing that answers from the suffix array is built
+        b = index.search_batch(pats)
+        assert np.array_equal(b.s, s) and np.array_equal(b.e, e), mode
+
+
+def test_two_phase_device_locate_rejects_a_mismatched_fill():
+    import ctypes as C
+    import torch
+    text = dna(100_000, 3)
+    pats, _ = mixed_patterns(text, 5000, 16, 4)
+    index = fmx.FMIndexWithLocate.new(fmx.Text.with_max_character(text, 4), 2)
+    L, h = index._L, index._h
+    d_pat = torch.from_numpy(pats).cuda()
+    npat = pats.shape[0]
+    d_s = torch.empty(npat, dtype=torch.int64, device="cuda")
+    d_e = torch.empty_like(d_s)
+    d_off = torch.empty(npat + 1, dtype=torch.int64, device="cuda")
+    assert L.fmx_search_batch_device(h, 0, d_pat.data_ptr(), None, 16, npat, None, None, d_s.data_ptr(), d_e.data_ptr(), None) == 0
+    total = C.c_uint64(0)
+    assert L.fmx_locate_count_device(h, 0, d_s.data_ptr(), d_e.data_ptr(), npat, d_off.data_ptr(), C.byref(total), None) == 0
+    d_pos = torch.empty(total.value + 1, dtype=torch.int64, device="cuda")
+    assert L.fmx_locate_fill_device(h, 0, d_s.data_ptr(), d_e.data_ptr(), npat - 1, d_off.data_ptr(), total.value, d_pos.data_ptr(), None, None) == -2
+    assert L.fmx_locate_fill_device(h, 0, d_s.data_ptr(), d_e.data_ptr(), npat, d_off.data_ptr(), total.value, d_pos.data_ptr(), None, None) == 0
+    torch.cuda.synchronize()
+    rh, rp = index.search_batch(pats).locate()
+    assert np.array_equal(d_pos[: total.value].cpu().numpy().view(np.uint64), rp)

@@ -7,26 +7,30 @@ from hypothesis import HealthCheck, given, settings
 from hypothesis import strategies as st
 
 import fmx_pkg
-from blobreader import Blob
+from blobreader import SEC_VSA, Blob
 from oracle import oracle as orc
 from refutil import build_text
 
 fmx = fmx_pkg.load()
 
-ENVS = [{}, {"FMX_SYM_BUDGET_MB": "0"}, {"FMX_FORCE_WAVELET": "1"}, {"FMX_VERIFY_BUDGET_MB": "0"}]
+ENVS = [{}, {"FMX_SYM_BUDGET_MB": "0"}, {"FMX_FORCE_WAVELET": "1"}, {"FMX_VERIFY_BUDGET_MB": "0"}, {"FMX_MODE": "rich"},
+        {"FMX_MODE": "rich", "FMX_SYM_BUDGET_MB": "0"}, {"FMX_MODE": "compact"}]
 
 
 @settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
 @given(seed=st.integers(0, 2**31 - 1), kind=st.sampled_from([0, 1, 2]), mc=st.sampled_from([1, 2, 4, 5, 9, 37, 255]),
-       level=st.sampled_from([None, 0, 1, 2, 3, 6]), env=st.sampled_from(ENVS), n=st.integers(2, 5000))
-def test_blob_answers_like_the_oracle(seed, kind, mc, level, env, n, monkeypatch):
-    for k in ("FMX_SYM_BUDGET_MB", "FMX_FORCE_WAVELET", "FMX_VERIFY_BUDGET_MB", "FMX_NO_VERIFY"):
+       level=st.sampled_from([None, 0, 1, 2, 3, 6]), env=st.sampled_from(ENVS), n=st.integers(2, 5000),
+       interior=st.booleans())
+def test_blob_answers_like_the_oracle(seed, kind, mc, level, env, n, interior, monkeypatch):
+    """`interior`: single-text kinds over a text WITH interior zeros (the reference accepts them, sais.rs:128-139)
+    and patterns that contain \\0 -- the case ADVICE r1 found the verify tail wrong on."""
+    for k in ("FMX_SYM_BUDGET_MB", "FMX_FORCE_WAVELET", "FMX_VERIFY_BUDGET_MB", "FMX_NO_VERIFY", "FMX_MODE"):
         monkeypatch.delenv(k, raising=False)
     monkeypatch.setenv("FMX_VERIFY_MIN_RANK_MB", "0")
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     rng = np.random.default_rng(seed)
-    multi = kind == 2
+    multi = kind == 2 or interior
     alpha = min(mc + 1, 9) if multi else min(mc, 8)
     if multi and alpha < 2:
         alpha = 2
@@ -45,7 +49,9 @@ def test_blob_answers_like_the_oracle(seed, kind, mc, level, env, n, monkeypatch
     for i in rows:
         c, nx = b.lf_step(i)
         assert c == o.get_l(i) and nx == o.lf_map(i)
-        if level is not None:
+        # (single-text kinds with interior zeros: LF is a permutation with several cycles, and the reference's own
+        # get_sa walk never ends on a cycle without a sampled row -- not comparable)
+        if level is not None and not (interior and kind != 2):
             assert b.get_sa(i) == o.get_sa(i)
     pats = []
     for _ in range(25):
@@ -57,9 +63,17 @@ def test_blob_answers_like_the_oracle(seed, kind, mc, level, env, n, monkeypatch
         if not multi and 0 in pat:
             continue
         pats.append(bytes(pat))
+    if interior and kind != 2:
+        assert b.verify == 0 and b.sec[SEC_VSA][1] == 0   # nothing that answers from the suffix array is built
+    elif env.get("FMX_MODE") == "rich" and n >= 64 and "FMX_VERIFY_BUDGET_MB" not in env:
+        assert b.sec[SEC_VSA][1] == 4 * n if (kind != 1 or level is not None) else True
+        if kind != 1:
+            assert b.verify == 1 and np.array_equal(b.vsa, orc.suffix_array(text).astype(np.uint32))
+    elif env.get("FMX_MODE") == "compact":
+        assert b.verify == 0 and b.sec[SEC_VSA][1] == 0
     for pat in pats:
         flat, off = orc.pack_patterns([pat])
-        for mode in ((0, 1, 2, 3) if multi else (0,)):
+        for mode in ((0, 1, 2, 3) if kind == 2 else (0,)):
             s, e, steps = o.search_batch(flat, off, mode, want_steps=True)
             assert b.search(list(pat), mode) == (int(s[0]), int(e[0]))
             if kind != 1:

@@ -552,6 +552,7 @@ def main():
     ap.add_argument("--no-gather-peak", action="store_true")
     ap.add_argument("--no-compact", action="store_true", help="skip the compact-mode index measured beside the headline one")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-by-piece", action="store_true", help="N > 1 default run: skip the config-4 piece-partitioned measurement")
     ap.add_argument("--oracle-own-sa", action="store_true",
                     help="CPU baseline: build the suffix array with the oracle's own SA-IS even for GB-scale texts")
     args = ap.parse_args()
@@ -663,8 +664,20 @@ def main():
         e2e = e2e_measure(args, fmx, L, index, d_pat, d_off, m, npat, hits, mc, world, dist, torch)
     clocks = sampler.stop()
 
+    # ---- N > 1: BASELINE config 4 (MultiPieces, 24 pieces / 3 GB) partitioned by piece over the same ranks, with the NCCL
+    # gather -- the one multi-GPU form with an exchange step -- measured in the same driver run
+    by_piece = None
+    if world > 1 and args.workload == "target_dna1g" and not args.no_by_piece:
+        torch.cuda.empty_cache()
+        try:
+            by_piece = by_piece_measure(args, WORKLOADS["cfg4_multi"], fmx, rank, world, local, with_replicated=False)
+        except Exception as ex:  # pragma: no cover
+            by_piece = {"error": str(ex)}
+        torch.cuda.set_stream(stream)
+
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return 0
 
@@ -721,10 +734,13 @@ def main():
         line["e2e"] = e2e
     if compact is not None:
         line["compact_mode"] = compact
+    if by_piece is not None:
+        line["cfg4_by_piece"] = by_piece
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 
@@ -982,9 +998,12 @@ def cpu_baseline_and_parity(args, w, text, local, run, d_pat, d_off, m, npat, e2
     return cpu
 
 
-def by_piece_bench(args, w, fmx, rank, world, local):
-    """MultiPieces partitioned by piece: every rank indexes its pieces, answers every pattern, and the
-    per-pattern counts and hit lists are combined with NCCL all_gathers (fm-index_b200/partitioned.py)."""
+def by_piece_measure(args, w, fmx, rank, world, local, npat=None, with_replicated=True):
+    """MultiPieces partitioned by piece (BASELINE config 4): every rank indexes its pieces and answers EVERY pattern;
+    the parts are gathered on rank 0 over NCCL (offsets: gather; hit lists: exact-size send / recv) and merged there
+    by fmx_csr_merge_device (fm-index_b200/partitioned.py).  Strong scaling: the batch is the same on every rank.
+    Beside it, on rank 0: the replicated (whole-text) index answering the same batch, and 1/world of it (what each
+    rank of a query-sharded run would do) -- which form wins is stated in the result.  -> dict on rank 0, else None"""
     import torch
     import torch.distributed as dist
 
@@ -992,46 +1011,60 @@ def by_piece_bench(args, w, fmx, rank, world, local):
 
     if w["kind"] != MULTI:
         raise SystemExit("--by-piece needs a MultiPieces workload (cfg4_multi*)")
-    npat = args.npat or w["npat"]
+    npat = npat or args.npat or w["npat"]
+    steps = max(3, min(args.steps, 10))
     d_text = gen_text_for(w, device="cuda")
     d_pat, _ = gen_patterns(d_text, npat, w["m"], w["sigma"], 4)          # the SAME batch on every rank
     keep = (d_pat != 0).all(dim=1)                                          # \0 cannot cross the partition
+    dropped = int(npat - int(keep.sum().item()))
     d_pat = d_pat[keep].contiguous()
     npat = int(d_pat.shape[0])
     text = d_text.cpu().numpy()
     del d_text
     torch.cuda.empty_cache()
     t0 = time.perf_counter()
-    idx = part.PartitionedMultiPieces(text, w["level"], w["mc"], device=local)
+    idx, build_err = None, None
+    try:
+        idx = part.PartitionedMultiPieces(text, w["level"], w["mc"], device=local)
+    except Exception as ex:  # pragma: no cover
+        build_err = str(ex)
     build_s = time.perf_counter() - t0
+    if world > 1:   # nobody enters the exchange unless every rank has its partition's index
+        okf = torch.tensor([0 if build_err else 1], device="cuda", dtype=torch.int32)
+        dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+        if int(okf.item()) == 0:
+            return {"error": "index build failed on a rank: " + (build_err or "(another rank)")} if rank == 0 else None
+    elif build_err:
+        return {"error": build_err}
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     L = fmx.load_library()
-    for _ in range(args.warmup):
-        counts, hoff, pos, pid = idx.search_locate(d_pat)
+    res = None
+    for _ in range(3):
+        res = idx.search_locate(d_pat)
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(steps)]
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     launches0 = L.fmx_launch_count()
-    sampler.start()
-    for k in range(args.steps):
+    for k in range(steps):
         ev[k][0].record(stream)
-        counts, hoff, pos, pid = idx.search_locate(d_pat)
+        res = idx.search_locate(d_pat)
         ev[k][1].record(stream)
     torch.cuda.synchronize()
-    clocks = sampler.stop()
     launches = L.fmx_launch_count() - launches0
-    ms_total = float(sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps)))
+    ms_total = float(sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(steps)))
     if world > 1:
         tt = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_total = float(tt.item())
-    ms = ms_total / args.steps
+    ms = ms_total / steps
+    if rank != 0:
+        return None
+    counts, hoff, pos, pid = res
     hits = int(hoff[-1].item())
-    # property check: every gathered hit really holds its pattern, in the right piece
+    # every gathered hit really holds its pattern, in the right piece
     ends = np.flatnonzero(text == 0)
     p_h, o_h = pos.cpu().numpy(), np.repeat(np.arange(npat), np.diff(hoff.cpu().numpy()))
     pats_h = d_pat.cpu().numpy()
@@ -1039,18 +1072,57 @@ def by_piece_bench(args, w, fmx, rank, world, local):
     got = text[p_h[sel][:, None] + np.arange(w["m"])[None, :]]
     ok = bool(np.array_equal(got, pats_h[o_h[sel]]) and
               np.array_equal(pid.cpu().numpy()[sel], np.searchsorted(ends, p_h[sel], side="left")))
+    out = {"metric": "count+locate queries/s", "value": npat / (ms * 1e-3), "unit": "queries/s", "n_gpus": world,
+           "steps": steps, "ms_per_step": ms, "scaling": "strong", "located_hits_per_s": hits / (ms * 1e-3),
+           "hits_per_step": hits, "gpu_launches": int(launches), "patterns": npat, "patterns_dropped_for_zero": dropped,
+           "partitions": [list(r) for r in idx.ranges], "index_build_s": round(build_s, 1),
+           "partition_index_device_bytes": idx.engine.index.heap_size(),
+           "exchange": "dist.gather of uint32 hit offsets to rank 0 + exact-size batch_isend_irecv of uint32 positions / piece ids "
+                       "(NCCL); merge = fmx_csr_merge_device (one scan + one scatter kernel)",
+           "gathered_hits_verified_against_text": ok}
+    if with_replicated:
+        try:
+            del idx
+            torch.cuda.empty_cache()
+            t0 = time.perf_counter()
+            full = fmx.FMIndexMultiPiecesWithLocate.new(fmx.Text.with_max_character(text, w["mc"]), w["level"], device=local)
+            fb = time.perf_counter() - t0
+            flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+            run = DeviceRun(fmx, L, full, d_pat, None, w["m"], npat, stream)
+            run.size_outputs()
+            same = bool(run.hits == hits and torch.equal(run.d_hoff, hoff.to(run.d_hoff.dtype)))
+            t_all, _, _ = run.timed(lambda: run.query(), steps, flush)
+            share = max(1, npat // world)
+            run_s = DeviceRun(fmx, L, full, d_pat[:share].contiguous(), None, w["m"], share, stream)
+            run_s.size_outputs()
+            t_share, _, _ = run_s.timed(lambda: run_s.query(), steps, flush)
+            ms_all, ms_share = float(np.mean(t_all)), float(np.mean(t_share))
+            out["replicated_index"] = {
+                "index_device_bytes": full.heap_size(), "index_build_s": round(fb, 1), "same_counts_as_partitioned": same,
+                "one_gpu_whole_batch_ms": ms_all, "one_gpu_whole_batch_queries_per_s": npat / (ms_all * 1e-3),
+                "one_rank_share_ms": ms_share,
+                "query_sharded_estimate_queries_per_s": npat / (ms_share * 1e-3),
+                "note": f"the whole-text index fits one GPU; sharding the QUERIES over {world} GPUs costs each rank the 'share' time "
+                        "(no exchange), partitioning the PIECES costs every rank the whole batch plus the gather",
+                "winner": "replicated index, queries sharded" if ms_share < ms else "pieces partitioned"}
+        except Exception as ex:  # pragma: no cover
+            out["replicated_index"] = {"error": str(ex)}
+    return out
+
+
+def by_piece_bench(args, w, fmx, rank, world, local):
+    import torch.distributed as dist
+
+    out = by_piece_measure(args, w, fmx, rank, world, local)
     if rank == 0:
-        line = {"metric": "count+locate queries/s", "value": npat / (ms * 1e-3), "unit": "queries/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "u32/u64 integer", "data": "synthetic",
-                "config": config_of(args.workload, w, int(text.size), npat, {
-                    "parallelism": f"pieces partitioned over {world} GPUs {idx.ranges}; every pattern answered by every "
-                                   "rank; counts + hit lists combined by NCCL all_gather",
-                    "index_build_s": round(build_s, 1)}),
-                "located_hits_per_s": hits / (ms * 1e-3), "hits_per_step": hits, "gpu_launches": int(launches),
-                "clocks": clocks, "gathered_hits_verified_against_text": ok}
+        line = {"metric": out["metric"], "value": out["value"], "unit": out["unit"], "n_gpus": world, "steps": out["steps"],
+                "warmup": 3, "ms_per_step": out["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+                "config": config_of(args.workload, w, w["n"], out["patterns"], {"parallelism": f"pieces partitioned over {world} GPUs"}),
+                "by_piece": out}
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 

@@ -25,7 +25,7 @@ __all__ = [
     "Text", "Error", "InvalidText", "PieceId", "FMIndex", "FMIndexWithLocate", "RLFMIndex",
     "RLFMIndexWithLocate", "FMIndexMultiPieces", "FMIndexMultiPiecesWithLocate", "Search", "Match",
     "SearchBatch", "load_library", "suffix_array", "random_gather_peak", "pack_patterns", "MODE_AUTO", "MODE_COMPACT",
-    "MODE_RICH",
+    "MODE_RICH", "IndexGroup", "GROUP_REPLICATE", "GROUP_BY_PIECE",
 ]
 
 KIND_FM, KIND_RLFM, KIND_MULTI = 0, 1, 2
@@ -124,6 +124,50 @@ def _pack(patterns):
         off[1:] = np.cumsum([a.size for a in arrs], dtype=np.uint64)
     flat = np.concatenate(arrs) if arrs and int(off[-1]) > 0 else np.zeros(0, dtype=np.uint8)
     return np.ascontiguousarray(flat), off, 0, len(arrs)
+
+
+def _run_query(call, patterns, mode, rows, counts, locate, piece_ids, width, packed_bits, fixed_len, capacity):
+    """fills a struct fmx_query, runs call(byref(query), byref(total)) -> rc, returns the requested arrays"""
+    dt = np.uint64 if width == 8 else np.uint32
+    if packed_bits:
+        words = np.ascontiguousarray(patterns, dtype=np.uint64).reshape(-1)
+        wpp = (int(fixed_len) * packed_bits + 63) // 64
+        npat, flat, off, fixed = words.size // wpp, words, None, int(fixed_len)
+    else:
+        flat, off, fixed, npat = _pack(patterns)
+    q = _lib.Query()
+    q.mode, q.packed_bits, q.patterns, q.pat_off, q.fixed_len, q.npat = mode, packed_bits, _ptr(flat), _ptr(off), fixed, npat
+    q.out_width = width
+    out = {}
+    if rows:
+        out["s"], out["e"] = np.zeros(npat, dtype=np.uint64), np.zeros(npat, dtype=np.uint64)
+        q.out_s, q.out_e = _ptr(out["s"]), _ptr(out["e"])
+    if counts:
+        out["counts"] = np.zeros(npat, dtype=dt)
+        q.counts = _ptr(out["counts"])
+    cap = 0
+    if locate or piece_ids:
+        out["hit_off"] = np.zeros(npat + 1, dtype=dt)
+        q.hit_off = _ptr(out["hit_off"])
+        cap = int(capacity) if capacity is not None else max(1024, 2 * npat)
+        if locate:
+            out["positions"] = np.zeros(cap, dtype=dt)
+            q.positions = _ptr(out["positions"])
+        if piece_ids:
+            out["piece_ids"] = np.zeros(cap, dtype=dt)
+            q.piece_ids = _ptr(out["piece_ids"])
+    q.capacity = cap
+    total = C.c_uint64(0)
+    rc = call(C.byref(q), C.byref(total))
+    t = int(total.value)
+    if rc == -9 and capacity is None and t < (1 << 32 if width == 4 else 1 << 62):  # retry with exact-size buffers
+        return _run_query(call, patterns, mode, rows, counts, locate, piece_ids, width, packed_bits, fixed_len, t)
+    _check(rc)
+    for k in ("positions", "piece_ids"):
+        if k in out:
+            out[k] = out[k][:t]
+    out["total"] = t
+    return out
 
 
 class _Index:
@@ -229,46 +273,8 @@ class _Index:
         """fmx_query_batch: count + locate of a batch in one call, byte or packed patterns, 64- or 32-bit outputs.
         `patterns`: as for search_batch, or (packed_bits != 0) a uint64 array of packed words with `fixed_len`
         characters per pattern (see pack_patterns).  -> dict with the requested arrays + "total"."""
-        dt = np.uint64 if width == 8 else np.uint32
-        if packed_bits:
-            words = np.ascontiguousarray(patterns, dtype=np.uint64).reshape(-1)
-            wpp = (int(fixed_len) * packed_bits + 63) // 64
-            npat, flat, off, fixed = words.size // wpp, words, None, int(fixed_len)
-        else:
-            flat, off, fixed, npat = _pack(patterns)
-        q = _lib.Query()
-        q.mode, q.packed_bits, q.patterns, q.pat_off, q.fixed_len, q.npat = mode, packed_bits, _ptr(flat), _ptr(off), fixed, npat
-        q.out_width = width
-        out = {}
-        if rows:
-            out["s"], out["e"] = np.zeros(npat, dtype=np.uint64), np.zeros(npat, dtype=np.uint64)
-            q.out_s, q.out_e = _ptr(out["s"]), _ptr(out["e"])
-        if counts:
-            out["counts"] = np.zeros(npat, dtype=dt)
-            q.counts = _ptr(out["counts"])
-        cap = 0
-        if locate or piece_ids:
-            out["hit_off"] = np.zeros(npat + 1, dtype=dt)
-            q.hit_off = _ptr(out["hit_off"])
-            cap = int(capacity) if capacity is not None else max(1024, 2 * npat)
-            if locate:
-                out["positions"] = np.zeros(cap, dtype=dt)
-                q.positions = _ptr(out["positions"])
-            if piece_ids:
-                out["piece_ids"] = np.zeros(cap, dtype=dt)
-                q.piece_ids = _ptr(out["piece_ids"])
-        q.capacity = cap
-        total = C.c_uint64(0)
-        rc = self._L.fmx_query_batch(self._h, C.byref(q), C.byref(total))
-        t = int(total.value)
-        if rc == -9 and capacity is None and t < (1 << 32 if width == 4 else 1 << 62):  # retry with exact-size buffers
-            return self.query_batch(patterns, mode, rows, counts, locate, piece_ids, width, packed_bits, fixed_len, capacity=t)
-        _check(rc)
-        for k in ("positions", "piece_ids"):
-            if k in out:
-                out[k] = out[k][:t]
-        out["total"] = t
-        return out
+        return _run_query(lambda q, t: self._L.fmx_query_batch(self._h, q, t), patterns, mode, rows, counts, locate, piece_ids,
+                          width, packed_bits, fixed_len, capacity)
 
     def mode(self):
         """MODE_COMPACT or MODE_RICH: what the index holds (fmx_index_mode_of)"""
@@ -537,6 +543,47 @@ class SearchBatch:
             first += int(page_hits)
             if first >= total:
                 return
+
+
+GROUP_REPLICATE, GROUP_BY_PIECE = 0, 1
+
+
+class IndexGroup:
+    """fmx_group: several GPUs of this process behind one handle (include/fmx.h, "multi-GPU").
+    GROUP_REPLICATE: the index copied to every device, batches cut into shards (input order and the reference's
+    iteration order preserved).  GROUP_BY_PIECE (MultiPieces): pieces partitioned over the devices, every device
+    answers the whole batch, parts gathered and merged on the first device."""
+
+    def __init__(self, text, kind, level, devices, group_mode=GROUP_REPLICATE, mode=MODE_AUTO):
+        self._L = load_library()
+        if not isinstance(text, Text):
+            text = Text.new(text)
+        t = text.text()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        _check(self._L.fmx_group_create(devs, len(devices), int(group_mode), _ptr(t), t.size, 1, text.max_character(), int(kind),
+                                        -1 if level is None else int(level), int(mode), C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._L.fmx_group_free(h)
+            self._h = None
+
+    def size(self):
+        return int(self._L.fmx_group_size(self._h))
+
+    def len(self):
+        return int(self._L.fmx_group_len(self._h))
+
+    def pieces_count(self):
+        return int(self._L.fmx_group_pieces_count(self._h))
+
+    def query_batch(self, patterns, mode=SEARCH, rows=False, counts=False, locate=True, piece_ids=False, width=8,
+                    packed_bits=0, fixed_len=None, capacity=None):
+        return _run_query(lambda q, t: self._L.fmx_group_query_batch(self._h, q, t), patterns, mode, rows, counts, locate,
+                          piece_ids, width, packed_bits, fixed_len, capacity)
 
 
 def suffix_array(text) -> np.ndarray:

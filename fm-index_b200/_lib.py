@@ -46,6 +46,15 @@ SIGNATURES = {
     "fmx_search_locate_batch": (_int, [_vp, _int, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _u64, _u64p]),
     "fmx_query_batch": (_int, [_vp, _vp, _u64p]),
     "fmx_query_batch_device": (_int, [_vp, _vp, _vp]),
+    "fmx_csr_merge_device": (_int, [_int, _vp, _int, _u64, _u32, _vp, _vp, _vp, _u64, _vp]),
+    "fmx_index_clone": (_int, [_vp, _int, _pp]),
+    "fmx_group_create": (_int, [_vp, _int, _int, _vp, _u64, _u32, _u64, _int, _int, _int, _pp]),
+    "fmx_group_free": (None, [_vp]),
+    "fmx_group_size": (_int, [_vp]),
+    "fmx_group_index": (_vp, [_vp, _int]),
+    "fmx_group_len": (_u64, [_vp]),
+    "fmx_group_pieces_count": (_u64, [_vp]),
+    "fmx_group_query_batch": (_int, [_vp, _vp, _u64p]),
     "fmx_locate_count_device": (_int, [_vp, _int, _vp, _vp, _u64, _vp, _u64p, _vp]),
     "fmx_locate_fill_device": (_int, [_vp, _int, _vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp]),
     "fmx_locate_page": (_int, [_vp, _vp, _vp, _u64, _u64, _u64, _vp, _vp, _u64p]),
@@ -70,6 +79,12 @@ class Query(C.Structure):
                 ("fixed_len", C.c_uint64), ("npat", C.c_uint64), ("out_width", C.c_uint32), ("reserved", C.c_uint32),
                 ("out_s", C.c_void_p), ("out_e", C.c_void_p), ("counts", C.c_void_p), ("hit_off", C.c_void_p),
                 ("positions", C.c_void_p), ("piece_ids", C.c_void_p), ("capacity", C.c_uint64)]
+
+
+class CsrPart(C.Structure):
+    """struct fmx_csr_part (include/fmx.h)"""
+    _fields_ = [("hit_off", C.c_void_p), ("positions", C.c_void_p), ("piece_ids", C.c_void_p),
+                ("position_base", C.c_uint64), ("piece_base", C.c_uint64)]
 
 
 _lib = None

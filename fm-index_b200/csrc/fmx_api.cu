@@ -118,7 +118,7 @@ struct fmx_index {
     int opt_locate_refill = 0;        // 1: per-lane refill k_locate (lost the A/B: it breaks the coalescing of adjacent rows)
     int opt_bucket = 0;               // 1: visit the batch in k-mer bucket order (lost the A/B, kept for experiments); -1 auto
     int opt_count_work = 0;           // 1: kernels count executed search iterations / LF steps (fmx_last_work)
-    int opt_phased = 1;               // 0: one-kernel k_search even when the dense verify structures exist (A/B)
+    int opt_phased = 2;               // dense verify structures: 2 = k_query_fused (one kernel), 1 = the three phased kernels, 0 = k_search
     int opt_locate_dense = 1;         // 0: LF walks to the samples even when the full suffix array is resident (A/B)
     uint32_t tab_embed = 0;           // one-row k-mer table entries carry the row's text position (SearchArgs::tab_embed)
     mutable DevBuf buf[B_COUNT];
@@ -233,37 +233,10 @@ int fmx_blob_build(const void *text, uint64_t n, uint32_t char_width, uint64_t m
 }
 
 // uploads a blob the caller owns (nothing of it is kept on the host: save() reads the device copy back)
-static int upload(const uint8_t *blob, uint64_t blob_bytes, int device, fmx_index **out) {
-    FmxBlobHeader hdr;
-    std::string err;
-    int rc = check_blob(blob, blob_bytes, hdr, err);
-    if (rc) return fail(rc, err);
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-        cudaGetLastError();
-        return fail(FMX_ERR_CUDA, "no CUDA device available (the engine has no CPU fallback)");
-    }
-    if (device < 0 || device >= ndev) return fail(FMX_ERR_INVALID_ARG, "device ordinal out of range");
-    CUDA_TRY(cudaSetDevice(device));
-    fmx_index *idx = new fmx_index();
-    idx->hdr = hdr;
-    idx->device = device;
-    cudaError_t e = cudaMalloc(&idx->d_blob, blob_bytes);
-    if (e != cudaSuccess) {
-        delete idx;
-        cudaGetLastError();
-        return fail(FMX_ERR_OOM, std::string("cudaMalloc index: ") + cudaGetErrorString(e));
-    }
-    e = cudaMemcpy(idx->d_blob, blob, blob_bytes, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMalloc(&idx->d_err, 256);
-    if (e == cudaSuccess) e = cudaMemset(idx->d_err, 0, 256);
-    if (e != cudaSuccess) {
-        cudaFree(idx->d_blob);
-        delete idx;
-        return fail(FMX_ERR_CUDA, std::string("index upload: ") + cudaGetErrorString(e));
-    }
-    idx->d_work = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(idx->d_err) + 64);
+// the kernels' view of the device-resident blob (FmxDev) from its header
+static void bind_sections(fmx_index *idx) {
+    const FmxBlobHeader &hdr = idx->hdr;
+    const int device = idx->device;
     const char *base = static_cast<const char *>(idx->d_blob);
     auto sec = [&](int k) -> const void * { return hdr.sec[k].bytes ? base + hdr.sec[k].offset : nullptr; };
     FmxDev &d = idx->dev;
@@ -315,11 +288,88 @@ static int upload(const uint8_t *blob, uint64_t blob_bytes, int device, fmx_inde
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&idx->persist_blocks_per_sm, k_search_steps<K(), LY()>, 256, 0);
     });
     if (idx->persist_blocks_per_sm < 1) idx->persist_blocks_per_sm = 1;
+}
+
+static int upload(const uint8_t *blob, uint64_t blob_bytes, int device, fmx_index **out) {
+    FmxBlobHeader hdr;
+    std::string err;
+    int rc = check_blob(blob, blob_bytes, hdr, err);
+    if (rc) return fail(rc, err);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(FMX_ERR_CUDA, "no CUDA device available (the engine has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(FMX_ERR_INVALID_ARG, "device ordinal out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    fmx_index *idx = new fmx_index();
+    idx->hdr = hdr;
+    idx->device = device;
+    cudaError_t e = cudaMalloc(&idx->d_blob, blob_bytes);
+    if (e != cudaSuccess) {
+        delete idx;
+        cudaGetLastError();
+        return fail(FMX_ERR_OOM, std::string("cudaMalloc index: ") + cudaGetErrorString(e));
+    }
+    e = cudaMemcpy(idx->d_blob, blob, blob_bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&idx->d_err, 256);
+    if (e == cudaSuccess) e = cudaMemset(idx->d_err, 0, 256);
+    if (e != cudaSuccess) {
+        cudaFree(idx->d_blob);
+        delete idx;
+        return fail(FMX_ERR_CUDA, std::string("index upload: ") + cudaGetErrorString(e));
+    }
+    idx->d_work = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(idx->d_err) + 64);
+    bind_sections(idx);
     rc = build_kmer_table(idx);
     if (rc) {
         fmx_index_free(idx);
         return rc;
     }
+    *out = idx;
+    return FMX_OK;
+}
+
+// A copy of an index on another device: the blob and the k-mer tables travel device to device (NVLink peer copies
+// when the GPUs are peers), nothing is rebuilt.
+int fmx_index_clone(const fmx_index *src, int device, fmx_index **out) {
+    if (!src || !out) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return fail(FMX_ERR_INVALID_ARG, "device ordinal out of range");
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    fmx_index *idx = new fmx_index();
+    idx->hdr = src->hdr;
+    idx->device = device;
+    auto dup = [&](const void *p, size_t bytes, void **q) -> cudaError_t {
+        *q = nullptr;
+        if (!p || !bytes) return cudaSuccess;
+        cudaError_t e = cudaMalloc(q, bytes);
+        if (e != cudaSuccess) return e;
+        return cudaMemcpyPeer(*q, device, p, src->device, bytes);
+    };
+    cudaError_t e = dup(src->d_blob, src->hdr.total_bytes, &idx->d_blob);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&idx->d_err, 256);
+    if (e == cudaSuccess) e = cudaMemset(idx->d_err, 0, 256);
+    if (e == cudaSuccess) e = dup(src->d_kmer_tab, src->kmer_entries * sizeof(uint2), reinterpret_cast<void **>(&idx->d_kmer_tab));
+    if (e == cudaSuccess) e = dup(src->d_kmer_steps, src->kmer_entries, reinterpret_cast<void **>(&idx->d_kmer_steps));
+    if (e == cudaSuccess) e = dup(src->d_big_tab, src->big_entries * sizeof(uint2), reinterpret_cast<void **>(&idx->d_big_tab));
+    if (e == cudaSuccess) e = dup(src->d_big_steps, src->big_entries, reinterpret_cast<void **>(&idx->d_big_steps));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        fmx_index_free(idx);
+        return fail(e == cudaErrorMemoryAllocation ? FMX_ERR_OOM : FMX_ERR_CUDA, std::string("index clone: ") + cudaGetErrorString(e));
+    }
+    idx->d_work = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(idx->d_err) + 64);
+    idx->kmer_k = src->kmer_k;
+    idx->kmer_entries = src->kmer_entries;
+    idx->big_k = src->big_k;
+    idx->big_entries = src->big_entries;
+    bind_sections(idx);
     *out = idx;
     return FMX_OK;
 }
@@ -436,7 +486,7 @@ int fmx_index_set_option(fmx_index *idx, const char *key, int64_t value) {
     else if (k == "locate_ranges") idx->opt_locate_ranges = value < 0 ? -1 : (value != 0);
     else if (k == "bucket") idx->opt_bucket = value < 0 ? -1 : (value != 0);
     else if (k == "count_work") idx->opt_count_work = value != 0;
-    else if (k == "search_phased") idx->opt_phased = value != 0;
+    else if (k == "search_phased") idx->opt_phased = value < 0 || value > 2 ? 2 : (int)value;
     else if (k == "locate_dense") idx->opt_locate_dense = value != 0;
     else if (k == "phase_timing") idx->opt_phase_timing = value != 0;
     else if (k == "pipeline_chunk") idx->opt_pipeline_chunk = value > 0 ? (uint64_t)value : 0;
@@ -799,10 +849,28 @@ static int search_phased(const fmx_index *idx, DevBuf *buf, const SearchArgs &a,
     if ((rc = buf[B_RS].ensure(npat * 4 + 16))) return rc;
     if ((rc = buf[B_RE].ensure(npat * 4 + 16))) return rc;
     if ((rc = buf[B_HINT].ensure(npat * 4 + 16))) return rc;
-    if ((rc = buf[B_QS].ensure(npat * 16 + 16))) return rc;
-    if ((rc = buf[B_QV].ensure(npat * 16 + 16))) return rc;
     if ((rc = buf[B_QN].ensure(64))) return rc;
     if (npat == 0) return 0;
+    if (idx->opt_phased == 2) {  // everything in one kernel: no queues
+        PhasedArgs g;
+        std::memset(&g, 0, sizeof(g));
+        g.a = a;
+        g.rs = buf[B_RS].as<uint32_t>();
+        g.re = buf[B_RE].as<uint32_t>();
+        g.hint = buf[B_HINT].as<uint32_t>();
+        g.want_rows = want_rows ? 1u : 0u;
+        uint64_t blocks = (npat + 255) / 256;
+        const uint64_t cap = (uint64_t)idx->sms * 8 * 8;
+        if (blocks > cap) blocks = cap;
+        dispatch(idx, [&](auto K, auto LY) {
+            if constexpr (K() != FMX_KIND_RLFM_) k_query_fused<K(), LY()><<<(unsigned)blocks, 256, 0, st>>>(idx->dev, g);
+        });
+        LAUNCH_CHECK();
+        phase_mark(idx, 1, st);
+        return 0;
+    }
+    if ((rc = buf[B_QS].ensure(npat * 16 + 16))) return rc;
+    if ((rc = buf[B_QV].ensure(npat * 16 + 16))) return rc;
     PhasedArgs g;
     g.a = a;
     g.rs = buf[B_RS].as<uint32_t>();
@@ -1666,7 +1734,8 @@ extern "C" int fmx_query_batch(const fmx_index *idx, const fmx_query *q, uint64_
         QueryOut o;
         if ((r = lane_out(L, n, cap, o))) return r;
         L.pos_cap = cap;
-        if ((r = query_device(idx, L.buf, q->mode, ps, n, o, L.st, false))) return r;
+        // work counters (option "count_work") are one set per index: only a batch that is a single chunk counts
+        if ((r = query_device(idx, L.buf, q->mode, ps, n, o, L.st, nchunks == 1))) return r;
         if (q->out_s) {
             CUDA_TRY(cudaMemcpyAsync(q->out_s + lo, o.out_s, n * 8, cudaMemcpyDeviceToHost, L.st));
             CUDA_TRY(cudaMemcpyAsync(q->out_e + lo, o.out_e, n * 8, cudaMemcpyDeviceToHost, L.st));
@@ -1763,6 +1832,104 @@ extern "C" int fmx_search_locate_batch(const fmx_index *idx, int mode, const uin
     q.piece_ids = piece_ids;
     q.capacity = capacity;
     return fmx_query_batch(idx, &q, total_hits);
+}
+
+// ------------------------------------------------------------------ CSR merge (piece-partitioned MultiPieces)
+// Each part (one per partition of the pieces) answered EVERY pattern on its own index: part r holds a CSR
+// (hit_off_r, positions_r, piece_ids_r) in its local coordinates.  A pattern without \0 cannot span two pieces, so
+// the match set of the whole text is the disjoint union of the parts' sets (multi_pieces.rs:188-223) and counts
+// add.  One scan over the interleaved counts C[p * R + r] gives every (pattern, part) its slot in the merged CSR;
+// one kernel moves the hits there, shifting positions and piece ids into the coordinates of the whole text.
+// Hits of one pattern come part-major, inside a part in that part's SA-row order.
+
+#define FMX_MAX_PARTS 16
+struct MergeParts {
+    const void *off[FMX_MAX_PARTS];
+    const void *pos[FMX_MAX_PARTS];
+    const void *pid[FMX_MAX_PARTS];
+    uint64_t pos_base[FMX_MAX_PARTS];
+    uint64_t pid_base[FMX_MAX_PARTS];
+    int n;
+};
+
+template <class T>
+__global__ void k_merge_counts(const __grid_constant__ MergeParts parts, uint64_t npat, uint32_t *cnt) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= npat * parts.n) return;
+    const uint64_t p = t / parts.n;
+    const int r = (int)(t % parts.n);
+    const T *off = static_cast<const T *>(parts.off[r]);
+    cnt[t] = (uint32_t)(off[p + 1] - off[p]);
+}
+
+template <class T>
+__global__ void k_merge_scatter(const __grid_constant__ MergeParts parts, uint64_t npat, const uint32_t *cnt, const uint64_t *slot,
+                                uint64_t *hit_off, uint64_t *positions, uint64_t *piece_ids, uint64_t capacity) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t total = npat * parts.n;
+    if (t > total) return;
+    if (t == total) {
+        hit_off[npat] = slot[total];
+        return;
+    }
+    const uint64_t p = t / parts.n;
+    const int r = (int)(t % parts.n);
+    const uint64_t dst = slot[t];
+    if (r == 0) hit_off[p] = dst;
+    const uint32_t c = cnt[t];
+    if (!c) return;
+    const uint64_t src = static_cast<const T *>(parts.off[r])[p];
+    const T *pos = static_cast<const T *>(parts.pos[r]);
+    const T *pid = static_cast<const T *>(parts.pid[r]);
+    for (uint32_t j = 0; j < c; j++) {
+        if (dst + j >= capacity) break;
+        if (positions && pos) positions[dst + j] = (uint64_t)pos[src + j] + parts.pos_base[r];
+        if (piece_ids && pid) piece_ids[dst + j] = (uint64_t)pid[src + j] + parts.pid_base[r];
+    }
+}
+
+static std::mutex g_merge_mu;
+static DevBuf g_merge_buf[64][3];  // per device: counts, slots, scan tiles
+
+extern "C" int fmx_csr_merge_device(int device, const fmx_csr_part *parts, int nparts, uint64_t npat, uint32_t width,
+                                    uint64_t *d_hit_off, uint64_t *d_positions, uint64_t *d_piece_ids, uint64_t capacity,
+                                    void *stream) {
+    if (!parts || !d_hit_off) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    if (nparts < 1 || nparts > FMX_MAX_PARTS) return fail(FMX_ERR_INVALID_ARG, "1 .. 16 parts");
+    if (width != 8 && width != 4) return fail(FMX_ERR_INVALID_ARG, "width must be 8 or 4");
+    if (device < 0 || device >= 64) return fail(FMX_ERR_INVALID_ARG, "device ordinal out of range");
+    if (npat * (uint64_t)nparts >= 0xFFFFFFFFull * 4) return fail(FMX_ERR_UNSUPPORTED, "too many (pattern, part) pairs");
+    MergeParts mp;
+    std::memset(&mp, 0, sizeof(mp));
+    mp.n = nparts;
+    for (int r = 0; r < nparts; r++) {
+        if (!parts[r].hit_off) return fail(FMX_ERR_INVALID_ARG, "part without hit offsets");
+        mp.off[r] = parts[r].hit_off;
+        mp.pos[r] = parts[r].positions;
+        mp.pid[r] = parts[r].piece_ids;
+        mp.pos_base[r] = parts[r].position_base;
+        mp.pid_base[r] = parts[r].piece_base;
+    }
+    std::lock_guard<std::mutex> lk(g_merge_mu);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const uint64_t total = npat * (uint64_t)nparts;
+    DevBuf *b = g_merge_buf[device];
+    int rc;
+    if ((rc = b[0].ensure(total * 4 + 16))) return rc;
+    if ((rc = b[1].ensure((total + 1) * 8))) return rc;
+    uint32_t *d_cnt = b[0].as<uint32_t>();
+    uint64_t *d_slot = b[1].as<uint64_t>();
+    if (total) {
+        if (width == 8) k_merge_counts<uint64_t><<<grid_for(total, 256), 256, 0, st>>>(mp, npat, d_cnt);
+        else k_merge_counts<uint32_t><<<grid_for(total, 256), 256, 0, st>>>(mp, npat, d_cnt);
+        LAUNCH_CHECK();
+    }
+    if ((rc = device_scan<uint32_t, uint64_t, OpSum, true>(d_cnt, total, d_slot, OpSum(), true, b[2], st))) return rc;
+    if (width == 8) k_merge_scatter<uint64_t><<<grid_for(total + 1, 256), 256, 0, st>>>(mp, npat, d_cnt, d_slot, d_hit_off, d_positions, d_piece_ids, capacity);
+    else k_merge_scatter<uint32_t><<<grid_for(total + 1, 256), 256, 0, st>>>(mp, npat, d_cnt, d_slot, d_hit_off, d_positions, d_piece_ids, capacity);
+    LAUNCH_CHECK();
+    return FMX_OK;
 }
 
 // ------------------------------------------------------------------ extraction / primitives

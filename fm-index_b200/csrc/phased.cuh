@@ -236,6 +236,116 @@ __global__ void __launch_bounds__(256) k_ph_verify(const __grid_constant__ FmxDe
     }
 }
 
+// ---- the same pipeline as ONE kernel (option "search_phased" = 2, the default).
+// Measured on the 1 GB DNA target (profiles/r02_*): the three-kernel form keeps every warp converged but pays for it --
+// every pattern that reaches the verify phase is read from HBM a second time (one more DRAM request, of the three it
+// makes in total), and the two queue appends of every warp are atomics on two hot addresses.  What bounds this
+// workload is the number of DRAM requests, which idle lanes do not issue, so here one thread takes one pattern
+// through table lookup, the few ordinary iterations and the text comparison without leaving the registers its
+// characters already sit in.  Same results, same hints, same step counts.
+template <int KIND, int LAYOUT, class Reader>
+__device__ __forceinline__ void query_one(const FmxDev &ix, const Tabs<LAYOUT> &tb, const PhasedArgs &g, Reader &rd, uint32_t len,
+                                          uint32_t &s, uint32_t &e, uint32_t &hint, unsigned long long &steps,
+                                          unsigned long long &reqs) {
+    const SearchArgs &a = g.a;
+    uint32_t it = 0, pos = FMX_NOHINT, k = len;
+    if (kmer_lookup(a, ix.max_character, rd, k, s, e, it, &pos)) reqs += (s == e && a.work) ? 2u : 1u;
+    bool armed = a.verify != 0;
+    hint = FMX_NOHINT;
+    while (k > 0) {  // the reference loop (wrapper.rs:103-124): the range is tested after a step, never before
+        if (armed && e - s == 1u && k >= FMX_VERIFY_MIN_DENSE) {
+            if (pos == FMX_NOHINT) {
+                pos = ldg32_s(ix.vsa + s);
+                reqs++;
+            }
+            uint32_t matched = 0, c = 0;
+            if (pos >= k) {
+                TextReader tr(ix.text + (pos - k), k);
+                while (matched < k) {
+                    const uint32_t tc = tr.get(k - 1u - matched);
+                    c = rd.get(k - 1u - matched);
+                    if (tc == 0u || c != tc) break;
+                    matched++;
+                }
+                const uint32_t last = pos - 1u, first = pos - (matched < k ? matched + 1u : k);
+                reqs += (last >> 5) - (first >> 5) + 1u;
+            }
+            it += matched;
+            if (pos >= k && matched == k) {  // the whole rest of the pattern stands in the text in front of the row
+                hint = pos - k;
+                if (g.want_rows) {
+                    s = ldg32_s(ix.isa + hint);
+                    reqs++;
+                } else {
+                    s = 0;
+                }
+                e = s + 1u;
+                k = 0;
+                break;
+            }
+            if (pos >= k && !g.want_rows && c != 0u && c <= ix.max_character) {  // true mismatch: the next iteration empties the range
+                it++;
+                s = e = 0;
+                break;
+            }
+            if (matched) {
+                s = ldg32_s(ix.isa + (pos - matched));
+                reqs++;
+                e = s + 1u;
+                k -= matched;
+            }
+            armed = false;  // as search_one: the tail is not tried again once an attempt stopped early
+            continue;
+        }
+        const uint32_t c = rd.get(k - 1u);
+        if (c > ix.max_character) {  // the reference panics here (cs[c] out of bounds, fm_index.rs:94)
+            atomicOr(a.err, 1u);
+            break;
+        }
+        if (a.work) reqs += pair_requests<LAYOUT>(ix, s, e);
+        lf_map2_pair<KIND, LAYOUT>(ix, tb, c, s, e);
+        pos = FMX_NOHINT;
+        it++;
+        k--;
+        if (s == e) break;
+    }
+    if (hint == FMX_NOHINT && e - s == 1u && k == 0) hint = pos;  // a one-row table entry that consumed the whole pattern
+    steps += it;
+}
+
+template <int KIND, int LAYOUT>
+__global__ void __launch_bounds__(256) k_query_fused(const __grid_constant__ FmxDev ix, const __grid_constant__ PhasedArgs g) {
+    __shared__ Tabs<LAYOUT> tb;
+    __shared__ uint32_t spat[8][256];
+    load_tables<LAYOUT>(ix, tb);
+    const SearchArgs &a = g.a;
+    unsigned long long steps = 0, reqs = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < a.npat; p += stride) {
+        uint64_t beg;
+        uint32_t len;
+        pattern_span(a, p, beg, len);
+        uint32_t s = a.s0, e = a.e0, hint;
+        if (a.packed_bits) {
+            AnyReader rd(a, p, beg, len);
+            query_one<KIND, LAYOUT>(ix, tb, g, rd, len, s, e, hint, steps, reqs);
+        } else if (a.staged) {
+            StagedReader rd(spat, a.pat + beg, len);
+            query_one<KIND, LAYOUT>(ix, tb, g, rd, len, s, e, hint, steps, reqs);
+        } else {
+            PatReader rd(a.pat + beg, len);
+            query_one<KIND, LAYOUT>(ix, tb, g, rd, len, s, e, hint, steps, reqs);
+        }
+        g.rs[p] = s;
+        g.re[p] = e;
+        g.hint[p] = hint;
+    }
+    if (a.work) {
+        warp_add(steps, a.work);
+        warp_add(reqs, a.work + 2);
+    }
+}
+
 // (rs, re) as the u64 arrays of the C ABI
 __global__ void k_ph_widen(const uint32_t *rs, const uint32_t *re, uint64_t npat, uint64_t *out_s, uint64_t *out_e) {
     const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -102,6 +102,9 @@ int fmx_blob_build_ex(const void *text, uint64_t n, uint32_t char_width, uint64_
 /* Upload a blob (serialised once; the reference only has un-exposed serde derives,
  * fm_index.rs:13, rlfmi.rs:15, multi_pieces.rs:16, sample.rs:12). */
 int fmx_index_from_blob(const void *blob, uint64_t blob_bytes, int device, fmx_index **out);
+/* A copy of a device-resident index on another device of this process (blob and k-mer tables copied device to
+ * device; nothing is rebuilt).  What FMX_GROUP_REPLICATE uses. */
+int fmx_index_clone(const fmx_index *src, int device, fmx_index **out);
 int fmx_index_save(const fmx_index *idx, const char *path);
 int fmx_index_load(const char *path, int device, fmx_index **out);
 void fmx_index_free(fmx_index *idx);
@@ -268,6 +271,50 @@ int fmx_query_batch_device(const fmx_index *idx, const fmx_query *q, void *strea
 /* Host buffers (pinned ones make the copies asynchronous): chunked H2D / kernels / D2H pipeline.  *total_hits
  * (nullable) receives hit_off[npat].  More hits than `capacity`: FMX_ERR_CAPACITY with counts / hit_off filled. */
 int fmx_query_batch(const fmx_index *idx, const fmx_query *q, uint64_t *total_hits);
+
+/* ---------------------------------------------------------------- multi-GPU
+ * Queries are independent, so FMIndex / RLFMIndex shard by query with the index REPLICATED per GPU and no exchange
+ * (SURVEY.md 8e).  FMIndexMultiPieces may instead be PARTITIONED BY PIECE: every GPU indexes a contiguous group of
+ * pieces, every pattern is answered by every GPU, and the per-pattern hit counts and hit lists are combined
+ * (multi_pieces.rs:188-223: a pattern without \0 cannot span two pieces, so counts add and the match sets are
+ * disjoint).  Match sets, counts, positions and piece ids equal the single index's; the reference's iteration ORDER
+ * is reproduced only by the replicated form (hits of a pattern come partition-major here).
+ *
+ * fmx_csr_merge_device: the combine step on ONE device, for callers that move the parts themselves (one process
+ * per GPU with NCCL: fm-index_b200/partitioned.py).  Part r is a CSR in its own coordinates -- hit_off (npat + 1),
+ * positions, piece_ids (nullable), all `width` bytes per entry, resident on `device` -- plus the text offset and the
+ * first piece of its partition.  Output is a uint64 CSR of at most `capacity` hits; hit_off[npat] is the total. */
+typedef struct fmx_csr_part {
+    const void *hit_off;
+    const void *positions;
+    const void *piece_ids;
+    uint64_t position_base;
+    uint64_t piece_base;
+} fmx_csr_part;
+int fmx_csr_merge_device(int device, const fmx_csr_part *parts, int nparts, uint64_t npat, uint32_t width,
+                         uint64_t *d_hit_off, uint64_t *d_positions, uint64_t *d_piece_ids, uint64_t capacity,
+                         void *stream);
+
+/* A group of GPUs of one process behind one handle.
+ *   FMX_GROUP_REPLICATE  the index is built once and uploaded to every device; a batch is cut into contiguous
+ *                        shards, one per device (fmx_query_batch on each, in parallel); results come back in input
+ *                        order, bit-identical to the single index -- iteration order included.
+ *   FMX_GROUP_BY_PIECE   (FMX_KIND_MULTI) the pieces are split into contiguous, length-balanced groups, one index
+ *                        per device; every device answers the whole batch; the parts are gathered on the first
+ *                        device over NVLink peer copies and merged there by fmx_csr_merge_device.  Patterns
+ *                        containing \0 are rejected (they could span the partition).
+ * fmx_group_query_batch takes the same descriptor as fmx_query_batch (host buffers; out_width 8; out_s / out_e
+ * are not available BY_PIECE: SA rows of different partitions are unrelated). */
+typedef struct fmx_group fmx_group;
+typedef enum fmx_group_mode { FMX_GROUP_REPLICATE = 0, FMX_GROUP_BY_PIECE = 1 } fmx_group_mode;
+int fmx_group_create(const int *device_ids, int ndev, int group_mode, const void *text, uint64_t n, uint32_t char_width,
+                     uint64_t max_character, int kind, int level, int index_mode, fmx_group **out);
+void fmx_group_free(fmx_group *g);
+int fmx_group_size(const fmx_group *g);
+const fmx_index *fmx_group_index(const fmx_group *g, int k);
+uint64_t fmx_group_len(const fmx_group *g);           /* SearchIndex::len of the whole text */
+uint64_t fmx_group_pieces_count(const fmx_group *g);  /* pieces of the whole text */
+int fmx_group_query_batch(const fmx_group *g, const fmx_query *q, uint64_t *total_hits);
 
 /* ---------------------------------------------------------------- extraction
  * Batched Match::iter_chars_backward / iter_chars_forward taken k characters deep

@@ -488,7 +488,7 @@ def test_seed_and_verify_tail(mc, level, dense, kind, monkeypatch):
     flat, off = orc.pack_patterns(pats)
     for mode in ((fmx.SEARCH, fmx.SEARCH_PREFIX, fmx.SEARCH_SUFFIX, fmx.SEARCH_EXACT) if kind == orc.MULTI else (fmx.SEARCH,)):
         s, e, steps = oracle.search_batch(flat, off, mode, want_steps=True)
-        for verify, phased in ((1, 1), (1, 0), (0, 1)):   # phased kernels / verify tail inside k_search / plain loop
+        for verify, phased in ((1, 2), (1, 1), (1, 0), (0, 2)):   # fused kernel / phased kernels / verify tail inside k_search / plain loop
             index.set_option("verify", verify)
             index.set_option("search_phased", phased)
             b = index.search_batch(pats, mode)
@@ -765,8 +765,9 @@ def test_rich_mode_query_parity(kind, mc, env, monkeypatch):
         assert index.last_work()[0] == int(steps.sum())
         got = b.locate(piece_ids=kind == orc.MULTI)             # two-call path: dense k_locate_simple
         assert np.array_equal(got[0], ooff) and np.array_equal(got[1], opos)
-        for rows in (True, False):
-            for width in (8, 4):
+        for rows, width, phased in ((True, 8, 2), (False, 8, 2), (True, 4, 2), (False, 4, 2), (True, 8, 1), (False, 4, 1)):
+            if True:
+                index.set_option("search_phased", phased)       # 2: one fused kernel (default); 1: seed / steps / verify kernels
                 r = index.query_batch(pats, mode, rows=rows, counts=True, piece_ids=kind == orc.MULTI, width=width)
                 if rows:
                     assert np.array_equal(r["s"], s) and np.array_equal(r["e"], e)
@@ -775,10 +776,12 @@ def test_rich_mode_query_parity(kind, mc, env, monkeypatch):
                 assert np.array_equal(r["positions"].astype(np.uint64), opos), (mode, rows, width)
                 if kind == orc.MULTI:
                     assert np.array_equal(r["piece_ids"].astype(np.uint64), opid)
-        r = index.query_batch(pats, mode, locate=False, counts=True)       # count only: no ISA request, no locate
-        assert np.array_equal(r["counts"], cnt)
-        if not po:
-            assert index.last_work()[0] == int(steps.sum())               # the shortcut counts the reference's last iteration too
+        for phased in (1, 2):
+            index.set_option("search_phased", phased)
+            r = index.query_batch(pats, mode, locate=False, counts=True)       # count only: no ISA request, no locate
+            assert np.array_equal(r["counts"], cnt)
+            if not po:
+                assert index.last_work()[0] == int(steps.sum()), phased        # the shortcut counts the reference's last iteration too
     # the rich paths off: same answers from the plain kernels
     ref = index.query_batch(pats, rows=True, counts=True)
     for key in ("search_phased", "locate_dense", "verify"):
@@ -786,8 +789,8 @@ def test_rich_mode_query_parity(kind, mc, env, monkeypatch):
         r = index.query_batch(pats, rows=True, counts=True)
         for k in ("s", "e", "counts", "hit_off", "positions"):
             assert np.array_equal(r[k], ref[k]), (key, k)
-    for key in ("search_phased", "locate_dense", "verify"):
-        index.set_option(key, 1)
+    for key, v in (("search_phased", 2), ("locate_dense", 1), ("verify", 1)):
+        index.set_option(key, v)
     if mc < 255:                                          # invalid characters: first processed, and deep inside a unique match
         bad = bytearray(text[1000:1040].tobytes())
         bad[5] = mc + 1
@@ -919,3 +922,220 @@ def test_two_phase_device_locate_rejects_a_mismatched_fill():
     torch.cuda.synchronize()
     rh, rp = index.search_batch(pats).locate()
     assert np.array_equal(d_pos[: total.value].cpu().numpy().view(np.uint64), rp)
+
+
+# ---------------------------------------------------------------- at-scale code paths
+# The paths that only switch on at scale -- the k = 16 table sized by sigma^k >= 4n, the default-on dense verify
+# structures (rank structure >= 192 MB), SYM at tens of GB, beyond-L2 behaviour -- compared with the oracle by the
+# driver's own pytest run.  The oracle's single-threaded SA-IS would take minutes here, so it is handed the
+# GPU-built suffix array, which it first VERIFIES with its own linear-time checker (tests/test_oracle_golden.py::
+# test_suffix_array_checker_and_build_from_sa pins that checker).
+
+def _oracle_from_gpu_sa(text, kind, level, mc):
+    sa, _ = fmx.suffix_array_device(text, mc)
+    return orc.OracleIndex(text, kind, level=level, max_character=mc, sa=sa)
+
+
+def _scale_check(index, oracle, text, pats, starts, m, sample=100_000, packed=False):
+    npat = pats.shape[0]
+    r = index.query_batch(pats, rows=True, counts=True, capacity=4 * npat)
+    flat, off = pats[:sample].reshape(-1), np.arange(sample + 1, dtype=np.uint64) * m
+    s, e, steps = oracle.search_batch(flat, off, want_steps=True)
+    ooff, opos, _ = oracle.locate_batch(s, e)
+    assert np.array_equal(r["s"][:sample], s) and np.array_equal(r["e"][:sample], e)
+    assert np.array_equal(r["hit_off"][: sample + 1], ooff) and np.array_equal(r["positions"][: int(ooff[-1])], opos)
+    # size-independent properties on the whole batch
+    class B:
+        pass
+    b = B()
+    b.s, b.e = r["s"], r["e"]
+    check_locate_properties(text, pats, starts, b, r["hit_off"], r["positions"])
+    # the fast form (no rows: hints, no inverse-suffix-array request) and 32-bit outputs give the same lists
+    r2 = index.query_batch(pats, width=4, capacity=4 * npat)
+    assert np.array_equal(r2["hit_off"].astype(np.uint64), r["hit_off"]) and np.array_equal(r2["positions"].astype(np.uint64), r["positions"])
+    if packed:
+        r3 = index.query_batch(fmx.pack_patterns(pats, 2), packed_bits=2, fixed_len=m, width=4, capacity=4 * npat)
+        assert np.array_equal(r3["positions"], r2["positions"])
+    # executed iterations on the sample: the table's early-break step counts included
+    index.set_option("count_work", 1)
+    index.set_option("pipeline_chunk", sample)                 # one chunk: the host call counts work
+    for rows in (True, False):
+        index.query_batch(pats[:sample], rows=rows, locate=False, counts=True)
+        assert index.last_work()[0] == int(steps.sum()), rows
+    index.set_option("pipeline_chunk", 0)
+    index.set_option("count_work", 0)
+    return r
+
+
+@pytest.mark.skipif(os.environ.get("FMX_SKIP_FULL") == "1", reason="full-size run disabled")
+def test_scale_dna_420m_rich_and_compact():
+    n, npat, m = 420_000_000, 1_000_000, 32           # rank structure 200 MiB: past the 192 MiB threshold of FMX_MODE_AUTO
+    text = dna(n, 1003)
+    pats, starts = mixed_patterns(text, npat, m, 1004)
+    index = fmx.FMIndexWithLocate.new(fmx.Text.with_max_character(text, 4), 2)
+    assert index.mode() == fmx.MODE_RICH and index.kmer_k(True) == 16        # default-on at this size
+    oracle = _oracle_from_gpu_sa(text, orc.FM, 2, 4)
+    r = _scale_check(index, oracle, text, pats, starts, m, packed=True)
+    for key in ("search_phased", "locate_dense"):                             # the round-1 kernels on the same index
+        index.set_option(key, 0)
+    r0 = index.query_batch(pats, rows=True, capacity=4 * npat)
+    for k in ("s", "e", "hit_off", "positions"):
+        assert np.array_equal(r0[k], r[k]), k
+    del index
+    compact = fmx.FMIndexWithLocate.new(fmx.Text.with_max_character(text, 4), 2, mode=fmx.MODE_COMPACT)
+    assert compact.mode() == fmx.MODE_COMPACT and compact.heap_size() < 2 * n
+    rc = compact.query_batch(pats, rows=True, capacity=4 * npat)
+    for k in ("s", "e", "hit_off", "positions"):
+        assert np.array_equal(rc[k], r[k]), k
+
+
+@pytest.mark.skipif(os.environ.get("FMX_SKIP_FULL") == "1", reason="full-size run disabled")
+def test_scale_bytes_64m_sym():
+    n, npat, m = 64_000_000, 400_000, 24
+    rng = np.random.default_rng(1005)
+    text = np.append(rng.integers(1, 256, n, dtype=np.uint8), np.uint8(0))
+    pats, starts = mixed_patterns(text, npat, m, 1006, sigma=255)
+    index = fmx.FMIndexWithLocate.new(fmx.Text.new(text), 2)
+    assert index.sectors_per_rank() == 1 and index.mode() == fmx.MODE_RICH    # SYM (2.7 GB) + dense verify structures
+    oracle = _oracle_from_gpu_sa(text, orc.FM, 2, 255)
+    _scale_check(index, oracle, text, pats, starts, m)
+
+
+@pytest.mark.skipif(os.environ.get("FMX_SKIP_FULL") == "1", reason="full-size run disabled")
+def test_scale_rlfm_256m_16_copies():
+    rng = np.random.default_rng(1007)
+    base = rng.integers(1, 5, 16 << 20, dtype=np.uint8)
+    parts = []
+    for _ in range(16):
+        x = base.copy()
+        mut = rng.random(x.size) < 0.001
+        x[mut] = rng.integers(1, 5, int(mut.sum()), dtype=np.uint8)
+        parts.append(x)
+    text = np.append(np.concatenate(parts), np.uint8(0))
+    npat, m = 200_000, 32
+    starts = rng.integers(0, text.size - 1 - m, npat)
+    pats = text[starts[:, None] + np.arange(m)[None, :]]
+    oracle = _oracle_from_gpu_sa(text, orc.RLFM, 2, 4)
+    flat, off = pats[:50_000].reshape(-1), np.arange(50_001, dtype=np.uint64) * m
+    s, e = oracle.search_batch(flat, off)
+    ooff, opos, _ = oracle.locate_batch(s, e)
+    for mode in (fmx.MODE_AUTO, fmx.MODE_RICH):
+        index = fmx.RLFMIndexWithLocate.new(fmx.Text.with_max_character(text, 4), 2, mode=mode)
+        r = index.query_batch(pats, rows=True, capacity=40 * npat)
+        assert np.array_equal(r["s"][:50_000], s) and np.array_equal(r["e"][:50_000], e)
+        assert np.array_equal(r["hit_off"][:50_001], ooff) and np.array_equal(r["positions"][: int(ooff[-1])], opos)
+        cnt = (r["e"] - r["s"]).astype(np.int64)
+        assert cnt.min() >= 1 and np.array_equal(np.diff(r["hit_off"].astype(np.int64)), cnt)
+        owner = np.repeat(np.arange(npat), cnt)
+        sel = rng.integers(0, owner.size, 300_000)
+        got = text[r["positions"][sel].astype(np.int64)[:, None] + np.arange(m)[None, :]]
+        assert np.array_equal(got, pats[owner[sel]])
+        del index
+
+
+# ---------------------------------------------------------------- multi-GPU forms (config 4)
+
+def _multi_case(seed, pieces=9, lo=3_000, hi=20_000, npat=20_000, m=14):
+    rng = np.random.default_rng(seed)
+    text = np.concatenate([np.append(rng.integers(1, 5, int(l), dtype=np.uint8), np.uint8(0)) for l in rng.integers(lo, hi, pieces)])
+    starts = rng.integers(0, text.size - m - 1, npat)
+    pats = rng.integers(1, 5, (npat, m), dtype=np.uint8)
+    samp = text[starts[:, None] + np.arange(m)[None, :]]
+    pats[::2] = samp[::2]
+    pats = pats[(pats != 0).all(axis=1)]
+    pats[5, :6] = pats[5, 6:12]                       # a few short-period patterns: many hits in some pieces
+    return text, np.ascontiguousarray(pats)
+
+
+def _same_match_sets(hoff, pos, pid, rh, rp, rd):
+    """equal CSR offsets and, per pattern, equal multisets of (position, piece id)"""
+    assert np.array_equal(np.asarray(hoff, dtype=np.uint64), np.asarray(rh, dtype=np.uint64))
+    owner = np.repeat(np.arange(len(rh) - 1), np.diff(np.asarray(rh, dtype=np.int64)))
+    a = np.lexsort((np.asarray(pos, dtype=np.int64), owner))
+    b = np.lexsort((np.asarray(rp, dtype=np.int64), owner))
+    assert np.array_equal(np.asarray(pos)[a], np.asarray(rp)[b]) and np.array_equal(np.asarray(pid)[a], np.asarray(rd)[b])
+
+
+@pytest.mark.parametrize("ndev", [1, 3])
+@pytest.mark.parametrize("imode", [fmx.MODE_COMPACT, fmx.MODE_RICH])
+def test_group_by_piece_and_replicated(ndev, imode):
+    """fmx_group on ONE physical GPU used `ndev` times (the code path is the same: per-member streams and buffers,
+    peer copies to the first member, fmx_csr_merge_device): BY_PIECE gives the replicated index's match sets, counts,
+    positions and piece ids; REPLICATE gives its exact lists, order included"""
+    text, pats = _multi_case(77 + ndev)
+    t = fmx.Text.with_max_character(text, 4)
+    single = fmx.FMIndexMultiPiecesWithLocate.new(t, 2, mode=imode)
+    oracle = orc.OracleIndex(text, orc.MULTI, level=2, max_character=4)
+    flat, off = pats.reshape(-1), np.arange(pats.shape[0] + 1, dtype=np.uint64) * pats.shape[1]
+    for mode in (fmx.SEARCH, fmx.SEARCH_PREFIX, fmx.SEARCH_SUFFIX, fmx.SEARCH_EXACT):
+        s, e = oracle.search_batch(flat, off, mode)
+        rh, rp, rd = oracle.locate_batch(s, e, prefix_only=mode in (1, 3), want_piece_ids=True)
+        ref = single.query_batch(pats, mode, piece_ids=True, capacity=int(rh[-1]) + 16)
+        assert np.array_equal(ref["hit_off"], rh) and np.array_equal(ref["positions"], rp) and np.array_equal(ref["piece_ids"], rd)
+        bp = fmx.IndexGroup(t, fmx.KIND_MULTI, 2, [0] * ndev, fmx.GROUP_BY_PIECE, mode=imode)
+        assert bp.size() == ndev and bp.len() == text.size and bp.pieces_count() == int((text == 0).sum())
+        r = bp.query_batch(pats, mode, piece_ids=True, counts=mode in (0, 2))
+        _same_match_sets(r["hit_off"], r["positions"], r["piece_ids"], rh, rp, rd)
+        if mode in (0, 2):
+            assert np.array_equal(r["counts"], np.where(e > s, e - s, 0))
+        r = bp.query_batch(pats, mode, capacity=5)                 # too small: retried with the exact size
+        assert r["total"] == int(rh[-1])
+        del bp
+    bad = pats.copy()
+    bad[3, 2] = 0
+    bp = fmx.IndexGroup(t, fmx.KIND_MULTI, 2, [0] * ndev, fmx.GROUP_BY_PIECE, mode=imode)
+    with pytest.raises(fmx.Error):
+        bp.query_batch(bad)
+    del bp
+    rep = fmx.IndexGroup(t, fmx.KIND_MULTI, 2, [0] * ndev, fmx.GROUP_REPLICATE, mode=imode)
+    s, e = oracle.search_batch(flat, off)
+    rh, rp, rd = oracle.locate_batch(s, e, want_piece_ids=True)
+    for width in (8, 4):
+        r = rep.query_batch(pats, rows=True, counts=True, piece_ids=True, width=width)
+        assert np.array_equal(r["s"], s) and np.array_equal(r["e"], e) and np.array_equal(r["counts"].astype(np.uint64), e - s)
+        assert np.array_equal(r["hit_off"].astype(np.uint64), rh) and np.array_equal(r["positions"].astype(np.uint64), rp)
+        assert np.array_equal(r["piece_ids"].astype(np.uint64), rd)
+    lens = np.random.default_rng(3).integers(1, 30, 5_000)         # ragged patterns through the sharded form
+    fl = np.random.default_rng(4).integers(1, 5, int(lens.sum()), dtype=np.uint8)
+    of = np.zeros(lens.size + 1, dtype=np.uint64)
+    of[1:] = np.cumsum(lens)
+    a, b = rep.query_batch((fl, of), rows=True), single.query_batch((fl, of), rows=True)
+    for k in ("s", "e", "hit_off", "positions"):
+        assert np.array_equal(a[k], b[k]), k
+    with pytest.raises(fmx.Error):
+        fmx.IndexGroup(fmx.Text.with_max_character(dna(5000, 1), 4), fmx.KIND_FM, 2, [0], fmx.GROUP_BY_PIECE)
+
+
+def test_partitioned_cuda_engine_and_merge_kernel():
+    """fm-index_b200/partitioned.py on one rank with the CUDA engine (fmx_query_batch_device, 32-bit CSR) and
+    fmx_csr_merge_device against (a) the replicated index and (b) the host merge the gloo tests pin"""
+    import torch
+    from fm_index_b200 import partitioned as part
+    text, pats = _multi_case(91, pieces=12)
+    idx = part.PartitionedMultiPieces(text, 2, 4, device=0)
+    counts, hoff, pos, pid = idx.search_locate(torch.from_numpy(pats))
+    single = fmx.FMIndexMultiPiecesWithLocate.new(fmx.Text.with_max_character(text, 4), 2)
+    ref = single.query_batch(pats, piece_ids=True, counts=True, capacity=int(hoff[-1].item()) + 8)
+    assert np.array_equal(hoff.cpu().numpy().view(np.uint64), ref["hit_off"])
+    assert np.array_equal(pos.cpu().numpy().view(np.uint64), ref["positions"])          # one partition: same order too
+    assert np.array_equal(pid.cpu().numpy().view(np.uint64), ref["piece_ids"])
+    assert np.array_equal(counts.cpu().numpy().view(np.uint64), ref["counts"])
+    # three partitions answered by three engines on this GPU, merged by the kernel and by the host merge
+    starts, ends = part.piece_bounds(text)
+    ranges = part.partition_pieces(ends - starts + 1, 3)
+    parts, bases = [], []
+    for a, b in ranges:
+        base = int(starts[a])
+        eng = part.CudaEngine(text[base:int(ends[b - 1]) + 1], 2, 4, 0)
+        off_r, pos_r, pid_r = eng.search_locate(torch.from_numpy(pats))
+        parts.append((off_r.clone(), pos_r.clone(), pid_r.clone()))
+        bases.append((base, int(a)))
+    dev = torch.device("cuda", 0)
+    k_off, k_pos, k_pid = part.merge_parts_cuda(parts, bases, pats.shape[0], dev)
+    h_off, h_pos, h_pid = part.merge_parts_host([tuple(t.cpu() for t in p) for p in parts], bases, pats.shape[0], None)
+    assert torch.equal(k_off.cpu(), h_off) and torch.equal(k_pos.cpu(), h_pos) and torch.equal(k_pid.cpu(), h_pid)
+    _same_match_sets(k_off.cpu().numpy(), k_pos.cpu().numpy(), k_pid.cpu().numpy(), ref["hit_off"], ref["positions"], ref["piece_ids"])
+    with pytest.raises(ValueError):
+        bad = pats.copy()
+        bad[0, 0] = 0
+        idx.search_locate(torch.from_numpy(bad))

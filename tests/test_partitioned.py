@@ -1,6 +1,8 @@
-"""Piece-partitioned MultiPieces: the N > 1 path, world_size 2 over gloo on CPU.
+"""Piece-partitioned MultiPieces: the N > 1 path, world_size 2 and 3 over gloo on CPU.
 The local engine is the oracle (test infrastructure); what is tested is the partitioning, the offset
-arithmetic and the two collectives of fm-index_b200/partitioned.py."""
+arithmetic, the gather of the offsets, the exact-size point-to-point transfers of the hit lists and the merge
+arithmetic of fm-index_b200/partitioned.py (on GPUs the merge is the CUDA kernel fmx_csr_merge_device, which
+tests/test_gpu_parity.py compares with the same host merge)."""
 import os
 import socket
 
@@ -51,7 +53,11 @@ def _worker(rank, world, port, q):
         full = orc.OracleIndex(text, orc.MULTI, level=2, max_character=4)
         ok = idx.pieces_count() == full.pieces_count() and idx.len() == full.len()
         for mode in (0, 1, 2, 3):
-            counts, hoff, pos, pid = idx.search_locate(pats, mode)
+            res = idx.search_locate(pats, mode)
+            if rank != 0:                       # gathered on rank 0 only: nobody else receives anything
+                ok &= res is None
+                continue
+            counts, hoff, pos, pid = res
             flat, off = pats.reshape(-1), np.arange(pats.shape[0] + 1, dtype=np.uint64) * np.uint64(pats.shape[1])
             s, e = full.search_batch(flat, off, mode)
             rh, rp, rd = full.locate_batch(s, e, prefix_only=mode in (1, 3), want_piece_ids=True)
@@ -79,20 +85,21 @@ def test_partition_pieces_balanced_and_contiguous():
         part.partition_pieces([5, 5], 3)
 
 
-def test_partitioned_multi_pieces_world2_gloo():
+@pytest.mark.parametrize("world", [2, 3])
+def test_partitioned_multi_pieces_gloo(world):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in procs]
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res), res
-    assert res[0][2] == res[1][2] and len(res[0][2]) == 2
+    assert all(r[2] == res[0][2] for r in res) and len(res[0][2]) == world
 
 
 def test_partitioned_rejects_zero_in_pattern_and_single_rank():

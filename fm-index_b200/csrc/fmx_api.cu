@@ -177,6 +177,8 @@ static void dispatch(const fmx_index *idx, F &&f) {
 extern "C" {
 
 const char *fmx_last_error(void) { return g_err.c_str(); }
+// fmx_group.cu reports its own errors through the same thread-local message
+void fmx_internal_set_error(const char *msg) { g_err = msg ? msg : ""; }
 int fmx_version(void) { return 100; }
 uint64_t fmx_launch_count(void) { return g_launches.load(); }
 void fmx_free(void *p) { std::free(p); }

@@ -74,10 +74,10 @@ struct fmx_group {
     std::mutex mu;
 };
 
-// fmx_last_error() is per thread and owned by fmx_api.cu: errors of the underlying C-ABI calls are reported there; the
-// group's own argument errors go to stderr.
+// fmx_last_error() is per thread and owned by fmx_api.cu: the group's own errors are stored there too
+extern "C" void fmx_internal_set_error(const char *msg);
 static int gfail(int code, const char *msg) {
-    std::fprintf(stderr, "fmx_group: %s\n", msg);
+    fmx_internal_set_error(msg);
     return code;
 }
 
@@ -277,7 +277,7 @@ static int query_replicated(fmx_group *g, const fmx_query *q, uint64_t *total_hi
     if (total_hits) *total_hits = running;
     if (want_hits && running > q->capacity) overflow = true;
     if (W == 4 && running > 0xFFFFFFFFull) overflow = true;
-    if (!q->hit_off) return overflow ? FMX_ERR_CAPACITY : FMX_OK;
+    if (!q->hit_off) return overflow ? gfail(FMX_ERR_CAPACITY, "output buffer too small: total_hits holds the size needed") : FMX_OK;
     // stitch: offsets rebased by the hits of the shards before, hit lists copied behind one another
     uint64_t base = 0;
     for (int k = 0; k < R; k++) {
@@ -308,7 +308,7 @@ static int query_replicated(fmx_group *g, const fmx_query *q, uint64_t *total_hi
     }
     if (W == 8) static_cast<uint64_t *>(q->hit_off)[npat] = running;
     else static_cast<uint32_t *>(q->hit_off)[npat] = (uint32_t)running;
-    return overflow ? FMX_ERR_CAPACITY : FMX_OK;
+    return overflow ? gfail(FMX_ERR_CAPACITY, "output buffer too small: total_hits holds the size needed") : FMX_OK;
 }
 
 #define G_TRY(expr)                                   \
@@ -431,7 +431,7 @@ static int query_by_piece(fmx_group *g, const fmx_query *q, uint64_t *total_hits
 #pragma omp parallel for schedule(static)
         for (int64_t p = 0; p < (int64_t)npat; p++) cnt[p] = off[p + 1] - off[p];
     }
-    return overflow ? FMX_ERR_CAPACITY : FMX_OK;
+    return overflow ? gfail(FMX_ERR_CAPACITY, "output buffer too small: total_hits holds the size needed") : FMX_OK;
 }
 
 extern "C" int fmx_group_query_batch(const fmx_group *gc, const fmx_query *q, uint64_t *total_hits) {

@@ -793,9 +793,8 @@ struct ByteReader {
         words = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
         off = (uint32_t)(a & 3u);
     }
-    // character k of the pattern, k < len
-    __device__ __forceinline__ uint32_t get(uint32_t k) {
-        const uint32_t idx = k + off, wi = idx >> 2;
+    // aligned word wi of the stream; bytes outside the pattern read as 0 and are never touched
+    __device__ __forceinline__ uint32_t word(uint32_t wi) {
         if (wi != cur) {
             cur = wi;
             const uint32_t first = wi << 2;  // the word covers pattern bytes [first - off, first - off + 4)
@@ -810,7 +809,20 @@ struct ByteReader {
                 }
             }
         }
-        return (w >> (8u * (idx & 3u))) & 0xFFu;
+        return w;
+    }
+    // character k of the pattern, k < len
+    __device__ __forceinline__ uint32_t get(uint32_t k) {
+        const uint32_t idx = k + off;
+        return (word(idx >> 2) >> (8u * (idx & 3u))) & 0xFFu;
+    }
+    // characters k .. k+3 (k + 4 <= len), character k in the low byte.  Walking a pattern downwards in steps of four,
+    // the lower word of one call is the upper word of the next: one new load per call.
+    __device__ __forceinline__ uint32_t get4(uint32_t k) {
+        const uint32_t idx = k + off, sh = (idx & 3u) * 8u;
+        const uint32_t hi = sh ? word((idx >> 2) + 1u) : 0u;
+        const uint32_t lo = word(idx >> 2);
+        return __funnelshift_r(lo, hi, sh);
     }
 };
 typedef ByteReader<false> PatReader;   // pattern bytes: streamed, default fill
@@ -834,6 +846,10 @@ struct AnyReader {
         }
         return ((uint32_t)(w >> (bit & 63u)) & ((1u << bits) - 1u)) + 1u;
     }
+    __device__ __forceinline__ uint32_t get4(uint32_t k) {
+        if (bits == 0) return pr.get4(k);
+        return get(k) | (get(k + 1u) << 8) | (get(k + 2u) << 16) | (get(k + 3u) << 24);
+    }
 };
 
 // table index of the last K characters of a pattern (base max_character, digit = c - 1);
@@ -849,6 +865,26 @@ __device__ __forceinline__ bool kmer_index(Reader &pr, uint32_t len, uint32_t K,
     }
     idx = v;
     return valid;
+}
+
+// The same for alphabets of four symbols (DNA coded 1..4), four characters per step: the
+// bytes c - 1 of a word are two-bit digits d0 (first character) .. d3, and one multiply gathers them into
+// d0 * 64 + d1 * 16 + d2 * 4 + d3 (the four partial products land in disjoint bit pairs of the top byte).
+template <class Reader>
+__device__ __forceinline__ bool kmer_index4(Reader &pr, uint32_t len, uint32_t K, uint32_t &idx) {
+    uint32_t v = 0, bad = 0, j = 0;
+    for (; j < (K & 3u); j++) {  // the K mod 4 leading characters one by one
+        const uint32_t d = pr.get(len - K + j) - 1u;
+        bad |= d & ~3u;
+        v = (v << 2) | (d & 3u);
+    }
+    for (; j < K; j += 4u) {
+        const uint32_t t = pr.get4(len - K + j) - 0x01010101u;  // per byte c - 1; a \0 character borrows and shows up as invalid
+        bad |= t & 0xFCFCFCFCu;
+        v = (v << 8) | (((t & 0x03030303u) * 0x40100401u) >> 24);
+    }
+    idx = v;
+    return bad == 0;
 }
 
 // memoised start of a fresh search: returns true and sets (s, e, it, len) when a table serves the
@@ -871,7 +907,11 @@ __device__ __forceinline__ bool kmer_lookup(const SearchArgs &a, uint32_t maxc, 
         return false;
     }
     uint32_t idx;
-    if (!kmer_index(q, len, K, maxc, idx)) return false;
+    if (maxc == 4u) {
+        if (!kmer_index4(q, len, K, idx)) return false;
+    } else if (!kmer_index(q, len, K, maxc, idx)) {
+        return false;
+    }
     uint2 t = ldg64_s(tab + idx);
     s = t.x;
     e = t.y;
@@ -923,7 +963,44 @@ struct StagedReader {
         const uint32_t idx = k - wb;
         return (sp[idx >> 2][threadIdx.x] >> (8u * (idx & 3u))) & 0xFFu;
     }
+    // characters k .. k+3, character k in the low byte
+    __device__ __forceinline__ uint32_t get4(uint32_t k) {
+        if (k >= wb && k + 4u <= wb + 32u) {
+            const uint32_t idx = k - wb, sh = (idx & 3u) * 8u, wi = idx >> 2;
+            const uint32_t lo = sp[wi][threadIdx.x], hi = sh ? sp[wi + 1u][threadIdx.x] : 0u;  // wi + 1 <= 7 when sh != 0
+            return __funnelshift_r(lo, hi, sh);
+        }
+        const uint32_t c3 = get(k + 3u), c2 = get(k + 2u), c1 = get(k + 1u), c0 = get(k);  // downwards: the tile moves once
+        return c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
+    }
 };
+
+// The comparison of the seed-and-verify tail: characters rd[0 .. rem) against text[pos - rem .. pos) (`tr` reads that
+// window), from the END backwards, four characters per step; stops in front of a \0 of the text or at the first
+// mismatch.  Returns the number of characters that match; `c` = the pattern character at the stop (unset when all match).
+template <class Reader>
+__device__ __forceinline__ uint32_t match_backward(Reader &rd, TextReader &tr, uint32_t rem, uint32_t &c) {
+    uint32_t matched = 0;
+    while (matched + 4u <= rem) {
+        const uint32_t i = rem - 4u - matched;
+        const uint32_t tw = tr.get4(i), pw = rd.get4(i);
+        const uint32_t stop = __vcmpne4(tw, pw) | __vcmpeq4(tw, 0u);  // 0xFF per byte that ends the match
+        if (stop) {
+            const uint32_t good = (uint32_t)__clz((int)stop) >> 3;   // matching characters above the first stop byte
+            matched += good;
+            c = (pw >> (8u * (3u - good))) & 0xFFu;
+            return matched;
+        }
+        matched += 4u;
+    }
+    while (matched < rem) {
+        const uint32_t tc = tr.get(rem - 1u - matched);
+        c = rd.get(rem - 1u - matched);
+        if (tc == 0u || c != tc) break;
+        matched++;
+    }
+    return matched;
+}
 
 // Seed-and-verify tail (fmx_layout.h): the range is the single row s and `rem` characters rd[0 .. rem) are
 // still to be consumed.  Locates the row, compares the characters with the text, and jumps to the row the
@@ -950,12 +1027,8 @@ __device__ __forceinline__ uint32_t verify_tail(const FmxDev &ix, const Tabs<LAY
     if (pos < rem) return 0;
     // characters rd[rem-1], rd[rem-2], .. against text[pos-1], text[pos-2], ..
     TextReader tr(ix.text + (pos - rem), rem);
-    uint32_t matched = 0;
-    while (matched < rem) {
-        const uint32_t t = tr.get(rem - 1u - matched);
-        if (t == 0u || rd.get(rem - 1u - matched) != t) break;
-        matched++;
-    }
+    uint32_t cstop;
+    const uint32_t matched = match_backward(rd, tr, rem, cstop);
     if (!matched) return 0;
     const uint32_t q = pos - matched, step = 1u << ix.isa_level;
     uint32_t q4 = (q + step - 1u) & ~(step - 1u), r;

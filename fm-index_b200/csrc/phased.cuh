@@ -193,12 +193,7 @@ __global__ void __launch_bounds__(256) k_ph_verify(const __grid_constant__ FmxDe
                 pattern_span(a, p, beg, len);
                 AnyReader rd(a, p, beg, len);
                 TextReader tr(ix.text + (pos - rem), rem);
-                while (matched < rem) {
-                    const uint32_t tc = tr.get(rem - 1u - matched);
-                    c = rd.get(rem - 1u - matched);
-                    if (tc == 0u || c != tc) break;
-                    matched++;
-                }
+                matched = match_backward(rd, tr, rem, c);
             }
             steps += matched;
             if (pos >= rem) {  // 32-byte sectors of the text the comparison read
@@ -261,12 +256,7 @@ __device__ __forceinline__ void query_one(const FmxDev &ix, const Tabs<LAYOUT> &
             uint32_t matched = 0, c = 0;
             if (pos >= k) {
                 TextReader tr(ix.text + (pos - k), k);
-                while (matched < k) {
-                    const uint32_t tc = tr.get(k - 1u - matched);
-                    c = rd.get(k - 1u - matched);
-                    if (tc == 0u || c != tc) break;
-                    matched++;
-                }
+                matched = match_backward(rd, tr, k, c);
                 const uint32_t last = pos - 1u, first = pos - (matched < k ? matched + 1u : k);
                 reqs += (last >> 5) - (first >> 5) + 1u;
             }

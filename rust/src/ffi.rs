@@ -17,13 +17,40 @@ pub const FMX_SEARCH_EXACT: c_int = 3;
 pub const FMX_LEVEL_COUNT_ONLY: c_int = -1;
 pub const FMX_ERR_INVALID_TEXT: c_int = -1;
 pub const FMX_ERR_PATTERN_CHAR: c_int = -5;
+pub const FMX_ERR_CAPACITY: c_int = -9;
+pub const FMX_MODE_AUTO: c_int = 0;
+pub const FMX_MODE_COMPACT: c_int = 1;
+pub const FMX_MODE_RICH: c_int = 2;
+
+/// struct fmx_query (include/fmx.h): one descriptor for the fused count + locate call
+#[repr(C)]
+pub struct fmx_query {
+    pub mode: c_int,
+    pub packed_bits: u32,
+    pub patterns: *const c_void,
+    pub pat_off: *const u64,
+    pub fixed_len: u64,
+    pub npat: u64,
+    pub out_width: u32,
+    pub reserved: u32,
+    pub out_s: *mut u64,
+    pub out_e: *mut u64,
+    pub counts: *mut c_void,
+    pub hit_off: *mut c_void,
+    pub positions: *mut c_void,
+    pub piece_ids: *mut c_void,
+    pub capacity: u64,
+}
 
 extern "C" {
     pub fn fmx_last_error() -> *const c_char;
     pub fn fmx_free(p: *mut c_void);
     pub fn fmx_index_build(text: *const c_void, n: u64, char_width: u32, max_character: u64, kind: c_int,
                            level: c_int, device: c_int, out: *mut *mut fmx_index) -> c_int;
+    pub fn fmx_index_build_ex(text: *const c_void, n: u64, char_width: u32, max_character: u64, kind: c_int,
+                              level: c_int, device: c_int, mode: c_int, out: *mut *mut fmx_index) -> c_int;
     pub fn fmx_index_free(idx: *mut fmx_index);
+    pub fn fmx_query_batch(idx: *const fmx_index, q: *const fmx_query, total_hits: *mut u64) -> c_int;
     pub fn fmx_index_len(idx: *const fmx_index) -> u64;
     pub fn fmx_index_device_bytes(idx: *const fmx_index) -> u64;
     pub fn fmx_index_pieces_count(idx: *const fmx_index) -> u64;

@@ -788,6 +788,9 @@ def roofline_block(args, w, index, mode_name, npat, hits, ms_step, ms_count, pha
         r["l2_read_requests_per_step"] = reqs
         r["requests_per_pattern"] = reqs / npat
         r["dram_bytes_per_pattern"] = traffic / npat
+        r["active_lanes_per_instruction"] = cap.get("active_lanes_per_instruction")
+        r["ncu_kernels"] = [{k: v for k, v in kd.items() if k in ("kernel", "ns_under_ncu", "l2_read_requests", "active_lanes_per_instruction")}
+                            for kd in cap.get("kernels", [])]
         if gp:
             fr_req = reqs / t / gp
             r["random_access"].update({"achieved_requests_per_s": reqs / t, "frac": fr_req})

@@ -8,8 +8,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfmx_b200.so")
-SOURCES = ["fmx_api.cu", "fmx_group.cu", "gpu_sa.cu", "builder.cpp"]
-DEPS = SOURCES + ["kernels.cuh", "phased.cuh", "fmx_layout.h", "builder.h", "sais.hpp", os.path.join("..", "..", "include", "fmx.h")]
+SOURCES = ["fmx_api.cu", "fmx_group.cu", "gpu_sa.cu", "gpu_build.cu", "builder.cpp"]
+DEPS = SOURCES + ["kernels.cuh", "phased.cuh", "scan3.cuh", "fmx_layout.h", "builder.h", "sais.hpp", os.path.join("..", "..", "include", "fmx.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -385,9 +385,7 @@ struct PhaseTimer {
     }
 };
 
-int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level,
-               HostBlob &blob, std::string &err, int sa_device, int mode) {
-    PhaseTimer tm;
+int resolve_mode(int &mode, std::string &err) {
     if (mode == FMX_MODE_AUTO) {
         const char *m = std::getenv("FMX_MODE");
         if (m && !std::strcmp(m, "compact")) mode = FMX_MODE_COMPACT;
@@ -397,6 +395,51 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
         err = "unknown index mode";
         return FMX_ERR_INVALID_ARG;
     }
+    return 0;
+}
+
+// Which of the structures that answer from the suffix array an index gets (fmx_layout.h; include/fmx.h "modes").
+VerifyPlan plan_verify(int kind, uint64_t n, int mode, int level, bool interior_zero, uint64_t rank_bytes, bool use_sym) {
+    VerifyPlan p;
+    bool verify = (kind == FMX_KIND_FM || kind == FMX_KIND_MULTI) && n >= (mode == FMX_MODE_RICH ? 64u : 4096u);
+    const char *nv = std::getenv("FMX_NO_VERIFY");
+    if (nv && nv[0] && nv[0] != '0') verify = false;
+    if (mode == FMX_MODE_COMPACT || interior_zero) verify = false;
+    uint64_t budget = 32768ull << 20;
+    if (const char *vb = std::getenv("FMX_VERIFY_BUDGET_MB")) budget = std::strtoull(vb, nullptr, 10) << 20;
+    // an index whose rank structure sits in the 126 MB L2 answers a step from L2; the tail's three or four
+    // DRAM reads are slower than that (measured on the 100 MB DNA config), so it is not built there
+    uint64_t min_rank = 192ull << 20;
+    if (const char *mr = std::getenv("FMX_VERIFY_MIN_RANK_MB")) min_rank = std::strtoull(mr, nullptr, 10) << 20;
+    if (rank_bytes < min_rank && mode != FMX_MODE_RICH) verify = false;
+    p.dense = verify && 9 * n <= budget;
+    if (verify && !p.dense) verify = kind == FMX_KIND_FM && use_sym && (level < 0 || level <= 3);
+    p.verify = verify;
+    p.dense_sa = p.dense;
+    // RLFM in the HBM-rich mode: no verify tail (its ranges rarely narrow to one row), but locate by the
+    // resident suffix array
+    if (kind == FMX_KIND_RLFM && mode == FMX_MODE_RICH && level >= 0 && !interior_zero && n >= 64 && 4 * n <= budget) p.dense_sa = true;
+    p.isa_level = p.dense ? 0u : 2u;
+    return p;
+}
+
+// section offsets (256-byte aligned, in enum order) and the total size, from the section sizes
+void layout_sections(FmxBlobHeader &hdr, const uint64_t bytes[SEC_COUNT]) {
+    uint64_t off = (sizeof(FmxBlobHeader) + FMX_SECTION_ALIGN - 1) / FMX_SECTION_ALIGN * FMX_SECTION_ALIGN;
+    for (int k = 0; k < (int)SEC_COUNT; k++) {
+        hdr.sec[k].offset = bytes[k] ? off : 0;
+        hdr.sec[k].bytes = bytes[k];
+        off += (bytes[k] + FMX_SECTION_ALIGN - 1) / FMX_SECTION_ALIGN * FMX_SECTION_ALIGN;
+    }
+    hdr.total_bytes = off;
+}
+
+bool q4_forbidden_by_env() { return force_binary_wavelet(); }
+
+int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level,
+               HostBlob &blob, std::string &err, int sa_device, int mode) {
+    PhaseTimer tm;
+    if (int mrc = resolve_mode(mode, err)) return mrc;
     if (mc == 0 || mc > 255) {
         err = "max_character must be in 1..=255 for u8 texts";
         return FMX_ERR_INVALID_ARG;
@@ -591,33 +634,15 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
     // seed-and-verify structures (fmx_layout.h): dense (full SA + full ISA) within the budget, else sampled
     // for the SYM layout (text, ISA every 4 positions, SA samples of level <= 3), else none
     std::vector<uint32_t> isa_s;
-    bool verify = (kind == FMX_KIND_FM || kind == FMX_KIND_MULTI) && n >= (mode == FMX_MODE_RICH ? 64u : 4096u), verify_dense = false;
     // A single-text index (FM, RLFM) over a text with INTERIOR zeros: the reference's lf_map2(0, i) = cs[0] + rank(i, 0)
     // (fm_index.rs:93-95) is not the true LF row there, so neither its walks nor its searches agree with the
     // suffix array; the structures that answer from the suffix array are not built for such texts.
     bool interior_zero = false;
     if (kind != FMX_KIND_MULTI && n >= 2) interior_zero = std::memchr(text, 0, n - 1) != nullptr;
-    bool dense_sa = false;  // SEC_VSA: the full suffix array (verify path; HBM-rich locate)
-    {
-        const char *nv = std::getenv("FMX_NO_VERIFY");
-        if (nv && nv[0] && nv[0] != '0') verify = false;
-        if (mode == FMX_MODE_COMPACT || interior_zero) verify = false;
-        uint64_t budget = 32768ull << 20;
-        if (const char *vb = std::getenv("FMX_VERIFY_BUDGET_MB")) budget = std::strtoull(vb, nullptr, 10) << 20;
-        // an index whose rank structure sits in the 126 MB L2 answers a step from L2; the tail's three or four
-        // DRAM reads are slower than that (measured on the 100 MB DNA config), so it is not built there
-        uint64_t min_rank = 192ull << 20;
-        if (const char *mr = std::getenv("FMX_VERIFY_MIN_RANK_MB")) min_rank = std::strtoull(mr, nullptr, 10) << 20;
-        const uint64_t rank_bytes = use_q4 ? (n / 64 + 1) * 32 : (use_sym ? sym_bytes(cs_len, n) : (uint64_t)L * (n / FMX_RB_BITS + 1) * 32);
-        if (rank_bytes < min_rank && mode != FMX_MODE_RICH) verify = false;
-        verify_dense = verify && 9 * n <= budget;
-        if (verify && !verify_dense) verify = kind == FMX_KIND_FM && use_sym && (level < 0 || level <= 3);
-        dense_sa = verify_dense;
-        // RLFM in the HBM-rich mode: no verify tail (its ranges rarely narrow to one row), but locate by the
-        // resident suffix array
-        if (kind == FMX_KIND_RLFM && mode == FMX_MODE_RICH && level >= 0 && !interior_zero && n >= 64 && 4 * n <= budget) dense_sa = true;
-    }
-    const uint32_t isa_level = verify_dense ? 0u : 2u;
+    const uint64_t rank_bytes = use_q4 ? (n / 64 + 1) * 32 : (use_sym ? sym_bytes(cs_len, n) : (uint64_t)L * (n / FMX_RB_BITS + 1) * 32);
+    const VerifyPlan vp = plan_verify(kind, n, mode, level, interior_zero, rank_bytes, use_sym);
+    const bool verify = vp.verify, verify_dense = vp.dense, dense_sa = vp.dense_sa;
+    const uint32_t isa_level = vp.isa_level;
     if (verify) {
         isa_s.assign(((n - 1) >> isa_level) + 1, 0);
 #pragma omp parallel for schedule(static)
@@ -678,13 +703,10 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
         sec[SEC_RL_BSEL] = {bsel.data(), bsel.size() * 4};
         sec[SEC_RL_BPSEL] = {bpsel.data(), bpsel.size() * 4};
     }
-    uint64_t off = (sizeof(FmxBlobHeader) + FMX_SECTION_ALIGN - 1) / FMX_SECTION_ALIGN * FMX_SECTION_ALIGN;
-    for (int k = 0; k < (int)SEC_COUNT; k++) {
-        hdr.sec[k].offset = sec[k].bytes ? off : 0;
-        hdr.sec[k].bytes = sec[k].bytes;
-        off += (sec[k].bytes + FMX_SECTION_ALIGN - 1) / FMX_SECTION_ALIGN * FMX_SECTION_ALIGN;
-    }
-    hdr.total_bytes = off;
+    uint64_t sec_bytes[SEC_COUNT];
+    for (int k = 0; k < (int)SEC_COUNT; k++) sec_bytes[k] = sec[k].bytes;
+    layout_sections(hdr, sec_bytes);
+    const uint64_t off = hdr.total_bytes;
     if (blob.alloc(off, true)) {
         err = "out of host memory for the index blob";
         return FMX_ERR_OOM;

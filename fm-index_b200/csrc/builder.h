@@ -34,7 +34,25 @@ struct HostBlob {
 int build_blob(const uint8_t *text, uint64_t n, uint64_t max_character, int kind, int level,
                HostBlob &blob, std::string &err, int sa_device = -1, int mode = 0);
 
+// pieces of build_blob shared with the GPU builder (gpu_build.cu)
+struct VerifyPlan {
+    bool verify = false, dense = false, dense_sa = false;
+    uint32_t isa_level = 0;
+};
+int resolve_mode(int &mode, std::string &err);
+VerifyPlan plan_verify(int kind, uint64_t n, int mode, int level, bool interior_zero, uint64_t rank_bytes, bool use_sym);
+void layout_sections(FmxBlobHeader &hdr, const uint64_t bytes[SEC_COUNT]);
+bool q4_forbidden_by_env();
+
+// gpu_build.cu: the whole blob built in device memory (Q4 layouts of FM / MultiPieces indexes).
+// Returns 0 and a cudaMalloc'd blob + its header; FMX_ERR_UNSUPPORTED when this text / kind is not its case
+// (the caller then takes the host builder).
+int gpu_build_q4_blob(const uint8_t *text, uint64_t n, uint64_t max_character, int kind, int level, int mode, int device,
+                      void **d_blob_out, FmxBlobHeader *hdr_out, std::string &err);
+
 // gpu_sa.cu
+int gpu_suffix_array_device(const uint8_t *d_text, uint64_t n, uint32_t bits, int device, uint32_t **d_sa_out, int *rounds_out,
+                            std::string &err);
 int gpu_suffix_array(const uint8_t *text, uint64_t n, uint32_t bits, int device, uint32_t *sa_out, int *rounds_out,
                      std::string &err);
 

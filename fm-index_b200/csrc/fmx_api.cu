@@ -132,6 +132,11 @@ struct fmx_index {
     mutable uint32_t pev_mask = 0;
 };
 
+static bool env_flag(const char *name) {
+    const char *v = std::getenv(name);
+    return v && v[0] && v[0] != '0';
+}
+
 static int build_kmer_table(fmx_index *idx);
 static int build_big_table(fmx_index *idx, uint64_t budget_bytes);
 
@@ -292,6 +297,28 @@ static void bind_sections(fmx_index *idx) {
     if (idx->persist_blocks_per_sm < 1) idx->persist_blocks_per_sm = 1;
 }
 
+// common tail of every constructor: the blob is resident in idx->d_blob
+static int finish_index(fmx_index *idx, fmx_index **out) {
+    cudaError_t e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&idx->d_err, 256);
+    if (e == cudaSuccess) e = cudaMemset(idx->d_err, 0, 256);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        fmx_index_free(idx);
+        return fail(FMX_ERR_CUDA, std::string("index setup: ") + cudaGetErrorString(e));
+    }
+    idx->d_work = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(idx->d_err) + 64);
+    bind_sections(idx);
+    int rc = build_kmer_table(idx);
+    if (rc) {
+        fmx_index_free(idx);
+        return rc;
+    }
+    *out = idx;
+    return FMX_OK;
+}
+
+// uploads a blob the caller owns (nothing of it is kept on the host: save() reads the device copy back)
 static int upload(const uint8_t *blob, uint64_t blob_bytes, int device, fmx_index **out) {
     FmxBlobHeader hdr;
     std::string err;
@@ -314,23 +341,22 @@ static int upload(const uint8_t *blob, uint64_t blob_bytes, int device, fmx_inde
         return fail(FMX_ERR_OOM, std::string("cudaMalloc index: ") + cudaGetErrorString(e));
     }
     e = cudaMemcpy(idx->d_blob, blob, blob_bytes, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMalloc(&idx->d_err, 256);
-    if (e == cudaSuccess) e = cudaMemset(idx->d_err, 0, 256);
     if (e != cudaSuccess) {
         cudaFree(idx->d_blob);
         delete idx;
         return fail(FMX_ERR_CUDA, std::string("index upload: ") + cudaGetErrorString(e));
     }
-    idx->d_work = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(idx->d_err) + 64);
-    bind_sections(idx);
-    rc = build_kmer_table(idx);
-    if (rc) {
-        fmx_index_free(idx);
-        return rc;
-    }
-    *out = idx;
-    return FMX_OK;
+    return finish_index(idx, out);
+}
+
+// takes over a blob that was built in device memory (gpu_build.cu)
+static int adopt(const FmxBlobHeader &hdr, void *d_blob, int device, fmx_index **out) {
+    CUDA_TRY(cudaSetDevice(device));
+    fmx_index *idx = new fmx_index();
+    idx->hdr = hdr;
+    idx->device = device;
+    idx->d_blob = d_blob;
+    return finish_index(idx, out);
 }
 
 // A copy of an index on another device: the blob and the k-mer tables travel device to device (NVLink peer copies
@@ -401,8 +427,17 @@ int fmx_index_build_ex(const void *text, uint64_t n, uint32_t char_width, uint64
         return fail(FMX_ERR_CUDA, "no CUDA device available (the engine has no CPU fallback)");
     }
     if (device < 0 || device >= ndev) return fail(FMX_ERR_INVALID_ARG, "device ordinal out of range");
-    HostBlob b;
     std::string err;
+    if (!env_flag("FMX_HOST_BUILD") && !env_flag("FMX_HOST_SA")) {
+        // Q4 layouts of FM / MultiPieces indexes: the whole blob is built in device memory (gpu_build.cu)
+        void *d_blob = nullptr;
+        FmxBlobHeader hdr;
+        int grc = gpu_build_q4_blob(static_cast<const uint8_t *>(text), n, max_character, kind, level, mode, device, &d_blob, &hdr, err);
+        if (grc == 0) return adopt(hdr, d_blob, device, out);
+        if (grc != FMX_ERR_UNSUPPORTED) return fail(grc, err);
+        err.clear();
+    }
+    HostBlob b;
     int rc = build_blob(static_cast<const uint8_t *>(text), n, max_character, kind, level, b, err, device, mode);
     if (rc) return fail(rc, err);
     return upload(b.p, b.n, device, out);
@@ -589,11 +624,6 @@ static int device_scan(const Tin *in, uint64_t n, Tout *out, Op op, bool write_t
 }
 
 // ------------------------------------------------------------------ search
-
-static bool env_flag(const char *name) {
-    const char *v = std::getenv(name);
-    return v && v[0] && v[0] != '0';
-}
 
 // k-mer bucketing of the batch (see SearchArgs::order): histogram, exclusive scan, scatter
 static int bucket_patterns(const fmx_index *idx, DevBuf *buf, SearchArgs &a, cudaStream_t st) {

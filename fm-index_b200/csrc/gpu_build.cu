@@ -1,0 +1,298 @@
+// gpu_build.cu -- index construction on the GPU, next to the suffix array.
+//
+// Round 1 built only the suffix array on the device; the BWT, the rank blocks, the inverse suffix array, the samples
+// and the blob assembly stayed host work (13 of the 14 s of the 1 GB DNA build, plus a 10.5 GB host-to-device copy).
+// Here the whole device-layout blob (fmx_layout.h) of a Q4 index -- max_character <= 4, FMIndex and
+// FMIndexMultiPieces: four of the five BASELINE configs -- is produced in device memory:
+//
+//   reference producer (file:line)                         here
+//   suffix array            sais.rs:115-144                gpu_sa.cu (prefix doubling), left on the device
+//   BWT                     fm_index.rs:44-58              k_bwt: bw[i] = text[sa[i] - 1], 0 when sa[i] == 0
+//   rank structure          (vers-vecs WaveletMatrix)      k_q4_pack -> own scans (scan3.cuh) -> k_q4_counts: Q4 blocks
+//   SA samples              sample.rs:21-44                k_samples: sa[i << level]
+//   inverse SA / full SA / text (verify, rich locate)      k_isa (scatter), device copies
+//   cs                      sais.rs:9-32                   host histogram of the text (5 counters)
+//   doc / first row         multi_pieces.rs:53-97          host, from the <= 1024 zero rows gathered from the device
+//
+// The result is byte-identical to the host builder's blob (tests/test_gpu_parity.py::
+// test_gpu_built_blob_identical_to_host_built): same header, same sections, same padding.
+// Other layouts (SYM, WM4, binary wavelet) and RLFM keep the host builder (builder.cpp).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/fmx.h"
+#include "builder.h"
+#include "scan3.cuh"
+
+namespace fmx {
+
+__global__ void k_bwt(const uint8_t *text, const uint32_t *sa, uint64_t n, uint8_t *bwt) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const uint32_t p = sa[i];
+        bwt[i] = p ? text[p - 1] : (uint8_t)0;
+    }
+}
+
+// one thread per Q4 block: 64 symbols -> two bit planes of the codes (symbol - 1; \0 stored as code 0) in words 4..7,
+// the block's own code counts to cnt[c * nblk + b] (prefix sums follow)
+__global__ void k_q4_pack(const uint8_t *bwt, uint64_t n, uint64_t nblk, uint32_t *blocks, uint32_t *cnt) {
+    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblk) return;
+    const uint64_t lo = b * 64, hi = lo + 64 < n ? lo + 64 : n;
+    uint32_t p0[2] = {0, 0}, p1[2] = {0, 0}, c[4] = {0, 0, 0, 0};
+    for (uint64_t i = lo; i < hi; i++) {
+        const uint32_t sym = bwt[i], code = sym ? sym - 1u : 0u, t = (uint32_t)(i - lo);
+        p0[t >> 5] |= (code & 1u) << (t & 31u);
+        p1[t >> 5] |= (code >> 1) << (t & 31u);
+        c[code]++;
+    }
+    uint32_t *blk = blocks + b * 8;
+    blk[4] = p0[0];
+    blk[5] = p0[1];
+    blk[6] = p1[0];
+    blk[7] = p1[1];
+    for (int k = 0; k < 4; k++) cnt[(uint64_t)k * nblk + b] = c[k];
+}
+
+__global__ void k_q4_counts(uint32_t *blocks, const uint32_t *cnt, uint64_t nblk) {
+    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblk) return;
+    for (int k = 0; k < 4; k++) blocks[b * 8 + k] = cnt[(uint64_t)k * nblk + b];
+}
+
+// rows whose BWT symbol is \0 (at most `cap`; *count keeps counting past it)
+__global__ void k_zero_rows(const uint8_t *bwt, uint64_t n, uint32_t *rows, uint32_t cap, unsigned *count) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && bwt[i] == 0) {
+        const unsigned k = atomicAdd(count, 1u);
+        if (k < cap) rows[k] = (uint32_t)i;
+    }
+}
+
+__global__ void k_gather32(const uint32_t *src, const uint32_t *idx, uint32_t m, uint32_t *out) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < m) out[k] = src[idx[k]];
+}
+
+__global__ void k_isa(const uint32_t *sa, uint64_t n, uint32_t *isa) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) isa[sa[i]] = (uint32_t)i;
+}
+
+__global__ void k_samples(const uint32_t *sa, uint64_t count, uint32_t level, uint32_t *out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = sa[i << level];
+}
+
+static inline uint32_t log2_u64(uint64_t x) { return 63u - (uint32_t)__builtin_clzll(x); }
+
+#define GB_TRY(expr)                                                                  \
+    do {                                                                              \
+        cudaError_t _e = (expr);                                                      \
+        if (_e != cudaSuccess) {                                                      \
+            err = std::string("GPU index build: ") + #expr + ": " + cudaGetErrorString(_e); \
+            rc = _e == cudaErrorMemoryAllocation ? FMX_ERR_OOM : FMX_ERR_CUDA;        \
+            goto fail;                                                                \
+        }                                                                             \
+    } while (0)
+
+int gpu_build_q4_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level, int mode, int device,
+                      void **d_blob_out, FmxBlobHeader *hdr_out, std::string &err) {
+    *d_blob_out = nullptr;
+    if (mc == 0 || mc > 4 || q4_forbidden_by_env() || (kind != FMX_KIND_FM && kind != FMX_KIND_MULTI) || n < (1u << 16) ||
+        n >= (1ull << 32) - 1)
+        return FMX_ERR_UNSUPPORTED;
+    // the text's zeros: the Q4 exception list holds as many, and they are the piece ends of a multi-piece text
+    std::vector<uint32_t> zeros;
+    {
+        const uint64_t chunk = 1ull << 22;
+        const int64_t nchunks = (int64_t)((n + chunk - 1) / chunk);
+        std::vector<std::vector<uint32_t>> part((size_t)nchunks);
+        int bad = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(| : bad)
+        for (int64_t c = 0; c < nchunks; c++) {
+            const uint64_t lo = (uint64_t)c * chunk, hi = lo + chunk < n ? lo + chunk : n;
+            for (uint64_t i = lo; i < hi; i++) {
+                bad |= text[i] > mc;
+                if (text[i] == 0) part[(size_t)c].push_back((uint32_t)i);
+            }
+        }
+        if (bad) return FMX_ERR_UNSUPPORTED;  // the host builder reports it
+        for (auto &v : part) zeros.insert(zeros.end(), v.begin(), v.end());
+    }
+    if (zeros.size() > FMX_MAX_EXC || zeros.empty() || zeros.back() != n - 1 || text[0] == 0 || (n >= 2 && text[n - 2] == 0))
+        return FMX_ERR_UNSUPPORTED;  // invalid texts and texts with many zeros: the host builder's business
+    const bool interior_zero = kind != FMX_KIND_MULTI && zeros.size() > 1;
+    if (int mrc = resolve_mode(mode, err)) return mrc;
+
+    const uint32_t L = log2_u64(mc) + 1, cs_len = (uint32_t)mc + 1;
+    const uint64_t nblk = n / 64 + 1;
+    const VerifyPlan vp = plan_verify(kind, n, mode, level, interior_zero, nblk * 32, false);
+    if (vp.verify && !vp.dense) return FMX_ERR_UNSUPPORTED;  // the sampled verify form exists for SYM layouts only
+
+    FmxBlobHeader hdr;
+    std::memset(&hdr, 0, sizeof(hdr));
+    hdr.magic = FMX_BLOB_MAGIC;
+    hdr.version = FMX_BLOB_VERSION;
+    hdr.kind = (uint32_t)kind;
+    hdr.n = n;
+    hdr.seq_len = n;
+    hdr.levels = L;
+    hdr.max_character = (uint32_t)mc;
+    hdr.cs_len = cs_len;
+    hdr.layout = FMX_LAYOUT_QUAT;
+    hdr.nexc = (uint32_t)zeros.size();
+    hdr.reserved[0] = (uint64_t)mode;
+    if (vp.verify) {
+        hdr.verify = 1;
+        hdr.isa_level = vp.isa_level;
+    }
+    if (level >= 0) {
+        hdr.has_locate = 1;
+        uint32_t lvl = (uint32_t)level;
+        hdr.sa_word_size = log2_u64(n) + 1;
+        if (lvl >= 63 || n <= (1ull << lvl)) lvl = 0;  // sample.rs:28-31
+        hdr.sa_level = lvl;
+        hdr.sa_count = ((n - 1) >> lvl) + 1;
+    }
+    hdr.vsa_level = vp.dense ? 0u : hdr.sa_level;
+    if (kind == FMX_KIND_MULTI) hdr.ndoc = zeros.size();
+
+    // cs (sais.rs:21-32)
+    std::vector<uint32_t> cs(cs_len + 1, 0), adj(cs_len, 0);
+    {
+        std::vector<uint64_t> occ(cs_len, 0);
+#pragma omp parallel
+        {
+            std::vector<uint64_t> mine(cs_len, 0);
+#pragma omp for schedule(static) nowait
+            for (int64_t i = 0; i < (int64_t)n; i++) mine[text[i]]++;
+#pragma omp critical
+            for (uint32_t c = 0; c < cs_len; c++) occ[c] += mine[c];
+        }
+        uint64_t sum = 0;
+        for (uint32_t c = 0; c < cs_len; c++) {
+            cs[c] = (uint32_t)sum;
+            sum += occ[c];
+        }
+        cs[cs_len] = (uint32_t)n;
+    }
+
+    uint64_t bytes[SEC_COUNT];
+    std::memset(bytes, 0, sizeof(bytes));
+    bytes[SEC_LEVEL0] = nblk * 32;
+    bytes[SEC_EXC] = zeros.size() * 4;
+    bytes[SEC_ADJ] = (uint64_t)cs_len * 4;
+    bytes[SEC_CS] = (uint64_t)(cs_len + 1) * 4;
+    if (hdr.has_locate) bytes[SEC_SA] = hdr.sa_count * 4;
+    if (vp.verify) {
+        bytes[SEC_TEXT] = n;
+        bytes[SEC_ISA] = n * 4;
+    }
+    if (vp.dense_sa) bytes[SEC_VSA] = n * 4;
+    if (kind == FMX_KIND_MULTI) {
+        bytes[SEC_DOC] = zeros.size() * 4;
+        bytes[SEC_PIECE_END] = zeros.size() * 4;
+    }
+    layout_sections(hdr, bytes);
+
+    int rc = FMX_ERR_CUDA;
+    uint8_t *d_text = nullptr, *d_bwt = nullptr, *blob = nullptr;
+    uint32_t *d_sa = nullptr, *d_cnt = nullptr, *d_rows = nullptr, *d_rowsa = nullptr;
+    unsigned *d_count = nullptr;
+    const unsigned T = 256;
+    auto grid = [&](uint64_t m) { return (unsigned)((m + T - 1) / T); };
+    auto at = [&](int k) { return blob + hdr.sec[k].offset; };
+    std::vector<uint32_t> rows, rowsa, doc;
+    unsigned nz = 0;
+
+    GB_TRY(cudaSetDevice(device));
+    GB_TRY(cudaMalloc(&d_text, n));
+    GB_TRY(cudaMemcpy(d_text, text, n, cudaMemcpyHostToDevice));
+    {
+        std::string serr;
+        int src = gpu_suffix_array_device(d_text, n, L, device, &d_sa, nullptr, serr);
+        if (src) {
+            err = "GPU suffix array construction failed: " + serr;
+            rc = src;
+            goto fail;
+        }
+    }
+    GB_TRY(cudaMalloc(&blob, hdr.total_bytes));
+    GB_TRY(cudaMemset(blob, 0, hdr.total_bytes));
+    GB_TRY(cudaMalloc(&d_bwt, n));
+    GB_TRY(cudaMalloc(&d_cnt, nblk * 16));
+    GB_TRY(cudaMalloc(&d_rows, FMX_MAX_EXC * 4));
+    GB_TRY(cudaMalloc(&d_rowsa, FMX_MAX_EXC * 4));
+    GB_TRY(cudaMalloc(&d_count, 4));
+    GB_TRY(cudaMemset(d_count, 0, 4));
+
+    k_bwt<<<grid(n), T>>>(d_text, d_sa, n, d_bwt);
+    k_q4_pack<<<grid(nblk), T>>>(d_bwt, n, nblk, reinterpret_cast<uint32_t *>(at(SEC_LEVEL0)), d_cnt);
+    GB_TRY(cudaGetLastError());
+    for (int c = 0; c < 4; c++)  // occurrences of code c before every block
+        GB_TRY((scan3::run<uint32_t, scan3::Sum32, true>(d_cnt + (uint64_t)c * nblk, nblk, d_cnt + (uint64_t)c * nblk, scan3::Sum32(), 0u, 0)));
+    k_q4_counts<<<grid(nblk), T>>>(reinterpret_cast<uint32_t *>(at(SEC_LEVEL0)), d_cnt, nblk);
+    k_zero_rows<<<grid(n), T>>>(d_bwt, n, d_rows, FMX_MAX_EXC, d_count);
+    GB_TRY(cudaGetLastError());
+    GB_TRY(cudaMemcpy(&nz, d_count, 4, cudaMemcpyDeviceToHost));
+    if (nz != zeros.size()) {
+        err = "GPU index build: the BWT holds another number of zeros than the text";
+        rc = FMX_ERR_CUDA;
+        goto fail;
+    }
+    rows.resize(nz);
+    GB_TRY(cudaMemcpy(rows.data(), d_rows, nz * 4, cudaMemcpyDeviceToHost));
+    std::sort(rows.begin(), rows.end());  // SEC_EXC: ascending rows whose symbol is \0
+    GB_TRY(cudaMemcpy(at(SEC_EXC), rows.data(), nz * 4, cudaMemcpyHostToDevice));
+    if (kind == FMX_KIND_MULTI) {  // multi_pieces.rs:53-79
+        GB_TRY(cudaMemcpy(d_rows, rows.data(), nz * 4, cudaMemcpyHostToDevice));
+        k_gather32<<<(nz + T - 1) / T, T>>>(d_sa, d_rows, nz, d_rowsa);
+        GB_TRY(cudaGetLastError());
+        rowsa.resize(nz);
+        GB_TRY(cudaMemcpy(rowsa.data(), d_rowsa, nz * 4, cudaMemcpyDeviceToHost));
+        doc.assign(nz, 0);
+        for (unsigned k = 0; k < nz; k++) {  // rows[k] = select(bw, k, 0)
+            const uint64_t em = rowsa[k] ? rowsa[k] - 1 : n - 1;  // modular_sub(sa[p], 1, n)
+            const uint64_t pid = (uint64_t)(std::lower_bound(zeros.begin(), zeros.end(), (uint32_t)em) - zeros.begin());
+            if (pid == nz - 1) hdr.first_row = rows[k];
+            doc[k] = (uint32_t)pid;
+        }
+        GB_TRY(cudaMemcpy(at(SEC_DOC), doc.data(), nz * 4, cudaMemcpyHostToDevice));
+        GB_TRY(cudaMemcpy(at(SEC_PIECE_END), zeros.data(), nz * 4, cudaMemcpyHostToDevice));
+    }
+    GB_TRY(cudaMemcpy(at(SEC_ADJ), adj.data(), adj.size() * 4, cudaMemcpyHostToDevice));
+    GB_TRY(cudaMemcpy(at(SEC_CS), cs.data(), cs.size() * 4, cudaMemcpyHostToDevice));
+    if (hdr.has_locate) k_samples<<<grid(hdr.sa_count), T>>>(d_sa, hdr.sa_count, hdr.sa_level, reinterpret_cast<uint32_t *>(at(SEC_SA)));
+    if (vp.verify) {
+        GB_TRY(cudaMemcpy(at(SEC_TEXT), d_text, n, cudaMemcpyDeviceToDevice));
+        k_isa<<<grid(n), T>>>(d_sa, n, reinterpret_cast<uint32_t *>(at(SEC_ISA)));
+    }
+    if (vp.dense_sa) GB_TRY(cudaMemcpy(at(SEC_VSA), d_sa, n * 4, cudaMemcpyDeviceToDevice));
+    GB_TRY(cudaGetLastError());
+    GB_TRY(cudaMemcpy(blob, &hdr, sizeof(hdr), cudaMemcpyHostToDevice));
+    GB_TRY(cudaDeviceSynchronize());
+    *d_blob_out = blob;
+    *hdr_out = hdr;
+    blob = nullptr;
+    rc = 0;
+fail:
+    cudaFree(d_text);
+    cudaFree(d_bwt);
+    cudaFree(d_sa);
+    cudaFree(d_cnt);
+    cudaFree(d_rows);
+    cudaFree(d_rowsa);
+    cudaFree(d_count);
+    cudaFree(blob);
+    if (rc) cudaGetLastError();
+    return rc;
+}
+
+}  // namespace fmx

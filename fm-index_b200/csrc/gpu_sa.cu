@@ -13,15 +13,15 @@
 //             radix-sort again; h doubles.  Stop when every group is a single suffix.
 // Result: plain lexicographic suffix order with \0 an ordinary smallest symbol, i.e. exactly what
 // sais::build_suffix_array (reference src/suffix_array/sais.rs:115-144) returns.
-// The sorts and scans are CUB primitives (library code is fine off the hot path).
+// The radix sorts are CUB's (library code off the hot path); the scans are this repo's own (scan3.cuh).
 #include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
 #include <cuda_runtime.h>
 
 #include <cstdint>
 #include <string>
 
 #include "../../include/fmx.h"
+#include "scan3.cuh"
 
 namespace fmx {
 
@@ -63,10 +63,6 @@ __global__ void k_sa_make_keys(const uint32_t *sa, const uint32_t *grp, const ui
     key[j] = ((uint64_t)grp[j] << 32) | r2;
 }
 
-struct MaxOp {
-    __device__ __forceinline__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
-};
-
 #define SA_TRY(expr)                                                                  \
     do {                                                                              \
         cudaError_t _e = (expr);                                                      \
@@ -76,20 +72,21 @@ struct MaxOp {
         }                                                                             \
     } while (0)
 
-// text: host pointer, n symbols each < 2^bits.  sa_out: host, n entries.
-int gpu_suffix_array(const uint8_t *text, uint64_t n, uint32_t bits, int device, uint32_t *sa_out, int *rounds_out,
-                     std::string &err) {
+// d_text: DEVICE pointer, n symbols each < 2^bits.  *d_sa_out: the suffix array in device memory (cudaMalloc'd; the
+// caller frees it).  Everything else is released before returning.
+int gpu_suffix_array_device(const uint8_t *d_text, uint64_t n, uint32_t bits, int device, uint32_t **d_sa_out, int *rounds_out,
+                            std::string &err) {
+    *d_sa_out = nullptr;
     if (n == 0) return 0;
     if (n >= 0xFFFFFFFEull) {
         err = "text length must be below 2^32 - 2";
         return FMX_ERR_UNSUPPORTED;
     }
-    uint8_t *d_text = nullptr;
     uint64_t *d_key[2] = {nullptr, nullptr};
     uint32_t *d_sa[2] = {nullptr, nullptr}, *d_rank = nullptr, *d_grp = nullptr;
     unsigned long long *d_nheads = nullptr;
     void *d_temp = nullptr;
-    size_t temp_bytes = 0, scan_bytes = 0;
+    size_t temp_bytes = 0;
     int rc = FMX_ERR_CUDA;
     int rounds = 0;
     const unsigned threads = 256;
@@ -99,7 +96,6 @@ int gpu_suffix_array(const uint8_t *text, uint64_t n, uint32_t bits, int device,
     while ((1ull << nbits_n) <= n + 1 && nbits_n < 32) nbits_n++;
 
     SA_TRY(cudaSetDevice(device));
-    SA_TRY(cudaMalloc(&d_text, n));
     SA_TRY(cudaMalloc(&d_key[0], n * 8));
     SA_TRY(cudaMalloc(&d_key[1], n * 8));
     SA_TRY(cudaMalloc(&d_sa[0], n * 4));
@@ -107,13 +103,10 @@ int gpu_suffix_array(const uint8_t *text, uint64_t n, uint32_t bits, int device,
     SA_TRY(cudaMalloc(&d_rank, n * 4));
     SA_TRY(cudaMalloc(&d_grp, n * 4));
     SA_TRY(cudaMalloc(&d_nheads, 8));
-    SA_TRY(cudaMemcpy(d_text, text, n, cudaMemcpyHostToDevice));
     {
         cub::DoubleBuffer<uint64_t> keys(d_key[0], d_key[1]);
         cub::DoubleBuffer<uint32_t> vals(d_sa[0], d_sa[1]);
         SA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys, vals, (long long)n, 0, 64));
-        SA_TRY(cub::DeviceScan::InclusiveScan(nullptr, scan_bytes, d_grp, d_grp, MaxOp(), (long long)n));
-        if (scan_bytes > temp_bytes) temp_bytes = scan_bytes;
         SA_TRY(cudaMalloc(&d_temp, temp_bytes));
 
         k_sa_init<<<grid, threads>>>(d_text, n, bits, k, keys.Current(), vals.Current());
@@ -134,8 +127,8 @@ int gpu_suffix_array(const uint8_t *text, uint64_t n, uint32_t bits, int device,
                 rc = FMX_ERR_CUDA;
                 goto fail;
             }
-            tb = temp_bytes;
-            SA_TRY(cub::DeviceScan::InclusiveScan(d_temp, tb, d_grp, d_grp, MaxOp(), (long long)n));
+            // group id of every suffix = index of its group's first member + 1: a running maximum over the head marks
+            SA_TRY((scan3::run<uint32_t, scan3::Max32, false>(d_grp, n, d_grp, scan3::Max32(), 0u, 0)));
             k_sa_scatter_rank<<<grid, threads>>>(vals.Current(), d_grp, n, d_rank);
             SA_TRY(cudaGetLastError());
             k_sa_make_keys<<<grid, threads>>>(vals.Current(), d_grp, d_rank, n, h, keys.Current());
@@ -144,11 +137,14 @@ int gpu_suffix_array(const uint8_t *text, uint64_t n, uint32_t bits, int device,
             SA_TRY(cub::DeviceRadixSort::SortPairs(d_temp, tb, keys, vals, (long long)n, 0, 32 + nbits_n));
             h *= 2;
         }
-        SA_TRY(cudaMemcpy(sa_out, vals.Current(), n * 4, cudaMemcpyDeviceToHost));
+        SA_TRY(cudaDeviceSynchronize());
+        // hand the buffer holding the result to the caller
+        const int cur = vals.Current() == d_sa[0] ? 0 : 1;
+        *d_sa_out = d_sa[cur];
+        d_sa[cur] = nullptr;
     }
     rc = 0;
 fail:
-    cudaFree(d_text);
     cudaFree(d_key[0]);
     cudaFree(d_key[1]);
     cudaFree(d_sa[0]);
@@ -159,6 +155,31 @@ fail:
     cudaFree(d_temp);
     if (rc) cudaGetLastError();
     if (rounds_out) *rounds_out = rounds;
+    return rc;
+}
+
+// text: host pointer, n symbols each < 2^bits.  sa_out: host, n entries.
+int gpu_suffix_array(const uint8_t *text, uint64_t n, uint32_t bits, int device, uint32_t *sa_out, int *rounds_out,
+                     std::string &err) {
+    if (n == 0) return 0;
+    uint8_t *d_text = nullptr;
+    uint32_t *d_sa = nullptr;
+    int rc = FMX_ERR_CUDA;
+    SA_TRY(cudaSetDevice(device));
+    SA_TRY(cudaMalloc(&d_text, n));
+    SA_TRY(cudaMemcpy(d_text, text, n, cudaMemcpyHostToDevice));
+    rc = gpu_suffix_array_device(d_text, n, bits, device, &d_sa, rounds_out, err);
+    if (rc == 0 && cudaMemcpy(sa_out, d_sa, n * 4, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        err = "suffix array: device to host copy failed";
+        rc = FMX_ERR_CUDA;
+    }
+    cudaFree(d_text);
+    cudaFree(d_sa);
+    if (rc) cudaGetLastError();
+    return rc;
+fail:
+    cudaFree(d_text);
+    cudaGetLastError();
     return rc;
 }
 

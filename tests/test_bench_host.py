@@ -52,3 +52,28 @@ def test_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["unit"] == "queries/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
     assert d["config"]["workload"] == "cfg1_dna1m"
+
+
+def test_ncu_capture_is_refused_when_stale(tmp_path, monkeypatch):
+    """profiles/ncu_traffic.json entries are used only for exactly these sources, this workload, batch and mode"""
+    h = bench.source_hash()
+    assert len(h) == 16 and h == bench.source_hash()
+    prof = tmp_path / "profiles"
+    prof.mkdir()
+    entry = {"source_hash": h, "npat": 1000, "dram_bytes_per_step": 1.0, "l2_read_requests_per_step": 2.0}
+    (prof / "ncu_traffic.json").write_text(json.dumps({"target_dna1g:rich": entry, "target_dna1g:compact": dict(entry, source_hash="0" * 16)}))
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    monkeypatch.setattr(bench, "source_hash", lambda: h)
+    assert bench.ncu_capture("target_dna1g", 1000, "rich") == entry
+    assert bench.ncu_capture("target_dna1g", 2000, "rich") is None          # another batch size: never scaled
+    assert bench.ncu_capture("target_dna1g", 1000, "compact") is None       # taken from other sources
+    assert bench.ncu_capture("cfg2_dna100m", 1000, "rich") is None
+
+
+def test_rank_affinity_helper_is_harmless_without_gpus():
+    before = os.sched_getaffinity(0)
+    try:
+        n = bench.pin_rank_to_numa(0, 1)
+        assert n is None or n >= 1
+    finally:
+        os.sched_setaffinity(0, before)

@@ -1078,8 +1078,9 @@ def test_group_by_piece_and_replicated(ndev, imode):
         _same_match_sets(r["hit_off"], r["positions"], r["piece_ids"], rh, rp, rd)
         if mode in (0, 2):
             assert np.array_equal(r["counts"], np.where(e > s, e - s, 0))
-        with pytest.raises(fmx.Error, match="too small"):          # an explicit capacity that is too small is an error ..
-            bp.query_batch(pats, mode, capacity=5)
+        if int(rh[-1]) > 5:
+            with pytest.raises(fmx.Error, match="too small"):      # an explicit capacity that is too small is an error ..
+                bp.query_batch(pats, mode, capacity=5)
         r = bp.query_batch(pats[:200], mode, capacity=None)        # .. the default one is retried with the exact size
         assert r["total"] == int(rh[200])
         del bp

@@ -1,12 +1,12 @@
-"""Rebuild profiles/ncu_traffic.json from the `ncu --set full` captures of tools/prof_step.py
-(run where ncu is installed; no GPU needed).
+"""Rebuild profiles/ncu_traffic.json from ncu captures of tools/prof_step.py (run where ncu is installed; no GPU needed).
 
-usage: python tools/ncu_traffic.py workload=gpurun_out/prof_X.ncu-rep:gpurun_out/prof_X.log ...
+usage: python tools/ncu_traffic.py gpurun_out/step_X.ncu-rep:gpurun_out/step_X.log ...
 
-Per workload it records, for the k_search and k_locate launches of ONE step: measured DRAM bytes
-(dram__bytes_read.sum + dram__bytes_write.sum), L2 read requests from the SMs
-(lts__t_requests_srcunit_tex_op_read.sum) and the duration under ncu, together with the batch size
-of the capture so that bench.py can scale them to its own batch."""
+Every capture holds exactly the launches of ONE step at the bench's batch size.  Per capture it stores, under the key
+"<workload>:<index mode>": the per-step SUMS of DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) and of L2 read
+requests from the SMs (lts__t_requests_srcunit_tex_op_read.sum), the per-kernel breakdown (time under ncu, bytes, requests,
+warp instructions, active lanes per instruction), the batch size and the SOURCE HASH of the kernels that were measured.
+bench.py uses an entry only when hash, workload, batch size and mode all match its own run; nothing is ever scaled."""
 import csv
 import json
 import os
@@ -14,11 +14,10 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-WANT = {"dram__bytes_read.sum": "dram_read_bytes", "dram__bytes_write.sum": "dram_write_bytes",
-        "lts__t_requests_srcunit_tex_op_read.sum": "l2_read_requests",
-        "lts__t_sectors_srcunit_tex_op_read.sum": "l2_read_sectors",
-        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum": "l1_load_sectors",
-        "smsp__inst_executed.sum": "warp_instructions", "gpu__time_duration.sum": "ns_under_ncu"}
+COLS = {"dram__bytes_read.sum": "dram_read_bytes", "dram__bytes_write.sum": "dram_write_bytes",
+        "lts__t_requests_srcunit_tex_op_read.sum": "l2_read_requests", "lts__t_sectors_srcunit_tex_op_read.sum": "l2_read_sectors",
+        "smsp__inst_executed.sum": "warp_instructions", "smsp__thread_inst_executed.sum": "thread_instructions",
+        "gpu__time_duration.sum": "ns_under_ncu"}
 
 
 def main():
@@ -27,37 +26,40 @@ def main():
         out = json.load(open(path))
     except Exception:
         out = {}
+    out = {k: v for k, v in out.items() if ":" in k}   # round-1 entries (scaled constants) are gone
     for arg in sys.argv[1:]:
-        name, rest = arg.split("=")
-        rep, log = rest.split(":")
+        rep, log = arg.split(":")
         meta = {}
         for line in open(log):
             if line.startswith("{"):
                 meta = json.loads(line)
-        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--print-units", "base"], capture_output=True,
-                             text=True).stdout
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--print-units", "base"], capture_output=True, text=True).stdout
         rows = list(csv.reader(txt.splitlines()))
         h = rows[0]
         ki = h.index("Kernel Name")
-        entry = {"npat": meta.get("npat"), "hits": meta.get("hits"), "source": f"{os.path.basename(rep)} (ncu --set full, one step of tools/prof_step.py)",
-                 "capture": meta}
+        kernels, tot = [], {v: 0.0 for v in COLS.values()}
         for r in rows[2:]:
-            kname = "k_search" if "k_search" in r[ki] else ("k_locate" if "k_locate" in r[ki] else None)
-            if not kname:
-                continue
-            d = {}
-            for col, key in WANT.items():
+            d = {"kernel": r[ki].split("(")[0].replace("void ", "").replace("fmx::", "")}
+            for col, key in COLS.items():
                 if col in h:
                     d[key] = float(r[h.index(col)].replace(",", ""))
-            d["dram_bytes"] = d.get("dram_read_bytes", 0) + d.get("dram_write_bytes", 0)
-            entry[kname] = d
-        # keys bench.py has always read
-        if "k_search" in entry:
-            entry["k_search_dram_bytes"] = entry["k_search"]["dram_bytes"]
-            entry["k_search_ms_under_ncu"] = entry["k_search"]["ns_under_ncu"] / 1e6
-        out[name] = entry
+                    tot[key] += d[key]
+            if d.get("warp_instructions"):
+                d["active_lanes_per_instruction"] = round(d.get("thread_instructions", 0) / d["warp_instructions"], 2)
+            kernels.append(d)
+        entry = {"workload": meta.get("workload"), "mode": meta.get("mode"), "npat": meta.get("npat"), "hits": meta.get("hits"),
+                 "source_hash": meta.get("source_hash"), "options": meta.get("options"),
+                 "step_ms_unprofiled": meta.get("step_ms"),
+                 "dram_bytes_per_step": tot["dram_read_bytes"] + tot["dram_write_bytes"],
+                 "l2_read_requests_per_step": tot["l2_read_requests"], "warp_instructions_per_step": tot["warp_instructions"],
+                 "active_lanes_per_instruction": round(tot["thread_instructions"] / max(1.0, tot["warp_instructions"]), 2),
+                 "kernels": kernels,
+                 "source": f"{os.path.basename(rep)}: ncu --clock-control none --profile-from-start off, one step of tools/prof_step.py"}
+        out[f"{meta.get('workload')}:{meta.get('mode')}"] = entry
     json.dump(out, open(path, "w"), indent=1)
-    print(json.dumps({k: {kk: vv for kk, vv in v.items() if kk in ("npat", "k_search_dram_bytes", "k_search_ms_under_ncu")} for k, v in out.items()}, indent=1))
+    for k, v in out.items():
+        print(k, v["npat"], v["source_hash"], f"{v['dram_bytes_per_step'] / 1e9:.2f} GB", f"{v['l2_read_requests_per_step'] / 1e6:.1f} M requests",
+              v["active_lanes_per_instruction"], "lanes")
 
 
 if __name__ == "__main__":

@@ -1,12 +1,13 @@
-"""One search+locate step of a bench workload between cudaProfilerStart/Stop, for ncu:
+"""One timed-step of a bench workload (fmx_query_batch_device: hit offsets + positions) between cudaProfilerStart/Stop, for ncu:
 
-    ncu --set full --clock-control none --import-source on --profile-from-start off \
-        -k regex:'k_search|k_locate' -o gpurun_out/prof_X python tools/prof_step.py --workload X [--npat N]
+    ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,lts__t_requests_srcunit_tex_op_read.sum,lts__t_sectors_srcunit_tex_op_read.sum,smsp__inst_executed.sum,smsp__thread_inst_executed.sum,gpu__time_duration.sum \
+        --clock-control none --profile-from-start off -o gpurun_out/step_X -f python tools/prof_step.py --workload X [--mode compact]
+    (or --set full --import-source on for a source-level look at one kernel)
 
-Index build, k-mer table build and warm-up run OUTSIDE the profiled range, so the report holds exactly
-the launches of one step.  Prints the step's own (un-profiled) timings first for reference."""
+Index build, k-mer table build and warm-up run OUTSIDE the profiled range, so the report holds exactly the launches of
+ONE step at the bench's own batch size.  Prints the step's own (un-profiled) timing, the source hash of the kernels and
+the batch, which tools/ncu_traffic.py stores next to the counters so that bench.py can refuse a stale capture."""
 import argparse
-import ctypes as C
 import json
 import os
 import sys
@@ -18,8 +19,9 @@ import bench
 import fmx_pkg
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--workload", default="cfg2_dna100m")
+ap.add_argument("--workload", default="target_dna1g")
 ap.add_argument("--npat", type=int, default=0)
+ap.add_argument("--mode", default="auto", choices=["auto", "rich", "compact"])
 ap.add_argument("--option", action="append", default=[], help="key=value index option (fmx_index_set_option)")
 args = ap.parse_args()
 fmx = fmx_pkg.load()
@@ -38,60 +40,32 @@ text = d_text.cpu().numpy()
 del d_text
 torch.cuda.empty_cache()
 cls = [fmx.FMIndexWithLocate, fmx.RLFMIndexWithLocate, fmx.FMIndexMultiPiecesWithLocate][kind]
-index = cls.new(fmx.Text.with_max_character(text, mc), level, device=0)
+mode_id = {"auto": fmx.MODE_AUTO, "rich": fmx.MODE_RICH, "compact": fmx.MODE_COMPACT}[args.mode]
+index = cls.new(fmx.Text.with_max_character(text, mc), level, device=0, mode=mode_id)
 for kv in args.option:
     k, v = kv.split("=")
     index.set_option(k, int(v))
-h = index._h
 stream = torch.cuda.Stream()
 torch.cuda.set_stream(stream)
-sp = C.c_void_p(stream.cuda_stream)
-d_s = torch.empty(npat, dtype=torch.int64, device="cuda")
-d_e = torch.empty(npat, dtype=torch.int64, device="cuda")
-d_hoff = torch.empty(npat + 1, dtype=torch.int64, device="cuda")
 flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
-p_off = d_off.data_ptr() if d_off is not None else None
-total = C.c_uint64(0)
-
-
-def chk(rc):
-    if rc != 0:
-        raise RuntimeError(L.fmx_last_error().decode())
-
-
-def search():
-    chk(L.fmx_search_batch_device(h, 0, d_pat.data_ptr(), p_off, m, npat, None, None, d_s.data_ptr(), d_e.data_ptr(), sp))
-
-
-search()
-chk(L.fmx_locate_count_device(h, 0, d_s.data_ptr(), d_e.data_ptr(), npat, d_hoff.data_ptr(), C.byref(total), sp))
-cap = int(total.value) + 1024
-d_pos = torch.empty(cap, dtype=torch.int64, device="cuda")
-
-
-def locate():
-    chk(L.fmx_locate_batch_device(h, 0, d_s.data_ptr(), d_e.data_ptr(), npat, d_hoff.data_ptr(), d_pos.data_ptr(),
-                                  None, cap, sp))
-
-
-ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+run = bench.DeviceRun(fmx, L, index, d_pat, d_off, m, npat, stream)
+run.size_outputs()
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+ms = []
 for _ in range(3):
     flush.zero_()
     ev[0].record(stream)
-    search()
+    run.query()
     ev[1].record(stream)
-    locate()
-    ev[2].record(stream)
-torch.cuda.synchronize()
-work = index.last_work(sp)
-print(json.dumps({"workload": args.workload, "npat": npat, "hits": int(total.value), "search_ms": ev[0].elapsed_time(ev[1]),
-                  "locate_ms": ev[1].elapsed_time(ev[2]), "search_steps": int(work[0]), "lf_steps": int(work[1]),
-                  "index_bytes": index.heap_size(), "sectors_per_rank": index.sectors_per_rank(),
-                  "kmer_k": [int(L.fmx_index_kmer_k(h, 0)), int(L.fmx_index_kmer_k(h, 1))]}), flush=True)
+    torch.cuda.synchronize()
+    ms.append(ev[0].elapsed_time(ev[1]))
+print(json.dumps({"workload": args.workload, "npat": npat, "hits": run.hits, "step_ms": min(ms),
+                  "mode": {fmx.MODE_RICH: "rich", fmx.MODE_COMPACT: "compact"}[index.mode()], "source_hash": bench.source_hash(),
+                  "index_bytes": index.heap_size(), "kmer_k": [index.kmer_k(False), index.kmer_k(True)],
+                  "options": args.option}), flush=True)
 flush.zero_()
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
-search()
-locate()
+run.query()
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()

@@ -70,6 +70,22 @@ def _as_u8(x) -> np.ndarray:
     return np.ascontiguousarray(np.asarray(list(x), dtype=np.uint8))
 
 
+WIDE_DTYPES = (np.dtype(np.uint16), np.dtype(np.uint32), np.dtype(np.uint64))   # character.rs:38-42 (usize = u64)
+
+
+def _char_dtype(x):
+    """character type of a text: the numpy dtype of a u16 / u32 / u64 array, u8 for everything else"""
+    dt = getattr(x, "dtype", None)
+    return np.dtype(dt) if dt is not None and np.dtype(dt) in WIDE_DTYPES else np.dtype(np.uint8)
+
+
+def _as_chars(x, dtype) -> np.ndarray:
+    dtype = np.dtype(dtype)
+    if dtype == np.uint8:
+        return _as_u8(x)
+    return np.ascontiguousarray(np.asarray(x, dtype=dtype))
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data
 
@@ -82,16 +98,21 @@ class PieceId(int):
 
 
 class Text:
-    """src/text.rs:10-64 (u8 characters)."""
+    """src/text.rs:10-64.  Characters are u8 unless `text` is a numpy array of u16 / u32 / u64 (character.rs:38-42)."""
 
-    def __init__(self, text, max_character=255):
-        self._text = _as_u8(text)
-        self._max_character = int(max_character)
+    def __init__(self, text, max_character=None):
+        self._dtype = _char_dtype(text)
+        self._text = _as_chars(text, self._dtype)
+        self._max_character = int(np.iinfo(self._dtype).max if max_character is None else max_character)
 
     @classmethod
     def new(cls, text):
-        """Text::new: max_character = C::max_value() (text.rs:28-33)"""
-        return cls(text, 255)
+        """Text::new: max_character = C::max_value() (text.rs:28-33).  For u32 / u64 texts that is beyond what any
+        index can hold (the reference would allocate max_character + 1 counters): use with_max_character there."""
+        return cls(text, None)
+
+    def dtype(self):
+        return self._dtype
 
     @classmethod
     def with_max_character(cls, text, max_character):
@@ -109,24 +130,24 @@ class Text:
         return int(self._max_character).bit_length()
 
 
-def _pack(patterns):
-    """-> (flat u8, offsets u64 or None, fixed_len, npat)"""
+def _pack(patterns, dtype=np.uint8):
+    """-> (flat characters of `dtype`, offsets u64 (in characters) or None, fixed_len, npat)"""
     if isinstance(patterns, np.ndarray) and patterns.ndim == 2:
-        p = np.ascontiguousarray(patterns, dtype=np.uint8)
+        p = np.ascontiguousarray(patterns, dtype=dtype)
         return p.reshape(-1), None, p.shape[1], p.shape[0]
     if isinstance(patterns, tuple) and len(patterns) == 2:
-        flat = np.ascontiguousarray(patterns[0], dtype=np.uint8)
+        flat = np.ascontiguousarray(patterns[0], dtype=dtype)
         off = np.ascontiguousarray(patterns[1], dtype=np.uint64)
         return flat, off, 0, off.size - 1
-    arrs = [_as_u8(p) for p in patterns]
+    arrs = [_as_chars(p, dtype) for p in patterns]
     off = np.zeros(len(arrs) + 1, dtype=np.uint64)
     if arrs:
         off[1:] = np.cumsum([a.size for a in arrs], dtype=np.uint64)
-    flat = np.concatenate(arrs) if arrs and int(off[-1]) > 0 else np.zeros(0, dtype=np.uint8)
+    flat = np.concatenate(arrs) if arrs and int(off[-1]) > 0 else np.zeros(0, dtype=dtype)
     return np.ascontiguousarray(flat), off, 0, len(arrs)
 
 
-def _run_query(call, patterns, mode, rows, counts, locate, piece_ids, width, packed_bits, fixed_len, capacity):
+def _run_query(call, patterns, mode, rows, counts, locate, piece_ids, width, packed_bits, fixed_len, capacity, dtype=np.uint8):
     """fills a struct fmx_query, runs call(byref(query), byref(total)) -> rc, returns the requested arrays"""
     dt = np.uint64 if width == 8 else np.uint32
     if packed_bits:
@@ -134,7 +155,7 @@ def _run_query(call, patterns, mode, rows, counts, locate, piece_ids, width, pac
         wpp = (int(fixed_len) * packed_bits + 63) // 64
         npat, flat, off, fixed = words.size // wpp, words, None, int(fixed_len)
     else:
-        flat, off, fixed, npat = _pack(patterns)
+        flat, off, fixed, npat = _pack(patterns, dtype)
     q = _lib.Query()
     q.mode, q.packed_bits, q.patterns, q.pat_off, q.fixed_len, q.npat = mode, packed_bits, _ptr(flat), _ptr(off), fixed, npat
     q.out_width = width
@@ -161,7 +182,7 @@ def _run_query(call, patterns, mode, rows, counts, locate, piece_ids, width, pac
     rc = call(C.byref(q), C.byref(total))
     t = int(total.value)
     if rc == -9 and capacity is None and t < (1 << 32 if width == 4 else 1 << 62):  # retry with exact-size buffers
-        return _run_query(call, patterns, mode, rows, counts, locate, piece_ids, width, packed_bits, fixed_len, t)
+        return _run_query(call, patterns, mode, rows, counts, locate, piece_ids, width, packed_bits, fixed_len, t, dtype)
     _check(rc)
     for k in ("positions", "piece_ids"):
         if k in out:
@@ -181,6 +202,7 @@ class _Index:
         self._L = L
         if _handle is not None:
             self._h = _handle
+            self._dtype = np.dtype({1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[int(L.fmx_index_char_width(_handle))])
             return
         if not isinstance(text, Text):
             text = Text.new(text)
@@ -190,8 +212,10 @@ class _Index:
                 raise TypeError("a sampling level is required (FMIndexWithLocate::new(&text, level))")
             lvl = int(level)
         t = text.text()
+        self._dtype = text.dtype()   # width of the text's characters = width of patterns and extracted characters
         h = C.c_void_p()
-        _check(L.fmx_index_build_ex(_ptr(t), t.size, 1, text.max_character(), self._kind, lvl, device, int(mode), C.byref(h)))
+        _check(L.fmx_index_build_ex(_ptr(t), t.size, self._dtype.itemsize, text.max_character(), self._kind, lvl, device, int(mode),
+                                    C.byref(h)))
         self._h = h
 
     @classmethod
@@ -235,7 +259,7 @@ class _Index:
     # ---- batched entries
     def search_batch(self, patterns, mode=SEARCH, init=None):
         """Batched SearchIndex::search over many patterns (one kernel launch)."""
-        flat, off, fixed, npat = _pack(patterns)
+        flat, off, fixed, npat = _pack(patterns, self._dtype)
         s = np.zeros(npat, dtype=np.uint64)
         e = np.zeros(npat, dtype=np.uint64)
         ins = ine = None
@@ -250,7 +274,7 @@ class _Index:
         """Fused, pipelined batched search + locate (fmx_search_locate_batch): the batched form of
         `index.search(p).iter_matches().map(|m| m.locate())`.
         -> (SearchBatch, hit_off[npat+1], positions[, piece_ids])"""
-        flat, off, fixed, npat = _pack(patterns)
+        flat, off, fixed, npat = _pack(patterns, self._dtype)
         s = np.zeros(npat, dtype=np.uint64)
         e = np.zeros(npat, dtype=np.uint64)
         hit_off = np.zeros(npat + 1, dtype=np.uint64)
@@ -274,7 +298,7 @@ class _Index:
         `patterns`: as for search_batch, or (packed_bits != 0) a uint64 array of packed words with `fixed_len`
         characters per pattern (see pack_patterns).  -> dict with the requested arrays + "total"."""
         return _run_query(lambda q, t: self._L.fmx_query_batch(self._h, q, t), patterns, mode, rows, counts, locate, piece_ids,
-                          width, packed_bits, fixed_len, capacity)
+                          width, packed_bits, fixed_len, capacity, self._dtype)
 
     def mode(self):
         """MODE_COMPACT or MODE_RICH: what the index holds (fmx_index_mode_of)"""
@@ -315,7 +339,7 @@ class _Index:
 
     def extract_batch(self, rows, k, forward):
         rows = np.ascontiguousarray(rows, dtype=np.uint64)
-        out = np.zeros((rows.size, k), dtype=np.uint8)
+        out = np.zeros((rows.size, k), dtype=self._dtype)
         out_len = np.zeros(rows.size, dtype=np.uint32)
         _check(self._L.fmx_extract_batch(self._h, _ptr(rows), rows.size, k, int(forward), _ptr(out), _ptr(out_len)))
         return out, out_len
@@ -327,7 +351,7 @@ class _Index:
         return out
 
     def lf_map2_batch(self, c, i):
-        c = np.ascontiguousarray(c, dtype=np.uint8)
+        c = np.ascontiguousarray(c, dtype=self._dtype)
         i = np.ascontiguousarray(i, dtype=np.uint64)
         out = np.zeros(i.size, dtype=np.uint64)
         _check(self._L.fmx_lf_map2_batch(self._h, _ptr(c), _ptr(i), i.size, _ptr(out)))
@@ -341,7 +365,8 @@ class _Index:
         """which device layout the builder chose (fmx_layout.h)"""
         return ["binary wavelet matrix (L sectors per rank)", "Q4: one quaternary level (1 sector per rank)",
                 "WM4: quaternary wavelet matrix (ceil(L/2) sectors per rank)",
-                "SYM: one bit vector per symbol (1 sector per rank)"][int(self._L.fmx_index_layout(self._h))]
+                "SYM: one bit vector per symbol (1 sector per rank)",
+                "WIDE: binary wavelet matrix of up to 32 levels, character tables in global memory"][int(self._L.fmx_index_layout(self._h))]
 
     def kmer_k(self, big=False):
         """characters memoised by the small / large k-mer table (0 = none)"""
@@ -414,7 +439,7 @@ class Search:
         self._cache = None
 
     def _refine(self, pattern):
-        p = _as_u8(pattern)
+        p = _as_chars(pattern, self._index._dtype)
         init = None if self._s is None else (np.array([self._s], dtype=np.uint64), np.array([self._e], dtype=np.uint64))
         b = self._index.search_batch([p], self._mode, init)
         return Search(self._index, self._mode, int(b.s[0]), int(b.e[0]))
@@ -588,9 +613,9 @@ class IndexGroup:
 
 def suffix_array(text) -> np.ndarray:
     """sais::build_suffix_array (sais.rs:115-144) through the C ABI (host side)."""
-    t = _as_u8(text)
+    t = _as_chars(text, _char_dtype(text))
     sa = np.zeros(max(t.size, 1), dtype=np.uint64)
-    _check(load_library().fmx_build_suffix_array(_ptr(t), t.size, 1, _ptr(sa)))
+    _check(load_library().fmx_build_suffix_array(_ptr(t), t.size, t.dtype.itemsize, _ptr(sa)))
     return sa[: t.size]
 
 
@@ -622,7 +647,7 @@ def blob_build(text: Text, kind, level=None, mode=MODE_AUTO) -> np.ndarray:
     L = load_library()
     t = text.text()
     p, nb = C.c_void_p(), C.c_uint64(0)
-    _check(L.fmx_blob_build_ex(_ptr(t), t.size, 1, text.max_character(), kind, -1 if level is None else level, int(mode),
+    _check(L.fmx_blob_build_ex(_ptr(t), t.size, t.dtype.itemsize, text.max_character(), kind, -1 if level is None else level, int(mode),
                                C.byref(p), C.byref(nb)))
     a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(nb.value,)).copy()
     L.fmx_free(p)

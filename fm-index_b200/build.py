@@ -34,18 +34,40 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile fm-index_b200/csrc into fm-index_b200/libfmx_b200.so with nvcc for sm_100a."""
+    """Compile fm-index_b200/csrc into fm-index_b200/libfmx_b200.so with nvcc for sm_100a: one object per source,
+    compiled side by side (objects under csrc/_obj, git-ignored), then one link."""
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES + ["-lgomp"]
     env = dict(os.environ)
     env.pop("CC", None)   # a broken gcc wrapper in CC/CXX must not leak into nvcc's host compile
     env.pop("CXX", None)
-    res = subprocess.run(cmd, cwd=CSRC, env=env, capture_output=True, text=True)
+    objdir = os.path.join(CSRC, "_obj")
+    os.makedirs(objdir, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+    newest_header = max(os.path.getmtime(os.path.join(CSRC, d)) for d in DEPS if d not in SOURCES)
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        stale = force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(os.path.join(CSRC, src)), newest_header)
+        if stale:
+            procs.append((src, subprocess.Popen([_nvcc()] + flags + ["-c", "-o", obj, src], cwd=CSRC, env=env,
+                                                stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = ""
+    for src, pr in procs:
+        out = pr.communicate()[0]
+        log += out
+        if pr.returncode != 0:
+            for _, other in procs:
+                if other.poll() is None:
+                    other.kill()
+            raise RuntimeError(f"nvcc failed on {src}:\n" + out)
+    objs = [os.path.join(objdir, os.path.splitext(src)[0] + ".o") for src in SOURCES]
+    res = subprocess.run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lgomp"],
+                         cwd=CSRC, env=env, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     if verbose:
-        print(res.stderr)
+        print(log + res.stderr)
     return LIB
 
 

@@ -49,6 +49,22 @@ static void suffix_array_u32(const uint8_t *text, uint64_t n, std::vector<uint32
     }
 }
 
+// Suffix array of a sequence of symbol ranks 0 .. nsym-1 (wide-character texts), n < 2^32 - 1.  The sequence need not
+// end in a unique minimum: a virtual sentinel is appended, as for byte texts with interior zeros.
+static void suffix_array_ranks(const uint32_t *rk, uint64_t n, uint64_t nsym, uint32_t *sa) {
+    if (n + 1 < (1ull << 31) - 2) {
+        std::vector<int32_t> tmp(n + 1);
+        SentinelAcc32 a{rk, (int64_t)n + 1};
+        sais_core<SentinelAcc32, int32_t>(a, tmp.data(), (int32_t)(n + 1), (int32_t)(nsym + 1));
+        for (uint64_t i = 0; i < n; i++) sa[i] = (uint32_t)tmp[i + 1];
+    } else {
+        std::vector<int64_t> tmp(n + 1);
+        SentinelAcc32 a{rk, (int64_t)n + 1};
+        sais_core<SentinelAcc32, int64_t>(a, tmp.data(), (int64_t)(n + 1), (int64_t)(nsym + 1));
+        for (uint64_t i = 0; i < n; i++) sa[i] = (uint32_t)tmp[i + 1];
+    }
+}
+
 int build_suffix_array(const uint8_t *text, uint64_t n, uint64_t *sa_out, std::string &err) {
     int rc = validate_text(text, n, err);
     if (rc) return rc;
@@ -136,12 +152,14 @@ struct WMat {
 };
 
 // vers WaveletMatrix::from_slice semantics: level 0 = MSB, stable zero/one partition per level
-static void build_wavelet(const uint8_t *seq, uint64_t n, uint32_t L, WMat &m) {
+template <class T>
+static void build_wavelet(const T *seq, uint64_t n, uint32_t L, WMat &m) {
     m.L = L;
     m.n = n;
     m.lv.clear();
+    m.lv.reserve(L);
     m.zeros.assign(L, 0);
-    std::vector<uint8_t> cur(seq, seq + n), nxt(n);
+    std::vector<T> cur(seq, seq + n), nxt(n);
     // chunks of whole rank blocks so that threads never share a payload word
     const uint64_t chunk = (uint64_t)FMX_RB_BITS * 4096;
     const int64_t nchunks = (int64_t)((n + chunk - 1) / chunk);
@@ -502,6 +520,7 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
     hdr.levels = L;
     hdr.max_character = (uint32_t)mc;
     hdr.cs_len = cs_len;
+    hdr.char_width = 1;
 
     WMat wm;
     Q4Vec q4;
@@ -729,6 +748,281 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
     return 0;
 }
 
+
+// ------------------------------------------------------------------ texts of wide characters (character.rs:38-42)
+// max_character > 255: the WIDE layout (fmx_layout.h).  Same producers as build_blob -- suffix array (sais.rs:115-144),
+// cs (sais.rs:9-32), BWT (fm_index.rs:44-58), runs (rlfmi.rs:37-96), doc (multi_pieces.rs:53-97), samples
+// (sample.rs:21-44) -- over u32 symbols.  No k-mer tables and no verify structures: those are sized for small alphabets.
+int build_blob_wide(const void *text_in, uint32_t cw, uint64_t n, uint64_t mc, int kind, int level, HostBlob &blob,
+                    std::string &err, int mode) {
+    if (int mrc = resolve_mode(mode, err)) return mrc;
+    if (cw != 2 && cw != 4 && cw != 8) {
+        err = "character width must be 1, 2, 4 or 8 bytes";
+        return FMX_ERR_INVALID_ARG;
+    }
+    if (mc <= 255 || mc >= 0xFFFFFFFFull || (cw == 2 && mc > 0xFFFF)) {
+        err = "max_character out of range for this character width (wide texts: 256 ..= 2^32 - 2)";
+        return FMX_ERR_INVALID_ARG;
+    }
+    if (kind != FMX_KIND_FM && kind != FMX_KIND_RLFM && kind != FMX_KIND_MULTI) {
+        err = "unknown index kind";
+        return FMX_ERR_INVALID_ARG;
+    }
+    if (n >= (1ull << 32) - 1) {
+        err = "text length must be below 2^32 - 1 (u32 rank counts in the device layout)";
+        return FMX_ERR_UNSUPPORTED;
+    }
+    std::vector<uint32_t> t(n);
+    {
+        int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+        for (int64_t i = 0; i < (int64_t)n; i++) {
+            uint64_t v = cw == 2 ? static_cast<const uint16_t *>(text_in)[i]
+                                 : (cw == 4 ? static_cast<const uint32_t *>(text_in)[i] : static_cast<const uint64_t *>(text_in)[i]);
+            bad |= v > mc;
+            t[(size_t)i] = (uint32_t)v;
+        }
+        if (bad) {  // sais.rs:16-18 would index occs out of bounds (panic)
+            err = "text contains a character larger than max_character";
+            return FMX_ERR_INVALID_ARG;
+        }
+    }
+    if (n > 1) {  // sais.rs:121-139
+        if (t[0] == 0) {
+            err = "the given text must not start with zero character";
+            return FMX_ERR_INVALID_TEXT;
+        }
+        if (!(t[n - 1] == 0 && t[n - 2] != 0)) {
+            err = "the given text must end with exactly one zero character";
+            return FMX_ERR_INVALID_TEXT;
+        }
+    }
+    const uint32_t L = log2_u64(mc) + 1;  // text.rs:61-63
+    const uint64_t cs_len = mc + 1;
+
+    // the symbols that occur, ascending; suffix sorting runs over their ranks (order preserving, so the same array)
+    std::vector<uint32_t> present(t);
+    std::sort(present.begin(), present.end());
+    present.erase(std::unique(present.begin(), present.end()), present.end());
+    std::vector<uint32_t> sa(n);
+    if (n == 1) sa[0] = 0;
+    if (n > 1) {
+        std::vector<uint32_t> rk(n);
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < (int64_t)n; i++)
+            rk[(size_t)i] = (uint32_t)(std::lower_bound(present.begin(), present.end(), t[(size_t)i]) - present.begin());
+        suffix_array_ranks(rk.data(), n, (uint64_t)present.size(), sa.data());
+    }
+    std::vector<uint32_t> bwt(n);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; i++) bwt[(size_t)i] = sa[(size_t)i] ? t[sa[(size_t)i] - 1] : (kind == FMX_KIND_RLFM && n ? t[n - 1] : 0u);
+
+    FmxBlobHeader hdr;
+    std::memset(&hdr, 0, sizeof(hdr));
+    hdr.magic = FMX_BLOB_MAGIC;
+    hdr.version = FMX_BLOB_VERSION;
+    hdr.kind = (uint32_t)kind;
+    hdr.n = n;
+    hdr.levels = L;
+    hdr.max_character = (uint32_t)mc;
+    hdr.cs_len = (uint32_t)cs_len;
+    hdr.layout = FMX_LAYOUT_WIDE;
+    hdr.char_width = cw;
+    hdr.reserved[0] = (uint64_t)FMX_MODE_COMPACT;
+
+    std::vector<uint32_t> cs, adj;
+    try {
+        cs.assign(cs_len + 1, 0);
+        adj.assign(cs_len, 0);
+    } catch (const std::bad_alloc &) {
+        err = "out of host memory for the character tables (max_character + 1 words each)";
+        return FMX_ERR_OOM;
+    }
+    WMat wm;
+    std::vector<uint32_t> heads, doc, piece_end, bsel, bpsel;
+    RBVec rb_b(0), rb_bp(0);
+    auto fill_cs = [&](const std::vector<uint32_t> &seq) {  // cs[c] = #symbols of seq below c (sais.rs:21-32)
+        for (uint32_t v : seq) cs[(size_t)v + 1]++;          // counts, shifted by one ...
+        uint64_t sum = 0;
+        for (uint64_t c = 0; c <= cs_len; c++) {             // ... then the running sum in place
+            sum += cs[c];
+            cs[c] = (uint32_t)sum;
+        }
+    };
+    if (kind == FMX_KIND_FM || kind == FMX_KIND_MULTI) {
+        fill_cs(t);
+        build_wavelet(bwt.data(), n, L, wm);
+        hdr.seq_len = n;
+        if (kind == FMX_KIND_MULTI) {  // multi_pieces.rs:53-79
+            for (uint64_t i = 0; i < n; i++)
+                if (t[i] == 0) piece_end.push_back((uint32_t)i);
+            const uint64_t zc = piece_end.size();
+            doc.assign(zc, 0);
+            uint64_t k = 0;
+            for (uint64_t p = 0; p < n; p++) {
+                if (bwt[p] != 0) continue;  // p = select(bw, k, 0)
+                if (k >= zc) {
+                    err = "text without a \\0 terminator cannot be indexed as multi-pieces";
+                    return FMX_ERR_INVALID_TEXT;
+                }
+                const uint64_t em = sa[p] ? sa[p] - 1 : n - 1;  // modular_sub(sa[p], 1, n)
+                const uint64_t pid = (uint64_t)(std::lower_bound(piece_end.begin(), piece_end.end(), (uint32_t)em) - piece_end.begin());
+                if (pid == zc - 1) hdr.first_row = p;
+                doc[k++] = (uint32_t)pid;
+            }
+            hdr.ndoc = zc;
+        }
+    } else {  // rlfmi.rs:37-96
+        std::vector<uint32_t> starts;
+        rb_b = RBVec(n);
+        rb_bp = RBVec(n);
+        uint32_t c0 = 0;
+        for (uint64_t i = 0; i < n; i++) {
+            const uint32_t c = bwt[i];
+            if (c0 != c) {
+                heads.push_back(c);
+                starts.push_back((uint32_t)i);
+                rb_b.set(i);
+            } else if (heads.empty()) {
+                err = "text not representable by RLFMIndex (the reference hits unreachable!() at rlfmi.rs:62)";
+                return FMX_ERR_INVALID_TEXT;
+            }
+            c0 = c;
+        }
+        rb_b.finish();
+        const uint64_t r = heads.size();
+        hdr.runs = r;
+        hdr.seq_len = r;
+        build_wavelet(heads.data(), r, L, wm);
+        bsel.assign(r + 1, (uint32_t)n);
+        for (uint64_t j = 0; j < r; j++) bsel[j] = starts[j];
+        fill_cs(heads);  // cs over run heads
+        // bp groups the runs by head character, stably: position of the group of c = total length of the runs of smaller heads
+        std::vector<uint64_t> len_of(present.size() + 1, 0), next_pos(present.size() + 1, 0), next_run(present.size() + 1, 0);
+        auto slot = [&](uint32_t c) { return (size_t)(std::lower_bound(present.begin(), present.end(), c) - present.begin()); };
+        for (uint64_t j = 0; j < r; j++) len_of[slot(heads[j])] += (uint64_t)bsel[j + 1] - bsel[j];
+        uint64_t pacc = 0;
+        for (size_t q = 0; q < present.size(); q++) {
+            next_pos[q] = pacc;
+            next_run[q] = cs[present[q]];
+            pacc += len_of[q];
+        }
+        bpsel.assign(r + 1, (uint32_t)n);
+        for (uint64_t j = 0; j < r; j++) {
+            const size_t q = slot(heads[j]);
+            rb_bp.set(next_pos[q]);
+            bpsel[next_run[q]++] = (uint32_t)next_pos[q];
+            next_pos[q] += (uint64_t)bsel[j + 1] - bsel[j];
+        }
+        rb_bp.finish();
+    }
+    // adj[c] = cs[c] - walk_c(0), for the symbols that occur (the kernels never read the others)
+#pragma omp parallel for schedule(static)
+    for (int64_t q = 0; q < (int64_t)present.size(); q++) {
+        const uint32_t c = present[(size_t)q];
+        adj[c] = cs[c] - (uint32_t)wm.walk(0, c);
+    }
+    std::vector<uint32_t> wzeros(L);
+    for (uint32_t l = 0; l < L; l++) wzeros[l] = (uint32_t)wm.zeros[l];
+
+    std::vector<uint32_t> samples;  // sample.rs:21-44
+    if (level >= 0) {
+        hdr.has_locate = 1;
+        uint32_t lvl = (uint32_t)level;
+        if (n > 0) {
+            hdr.sa_word_size = log2_u64(n) + 1;
+            if (lvl >= 63 || n <= (1ull << lvl)) lvl = 0;  // sample.rs:28-31
+            hdr.sa_level = lvl;
+            hdr.sa_count = ((n - 1) >> lvl) + 1;
+            samples.resize(hdr.sa_count);
+            for (uint64_t i = 0; i < hdr.sa_count; i++) samples[i] = sa[i << lvl];
+        }
+    }
+    hdr.vsa_level = hdr.sa_level;
+
+    const uint64_t level_bytes = (hdr.seq_len / FMX_RB_BITS + 1) * 32;
+    uint64_t sec_bytes[SEC_COUNT];
+    std::memset(sec_bytes, 0, sizeof(sec_bytes));
+    sec_bytes[SEC_LEVEL0] = level_bytes * L;
+    sec_bytes[SEC_WZEROS] = (uint64_t)L * 4;
+    sec_bytes[SEC_ADJ] = adj.size() * 4;
+    sec_bytes[SEC_CS] = cs.size() * 4;
+    sec_bytes[SEC_SA] = samples.size() * 4;
+    sec_bytes[SEC_DOC] = doc.size() * 4;
+    sec_bytes[SEC_PIECE_END] = piece_end.size() * 4;
+    if (kind == FMX_KIND_RLFM) {
+        sec_bytes[SEC_RL_B] = rb_b.bytes();
+        sec_bytes[SEC_RL_BP] = rb_bp.bytes();
+        sec_bytes[SEC_RL_BSEL] = bsel.size() * 4;
+        sec_bytes[SEC_RL_BPSEL] = bpsel.size() * 4;
+    }
+    layout_sections(hdr, sec_bytes);
+    if (blob.alloc(hdr.total_bytes, true)) {
+        err = "out of host memory for the index blob";
+        return FMX_ERR_OOM;
+    }
+    std::memcpy(blob.p, &hdr, sizeof(hdr));
+    auto put = [&](int k, const void *src, uint64_t bytes) {
+        if (bytes) std::memcpy(blob.p + hdr.sec[k].offset, src, bytes);
+    };
+    for (uint32_t l = 0; l < L; l++) std::memcpy(blob.p + hdr.sec[SEC_LEVEL0].offset + l * level_bytes, wm.lv[l].w.data(), level_bytes);
+    put(SEC_WZEROS, wzeros.data(), wzeros.size() * 4);
+    put(SEC_ADJ, adj.data(), adj.size() * 4);
+    put(SEC_CS, cs.data(), cs.size() * 4);
+    put(SEC_SA, samples.data(), samples.size() * 4);
+    put(SEC_DOC, doc.data(), doc.size() * 4);
+    put(SEC_PIECE_END, piece_end.data(), piece_end.size() * 4);
+    if (kind == FMX_KIND_RLFM) {
+        put(SEC_RL_B, rb_b.w.data(), rb_b.bytes());
+        put(SEC_RL_BP, rb_bp.w.data(), rb_bp.bytes());
+        put(SEC_RL_BSEL, bsel.data(), bsel.size() * 4);
+        put(SEC_RL_BPSEL, bpsel.data(), bpsel.size() * 4);
+    }
+    return 0;
+}
+
+// Suffix array of a wide-character text, for fmx_build_suffix_array (tests).  Characters below 2^32.
+int build_suffix_array_wide(const void *text_in, uint32_t cw, uint64_t n, uint64_t *sa_out, std::string &err) {
+    if (cw != 2 && cw != 4 && cw != 8) {
+        err = "character width must be 1, 2, 4 or 8 bytes";
+        return FMX_ERR_INVALID_ARG;
+    }
+    if (n >= (1ull << 32) - 1) {
+        err = "text length must be below 2^32 - 1";
+        return FMX_ERR_UNSUPPORTED;
+    }
+    std::vector<uint32_t> t(n);
+    for (uint64_t i = 0; i < n; i++) {
+        const uint64_t v = cw == 2 ? static_cast<const uint16_t *>(text_in)[i]
+                                   : (cw == 4 ? static_cast<const uint32_t *>(text_in)[i] : static_cast<const uint64_t *>(text_in)[i]);
+        if (v >= 0xFFFFFFFFull) {
+            err = "characters must be below 2^32 - 1";
+            return FMX_ERR_UNSUPPORTED;
+        }
+        t[i] = (uint32_t)v;
+    }
+    if (n > 1) {
+        if (t[0] == 0) {
+            err = "the given text must not start with zero character";
+            return FMX_ERR_INVALID_TEXT;
+        }
+        if (!(t[n - 1] == 0 && t[n - 2] != 0)) {
+            err = "the given text must end with exactly one zero character";
+            return FMX_ERR_INVALID_TEXT;
+        }
+    }
+    if (n == 1) sa_out[0] = 0;
+    if (n <= 1) return 0;
+    std::vector<uint32_t> present(t);
+    std::sort(present.begin(), present.end());
+    present.erase(std::unique(present.begin(), present.end()), present.end());
+    std::vector<uint32_t> rk(n), sa(n);
+    for (uint64_t i = 0; i < n; i++) rk[i] = (uint32_t)(std::lower_bound(present.begin(), present.end(), t[i]) - present.begin());
+    suffix_array_ranks(rk.data(), n, (uint64_t)present.size(), sa.data());
+    for (uint64_t i = 0; i < n; i++) sa_out[i] = sa[i];
+    return 0;
+}
+
 int check_blob(const void *blob, uint64_t bytes, FmxBlobHeader &hdr, std::string &err) {
     if (!blob || bytes < sizeof(FmxBlobHeader)) {
         err = "blob too small";
@@ -744,11 +1038,17 @@ int check_blob(const void *blob, uint64_t bytes, FmxBlobHeader &hdr, std::string
         return FMX_ERR_INVALID_ARG;
     };
     if (hdr.total_bytes != bytes) return bad("total size");
-    if (hdr.levels == 0 || hdr.levels > FMX_MAX_LEVELS || hdr.kind > 2 || hdr.layout > 3 || hdr.qlevels > FMX_MAX_QLEVELS ||
-        hdr.nexc > FMX_MAX_EXC)
+    const bool wide = hdr.layout == FMX_LAYOUT_WIDE;
+    if (hdr.levels == 0 || hdr.levels > (wide ? FMX_MAX_WIDE_LEVELS : FMX_MAX_LEVELS) || hdr.kind > 2 || hdr.layout > FMX_LAYOUT_WIDE ||
+        hdr.qlevels > FMX_MAX_QLEVELS || hdr.nexc > FMX_MAX_EXC)
         return bad("header");
-    // the kernels copy cs_len + 1 words into shared tables of 256 / 257 entries and index rows with u32
-    if (hdr.max_character == 0 || hdr.max_character > 255 || hdr.cs_len != hdr.max_character + 1) return bad("alphabet");
+    if (hdr.char_width != 0 && hdr.char_width != 1 && hdr.char_width != 2 && hdr.char_width != 4 && hdr.char_width != 8) return bad("character width");
+    // the kernels copy cs_len + 1 words into shared tables of 256 / 257 entries (WIDE: read them from global memory)
+    // and index rows with u32
+    if (hdr.max_character == 0 || hdr.max_character == 0xFFFFFFFFu || (hdr.max_character > 255) != wide ||
+        hdr.cs_len != hdr.max_character + 1)
+        return bad("alphabet");
+    if (wide && (hdr.char_width < 2 || hdr.verify || hdr.sec[SEC_VSA].bytes)) return bad("wide layout");
     if (hdr.levels != 64u - (uint32_t)__builtin_clzll((uint64_t)hdr.max_character)) return bad("levels");
     if (hdr.n >= 0xFFFFFFFFull || hdr.seq_len > hdr.n || hdr.runs > hdr.n || hdr.ndoc > hdr.n) return bad("lengths");
     if (hdr.sa_level >= 32 || hdr.isa_level >= 32 || hdr.vsa_level >= 32) return bad("sampling levels");
@@ -773,6 +1073,9 @@ int check_blob(const void *blob, uint64_t bytes, FmxBlobHeader &hdr, std::string
             for (int d = 0; d < 4; d++)
                 if (hdr.qoff[l][d] > len) return bad("WM4 offsets");
         }
+    } else if (wide) {
+        if (!need(SEC_LEVEL0, (uint64_t)hdr.levels * (len / FMX_RB_BITS + 1) * 32) || !need(SEC_WZEROS, (uint64_t)hdr.levels * 4))
+            return bad("wide wavelet levels");
     } else {
         for (uint32_t l = 0; l < hdr.levels; l++)
             if (!need(SEC_LEVEL0 + l, (len / FMX_RB_BITS + 1) * 32) || hdr.zeros[l] > len) return bad("wavelet level");

@@ -34,6 +34,11 @@ struct HostBlob {
 int build_blob(const uint8_t *text, uint64_t n, uint64_t max_character, int kind, int level,
                HostBlob &blob, std::string &err, int sa_device = -1, int mode = 0);
 
+// Texts of u16 / u32 / u64 characters with max_character > 255: the WIDE layout (fmx_layout.h).  char_width = 2, 4 or 8.
+int build_blob_wide(const void *text, uint32_t char_width, uint64_t n, uint64_t max_character, int kind, int level,
+                    HostBlob &blob, std::string &err, int mode = 0);
+int build_suffix_array_wide(const void *text, uint32_t char_width, uint64_t n, uint64_t *sa_out, std::string &err);
+
 // pieces of build_blob shared with the GPU builder (gpu_build.cu)
 struct VerifyPlan {
     bool verify = false, dense = false, dense_sa = false;

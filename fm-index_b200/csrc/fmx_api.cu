@@ -137,6 +137,9 @@ static bool env_flag(const char *name) {
     return v && v[0] && v[0] != '0';
 }
 
+// bytes per character of patterns and extracted characters (1 for every u8 index)
+static inline uint64_t char_width_of(const fmx_index *idx) { return 1ull << idx->dev.cw_shift; }
+
 static int build_kmer_table(fmx_index *idx);
 static int build_big_table(fmx_index *idx, uint64_t budget_bytes);
 
@@ -163,19 +166,22 @@ static inline bool locate_dense(const fmx_index *idx) { return has_dense_sa(idx)
 template <class F>
 static void dispatch(const fmx_index *idx, F &&f) {
     using std::integral_constant;
-    switch (idx->hdr.kind * 4 + idx->hdr.layout) {
+    switch (idx->hdr.kind * 8 + idx->hdr.layout) {
         case 0: f(integral_constant<int, 0>{}, integral_constant<int, 0>{}); break;
         case 1: f(integral_constant<int, 0>{}, integral_constant<int, 1>{}); break;
         case 2: f(integral_constant<int, 0>{}, integral_constant<int, 2>{}); break;
         case 3: f(integral_constant<int, 0>{}, integral_constant<int, 3>{}); break;
-        case 4: f(integral_constant<int, 1>{}, integral_constant<int, 0>{}); break;
-        case 5: f(integral_constant<int, 1>{}, integral_constant<int, 1>{}); break;
-        case 6: f(integral_constant<int, 1>{}, integral_constant<int, 2>{}); break;
-        case 7: f(integral_constant<int, 1>{}, integral_constant<int, 3>{}); break;
-        case 8: f(integral_constant<int, 2>{}, integral_constant<int, 0>{}); break;
-        case 9: f(integral_constant<int, 2>{}, integral_constant<int, 1>{}); break;
-        case 10: f(integral_constant<int, 2>{}, integral_constant<int, 2>{}); break;
-        default: f(integral_constant<int, 2>{}, integral_constant<int, 3>{}); break;
+        case 4: f(integral_constant<int, 0>{}, integral_constant<int, 4>{}); break;
+        case 8: f(integral_constant<int, 1>{}, integral_constant<int, 0>{}); break;
+        case 9: f(integral_constant<int, 1>{}, integral_constant<int, 1>{}); break;
+        case 10: f(integral_constant<int, 1>{}, integral_constant<int, 2>{}); break;
+        case 11: f(integral_constant<int, 1>{}, integral_constant<int, 3>{}); break;
+        case 12: f(integral_constant<int, 1>{}, integral_constant<int, 4>{}); break;
+        case 16: f(integral_constant<int, 2>{}, integral_constant<int, 0>{}); break;
+        case 17: f(integral_constant<int, 2>{}, integral_constant<int, 1>{}); break;
+        case 18: f(integral_constant<int, 2>{}, integral_constant<int, 2>{}); break;
+        case 19: f(integral_constant<int, 2>{}, integral_constant<int, 3>{}); break;
+        default: f(integral_constant<int, 2>{}, integral_constant<int, 4>{}); break;
     }
 }
 
@@ -198,9 +204,9 @@ int fmx_device_count(void) {
 }
 
 int fmx_build_suffix_array(const void *text, uint64_t n, uint32_t char_width, uint64_t *sa_out) {
-    if (char_width != 1) return fail(FMX_ERR_UNSUPPORTED, "only u8 texts (char_width == 1) are supported");
     std::string err;
-    int rc = build_suffix_array(static_cast<const uint8_t *>(text), n, sa_out, err);
+    int rc = char_width == 1 ? build_suffix_array(static_cast<const uint8_t *>(text), n, sa_out, err)
+                             : build_suffix_array_wide(text, char_width, n, sa_out, err);
     return rc ? fail(rc, err) : FMX_OK;
 }
 
@@ -221,13 +227,44 @@ int fmx_build_suffix_array_device(const void *text, uint64_t n, uint32_t char_wi
     return FMX_OK;
 }
 
+// Host blob of a text of any character width (character.rs:38-42).  u8: build_blob.  u16 / u32 / u64 with
+// max_character > 255: the WIDE layout (build_blob_wide).  Wide characters over a small alphabet (max_character <= 255):
+// the text is narrowed and takes the u8 layouts; only the header's char_width -- the width of patterns and extracted
+// characters at the ABI -- differs, and the index is a compact one (no tables, no verify structures: kernels.cuh AnyReader).
+static int build_blob_any(const void *text, uint64_t n, uint32_t char_width, uint64_t max_character, int kind, int level,
+                          HostBlob &b, std::string &err, int sa_device, int mode) {
+    if (char_width == 1) return build_blob(static_cast<const uint8_t *>(text), n, max_character, kind, level, b, err, sa_device, mode);
+    if (char_width != 2 && char_width != 4 && char_width != 8) {
+        err = "character width must be 1, 2, 4 or 8 bytes";
+        return FMX_ERR_INVALID_ARG;
+    }
+    if (max_character > 255) return build_blob_wide(text, char_width, n, max_character, kind, level, b, err, mode);
+    std::vector<uint8_t> narrow(n);
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        const uint64_t v = char_width == 2 ? static_cast<const uint16_t *>(text)[i]
+                         : char_width == 4 ? static_cast<const uint32_t *>(text)[i] : static_cast<const uint64_t *>(text)[i];
+        bad |= v > max_character;
+        narrow[(size_t)i] = (uint8_t)v;
+    }
+    if (bad) {
+        err = "text contains a character larger than max_character";
+        return FMX_ERR_INVALID_ARG;
+    }
+    if (int mrc = resolve_mode(mode, err)) return mrc;
+    int rc = build_blob(narrow.data(), n, max_character, kind, level, b, err, sa_device, FMX_MODE_COMPACT);
+    if (rc) return rc;
+    reinterpret_cast<FmxBlobHeader *>(b.p)->char_width = char_width;
+    return 0;
+}
+
 int fmx_blob_build_ex(const void *text, uint64_t n, uint32_t char_width, uint64_t max_character, int kind, int level,
                       int mode, void **blob, uint64_t *blob_bytes) {
     if (!blob || !blob_bytes || (!text && n)) return fail(FMX_ERR_INVALID_ARG, "null argument");
-    if (char_width != 1) return fail(FMX_ERR_UNSUPPORTED, "only u8 texts (char_width == 1) are supported");
     HostBlob b;
     std::string err;
-    int rc = build_blob(static_cast<const uint8_t *>(text), n, max_character, kind, level, b, err, -1, mode);
+    int rc = build_blob_any(text, n, char_width, max_character, kind, level, b, err, -1, mode);
     if (rc) return fail(rc, err);
     *blob_bytes = b.n;
     *blob = b.release();  // malloc'd: the caller frees it with fmx_free
@@ -248,9 +285,18 @@ static void bind_sections(fmx_index *idx) {
     auto sec = [&](int k) -> const void * { return hdr.sec[k].bytes ? base + hdr.sec[k].offset : nullptr; };
     FmxDev &d = idx->dev;
     std::memset(&d, 0, sizeof(d));
-    for (uint32_t l = 0; l < hdr.levels; l++) {
+    for (uint32_t l = 0; l < hdr.levels && l < FMX_MAX_LEVELS && hdr.layout != FMX_LAYOUT_WIDE; l++) {
         d.lv[l] = static_cast<const uint4 *>(sec(SEC_LEVEL0 + l));
         d.zeros[l] = (uint32_t)hdr.zeros[l];
+    }
+    if (hdr.layout == FMX_LAYOUT_WIDE) {  // all levels in SEC_LEVEL0, zeros per level in SEC_WZEROS
+        d.lv[0] = static_cast<const uint4 *>(sec(SEC_LEVEL0));
+        d.wzeros = static_cast<const uint32_t *>(sec(SEC_WZEROS));
+        d.wide_nblk = (uint32_t)(hdr.seq_len / FMX_RB_BITS + 1);
+    }
+    {
+        const uint32_t cw = hdr.char_width ? hdr.char_width : 1u;
+        d.cw_shift = cw == 8 ? 3u : (cw == 4 ? 2u : (cw == 2 ? 1u : 0u));
     }
     if (hdr.layout == FMX_LAYOUT_SYM) {
         d.lv[0] = static_cast<const uint4 *>(sec(SEC_LEVEL0));
@@ -420,7 +466,6 @@ int fmx_index_mode_of(const fmx_index *idx) {
 int fmx_index_build_ex(const void *text, uint64_t n, uint32_t char_width, uint64_t max_character, int kind, int level,
                        int device, int mode, fmx_index **out) {
     if (!out || (!text && n)) return fail(FMX_ERR_INVALID_ARG, "null argument");
-    if (char_width != 1) return fail(FMX_ERR_UNSUPPORTED, "only u8 texts (char_width == 1) are supported");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -428,7 +473,7 @@ int fmx_index_build_ex(const void *text, uint64_t n, uint32_t char_width, uint64
     }
     if (device < 0 || device >= ndev) return fail(FMX_ERR_INVALID_ARG, "device ordinal out of range");
     std::string err;
-    if (!env_flag("FMX_HOST_BUILD") && !env_flag("FMX_HOST_SA")) {
+    if (char_width == 1 && !env_flag("FMX_HOST_BUILD") && !env_flag("FMX_HOST_SA")) {
         // Q4 layouts of FM / MultiPieces indexes: the whole blob is built in device memory (gpu_build.cu)
         void *d_blob = nullptr;
         FmxBlobHeader hdr;
@@ -438,7 +483,7 @@ int fmx_index_build_ex(const void *text, uint64_t n, uint32_t char_width, uint64
         err.clear();
     }
     HostBlob b;
-    int rc = build_blob(static_cast<const uint8_t *>(text), n, max_character, kind, level, b, err, device, mode);
+    int rc = build_blob_any(text, n, char_width, max_character, kind, level, b, err, device, mode);
     if (rc) return fail(rc, err);
     return upload(b.p, b.n, device, out);
 }
@@ -551,6 +596,7 @@ int fmx_index_device(const fmx_index *idx) { return idx ? idx->device : -1; }
 uint32_t fmx_index_wavelet_levels(const fmx_index *idx) { return idx ? idx->hdr.levels : 0; }
 uint32_t fmx_index_sample_level(const fmx_index *idx) { return idx && idx->hdr.has_locate ? idx->hdr.sa_level : 0; }
 uint32_t fmx_index_layout(const fmx_index *idx) { return idx ? idx->hdr.layout : 0; }
+uint32_t fmx_index_char_width(const fmx_index *idx) { return idx ? (idx->hdr.char_width ? idx->hdr.char_width : 1u) : 0; }
 uint32_t fmx_index_sectors_per_rank(const fmx_index *idx) {
     if (!idx) return 0;
     if (idx->hdr.layout == FMX_LAYOUT_QUAT || idx->hdr.layout == FMX_LAYOUT_SYM) return 1u;
@@ -784,6 +830,7 @@ static int build_big_table(fmx_index *idx, uint64_t budget_bytes) {
 }
 
 static int build_kmer_table(fmx_index *idx) {
+    if (idx->dev.cw_shift) return 0;  // indexes over wide characters run the plain search kernel (no tables, no verify tail)
     if (env_flag("FMX_NO_KMER") || idx->hdr.n < 2) return 0;
     const bool large_text = idx->hdr.n >= (1ull << 22);
     uint32_t k;
@@ -835,6 +882,8 @@ static int make_search_args(const fmx_index *idx, int mode, const PatSrc &ps, ui
     a.pat = ps.pat;
     a.pat_off = ps.pat_off;
     a.fixed_len = ps.fixed_len;
+    a.cw_shift = idx->dev.cw_shift;
+    if (ps.packed_bits && a.cw_shift) return fail(FMX_ERR_UNSUPPORTED, "packed patterns are for u8 indexes");
     if (ps.packed_bits) {
         if (ps.packed_bits != 2 && ps.packed_bits != 4) return fail(FMX_ERR_INVALID_ARG, "packed_bits must be 0, 2 or 4");
         if (idx->hdr.max_character > (1u << ps.packed_bits))
@@ -852,7 +901,7 @@ static int make_search_args(const fmx_index *idx, int mode, const PatSrc &ps, ui
     a.e0 = (mode == FMX_SEARCH_SUFFIX || mode == FMX_SEARCH_EXACT) ? (uint32_t)idx->hdr.ndoc : (uint32_t)idx->hdr.n;
     a.err = idx->d_err;
     a.work = (count_work && idx->opt_count_work) ? idx->d_work : nullptr;
-    a.staged = (!ps.packed_bits && !ps.pat_off && ps.fixed_len > 0 && ps.fixed_len % 16 == 0 &&
+    a.staged = (!ps.packed_bits && !a.cw_shift && !ps.pat_off && ps.fixed_len > 0 && ps.fixed_len % 16 == 0 &&
                 reinterpret_cast<uintptr_t>(ps.pat) % 16 == 0 && idx->opt_stage_patterns) ? 1u : 0u;
     a.verify = (idx->dev.verify && idx->opt_verify) ? 1u : 0u;
     // the table memoises searches that start from (0, n): fresh search / search_prefix
@@ -956,7 +1005,7 @@ static int search_device(const fmx_index *idx, int mode, const PatSrc &ps, uint6
         }
         return 0;
     }
-    return dispatch_search(idx, a, st, force_simple || a.packed_bits != 0, buf);
+    return dispatch_search(idx, a, st, force_simple || a.packed_bits != 0 || a.cw_shift != 0, buf);
 }
 
 static int check_err_flag(const fmx_index *idx, cudaStream_t st) {
@@ -998,7 +1047,7 @@ extern "C" int fmx_search_batch(const fmx_index *idx, int mode, const uint8_t *p
     std::lock_guard<std::mutex> lk(idx->mu);
     CUDA_TRY(cudaSetDevice(idx->device));
     cudaStream_t st = idx->stream;
-    uint64_t pat_bytes = pat_off ? pat_off[npat] : npat * fixed_len;
+    uint64_t pat_bytes = (pat_off ? pat_off[npat] : npat * fixed_len) * char_width_of(idx);
     if (pat_bytes && !pat) return fail(FMX_ERR_INVALID_ARG, "null pattern buffer");
     int rc;
     if ((rc = idx->buf[B_PAT].ensure(pat_bytes + 16))) return rc;
@@ -1708,8 +1757,9 @@ extern "C" int fmx_query_batch(const fmx_index *idx, const fmx_query *q, uint64_
             ps.fixed_len = q->fixed_len;
             return;
         }
-        const uint64_t off0 = q->pat_off ? q->pat_off[lo] : lo * q->fixed_len;
-        const uint64_t nbytes = (q->pat_off ? q->pat_off[lo + n] : (lo + n) * q->fixed_len) - off0;
+        const uint64_t cw = char_width_of(idx);
+        const uint64_t off0 = (q->pat_off ? q->pat_off[lo] : lo * q->fixed_len) * cw;
+        const uint64_t nbytes = (q->pat_off ? q->pat_off[lo + n] : (lo + n) * q->fixed_len) * cw - off0;
         if ((r = L.buf[B_PAT].ensure(nbytes + 16))) return;
         if (nbytes && cudaMemcpyAsync(L.buf[B_PAT].p, pat8 + off0, nbytes, cudaMemcpyHostToDevice, L.st) != cudaSuccess) {
             r = fail(FMX_ERR_CUDA, "H2D copy of the patterns failed");
@@ -1802,7 +1852,7 @@ extern "C" int fmx_query_batch(const fmx_index *idx, const fmx_query *q, uint64_
                 ps.pat = L.buf[B_PAT].as<uint8_t>();
                 if (q->pat_off) {
                     ps.pat_off = L.buf[B_OFF].as<uint64_t>();
-                    ps.pat -= q->pat_off[lo];
+                    ps.pat -= q->pat_off[lo] * char_width_of(idx);
                 }
             }
             ps.fixed_len = q->fixed_len;
@@ -1993,13 +2043,14 @@ extern "C" int fmx_extract_batch(const fmx_index *idx, const uint64_t *rows, uin
     cudaStream_t st = idx->stream;
     int rc;
     if ((rc = idx->buf[B_S].ensure(nrows * 8))) return rc;
-    if ((rc = idx->buf[B_OUT8].ensure(nrows * (uint64_t)k + 16))) return rc;
+    const uint64_t out_bytes = nrows * (uint64_t)k * char_width_of(idx);  // characters leave in the text's width
+    if ((rc = idx->buf[B_OUT8].ensure(out_bytes + 16))) return rc;
     if ((rc = idx->buf[B_OUT32].ensure(nrows * 4))) return rc;
     CUDA_TRY(cudaMemcpyAsync(idx->buf[B_S].p, rows, nrows * 8, cudaMemcpyHostToDevice, st));
     if ((rc = extract_device(idx, idx->buf[B_S].as<uint64_t>(), nrows, k, forward, idx->buf[B_OUT8].as<uint8_t>(),
                              idx->buf[B_OUT32].as<uint32_t>(), st)))
         return rc;
-    if (k) CUDA_TRY(cudaMemcpyAsync(out, idx->buf[B_OUT8].p, nrows * (uint64_t)k, cudaMemcpyDeviceToHost, st));
+    if (k) CUDA_TRY(cudaMemcpyAsync(out, idx->buf[B_OUT8].p, out_bytes, cudaMemcpyDeviceToHost, st));
     if (out_len) {
         if (k) CUDA_TRY(cudaMemcpyAsync(out_len, idx->buf[B_OUT32].p, nrows * 4, cudaMemcpyDeviceToHost, st));
         else std::memset(out_len, 0, nrows * 4);
@@ -2036,9 +2087,16 @@ extern "C" int fmx_rows_op(const fmx_index *idx, int op, const uint64_t *rows, u
 extern "C" int fmx_lf_map2_batch(const fmx_index *idx, const uint8_t *c, const uint64_t *i, uint64_t nrows, uint64_t *out) {
     if (!idx || ((!c || !i || !out) && nrows)) return fail(FMX_ERR_INVALID_ARG, "null argument");
     if (nrows == 0) return FMX_OK;
+    // characters arrive in the index's character width; the kernel takes them as u32
+    const uint64_t cw = char_width_of(idx);
+    std::vector<uint32_t> c32(nrows);
     for (uint64_t r = 0; r < nrows; r++) {
         if (i[r] > idx->hdr.n) return fail(FMX_ERR_INVALID_ARG, "row out of range");
-        if (c[r] > idx->hdr.max_character) return fail(FMX_ERR_PATTERN_CHAR, "character larger than max_character");
+        const uint64_t v = cw == 1 ? c[r]
+                         : cw == 2 ? reinterpret_cast<const uint16_t *>(c)[r]
+                         : cw == 4 ? reinterpret_cast<const uint32_t *>(c)[r] : reinterpret_cast<const uint64_t *>(c)[r];
+        if (v > idx->hdr.max_character) return fail(FMX_ERR_PATTERN_CHAR, "character larger than max_character");
+        c32[r] = (uint32_t)v;
     }
     std::lock_guard<std::mutex> lk(idx->mu);
     CUDA_TRY(cudaSetDevice(idx->device));
@@ -2046,11 +2104,12 @@ extern "C" int fmx_lf_map2_batch(const fmx_index *idx, const uint8_t *c, const u
     int rc;
     if ((rc = idx->buf[B_S].ensure(nrows * 8))) return rc;
     if ((rc = idx->buf[B_E].ensure(nrows * 8))) return rc;
-    if ((rc = idx->buf[B_PAT].ensure(nrows + 16))) return rc;
+    if ((rc = idx->buf[B_PAT].ensure(nrows * 4 + 16))) return rc;
     CUDA_TRY(cudaMemcpyAsync(idx->buf[B_S].p, i, nrows * 8, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(idx->buf[B_PAT].p, c, nrows, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(idx->buf[B_PAT].p, c32.data(), nrows * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));  // c32 is a local
     unsigned g = grid_for(nrows, 256);
-    const uint8_t *d_c = idx->buf[B_PAT].as<uint8_t>();
+    const uint32_t *d_c = idx->buf[B_PAT].as<uint32_t>();
     const uint64_t *d_i = idx->buf[B_S].as<uint64_t>();
     uint64_t *d_out = idx->buf[B_E].as<uint64_t>();
     dispatch(idx, [&](auto K, auto LY) { k_lf_map2<K(), LY()><<<g, 256, 0, st>>>(idx->dev, d_c, d_i, nrows, d_out); });

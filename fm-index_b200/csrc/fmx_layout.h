@@ -62,6 +62,14 @@
 // acceleration structures of the SEARCH, like the k-mer tables: locate still walks to the samples of the
 // level the caller asked for.
 //
+// WIDE ALPHABETS ("WIDE": max_character > 255, i.e. texts of u16 / u32 / u64 characters, character.rs:38-42).
+// The binary wavelet matrix with L = floor(log2 max_character) + 1 <= 32 levels, all levels in SEC_LEVEL0 one after the
+// other (level l starts at block l * wide_nblk), zeros per level in SEC_WZEROS, and cs / adj -- max_character + 1 words
+// each, as in the reference (sais.rs:9-19) -- read from global memory instead of being staged in shared memory.
+// adj[c] is only filled for symbols that occur; for the others rank(., c) = 0 and the kernels return cs[c] without
+// touching the matrix (cs[c + 1] == cs[c] marks them).  Texts of wide characters whose max_character is <= 255 take
+// the u8 layouts above; only the pattern / extraction character width (header char_width) differs.
+//
 // Q4 DETAILS.  The rare symbol 0
 // (the \0 terminators: 1 for a single text, one per piece for MultiPieces) is stored as code 0
 // and its positions are listed in SEC_EXC (sorted; staged in shared memory), which corrects
@@ -74,7 +82,7 @@
 #include <vector_types.h>  // uint4 (CUDA toolkit header, host-safe)
 
 #define FMX_BLOB_MAGIC 0x3030324258584d46ull /* "FMXXB200" little endian-ish tag */
-#define FMX_BLOB_VERSION 6u
+#define FMX_BLOB_VERSION 7u
 #define FMX_MAX_LEVELS 8
 #define FMX_RB_BITS 192u
 #define FMX_MAX_EXC 1024u   /* Q4 layout: at most this many \0 symbols in the sequence */
@@ -82,6 +90,8 @@
 #define FMX_LAYOUT_QUAT 1u
 #define FMX_LAYOUT_WM4 2u
 #define FMX_LAYOUT_SYM 3u
+#define FMX_LAYOUT_WIDE 4u
+#define FMX_MAX_WIDE_LEVELS 32
 #define FMX_MAX_QLEVELS 4
 #define FMX_SECTION_ALIGN 256u
 
@@ -100,7 +110,8 @@ enum FmxSection : uint32_t {
     SEC_TEXT = 18,      // u8[n]      the text itself (verify path, FM kind)
     SEC_ISA = 19,       // u32[ceil(n / 2^isa_level)]  row of the suffix starting at text position k << isa_level
     SEC_VSA = 20,       // u32[n]     the FULL suffix array, for the verify path only (locate keeps the caller's level)
-    SEC_COUNT = 21
+    SEC_WZEROS = 21,    // u32[levels]  WIDE layout: zeros per wavelet level
+    SEC_COUNT = 22
 };
 
 struct FmxSectionEntry {
@@ -127,14 +138,14 @@ struct FmxBlobHeader {
     uint64_t zeros[FMX_MAX_LEVELS];  // zeros per level
     uint64_t total_bytes;
     FmxSectionEntry sec[SEC_COUNT];
-    uint32_t layout;  // FMX_LAYOUT_WAVELET | FMX_LAYOUT_QUAT | FMX_LAYOUT_WM4
+    uint32_t layout;  // FMX_LAYOUT_WAVELET | FMX_LAYOUT_QUAT | FMX_LAYOUT_WM4 | FMX_LAYOUT_SYM | FMX_LAYOUT_WIDE
     uint32_t nexc;    // Q4: number of zeros in the sequence
     uint32_t qlevels; // WM4: ceil(levels / 2)
     uint32_t sym_nblk; // SYM: RB192 blocks per symbol vector (seq_len / 192 + 1)
     uint32_t verify;     // 1: SEC_TEXT / SEC_ISA / SEC_SA present for the seed-and-verify tail of k_search
     uint32_t isa_level;  // ISA sampling: every 2^isa_level-th text position (0 with the dense structures)
     uint32_t vsa_level;  // sampling level of the suffix-array samples the verify path walks to (0 = SEC_VSA / dense)
-    uint32_t pad1;
+    uint32_t char_width; // bytes per character of the text the index was built from (1, 2, 4, 8): width of patterns and extracted characters
     uint64_t qoff[FMX_MAX_QLEVELS][4];  // WM4: start of digit group d at level l
     uint64_t reserved[4];
 };
@@ -176,4 +187,7 @@ struct FmxDev {
     uint32_t isa_level;
     const uint32_t *vsa;  // verify path: suffix-array samples of level vsa_level (the full array when dense)
     uint32_t vsa_level;
+    const uint32_t *wzeros;  // WIDE: zeros per level
+    uint32_t wide_nblk;      // WIDE: RB192 blocks per level (seq_len / 192 + 1)
+    uint32_t cw_shift;       // log2(char_width)
 };

@@ -147,6 +147,7 @@ int gpu_build_q4_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, in
     hdr.max_character = (uint32_t)mc;
     hdr.cs_len = cs_len;
     hdr.layout = FMX_LAYOUT_QUAT;
+    hdr.char_width = 1;
     hdr.nexc = (uint32_t)zeros.size();
     hdr.reserved[0] = (uint64_t)mode;
     if (vp.verify) {

@@ -155,11 +155,20 @@ __device__ __forceinline__ uint32_t rbv_select0(const uint4 *__restrict__ v, uin
 #define FMX_LAYOUT_W4 2  // quaternary wavelet matrix, ceil(L/2) levels (alphabets too large for SYM's budget)
 #define FMX_LAYOUT_SY 3  // one RB192 bit vector per symbol + the raw sequence: ONE sector per lf_map2
 
+#define FMX_LAYOUT_WW 4  // WIDE: binary wavelet matrix of up to 32 levels, cs / adj in global memory (max_character > 255)
+
 template <int LAYOUT>
 struct Tabs {
     uint32_t adj[256];  // WM: cs[c] - walk_c(0)
     uint32_t cs[257];   // cs[c], cs[cs_len] = sequence length
     uint32_t exc[LAYOUT == FMX_LAYOUT_Q4 ? FMX_MAX_EXC : 1];  // Q4: sorted positions whose symbol is 0
+};
+// wide alphabets: max_character + 1 entries each, far beyond shared memory -- the tables stay where they are
+template <>
+struct Tabs<FMX_LAYOUT_WW> {
+    const uint32_t *adj;
+    const uint32_t *cs;
+    uint32_t exc[1];
 };
 
 template <int LAYOUT>
@@ -170,24 +179,49 @@ __device__ __forceinline__ void load_tables(const FmxDev &ix, Tabs<LAYOUT> &t) {
         for (uint32_t k = threadIdx.x; k < ix.nexc; k += blockDim.x) t.exc[k] = __ldg(ix.exc + k);
     __syncthreads();
 }
+template <>
+__device__ __forceinline__ void load_tables<FMX_LAYOUT_WW>(const FmxDev &ix, Tabs<FMX_LAYOUT_WW> &t) {
+    if (threadIdx.x == 0) {
+        t.adj = ix.adj;
+        t.cs = ix.cs;
+    }
+    __syncthreads();
+}
+
+// level l of the binary wavelet matrix and its zero count: per-level sections (WM) or one section (WIDE)
+template <int LAYOUT>
+__device__ __forceinline__ const uint4 *wm_lv(const FmxDev &ix, uint32_t l) {
+    return LAYOUT == FMX_LAYOUT_WW ? ix.lv[0] + 2ull * l * ix.wide_nblk : ix.lv[l];  // a block is two uint4
+}
+template <int LAYOUT>
+__device__ __forceinline__ uint32_t wm_zeros(const FmxDev &ix, uint32_t l) {
+    return LAYOUT == FMX_LAYOUT_WW ? __ldg(ix.wzeros + l) : ix.zeros[l];
+}
+// WIDE: symbols that do not occur have rank 0 everywhere and no adj entry (cs[c + 1] == cs[c] marks them)
+template <int LAYOUT>
+__device__ __forceinline__ bool sym_absent(const Tabs<LAYOUT> &t, uint32_t c) {
+    return LAYOUT == FMX_LAYOUT_WW && t.cs[c + 1] == t.cs[c];
+}
 
 // ------------------------------------------------------------------ wavelet matrix (LAYOUT_WM)
 
 // position of `pos` after walking symbol c's path down all levels (rank(i,c) = walk - walk_c(0))
+template <int LAYOUT>
 __device__ __forceinline__ uint32_t wm_walk(const FmxDev &ix, uint32_t c, uint32_t pos) {
     const uint32_t L = ix.levels;
 #pragma unroll 1
     for (uint32_t l = 0; l < L; l++) {
         uint32_t blk, r;
         rb_split(pos, blk, r);
-        RB b = rb_load(ix.lv[l], blk);
+        RB b = rb_load(wm_lv<LAYOUT>(ix, l), blk);
         uint32_t ones = rb_rank(b, r);
-        pos = ((c >> (L - 1 - l)) & 1u) ? ix.zeros[l] + ones : pos - ones;
+        pos = ((c >> (L - 1 - l)) & 1u) ? wm_zeros<LAYOUT>(ix, l) + ones : pos - ones;
     }
     return pos;
 }
 
 // the same for the two ends of an SA range; shares the sector when both fall in one block
+template <int LAYOUT>
 __device__ __forceinline__ void wm_walk2(const FmxDev &ix, uint32_t c, uint32_t &s, uint32_t &e) {
     const uint32_t L = ix.levels;
 #pragma unroll 1
@@ -195,13 +229,13 @@ __device__ __forceinline__ void wm_walk2(const FmxDev &ix, uint32_t c, uint32_t 
         uint32_t bs, rs, be, re;
         rb_split(s, bs, rs);
         rb_split(e, be, re);
-        const uint4 *v = ix.lv[l];
+        const uint4 *v = wm_lv<LAYOUT>(ix, l);
         RB a = rb_load(v, bs);
         RB b = a;
         if (be != bs) b = rb_load(v, be);
         uint32_t os = rb_rank(a, rs), oe = rb_rank(b, re);
         if ((c >> (L - 1 - l)) & 1u) {
-            uint32_t z = ix.zeros[l];
+            uint32_t z = wm_zeros<LAYOUT>(ix, l);
             s = z + os;
             e = z + oe;
         } else {
@@ -213,6 +247,7 @@ __device__ __forceinline__ void wm_walk2(const FmxDev &ix, uint32_t c, uint32_t 
 
 // access + walk fused: symbol at `pos` and its position at the bottom level (one sector / level;
 // the reference does get_l then rank separately, fm_index.rs:87-89)
+template <int LAYOUT>
 __device__ __forceinline__ uint32_t wm_access_walk(const FmxDev &ix, uint32_t pos, uint32_t &sym) {
     const uint32_t L = ix.levels;
     uint32_t c = 0;
@@ -220,25 +255,26 @@ __device__ __forceinline__ uint32_t wm_access_walk(const FmxDev &ix, uint32_t po
     for (uint32_t l = 0; l < L; l++) {
         uint32_t blk, r;
         rb_split(pos, blk, r);
-        RB b = rb_load(ix.lv[l], blk);
+        RB b = rb_load(wm_lv<LAYOUT>(ix, l), blk);
         uint32_t bit;
         uint32_t ones = rb_rank_bit(b, r, bit);
         c = (c << 1) | bit;
-        pos = bit ? ix.zeros[l] + ones : pos - ones;
+        pos = bit ? wm_zeros<LAYOUT>(ix, l) + ones : pos - ones;
     }
     sym = c;
     return pos;
 }
 
 // select_u64_unchecked(k, c): position of the k-th c.  base = walk_c(0).
+template <int LAYOUT>
 __device__ __forceinline__ uint32_t wm_select(const FmxDev &ix, uint32_t c, uint32_t k, uint32_t base) {
     const uint32_t L = ix.levels;
     const uint32_t nblk = ix.seq_len / FMX_RB_BITS + 1;
     uint32_t pos = base + k;
 #pragma unroll 1
     for (uint32_t l = L; l-- > 0;) {
-        if ((c >> (L - 1 - l)) & 1u) pos = rbv_select1(ix.lv[l], nblk, pos - ix.zeros[l]);
-        else pos = rbv_select0(ix.lv[l], nblk, pos);
+        if ((c >> (L - 1 - l)) & 1u) pos = rbv_select1(wm_lv<LAYOUT>(ix, l), nblk, pos - wm_zeros<LAYOUT>(ix, l));
+        else pos = rbv_select0(wm_lv<LAYOUT>(ix, l), nblk, pos);
     }
     return pos;
 }
@@ -456,7 +492,8 @@ __device__ __forceinline__ uint32_t seq_lf(const FmxDev &ix, const Tabs<LAYOUT> 
     } else if (LAYOUT == FMX_LAYOUT_W4) {
         return t.adj[c] + w4_walk(ix, c, i);
     } else {
-        return t.adj[c] + wm_walk(ix, c, i);
+        if (sym_absent<LAYOUT>(t, c)) return t.cs[c];
+        return t.adj[c] + wm_walk<LAYOUT>(ix, c, i);
     }
 }
 
@@ -480,8 +517,12 @@ __device__ __forceinline__ void seq_lf2(const FmxDev &ix, const Tabs<LAYOUT> &t,
         s = base + rb_rank(a, rs);
         e = base + rb_rank(b, re);
     } else {
+        if (sym_absent<LAYOUT>(t, c)) {
+            s = e = t.cs[c];
+            return;
+        }
         if (LAYOUT == FMX_LAYOUT_W4) w4_walk2(ix, c, s, e);
-        else wm_walk2(ix, c, s, e);
+        else wm_walk2<LAYOUT>(ix, c, s, e);
         uint32_t a = t.adj[c];
         s += a;
         e += a;
@@ -502,7 +543,7 @@ __device__ __forceinline__ uint32_t seq_access_lf(const FmxDev &ix, const Tabs<L
         return t.cs[c] + rbv_rank1(sy_vec(ix, c), i);
     } else {
         uint32_t c;
-        uint32_t w = LAYOUT == FMX_LAYOUT_W4 ? w4_access_walk(ix, i, c) : wm_access_walk(ix, i, c);
+        uint32_t w = LAYOUT == FMX_LAYOUT_W4 ? w4_access_walk(ix, i, c) : wm_access_walk<LAYOUT>(ix, i, c);
         sym = c;
         return w + t.adj[c];
     }
@@ -519,7 +560,7 @@ __device__ __forceinline__ uint32_t seq_access(const FmxDev &ix, const Tabs<LAYO
     } else {
         uint32_t c;
         if (LAYOUT == FMX_LAYOUT_W4) w4_access_walk(ix, i, c);
-        else wm_access_walk(ix, i, c);
+        else wm_access_walk<LAYOUT>(ix, i, c);
         return c;
     }
 }
@@ -530,7 +571,7 @@ __device__ __forceinline__ uint32_t seq_select(const FmxDev &ix, const Tabs<LAYO
     if (LAYOUT == FMX_LAYOUT_Q4) return q4_select(ix, t.exc, c, k);
     if (LAYOUT == FMX_LAYOUT_SY) return rbv_select1(sy_vec(ix, c), ix.sym_nblk, k);
     if (LAYOUT == FMX_LAYOUT_W4) return w4_select(ix, c, k, t.cs[c] - t.adj[c]);
-    return wm_select(ix, c, k, t.cs[c] - t.adj[c]);
+    return wm_select<LAYOUT>(ix, c, k, t.cs[c] - t.adj[c]);
 }
 
 // ------------------------------------------------------------------ backend primitives
@@ -589,6 +630,11 @@ __device__ __forceinline__ void rl_probe(const FmxDev &ix, const Tabs<LAYOUT> &t
         nrc = t.adj[c] + p;
         hit = alive;
     } else {
+        if (sym_absent<LAYOUT>(t, c)) {  // no run of c: rank 0, and the run of row i has another head
+            nrc = t.cs[c];
+            hit = false;
+            return;
+        }
         const uint32_t L = ix.levels;
         uint32_t p = j, q = h;
         bool alive = true;
@@ -598,7 +644,7 @@ __device__ __forceinline__ void rl_probe(const FmxDev &ix, const Tabs<LAYOUT> &t
             uint32_t bp_, rp, bq, rq;
             rb_split(p, bp_, rp);
             rb_split(q, bq, rq);
-            const uint4 *v = ix.lv[l];
+            const uint4 *v = wm_lv<LAYOUT>(ix, l);
             RB a = rb_load(v, bp_);
             uint32_t op = rb_rank(a, rp);
             if (alive) {
@@ -607,9 +653,9 @@ __device__ __forceinline__ void rl_probe(const FmxDev &ix, const Tabs<LAYOUT> &t
                 uint32_t qbit;
                 uint32_t oq = rb_rank_bit(d, rq, qbit);
                 alive = qbit == bit;
-                q = bit ? ix.zeros[l] + oq : q - oq;
+                q = bit ? wm_zeros<LAYOUT>(ix, l) + oq : q - oq;
             }
-            p = bit ? ix.zeros[l] + op : p - op;
+            p = bit ? wm_zeros<LAYOUT>(ix, l) + op : p - op;
         }
         nrc = t.adj[c] + p;
         hit = alive;
@@ -763,6 +809,9 @@ struct SearchArgs {
     const uint64_t *packed;
     uint32_t packed_bits;
     uint32_t packed_wpp;
+    // log2 of the bytes per pattern character (0 for u8 indexes): `pat` then holds characters of 2, 4 or 8 bytes,
+    // offsets and lengths count characters (character.rs:38-42)
+    uint32_t cw_shift;
 };
 #define FMX_TAB_POS_FLAG 0x80000000u
 #define FMX_NOHINT 0xFFFFFFFFu
@@ -828,16 +877,26 @@ struct ByteReader {
 typedef ByteReader<false> PatReader;   // pattern bytes: streamed, default fill
 typedef ByteReader<true> TextReader;   // text bytes at a random position: sector-granular fill
 
-// Patterns in either input form behind one get(k): bytes (PatReader) or packed codes (SearchArgs::packed)
+// Patterns in any input form behind one get(k): bytes (PatReader), packed codes (SearchArgs::packed) or characters of
+// 2 / 4 / 8 bytes (SearchArgs::cw_shift; a u64 character beyond 32 bits reads as 0xFFFFFFFF, which is above every
+// max_character the index accepts, so it raises the same error as in the reference)
 struct AnyReader {
     PatReader pr;
     const uint64_t *pw;
-    uint32_t bits, curw;
+    const uint8_t *wide;
+    uint32_t bits, curw, cws;
     uint64_t w;
     __device__ __forceinline__ AnyReader(const SearchArgs &a, uint64_t p, uint64_t beg, uint32_t len)
-        : pr(a.pat + (a.packed_bits ? 0 : beg), a.packed_bits ? 0u : len), pw(a.packed + p * a.packed_wpp), bits(a.packed_bits),
-          curw(0xFFFFFFFFu), w(0) {}
+        : pr(a.pat + ((a.packed_bits || a.cw_shift) ? 0 : beg), (a.packed_bits || a.cw_shift) ? 0u : len),
+          pw(a.packed + p * a.packed_wpp), wide(a.pat + (beg << a.cw_shift)), bits(a.packed_bits), curw(0xFFFFFFFFu),
+          cws(a.cw_shift), w(0) {}
     __device__ __forceinline__ uint32_t get(uint32_t k) {
+        if (cws) {
+            if (cws == 1) return __ldg(reinterpret_cast<const uint16_t *>(wide) + k);
+            if (cws == 2) return __ldg(reinterpret_cast<const uint32_t *>(wide) + k);
+            const unsigned long long v = __ldg(reinterpret_cast<const unsigned long long *>(wide) + k);
+            return v > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)v;
+        }
         if (bits == 0) return pr.get(k);
         const uint32_t bit = k * bits, wi = bit >> 6;
         if (wi != curw) {
@@ -1095,7 +1154,7 @@ __global__ void __launch_bounds__(256) k_search(const __grid_constant__ FmxDev i
         uint32_t e = a.init_e ? (uint32_t)a.init_e[p] : a.e0;
         const uint8_t *q = a.pat + beg;
         uint32_t it = 0;
-        if (a.packed_bits) {
+        if (a.packed_bits || a.cw_shift) {
             AnyReader rd(a, p, beg, len);
             search_one<KIND, LAYOUT>(ix, tb, a, rd, len, s, e, it);
         } else if (a.staged) {
@@ -1711,7 +1770,14 @@ __global__ void __launch_bounds__(256) k_extract(const __grid_constant__ FmxDev 
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nrows) return;
     uint32_t i = (uint32_t)rows[r], got = 0;
-    uint8_t *o = out + r * k;
+    const uint32_t cws = ix.cw_shift;  // characters leave in the width of the text the index was built from
+    uint8_t *o = out + ((r * k) << cws);
+    auto put = [&](uint32_t t, uint32_t c) {
+        if (cws == 0) o[t] = (uint8_t)c;
+        else if (cws == 1) reinterpret_cast<uint16_t *>(o)[t] = (uint16_t)c;
+        else if (cws == 2) reinterpret_cast<uint32_t *>(o)[t] = c;
+        else reinterpret_cast<unsigned long long *>(o)[t] = c;
+    };
     for (uint32_t t = 0; t < k; t++) {
         uint32_t c, nx;
         if (!forward) {
@@ -1719,11 +1785,11 @@ __global__ void __launch_bounds__(256) k_extract(const __grid_constant__ FmxDev 
         } else if (!fl_step<KIND, LAYOUT>(ix, tb, i, c, nx)) {
             break;
         }
-        o[t] = (uint8_t)c;
+        put(t, c);
         i = nx;
         got++;
     }
-    for (uint32_t t = got; t < k; t++) o[t] = 0;
+    for (uint32_t t = got; t < k; t++) put(t, 0u);
     if (out_len) out_len[r] = got;
 }
 
@@ -1773,7 +1839,7 @@ __global__ void __launch_bounds__(256) k_rows_op(const __grid_constant__ FmxDev 
 }
 
 template <int KIND, int LAYOUT>
-__global__ void __launch_bounds__(256) k_lf_map2(const __grid_constant__ FmxDev ix, const uint8_t *c, const uint64_t *i,
+__global__ void __launch_bounds__(256) k_lf_map2(const __grid_constant__ FmxDev ix, const uint32_t *c, const uint64_t *i,
                                                  uint64_t nrows, uint64_t *out) {
     __shared__ Tabs<LAYOUT> tb;
     load_tables<LAYOUT>(ix, tb);

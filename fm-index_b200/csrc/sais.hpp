@@ -33,6 +33,13 @@ struct SentinelAcc {
     inline int64_t operator()(int64_t i) const { return i == n - 1 ? 0 : (int64_t)t[i] + 1; }
 };
 
+// the same over 32-bit symbols (ranks of wide characters)
+struct SentinelAcc32 {
+    const uint32_t *t;
+    int64_t n;
+    inline int64_t operator()(int64_t i) const { return i == n - 1 ? 0 : (int64_t)t[i] + 1; }
+};
+
 template <class Acc, class I>
 static void sais_buckets(const Acc &s, I n, std::vector<I> &cnt, std::vector<I> &bkt, bool end) {
     (void)s;

@@ -81,8 +81,15 @@ void fmx_free(void *p);
 
 /* ---------------------------------------------------------------- construction
  * Replaces Text::{new, with_max_character} (src/text.rs:28-49) + the six ::new
- * constructors (src/frontend.rs:195-267).  char_width must be 1 (u8 texts).
- * max_character = 255 is Text::new; anything else is Text::with_max_character.
+ * constructors (src/frontend.rs:195-267).
+ * char_width = bytes per character of `text`: 1, 2, 4 or 8 for Text<u8>, <u16>, <u32>, <u64 / usize>
+ * (src/character.rs:38-42).  Every character must be <= max_character, and max_character < 2^32 - 1 (the reference
+ * allocates max_character + 1 counters, sais.rs:9-19, so it cannot go further either): Text::new's
+ * C::max_value() is therefore available for u8 and u16 texts, wider ones use Text::with_max_character.
+ * An index over wide characters takes patterns (pat, fixed_len, pat_off: all counted in CHARACTERS) and returns
+ * extracted characters in that same width; it is a compact index (no k-mer tables, no packed patterns), and with
+ * max_character > 255 its rank structure is the WIDE layout (csrc/fmx_layout.h).  Multi-GPU groups take u8 texts.
+ * max_character = 255 is Text::new for u8; anything else is Text::with_max_character.
  * level = FMX_LEVEL_COUNT_ONLY builds the count-only variant; level >= 0 the
  * ...WithLocate variant with that sampling level (sample.rs:21-44).
  * Text validation and its messages follow sais.rs:128-139. */
@@ -149,8 +156,10 @@ uint32_t fmx_index_sample_level(const fmx_index *idx);
  * 1 for Q4 (max_character <= 4) and SYM (per-symbol bit vectors), ceil(L/2) for the quaternary
  * wavelet matrix, L for the binary one. */
 uint32_t fmx_index_sectors_per_rank(const fmx_index *idx);
-/* the device layout the builder chose: 0 binary wavelet matrix, 1 Q4, 2 WM4, 3 SYM (csrc/fmx_layout.h) */
+/* the device layout the builder chose: 0 binary wavelet matrix, 1 Q4, 2 WM4, 3 SYM, 4 WIDE (csrc/fmx_layout.h) */
 uint32_t fmx_index_layout(const fmx_index *idx);
+/* bytes per character of the text the index was built from = width of pattern and extracted characters (1, 2, 4, 8) */
+uint32_t fmx_index_char_width(const fmx_index *idx);
 /* characters memoised by the small (big = 0) / large (big = 1) k-mer table of fresh searches; 0 = none */
 uint32_t fmx_index_kmer_k(const fmx_index *idx, int big);
 
@@ -319,7 +328,8 @@ int fmx_group_query_batch(const fmx_group *g, const fmx_query *q, uint64_t *tota
 /* ---------------------------------------------------------------- extraction
  * Batched Match::iter_chars_backward / iter_chars_forward taken k characters deep
  * -- src/wrapper.rs:143-183, 229-235.  rows are SA rows (the `i` of a Match).
- * out is nrows*k bytes, row-major; out_len[r] is the number of characters produced
+ * out is nrows*k characters of fmx_index_char_width(idx) bytes each (bytes for u8 indexes), row-major;
+ * out_len[r] is the number of characters produced
  * (always k backward; forward stops early on MultiPieces when fl_map is None,
  * multi_pieces.rs:171-181).  Unproduced bytes are 0. */
 int fmx_extract_batch(const fmx_index *idx, const uint64_t *rows, uint64_t nrows, uint32_t k,
@@ -332,7 +342,7 @@ int fmx_extract_batch_device(const fmx_index *idx, const uint64_t *d_rows, uint6
  * exposed for parity tests: op 0 = get_l, 1 = lf_map, 2 = get_f, 3 = fl_map (UINT64_MAX = None),
  * 4 = get_sa, 5 = piece_id via the reference's literal LF walk. */
 int fmx_rows_op(const fmx_index *idx, int op, const uint64_t *rows, uint64_t nrows, uint64_t *out);
-/* lf_map2(c[k], i[k]) for a batch (backend.rs:16). */
+/* lf_map2(c[k], i[k]) for a batch (backend.rs:16); c holds nrows characters of fmx_index_char_width(idx) bytes each. */
 int fmx_lf_map2_batch(const fmx_index *idx, const uint8_t *c, const uint64_t *i, uint64_t nrows,
                       uint64_t *out);
 

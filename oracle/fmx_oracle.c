@@ -42,6 +42,38 @@ static void set_err(char *err, size_t errlen, const char *msg) {
     }
 }
 
+/* ------------------------------------------------------------------ characters
+ * character.rs:24-42: u8, u16, u32, u64, usize texts.  A text (or pattern) is a pointer plus the width of one
+ * character in bytes; every character is read through tget.  Values must stay below 2^32 (the reference sizes
+ * its `cs` table by max_character + 1 words, so larger alphabets are out of reach there as well). */
+typedef struct {
+    const void *p;
+    uint32_t w; /* 1, 2, 4 or 8 */
+} tview;
+
+static inline uint64_t tget(tview t, uint64_t i) {
+    switch (t.w) {
+        case 1: return ((const uint8_t *)t.p)[i];
+        case 2: return ((const uint16_t *)t.p)[i];
+        case 4: return ((const uint32_t *)t.p)[i];
+        default: return ((const uint64_t *)t.p)[i];
+    }
+}
+static inline tview tview_at(tview t, uint64_t i) {
+    tview r;
+    r.p = (const uint8_t *)t.p + i * t.w;
+    r.w = t.w;
+    return r;
+}
+static inline void tput(void *p, uint32_t w, uint64_t i, uint64_t v) {
+    switch (w) {
+        case 1: ((uint8_t *)p)[i] = (uint8_t)v; break;
+        case 2: ((uint16_t *)p)[i] = (uint16_t)v; break;
+        case 4: ((uint32_t *)p)[i] = (uint32_t)v; break;
+        default: ((uint64_t *)p)[i] = v; break;
+    }
+}
+
 /* ------------------------------------------------------------------ SA-IS
  * Suffix array of the text under plain lexicographic order with \0 an ordinary
  * (smallest) symbol, which is what sais.rs produces (pinned there against a naive
@@ -50,14 +82,16 @@ static void set_err(char *err, size_t errlen, const char *msg) {
  * (symbols shifted by +1) so arbitrary texts, incl. interior zeros, are handled. */
 
 typedef struct {
-    const uint8_t *t8;  /* mode 0: original text, virtual sentinel at n-1 */
+    const uint8_t *t8;  /* mode 0: original u8 text, virtual sentinel at n-1 */
     const int64_t *t64; /* mode 1: reduced string */
+    tview tw;           /* mode 2: original text of wider characters, virtual sentinel at n-1 */
     int64_t n;
     int mode;
 } sstr;
 
 static inline int64_t sch(const sstr *s, int64_t i) {
     if (s->mode == 0) return i == s->n - 1 ? 0 : (int64_t)s->t8[i] + 1;
+    if (s->mode == 2) return i == s->n - 1 ? 0 : (int64_t)tget(s->tw, (uint64_t)i) + 1;
     return s->t64[i];
 }
 
@@ -173,20 +207,20 @@ static void sais_core(const sstr *s, int64_t *SA, int64_t K) {
 }
 
 /* sais.rs:115-144 */
-int orc_suffix_array(const uint8_t *text, uint64_t n, uint64_t *sa, char *err, size_t errlen) {
+static int suffix_array_view(tview text, uint64_t n, uint64_t mc, uint64_t *sa, char *err, size_t errlen) {
     if (n == 0) return 0;
     if (n == 1) {
         sa[0] = 0;
         return 0;
     }
-    if (text[0] == 0) { /* sais.rs:128-133 */
+    if (tget(text, 0) == 0) { /* sais.rs:128-133 */
         set_err(err, errlen, "the given text must not start with zero character");
         return -1;
     }
     { /* sais.rs:134-139: rposition of the last non-zero char must be n-2 */
         int64_t last_nz = -1;
         for (int64_t i = (int64_t)n - 1; i >= 0; i--)
-            if (text[i] != 0) {
+            if (tget(text, (uint64_t)i) != 0) {
                 last_nz = i;
                 break;
             }
@@ -197,14 +231,32 @@ int orc_suffix_array(const uint8_t *text, uint64_t n, uint64_t *sa, char *err, s
     }
     int64_t *tmp = (int64_t *)malloc((size_t)(n + 1) * sizeof(int64_t));
     sstr s;
-    s.t8 = text;
+    s.t8 = (const uint8_t *)text.p;
     s.t64 = NULL;
+    s.tw = text;
     s.n = (int64_t)n + 1;
-    s.mode = 0;
-    sais_core(&s, tmp, 257);
+    s.mode = text.w == 1 ? 0 : 2;
+    sais_core(&s, tmp, text.w == 1 ? 257 : (int64_t)mc + 2);
     for (uint64_t i = 0; i < n; i++) sa[i] = (uint64_t)tmp[i + 1];
     free(tmp);
     return 0;
+}
+
+int orc_suffix_array(const uint8_t *text, uint64_t n, uint64_t *sa, char *err, size_t errlen) {
+    tview t = {text, 1};
+    return suffix_array_view(t, n, 255, sa, err, errlen);
+}
+
+/* texts of u16 / u32 / u64 characters (character.rs:38-42); every character <= max_character < 2^32 */
+int orc_suffix_array_w(const void *text, uint32_t char_width, uint64_t n, uint64_t max_character, uint64_t *sa, char *err,
+                       size_t errlen) {
+    tview t = {text, char_width};
+    for (uint64_t i = 0; i < n; i++)
+        if (tget(t, i) > max_character) {
+            set_err(err, errlen, "text contains a character larger than max_character");
+            return -1;
+        }
+    return suffix_array_view(t, n, max_character, sa, err, errlen);
 }
 
 /* ------------------------------------------------------------------ RsVec
@@ -322,32 +374,40 @@ typedef struct {
     uint64_t *zeros;
 } wmat;
 
-static void wm_build(wmat *m, const uint8_t *seq, uint64_t n, uint32_t L) {
+/* seq: n symbols of `w` bytes each (1: the u8 texts of every BASELINE config; 4: wider alphabets) */
+#define WM_BUILD_BODY(T)                                                                  \
+    T *cur = (T *)malloc((n ? n : 1) * sizeof(T)), *nxt = (T *)malloc((n ? n : 1) * sizeof(T)); \
+    memcpy(cur, seq, n * sizeof(T));                                                      \
+    for (uint32_t l = 0; l < L; l++) {                                                    \
+        uint32_t sh = L - 1 - l;                                                          \
+        rs_init(&m->lv[l], n);                                                            \
+        uint64_t z = 0;                                                                   \
+        for (uint64_t i = 0; i < n; i++) {                                                \
+            if ((cur[i] >> sh) & 1) rs_setbit(&m->lv[l], i); else z++;                    \
+        }                                                                                 \
+        rs_finish(&m->lv[l]);                                                             \
+        m->zeros[l] = z;                                                                  \
+        uint64_t p0 = 0, p1 = z;                                                          \
+        for (uint64_t i = 0; i < n; i++) {                                                \
+            if ((cur[i] >> sh) & 1) nxt[p1++] = cur[i]; else nxt[p0++] = cur[i];          \
+        }                                                                                 \
+        T *tmp = cur;                                                                     \
+        cur = nxt;                                                                        \
+        nxt = tmp;                                                                        \
+    }                                                                                     \
+    free(cur);                                                                            \
+    free(nxt);
+
+static void wm_build(wmat *m, const void *seq, uint32_t w, uint64_t n, uint32_t L) {
     m->L = L;
     m->n = n;
     m->lv = (rsvec *)calloc(L, sizeof(rsvec));
     m->zeros = (uint64_t *)calloc(L, 8);
-    uint8_t *cur = (uint8_t *)malloc(n ? n : 1), *nxt = (uint8_t *)malloc(n ? n : 1);
-    memcpy(cur, seq, n);
-    for (uint32_t l = 0; l < L; l++) {
-        uint32_t sh = L - 1 - l;
-        rs_init(&m->lv[l], n);
-        uint64_t z = 0;
-        for (uint64_t i = 0; i < n; i++) {
-            if ((cur[i] >> sh) & 1) rs_setbit(&m->lv[l], i); else z++;
-        }
-        rs_finish(&m->lv[l]);
-        m->zeros[l] = z;
-        uint64_t p0 = 0, p1 = z;
-        for (uint64_t i = 0; i < n; i++) {
-            if ((cur[i] >> sh) & 1) nxt[p1++] = cur[i]; else nxt[p0++] = cur[i];
-        }
-        uint8_t *tmp = cur;
-        cur = nxt;
-        nxt = tmp;
+    if (w == 1) {
+        WM_BUILD_BODY(uint8_t)
+    } else {
+        WM_BUILD_BODY(uint32_t)
     }
-    free(cur);
-    free(nxt);
 }
 static void wm_free(wmat *m) {
     for (uint32_t l = 0; l < m->L; l++) rs_free(&m->lv[l]);
@@ -468,7 +528,7 @@ void orc_free(orc_index *x) {
  * text[a] == text[b] and suffix a+1 sorts before suffix b+1 (by its rank; the empty suffix first).
  * (1) + (2) for all i imply the order is the suffix order by induction on the suffix length.
  * returns 0 when it is.  Lets bench.py hand a GPU-built SA to the oracle without trusting it. */
-int orc_check_suffix_array(const uint8_t *text, uint64_t n, const uint64_t *sa) {
+static int check_suffix_array_view(tview text, uint64_t n, const uint64_t *sa) {
     if (n == 0) return 0;
     uint64_t *isa = (uint64_t *)malloc(n * 8);
     if (!isa) return -2;
@@ -488,8 +548,9 @@ int orc_check_suffix_array(const uint8_t *text, uint64_t n, const uint64_t *sa) 
 #pragma omp parallel for schedule(static) reduction(| : bad)
         for (int64_t i = 0; i < (int64_t)n - 1; i++) {
             uint64_t a = sa[i], b = sa[i + 1];
-            if (text[a] < text[b]) continue;
-            if (text[a] > text[b]) { bad |= 1; continue; }
+            uint64_t ca = tget(text, a), cb = tget(text, b);
+            if (ca < cb) continue;
+            if (ca > cb) { bad |= 1; continue; }
             if (a + 1 == n) continue;            /* suffix a is a proper prefix of suffix b */
             if (b + 1 == n) { bad |= 1; continue; }
             if (isa[a + 1] > isa[b + 1]) bad |= 1;
@@ -498,15 +559,25 @@ int orc_check_suffix_array(const uint8_t *text, uint64_t n, const uint64_t *sa) 
     free(isa);
     return bad ? -1 : 0;
 }
+int orc_check_suffix_array(const uint8_t *text, uint64_t n, const uint64_t *sa) {
+    tview t = {text, 1};
+    return check_suffix_array_view(t, n, sa);
+}
 
-static orc_index *build_impl(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level,
+static orc_index *build_impl(tview text, uint64_t n, uint64_t mc, int kind, int level,
                              const uint64_t *sa_in, char *err, size_t errlen) {
-    if (mc == 0 || mc > 255) {
+    if (text.w == 1 && (mc == 0 || mc > 255)) {
         set_err(err, errlen, "max_character must be in 1..=255 for u8 texts");
         return NULL;
     }
+    if (text.w != 1 && (mc == 0 || mc >= 0xFFFFFFFFull || (text.w == 2 && mc > 0xFFFF))) {
+        set_err(err, errlen, "max_character out of range for this character width (wide texts: below 2^32 - 1)");
+        return NULL;
+    }
+    /* working width of the BWT / run heads: bytes for u8 texts, u32 for everything wider */
+    const uint32_t sw = text.w == 1 ? 1u : 4u;
     for (uint64_t i = 0; i < n; i++) {
-        if (text[i] > mc) { /* sais.rs:16-18 would index out of bounds (panic) */
+        if (tget(text, i) > mc) { /* sais.rs:16-18 would index out of bounds (panic) */
             set_err(err, errlen, "text contains a character larger than max_character");
             return NULL;
         }
@@ -515,24 +586,24 @@ static orc_index *build_impl(const uint8_t *text, uint64_t n, uint64_t mc, int k
     if (sa_in) {
         /* still run the validation rules (sais.rs:128-139) */
         if (n >= 2) {
-            if (text[0] == 0) {
+            if (tget(text, 0) == 0) {
                 set_err(err, errlen, "the given text must not start with zero character");
                 free(sa);
                 return NULL;
             }
-            if (!(text[n - 1] == 0 && text[n - 2] != 0)) {
+            if (!(tget(text, n - 1) == 0 && tget(text, n - 2) != 0)) {
                 set_err(err, errlen, "the given text must end with exactly one zero character");
                 free(sa);
                 return NULL;
             }
         }
-        if (orc_check_suffix_array(text, n, sa_in) != 0) {
+        if (check_suffix_array_view(text, n, sa_in) != 0) {
             set_err(err, errlen, "the supplied array is not the suffix array of the text");
             free(sa);
             return NULL;
         }
         memcpy(sa, sa_in, n * 8);
-    } else if (orc_suffix_array(text, n, sa, err, errlen) != 0) {
+    } else if (suffix_array_view(text, n, mc, sa, err, errlen) != 0) {
         free(sa);
         return NULL;
     }
@@ -547,7 +618,7 @@ static orc_index *build_impl(const uint8_t *text, uint64_t n, uint64_t mc, int k
     if (kind == ORC_FM || kind == ORC_MULTI) {
         /* sais.rs:9-32: cs[c] = #chars < c */
         uint64_t *occ = (uint64_t *)calloc(x->cs_len, 8);
-        for (uint64_t i = 0; i < n; i++) occ[text[i]]++;
+        for (uint64_t i = 0; i < n; i++) occ[tget(text, i)]++;
         uint64_t sum = 0;
         for (uint64_t c = 0; c < x->cs_len; c++) {
             x->cs[c] = sum;
@@ -555,20 +626,20 @@ static orc_index *build_impl(const uint8_t *text, uint64_t n, uint64_t mc, int k
         }
         free(occ);
         /* fm_index.rs:44-58 / multi_pieces.rs:81-97: bw[i] = text[sa[i]-1], 0 if sa[i]==0 */
-        uint8_t *bw = (uint8_t *)calloc(n ? n : 1, 1);
+        void *bw = calloc(n ? n : 1, sw);
         for (uint64_t i = 0; i < n; i++)
-            if (sa[i] > 0) bw[i] = text[sa[i] - 1];
-        wm_build(&x->bw, bw, n, x->L);
+            if (sa[i] > 0) tput(bw, sw, i, tget(text, sa[i] - 1));
+        wm_build(&x->bw, bw, sw, n, x->L);
         free(bw);
         if (kind == ORC_MULTI) {
             /* multi_pieces.rs:53-79 */
             uint64_t zc = 0;
-            for (uint64_t i = 0; i < n; i++) zc += text[i] == 0;
+            for (uint64_t i = 0; i < n; i++) zc += tget(text, i) == 0;
             uint64_t *zeros_before = (uint64_t *)malloc((n + 1) * 8); /* rank1 of end-marker flags */
             uint64_t acc = 0;
             for (uint64_t i = 0; i < n; i++) {
                 zeros_before[i] = acc;
-                acc += text[i] == 0;
+                acc += tget(text, i) == 0;
             }
             zeros_before[n] = acc;
             x->ndoc = zc;
@@ -586,7 +657,8 @@ static orc_index *build_impl(const uint8_t *text, uint64_t n, uint64_t mc, int k
     } else {
         /* rlfmi.rs:37-96 */
         uint64_t m = x->cs_len;
-        uint8_t *heads = (uint8_t *)malloc(n ? n : 1);
+        void *heads = malloc((n ? n : 1) * sw);
+        const tview hv = {heads, sw};
         uint64_t r = 0;
         rs_init(&x->b, n);
         rs_init(&x->bp, n);
@@ -595,9 +667,9 @@ static orc_index *build_impl(const uint8_t *text, uint64_t n, uint64_t mc, int k
         uint64_t c0 = 0;
         for (uint64_t i = 0; i < n; i++) {
             uint64_t k = sa[i];
-            uint64_t c = k > 0 ? text[k - 1] : text[n - 1];
+            uint64_t c = k > 0 ? tget(text, k - 1) : tget(text, n - 1);
             if (c0 != c) {
-                heads[r] = (uint8_t)c;
+                tput(heads, sw, r, c);
                 runlen[r] = 1;
                 r++;
                 rs_setbit(&x->b, i);
@@ -616,10 +688,10 @@ static orc_index *build_impl(const uint8_t *text, uint64_t n, uint64_t mc, int k
         }
         rs_finish(&x->b);
         x->runs = r;
-        wm_build(&x->bw, heads, r, x->L);
+        wm_build(&x->bw, heads, sw, r, x->L);
         /* bp: runs grouped by head character (stable), each encoded 1 0^{len-1}; cs = #runs with head < c */
         uint64_t *cnt = (uint64_t *)calloc(m + 1, 8);
-        for (uint64_t j = 0; j < r; j++) cnt[heads[j]]++;
+        for (uint64_t j = 0; j < r; j++) cnt[tget(hv, j)]++;
         uint64_t acc = 0;
         for (uint64_t c = 0; c < m; c++) {
             x->cs[c] = acc;
@@ -627,7 +699,7 @@ static orc_index *build_impl(const uint8_t *text, uint64_t n, uint64_t mc, int k
         }
         /* start bit position of each char group in bp */
         uint64_t *len_by_c = (uint64_t *)calloc(m + 1, 8);
-        for (uint64_t j = 0; j < r; j++) len_by_c[heads[j]] += runlen[j];
+        for (uint64_t j = 0; j < r; j++) len_by_c[tget(hv, j)] += runlen[j];
         uint64_t *pos_c = (uint64_t *)calloc(m + 1, 8);
         acc = 0;
         for (uint64_t c = 0; c < m; c++) {
@@ -635,7 +707,7 @@ static orc_index *build_impl(const uint8_t *text, uint64_t n, uint64_t mc, int k
             acc += len_by_c[c];
         }
         for (uint64_t j = 0; j < r; j++) {
-            uint8_t c = heads[j];
+            uint64_t c = tget(hv, j);
             rs_setbit(&x->bp, pos_c[c]);
             pos_c[c] += runlen[j];
         }
@@ -653,11 +725,23 @@ static orc_index *build_impl(const uint8_t *text, uint64_t n, uint64_t mc, int k
 
 orc_index *orc_build(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level, char *err,
                      size_t errlen) {
-    return build_impl(text, n, mc, kind, level, NULL, err, errlen);
+    tview t = {text, 1};
+    return build_impl(t, n, mc, kind, level, NULL, err, errlen);
 }
 orc_index *orc_build_from_sa(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level,
                              const uint64_t *sa, char *err, size_t errlen) {
-    return build_impl(text, n, mc, kind, level, sa, err, errlen);
+    tview t = {text, 1};
+    return build_impl(t, n, mc, kind, level, sa, err, errlen);
+}
+/* Text<C> for C = u16 / u32 / u64 / usize (character.rs:38-42, text.rs:28-49) */
+orc_index *orc_build_w(const void *text, uint32_t char_width, uint64_t n, uint64_t mc, int kind, int level, char *err,
+                       size_t errlen) {
+    tview t = {text, char_width};
+    if (char_width != 1 && char_width != 2 && char_width != 4 && char_width != 8) {
+        set_err(err, errlen, "character width must be 1, 2, 4 or 8 bytes");
+        return NULL;
+    }
+    return build_impl(t, n, mc, kind, level, NULL, err, errlen);
 }
 
 uint64_t orc_len(const orc_index *x) { return x->n; }
@@ -774,8 +858,8 @@ uint64_t orc_piece_id(const orc_index *x, uint64_t i) {
 /* ---- wrapper.rs ---- */
 
 /* wrapper.rs:37-42, 61-82 (initial range) + 103-124 (loop) */
-int64_t orc_search(const orc_index *x, int mode, const uint8_t *pat, uint64_t m, int use_init,
-                   uint64_t init_s, uint64_t init_e, uint64_t *so, uint64_t *eo) {
+static int64_t search_view(const orc_index *x, int mode, tview pat, uint64_t m, int use_init,
+                           uint64_t init_s, uint64_t init_e, uint64_t *so, uint64_t *eo) {
     uint64_t s, e;
     if (use_init) {
         s = init_s;
@@ -786,7 +870,7 @@ int64_t orc_search(const orc_index *x, int mode, const uint8_t *pat, uint64_t m,
     }
     int64_t it = 0;
     for (uint64_t k = m; k-- > 0;) {
-        uint64_t c = pat[k];
+        uint64_t c = tget(pat, k);
         if (c > x->max_character) return -1; /* cs[c] out of bounds => panic in the reference */
         s = orc_lf_map2(x, c, s);
         e = orc_lf_map2(x, c, e);
@@ -798,6 +882,12 @@ int64_t orc_search(const orc_index *x, int mode, const uint8_t *pat, uint64_t m,
     return it;
 }
 
+int64_t orc_search(const orc_index *x, int mode, const uint8_t *pat, uint64_t m, int use_init,
+                   uint64_t init_s, uint64_t init_e, uint64_t *so, uint64_t *eo) {
+    tview t = {pat, 1};
+    return search_view(x, mode, t, m, use_init, init_s, init_e, so, eo);
+}
+
 int orc_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
@@ -806,15 +896,15 @@ int orc_max_threads(void) {
 #endif
 }
 
-int orc_search_batch(const orc_index *x, int mode, const uint8_t *pat, const uint64_t *off,
-                     uint64_t npat, const uint64_t *is, const uint64_t *ie, uint64_t *s,
-                     uint64_t *e, uint32_t *steps, int nthreads) {
+static int search_batch_view(const orc_index *x, int mode, tview pat, const uint64_t *off,
+                             uint64_t npat, const uint64_t *is, const uint64_t *ie, uint64_t *s,
+                             uint64_t *e, uint32_t *steps, int nthreads) {
     int bad = 0;
     if (nthreads <= 0) nthreads = orc_max_threads();
 #pragma omp parallel for schedule(static) num_threads(nthreads) reduction(| : bad)
     for (int64_t p = 0; p < (int64_t)npat; p++) {
-        int64_t it = orc_search(x, mode, pat + off[p], off[p + 1] - off[p], is != NULL,
-                                is ? is[p] : 0, ie ? ie[p] : 0, &s[p], &e[p]);
+        int64_t it = search_view(x, mode, tview_at(pat, off[p]), off[p + 1] - off[p], is != NULL,
+                                 is ? is[p] : 0, ie ? ie[p] : 0, &s[p], &e[p]);
         if (it < 0) {
             bad |= 1;
             it = 0;
@@ -822,6 +912,21 @@ int orc_search_batch(const orc_index *x, int mode, const uint8_t *pat, const uin
         if (steps) steps[p] = (uint32_t)it;
     }
     return bad ? -1 : 0;
+}
+
+int orc_search_batch(const orc_index *x, int mode, const uint8_t *pat, const uint64_t *off,
+                     uint64_t npat, const uint64_t *is, const uint64_t *ie, uint64_t *s,
+                     uint64_t *e, uint32_t *steps, int nthreads) {
+    tview t = {pat, 1};
+    return search_batch_view(x, mode, t, off, npat, is, ie, s, e, steps, nthreads);
+}
+
+/* patterns of u16 / u32 / u64 characters; `off` counts characters */
+int orc_search_batch_w(const orc_index *x, int mode, const void *pat, uint32_t char_width, const uint64_t *off,
+                       uint64_t npat, const uint64_t *is, const uint64_t *ie, uint64_t *s,
+                       uint64_t *e, uint32_t *steps, int nthreads) {
+    tview t = {pat, char_width};
+    return search_batch_view(x, mode, t, off, npat, is, ie, s, e, steps, nthreads);
 }
 
 int orc_locate_batch(const orc_index *x, int prefix_only, const uint64_t *s, const uint64_t *e,
@@ -867,28 +972,39 @@ int orc_locate_batch(const orc_index *x, int prefix_only, const uint64_t *s, con
 
 /* wrapper.rs:154-161 (backward: c = get_l(i); i = lf_map(i)) and :175-183
  * (forward: c = get_f(i); i = fl_map(i)?; yield c) */
-void orc_extract_batch(const orc_index *x, const uint64_t *rows, uint64_t nrows, uint32_t k,
-                       int forward, uint8_t *out, uint32_t *out_len, int nthreads) {
+static void extract_batch_w(const orc_index *x, const uint64_t *rows, uint64_t nrows, uint32_t k,
+                            int forward, void *out, uint32_t w, uint32_t *out_len, int nthreads) {
     if (nthreads <= 0) nthreads = orc_max_threads();
 #pragma omp parallel for schedule(static) num_threads(nthreads)
     for (int64_t r = 0; r < (int64_t)nrows; r++) {
         uint64_t i = rows[r];
-        uint8_t *o = out + (uint64_t)r * k;
+        uint8_t *o = (uint8_t *)out + (uint64_t)r * k * w;
         uint32_t got = 0;
-        memset(o, 0, k);
+        memset(o, 0, (size_t)k * w);
         for (uint32_t t = 0; t < k; t++) {
             if (!forward) {
-                o[t] = (uint8_t)orc_get_l(x, i);
+                tput(o, w, t, orc_get_l(x, i));
                 i = orc_lf_map(x, i);
             } else {
                 uint64_t c = orc_get_f(x, i);
                 uint64_t nx = orc_fl_map(x, i);
                 if (nx == ORC_NONE) break;
                 i = nx;
-                o[t] = (uint8_t)c;
+                tput(o, w, t, c);
             }
             got++;
         }
         if (out_len) out_len[r] = got;
     }
+}
+
+void orc_extract_batch(const orc_index *x, const uint64_t *rows, uint64_t nrows, uint32_t k,
+                       int forward, uint8_t *out, uint32_t *out_len, int nthreads) {
+    extract_batch_w(x, rows, nrows, k, forward, out, 1, out_len, nthreads);
+}
+
+/* the same with characters of char_width bytes in `out` (k characters per row) */
+void orc_extract_batch_w(const orc_index *x, const uint64_t *rows, uint64_t nrows, uint32_t k,
+                         int forward, void *out, uint32_t char_width, uint32_t *out_len, int nthreads) {
+    extract_batch_w(x, rows, nrows, k, forward, out, char_width, out_len, nthreads);
 }

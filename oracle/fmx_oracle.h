@@ -111,6 +111,20 @@ void orc_extract_batch(const orc_index *idx, const uint64_t *rows, uint64_t nrow
 
 int orc_max_threads(void);
 
+/* ---- texts and patterns of wider characters (character.rs:24-42: u16, u32, u64, usize) ----
+ * char_width = bytes per character (2, 4 or 8; 1 gives the u8 entry points above); every character and
+ * max_character must be below 2^32 - 1 (the reference allocates max_character + 1 counters, sais.rs:9-19).
+ * Offsets count characters.  Everything else (locate, primitives, accessors) is shared with the u8 index. */
+orc_index *orc_build_w(const void *text, uint32_t char_width, uint64_t n, uint64_t max_character, int kind, int level,
+                       char *err, size_t errlen);
+int orc_suffix_array_w(const void *text, uint32_t char_width, uint64_t n, uint64_t max_character, uint64_t *sa, char *err,
+                       size_t errlen);
+int orc_search_batch_w(const orc_index *idx, int mode, const void *pat, uint32_t char_width, const uint64_t *off,
+                       uint64_t npat, const uint64_t *init_s, const uint64_t *init_e, uint64_t *s, uint64_t *e,
+                       uint32_t *steps, int nthreads);
+void orc_extract_batch_w(const orc_index *idx, const uint64_t *rows, uint64_t nrows, uint32_t k, int forward, void *out,
+                         uint32_t char_width, uint32_t *out_len, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,6 +81,14 @@ def lib():
     L.orc_extract_batch.restype = None
     L.orc_extract_batch.argtypes = [vp, vp, u64, C.c_uint32, C.c_int, vp, vp, C.c_int]
     L.orc_max_threads.restype = C.c_int
+    L.orc_build_w.restype = vp
+    L.orc_build_w.argtypes = [vp, C.c_uint32, u64, u64, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
+    L.orc_suffix_array_w.restype = C.c_int
+    L.orc_suffix_array_w.argtypes = [vp, C.c_uint32, u64, u64, vp, C.c_char_p, C.c_size_t]
+    L.orc_search_batch_w.restype = C.c_int
+    L.orc_search_batch_w.argtypes = [vp, C.c_int, vp, C.c_uint32, vp, u64, vp, vp, vp, vp, vp, C.c_int]
+    L.orc_extract_batch_w.restype = None
+    L.orc_extract_batch_w.argtypes = [vp, vp, u64, C.c_uint32, C.c_int, vp, C.c_uint32, vp, C.c_int]
     _lib = L
     return L
 
@@ -97,21 +105,44 @@ def _as_u8(x) -> np.ndarray:
     return np.ascontiguousarray(np.asarray(x, dtype=np.uint8))
 
 
-def pack_patterns(patterns):
-    """list of byte strings -> (flat u8 array, u64 offsets[npat+1])."""
-    arrs = [_as_u8(p) for p in patterns]
+WIDE_DTYPES = (np.uint16, np.uint32, np.uint64)   # character.rs:38-42 (usize = u64)
+
+
+def _char_dtype(x):
+    """numpy dtype of a text / pattern: the array's own when it is one of the wide character types, else u8"""
+    dt = getattr(x, "dtype", None)
+    if dt is not None and np.dtype(dt) in [np.dtype(d) for d in WIDE_DTYPES]:
+        return np.dtype(dt)
+    return np.dtype(np.uint8)
+
+
+def _as_chars(x, dtype) -> np.ndarray:
+    dtype = np.dtype(dtype)
+    if dtype == np.uint8:
+        return _as_u8(x)
+    return np.ascontiguousarray(np.asarray(x, dtype=dtype))
+
+
+def pack_patterns(patterns, dtype=np.uint8):
+    """list of patterns -> (flat character array, u64 offsets[npat+1] in characters)."""
+    arrs = [_as_chars(p, dtype) for p in patterns]
     off = np.zeros(len(arrs) + 1, dtype=np.uint64)
     if arrs:
         off[1:] = np.cumsum([a.size for a in arrs], dtype=np.uint64)
-    flat = np.concatenate(arrs) if arrs and off[-1] > 0 else np.zeros(0, dtype=np.uint8)
+    flat = np.concatenate(arrs) if arrs and off[-1] > 0 else np.zeros(0, dtype=dtype)
     return np.ascontiguousarray(flat), off
 
 
-def suffix_array(text) -> np.ndarray:
-    t = _as_u8(text)
+def suffix_array(text, max_character=None) -> np.ndarray:
+    dt = _char_dtype(text)
+    t = _as_chars(text, dt)
     sa = np.zeros(max(t.size, 1), dtype=np.uint64)
     err = C.create_string_buffer(256)
-    rc = lib().orc_suffix_array(t.ctypes.data, t.size, sa.ctypes.data, err, 256)
+    if dt == np.uint8:
+        rc = lib().orc_suffix_array(t.ctypes.data, t.size, sa.ctypes.data, err, 256)
+    else:
+        mc = int(t.max()) if max_character is None and t.size else int(max_character or 1)
+        rc = lib().orc_suffix_array_w(t.ctypes.data, dt.itemsize, t.size, mc, sa.ctypes.data, err, 256)
     if rc != 0:
         raise InvalidText(err.value.decode())
     return sa[: t.size]
@@ -130,11 +161,16 @@ class OracleIndex:
     """One of the reference's six index types, by (kind, level)."""
 
     def __init__(self, text, kind=FM, level=None, max_character=255, sa=None):
-        self._t = _as_u8(text)
+        self.dtype = _char_dtype(text)   # u8 unless the text is a numpy array of u16 / u32 / u64 characters
+        self._t = _as_chars(text, self.dtype)
         self.kind = kind
         err = C.create_string_buffer(256)
         lvl = -1 if level is None else int(level)
-        if sa is None:
+        if self.dtype != np.uint8:
+            if sa is not None:
+                raise ValueError("a supplied suffix array is only taken for u8 texts")
+            h = lib().orc_build_w(self._t.ctypes.data, self.dtype.itemsize, self._t.size, max_character, kind, lvl, err, 256)
+        elif sa is None:
             h = lib().orc_build(self._t.ctypes.data, self._t.size, max_character, kind, lvl, err, 256)
         else:
             sa = np.ascontiguousarray(sa, dtype=np.uint64)
@@ -192,6 +228,11 @@ class OracleIndex:
 
     # ---- wrapper.rs
     def search(self, pattern, mode=SEARCH, init=None):
+        if self.dtype != np.uint8:
+            p = _as_chars(pattern, self.dtype)
+            s, e = self.search_batch(p, np.array([0, p.size], dtype=np.uint64), mode,
+                                     None if init is None else [init[0]], None if init is None else [init[1]])
+            return int(s[0]), int(e[0])
         p = _as_u8(pattern)
         s, e = C.c_uint64(0), C.c_uint64(0)
         it = lib().orc_search(self._h, mode, p.ctypes.data, p.size, init is not None,
@@ -201,13 +242,18 @@ class OracleIndex:
         return s.value, e.value
 
     def search_batch(self, flat, off, mode=SEARCH, init_s=None, init_e=None, nthreads=0, want_steps=False):
-        flat = np.ascontiguousarray(flat, dtype=np.uint8)
+        flat = np.ascontiguousarray(flat, dtype=self.dtype)
         off = np.ascontiguousarray(off, dtype=np.uint64)
         npat = off.size - 1
         s = np.zeros(npat, dtype=np.uint64)
         e = np.zeros(npat, dtype=np.uint64)
         steps = np.zeros(npat, dtype=np.uint32) if want_steps else None
-        rc = lib().orc_search_batch(
+        if self.dtype != np.uint8:
+            def call(*a):
+                return lib().orc_search_batch_w(a[0], a[1], a[2], self.dtype.itemsize, *a[3:])
+        else:
+            call = lib().orc_search_batch
+        rc = call(
             self._h, mode, flat.ctypes.data, off.ctypes.data, npat,
             None if init_s is None else np.ascontiguousarray(init_s, dtype=np.uint64).ctypes.data,
             None if init_e is None else np.ascontiguousarray(init_e, dtype=np.uint64).ctypes.data,
@@ -236,10 +282,10 @@ class OracleIndex:
 
     def extract_batch(self, rows, k, forward, nthreads=0):
         rows = np.ascontiguousarray(rows, dtype=np.uint64)
-        out = np.zeros((rows.size, k), dtype=np.uint8)
+        out = np.zeros((rows.size, k), dtype=self.dtype)
         out_len = np.zeros(rows.size, dtype=np.uint32)
-        lib().orc_extract_batch(self._h, rows.ctypes.data, rows.size, k, int(forward), out.ctypes.data,
-                                out_len.ctypes.data, nthreads)
+        lib().orc_extract_batch_w(self._h, rows.ctypes.data, rows.size, k, int(forward), out.ctypes.data,
+                                  self.dtype.itemsize, out_len.ctypes.data, nthreads)
         return out, out_len
 
     # convenience mirroring the crate's Search/Match use in its tests

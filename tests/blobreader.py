@@ -5,7 +5,7 @@ import struct
 import numpy as np
 
 SEC_LEVEL0, SEC_ADJ, SEC_CS, SEC_SA, SEC_DOC, SEC_PIECE_END, SEC_RL_B, SEC_RL_BP, SEC_RL_BSEL, SEC_RL_BPSEL, SEC_EXC, SEC_TEXT, SEC_ISA, \
-    SEC_VSA, SEC_COUNT = 0, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21
+    SEC_VSA, SEC_WZEROS, SEC_COUNT = 0, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22
 RB_BITS = 192
 M32 = 0xFFFFFFFF
 
@@ -41,11 +41,18 @@ class Blob:
         o += 16 * SEC_COUNT
         self.layout, self.nexc, self.qlevels, self.sym_nblk = struct.unpack_from("<IIII", raw, o)
         o += 16
-        self.verify, self.isa_level, self.vsa_level, _ = struct.unpack_from("<IIII", raw, o)
+        self.verify, self.isa_level, self.vsa_level, self.char_width = struct.unpack_from("<IIII", raw, o)
         o += 16
         self.qoff = [struct.unpack_from("<4Q", raw, o + 32 * l) for l in range(4)]
         assert self.total_bytes == len(raw)
-        if self.layout == 3:
+        if self.layout == 4:   # WIDE: all levels in SEC_LEVEL0, zeros per level in SEC_WZEROS, cs / adj of max_character + 1 words
+            nblk = self.seq_len // RB_BITS + 1
+            all_lv = self._sec(SEC_LEVEL0)
+            assert len(all_lv) == self.levels * nblk * 32
+            self.lv = [RBVec(all_lv[l * nblk * 32:(l + 1) * nblk * 32]) for l in range(self.levels)]
+            self.zeros = [int(v) for v in np.frombuffer(self._sec(SEC_WZEROS), dtype=np.uint32)]
+            assert len(self.zeros) == self.levels and self.char_width in (2, 4, 8) and self.max_character > 255
+        elif self.layout == 3:
             assert self.sym_nblk == self.seq_len // RB_BITS + 1
             allv = np.frombuffer(self._sec(SEC_LEVEL0), dtype=np.uint32).reshape(self.cs_len, self.sym_nblk, 8)
             self.symv = [RBVec(allv[c].tobytes()) for c in range(self.cs_len)]
@@ -110,6 +117,8 @@ class Blob:
             return int(self.cs[c]) + self.symv[c].rank1(i)
         if self.layout == 1:
             return int(self.cs[c]) + self.q4_rank(i, c)
+        if self.layout == 4 and int(self.cs[c + 1]) == int(self.cs[c]):   # a symbol that does not occur (kernels.cuh sym_absent)
+            return int(self.cs[c])
         return (int(self.adj[c]) + self.walk(c, i)) & M32
 
     def seq_access_lf(self, i):

@@ -1142,3 +1142,99 @@ def test_partitioned_cuda_engine_and_merge_kernel():
         bad = pats.copy()
         bad[0, 0] = 0
         idx.search_locate(torch.from_numpy(bad))
+
+
+# ---- texts of wide characters (character.rs:38-42): u16 / u32 / u64, WIDE layout (max_character > 255) and the u8
+# layouts behind wide patterns (max_character <= 255); every entry point against the oracle
+def _wide_text(rng, n, mc, dtype, multi, nsym=40):
+    used = np.unique(np.concatenate([rng.integers(1, mc + 1, nsym), [mc]]))
+    body = rng.choice(used, n)
+    if multi:
+        body[rng.integers(2, n - 2, max(1, n // 400)) // 2 * 2] = 0
+    return np.append(body, 0).astype(dtype)
+
+
+@pytest.mark.parametrize("kind", [orc.FM, orc.RLFM, orc.MULTI])
+@pytest.mark.parametrize("dtype,mc", [(np.uint16, 4), (np.uint16, 300), (np.uint16, 65535), (np.uint32, 5_000_011), (np.uint64, 70_000)])
+def test_wide_character_texts(kind, dtype, mc, tmp_path):
+    rng = np.random.default_rng(kind * 31 + mc % 101)
+    multi = kind == orc.MULTI
+    n = 40_000
+    text = _wide_text(rng, n, mc, dtype, multi, nsym=3 if mc == 4 else 40)
+    level = 2
+    index = KINDS[kind][1].new(fmx.Text.with_max_character(text, mc), level)
+    oracle = orc.OracleIndex(text, kind, level=level, max_character=mc)
+    assert index.len() == text.size and index.layout_name().startswith("WIDE" if mc > 255 else "Q4")
+    pats = []
+    for t in range(3000):
+        m = int(rng.integers(1, 12))
+        p0 = int(rng.integers(0, n - m))
+        p = text[p0:p0 + m].copy() if t % 3 else rng.integers(1, mc + 1, m).astype(dtype)
+        if t % 7 == 0 and m > 2:
+            p[int(rng.integers(0, m))] = rng.integers(1, mc + 1)       # a mismatch, often a symbol that never occurs
+        if not multi and 0 in p:
+            continue
+        pats.append(p)
+    flat, off = orc.pack_patterns(pats, dtype)
+    modes = [fmx.SEARCH] + ([fmx.SEARCH_PREFIX, fmx.SEARCH_SUFFIX, fmx.SEARCH_EXACT] if multi else [])
+    for mode in modes:
+        b = index.search_batch((flat, off), mode)
+        os_, oe = oracle.search_batch(flat, off, mode)
+        assert np.array_equal(b.s, os_) and np.array_equal(b.e, oe)
+        po = mode in (fmx.SEARCH_PREFIX, fmx.SEARCH_EXACT)
+        if multi:
+            hoff, pos, pid = b.locate(piece_ids=True)
+            ooff, opos, opid = oracle.locate_batch(os_, oe, prefix_only=po, want_piece_ids=True)
+            assert np.array_equal(pid, opid)
+        else:
+            hoff, pos = b.locate()
+            ooff, opos, _ = oracle.locate_batch(os_, oe, prefix_only=po)
+        assert np.array_equal(hoff, ooff) and np.array_equal(pos, opos)         # order included
+        r = index.query_batch((flat, off), mode, rows=True, counts=True, locate=True, width=4)
+        assert np.array_equal(r["s"], os_) and np.array_equal(r["e"], oe)
+        assert np.array_equal(r["hit_off"], ooff) and np.array_equal(r["positions"], opos)
+        fb, fh, fp = index.search_locate_batch((flat, off), mode)[:3]
+        assert np.array_equal(fh, ooff) and np.array_equal(fp, opos)
+    # fixed-length patterns, refinement, the Search / Match objects
+    fixed = np.stack([text[i:i + 8] for i in rng.integers(0, n - 8, 500)])
+    fixed = fixed[~(fixed == 0).any(axis=1)] if not multi else fixed
+    fb = index.search_batch(fixed)
+    fs, fe = oracle.search_batch(fixed.reshape(-1), np.arange(fixed.shape[0] + 1, dtype=np.uint64) * 8)
+    assert np.array_equal(fb.s, fs) and np.array_equal(fb.e, fe)
+    head, tail = fixed[:, :3], fixed[:, 3:]
+    rb = index.search_batch(tail).search_batch(head)                             # Search::search refines by prepending
+    assert np.array_equal(rb.s, fs) and np.array_equal(rb.e, fe)
+    one = index.search(fixed[0])
+    assert one.count() == int(fe[0] - fs[0])
+    m0 = next(iter(one.iter_matches()))
+    assert m0.locate() == oracle.get_sa(int(fs[0]))
+    got = [c for _, c in zip(range(8), m0.iter_chars_forward())]
+    assert got[:len(fixed[0])] == [int(c) for c in fixed[0]][:len(got)]
+    # primitives and extraction, in the text's character width
+    rows = rng.integers(0, text.size, 400).astype(np.uint64)
+    assert list(index.rows_op(0, rows)) == [oracle.get_l(int(i)) for i in rows]
+    assert list(index.rows_op(1, rows)) == [oracle.lf_map(int(i)) for i in rows]
+    assert list(index.rows_op(2, rows)) == [oracle.get_f(int(i)) for i in rows]
+    assert list(index.rows_op(3, rows)) == [(1 << 64) - 1 if oracle.fl_map(int(i)) is None else oracle.fl_map(int(i)) for i in rows]
+    assert list(index.rows_op(4, rows)) == [oracle.get_sa(int(i)) for i in rows]
+    cs_, is_ = [], []
+    for c in [int(v) for v in np.unique(text)[:20]] + [mc, 1]:
+        for i in list(rng.integers(0, text.size + 1, 40)) + [0, text.size]:
+            cs_.append(c)
+            is_.append(int(i))
+    assert list(index.lf_map2_batch(cs_, is_)) == [oracle.lf_map2(c, i) for c, i in zip(cs_, is_)]
+    for fwd in (False, True):
+        out, ln = index.extract_batch(rows, 21, fwd)
+        oout, oln = oracle.extract_batch(rows, 21, fwd)
+        assert out.dtype == np.dtype(dtype) and np.array_equal(ln, oln) and np.array_equal(out, oout)
+    # a character above max_character is the reference's panic (fm_index.rs:94)
+    if mc < np.iinfo(dtype).max:
+        with pytest.raises(IndexError):
+            index.search_batch([np.array([int(text[0]), mc + 1], dtype=dtype)])
+    # save / load keeps the character width
+    p = tmp_path / "wide.fmx"
+    index.save(p)
+    again = KINDS[kind][1].load(p)
+    lb = again.search_batch((flat, off))
+    os_, oe = oracle.search_batch(flat, off)
+    assert again._dtype == np.dtype(dtype) and np.array_equal(lb.s, os_) and np.array_equal(lb.e, oe)

@@ -196,3 +196,94 @@ def test_verify_structures_and_tail_logic(mc, level, kind, dense, monkeypatch):
             os_, oe, osteps = o.search_batch(*orc.pack_patterns([bytes(pat)]), mode, want_steps=True)
             assert (s, e) == (int(os_[0]), int(oe[0])), (t, variant, mode)
             assert it == int(osteps[0]), (t, variant, mode)
+
+
+# ---- texts of wide characters (character.rs:38-42: u16 / u32 / u64 / usize)
+
+def _wide_text(rng, n, mc, dtype, multi):
+    """random text over 1..=mc (a small set of symbols actually used, so patterns recur), \\0 pieces when multi"""
+    used = np.unique(np.concatenate([rng.integers(1, mc + 1, 12), [mc]]))
+    body = rng.choice(used, n)
+    if multi:
+        body[rng.integers(2, n - 2, max(1, n // 60)) // 2 * 2] = 0   # never two \0 in a row, none at either end
+    return np.append(body, 0).astype(dtype)
+
+
+def test_oracle_wide_characters_are_pinned_to_the_u8_oracle():
+    """The reference holds no wide-character vectors; the oracle's wide path is pinned to its own u8 path (which the
+    reference's golden vectors pin, test_oracle_golden.py): the same text widened gives the same index, answer for answer."""
+    rng = np.random.default_rng(11)
+    for kind in (orc.FM, orc.RLFM, orc.MULTI):
+        t8 = np.frombuffer(build_text(rng, 1500, 7, kind == orc.MULTI), dtype=np.uint8)
+        a = orc.OracleIndex(t8, kind, 2, max_character=255)
+        pats = [t8[i:i + int(rng.integers(1, 7))] for i in rng.integers(0, 1400, 150)]
+        pats = [p for p in pats if 0 not in p or kind == orc.MULTI]
+        f, o = orc.pack_patterns(pats)
+        for dt in (np.uint16, np.uint32, np.uint64):
+            b = orc.OracleIndex(t8.astype(dt), kind, 2, max_character=255)
+            s1, e1, st1 = a.search_batch(f, o, want_steps=True)
+            s2, e2, st2 = b.search_batch(f.astype(dt), o, want_steps=True)
+            assert np.array_equal(s1, s2) and np.array_equal(e1, e2) and np.array_equal(st1, st2)
+            assert np.array_equal(a.locate_batch(s1, e1)[1], b.locate_batch(s2, e2)[1])
+            for fwd in (False, True):
+                x1, l1 = a.extract_batch(np.arange(0, 1500, 7), 9, fwd)
+                x2, l2 = b.extract_batch(np.arange(0, 1500, 7), 9, fwd)
+                assert x2.dtype == dt and np.array_equal(x1, x2) and np.array_equal(l1, l2)
+            assert np.array_equal(orc.suffix_array(t8), orc.suffix_array(t8.astype(dt)))
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+@pytest.mark.parametrize("dtype,mc", [(np.uint16, 300), (np.uint16, 65535), (np.uint32, 1_000_003), (np.uint64, 70_000)])
+def test_wide_blob_matches_oracle(kind, dtype, mc):
+    """max_character > 255: the WIDE layout (all levels in one section, cs / adj of max_character + 1 words),
+    read back on the CPU against the oracle: primitives, walks to the samples, searches in every mode"""
+    rng = np.random.default_rng(kind * 10 + mc % 97)
+    n = 900
+    text = _wide_text(rng, n, mc, dtype, kind == 2)
+    level = int(rng.integers(0, 4))
+    o = orc.OracleIndex(text, kind, level=level, max_character=mc)
+    b = Blob(fmx.blob_build(fmx.Text.with_max_character(text, mc), kind, level))
+    n = text.size
+    assert (b.n, b.kind, b.levels, b.cs_len, b.layout, b.char_width) == (n, kind, int(mc).bit_length(), mc + 1, 4, np.dtype(dtype).itemsize)
+    assert not b.verify and b.sa_level == orc.lib().orc_sample_level(o._h)
+    assert np.array_equal(fmx.suffix_array(text), orc.suffix_array(text, mc))
+    rows = [int(v) for v in rng.integers(0, n, 150)] + [0, n - 1]
+    for i in rows:
+        c, nx = b.lf_step(i)
+        assert c == o.get_l(i) and nx == o.lf_map(i)
+        assert b.get_sa(i) == o.get_sa(i)
+    present = [int(c) for c in np.unique(text)]
+    absent = [c for c in (1, 2, mc - 1, mc, present[1] + 1) if c not in present and c <= mc]
+    for c in present + absent:
+        for i in rows[:40] + [n]:
+            assert b.lf_map2(c, i) == o.lf_map2(c, i), (c, i)
+    for _ in range(60):
+        m = int(rng.integers(1, 6))
+        p0 = int(rng.integers(0, n - m))
+        pat = text[p0:p0 + m] if rng.random() < 0.7 else rng.integers(1, mc + 1, m).astype(dtype)
+        if kind != 2 and 0 in pat:
+            continue
+        for mode in ((0, 1, 2, 3) if kind == 2 else (0,)):
+            assert b.search([int(c) for c in pat], mode) == o.search(pat, mode)
+    if kind == 2:
+        assert b.ndoc == o.pieces_count() and b.first_row == orc.lib().orc_first_row(o._h)
+        assert [int(v) for v in b.doc] == [orc.lib().orc_doc(o._h, k) for k in range(b.ndoc)]
+
+
+def test_wide_characters_over_a_small_alphabet_take_the_u8_layouts():
+    """u16 / u32 / u64 texts with max_character <= 255: narrowed, same blob as the u8 text except the header's char_width"""
+    rng = np.random.default_rng(5)
+    t8 = np.frombuffer(build_text(rng, 3000, 4, False), dtype=np.uint8)
+    ref = fmx.blob_build(fmx.Text.with_max_character(t8, 4), 0, 2, mode=fmx.MODE_COMPACT)
+    for dt in (np.uint16, np.uint32, np.uint64):
+        w = fmx.blob_build(fmx.Text.with_max_character(t8.astype(dt), 4), 0, 2)
+        bw = Blob(w)
+        assert bw.char_width == np.dtype(dt).itemsize and bw.layout == 1 and not bw.verify
+        diff = np.nonzero(w != ref)[0]
+        assert diff.size <= 1      # the char_width field of the header only
+    with pytest.raises(fmx.Error, match="larger than max_character"):
+        fmx.blob_build(fmx.Text.with_max_character(np.array([1, 300, 2, 0], dtype=np.uint16), 255), 0, 2)
+    with pytest.raises(fmx.InvalidText, match="must end with exactly one zero"):
+        fmx.blob_build(fmx.Text.with_max_character(np.array([1, 300, 2], dtype=np.uint16), 300), 0, 2)
+    with pytest.raises(fmx.Error, match="out of range"):
+        fmx.blob_build(fmx.Text.new(np.array([1, 300, 2, 0], dtype=np.uint32)), 0, 2)   # Text::new on u32: C::max_value()

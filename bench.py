@@ -552,6 +552,8 @@ def main():
     ap.add_argument("--no-gather-peak", action="store_true")
     ap.add_argument("--no-compact", action="store_true", help="skip the compact-mode index measured beside the headline one")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extract", action="store_true", help="skip the extraction (iter_chars_*) measurement")
+    ap.add_argument("--extract-rows", type=int, default=4_000_000)
     ap.add_argument("--no-by-piece", action="store_true", help="N > 1 default run: skip the config-4 piece-partitioned measurement")
     ap.add_argument("--oracle-own-sa", action="store_true",
                     help="CPU baseline: build the suffix array with the oracle's own SA-IS even for GB-scale texts")
@@ -695,6 +697,14 @@ def main():
     roofline = roofline_block(args, w, index, mode_name, npat, hits, ms_per_step, ms_count, phase_ms, dominant, search_steps,
                               lf_steps, req_search, req_emit, peak, peak_src, gp)
 
+    # ---- extraction walks (wrapper.rs:143-183) from random rows of the same index
+    extraction = None
+    if not args.no_extract and world == 1:
+        try:
+            extraction = extraction_measure(args, L, index, int(text.size), int(mc).bit_length(), flush, stream, gp)
+        except Exception as ex:  # pragma: no cover
+            extraction = {"error": str(ex)[:300]}
+
     # ---- the same batch on a COMPACT index (reference-sized: rank structure + samples + L2-resident table)
     compact = None
     if not args.no_compact and mode_name == "rich" and world == 1:
@@ -732,6 +742,8 @@ def main():
     }
     if e2e is not None:
         line["e2e"] = e2e
+    if extraction is not None:
+        line["extraction"] = extraction
     if compact is not None:
         line["compact_mode"] = compact
     if by_piece is not None:
@@ -951,6 +963,78 @@ def e2e_measure(args, fmx, L, index, d_pat, d_off, m, npat, hits, mc, world, dis
     out["api"] = best_api + " (pinned buffers; chunked H2D / kernels / D2H pipeline, one host wait per chunk)"
     out["_bytes_form_results"] = keep
     return out
+
+
+def extraction_measure(args, L, index, n, Lw, flush, stream, gp, k=32):
+    """Match::iter_chars_backward / iter_chars_forward taken k characters deep from random rows (fmx_extract_batch_device).
+    Two kernels answer it: k_extract_text (HBM-rich indexes: characters read from the text at SA[row]) and k_extract
+    (every index: one LF step per character backward, one FL step = C-array search + select forward).  Both are timed on
+    this index when it holds the text; results are compared byte for byte."""
+    import torch
+
+    h = index._h
+    sp = C.c_void_p(stream.cuda_stream)
+    nrows = int(min(args.extract_rows, max(1, n)))
+    g = torch.Generator(device="cuda")
+    g.manual_seed(4242)
+    d_rows = torch.randint(0, n, (nrows,), generator=g, device="cuda", dtype=torch.int64)
+    outs = {}
+
+    def run(forward, d_out, d_len):
+        rc = L.fmx_extract_batch_device(h, d_rows.data_ptr(), nrows, k, int(forward), d_out.data_ptr(), d_len.data_ptr(), sp)
+        if rc != 0:
+            raise RuntimeError(L.fmx_last_error().decode())
+
+    def timed(forward, reps=5):
+        d_out = torch.empty((nrows, k), dtype=torch.uint8, device="cuda")
+        d_len = torch.empty(nrows, dtype=torch.int32, device="cuda")
+        run(forward, d_out, d_len)
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            run(forward, d_out, d_len)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        return float(np.mean(ms)), d_out, d_len
+
+    res = {"rows": nrows, "chars_per_row": k,
+           "algorithmic_bytes_per_char": {"backward": 32 * Lw, "forward": 32 * Lw,
+                                          "note": "SURVEY.md 8(d): one sector per wavelet level per character"}}
+    variants = [("walk", 0)]
+    has_text = False
+    try:
+        index.set_option("extract_text", 1)
+        has_text = index.mode() == 2 or bool(L.fmx_index_has_text(h))
+    except Exception:
+        has_text = False
+    if has_text:
+        variants.append(("text", 1))
+    for name, opt in variants:
+        index.set_option("extract_text", opt)
+        v = {}
+        for forward in (False, True):
+            ms, d_out, d_len = timed(forward)
+            chars = int(d_len.sum().item())
+            key = "forward" if forward else "backward"
+            v[key] = {"ms": ms, "chars_per_s": chars / (ms * 1e-3), "rows_per_s": nrows / (ms * 1e-3)}
+            outs[(name, forward)] = (d_out, d_len)
+        res["k_extract_text (text at SA[row])" if name == "text" else "k_extract (LF / FL steps)"] = v
+    index.set_option("extract_text", 1)
+    if has_text:
+        res["same_characters_both_kernels"] = bool(all(
+            torch.equal(outs[("walk", f)][0], outs[("text", f)][0]) and torch.equal(outs[("walk", f)][1], outs[("text", f)][1])
+            for f in (False, True)))
+        # hardware view of the text kernel: one suffix-array request + the text sectors of k characters per row
+        ms = res["k_extract_text (text at SA[row])"]["backward"]["ms"]
+        req = nrows * (1 + (k + 31 + 31) // 32)
+        res["text_kernel_requests_per_s_upper_bound"] = req / (ms * 1e-3)
+        if gp:
+            res["text_kernel_frac_of_random_request_peak"] = req / (ms * 1e-3) / gp
+    return res
 
 
 def compact_measure(args, fmx, L, cls, text, mc, level, local, d_pat, d_off, m, npat, stream, flush, rich_run, gp):

@@ -40,6 +40,7 @@ SIGNATURES = {
     "fmx_index_kmer_k": (_u32, [_vp, _int]),
     "fmx_index_layout": (_u32, [_vp]),
     "fmx_index_char_width": (_u32, [_vp]),
+    "fmx_index_has_text": (_int, [_vp]),
     "fmx_search_batch": (_int, [_vp, _int, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp]),
     "fmx_search_batch_device": (_int, [_vp, _int, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _vp, _vp]),
     "fmx_search_check": (_int, [_vp, _vp]),

@@ -8,6 +8,7 @@
 #include "builder.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -319,11 +320,19 @@ static bool force_binary_wavelet() {
     return force && force[0] && force[0] != '0';
 }
 
+// Free memory of the device the index is being built for (0 = unknown / host-only build): the HBM-for-requests trades
+// below are sized for a B200's 180 GB and shrink with it on a smaller device instead of failing with FMX_ERR_OOM.
+static std::atomic<uint64_t> g_device_free_hint{0};
+void set_device_memory_hint(uint64_t free_bytes) { g_device_free_hint.store(free_bytes); }
+
 // Per-symbol RB192 bit vectors (fmx_layout.h "SYM"), built in place inside the blob.
 static uint64_t sym_budget_bytes() {
     const char *e = std::getenv("FMX_SYM_BUDGET_MB");
     if (e && e[0]) return (uint64_t)std::strtoull(e, nullptr, 10) << 20;
-    return 49152ull << 20;
+    uint64_t b = 49152ull << 20;
+    const uint64_t hint = g_device_free_hint.load();
+    if (hint && b > hint / 100 * 45) b = hint / 100 * 45;
+    return b;
 }
 static uint64_t sym_bytes(uint64_t cs_len, uint64_t n) { return cs_len * (n / FMX_RB_BITS + 1) * 32; }
 static void sym_build(const uint8_t *seq, uint64_t n, uint32_t cs_len, uint32_t *dst) {
@@ -424,6 +433,7 @@ VerifyPlan plan_verify(int kind, uint64_t n, int mode, int level, bool interior_
     if (nv && nv[0] && nv[0] != '0') verify = false;
     if (mode == FMX_MODE_COMPACT || interior_zero) verify = false;
     uint64_t budget = 32768ull << 20;
+    if (const uint64_t hint = g_device_free_hint.load()) budget = std::min<uint64_t>(budget, hint / 4);
     if (const char *vb = std::getenv("FMX_VERIFY_BUDGET_MB")) budget = std::strtoull(vb, nullptr, 10) << 20;
     // an index whose rank structure sits in the 126 MB L2 answers a step from L2; the tail's three or four
     // DRAM reads are slower than that (measured on the 100 MB DNA config), so it is not built there
@@ -453,6 +463,9 @@ void layout_sections(FmxBlobHeader &hdr, const uint64_t bytes[SEC_COUNT]) {
 }
 
 bool q4_forbidden_by_env() { return force_binary_wavelet(); }
+// SYM is the layout of a sequence of `len` symbols over cs_len table entries that Q4 does not take
+bool sym_layout_chosen(uint64_t cs_len, uint64_t len) { return !force_binary_wavelet() && sym_bytes(cs_len, len) + len <= sym_budget_bytes(); }
+uint64_t sym_layout_bytes(uint64_t cs_len, uint64_t len) { return sym_bytes(cs_len, len); }
 
 int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level,
                HostBlob &blob, std::string &err, int sa_device, int mode) {
@@ -712,6 +725,8 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
     if (verify) {
         sec[SEC_TEXT] = {text, n};
         sec[SEC_ISA] = {isa_s.data(), isa_s.size() * 4};
+    } else if (dense_sa) {
+        sec[SEC_TEXT] = {text, n};  // RLFM in the HBM-rich mode: extraction reads the text at SA[row] (k_extract_text)
     }
     if (dense_sa) sec[SEC_VSA] = {sa.data(), sa.size() * 4};
     if (!doc.empty()) sec[SEC_DOC] = {doc.data(), doc.size() * 4};

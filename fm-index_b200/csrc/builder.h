@@ -44,15 +44,19 @@ struct VerifyPlan {
     bool verify = false, dense = false, dense_sa = false;
     uint32_t isa_level = 0;
 };
+// free bytes of the device being built for (0 = none): clamps the SYM and verify budgets (sized for 180 GB of HBM)
+void set_device_memory_hint(uint64_t free_bytes);
 int resolve_mode(int &mode, std::string &err);
 VerifyPlan plan_verify(int kind, uint64_t n, int mode, int level, bool interior_zero, uint64_t rank_bytes, bool use_sym);
 void layout_sections(FmxBlobHeader &hdr, const uint64_t bytes[SEC_COUNT]);
 bool q4_forbidden_by_env();
+bool sym_layout_chosen(uint64_t cs_len, uint64_t len);
+uint64_t sym_layout_bytes(uint64_t cs_len, uint64_t len);
 
-// gpu_build.cu: the whole blob built in device memory (Q4 layouts of FM / MultiPieces indexes).
+// gpu_build.cu: the whole blob built in device memory (Q4 and SYM layouts of FM / MultiPieces indexes).
 // Returns 0 and a cudaMalloc'd blob + its header; FMX_ERR_UNSUPPORTED when this text / kind is not its case
 // (the caller then takes the host builder).
-int gpu_build_q4_blob(const uint8_t *text, uint64_t n, uint64_t max_character, int kind, int level, int mode, int device,
+int gpu_build_blob(const uint8_t *text, uint64_t n, uint64_t max_character, int kind, int level, int mode, int device,
                       void **d_blob_out, FmxBlobHeader *hdr_out, std::string &err);
 
 // gpu_sa.cu

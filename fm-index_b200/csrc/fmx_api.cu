@@ -119,6 +119,7 @@ struct fmx_index {
     int opt_bucket = 0;               // 1: visit the batch in k-mer bucket order (lost the A/B, kept for experiments); -1 auto
     int opt_count_work = 0;           // 1: kernels count executed search iterations / LF steps (fmx_last_work)
     int opt_phased = 2;               // dense verify structures: 2 = k_query_fused (one kernel), 1 = the three phased kernels, 0 = k_search
+    int opt_extract_text = 1;         // 0: extraction by LF / FL steps even when text and suffix array are resident (A/B)
     int opt_locate_dense = 1;         // 0: LF walks to the samples even when the full suffix array is resident (A/B)
     uint32_t tab_embed = 0;           // one-row k-mer table entries carry the row's text position (SearchArgs::tab_embed)
     mutable DevBuf buf[B_COUNT];
@@ -262,6 +263,7 @@ static int build_blob_any(const void *text, uint64_t n, uint32_t char_width, uin
 int fmx_blob_build_ex(const void *text, uint64_t n, uint32_t char_width, uint64_t max_character, int kind, int level,
                       int mode, void **blob, uint64_t *blob_bytes) {
     if (!blob || !blob_bytes || (!text && n)) return fail(FMX_ERR_INVALID_ARG, "null argument");
+    set_device_memory_hint(0);  // a host-only build knows of no device
     HostBlob b;
     std::string err;
     int rc = build_blob_any(text, n, char_width, max_character, kind, level, b, err, -1, mode);
@@ -472,12 +474,18 @@ int fmx_index_build_ex(const void *text, uint64_t n, uint32_t char_width, uint64
         return fail(FMX_ERR_CUDA, "no CUDA device available (the engine has no CPU fallback)");
     }
     if (device < 0 || device >= ndev) return fail(FMX_ERR_INVALID_ARG, "device ordinal out of range");
+    {   // the layout budgets follow the device's free memory (a B200's 180 GB leaves them at their defaults)
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaSetDevice(device));
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) set_device_memory_hint(free_b);
+        else cudaGetLastError();
+    }
     std::string err;
     if (char_width == 1 && !env_flag("FMX_HOST_BUILD") && !env_flag("FMX_HOST_SA")) {
-        // Q4 layouts of FM / MultiPieces indexes: the whole blob is built in device memory (gpu_build.cu)
+        // Q4 and SYM layouts of FM / MultiPieces indexes: the whole blob is built in device memory (gpu_build.cu)
         void *d_blob = nullptr;
         FmxBlobHeader hdr;
-        int grc = gpu_build_q4_blob(static_cast<const uint8_t *>(text), n, max_character, kind, level, mode, device, &d_blob, &hdr, err);
+        int grc = gpu_build_blob(static_cast<const uint8_t *>(text), n, max_character, kind, level, mode, device, &d_blob, &hdr, err);
         if (grc == 0) return adopt(hdr, d_blob, device, out);
         if (grc != FMX_ERR_UNSUPPORTED) return fail(grc, err);
         err.clear();
@@ -570,6 +578,7 @@ int fmx_index_set_option(fmx_index *idx, const char *key, int64_t value) {
     else if (k == "count_work") idx->opt_count_work = value != 0;
     else if (k == "search_phased") idx->opt_phased = value < 0 || value > 2 ? 2 : (int)value;
     else if (k == "locate_dense") idx->opt_locate_dense = value != 0;
+    else if (k == "extract_text") idx->opt_extract_text = value != 0;
     else if (k == "phase_timing") idx->opt_phase_timing = value != 0;
     else if (k == "pipeline_chunk") idx->opt_pipeline_chunk = value > 0 ? (uint64_t)value : 0;
     else if (k == "l2_fetch_granularity") {
@@ -596,6 +605,7 @@ int fmx_index_device(const fmx_index *idx) { return idx ? idx->device : -1; }
 uint32_t fmx_index_wavelet_levels(const fmx_index *idx) { return idx ? idx->hdr.levels : 0; }
 uint32_t fmx_index_sample_level(const fmx_index *idx) { return idx && idx->hdr.has_locate ? idx->hdr.sa_level : 0; }
 uint32_t fmx_index_layout(const fmx_index *idx) { return idx ? idx->hdr.layout : 0; }
+int fmx_index_has_text(const fmx_index *idx) { return idx && idx->dev.text && has_dense_sa(idx) && idx->dev.cw_shift == 0 ? 1 : 0; }
 uint32_t fmx_index_char_width(const fmx_index *idx) { return idx ? (idx->hdr.char_width ? idx->hdr.char_width : 1u) : 0; }
 uint32_t fmx_index_sectors_per_rank(const fmx_index *idx) {
     if (!idx) return 0;
@@ -2019,6 +2029,14 @@ extern "C" int fmx_csr_merge_device(int device, const fmx_csr_part *parts, int n
 static int extract_device(const fmx_index *idx, const uint64_t *d_rows, uint64_t nrows, uint32_t k, int forward,
                           uint8_t *d_out, uint32_t *d_len, cudaStream_t st) {
     if (nrows == 0 || k == 0) return 0;
+    if (idx->dev.text && has_dense_sa(idx) && idx->opt_extract_text && idx->dev.cw_shift == 0) {
+        // HBM-rich indexes: the characters are read from the text at SA[row] (k_extract_text)
+        const unsigned gt = grid_for(nrows * FMX_XT_LANES, 256);
+        if (idx->hdr.kind == FMX_KIND_MULTI) k_extract_text<FMX_KIND_MULTI_><<<gt, 256, 0, st>>>(idx->dev, d_rows, nrows, k, forward, d_out, d_len);
+        else k_extract_text<FMX_KIND_FM_><<<gt, 256, 0, st>>>(idx->dev, d_rows, nrows, k, forward, d_out, d_len);
+        LAUNCH_CHECK();
+        return 0;
+    }
     unsigned g = grid_for(nrows, 256);
     dispatch(idx, [&](auto K, auto LY) { k_extract<K(), LY()><<<g, 256, 0, st>>>(idx->dev, d_rows, nrows, k, forward, d_out, d_len); });
     LAUNCH_CHECK();

@@ -2,13 +2,15 @@
 //
 // Round 1 built only the suffix array on the device; the BWT, the rank blocks, the inverse suffix array, the samples
 // and the blob assembly stayed host work (13 of the 14 s of the 1 GB DNA build, plus a 10.5 GB host-to-device copy).
-// Here the whole device-layout blob (fmx_layout.h) of a Q4 index -- max_character <= 4, FMIndex and
-// FMIndexMultiPieces: four of the five BASELINE configs -- is produced in device memory:
+// Here the whole device-layout blob (fmx_layout.h) of an FMIndex / FMIndexMultiPieces index in the Q4 layout
+// (max_character <= 4: the DNA configs) or the SYM layout (every other u8 alphabet within the budget: the byte
+// config) is produced in device memory:
 //
 //   reference producer (file:line)                         here
 //   suffix array            sais.rs:115-144                gpu_sa.cu (prefix doubling), left on the device
 //   BWT                     fm_index.rs:44-58              k_bwt: bw[i] = text[sa[i] - 1], 0 when sa[i] == 0
 //   rank structure          (vers-vecs WaveletMatrix)      k_q4_pack -> own scans (scan3.cuh) -> k_q4_counts: Q4 blocks
+//                                                          k_sym_pack -> one scan -> k_sym_counts: per-symbol RB192 vectors
 //   SA samples              sample.rs:21-44                k_samples: sa[i << level]
 //   inverse SA / full SA / text (verify, rich locate)      k_isa (scatter), device copies
 //   cs                      sais.rs:9-32                   host histogram of the text (5 counters)
@@ -16,7 +18,7 @@
 //
 // The result is byte-identical to the host builder's blob (tests/test_gpu_parity.py::
 // test_gpu_built_blob_identical_to_host_built): same header, same sections, same padding.
-// Other layouts (SYM, WM4, binary wavelet) and RLFM keep the host builder (builder.cpp).
+// Other layouts (WM4, binary wavelet, WIDE) and RLFM keep the host builder (builder.cpp).
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -66,6 +68,51 @@ __global__ void k_q4_counts(uint32_t *blocks, const uint32_t *cnt, uint64_t nblk
     for (int k = 0; k < 4; k++) blocks[b * 8 + k] = cnt[(uint64_t)k * nblk + b];
 }
 
+// SYM layout: thread (b, c) builds block b of symbol c's RB192 vector -- payload bit t = [bwt[192 b + t] == c], the two
+// in-block sub-counts -- and leaves the block's popcount in cnt[c * nblk + b] for the prefix sums.  The 192 bytes of a
+// block are compared four at a time; threads of a warp share b's bytes through L1.
+__global__ void __launch_bounds__(256) k_sym_pack(const uint8_t *bwt, uint64_t n, uint64_t nblk, uint32_t cs_len, uint32_t *blocks,
+                                                  uint32_t *cnt) {
+    const uint64_t b = (uint64_t)blockIdx.x * (256 / 32) + threadIdx.x / 32;  // a warp per block b, lanes over symbols
+    if (b >= nblk) return;
+    const uint64_t lo = b * FMX_RB_BITS;
+    const uint32_t *w4 = reinterpret_cast<const uint32_t *>(bwt + lo);  // 192 b is a multiple of 4; bwt is cudaMalloc'd
+    const uint64_t avail = lo < n ? (n - lo < FMX_RB_BITS ? n - lo : FMX_RB_BITS) : 0;
+    for (uint32_t c = threadIdx.x & 31; c < cs_len; c += 32) {
+        uint32_t pay[6];
+        const uint32_t pat = c * 0x01010101u;
+#pragma unroll
+        for (uint32_t w = 0; w < 6; w++) {  // payload word w = symbols 32 w .. 32 w + 31 = text words 8 w .. 8 w + 7
+            uint32_t acc = 0;
+#pragma unroll
+            for (uint32_t q = 0; q < 8; q++) {
+                const uint32_t k = w * 8 + q;  // 4 symbols per text word
+                if ((uint64_t)k * 4 < avail) {
+                    uint32_t m = __vcmpeq4(__ldg(w4 + k), pat) & 0x01010101u;
+                    const uint64_t left = avail - (uint64_t)k * 4;
+                    if (left < 4) m &= 0x01010101u >> (8u * (4u - (uint32_t)left));
+                    acc |= ((m * 0x01020408u) >> 24) << (q * 4u);  // byte j of the word -> bit j
+                }
+            }
+            pay[w] = acc;
+        }
+        const uint32_t p0 = __popc(pay[0]) + __popc(pay[1]), p1 = __popc(pay[2]) + __popc(pay[3]), p2 = __popc(pay[4]) + __popc(pay[5]);
+        uint32_t *blk = blocks + ((uint64_t)c * nblk + b) * 8;
+        blk[1] = (p0 << 8) | ((p0 + p1) << 16);
+        for (int k = 0; k < 6; k++) blk[2 + k] = pay[k];
+        cnt[(uint64_t)c * nblk + b] = p0 + p1 + p2;
+    }
+}
+
+// word 0 of every block = ones of its vector before it: the running sum over the whole (symbol-major) count array minus
+// the sum at the start of the symbol's vector
+__global__ void k_sym_counts(uint32_t *blocks, const uint32_t *scan, uint64_t nblk, uint64_t total_blocks) {
+    const uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= total_blocks) return;
+    const uint64_t c = x / nblk;
+    blocks[x * 8] = scan[x] - scan[c * nblk];
+}
+
 // rows whose BWT symbol is \0 (at most `cap`; *count keeps counting past it)
 __global__ void k_zero_rows(const uint8_t *bwt, uint64_t n, uint32_t *rows, uint32_t cap, unsigned *count) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -102,11 +149,10 @@ static inline uint32_t log2_u64(uint64_t x) { return 63u - (uint32_t)__builtin_c
         }                                                                             \
     } while (0)
 
-int gpu_build_q4_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level, int mode, int device,
-                      void **d_blob_out, FmxBlobHeader *hdr_out, std::string &err) {
+int gpu_build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level, int mode, int device,
+                   void **d_blob_out, FmxBlobHeader *hdr_out, std::string &err) {
     *d_blob_out = nullptr;
-    if (mc == 0 || mc > 4 || q4_forbidden_by_env() || (kind != FMX_KIND_FM && kind != FMX_KIND_MULTI) || n < (1u << 16) ||
-        n >= (1ull << 32) - 1)
+    if (mc == 0 || mc > 255 || (kind != FMX_KIND_FM && kind != FMX_KIND_MULTI) || n < (1u << 16) || n >= (1ull << 32) - 1)
         return FMX_ERR_UNSUPPORTED;
     // the text's zeros: the Q4 exception list holds as many, and they are the piece ends of a multi-piece text
     std::vector<uint32_t> zeros;
@@ -126,15 +172,23 @@ int gpu_build_q4_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, in
         if (bad) return FMX_ERR_UNSUPPORTED;  // the host builder reports it
         for (auto &v : part) zeros.insert(zeros.end(), v.begin(), v.end());
     }
-    if (zeros.size() > FMX_MAX_EXC || zeros.empty() || zeros.back() != n - 1 || text[0] == 0 || (n >= 2 && text[n - 2] == 0))
-        return FMX_ERR_UNSUPPORTED;  // invalid texts and texts with many zeros: the host builder's business
+    if (zeros.empty() || zeros.back() != n - 1 || text[0] == 0 || (n >= 2 && text[n - 2] == 0))
+        return FMX_ERR_UNSUPPORTED;  // invalid texts: the host builder's business
+    const uint32_t L = log2_u64(mc) + 1, cs_len = (uint32_t)mc + 1;
+    // the layout, by the host builder's rules (builder.cpp: want_q4, then SYM within its budget)
+    const bool use_q4 = mc <= 4 && !q4_forbidden_by_env() && zeros.size() <= FMX_MAX_EXC;
+    const bool use_sym = !use_q4 && sym_layout_chosen(cs_len, n);
+    if (!use_q4 && !use_sym) return FMX_ERR_UNSUPPORTED;
+    const bool need_rows = use_q4 || kind == FMX_KIND_MULTI;  // rows of the \0 symbols: exception list, doc
+    const uint32_t row_cap = use_q4 ? FMX_MAX_EXC : (1u << 22);
+    if (need_rows && zeros.size() > row_cap) return FMX_ERR_UNSUPPORTED;
     const bool interior_zero = kind != FMX_KIND_MULTI && zeros.size() > 1;
     if (int mrc = resolve_mode(mode, err)) return mrc;
 
-    const uint32_t L = log2_u64(mc) + 1, cs_len = (uint32_t)mc + 1;
-    const uint64_t nblk = n / 64 + 1;
-    const VerifyPlan vp = plan_verify(kind, n, mode, level, interior_zero, nblk * 32, false);
-    if (vp.verify && !vp.dense) return FMX_ERR_UNSUPPORTED;  // the sampled verify form exists for SYM layouts only
+    const uint64_t nblk = use_q4 ? n / 64 + 1 : n / FMX_RB_BITS + 1;
+    const uint64_t rank_bytes = use_q4 ? nblk * 32 : sym_layout_bytes(cs_len, n);
+    const VerifyPlan vp = plan_verify(kind, n, mode, level, interior_zero, rank_bytes, use_sym);
+    if (vp.verify && !vp.dense) return FMX_ERR_UNSUPPORTED;  // the sampled verify form: host builder
 
     FmxBlobHeader hdr;
     std::memset(&hdr, 0, sizeof(hdr));
@@ -146,9 +200,10 @@ int gpu_build_q4_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, in
     hdr.levels = L;
     hdr.max_character = (uint32_t)mc;
     hdr.cs_len = cs_len;
-    hdr.layout = FMX_LAYOUT_QUAT;
+    hdr.layout = use_q4 ? FMX_LAYOUT_QUAT : FMX_LAYOUT_SYM;
     hdr.char_width = 1;
-    hdr.nexc = (uint32_t)zeros.size();
+    hdr.nexc = use_q4 ? (uint32_t)zeros.size() : 0u;
+    hdr.sym_nblk = use_sym ? (uint32_t)nblk : 0u;
     hdr.reserved[0] = (uint64_t)mode;
     if (vp.verify) {
         hdr.verify = 1;
@@ -187,8 +242,9 @@ int gpu_build_q4_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, in
 
     uint64_t bytes[SEC_COUNT];
     std::memset(bytes, 0, sizeof(bytes));
-    bytes[SEC_LEVEL0] = nblk * 32;
-    bytes[SEC_EXC] = zeros.size() * 4;
+    bytes[SEC_LEVEL0] = rank_bytes;
+    if (use_sym) bytes[SEC_LEVEL0 + 1] = n;  // the raw sequence
+    if (use_q4) bytes[SEC_EXC] = zeros.size() * 4;
     bytes[SEC_ADJ] = (uint64_t)cs_len * 4;
     bytes[SEC_CS] = (uint64_t)(cs_len + 1) * 4;
     if (hdr.has_locate) bytes[SEC_SA] = hdr.sa_count * 4;
@@ -212,6 +268,7 @@ int gpu_build_q4_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, in
     auto at = [&](int k) { return blob + hdr.sec[k].offset; };
     std::vector<uint32_t> rows, rowsa, doc;
     unsigned nz = 0;
+    const uint64_t cnt_entries = use_q4 ? nblk * 4 : nblk * cs_len;
 
     GB_TRY(cudaSetDevice(device));
     GB_TRY(cudaMalloc(&d_text, n));
@@ -227,37 +284,50 @@ int gpu_build_q4_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, in
     }
     GB_TRY(cudaMalloc(&blob, hdr.total_bytes));
     GB_TRY(cudaMemset(blob, 0, hdr.total_bytes));
-    GB_TRY(cudaMalloc(&d_bwt, n));
-    GB_TRY(cudaMalloc(&d_cnt, nblk * 16));
-    GB_TRY(cudaMalloc(&d_rows, FMX_MAX_EXC * 4));
-    GB_TRY(cudaMalloc(&d_rowsa, FMX_MAX_EXC * 4));
+    GB_TRY(cudaMalloc(&d_bwt, n + 16));  // k_sym_pack reads whole words
+    GB_TRY(cudaMemset(d_bwt + n, 0, 16));
+    GB_TRY(cudaMalloc(&d_cnt, cnt_entries * 4));
+    GB_TRY(cudaMalloc(&d_rows, (uint64_t)row_cap * 4));
+    GB_TRY(cudaMalloc(&d_rowsa, (uint64_t)row_cap * 4));
     GB_TRY(cudaMalloc(&d_count, 4));
     GB_TRY(cudaMemset(d_count, 0, 4));
 
     k_bwt<<<grid(n), T>>>(d_text, d_sa, n, d_bwt);
-    k_q4_pack<<<grid(nblk), T>>>(d_bwt, n, nblk, reinterpret_cast<uint32_t *>(at(SEC_LEVEL0)), d_cnt);
-    GB_TRY(cudaGetLastError());
-    for (int c = 0; c < 4; c++)  // occurrences of code c before every block
-        GB_TRY((scan3::run<uint32_t, scan3::Sum32, true>(d_cnt + (uint64_t)c * nblk, nblk, d_cnt + (uint64_t)c * nblk, scan3::Sum32(), 0u, 0)));
-    k_q4_counts<<<grid(nblk), T>>>(reinterpret_cast<uint32_t *>(at(SEC_LEVEL0)), d_cnt, nblk);
-    k_zero_rows<<<grid(n), T>>>(d_bwt, n, d_rows, FMX_MAX_EXC, d_count);
-    GB_TRY(cudaGetLastError());
-    GB_TRY(cudaMemcpy(&nz, d_count, 4, cudaMemcpyDeviceToHost));
-    if (nz != zeros.size()) {
-        err = "GPU index build: the BWT holds another number of zeros than the text";
-        rc = FMX_ERR_CUDA;
-        goto fail;
+    if (use_q4) {
+        k_q4_pack<<<grid(nblk), T>>>(d_bwt, n, nblk, reinterpret_cast<uint32_t *>(at(SEC_LEVEL0)), d_cnt);
+        GB_TRY(cudaGetLastError());
+        for (int c = 0; c < 4; c++)  // occurrences of code c before every block
+            GB_TRY((scan3::run<uint32_t, scan3::Sum32, true>(d_cnt + (uint64_t)c * nblk, nblk, d_cnt + (uint64_t)c * nblk, scan3::Sum32(), 0u, 0)));
+        k_q4_counts<<<grid(nblk), T>>>(reinterpret_cast<uint32_t *>(at(SEC_LEVEL0)), d_cnt, nblk);
+    } else {
+        k_sym_pack<<<(unsigned)((nblk + 7) / 8), 256>>>(d_bwt, n, nblk, cs_len, reinterpret_cast<uint32_t *>(at(SEC_LEVEL0)), d_cnt);
+        GB_TRY(cudaGetLastError());
+        // one running sum over all vectors' block popcounts (symbol-major; the grand total is n < 2^32)
+        GB_TRY((scan3::run<uint32_t, scan3::Sum32, true>(d_cnt, cnt_entries, d_cnt, scan3::Sum32(), 0u, 0)));
+        k_sym_counts<<<grid(cnt_entries), T>>>(reinterpret_cast<uint32_t *>(at(SEC_LEVEL0)), d_cnt, nblk, cnt_entries);
+        GB_TRY(cudaMemcpy(at(SEC_LEVEL0 + 1), d_bwt, n, cudaMemcpyDeviceToDevice));
     }
-    rows.resize(nz);
-    GB_TRY(cudaMemcpy(rows.data(), d_rows, nz * 4, cudaMemcpyDeviceToHost));
-    std::sort(rows.begin(), rows.end());  // SEC_EXC: ascending rows whose symbol is \0
-    GB_TRY(cudaMemcpy(at(SEC_EXC), rows.data(), nz * 4, cudaMemcpyHostToDevice));
+    GB_TRY(cudaGetLastError());
+    if (need_rows) {
+        k_zero_rows<<<grid(n), T>>>(d_bwt, n, d_rows, row_cap, d_count);
+        GB_TRY(cudaGetLastError());
+        GB_TRY(cudaMemcpy(&nz, d_count, 4, cudaMemcpyDeviceToHost));
+        if (nz != zeros.size()) {
+            err = "GPU index build: the BWT holds another number of zeros than the text";
+            rc = FMX_ERR_CUDA;
+            goto fail;
+        }
+        rows.resize(nz);
+        GB_TRY(cudaMemcpy(rows.data(), d_rows, (uint64_t)nz * 4, cudaMemcpyDeviceToHost));
+        std::sort(rows.begin(), rows.end());  // ascending rows whose symbol is \0: SEC_EXC, and select(bw, k, 0)
+        if (use_q4) GB_TRY(cudaMemcpy(at(SEC_EXC), rows.data(), (uint64_t)nz * 4, cudaMemcpyHostToDevice));
+    }
     if (kind == FMX_KIND_MULTI) {  // multi_pieces.rs:53-79
-        GB_TRY(cudaMemcpy(d_rows, rows.data(), nz * 4, cudaMemcpyHostToDevice));
+        GB_TRY(cudaMemcpy(d_rows, rows.data(), (uint64_t)nz * 4, cudaMemcpyHostToDevice));
         k_gather32<<<(nz + T - 1) / T, T>>>(d_sa, d_rows, nz, d_rowsa);
         GB_TRY(cudaGetLastError());
         rowsa.resize(nz);
-        GB_TRY(cudaMemcpy(rowsa.data(), d_rowsa, nz * 4, cudaMemcpyDeviceToHost));
+        GB_TRY(cudaMemcpy(rowsa.data(), d_rowsa, (uint64_t)nz * 4, cudaMemcpyDeviceToHost));
         doc.assign(nz, 0);
         for (unsigned k = 0; k < nz; k++) {  // rows[k] = select(bw, k, 0)
             const uint64_t em = rowsa[k] ? rowsa[k] - 1 : n - 1;  // modular_sub(sa[p], 1, n)
@@ -265,8 +335,8 @@ int gpu_build_q4_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, in
             if (pid == nz - 1) hdr.first_row = rows[k];
             doc[k] = (uint32_t)pid;
         }
-        GB_TRY(cudaMemcpy(at(SEC_DOC), doc.data(), nz * 4, cudaMemcpyHostToDevice));
-        GB_TRY(cudaMemcpy(at(SEC_PIECE_END), zeros.data(), nz * 4, cudaMemcpyHostToDevice));
+        GB_TRY(cudaMemcpy(at(SEC_DOC), doc.data(), (uint64_t)nz * 4, cudaMemcpyHostToDevice));
+        GB_TRY(cudaMemcpy(at(SEC_PIECE_END), zeros.data(), (uint64_t)nz * 4, cudaMemcpyHostToDevice));
     }
     GB_TRY(cudaMemcpy(at(SEC_ADJ), adj.data(), adj.size() * 4, cudaMemcpyHostToDevice));
     GB_TRY(cudaMemcpy(at(SEC_CS), cs.data(), cs.size() * 4, cudaMemcpyHostToDevice));

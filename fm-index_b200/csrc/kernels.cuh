@@ -1793,6 +1793,55 @@ __global__ void __launch_bounds__(256) k_extract(const __grid_constant__ FmxDev 
     if (out_len) out_len[r] = got;
 }
 
+// The same characters straight from the text, for indexes that hold the text and the full suffix array (HBM-rich mode).
+// With p = SA[row]: the reference's forward iterator yields text[p], text[p + 1], .. (get_f(i) = text[SA[i]], fl_map(i) =
+// row of suffix SA[i] + 1; a MultiPieces index stops IN FRONT of a \0, multi_pieces.rs:171-181), its backward iterator
+// text[p - 1], text[p - 2], .. (get_l(i) = text[SA[i] - 1], lf_map(i) = row of suffix SA[i] - 1), both cyclic over the
+// text: fm_index.rs:78-120, wrapper.rs:143-183.  (Single texts with interior \0, where the reference's lf_map2(0, .) is
+// not the true LF row, never carry these structures.)  So k characters cost one suffix-array request plus the one or
+// two text sectors they lie in, instead of k rank -- or k select -- probes.
+// Eight lanes per row: four characters each per round, aligned 4-byte loads and stores.
+#define FMX_XT_LANES 8u
+template <int KIND>
+__global__ void __launch_bounds__(256) k_extract_text(const __grid_constant__ FmxDev ix, const uint64_t *rows, uint64_t nrows,
+                                                      uint32_t k, int forward, uint8_t *out, uint32_t *out_len) {
+    const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / FMX_XT_LANES;
+    const uint32_t j = threadIdx.x % FMX_XT_LANES;
+    if (r >= nrows) return;
+    const uint32_t n = ix.n;
+    const uint32_t p = ldg32_s(ix.vsa + (uint32_t)rows[r]);
+    uint8_t *o = out + r * k;
+    uint32_t got = k;
+    if (KIND == FMX_KIND_MULTI_ && forward) {  // the walk ends in front of the piece's \0
+        const uint32_t end = __ldg(ix.piece_end + piece_of(ix, p));
+        if (end - p < got) got = end - p;
+    }
+    if (j == 0 && out_len) out_len[r] = got;
+    const uint32_t *tw = reinterpret_cast<const uint32_t *>(ix.text);
+    const bool inside = forward ? (uint64_t)p + k <= n : p >= k;  // no wrap around the end of the text
+    if (inside && (k & 3u) == 0 && (reinterpret_cast<uintptr_t>(o) & 3u) == 0) {
+        for (uint32_t t = 4u * j; t < k; t += 4u * FMX_XT_LANES) {
+            const uint32_t a = forward ? p + t : p - t - 4u;  // the four text bytes, ascending
+            const uint32_t sh = (a & 3u) * 8u;
+            const uint32_t lo = ldg32_s(tw + (a >> 2));
+            const uint32_t hi = sh ? ldg32_s(tw + (a >> 2) + 1u) : 0u;
+            uint32_t v = __funnelshift_r(lo, hi, sh);
+            if (!forward) v = __byte_perm(v, 0u, 0x0123);  // out[t] = text[p - 1 - t]
+            if (t + 4u > got) v = t >= got ? 0u : v & (0xFFFFFFFFu >> (8u * (t + 4u - got)));
+            *reinterpret_cast<uint32_t *>(o + t) = v;
+        }
+        return;
+    }
+    for (uint32_t t = j; t < k; t += FMX_XT_LANES) {  // odd sizes and walks that wrap: byte by byte
+        uint32_t c = 0;
+        if (t < got) {
+            uint64_t q = forward ? ((uint64_t)p + t) % n : ((uint64_t)p + (uint64_t)n - 1u - (t % n)) % n;
+            c = ldg8_s(ix.text + q);
+        }
+        o[t] = (uint8_t)c;
+    }
+}
+
 // backend primitives over a batch of rows, for parity tests (src/backend.rs:5-40)
 template <int KIND, int LAYOUT>
 __global__ void __launch_bounds__(256) k_rows_op(const __grid_constant__ FmxDev ix, int op, const uint64_t *rows,

@@ -158,6 +158,9 @@ uint32_t fmx_index_sample_level(const fmx_index *idx);
 uint32_t fmx_index_sectors_per_rank(const fmx_index *idx);
 /* the device layout the builder chose: 0 binary wavelet matrix, 1 Q4, 2 WM4, 3 SYM, 4 WIDE (csrc/fmx_layout.h) */
 uint32_t fmx_index_layout(const fmx_index *idx);
+/* 1 when the index holds the text and the full suffix array (HBM-rich mode): extraction then reads the characters
+ * from the text at SA[row] instead of walking LF / FL steps (same characters; option "extract_text" 0|1 for A/B) */
+int fmx_index_has_text(const fmx_index *idx);
 /* bytes per character of the text the index was built from = width of pattern and extracted characters (1, 2, 4, 8) */
 uint32_t fmx_index_char_width(const fmx_index *idx);
 /* characters memoised by the small (big = 0) / large (big = 1) k-mer table of fresh searches; 0 = none */

@@ -166,6 +166,31 @@ def test_extraction_vs_oracle(kind):
         assert np.array_equal(ln, oln) and np.array_equal(out, oout)
 
 
+@pytest.mark.parametrize("kind", [orc.FM, orc.RLFM, orc.MULTI])
+def test_extraction_from_the_text_in_rich_mode(kind):
+    """HBM-rich indexes read extracted characters from the text at SA[row] (k_extract_text): same characters and
+    lengths as the oracle's LF / FL walks, forward and backward, incl. walks that wrap around the text, odd lengths,
+    pieces that end early, and the A/B option that forces the walking kernel"""
+    rng = np.random.default_rng(70 + kind)
+    L = fmx.load_library()
+    for n, mc in ((70, 4), (5000, 4), (40_000, 200)):
+        text = build_text(rng, n, min(mc + 1, 8) if kind == orc.MULTI else min(mc, 7), kind == orc.MULTI)
+        if kind != orc.MULTI and 0 in text[:-1]:
+            continue
+        index = KINDS[kind][1].new(fmx.Text.with_max_character(text, mc), 2, mode=fmx.MODE_RICH)
+        oracle = orc.OracleIndex(text, kind, level=2, max_character=mc)
+        assert L.fmx_index_has_text(index._h) == 1
+        rows = np.concatenate([np.arange(min(len(text), 300)), rng.integers(0, len(text), 700)]).astype(np.uint64)
+        for k in (1, 4, 7, 32, 37, 100):
+            for fwd in (False, True):
+                oout, oln = oracle.extract_batch(rows, k, fwd)
+                for opt in (1, 0):
+                    index.set_option("extract_text", opt)
+                    out, ln = index.extract_batch(rows, k, fwd)
+                    assert np.array_equal(ln, oln) and np.array_equal(out, oout), (n, mc, k, fwd, opt)
+    compact = KINDS[kind][1].new(fmx.Text.with_max_character(text, mc), 2, mode=fmx.MODE_COMPACT)
+    assert L.fmx_index_has_text(compact._h) == 0
+
 
 # ---- the four device layouts (fmx_layout.h) answer identically: the builder picks Q4 for DNA-coded
 # texts and per-symbol bit vectors (SYM) otherwise; a zero SYM budget gives the quaternary wavelet
@@ -611,20 +636,26 @@ def test_gpu_suffix_array_matches_oracle():
         assert np.array_equal(sa, orc.suffix_array(text)), (len(text), mc, rounds)
 
 
+@pytest.mark.parametrize("mc", [4, 255])
 @pytest.mark.parametrize("kind", [orc.FM, orc.RLFM, orc.MULTI])
-def test_gpu_built_blob_identical_to_host_built(kind, tmp_path):
-    rng = np.random.default_rng(500 + kind)
+def test_gpu_built_blob_identical_to_host_built(kind, mc, tmp_path):
+    """FM / MultiPieces indexes in the Q4 (mc = 4) and SYM (mc = 255) layouts are built entirely in device memory
+    (gpu_build.cu): the saved index equals the host builder's blob byte for byte, in both modes"""
+    rng = np.random.default_rng(500 + kind + mc)
+    hi = 5 if mc == 4 else 256
     if kind == orc.MULTI:
-        text = np.concatenate([np.append(rng.integers(1, 5, int(l), dtype=np.uint8), np.uint8(0))
+        text = np.concatenate([np.append(rng.integers(1, hi, int(l), dtype=np.uint8), np.uint8(0))
                                for l in rng.integers(5_000, 40_000, 9)])
     else:
-        text = dna(200_000, 60 + kind)
-    t = fmx.Text.with_max_character(text, 4)
-    index = KINDS[kind][1].new(t, 2)                 # >= 2^16 symbols: suffix array built on the GPU
-    p = tmp_path / "gpu_built.fmx"
-    index.save(p)
-    host = fmx.blob_build(t, kind, 2)                # host SA-IS
-    assert np.array_equal(np.fromfile(p, dtype=np.uint8), host)
+        text = np.append(rng.integers(1, hi, 200_000, dtype=np.uint8), np.uint8(0))
+    t = fmx.Text.with_max_character(text, mc)
+    for mode in (fmx.MODE_COMPACT, fmx.MODE_RICH):
+        index = KINDS[kind][1].new(t, 2, mode=mode)      # >= 2^16 symbols: built on the GPU
+        p = tmp_path / f"gpu_built_{mode}.fmx"
+        index.save(p)
+        host = fmx.blob_build(t, kind, 2, mode=mode)     # host SA-IS, host rank structures
+        assert np.array_equal(np.fromfile(p, dtype=np.uint8), host)
+        del index
 
 
 def test_search_options_do_not_change_results():
@@ -1197,7 +1228,7 @@ def test_wide_character_texts(kind, dtype, mc, tmp_path):
         assert np.array_equal(fh, ooff) and np.array_equal(fp, opos)
     # fixed-length patterns, refinement, the Search / Match objects
     fixed = np.stack([text[i:i + 8] for i in rng.integers(0, n - 8, 500)])
-    fixed = fixed[~(fixed == 0).any(axis=1)] if not multi else fixed
+    fixed = fixed[~(fixed == 0).any(axis=1)]
     fb = index.search_batch(fixed)
     fs, fe = oracle.search_batch(fixed.reshape(-1), np.arange(fixed.shape[0] + 1, dtype=np.uint64) * 8)
     assert np.array_equal(fb.s, fs) and np.array_equal(fb.e, fe)

@@ -59,6 +59,9 @@ uint64_t sym_layout_bytes(uint64_t cs_len, uint64_t len);
 int gpu_build_blob(const uint8_t *text, uint64_t n, uint64_t max_character, int kind, int level, int mode, int device,
                       void **d_blob_out, FmxBlobHeader *hdr_out, std::string &err);
 
+int gpu_build_rlfm_blob(const uint8_t *text, uint64_t n, uint64_t max_character, int level, int mode, int device,
+                        void **d_blob_out, FmxBlobHeader *hdr_out, std::string &err);
+
 // gpu_sa.cu
 int gpu_suffix_array_device(const uint8_t *d_text, uint64_t n, uint32_t bits, int device, uint32_t **d_sa_out, int *rounds_out,
                             std::string &err);

@@ -485,7 +485,9 @@ int fmx_index_build_ex(const void *text, uint64_t n, uint32_t char_width, uint64
         // Q4 and SYM layouts of FM / MultiPieces indexes: the whole blob is built in device memory (gpu_build.cu)
         void *d_blob = nullptr;
         FmxBlobHeader hdr;
-        int grc = gpu_build_blob(static_cast<const uint8_t *>(text), n, max_character, kind, level, mode, device, &d_blob, &hdr, err);
+        int grc = kind == FMX_KIND_RLFM
+                      ? gpu_build_rlfm_blob(static_cast<const uint8_t *>(text), n, max_character, level, mode, device, &d_blob, &hdr, err)
+                      : gpu_build_blob(static_cast<const uint8_t *>(text), n, max_character, kind, level, mode, device, &d_blob, &hdr, err);
         if (grc == 0) return adopt(hdr, d_blob, device, out);
         if (grc != FMX_ERR_UNSUPPORTED) return fail(grc, err);
         err.clear();

@@ -18,7 +18,9 @@
 //
 // The result is byte-identical to the host builder's blob (tests/test_gpu_parity.py::
 // test_gpu_built_blob_identical_to_host_built): same header, same sections, same padding.
-// Other layouts (WM4, binary wavelet, WIDE) and RLFM keep the host builder (builder.cpp).
+// RLFMIndex: gpu_build_rlfm_blob below (run encoding rlfmi.rs:37-96 on the device).
+// Other layouts (WM4, binary wavelet, WIDE) keep the host builder (builder.cpp).
+#include <cub/device/device_radix_sort.cuh>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -135,6 +137,67 @@ __global__ void k_isa(const uint32_t *sa, uint64_t n, uint32_t *isa) {
 __global__ void k_samples(const uint32_t *sa, uint64_t count, uint32_t level, uint32_t *out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) out[i] = sa[i << level];
+}
+
+// ---- run-length encoding (rlfmi.rs:37-96) on the device
+// a run starts at row i when the BWT symbol differs from the previous one (the symbol "before" row 0 is \0, rlfmi.rs:47)
+__global__ void k_run_flags(const uint8_t *bwt, uint64_t n, uint8_t *flag, uint32_t *flag32) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const uint8_t f = bwt[i] != (i ? bwt[i - 1] : (uint8_t)0);
+        flag[i] = f;
+        flag32[i] = f;
+    }
+}
+// RB192 vector from a 0/1 byte per position: one thread per block (payload + in-block sub-counts; cnt[b] = its ones)
+__global__ void k_rb_pack(const uint8_t *flag, uint64_t n, uint64_t nblk, uint32_t *blocks, uint32_t *cnt) {
+    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblk) return;
+    const uint64_t lo = b * FMX_RB_BITS;
+    uint32_t w[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        uint32_t acc = 0;
+        for (uint32_t t = 0; t < 32; t++) {
+            const uint64_t i = lo + (uint64_t)k * 32 + t;
+            if (i < n && flag[i]) acc |= 1u << t;
+        }
+        w[k] = acc;
+    }
+    const uint32_t p0 = __popc(w[0]) + __popc(w[1]), p1 = __popc(w[2]) + __popc(w[3]), p2 = __popc(w[4]) + __popc(w[5]);
+    uint32_t *blk = blocks + b * 8;
+    blk[1] = (p0 << 8) | ((p0 + p1) << 16);
+#pragma unroll
+    for (int k = 0; k < 6; k++) blk[2 + k] = w[k];
+    cnt[b] = p0 + p1 + p2;
+}
+__global__ void k_rb_counts(uint32_t *blocks, const uint32_t *scan, uint64_t nblk) {
+    const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nblk) blocks[b * 8] = scan[b];
+}
+// run j = (number of run starts before row i) for every flagged row: its first row and its head symbol
+__global__ void k_runs_scatter(const uint8_t *flag, const uint32_t *ridx, const uint8_t *bwt, uint64_t n, uint32_t *starts,
+                               uint8_t *heads, uint32_t *order) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flag[i]) {
+        const uint32_t j = ridx[i];
+        starts[j] = (uint32_t)i;
+        heads[j] = bwt[i];
+        order[j] = j;
+    }
+}
+// length of the run that is k-th in (head, run index) order
+__global__ void k_sorted_run_len(const uint32_t *order, const uint32_t *starts, uint64_t r, uint64_t n, uint32_t *len) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < r) {
+        const uint32_t j = order[k];
+        len[k] = (j + 1 < r ? starts[j + 1] : (uint32_t)n) - starts[j];
+    }
+}
+// bp holds, head by head, every run as 1 0^{len-1} (rlfmi.rs:70-83): the k-th sorted run starts at pos[k]
+__global__ void k_mark_bp(const uint32_t *pos, uint64_t r, uint8_t *flag) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < r) flag[pos[k]] = 1;
 }
 
 static inline uint32_t log2_u64(uint64_t x) { return 63u - (uint32_t)__builtin_clzll(x); }
@@ -361,6 +424,252 @@ fail:
     cudaFree(d_rows);
     cudaFree(d_rowsa);
     cudaFree(d_count);
+    cudaFree(blob);
+    if (rc) cudaGetLastError();
+    return rc;
+}
+
+// RLFMIndex (rlfmi.rs:37-96) in device memory: suffix array, BWT, run starts -> b, run heads -> their rank structure
+// (Q4 or SYM over `runs` symbols), runs sorted stably by head -> bp and the two select tables, samples; in the HBM-rich
+// mode also the full suffix array and the text.  Byte-identical to the host builder's blob.
+int gpu_build_rlfm_blob(const uint8_t *text, uint64_t n, uint64_t mc, int level, int mode, int device, void **d_blob_out,
+                        FmxBlobHeader *hdr_out, std::string &err) {
+    *d_blob_out = nullptr;
+    if (mc == 0 || mc > 255 || n < (1u << 16) || n >= (1ull << 32) - 1) return FMX_ERR_UNSUPPORTED;
+    if (text[0] == 0 || text[n - 1] != 0 || text[n - 2] == 0) return FMX_ERR_UNSUPPORTED;  // invalid texts: the host builder reports
+    bool interior_zero = false, bad_char = false;
+    {
+        int iz = 0, bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : iz, bad)
+        for (int64_t i = 0; i < (int64_t)n - 1; i++) {
+            iz |= text[i] == 0;
+            bad |= text[i] > mc;
+        }
+        interior_zero = iz != 0;
+        bad_char = bad != 0;
+    }
+    if (bad_char) return FMX_ERR_UNSUPPORTED;
+    if (int mrc = resolve_mode(mode, err)) return mrc;
+    const uint32_t L = log2_u64(mc) + 1, cs_len = (uint32_t)mc + 1;
+    const VerifyPlan vp = plan_verify(FMX_KIND_RLFM, n, mode, level, interior_zero, 0, false);
+
+    int rc = FMX_ERR_CUDA;
+    uint8_t *d_text = nullptr, *d_bwt = nullptr, *d_flag = nullptr, *d_heads = nullptr, *d_heads_sorted = nullptr, *blob = nullptr;
+    uint32_t *d_sa = nullptr, *d_ridx = nullptr, *d_starts = nullptr, *d_order = nullptr, *d_order2 = nullptr, *d_len = nullptr,
+             *d_cnt = nullptr, *d_rows = nullptr;
+    unsigned *d_count = nullptr;
+    void *d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+    const unsigned T = 256;
+    auto grid = [&](uint64_t m) { return (unsigned)((m + T - 1) / T); };
+    FmxBlobHeader hdr;
+    std::memset(&hdr, 0, sizeof(hdr));
+    auto at = [&](int k) { return blob + hdr.sec[k].offset; };
+    const uint64_t nblk_n = n / FMX_RB_BITS + 1;
+    uint64_t r = 0, nblk = 0, cnt_entries = 0;
+    uint32_t last_idx = 0;
+    uint8_t last_flag = 0;
+    bool use_q4 = false, use_sym = false;
+    std::vector<uint8_t> heads;
+    std::vector<uint32_t> cs(cs_len + 1, 0), adj(cs_len, 0), rows;
+    std::vector<uint64_t> occ(cs_len, 0);
+    uint64_t bytes[SEC_COUNT];
+    unsigned nz = 0;
+    const uint32_t n32 = (uint32_t)n;
+
+    GB_TRY(cudaSetDevice(device));
+    GB_TRY(cudaMalloc(&d_text, n));
+    GB_TRY(cudaMemcpy(d_text, text, n, cudaMemcpyHostToDevice));
+    {
+        std::string serr;
+        int src = gpu_suffix_array_device(d_text, n, L, device, &d_sa, nullptr, serr);
+        if (src) {
+            err = "GPU suffix array construction failed: " + serr;
+            rc = src;
+            goto fail;
+        }
+    }
+    GB_TRY(cudaMalloc(&d_bwt, n + 16));
+    GB_TRY(cudaMemset(d_bwt + n, 0, 16));
+    GB_TRY(cudaMalloc(&d_flag, n));
+    GB_TRY(cudaMalloc(&d_ridx, n * 4));
+    // rlfmi.rs:49-53 takes text[n - 1] where fm_index.rs takes 0: the same \0 for every valid text
+    k_bwt<<<grid(n), T>>>(d_text, d_sa, n, d_bwt);
+    k_run_flags<<<grid(n), T>>>(d_bwt, n, d_flag, d_ridx);
+    GB_TRY(cudaGetLastError());
+    GB_TRY(cudaMemcpy(&last_flag, d_flag + n - 1, 1, cudaMemcpyDeviceToHost));
+    GB_TRY((scan3::run<uint32_t, scan3::Sum32, true>(d_ridx, n, d_ridx, scan3::Sum32(), 0u, 0)));
+    GB_TRY(cudaMemcpy(&last_idx, d_ridx + n - 1, 4, cudaMemcpyDeviceToHost));
+    r = (uint64_t)last_idx + last_flag;
+    if (r == 0) {
+        rc = FMX_ERR_UNSUPPORTED;
+        goto fail;
+    }
+    GB_TRY(cudaMalloc(&d_starts, r * 4));
+    GB_TRY(cudaMalloc(&d_heads, r + 16));
+    GB_TRY(cudaMemset(d_heads + r, 0, 16));
+    GB_TRY(cudaMalloc(&d_heads_sorted, r));
+    GB_TRY(cudaMalloc(&d_order, r * 4));
+    GB_TRY(cudaMalloc(&d_order2, r * 4));
+    GB_TRY(cudaMalloc(&d_len, r * 4));
+    k_runs_scatter<<<grid(n), T>>>(d_flag, d_ridx, d_bwt, n, d_starts, d_heads, d_order);
+    GB_TRY(cudaGetLastError());
+    heads.resize(r);
+    GB_TRY(cudaMemcpy(heads.data(), d_heads, r, cudaMemcpyDeviceToHost));
+    if (heads[0] == 0) {  // the reference hits unreachable!() (rlfmi.rs:62); cannot happen for a valid text
+        rc = FMX_ERR_UNSUPPORTED;
+        goto fail;
+    }
+    for (uint64_t j = 0; j < r; j++) occ[heads[j]]++;
+    {
+        uint64_t sum = 0;
+        for (uint32_t c = 0; c < cs_len; c++) {  // cs over the run heads
+            cs[c] = (uint32_t)sum;
+            sum += occ[c];
+        }
+        cs[cs_len] = (uint32_t)r;
+    }
+    use_q4 = mc <= 4 && !q4_forbidden_by_env() && occ[0] <= FMX_MAX_EXC;
+    use_sym = !use_q4 && sym_layout_chosen(cs_len, r);
+    if (!use_q4 && !use_sym) {
+        rc = FMX_ERR_UNSUPPORTED;
+        goto fail;
+    }
+    nblk = use_q4 ? r / 64 + 1 : r / FMX_RB_BITS + 1;
+    cnt_entries = use_q4 ? nblk * 4 : nblk * cs_len;
+    if (cnt_entries < nblk_n) cnt_entries = nblk_n;  // the same buffer serves the block counts of b and bp
+
+    hdr.magic = FMX_BLOB_MAGIC;
+    hdr.version = FMX_BLOB_VERSION;
+    hdr.kind = FMX_KIND_RLFM;
+    hdr.n = n;
+    hdr.seq_len = r;
+    hdr.runs = r;
+    hdr.levels = L;
+    hdr.max_character = (uint32_t)mc;
+    hdr.cs_len = cs_len;
+    hdr.layout = use_q4 ? FMX_LAYOUT_QUAT : FMX_LAYOUT_SYM;
+    hdr.char_width = 1;
+    hdr.nexc = use_q4 ? (uint32_t)occ[0] : 0u;
+    hdr.sym_nblk = use_sym ? (uint32_t)nblk : 0u;
+    hdr.reserved[0] = (uint64_t)mode;
+    if (level >= 0) {
+        hdr.has_locate = 1;
+        uint32_t lvl = (uint32_t)level;
+        hdr.sa_word_size = log2_u64(n) + 1;
+        if (lvl >= 63 || n <= (1ull << lvl)) lvl = 0;  // sample.rs:28-31
+        hdr.sa_level = lvl;
+        hdr.sa_count = ((n - 1) >> lvl) + 1;
+    }
+    hdr.vsa_level = hdr.sa_level;
+    std::memset(bytes, 0, sizeof(bytes));
+    bytes[SEC_LEVEL0] = use_q4 ? nblk * 32 : sym_layout_bytes(cs_len, r);
+    if (use_sym) bytes[SEC_LEVEL0 + 1] = r;
+    if (use_q4) bytes[SEC_EXC] = occ[0] * 4;
+    bytes[SEC_ADJ] = (uint64_t)cs_len * 4;
+    bytes[SEC_CS] = (uint64_t)(cs_len + 1) * 4;
+    if (hdr.has_locate) bytes[SEC_SA] = hdr.sa_count * 4;
+    bytes[SEC_RL_B] = nblk_n * 32;
+    bytes[SEC_RL_BP] = nblk_n * 32;
+    bytes[SEC_RL_BSEL] = (r + 1) * 4;
+    bytes[SEC_RL_BPSEL] = (r + 1) * 4;
+    if (vp.dense_sa) {
+        bytes[SEC_VSA] = n * 4;
+        bytes[SEC_TEXT] = n;
+    }
+    layout_sections(hdr, bytes);
+    GB_TRY(cudaMalloc(&blob, hdr.total_bytes));
+    GB_TRY(cudaMemset(blob, 0, hdr.total_bytes));
+    GB_TRY(cudaMalloc(&d_cnt, cnt_entries * 4));
+
+    // b: run starts in L order
+    k_rb_pack<<<grid(nblk_n), T>>>(d_flag, n, nblk_n, reinterpret_cast<uint32_t *>(at(SEC_RL_B)), d_cnt);
+    GB_TRY(cudaGetLastError());
+    GB_TRY((scan3::run<uint32_t, scan3::Sum32, true>(d_cnt, nblk_n, d_cnt, scan3::Sum32(), 0u, 0)));
+    k_rb_counts<<<grid(nblk_n), T>>>(reinterpret_cast<uint32_t *>(at(SEC_RL_B)), d_cnt, nblk_n);
+    // select1(b, j) = first row of run j; [runs] = n (vers: select past the last one returns len, rlfmi.rs:285-309)
+    GB_TRY(cudaMemcpy(at(SEC_RL_BSEL), d_starts, r * 4, cudaMemcpyDeviceToDevice));
+    GB_TRY(cudaMemcpy(at(SEC_RL_BSEL) + r * 4, &n32, 4, cudaMemcpyHostToDevice));
+    // bp: runs grouped by head, stably (rlfmi.rs:70-83) = a stable sort of the runs by their head symbol
+    {
+        GB_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_heads, d_heads_sorted, d_order, d_order2, (long long)r, 0, 8));
+        GB_TRY(cudaMalloc(&d_tmp, tmp_bytes));
+        GB_TRY(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_heads, d_heads_sorted, d_order, d_order2, (long long)r, 0, 8));
+    }
+    k_sorted_run_len<<<grid(r), T>>>(d_order2, d_starts, r, n, d_len);
+    GB_TRY(cudaGetLastError());
+    GB_TRY((scan3::run<uint32_t, scan3::Sum32, true>(d_len, r, d_len, scan3::Sum32(), 0u, 0)));  // position of every sorted run in bp
+    GB_TRY(cudaMemcpy(at(SEC_RL_BPSEL), d_len, r * 4, cudaMemcpyDeviceToDevice));
+    GB_TRY(cudaMemcpy(at(SEC_RL_BPSEL) + r * 4, &n32, 4, cudaMemcpyHostToDevice));
+    GB_TRY(cudaMemset(d_flag, 0, n));
+    k_mark_bp<<<grid(r), T>>>(d_len, r, d_flag);
+    k_rb_pack<<<grid(nblk_n), T>>>(d_flag, n, nblk_n, reinterpret_cast<uint32_t *>(at(SEC_RL_BP)), d_cnt);
+    GB_TRY(cudaGetLastError());
+    GB_TRY((scan3::run<uint32_t, scan3::Sum32, true>(d_cnt, nblk_n, d_cnt, scan3::Sum32(), 0u, 0)));
+    k_rb_counts<<<grid(nblk_n), T>>>(reinterpret_cast<uint32_t *>(at(SEC_RL_BP)), d_cnt, nblk_n);
+    // the run heads' own rank structure
+    if (use_q4) {
+        k_q4_pack<<<grid(nblk), T>>>(d_heads, r, nblk, reinterpret_cast<uint32_t *>(at(SEC_LEVEL0)), d_cnt);
+        GB_TRY(cudaGetLastError());
+        for (int c = 0; c < 4; c++)
+            GB_TRY((scan3::run<uint32_t, scan3::Sum32, true>(d_cnt + (uint64_t)c * nblk, nblk, d_cnt + (uint64_t)c * nblk, scan3::Sum32(), 0u, 0)));
+        k_q4_counts<<<grid(nblk), T>>>(reinterpret_cast<uint32_t *>(at(SEC_LEVEL0)), d_cnt, nblk);
+        if (occ[0]) {
+            GB_TRY(cudaMalloc(&d_rows, FMX_MAX_EXC * 4));
+            GB_TRY(cudaMalloc(&d_count, 4));
+            GB_TRY(cudaMemset(d_count, 0, 4));
+            k_zero_rows<<<grid(r), T>>>(d_heads, r, d_rows, FMX_MAX_EXC, d_count);
+            GB_TRY(cudaGetLastError());
+            GB_TRY(cudaMemcpy(&nz, d_count, 4, cudaMemcpyDeviceToHost));
+            if (nz != occ[0]) {
+                err = "GPU index build: run heads hold another number of zeros than counted";
+                rc = FMX_ERR_CUDA;
+                goto fail;
+            }
+            rows.resize(nz);
+            GB_TRY(cudaMemcpy(rows.data(), d_rows, (uint64_t)nz * 4, cudaMemcpyDeviceToHost));
+            std::sort(rows.begin(), rows.end());
+            GB_TRY(cudaMemcpy(at(SEC_EXC), rows.data(), (uint64_t)nz * 4, cudaMemcpyHostToDevice));
+        }
+    } else {
+        const uint64_t sym_entries = nblk * cs_len;
+        k_sym_pack<<<(unsigned)((nblk + 7) / 8), 256>>>(d_heads, r, nblk, cs_len, reinterpret_cast<uint32_t *>(at(SEC_LEVEL0)), d_cnt);
+        GB_TRY(cudaGetLastError());
+        GB_TRY((scan3::run<uint32_t, scan3::Sum32, true>(d_cnt, sym_entries, d_cnt, scan3::Sum32(), 0u, 0)));
+        k_sym_counts<<<grid(sym_entries), T>>>(reinterpret_cast<uint32_t *>(at(SEC_LEVEL0)), d_cnt, nblk, sym_entries);
+        GB_TRY(cudaMemcpy(at(SEC_LEVEL0 + 1), d_heads, r, cudaMemcpyDeviceToDevice));
+    }
+    GB_TRY(cudaGetLastError());
+    GB_TRY(cudaMemcpy(at(SEC_ADJ), adj.data(), adj.size() * 4, cudaMemcpyHostToDevice));
+    GB_TRY(cudaMemcpy(at(SEC_CS), cs.data(), cs.size() * 4, cudaMemcpyHostToDevice));
+    if (hdr.has_locate) k_samples<<<grid(hdr.sa_count), T>>>(d_sa, hdr.sa_count, hdr.sa_level, reinterpret_cast<uint32_t *>(at(SEC_SA)));
+    if (vp.dense_sa) {
+        GB_TRY(cudaMemcpy(at(SEC_VSA), d_sa, n * 4, cudaMemcpyDeviceToDevice));
+        GB_TRY(cudaMemcpy(at(SEC_TEXT), d_text, n, cudaMemcpyDeviceToDevice));
+    }
+    GB_TRY(cudaGetLastError());
+    GB_TRY(cudaMemcpy(blob, &hdr, sizeof(hdr), cudaMemcpyHostToDevice));
+    GB_TRY(cudaDeviceSynchronize());
+    *d_blob_out = blob;
+    *hdr_out = hdr;
+    blob = nullptr;
+    rc = 0;
+fail:
+    cudaFree(d_text);
+    cudaFree(d_bwt);
+    cudaFree(d_flag);
+    cudaFree(d_heads);
+    cudaFree(d_heads_sorted);
+    cudaFree(d_sa);
+    cudaFree(d_ridx);
+    cudaFree(d_starts);
+    cudaFree(d_order);
+    cudaFree(d_order2);
+    cudaFree(d_len);
+    cudaFree(d_cnt);
+    cudaFree(d_rows);
+    cudaFree(d_count);
+    cudaFree(d_tmp);
     cudaFree(blob);
     if (rc) cudaGetLastError();
     return rc;

@@ -38,6 +38,7 @@ SIGNATURES = {
     "fmx_index_sample_level": (_u32, [_vp]),
     "fmx_index_sectors_per_rank": (_u32, [_vp]),
     "fmx_index_kmer_k": (_u32, [_vp, _int]),
+    "fmx_index_kmer_entry_bytes": (_u32, [_vp]),
     "fmx_index_layout": (_u32, [_vp]),
     "fmx_index_char_width": (_u32, [_vp]),
     "fmx_index_has_text": (_int, [_vp]),

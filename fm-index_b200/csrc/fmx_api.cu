@@ -100,6 +100,8 @@ struct fmx_index {
     uint8_t *d_kmer_steps = nullptr;
     uint32_t kmer_k = 0;
     uint64_t kmer_entries = 0;
+    uint4 *d_big_tab4 = nullptr;           // the large table with 16-byte entries (text context of one-row entries); replaces d_big_tab
+    int opt_table_ctx = 1;                 // 0: keep 8-byte entries (A/B)
     uint2 *d_big_tab = nullptr;            // the large (HBM-resident) table
     uint8_t *d_big_steps = nullptr;
     uint32_t big_k = 0;
@@ -434,6 +436,7 @@ int fmx_index_clone(const fmx_index *src, int device, fmx_index **out) {
     if (e == cudaSuccess) e = dup(src->d_kmer_tab, src->kmer_entries * sizeof(uint2), reinterpret_cast<void **>(&idx->d_kmer_tab));
     if (e == cudaSuccess) e = dup(src->d_kmer_steps, src->kmer_entries, reinterpret_cast<void **>(&idx->d_kmer_steps));
     if (e == cudaSuccess) e = dup(src->d_big_tab, src->big_entries * sizeof(uint2), reinterpret_cast<void **>(&idx->d_big_tab));
+    if (e == cudaSuccess) e = dup(src->d_big_tab4, src->d_big_tab4 ? src->big_entries * sizeof(uint4) : 0, reinterpret_cast<void **>(&idx->d_big_tab4));
     if (e == cudaSuccess) e = dup(src->d_big_steps, src->big_entries, reinterpret_cast<void **>(&idx->d_big_steps));
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -553,6 +556,7 @@ void fmx_index_free(fmx_index *idx) {
     if (idx->d_kmer_tab) cudaFree(idx->d_kmer_tab);
     if (idx->d_kmer_steps) cudaFree(idx->d_kmer_steps);
     if (idx->d_big_tab) cudaFree(idx->d_big_tab);
+    if (idx->d_big_tab4) cudaFree(idx->d_big_tab4);
     if (idx->d_big_steps) cudaFree(idx->d_big_steps);
     if (idx->stream) cudaStreamDestroy(idx->stream);
     for (auto &e : idx->pev)
@@ -581,6 +585,14 @@ int fmx_index_set_option(fmx_index *idx, const char *key, int64_t value) {
     else if (k == "search_phased") idx->opt_phased = value < 0 || value > 2 ? 2 : (int)value;
     else if (k == "locate_dense") idx->opt_locate_dense = value != 0;
     else if (k == "extract_text") idx->opt_extract_text = value != 0;
+    else if (k == "table_ctx") {  // 16-byte table entries on / off: takes effect by rebuilding the large table
+        idx->opt_table_ctx = value != 0;
+        if (idx->big_entries) {
+            CUDA_TRY(cudaSetDevice(idx->device));
+            int rc = build_big_table(idx, idx->big_entries * 9);
+            if (rc) return rc;
+        }
+    }
     else if (k == "phase_timing") idx->opt_phase_timing = value != 0;
     else if (k == "pipeline_chunk") idx->opt_pipeline_chunk = value > 0 ? (uint64_t)value : 0;
     else if (k == "l2_fetch_granularity") {
@@ -597,9 +609,10 @@ int fmx_index_set_option(fmx_index *idx, const char *key, int64_t value) {
 
 uint64_t fmx_index_len(const fmx_index *idx) { return idx ? idx->hdr.n : 0; }
 uint64_t fmx_index_device_bytes(const fmx_index *idx) {
-    return idx ? idx->hdr.total_bytes + (idx->kmer_entries + idx->big_entries) * 9 : 0;
+    return idx ? idx->hdr.total_bytes + idx->kmer_entries * 9 + idx->big_entries * (idx->d_big_tab4 ? 17 : 9) : 0;
 }
 uint32_t fmx_index_kmer_k(const fmx_index *idx, int big) { return idx ? (big ? idx->big_k : idx->kmer_k) : 0; }
+uint32_t fmx_index_kmer_entry_bytes(const fmx_index *idx) { return idx && idx->big_entries ? (idx->d_big_tab4 ? 16u : 8u) : 0u; }
 uint64_t fmx_index_pieces_count(const fmx_index *idx) { return idx ? idx->hdr.ndoc : 0; }
 int fmx_index_kind(const fmx_index *idx) { return idx ? (int)idx->hdr.kind : -1; }
 int fmx_index_has_locate(const fmx_index *idx) { return idx ? (int)idx->hdr.has_locate : 0; }
@@ -820,8 +833,10 @@ static void pick_k(uint64_t base, uint64_t max_entries, uint32_t &k, uint64_t &e
 // the large table: as many characters as `budget_bytes` of HBM buy (9 bytes per entry)
 static int build_big_table(fmx_index *idx, uint64_t budget_bytes) {
     if (idx->d_big_tab) cudaFree(idx->d_big_tab);
+    if (idx->d_big_tab4) cudaFree(idx->d_big_tab4);
     if (idx->d_big_steps) cudaFree(idx->d_big_steps);
     idx->d_big_tab = nullptr;
+    idx->d_big_tab4 = nullptr;
     idx->d_big_steps = nullptr;
     idx->big_k = 0;
     idx->big_entries = 0;
@@ -838,6 +853,33 @@ static int build_big_table(fmx_index *idx, uint64_t budget_bytes) {
     if (rc) return rc;
     idx->big_k = k;
     idx->big_entries = entries;
+    // DNA-sized alphabets on HBM-rich indexes: 16-byte entries that carry the text in front of one-row ranges, so that a
+    // pattern with <= 16 characters left after the table is finished without a text request (kernels.cuh big_tab4).
+    // Twice the table's HBM; only when half of what is free still holds it.
+    if (idx->tab_embed && idx->opt_table_ctx && !env_flag("FMX_NO_TABLE_CTX") && idx->hdr.max_character <= 4 && idx->dev.text) {
+        size_t f2 = 0, t2 = 0;
+        const uint64_t wide_b = entries * sizeof(uint4), narrow_b = entries * sizeof(uint2);
+        // both forms are resident while the entries are copied over; afterwards at least as much must stay free as the table takes
+        if (cudaMemGetInfo(&f2, &t2) == cudaSuccess && wide_b + (8ull << 30) <= f2 && wide_b <= (f2 + narrow_b) / 2) {
+            uint4 *t4 = nullptr;
+            if (cudaMalloc(&t4, entries * sizeof(uint4)) == cudaSuccess) {
+                k_table_widen<<<grid_for(entries, 256), 256, 0, idx->stream>>>(idx->d_big_tab, entries, idx->dev.text, t4);
+                g_launches.fetch_add(1, std::memory_order_relaxed);
+                if (cudaStreamSynchronize(idx->stream) == cudaSuccess) {
+                    cudaFree(idx->d_big_tab);
+                    idx->d_big_tab = nullptr;
+                    idx->d_big_tab4 = t4;
+                } else {
+                    cudaGetLastError();
+                    cudaFree(t4);
+                }
+            } else {
+                cudaGetLastError();
+            }
+        } else {
+            cudaGetLastError();
+        }
+    }
     return 0;
 }
 
@@ -921,8 +963,9 @@ static int make_search_args(const fmx_index *idx, int mode, const PatSrc &ps, ui
     a.kmer_tab = tab_ok ? idx->d_kmer_tab : nullptr;
     a.kmer_steps = tab_ok ? idx->d_kmer_steps : nullptr;
     a.kmer_k = tab_ok ? idx->kmer_k : 0;
-    const bool big_ok = tab_ok && idx->d_big_tab && idx->opt_kmer_big;
+    const bool big_ok = tab_ok && (idx->d_big_tab || idx->d_big_tab4) && idx->opt_kmer_big;
     a.big_tab = big_ok ? idx->d_big_tab : nullptr;
+    a.big_tab4 = big_ok ? idx->d_big_tab4 : nullptr;
     a.big_steps = big_ok ? idx->d_big_steps : nullptr;
     a.big_k = big_ok ? idx->big_k : 0;
     a.tab_embed = tab_ok ? idx->tab_embed : 0u;

@@ -55,6 +55,11 @@ __device__ __forceinline__ uint2 ldg64_s(const uint2 *p) {
     asm(FMX_LD_S ".v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
     return v;
 }
+__device__ __forceinline__ uint4 ldg128_s(const uint4 *p) {
+    uint4 v;
+    asm volatile(FMX_LD_S ".v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ uint32_t ldg8_s(const uint8_t *p) {
     uint32_t v;
     asm(FMX_LD_S ".u8 %0, [%1];" : "=r"(v) : "l"(p));
@@ -788,6 +793,12 @@ struct SearchArgs {
     const uint2 *big_tab;
     const uint8_t *big_steps;
     uint32_t big_k;
+    // the large table with 16-byte entries (alphabets of <= 4 symbols, HBM-rich indexes): {s, e | FLAG + SA[s], ctx, ctx_len}.
+    // For a one-row entry, ctx holds the up to 16 text characters IN FRONT of the row's suffix -- character
+    // text[SA[s] - 1 - j] as the 2-bit code c - 1 in bits [2j, 2j + 2) -- and ctx_len how many of them exist (the
+    // window ends at the start of the text or in front of a \0).  A pattern with no more than ctx_len characters left is
+    // then finished by one 32-bit comparison: the verify tail without its text request.  Replaces big_tab when set.
+    const uint4 *big_tab4;
     uint8_t *steps_out;             // nullable: per-pattern executed iterations (table build)
     // nullable: order[t] = pattern handled by thread t.  Patterns bucketed by their k-mer table index
     // (= sorted by SA range start to within one k-mer range) touch the index quasi-sequentially, so
@@ -950,11 +961,12 @@ __device__ __forceinline__ bool kmer_index4(Reader &pr, uint32_t len, uint32_t K
 // pattern; otherwise the caller walks from (s0, e0) so errors show up (or not) exactly as in the reference
 template <class Reader>
 __device__ __forceinline__ bool kmer_lookup(const SearchArgs &a, uint32_t maxc, Reader &q, uint32_t &len,
-                                            uint32_t &s, uint32_t &e, uint32_t &it, uint32_t *pos = nullptr) {
+                                            uint32_t &s, uint32_t &e, uint32_t &it, uint32_t *pos = nullptr,
+                                            uint32_t *ctx = nullptr, uint32_t *ctx_len = nullptr) {
     const uint2 *tab = nullptr;
     const uint8_t *stp = nullptr;
     uint32_t K = 0;
-    if (a.big_tab != nullptr && len >= a.big_k) {
+    if ((a.big_tab != nullptr || a.big_tab4 != nullptr) && len >= a.big_k) {
         tab = a.big_tab;
         stp = a.big_steps;
         K = a.big_k;
@@ -971,7 +983,15 @@ __device__ __forceinline__ bool kmer_lookup(const SearchArgs &a, uint32_t maxc, 
     } else if (!kmer_index(q, len, K, maxc, idx)) {
         return false;
     }
-    uint2 t = ldg64_s(tab + idx);
+    uint2 t;
+    if (tab == a.big_tab && a.big_tab4 != nullptr) {  // 16-byte entries: the row's text context rides along
+        const uint4 t4 = ldg128_s(a.big_tab4 + idx);
+        t = make_uint2(t4.x, t4.y);
+        if (ctx) *ctx = t4.z;
+        if (ctx_len) *ctx_len = t4.w;
+    } else {
+        t = ldg64_s(tab + idx);
+    }
     s = t.x;
     e = t.y;
     if (a.tab_embed && (e & FMX_TAB_POS_FLAG)) {  // one-row range: y carries SA[s]

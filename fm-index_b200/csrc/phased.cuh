@@ -243,25 +243,36 @@ __device__ __forceinline__ void query_one(const FmxDev &ix, const Tabs<LAYOUT> &
                                           uint32_t &s, uint32_t &e, uint32_t &hint, unsigned long long &steps,
                                           unsigned long long &reqs) {
     const SearchArgs &a = g.a;
-    uint32_t it = 0, pos = FMX_NOHINT, k = len;
-    if (kmer_lookup(a, ix.max_character, rd, k, s, e, it, &pos)) reqs += (s == e && a.work) ? 2u : 1u;
+    uint32_t it = 0, pos = FMX_NOHINT, k = len, ctx = 0, ctx_len = 0;
+    if (kmer_lookup(a, ix.max_character, rd, k, s, e, it, &pos, &ctx, &ctx_len)) reqs += (s == e && a.work) ? 2u : 1u;
     bool armed = a.verify != 0;
     hint = FMX_NOHINT;
+    if (pos == FMX_NOHINT) ctx_len = 0;  // the context belongs to the row of a one-row entry
     while (k > 0) {  // the reference loop (wrapper.rs:103-124): the range is tested after a step, never before
-        if (armed && e - s == 1u && k >= FMX_VERIFY_MIN_DENSE) {
+        if (armed && e - s == 1u && (k >= FMX_VERIFY_MIN_DENSE || k <= ctx_len)) {
             if (pos == FMX_NOHINT) {
                 pos = ldg32_s(ix.vsa + s);
                 reqs++;
             }
-            uint32_t matched = 0, c = 0;
-            if (pos >= k) {
+            uint32_t matched = 0, c = 0, pk;
+            bool compared = false;
+            if (k <= ctx_len && kmer_index4(rd, k, k, pk)) {
+                // the table entry carries the characters in front of the row: the rest of the pattern (as 2-bit codes, last
+                // character lowest -- exactly its k-mer index) against them, no text request
+                const uint32_t diff = (pk ^ ctx) & (k < 16u ? (1u << (2u * k)) - 1u : 0xFFFFFFFFu);
+                matched = diff ? (uint32_t)(__ffs((int)((diff | (diff >> 1)) & 0x55555555u)) - 1) >> 1 : k;
+                c = matched < k ? ((pk >> (2u * matched)) & 3u) + 1u : 0u;  // the pattern character at the stop
+                compared = true;
+            } else if (pos >= k) {
                 TextReader tr(ix.text + (pos - k), k);
                 matched = match_backward(rd, tr, k, c);
                 const uint32_t last = pos - 1u, first = pos - (matched < k ? matched + 1u : k);
                 reqs += (last >> 5) - (first >> 5) + 1u;
+                compared = true;
             }
+            ctx_len = 0;
             it += matched;
-            if (pos >= k && matched == k) {  // the whole rest of the pattern stands in the text in front of the row
+            if (compared && matched == k) {  // the whole rest of the pattern stands in the text in front of the row
                 hint = pos - k;
                 if (g.want_rows) {
                     s = ldg32_s(ix.isa + hint);
@@ -273,7 +284,7 @@ __device__ __forceinline__ void query_one(const FmxDev &ix, const Tabs<LAYOUT> &
                 k = 0;
                 break;
             }
-            if (pos >= k && !g.want_rows && c != 0u && c <= ix.max_character) {  // true mismatch: the next iteration empties the range
+            if (compared && !g.want_rows && c != 0u && c <= ix.max_character) {  // true mismatch: the next iteration empties the range
                 it++;
                 s = e = 0;
                 break;
@@ -295,6 +306,7 @@ __device__ __forceinline__ void query_one(const FmxDev &ix, const Tabs<LAYOUT> &
         if (a.work) reqs += pair_requests<LAYOUT>(ix, s, e);
         lf_map2_pair<KIND, LAYOUT>(ix, tb, c, s, e);
         pos = FMX_NOHINT;
+        ctx_len = 0;
         it++;
         k--;
         if (s == e) break;
@@ -432,6 +444,25 @@ __global__ void k_table_embed(uint2 *tab, uint64_t entries, const uint32_t *vsa)
     if (t >= entries) return;
     const uint2 v = tab[t];
     if (v.y == v.x + 1u) tab[t] = make_uint2(v.x, FMX_TAB_POS_FLAG | ldg32_s(vsa + v.x));
+}
+
+// 16-byte entries from 8-byte ones (SearchArgs::big_tab4): a one-row entry also gets the up to 16 text characters in
+// front of its row as 2-bit codes (alphabets of <= 4 symbols), stopping at the start of the text or in front of a \0
+__global__ void k_table_widen(const uint2 *tab, uint64_t entries, const uint8_t *text, uint4 *tab4) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= entries) return;
+    const uint2 v = tab[t];
+    uint32_t ctx = 0, len = 0;
+    if (v.y & FMX_TAB_POS_FLAG) {
+        const uint32_t pos = v.y & ~FMX_TAB_POS_FLAG;
+        while (len < 16u && len < pos) {
+            const uint32_t ch = ldg8_s(text + (pos - 1u - len));
+            if (ch == 0u || ch > 4u) break;
+            ctx |= (ch - 1u) << (2u * len);
+            len++;
+        }
+    }
+    tab4[t] = make_uint4(v.x, v.y, ctx, len);
 }
 
 }  // namespace fmx

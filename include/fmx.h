@@ -134,7 +134,10 @@ int fmx_build_suffix_array_device(const void *text, uint64_t n, uint32_t char_wi
  * locate kernel; 2 = stable warp-level compaction), "verify" 0|1 (seed-and-verify tail of the search),
  * "stage_patterns" 0|1 (fixed-length pattern bytes through shared memory), "locate_expand" 0|1|2 (hit rows: auto / always expanded by scans / always found by
  * binary search inside the locate kernel), "locate_ranges" -1|0|1 (walk whole SA sub-ranges instead of
- * single rows: auto = RLFM indexes whose patterns average >= 8 matches / never / always).  Environment at construction time: FMX_FORCE_WAVELET=1
+ * single rows: auto = RLFM indexes whose patterns average >= 8 matches / never / always), "extract_text" 0|1
+ * (extraction from the resident text), "table_ctx" 0|1 (16-byte entries of the large k-mer table that carry the 16 text
+ * characters in front of one-row ranges: a pattern with <= 16 characters left after the table is finished by ONE
+ * request; rebuilds the table; FMX_NO_TABLE_CTX=1 at construction time).  Environment at construction time: FMX_FORCE_WAVELET=1
  * keeps the binary wavelet matrix; FMX_SYM_BUDGET_MB caps the per-symbol bit-vector layout (default
  * 49152; 0 = use the quaternary wavelet matrix instead); FMX_VERIFY_BUDGET_MB caps the dense
  * seed-and-verify structures (text + full suffix array + inverse, 9 bytes per symbol; default 32768),
@@ -165,6 +168,8 @@ int fmx_index_has_text(const fmx_index *idx);
 uint32_t fmx_index_char_width(const fmx_index *idx);
 /* characters memoised by the small (big = 0) / large (big = 1) k-mer table of fresh searches; 0 = none */
 uint32_t fmx_index_kmer_k(const fmx_index *idx, int big);
+/* bytes per entry of the large table: 8 ((s, e) or (s, position)), 16 (+ the text in front of one-row ranges), 0 = no such table */
+uint32_t fmx_index_kmer_entry_bytes(const fmx_index *idx);
 
 /* ---------------------------------------------------------------- search / count
  * Batched SearchIndex::search / search_prefix / search_suffix / search_exact and

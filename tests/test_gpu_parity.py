@@ -832,6 +832,76 @@ def test_rich_mode_query_parity(kind, mc, env, monkeypatch):
         assert index.query_batch([bytes([1])], locate=False, counts=True)["counts"][0] > 0   # still usable
 
 
+@pytest.mark.parametrize("kind", [orc.FM, orc.MULTI])
+def test_table_entries_with_text_context(kind):
+    """The large k-mer table of HBM-rich DNA indexes has 16-byte entries whose one-row ranges carry the 16 text characters
+    in front of the row (SearchArgs::big_tab4): patterns with <= 16 characters left after the table are finished without a
+    text request.  Same ranges, counts, ordered positions, piece ids and executed step counts as the oracle -- with the
+    context entries (default), and with 8-byte entries (option table_ctx = 0) -- for pattern lengths on both sides of
+    k and k + 16, mismatches at every depth, patterns that run off the start of the text or across a piece boundary,
+    and invalid characters."""
+    rng = np.random.default_rng(900 + kind)
+    n = 4_300_000                                               # >= 2^22: the large table exists
+    text = np.append(rng.integers(1, 5, n, dtype=np.uint8), np.uint8(0))
+    if kind == orc.MULTI:
+        text[rng.integers(40, n - 40, 300) // 2 * 2] = 0
+    index = KINDS[kind][1].new(fmx.Text.with_max_character(text, 4), 2, mode=fmx.MODE_RICH)
+    index.set_option("kmer_budget_mb", 200)                     # k = 12: 16.7 M entries, 0.26 occurrences per 12-mer
+    assert index.kmer_k(True) == 12
+    oracle = _oracle_from_gpu_sa(text, kind, 2, 4)
+    pats = []
+    for t in range(60_000):
+        m = int(rng.integers(1, 50))
+        p0 = int(rng.integers(0, n - m))
+        pat = text[p0:p0 + m].copy()
+        v = t % 8
+        if v in (1, 5):                                          # one mismatch, anywhere
+            j = int(rng.integers(0, m))
+            pat[j] = pat[j] % 4 + 1
+        elif v == 2:                                             # runs off the start of the text
+            pat = np.concatenate([rng.integers(1, 5, int(rng.integers(1, 20)), dtype=np.uint8), text[:m]])
+        elif v == 3:
+            pat = rng.integers(1, 5, m, dtype=np.uint8)
+        elif v == 4 and kind == orc.MULTI and m > 13:            # a \0 inside the part the context would cover
+            pat[int(rng.integers(0, m - 12))] = 0
+        pats.append(pat.tobytes())
+    pats += [text[:30].tobytes(), text[:12].tobytes(), text[1:29].tobytes(), b"", bytes([1])]
+    flat, off = orc.pack_patterns(pats)
+    modes = [fmx.SEARCH] + ([fmx.SEARCH_PREFIX] if kind == orc.MULTI else [])
+    index.set_option("count_work", 1)
+    for ctx in (1, 0):
+        index.set_option("table_ctx", ctx)
+        assert index.kmer_k(True) == 12
+        for mode in modes:
+            po = mode == fmx.SEARCH_PREFIX
+            s, e, steps = oracle.search_batch(flat, off, mode, want_steps=True)
+            ooff, opos, opid = oracle.locate_batch(s, e, prefix_only=po, want_piece_ids=kind == orc.MULTI)
+            for rows in (True, False):
+                r = index.query_batch(pats, mode, rows=rows, counts=True, piece_ids=kind == orc.MULTI, capacity=int(ooff[-1]) + 8)
+                if rows:
+                    assert np.array_equal(r["s"], s) and np.array_equal(r["e"], e), (ctx, mode)
+                assert np.array_equal(r["counts"], np.where(e > s, e - s, 0)), (ctx, mode, rows)
+                assert np.array_equal(r["hit_off"], ooff) and np.array_equal(r["positions"], opos), (ctx, mode, rows)
+                if kind == orc.MULTI:
+                    assert np.array_equal(r["piece_ids"], opid)
+                if not po:
+                    assert index.last_work()[0] == int(steps.sum()), (ctx, mode, rows)
+        bad = bytearray(text[1000:1028].tobytes())               # an invalid character inside the context window
+        bad[5] = 5
+        for rows in (True, False):
+            if 0 not in bad:
+                with pytest.raises(IndexError):
+                    index.query_batch([bytes(bad)], rows=rows)
+    fixed = np.stack([text[i:i + 28] for i in rng.integers(0, n - 28, 20_000)])
+    fixed = fixed[~(fixed == 0).any(axis=1)]
+    ref = index.query_batch(fixed, rows=True, counts=True)
+    index.set_option("table_ctx", 1)
+    packed = fmx.pack_patterns(fixed, 2)
+    r = index.query_batch(packed, rows=True, counts=True, packed_bits=2, fixed_len=28)   # the packed reader through the same path
+    for k in ("s", "e", "counts", "hit_off", "positions"):
+        assert np.array_equal(r[k], ref[k]), k
+
+
 def test_rich_mode_many_hits_and_pipeline():
     """patterns with thousands of matches (k_emit_big), a chunked pipeline with a position-capacity guess that is too
     small for the first chunks, a too-small caller capacity"""

@@ -507,7 +507,9 @@ int build_blob(const uint8_t *text, uint64_t n, uint64_t mc, int kind, int level
             sa.resize(n);
             std::string gerr;
             int grc = gpu_suffix_array(text, n, L, sa_device, sa.data(), nullptr, gerr);
-            if (grc) {
+            if (grc == FMX_ERR_OOM) {  // the device has no room for the sorter's working set: sort on the host
+                suffix_array_u32(text, n, sa);
+            } else if (grc) {
                 err = "GPU suffix array construction failed: " + gerr;
                 return grc;
             }

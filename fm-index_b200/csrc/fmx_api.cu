@@ -492,7 +492,9 @@ int fmx_index_build_ex(const void *text, uint64_t n, uint32_t char_width, uint64
                       ? gpu_build_rlfm_blob(static_cast<const uint8_t *>(text), n, max_character, level, mode, device, &d_blob, &hdr, err)
                       : gpu_build_blob(static_cast<const uint8_t *>(text), n, max_character, kind, level, mode, device, &d_blob, &hdr, err);
         if (grc == 0) return adopt(hdr, d_blob, device, out);
-        if (grc != FMX_ERR_UNSUPPORTED) return fail(grc, err);
+        // not its case, or not enough free HBM for the construction's working set (32 bytes per symbol while sorting):
+        // the host builder takes over
+        if (grc != FMX_ERR_UNSUPPORTED && grc != FMX_ERR_OOM) return fail(grc, err);
         err.clear();
     }
     HostBlob b;

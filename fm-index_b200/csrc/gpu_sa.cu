@@ -68,6 +68,7 @@ __global__ void k_sa_make_keys(const uint32_t *sa, const uint32_t *grp, const ui
         cudaError_t _e = (expr);                                                      \
         if (_e != cudaSuccess) {                                                      \
             err = std::string(#expr) + ": " + cudaGetErrorString(_e);                 \
+            if (_e == cudaErrorMemoryAllocation) rc = FMX_ERR_OOM;                    \
             goto fail;                                                                \
         }                                                                             \
     } while (0)

@@ -851,7 +851,7 @@ def test_table_entries_with_text_context(kind):
     oracle = _oracle_from_gpu_sa(text, kind, 2, 4)
     pats = []
     for t in range(60_000):
-        m = int(rng.integers(1, 50))
+        m = int(rng.integers(9, 50))                              # >= 9: a few dozen matches at most (the oracle locates every one)
         p0 = int(rng.integers(0, n - m))
         pat = text[p0:p0 + m].copy()
         v = t % 8
@@ -865,8 +865,9 @@ def test_table_entries_with_text_context(kind):
         elif v == 4 and kind == orc.MULTI and m > 13:            # a \0 inside the part the context would cover
             pat[int(rng.integers(0, m - 12))] = 0
         pats.append(pat.tobytes())
-    pats += [text[:30].tobytes(), text[:12].tobytes(), text[1:29].tobytes(), b"", bytes([1])]
+    pats += [text[:30].tobytes(), text[:12].tobytes(), text[1:29].tobytes()]
     flat, off = orc.pack_patterns(pats)
+    zeros = np.nonzero(text == 0)[0]
     modes = [fmx.SEARCH] + ([fmx.SEARCH_PREFIX] if kind == orc.MULTI else [])
     index.set_option("count_work", 1)
     for ctx in (1, 0):
@@ -875,7 +876,10 @@ def test_table_entries_with_text_context(kind):
         for mode in modes:
             po = mode == fmx.SEARCH_PREFIX
             s, e, steps = oracle.search_batch(flat, off, mode, want_steps=True)
-            ooff, opos, opid = oracle.locate_batch(s, e, prefix_only=po, want_piece_ids=kind == orc.MULTI)
+            ooff, opos, _ = oracle.locate_batch(s, e, prefix_only=po)
+            # piece of a position = zeros before it (multi_pieces.rs:287-296; the literal walk is pinned in other tests and
+            # would take piece-length LF steps per hit here)
+            opid = np.searchsorted(zeros, opos, side="left").astype(np.uint64)
             for rows in (True, False):
                 r = index.query_batch(pats, mode, rows=rows, counts=True, piece_ids=kind == orc.MULTI, capacity=int(ooff[-1]) + 8)
                 if rows:

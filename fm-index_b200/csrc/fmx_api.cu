@@ -121,6 +121,7 @@ struct fmx_index {
     int opt_bucket = 0;               // 1: visit the batch in k-mer bucket order (lost the A/B, kept for experiments); -1 auto
     int opt_count_work = 0;           // 1: kernels count executed search iterations / LF steps (fmx_last_work)
     int opt_phased = 2;               // dense verify structures: 2 = k_query_fused (one kernel), 1 = the three phased kernels, 0 = k_search
+    int opt_order_by_length = 0;      // 1: ragged batches through the fused kernel in order of pattern length (A/B: lost, see search_phased)
     int opt_extract_text = 1;         // 0: extraction by LF / FL steps even when text and suffix array are resident (A/B)
     int opt_locate_dense = 1;         // 0: LF walks to the samples even when the full suffix array is resident (A/B)
     uint32_t tab_embed = 0;           // one-row k-mer table entries carry the row's text position (SearchArgs::tab_embed)
@@ -587,6 +588,7 @@ int fmx_index_set_option(fmx_index *idx, const char *key, int64_t value) {
     else if (k == "search_phased") idx->opt_phased = value < 0 || value > 2 ? 2 : (int)value;
     else if (k == "locate_dense") idx->opt_locate_dense = value != 0;
     else if (k == "extract_text") idx->opt_extract_text = value != 0;
+    else if (k == "order_by_length") idx->opt_order_by_length = value > 0 ? 1 : 0;
     else if (k == "table_ctx") {  // 16-byte table entries on / off: takes effect by rebuilding the large table
         idx->opt_table_ctx = value != 0;
         if (idx->big_entries) {
@@ -993,6 +995,25 @@ static int search_phased(const fmx_index *idx, DevBuf *buf, const SearchArgs &a,
         PhasedArgs g;
         std::memset(&g, 0, sizeof(g));
         g.a = a;
+        // Option "order_by_length": ragged byte patterns visited in order of length, so that a warp's lanes run loops of
+        // equal trip counts.  Measured on config 5 (100 M patterns of 8..64 bytes): 23.7 ms against 16.6 ms in input
+        // order -- the scattered pattern reads and result writes cost more than the convergence buys
+        // (profiles/r02_c10b_bench_cfg5_order{0,1}.json).  Off by default.
+        const bool by_len = a.pat_off && !a.packed_bits && !a.order && npat < 0xFFFFFFFFull && idx->opt_order_by_length == 1;
+        if (by_len) {
+            if ((rc = buf[B_BHIST].ensure(FMX_LEN_BUCKETS * 4 + 16))) return rc;
+            if ((rc = buf[B_ORDER].ensure(npat * 4))) return rc;
+            uint32_t *d_hist = buf[B_BHIST].as<uint32_t>();
+            CUDA_TRY(cudaMemsetAsync(d_hist, 0, FMX_LEN_BUCKETS * 4, st));
+            uint64_t hb = (npat + 255) / 256;
+            if (hb > (uint64_t)idx->sms * 16) hb = (uint64_t)idx->sms * 16;
+            k_len_hist<<<(unsigned)hb, 256, 0, st>>>(a.pat_off, npat, d_hist);
+            k_len_cursor<<<1, 32, 0, st>>>(d_hist);
+            k_len_scatter<<<grid_for(npat, 256u * FMX_LEN_ITEMS), 256, 0, st>>>(a.pat_off, npat, d_hist, buf[B_ORDER].as<uint32_t>());
+            g_launches.fetch_add(2, std::memory_order_relaxed);
+            LAUNCH_CHECK();
+            g.a.order = buf[B_ORDER].as<uint32_t>();
+        }
         g.rs = buf[B_RS].as<uint32_t>();
         g.re = buf[B_RE].as<uint32_t>();
         g.hint = buf[B_HINT].as<uint32_t>();

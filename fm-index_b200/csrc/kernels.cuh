@@ -1236,6 +1236,58 @@ __global__ void __launch_bounds__(256) k_bucket_scatter(const uint32_t *bucket, 
     if (p < npat) order[atomicAdd(cursor + bucket[p], 1u)] = (uint32_t)p;
 }
 
+// Ragged batches (option "order_by_length"): patterns visited in order of their length, so that the 32 lanes of a warp run
+// loops of the same trip count (table depth, comparison length).  Counting sort over FMX_LEN_BUCKETS lengths, two
+// passes over the offsets; a block counts in shared memory and reserves its slots with one atomic per bucket.
+#define FMX_LEN_BUCKETS 128u
+__device__ __forceinline__ uint32_t len_bucket(const uint64_t *off, uint64_t p) {
+    const uint64_t len = off[p + 1] - off[p];
+    return len < FMX_LEN_BUCKETS ? (uint32_t)len : FMX_LEN_BUCKETS - 1u;
+}
+__global__ void __launch_bounds__(256) k_len_hist(const uint64_t *off, uint64_t npat, uint32_t *hist) {
+    __shared__ uint32_t sh[FMX_LEN_BUCKETS];
+    for (uint32_t k = threadIdx.x; k < FMX_LEN_BUCKETS; k += blockDim.x) sh[k] = 0;
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < npat; p += stride) atomicAdd(&sh[len_bucket(off, p)], 1u);
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < FMX_LEN_BUCKETS; k += blockDim.x)
+        if (sh[k]) atomicAdd(&hist[k], sh[k]);
+}
+__global__ void k_len_cursor(uint32_t *hist) {  // exclusive prefix sums, in place (one thread: 128 counters)
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (uint32_t k = 0; k < FMX_LEN_BUCKETS; k++) {
+            const uint32_t v = hist[k];
+            hist[k] = acc;
+            acc += v;
+        }
+    }
+}
+#define FMX_LEN_ITEMS 8u
+__global__ void __launch_bounds__(256) k_len_scatter(const uint64_t *off, uint64_t npat, uint32_t *cursor, uint32_t *order) {
+    __shared__ uint32_t cnt[FMX_LEN_BUCKETS], base[FMX_LEN_BUCKETS];
+    for (uint32_t k = threadIdx.x; k < FMX_LEN_BUCKETS; k += blockDim.x) cnt[k] = 0;
+    __syncthreads();
+    const uint64_t first = (uint64_t)blockIdx.x * (256u * FMX_LEN_ITEMS);
+    uint32_t b[FMX_LEN_ITEMS], r[FMX_LEN_ITEMS];
+#pragma unroll
+    for (uint32_t i = 0; i < FMX_LEN_ITEMS; i++) {
+        const uint64_t p = first + i * 256u + threadIdx.x;
+        b[i] = 0xFFFFFFFFu;
+        if (p < npat) {
+            b[i] = len_bucket(off, p);
+            r[i] = atomicAdd(&cnt[b[i]], 1u);  // rank inside the block's share of the bucket
+        }
+    }
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < FMX_LEN_BUCKETS; k += blockDim.x) base[k] = cnt[k] ? atomicAdd(&cursor[k], cnt[k]) : 0u;
+    __syncthreads();
+#pragma unroll
+    for (uint32_t i = 0; i < FMX_LEN_ITEMS; i++)
+        if (b[i] != 0xFFFFFFFFu) order[base[b[i]] + r[i]] = (uint32_t)(first + i * 256u + threadIdx.x);
+}
+
 // Backward search, persistent variant (option "search_persistent"), phase A: one pattern per thread, fully converged.
 // Sets up (s, e) and the number of characters still to consume; the first kmer_k iterations of a
 // fresh search are ONE table lookup.  Patterns the table already finishes (their range emptied

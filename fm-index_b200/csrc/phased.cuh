@@ -327,7 +327,8 @@ __global__ void __launch_bounds__(256, 5) k_query_fused(const __grid_constant__ 
     const SearchArgs &a = g.a;
     unsigned long long steps = 0, reqs = 0;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < a.npat; p += stride) {
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < a.npat; t += stride) {
+        const uint64_t p = a.order ? (uint64_t)a.order[t] : t;  // ragged batches: in order of length (k_len_scatter)
         uint64_t beg;
         uint32_t len;
         pattern_span(a, p, beg, len);

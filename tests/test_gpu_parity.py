@@ -906,6 +906,28 @@ def test_table_entries_with_text_context(kind):
         assert np.array_equal(r[k], ref[k]), k
 
 
+@pytest.mark.parametrize("kind,mc", [(orc.FM, 4), (orc.FM, 255), (orc.MULTI, 4)])
+def test_ragged_batches_in_order_of_length(kind, mc):
+    """option order_by_length: the fused kernel visits a ragged batch sorted by pattern length (k_len_hist / k_len_scatter);
+    results stay in input order and equal the oracle's, lengths beyond the last bucket included"""
+    text, pats = _rich_case(kind, mc, 7000 + kind + mc)
+    rng = np.random.default_rng(3)
+    pats = pats + [text[i:i + int(m)].tobytes() for i, m in zip(rng.integers(0, 50_000, 40), rng.integers(120, 400, 40))]
+    index = KINDS[kind][1].new(fmx.Text.with_max_character(text, mc), 2, mode=fmx.MODE_RICH)
+    oracle = orc.OracleIndex(text, kind, level=2, max_character=mc)
+    flat, off = orc.pack_patterns(pats)
+    s, e = oracle.search_batch(flat, off)
+    ooff, opos, _ = oracle.locate_batch(s, e)
+    for opt in (1, 0):
+        index.set_option("order_by_length", opt)
+        for rows in (True, False):
+            r = index.query_batch(pats, rows=rows, counts=True)
+            if rows:
+                assert np.array_equal(r["s"], s) and np.array_equal(r["e"], e), opt
+            assert np.array_equal(r["counts"], np.where(e > s, e - s, 0)), opt
+            assert np.array_equal(r["hit_off"], ooff) and np.array_equal(r["positions"], opos), opt
+
+
 def test_rich_mode_many_hits_and_pipeline():
     """patterns with thousands of matches (k_emit_big), a chunked pipeline with a position-capacity guess that is too
     small for the first chunks, a too-small caller capacity"""

@@ -238,43 +238,85 @@ __global__ void __launch_bounds__(256) k_ph_verify(const __grid_constant__ FmxDe
 // workload is the number of DRAM requests, which idle lanes do not issue, so here one thread takes one pattern
 // through table lookup, the few ordinary iterations and the text comparison without leaving the registers its
 // characters already sit in.  Same results, same hints, same step counts.
+// HEAD of a query: the table lookup and -- when the entry is a one-row range that carries enough of the text in front of
+// its row (SearchArgs::big_tab4) -- the comparison of the rest of the pattern against that context.  Returns true when
+// (s, e, hint) are final; otherwise (k, s, e, pos, armed) is the state query_tail continues from.
 template <int KIND, int LAYOUT, class Reader>
-__device__ __forceinline__ void query_one(const FmxDev &ix, const Tabs<LAYOUT> &tb, const PhasedArgs &g, Reader &rd, uint32_t len,
-                                          uint32_t &s, uint32_t &e, uint32_t &hint, unsigned long long &steps,
-                                          unsigned long long &reqs) {
+__device__ __forceinline__ bool query_head(const FmxDev &ix, const PhasedArgs &g, Reader &rd, uint32_t len, uint32_t &k, uint32_t &s,
+                                           uint32_t &e, uint32_t &pos, bool &armed, uint32_t &hint, unsigned long long &steps,
+                                           unsigned long long &reqs) {
     const SearchArgs &a = g.a;
-    uint32_t it = 0, pos = FMX_NOHINT, k = len, ctx = 0, ctx_len = 0;
+    uint32_t it = 0, ctx = 0, ctx_len = 0;
+    pos = FMX_NOHINT;
+    k = len;
     // one request: the entry.  (A pass that counts work also reads the step byte of an emptied range; the timed pass
     // does not, and the request counter reports what the timed pass issues.)
     if (kmer_lookup(a, ix.max_character, rd, k, s, e, it, &pos, &ctx, &ctx_len)) reqs += 1u;
-    bool armed = a.verify != 0;
+    armed = a.verify != 0;
     hint = FMX_NOHINT;
-    if (pos == FMX_NOHINT) ctx_len = 0;  // the context belongs to the row of a one-row entry
-    while (k > 0) {  // the reference loop (wrapper.rs:103-124): the range is tested after a step, never before
-        if (armed && e - s == 1u && (k >= FMX_VERIFY_MIN_DENSE || k <= ctx_len)) {
+    steps += it;
+    if (k == 0 || s == e) {  // the table finished the pattern (the reference loop tests the range after a step, never before)
+        if (k == 0 && e - s == 1u) hint = pos;  // a one-row entry that consumed the whole pattern
+        return it != 0 || k == 0;  // nothing consumed and characters left: an empty INITIAL range still runs the loop
+    }
+    uint32_t pk;
+    if (armed && pos != FMX_NOHINT && e - s == 1u && k <= ctx_len && kmer_index4(rd, k, k, pk)) {
+        // the rest of the pattern (as 2-bit codes, last character lowest -- exactly its k-mer index) against the
+        // characters in front of the row: no text request
+        const uint32_t diff = (pk ^ ctx) & (k < 16u ? (1u << (2u * k)) - 1u : 0xFFFFFFFFu);
+        const uint32_t matched = diff ? (uint32_t)(__ffs((int)((diff | (diff >> 1)) & 0x55555555u)) - 1) >> 1 : k;
+        steps += matched;
+        if (matched == k) {  // the whole rest of the pattern stands in the text in front of the row
+            hint = pos - k;
+            if (g.want_rows) {
+                s = ldg32_s(ix.isa + hint);
+                reqs++;
+            } else {
+                s = 0;
+            }
+            e = s + 1u;
+            k = 0;
+            return true;
+        }
+        if (!g.want_rows) {  // a true mismatch (the characters are valid): the next iteration empties the range
+            steps++;
+            s = e = 0;
+            return true;
+        }
+        if (matched) {  // exact rows wanted: go on from the row the reference reaches after the characters that match
+            s = ldg32_s(ix.isa + (pos - matched));
+            reqs++;
+            e = s + 1u;
+            k -= matched;
+        }
+        armed = false;  // as search_one: the tail is not tried again once an attempt stopped early
+    }
+    return false;
+}
+
+// TAIL of a query: the reference loop (wrapper.rs:103-124) from the state the head left, with the seed-and-verify
+// tail against the text for one-row ranges.
+template <int KIND, int LAYOUT, class Reader>
+__device__ __forceinline__ void query_tail(const FmxDev &ix, const Tabs<LAYOUT> &tb, const PhasedArgs &g, Reader &rd, uint32_t k,
+                                           uint32_t &s, uint32_t &e, uint32_t pos, bool armed, uint32_t &hint,
+                                           unsigned long long &steps, unsigned long long &reqs) {
+    const SearchArgs &a = g.a;
+    uint32_t it = 0;
+    while (k > 0) {  // the range is tested after a step, never before
+        if (armed && e - s == 1u && k >= FMX_VERIFY_MIN_DENSE) {
             if (pos == FMX_NOHINT) {
                 pos = ldg32_s(ix.vsa + s);
                 reqs++;
             }
-            uint32_t matched = 0, c = 0, pk;
-            bool compared = false;
-            if (k <= ctx_len && kmer_index4(rd, k, k, pk)) {
-                // the table entry carries the characters in front of the row: the rest of the pattern (as 2-bit codes, last
-                // character lowest -- exactly its k-mer index) against them, no text request
-                const uint32_t diff = (pk ^ ctx) & (k < 16u ? (1u << (2u * k)) - 1u : 0xFFFFFFFFu);
-                matched = diff ? (uint32_t)(__ffs((int)((diff | (diff >> 1)) & 0x55555555u)) - 1) >> 1 : k;
-                c = matched < k ? ((pk >> (2u * matched)) & 3u) + 1u : 0u;  // the pattern character at the stop
-                compared = true;
-            } else if (pos >= k) {
+            uint32_t matched = 0, c = 0;
+            if (pos >= k) {
                 TextReader tr(ix.text + (pos - k), k);
                 matched = match_backward(rd, tr, k, c);
                 const uint32_t last = pos - 1u, first = pos - (matched < k ? matched + 1u : k);
                 reqs += (last >> 5) - (first >> 5) + 1u;
-                compared = true;
             }
-            ctx_len = 0;
             it += matched;
-            if (compared && matched == k) {  // the whole rest of the pattern stands in the text in front of the row
+            if (pos >= k && matched == k) {  // the whole rest of the pattern stands in the text in front of the row
                 hint = pos - k;
                 if (g.want_rows) {
                     s = ldg32_s(ix.isa + hint);
@@ -286,7 +328,7 @@ __device__ __forceinline__ void query_one(const FmxDev &ix, const Tabs<LAYOUT> &
                 k = 0;
                 break;
             }
-            if (compared && !g.want_rows && c != 0u && c <= ix.max_character) {  // true mismatch: the next iteration empties the range
+            if (pos >= k && !g.want_rows && c != 0u && c <= ix.max_character) {  // true mismatch: the next iteration empties the range
                 it++;
                 s = e = 0;
                 break;
@@ -308,13 +350,22 @@ __device__ __forceinline__ void query_one(const FmxDev &ix, const Tabs<LAYOUT> &
         if (a.work) reqs += pair_requests<LAYOUT>(ix, s, e);
         lf_map2_pair<KIND, LAYOUT>(ix, tb, c, s, e);
         pos = FMX_NOHINT;
-        ctx_len = 0;
         it++;
         k--;
         if (s == e) break;
     }
-    if (hint == FMX_NOHINT && e - s == 1u && k == 0) hint = pos;  // a one-row table entry that consumed the whole pattern
+    if (hint == FMX_NOHINT && e - s == 1u && k == 0) hint = pos;  // a one-row range whose position is known
     steps += it;
+}
+
+template <int KIND, int LAYOUT, class Reader>
+__device__ __forceinline__ void query_one(const FmxDev &ix, const Tabs<LAYOUT> &tb, const PhasedArgs &g, Reader &rd, uint32_t len,
+                                          uint32_t &s, uint32_t &e, uint32_t &hint, unsigned long long &steps,
+                                          unsigned long long &reqs) {
+    uint32_t k, pos;
+    bool armed;
+    if (!query_head<KIND, LAYOUT>(ix, g, rd, len, k, s, e, pos, armed, hint, steps, reqs))
+        query_tail<KIND, LAYOUT>(ix, tb, g, rd, k, s, e, pos, armed, hint, steps, reqs);
 }
 
 // five resident blocks per SM (<= 48 registers): this kernel lives on memory requests in flight; at 56 registers (four
@@ -347,6 +398,104 @@ __global__ void __launch_bounds__(256, 5) k_query_fused(const __grid_constant__ 
         g.re[p] = e;
         g.hint[p] = hint;
     }
+    if (a.work) {
+        warp_add(steps, a.work);
+        warp_add(reqs, a.work + 2);
+    }
+}
+
+// ---- the fused kernel with a block-local second pass (option "fused_defer").
+// With the 16-byte table entries nine patterns in ten are finished by query_head (one request, ~300 instructions, all 32
+// lanes of the warp in step); the tenth -- a k-mer that occurs more than once, a pattern longer than the context --
+// needs rank steps, SA[row] and a text comparison: ~1100 instructions that the plain fused kernel executes with ~3 of
+// 32 lanes active, which is 80 % of its issue slots (profiles/r02_c10_target_k_query_fused_ctx_ncu.txt: 9.4 lanes,
+// issue-active 64 %).  Here a thread whose pattern is not finished by the head parks its state (pattern, characters
+// left, range, position: five words) in a shared-memory queue; whenever the block holds 256 parked states all of its
+// threads take one each through query_tail, so the expensive path runs with full warps.  No global queue, no second
+// kernel; the only extra traffic is re-reading the parked patterns' characters.
+#define FMX_DEFER_CAP 512u
+template <int KIND, int LAYOUT>
+__device__ __forceinline__ void defer_tail(const FmxDev &ix, const Tabs<LAYOUT> &tb, const PhasedArgs &g, uint32_t (*spat)[256],
+                                           const uint32_t (*dq)[FMX_DEFER_CAP], uint32_t slot, unsigned long long &steps,
+                                           unsigned long long &reqs) {
+    const SearchArgs &a = g.a;
+    const uint64_t p = dq[0][slot];
+    const uint32_t k = dq[1][slot] & 0x7FFFFFFFu;
+    const bool armed = (dq[1][slot] >> 31) != 0;
+    uint32_t s = dq[2][slot], e = dq[3][slot], hint = FMX_NOHINT;
+    const uint32_t pos = dq[4][slot];
+    uint64_t beg;
+    uint32_t len;
+    pattern_span(a, p, beg, len);
+    if (a.packed_bits) {
+        AnyReader rd(a, p, beg, len);
+        query_tail<KIND, LAYOUT>(ix, tb, g, rd, k, s, e, pos, armed, hint, steps, reqs);
+    } else if (a.staged) {
+        StagedReader rd(spat, a.pat + beg, len);
+        query_tail<KIND, LAYOUT>(ix, tb, g, rd, k, s, e, pos, armed, hint, steps, reqs);
+    } else {
+        PatReader rd(a.pat + beg, len);
+        query_tail<KIND, LAYOUT>(ix, tb, g, rd, k, s, e, pos, armed, hint, steps, reqs);
+    }
+    g.rs[p] = s;
+    g.re[p] = e;
+    g.hint[p] = hint;
+}
+
+template <int KIND, int LAYOUT>
+__global__ void __launch_bounds__(256, 5) k_query_fused_defer(const __grid_constant__ FmxDev ix, const __grid_constant__ PhasedArgs g) {
+    __shared__ Tabs<LAYOUT> tb;
+    __shared__ uint32_t spat[8][256];
+    __shared__ uint32_t dq[5][FMX_DEFER_CAP];
+    __shared__ uint32_t dq_n;
+    load_tables<LAYOUT>(ix, tb);
+    if (threadIdx.x == 0) dq_n = 0;
+    __syncthreads();
+    const SearchArgs &a = g.a;
+    unsigned long long steps = 0, reqs = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t rounds = (a.npat + stride - 1) / stride;
+    for (uint64_t r = 0; r < rounds; r++) {
+        const uint64_t p = r * stride + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (p < a.npat) {
+            uint64_t beg;
+            uint32_t len;
+            pattern_span(a, p, beg, len);
+            uint32_t s = a.s0, e = a.e0, hint, k, pos;
+            bool armed, done;
+            if (a.packed_bits) {
+                AnyReader rd(a, p, beg, len);
+                done = query_head<KIND, LAYOUT>(ix, g, rd, len, k, s, e, pos, armed, hint, steps, reqs);
+            } else if (a.staged) {
+                StagedReader rd(spat, a.pat + beg, len);
+                done = query_head<KIND, LAYOUT>(ix, g, rd, len, k, s, e, pos, armed, hint, steps, reqs);
+            } else {
+                PatReader rd(a.pat + beg, len);
+                done = query_head<KIND, LAYOUT>(ix, g, rd, len, k, s, e, pos, armed, hint, steps, reqs);
+            }
+            if (done) {
+                g.rs[p] = s;
+                g.re[p] = e;
+                g.hint[p] = hint;
+            } else {  // park the state: at most 256 new entries per round on top of fewer than 256 left over
+                const uint32_t slot = atomicAdd(&dq_n, 1u);
+                dq[0][slot] = (uint32_t)p;
+                dq[1][slot] = k | (armed ? 0x80000000u : 0u);
+                dq[2][slot] = s;
+                dq[3][slot] = e;
+                dq[4][slot] = pos;
+            }
+        }
+        __syncthreads();
+        while (dq_n >= 256u) {  // the same value for every thread: read between two barriers
+            const uint32_t base = dq_n - 256u;
+            defer_tail<KIND, LAYOUT>(ix, tb, g, spat, dq, base + threadIdx.x, steps, reqs);
+            __syncthreads();
+            if (threadIdx.x == 0) dq_n = base;
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x < dq_n) defer_tail<KIND, LAYOUT>(ix, tb, g, spat, dq, threadIdx.x, steps, reqs);
     if (a.work) {
         warp_add(steps, a.work);
         warp_add(reqs, a.work + 2);

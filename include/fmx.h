@@ -136,7 +136,8 @@ int fmx_build_suffix_array_device(const void *text, uint64_t n, uint32_t char_wi
  * binary search inside the locate kernel), "locate_ranges" -1|0|1 (walk whole SA sub-ranges instead of
  * single rows: auto = RLFM indexes whose patterns average >= 8 matches / never / always), "extract_text" 0|1
  * (extraction from the resident text), "order_by_length" 0|1 (ragged batches through the fused kernel in order of
- * pattern length; off: it measured slower), "table_ctx" 0|1 (16-byte entries of the large k-mer table that carry the 16 text
+ * pattern length; off: it measured slower), "fused_defer" 0|1 (the fused query kernel parks the patterns its table lookup does not finish
+ * in a shared-memory queue and runs them with full warps), "table_ctx" 0|1 (16-byte entries of the large k-mer table that carry the 16 text
  * characters in front of one-row ranges: a pattern with <= 16 characters left after the table is finished by ONE
  * request; rebuilds the table; FMX_NO_TABLE_CTX=1 at construction time).  Environment at construction time: FMX_FORCE_WAVELET=1
  * keeps the binary wavelet matrix; FMX_SYM_BUDGET_MB caps the per-symbol bit-vector layout (default

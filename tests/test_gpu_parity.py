@@ -880,16 +880,18 @@ def test_table_entries_with_text_context(kind):
             # piece of a position = zeros before it (multi_pieces.rs:287-296; the literal walk is pinned in other tests and
             # would take piece-length LF steps per hit here)
             opid = np.searchsorted(zeros, opos, side="left").astype(np.uint64)
-            for rows in (True, False):
+            for rows, defer in ((True, 1), (False, 1), (True, 0), (False, 0)):
+                index.set_option("fused_defer", defer)       # 1: block-local second pass for the patterns the head does not finish
                 r = index.query_batch(pats, mode, rows=rows, counts=True, piece_ids=kind == orc.MULTI, capacity=int(ooff[-1]) + 8)
                 if rows:
-                    assert np.array_equal(r["s"], s) and np.array_equal(r["e"], e), (ctx, mode)
-                assert np.array_equal(r["counts"], np.where(e > s, e - s, 0)), (ctx, mode, rows)
-                assert np.array_equal(r["hit_off"], ooff) and np.array_equal(r["positions"], opos), (ctx, mode, rows)
+                    assert np.array_equal(r["s"], s) and np.array_equal(r["e"], e), (ctx, mode, defer)
+                assert np.array_equal(r["counts"], np.where(e > s, e - s, 0)), (ctx, mode, rows, defer)
+                assert np.array_equal(r["hit_off"], ooff) and np.array_equal(r["positions"], opos), (ctx, mode, rows, defer)
                 if kind == orc.MULTI:
                     assert np.array_equal(r["piece_ids"], opid)
                 if not po:
-                    assert index.last_work()[0] == int(steps.sum()), (ctx, mode, rows)
+                    assert index.last_work()[0] == int(steps.sum()), (ctx, mode, rows, defer)
+            index.set_option("fused_defer", 1)
         bad = bytearray(text[1000:1028].tobytes())               # an invalid character inside the context window
         bad[5] = 5
         for rows in (True, False):

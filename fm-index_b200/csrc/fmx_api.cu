@@ -866,7 +866,9 @@ static int build_big_table(fmx_index *idx, uint64_t budget_bytes) {
         size_t f2 = 0, t2 = 0;
         const uint64_t wide_b = entries * sizeof(uint4), narrow_b = entries * sizeof(uint2);
         // both forms are resident while the entries are copied over; afterwards at least as much must stay free as the table takes
-        if (cudaMemGetInfo(&f2, &t2) == cudaSuccess && wide_b + (8ull << 30) <= f2 && wide_b <= (f2 + narrow_b) / 2) {
+        // (FMX_TABLE_CTX_FORCE=1 drops the second condition: for callers who know nothing else will be built next to the index)
+        if (cudaMemGetInfo(&f2, &t2) == cudaSuccess && wide_b + (8ull << 30) <= f2 &&
+            (wide_b <= (f2 + narrow_b) / 2 || env_flag("FMX_TABLE_CTX_FORCE"))) {
             uint4 *t4 = nullptr;
             if (cudaMalloc(&t4, entries * sizeof(uint4)) == cudaSuccess) {
                 k_table_widen<<<grid_for(entries, 256), 256, 0, idx->stream>>>(idx->d_big_tab, entries, idx->dev.text, t4);

@@ -139,7 +139,8 @@ int fmx_build_suffix_array_device(const void *text, uint64_t n, uint32_t char_wi
  * pattern length; off: it measured slower), "fused_defer" 0|1 (the fused query kernel parks the patterns its table lookup does not finish
  * in a shared-memory queue and runs them with full warps), "table_ctx" 0|1 (16-byte entries of the large k-mer table that carry the 16 text
  * characters in front of one-row ranges: a pattern with <= 16 characters left after the table is finished by ONE
- * request; rebuilds the table; FMX_NO_TABLE_CTX=1 at construction time).  Environment at construction time: FMX_FORCE_WAVELET=1
+ * request; rebuilds the table; FMX_NO_TABLE_CTX=1 at construction time; built while afterwards at least as much HBM stays
+ * free as the table takes, FMX_TABLE_CTX_FORCE=1 lifts that).  Environment at construction time: FMX_FORCE_WAVELET=1
  * keeps the binary wavelet matrix; FMX_SYM_BUDGET_MB caps the per-symbol bit-vector layout (default
  * 49152; 0 = use the quaternary wavelet matrix instead); FMX_VERIFY_BUDGET_MB caps the dense
  * seed-and-verify structures (text + full suffix array + inverse, 9 bytes per symbol; default 32768),

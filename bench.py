@@ -428,8 +428,9 @@ def reference_arm(args, name, w):
     return 0
 
 
-PHASES = ["seed (k-mer table lookup; the whole k_search on indexes without the phased kernels)", "steps (k_ph_steps)",
-          "verify (k_ph_verify)", "steps, second pass (+ widen)", "counts + offsets scan", "emit / locate"]
+PHASES = ["query kernel (rich: k_query_fused[_defer] = table lookup + rank steps + verify in one launch; compact: k_search; "
+          "option search_phased=1: k_ph_seed)", "steps (k_ph_steps; search_phased=1 only)", "verify (k_ph_verify; search_phased=1 only)",
+          "steps, second pass (+ widen)", "counts + offsets scan", "emit / locate"]
 
 
 class DeviceRun:
@@ -780,8 +781,14 @@ def roofline_block(args, w, index, mode_name, npat, hits, ms_step, ms_count, pha
     cap = ncu_capture(args.workload, npat, mode_name)
     t = ms_step * 1e-3
     names = ["k_ph_seed", "k_ph_steps", "k_ph_verify", "k_ph_steps (second pass)", "scan", "k_emit_small + k_emit_big / k_locate_*"]
-    if not req_search:
+    opts = dict(kv.split("=") for kv in args.option)
+    if not req_search or mode_name != "rich" or kind == RLFM:
         names[0] = "k_search"
+    elif int(opts.get("search_phased", 2)) == 2:
+        # fmx_api.cu search_phased: the block-local second pass runs with the 16-byte table entries (fused_defer = 1) or always (= 2)
+        defer = int(opts.get("fused_defer", 1))
+        entry16 = int(index._L.fmx_index_kmer_entry_bytes(index._h)) == 16
+        names[0] = "k_query_fused_defer" if (defer == 2 or (defer == 1 and entry16)) and not int(opts.get("order_by_length", 0)) else "k_query_fused"
     r = {"bound": "hbm", "kernel": names[dominant], "peak": peak, "unit": "GB/s", "peak_source": peak_src,
          "step_ms": ms_step, "phase_ms": {PHASES[k]: round(float(phase_ms[k]), 4) for k in range(len(PHASES))},
          "phase_ms_note": "CUDA events the library records between its own launches, separate untimed-region passes with the same L2 flush",

@@ -445,8 +445,11 @@ VerifyPlan plan_verify(int kind, uint64_t n, int mode, int level, bool interior_
     p.verify = verify;
     p.dense_sa = p.dense;
     // RLFM in the HBM-rich mode: no verify tail (its ranges rarely narrow to one row), but locate by the
-    // resident suffix array
-    if (kind == FMX_KIND_RLFM && mode == FMX_MODE_RICH && level >= 0 && !interior_zero && n >= 64 && 4 * n <= budget) p.dense_sa = true;
+    // resident suffix array.  AUTO takes it once the text has 2^27 symbols: from there on the sampled walk
+    // (2^level - 1 run-length LF steps per hit, each several requests) leaves L2, and on the 1 GiB config the
+    // resident array answers 6.1e8 hits in 2.7 ms against 31.9 ms (profiles/r02_c7_bench_cfg3_rlfm_rich.json)
+    const bool rl_rich = mode == FMX_MODE_RICH || (mode == FMX_MODE_AUTO && n >= (1ull << 27));
+    if (kind == FMX_KIND_RLFM && rl_rich && level >= 0 && !interior_zero && n >= 64 && 4 * n <= budget) p.dense_sa = true;
     p.isa_level = p.dense ? 0u : 2u;
     return p;
 }

@@ -143,8 +143,12 @@ int fmx_group_create(const int *device_ids, int ndev, int group_mode, const void
     } else {
         // piece k is text[start_k, end_k] with text[end_k] == 0 (multi_pieces.rs:53-79)
         std::vector<uint64_t> ends;
-        for (uint64_t i = 0; i < n; i++)
-            if (t[i] == 0) ends.push_back(i);
+        for (const uint8_t *p = t, *stop = t + n; p < stop;) {
+            const uint8_t *z = static_cast<const uint8_t *>(std::memchr(p, 0, (size_t)(stop - p)));
+            if (!z) break;
+            ends.push_back((uint64_t)(z - t));
+            p = z + 1;
+        }
         if (ends.empty() || ends.back() != n - 1) {
             fmx_group_free(g);
             return gfail(FMX_ERR_INVALID_TEXT, "the given text must end with exactly one zero character");
@@ -162,6 +166,11 @@ int fmx_group_create(const int *device_ids, int ndev, int group_mode, const void
             const uint64_t base = first ? ends[first - 1] + 1 : 0;
             g->m[(size_t)k].pos_base = base;
             g->m[(size_t)k].pid_base = first;
+            // one index addresses rows with u32; the WHOLE text may be longer (positions are base + local, u64)
+            if (ends[last - 1] + 1 - base >= 0xFFFFFFFFull) {
+                fmx_group_free(g);
+                return gfail(FMX_ERR_UNSUPPORTED, "a partition holds 2^32 - 1 symbols or more: use more partitions (device ids may repeat)");
+            }
             rc = fmx_index_build_ex(t + base, ends[last - 1] + 1 - base, char_width, max_character, kind, level, device_ids[k],
                                     index_mode, &g->m[(size_t)k].idx);
         }

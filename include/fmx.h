@@ -70,8 +70,8 @@ typedef enum fmx_mode {
  *   RICH     additionally the text, the FULL suffix array and its inverse (9 n bytes) and a k-mer table sized to
  *            end the search of an absent pattern: every query step that the reference answers with a chain of
  *            dependent rank probes becomes one or two memory requests, locate is SA[row].  Bit-identical results.
- *   AUTO     RICH when the rank structure does not fit the 126 MB L2 and the budgets allow, else COMPACT
- *            (FMX_MODE=compact|rich in the environment overrides AUTO). */
+ *   AUTO     RICH when the rank structure does not fit the 126 MB L2 (RLFM with locate: when the text has 2^27 symbols
+ *            or more) and the budgets allow, else COMPACT (FMX_MODE=compact|rich in the environment overrides AUTO). */
 typedef enum fmx_index_mode { FMX_MODE_AUTO = 0, FMX_MODE_COMPACT = 1, FMX_MODE_RICH = 2 } fmx_index_mode;
 
 const char *fmx_last_error(void);

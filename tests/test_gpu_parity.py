@@ -1148,8 +1148,10 @@ def test_scale_rlfm_256m_16_copies():
     flat, off = pats[:50_000].reshape(-1), np.arange(50_001, dtype=np.uint64) * m
     s, e = oracle.search_batch(flat, off)
     ooff, opos, _ = oracle.locate_batch(s, e)
-    for mode in (fmx.MODE_AUTO, fmx.MODE_RICH):
+    for mode in (fmx.MODE_COMPACT, fmx.MODE_AUTO):
         index = fmx.RLFMIndexWithLocate.new(fmx.Text.with_max_character(text, 4), 2, mode=mode)
+        # AUTO keeps the suffix array resident from 2^27 symbols on (locate = SA[row]); COMPACT walks to the samples
+        assert index.mode() == (fmx.MODE_COMPACT if mode == fmx.MODE_COMPACT else fmx.MODE_RICH)
         r = index.query_batch(pats, rows=True, capacity=40 * npat)
         assert np.array_equal(r["s"][:50_000], s) and np.array_equal(r["e"][:50_000], e)
         assert np.array_equal(r["hit_off"][:50_001], ooff) and np.array_equal(r["positions"][: int(ooff[-1])], opos)
@@ -1236,6 +1238,50 @@ def test_group_by_piece_and_replicated(ndev, imode):
         assert np.array_equal(a[k], b[k]), k
     with pytest.raises(fmx.Error):
         fmx.IndexGroup(fmx.Text.with_max_character(dna(5000, 1), 4), fmx.KIND_FM, 2, [0], fmx.GROUP_BY_PIECE)
+
+
+@pytest.mark.skipif(os.environ.get("FMX_SKIP_FULL") == "1", reason="full-size run disabled")
+def test_group_by_piece_over_a_text_beyond_2_32_symbols():
+    """The reference's positions are usize (multi_pieces.rs:188-223); one fmx index addresses rows with u32.  A
+    MultiPieces text of 4.4e9 symbols is served as a BY_PIECE group whose partitions (here two, both on device 0) stay
+    below 2^32 each: hit offsets, positions (beyond 2^32) and piece ids come back as u64 in the coordinates of the
+    WHOLE text.  32-mers cut from random DNA of this size occur once (4^32 >> n), so the expected answer of a
+    sampled pattern is exactly its origin, and of a random one (almost surely) nothing; every hit is checked
+    against the text."""
+    pieces, plen, npat, m = 8, 550_000_000, 200_000, 32
+    n = pieces * plen
+    assert n > (1 << 32)
+    import torch
+    rng = np.random.default_rng(2032)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(2032)
+    text = np.empty(n, dtype=np.uint8)                         # random DNA, generated on the GPU piece by piece
+    for k in range(pieces):
+        text[k * plen:(k + 1) * plen] = torch.randint(1, 5, (plen,), dtype=torch.uint8, device="cuda", generator=gen).cpu().numpy()
+    text[plen - 1::plen] = 0
+    torch.cuda.empty_cache()
+    starts = rng.integers(0, n - m - 1, npat)
+    starts[:8:2] = [0, n - m - 1, plen, (1 << 32) - 7]        # first / last piece, a piece start, across the u32 wall
+    pats = rng.integers(1, 5, (npat, m), dtype=np.uint8)
+    sampled = text[starts[:, None] + np.arange(m)[None, :]]
+    inside = (sampled != 0).all(axis=1)                        # a pattern may not span a piece boundary
+    inside[1::2] = False
+    pats[inside] = sampled[inside]
+    group = fmx.IndexGroup(fmx.Text.with_max_character(text, 4), fmx.KIND_MULTI, 4, [0, 0], fmx.GROUP_BY_PIECE, mode=fmx.MODE_COMPACT)
+    assert group.len() == n and group.pieces_count() == pieces
+    r = group.query_batch(pats, piece_ids=True, counts=True)
+    hoff, pos, pid = r["hit_off"].astype(np.int64), r["positions"].astype(np.int64), r["piece_ids"].astype(np.int64)
+    cnt = np.diff(hoff)
+    assert np.array_equal(cnt, r["counts"].astype(np.int64)) and r["total"] == int(hoff[-1]) == pos.size
+    assert np.all(cnt[inside] >= 1) and int(cnt[~inside].sum()) <= 2
+    owner = np.repeat(np.arange(npat), cnt)
+    assert np.array_equal(text[pos[:, None] + np.arange(m)[None, :]], pats[owner])          # every hit holds its pattern
+    assert np.array_equal(pid, pos // plen)
+    first = hoff[:-1][inside]
+    once = cnt[inside] == 1
+    assert once.mean() > 0.999 and np.array_equal(pos[first[once]], starts[inside][once])  # .. and is the origin
+    assert int(pos.max()) > (1 << 32) and pos[hoff[6]] == (1 << 32) - 7
+    del group
 
 
 def test_partitioned_cuda_engine_and_merge_kernel():

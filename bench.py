@@ -814,6 +814,13 @@ def roofline_block(args, w, index, mode_name, npat, hits, ms_step, ms_count, pha
         if gp:
             fr_req = reqs / t / gp
             r["random_access"].update({"achieved_requests_per_s": reqs / t, "frac": fr_req})
+            issued = float(req_search + req_emit)
+            if issued:
+                # the part of those requests that is RANDOM (index loads the kernels count themselves; the rest streams
+                # patterns, ranges and offsets): the conservative reading of the same fraction
+                r["random_access"].update({"index_requests_per_step": issued, "index_requests_per_pattern": issued / npat,
+                                           "index_requests_frac": issued / t / gp,
+                                           "index_requests_frac_in_query_kernel": float(req_search) / (phase_ms[0] * 1e-3) / gp if phase_ms[0] > 0 else None})
         r["frac"] = max(fr_bw, fr_req or 0.0)
         r["frac_source"] = "max(DRAM bytes / time / HBM peak = %.3f, L2 read requests / time / random-request peak = %s); ncu capture of these sources" % (
             fr_bw, "%.3f" % fr_req if fr_req is not None else "n/a")

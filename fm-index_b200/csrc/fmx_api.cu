@@ -123,6 +123,7 @@ struct fmx_index {
     int opt_phased = 2;               // dense verify structures: 2 = k_query_fused (one kernel), 1 = the three phased kernels, 0 = k_search
     int opt_order_by_length = 0;      // 1: ragged batches through the fused kernel in order of pattern length (A/B: lost, see search_phased)
     int opt_fused_defer = 1;          // fused kernel with the block-local second pass when the 16-byte table is in use (phased.cuh)
+    int opt_query_blocks = 0;         // > 0: at most this many blocks for the fused query kernels (tests: many rounds per block on small batches)
     int opt_extract_text = 1;         // 0: extraction by LF / FL steps even when text and suffix array are resident (A/B)
     int opt_locate_dense = 1;         // 0: LF walks to the samples even when the full suffix array is resident (A/B)
     uint32_t tab_embed = 0;           // one-row k-mer table entries carry the row's text position (SearchArgs::tab_embed)
@@ -589,8 +590,9 @@ int fmx_index_set_option(fmx_index *idx, const char *key, int64_t value) {
     else if (k == "search_phased") idx->opt_phased = value < 0 || value > 2 ? 2 : (int)value;
     else if (k == "locate_dense") idx->opt_locate_dense = value != 0;
     else if (k == "extract_text") idx->opt_extract_text = value != 0;
-    else if (k == "fused_defer") idx->opt_fused_defer = value < 0 || value > 2 ? 1 : (int)value;
+    else if (k == "fused_defer") idx->opt_fused_defer = value < 0 || value > 7 ? 1 : (int)value;
     else if (k == "order_by_length") idx->opt_order_by_length = value > 0 ? 1 : 0;
+    else if (k == "query_blocks") idx->opt_query_blocks = value > 0 && value < (1 << 20) ? (int)value : 0;
     else if (k == "table_ctx") {  // 16-byte table entries on / off: takes effect by rebuilding the large table
         idx->opt_table_ctx = value != 0;
         if (idx->big_entries) {
@@ -1022,16 +1024,30 @@ static int search_phased(const fmx_index *idx, DevBuf *buf, const SearchArgs &a,
         g.re = buf[B_RE].as<uint32_t>();
         g.hint = buf[B_HINT].as<uint32_t>();
         g.want_rows = want_rows ? 1u : 0u;
-        uint64_t blocks = (npat + 255) / 256;
-        const uint64_t cap = (uint64_t)idx->sms * 8 * 8;
-        if (blocks > cap) blocks = cap;
         // 1 (default): with the 16-byte table, where the head finishes nine patterns in ten; 2: always (A/B)
-        const bool defer = ((g.a.big_tab4 != nullptr && idx->opt_fused_defer == 1) || idx->opt_fused_defer == 2) && !g.a.order &&
-                           npat < 0xFFFFFFFFull;
+        // 3 .. 7: as 1 with (resident blocks per SM, rounds between two looks at the queue) = (6,1) (5,1) (5,2) (6,2) (5,4):
+        // the A/B of FMX_DEFER_BLOCKS / FMX_DEFER_ROUNDS; the 16-byte table exists for the Q4 layout only
+        const int od = idx->opt_fused_defer;
+        const bool defer = ((g.a.big_tab4 != nullptr && od != 0) || od == 2) && !g.a.order && npat < 0xFFFFFFFFull;
+        uint64_t blocks = (npat + 255) / 256;
+        const uint64_t cap = idx->opt_query_blocks > 0 ? (uint64_t)idx->opt_query_blocks
+                                                       : (uint64_t)idx->sms * (defer ? FMX_QUERY_BLOCKS_PER_SM : 64);
+        if (blocks > cap) blocks = cap;
         dispatch(idx, [&](auto K, auto LY) {
             if constexpr (K() != FMX_KIND_RLFM_) {
-                if (defer) k_query_fused_defer<K(), LY()><<<(unsigned)blocks, 256, 0, st>>>(idx->dev, g);
-                else k_query_fused<K(), LY()><<<(unsigned)blocks, 256, 0, st>>>(idx->dev, g);
+                const unsigned nb = (unsigned)blocks;
+                if (!defer) {
+                    k_query_fused<K(), LY()><<<nb, 256, 0, st>>>(idx->dev, g);
+                    return;
+                }
+                if constexpr (LY() == FMX_LAYOUT_Q4) {
+                    if (od == 3) return (void)k_query_fused_defer<K(), LY(), 6, 1><<<nb, 256, 0, st>>>(idx->dev, g);
+                    if (od == 4) return (void)k_query_fused_defer<K(), LY(), 5, 1><<<nb, 256, 0, st>>>(idx->dev, g);
+                    if (od == 5) return (void)k_query_fused_defer<K(), LY(), 5, 2><<<nb, 256, 0, st>>>(idx->dev, g);
+                    if (od == 6) return (void)k_query_fused_defer<K(), LY(), 6, 2><<<nb, 256, 0, st>>>(idx->dev, g);
+                    if (od == 7) return (void)k_query_fused_defer<K(), LY(), 5, 4><<<nb, 256, 0, st>>>(idx->dev, g);
+                }
+                k_query_fused_defer<K(), LY(), FMX_DEFER_BLOCKS, FMX_DEFER_ROUNDS><<<nb, 256, 0, st>>>(idx->dev, g);
             }
         });
         LAUNCH_CHECK();

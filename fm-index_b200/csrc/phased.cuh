@@ -413,10 +413,9 @@ __global__ void __launch_bounds__(256, 5) k_query_fused(const __grid_constant__ 
 // left, range, position: five words) in a shared-memory queue; whenever the block holds 256 parked states all of its
 // threads take one each through query_tail, so the expensive path runs with full warps.  No global queue, no second
 // kernel; the only extra traffic is re-reading the parked patterns' characters.
-#define FMX_DEFER_CAP 512u
-template <int KIND, int LAYOUT>
+template <int KIND, int LAYOUT, uint32_t CAP>
 __device__ __forceinline__ void defer_tail(const FmxDev &ix, const Tabs<LAYOUT> &tb, const PhasedArgs &g, uint32_t (*spat)[256],
-                                           const uint32_t (*dq)[FMX_DEFER_CAP], uint32_t slot, unsigned long long &steps,
+                                           const uint32_t (*dq)[CAP], uint32_t slot, unsigned long long &steps,
                                            unsigned long long &reqs) {
     const SearchArgs &a = g.a;
     const uint64_t p = dq[0][slot];
@@ -442,11 +441,24 @@ __device__ __forceinline__ void defer_tail(const FmxDev &ix, const Tabs<LAYOUT> 
     g.hint[p] = hint;
 }
 
-template <int KIND, int LAYOUT>
-__global__ void __launch_bounds__(256, 5) k_query_fused_defer(const __grid_constant__ FmxDev ix, const __grid_constant__ PhasedArgs g) {
+// Two knobs, both A/B'd on the target (option fused_defer = 3 .. 6, profiles/r02_c18_*):
+//   MINB    resident blocks per SM.  The kernel lives on requests in flight: 5 blocks (<= 48 registers, no spills)
+//           against 6 (<= 40 registers, 40-400 bytes of spills per thread).
+//   ROUNDS  rounds of 256 patterns between two looks at the queue.  One pattern in ten is parked, so the queue needs
+//           ~10 rounds to fill a drain of 256; looking after every round costs two block barriers per round, each
+//           making every warp wait for the slowest table lookup of the block.  The queue holds 256 * (ROUNDS + 1)
+//           states: fewer than 256 left over plus at most 256 per round.
+//   grid    blocks per SM of this kernel's grid-stride loop (FMX_QUERY_BLOCKS_PER_SM x SMs at most; option query_blocks
+//           overrides; k_query_fused keeps 64): many short-lived blocks against exactly the resident ones.
+#define FMX_DEFER_BLOCKS 5
+#define FMX_DEFER_ROUNDS 1
+#define FMX_QUERY_BLOCKS_PER_SM 64
+template <int KIND, int LAYOUT, int MINB, int ROUNDS>
+__global__ void __launch_bounds__(256, MINB) k_query_fused_defer(const __grid_constant__ FmxDev ix, const __grid_constant__ PhasedArgs g) {
+    constexpr uint32_t CAP = 256u * (ROUNDS + 1);
     __shared__ Tabs<LAYOUT> tb;
     __shared__ uint32_t spat[8][256];
-    __shared__ uint32_t dq[5][FMX_DEFER_CAP];
+    __shared__ uint32_t dq[5][CAP];
     __shared__ uint32_t dq_n;
     load_tables<LAYOUT>(ix, tb);
     if (threadIdx.x == 0) dq_n = 0;
@@ -477,7 +489,7 @@ __global__ void __launch_bounds__(256, 5) k_query_fused_defer(const __grid_const
                 g.rs[p] = s;
                 g.re[p] = e;
                 g.hint[p] = hint;
-            } else {  // park the state: at most 256 new entries per round on top of fewer than 256 left over
+            } else {  // park the state
                 const uint32_t slot = atomicAdd(&dq_n, 1u);
                 dq[0][slot] = (uint32_t)p;
                 dq[1][slot] = k | (armed ? 0x80000000u : 0u);
@@ -486,16 +498,18 @@ __global__ void __launch_bounds__(256, 5) k_query_fused_defer(const __grid_const
                 dq[4][slot] = pos;
             }
         }
+        if (ROUNDS > 1 && (r + 1) % ROUNDS != 0) continue;  // r is the same for every thread of the block
         __syncthreads();
         while (dq_n >= 256u) {  // the same value for every thread: read between two barriers
             const uint32_t base = dq_n - 256u;
-            defer_tail<KIND, LAYOUT>(ix, tb, g, spat, dq, base + threadIdx.x, steps, reqs);
+            defer_tail<KIND, LAYOUT, CAP>(ix, tb, g, spat, dq, base + threadIdx.x, steps, reqs);
             __syncthreads();
             if (threadIdx.x == 0) dq_n = base;
             __syncthreads();
         }
     }
-    if (threadIdx.x < dq_n) defer_tail<KIND, LAYOUT>(ix, tb, g, spat, dq, threadIdx.x, steps, reqs);
+    __syncthreads();
+    for (uint32_t slot = threadIdx.x; slot < dq_n; slot += 256u) defer_tail<KIND, LAYOUT, CAP>(ix, tb, g, spat, dq, slot, steps, reqs);
     if (a.work) {
         warp_add(steps, a.work);
         warp_add(reqs, a.work + 2);

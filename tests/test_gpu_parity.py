@@ -880,8 +880,12 @@ def test_table_entries_with_text_context(kind):
             # piece of a position = zeros before it (multi_pieces.rs:287-296; the literal walk is pinned in other tests and
             # would take piece-length LF steps per hit here)
             opid = np.searchsorted(zeros, opos, side="left").astype(np.uint64)
-            for rows, defer in ((True, 1), (False, 1), (True, 0), (False, 0)):
-                index.set_option("fused_defer", defer)       # 1: block-local second pass for the patterns the head does not finish
+            # 1: block-local second pass for the patterns the head does not finish; 3 .. 7: its occupancy / queue variants
+            # (60 k patterns are one round of 235 blocks; 7 blocks make it 34 rounds: queue drains and leftovers as at scale)
+            for rows, defer, nblocks in ((True, 1, 0), (False, 1, 7), (True, 0, 0), (False, 0, 7), (True, 3, 7), (False, 5, 7), (True, 6, 7),
+                                        (False, 7, 7), (True, 7, 3)):
+                index.set_option("fused_defer", defer)
+                index.set_option("query_blocks", nblocks)
                 r = index.query_batch(pats, mode, rows=rows, counts=True, piece_ids=kind == orc.MULTI, capacity=int(ooff[-1]) + 8)
                 if rows:
                     assert np.array_equal(r["s"], s) and np.array_equal(r["e"], e), (ctx, mode, defer)
@@ -892,6 +896,7 @@ def test_table_entries_with_text_context(kind):
                 if not po:
                     assert index.last_work()[0] == int(steps.sum()), (ctx, mode, rows, defer)
             index.set_option("fused_defer", 1)
+            index.set_option("query_blocks", 0)
         bad = bytearray(text[1000:1028].tobytes())               # an invalid character inside the context window
         bad[5] = 5
         for rows in (True, False):

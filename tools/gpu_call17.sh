@@ -4,7 +4,7 @@
 # launch list of the default bench command, ncu --set full of the fused query kernel
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q --timeout=600 --tb=short -rf --durations=30 > gpurun_out/r02_c17_pytest.log 2>&1
+timeout 780 python -m pytest tests -m gpu -q --timeout=600 --tb=short -rf --durations=30 > gpurun_out/r02_c17_pytest.log 2>&1
 echo "pytest rc=$?"; tail -45 gpurun_out/r02_c17_pytest.log
 M="dram__bytes_read.sum,dram__bytes_write.sum,lts__t_requests_srcunit_tex_op_read.sum,lts__t_sectors_srcunit_tex_op_read.sum,smsp__inst_executed.sum,smsp__thread_inst_executed.sum,gpu__time_duration.sum"
 timeout 400 ncu --metrics $M --clock-control none --profile-from-start off -o gpurun_out/r02_c17_step_target_rich -f python tools/prof_step.py --workload target_dna1g > gpurun_out/r02_c17_step_target_rich.log 2>&1

@@ -826,7 +826,8 @@ def roofline_block(args, w, index, mode_name, npat, hits, ms_step, ms_count, pha
             fr_bw, "%.3f" % fr_req if fr_req is not None else "n/a")
     else:
         r["traffic"] = None
-        issued = float(req_search + req_emit)
+        # k_search (compact indexes, RLFM) carries no request counters: the emit kernel's alone would say nothing about the step
+        issued = float(req_search + req_emit) if req_search else 0.0
         r["issued_index_requests_per_step"] = issued
         r["requests_per_pattern"] = issued / npat if issued else None
         est_bytes = issued * 64.0   # every index load carries .L2::64B: a miss fills 64 bytes

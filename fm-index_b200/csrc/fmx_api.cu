@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <type_traits>
@@ -123,6 +124,7 @@ struct fmx_index {
     int opt_phased = 2;               // dense verify structures: 2 = k_query_fused (one kernel), 1 = the three phased kernels, 0 = k_search
     int opt_order_by_length = 0;      // 1: ragged batches through the fused kernel in order of pattern length (A/B: lost, see search_phased)
     int opt_fused_defer = 1;          // fused kernel with the block-local second pass when the 16-byte table is in use (phased.cuh)
+    int opt_emit_fused = FMX_EMIT_FUSED_DEFAULT;  // rich locate: offsets + positions in one pass over the ranges (k_offsets_emit); FMX_EMIT_FUSED=0|1 at construction
     int opt_query_blocks = 0;         // > 0: at most this many blocks for the fused query kernels (tests: many rounds per block on small batches)
     int opt_extract_text = 1;         // 0: extraction by LF / FL steps even when text and suffix array are resident (A/B)
     int opt_locate_dense = 1;         // 0: LF walks to the samples even when the full suffix array is resident (A/B)
@@ -361,6 +363,7 @@ static int finish_index(fmx_index *idx, fmx_index **out) {
         return fail(FMX_ERR_CUDA, std::string("index setup: ") + cudaGetErrorString(e));
     }
     idx->d_work = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(idx->d_err) + 64);
+    if (const char *ef = std::getenv("FMX_EMIT_FUSED")) idx->opt_emit_fused = ef[0] && ef[0] != '0' ? 1 : 0;
     bind_sections(idx);
     int rc = build_kmer_table(idx);
     if (rc) {
@@ -592,6 +595,7 @@ int fmx_index_set_option(fmx_index *idx, const char *key, int64_t value) {
     else if (k == "extract_text") idx->opt_extract_text = value != 0;
     else if (k == "fused_defer") idx->opt_fused_defer = value < 0 || value > 7 ? 1 : (int)value;
     else if (k == "order_by_length") idx->opt_order_by_length = value > 0 ? 1 : 0;
+    else if (k == "emit_fused") idx->opt_emit_fused = value > 0 ? 1 : 0;
     else if (k == "query_blocks") idx->opt_query_blocks = value > 0 && value < (1 << 20) ? (int)value : 0;
     else if (k == "table_ctx") {  // 16-byte table entries on / off: takes effect by rebuilding the large table
         idx->opt_table_ctx = value != 0;
@@ -643,14 +647,20 @@ uint32_t fmx_index_sectors_per_rank(const fmx_index *idx) {
 // tiles below this count: each block of the last phase reduces the preceding tile sums itself
 #define FMX_SCAN_SELF_CARRY_TILES 4096
 
+// `last` (optional): launches the last phase itself -- (tiles, scanned tile prefixes or null, tile sums or null) as
+// k_scan_apply takes them -- so that a consumer of the offsets can be fused into it (k_offsets_emit)
+using ScanLast = std::function<int(unsigned, const uint64_t *, const uint64_t *)>;
+
 template <class Load, class Tout, class Op, bool EXCL>
-static int device_scan_load(Load in, uint64_t n, Tout *out, Op op, bool write_total, DevBuf &tiles, cudaStream_t st) {
+static int device_scan_load(Load in, uint64_t n, Tout *out, Op op, bool write_total, DevBuf &tiles, cudaStream_t st,
+                            const ScanLast *last = nullptr) {
     if (n == 0) {
         if (EXCL && write_total) CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(Tout), st));
         return 0;
     }
     uint64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     if (ntiles == 1) {
+        if (last) return (*last)(1u, nullptr, nullptr);
         k_scan_apply<Load, Tout, Op, EXCL><<<1, SCAN_THREADS, 0, st>>>(in, n, nullptr, nullptr, out, op, write_total ? 1 : 0);
         LAUNCH_CHECK();
         return 0;
@@ -666,6 +676,7 @@ static int device_scan_load(Load in, uint64_t n, Tout *out, Op op, bool write_to
     k_scan_reduce<Load, Op><<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(in, n, sum0, op);
     LAUNCH_CHECK();
     if (ntiles <= FMX_SCAN_SELF_CARRY_TILES) {
+        if (last) return (*last)((unsigned)ntiles, nullptr, sum0);
         k_scan_apply<Load, Tout, Op, EXCL><<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(in, n, nullptr, sum0, out, op, write_total ? 1 : 0);
         LAUNCH_CHECK();
         return 0;
@@ -692,6 +703,7 @@ static int device_scan_load(Load in, uint64_t n, Tout *out, Op op, bool write_to
         k_scan_apply<L64, uint64_t, Op, true><<<g, SCAN_THREADS, 0, st>>>(L64{lv[k].sum}, lv[k].n, carry, nullptr, lv[k].pre, op, 0);
         LAUNCH_CHECK();
     }
+    if (last) return (*last)((unsigned)ntiles, pre0, nullptr);
     k_scan_apply<Load, Tout, Op, EXCL><<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(in, n, pre0, nullptr, out, op, write_total ? 1 : 0);
     LAUNCH_CHECK();
     return 0;
@@ -1657,6 +1669,46 @@ static int emit_dense(const fmx_index *idx, DevBuf *buf, uint64_t npat, const ui
     return 0;
 }
 
+// counts -> offsets -> positions of a rich index in one pass over the ranges (k_offsets_emit as the last phase of the
+// scan) + k_emit_big for the patterns with many matches
+template <class Tw>
+static int offsets_emit_fused(const fmx_index *idx, DevBuf *buf, uint64_t npat, const uint32_t *hint, const QueryOut &o, cudaStream_t st,
+                              bool count_work) {
+    int rc;
+    if ((rc = buf[B_BIGQ].ensure(npat * 4 + 16))) return rc;
+    if ((rc = buf[B_QN].ensure(64))) return rc;
+    EmitArgs<Tw, Tw> g;
+    g.rs = buf[B_RS].as<uint32_t>();
+    g.re = buf[B_RE].as<uint32_t>();
+    g.hint = hint;
+    g.off = static_cast<const Tw *>(o.hit_off);
+    g.npat = npat;
+    g.capacity = o.capacity;
+    g.positions = static_cast<Tw *>(o.positions);
+    g.piece_ids = static_cast<Tw *>(o.piece_ids);
+    g.bigq = buf[B_BIGQ].as<uint32_t>();
+    g.bign = buf[B_QN].as<unsigned long long>() + 4;
+    g.req = count_work ? idx->d_work + 3 : nullptr;
+    CUDA_TRY(cudaMemsetAsync(g.bign, 0, 8, st));
+    const bool multi = idx->hdr.kind == FMX_KIND_MULTI;
+    Tw *off_out = static_cast<Tw *>(o.hit_off);
+    const ScanLast last = [&](unsigned ntiles, const uint64_t *prefix, const uint64_t *sums) -> int {
+        if (multi) k_offsets_emit<FMX_KIND_MULTI_, Tw><<<ntiles, SCAN_THREADS, 0, st>>>(idx->dev, g, off_out, prefix, sums);
+        else k_offsets_emit<FMX_KIND_FM_, Tw><<<ntiles, SCAN_THREADS, 0, st>>>(idx->dev, g, off_out, prefix, sums);
+        LAUNCH_CHECK();
+        return 0;
+    };
+    if ((rc = device_scan_load<LoadCount32, Tw, OpSum, true>(LoadCount32{g.rs, g.re}, npat, off_out, OpSum(), true, buf[B_TILES], st, &last)))
+        return rc;
+    phase_mark(idx, 5, st);
+    uint64_t bblocks = (uint64_t)idx->sms * 8;
+    if (bblocks > (npat + 7) / 8) bblocks = (npat + 7) / 8;
+    if (multi) k_emit_big<FMX_KIND_MULTI_, Tw, Tw><<<(unsigned)bblocks, 256, 0, st>>>(idx->dev, g);
+    else k_emit_big<FMX_KIND_FM_, Tw, Tw><<<(unsigned)bblocks, 256, 0, st>>>(idx->dev, g);
+    LAUNCH_CHECK();
+    return 0;
+}
+
 // The whole query on device buffers, asynchronous.  HBM-rich indexes: phased search (no inverse-suffix-array
 // request unless the caller wants the rows) + positions from the hints / the resident suffix array.  Every other
 // index: k_search + the LF-walk locate kernels.
@@ -1727,6 +1779,13 @@ static int query_device(const fmx_index *idx, DevBuf *buf, int mode, const PatSr
             LAUNCH_CHECK();
         }
         if (!want_off) return 0;
+        if (want_hits && o.capacity > 0 && idx->opt_emit_fused) {  // offsets and positions in one pass over the ranges
+            if (a.work) CUDA_TRY(cudaMemsetAsync(idx->d_work + 1, 0, sizeof(unsigned long long), st));
+            rc = o.width == 8 ? offsets_emit_fused<uint64_t>(idx, buf, npat, hint, o, st, a.work != nullptr)
+                              : offsets_emit_fused<uint32_t>(idx, buf, npat, hint, o, st, a.work != nullptr);
+            phase_mark(idx, 6, st);
+            return rc;
+        }
         if (o.width == 8) rc = device_scan_load<LoadCount32, uint64_t, OpSum, true>(LoadCount32{rs, re}, npat, static_cast<uint64_t *>(o.hit_off), OpSum(), true, buf[B_TILES], st);
         else rc = device_scan_load<LoadCount32, uint32_t, OpSum, true>(LoadCount32{rs, re}, npat, static_cast<uint32_t *>(o.hit_off), OpSum(), true, buf[B_TILES], st);
         if (rc) return rc;

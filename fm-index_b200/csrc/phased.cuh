@@ -587,6 +587,90 @@ __global__ void __launch_bounds__(256) k_emit_small(const __grid_constant__ FmxD
     if (g.req) warp_add(reqs, g.req);
 }
 
+#define FMX_EMIT_FUSED_DEFAULT 0
+// ---- counts -> offsets -> positions in ONE pass over the ranges (option "emit_fused"): the last phase of the scan
+// (k_scan_apply<LoadCount32>) and k_emit_small as one kernel.  The separate kernels read every range twice more and the
+// offsets once more than needed (1.6 GB per 100 M patterns).  Here a warp owns 256 consecutive patterns and visits them
+// 32 at a time, lane = pattern, so the loads of (rs, re, hint) and the stores of offsets and positions are the coalesced
+// ones of k_emit_small; the match counts stay in registers between the two sweeps (warp total -> warp base -> offsets).
+// tile_prefix / tile_sums: as in k_scan_apply.  Patterns with more than FMX_EMIT_SMALL matches go to k_emit_big's queue.
+template <int KIND, class Tw>
+__global__ void __launch_bounds__(SCAN_THREADS) k_offsets_emit(const __grid_constant__ FmxDev ix, const __grid_constant__ EmitArgs<Tw, Tw> g,
+                                                              Tw *off_out, const uint64_t *tile_prefix, const uint64_t *tile_sums) {
+    __shared__ uint64_t s_warp[SCAN_THREADS / 32];
+    OpSum op;
+    uint64_t tile_carry = 0;
+    if (tile_prefix) {
+        tile_carry = tile_prefix[blockIdx.x];
+    } else if (tile_sums) {
+        uint64_t part = 0;
+        for (uint32_t i = threadIdx.x; i < blockIdx.x; i += SCAN_THREADS) part += tile_sums[i];
+        block_scan_excl(part, op, tile_carry, s_warp);   // ends with a barrier: s_warp is free again
+    }
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint64_t wbase = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)wid * (32u * SCAN_ITEMS);
+    uint32_t cnt[SCAN_ITEMS];
+    uint64_t wtot = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; j++) {
+        const uint64_t p = wbase + (uint64_t)j * 32u + lane;
+        uint32_t c = 0;
+        if (p < g.npat) {
+            const uint32_t s = g.rs[p], e = g.re[p];
+            c = e > s ? e - s : 0u;
+        }
+        cnt[j] = c;
+        wtot += c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wtot += __shfl_xor_sync(0xffffffffu, wtot, o);
+    if (lane == 0) s_warp[wid] = wtot;
+    __syncthreads();
+    uint64_t carry = tile_carry;
+    for (uint32_t w = 0; w < wid; w++) carry += s_warp[w];
+    unsigned long long reqs = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; j++) {
+        const uint64_t p = wbase + (uint64_t)j * 32u + lane;
+        const uint32_t c = cnt[j];
+        uint64_t inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc += t;
+        }
+        const uint64_t o = carry + inc - c;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+        bool big = false;
+        if (p < g.npat) {
+            off_out[p] = (Tw)o;
+            if (p == g.npat - 1) off_out[g.npat] = (Tw)(o + c);
+            if (c > FMX_EMIT_SMALL) {
+                big = true;
+            } else if (c) {
+                const uint32_t s = g.rs[p];
+                const uint32_t h = (g.hint && c == 1u) ? g.hint[p] : FMX_NOHINT;
+                for (uint32_t i = 0; i < c; i++) {
+                    if (o + i >= g.capacity) break;
+                    const uint32_t v = h != FMX_NOHINT ? h : ldg32_s(ix.vsa + s + i);
+                    reqs += h != FMX_NOHINT ? 0u : 1u;
+                    if (g.positions) g.positions[o + i] = (Tw)v;
+                    if (KIND == FMX_KIND_MULTI_ && g.piece_ids) g.piece_ids[o + i] = (Tw)piece_of(ix, v);
+                }
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, big);
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(g.bign, (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (big) g.bigq[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)p;
+        }
+    }
+    if (g.req) warp_add(reqs, g.req);
+}
+
 // one warp per pattern with many matches: SA[s .. e) is a contiguous read, the output a contiguous write
 template <int KIND, class Toff, class Tout>
 __global__ void __launch_bounds__(256) k_emit_big(const __grid_constant__ FmxDev ix, const __grid_constant__ EmitArgs<Toff, Tout> g) {

@@ -138,7 +138,8 @@ int fmx_build_suffix_array_device(const void *text, uint64_t n, uint32_t char_wi
  * (extraction from the resident text), "order_by_length" 0|1 (ragged batches through the fused kernel in order of
  * pattern length; off: it measured slower), "fused_defer" 0|1|2 (the fused query kernel parks the patterns its table lookup does not finish
  * in a shared-memory queue and runs them with full warps: never / with the 16-byte table entries / always; 3..7 = as 1 with
- * (resident blocks per SM, rounds between two looks at the queue) = (6,1) (5,1) (5,2) (6,2) (5,4): tuning A/B), "query_blocks" (> 0: at most this many blocks for the fused query kernels; tests), "table_ctx" 0|1 (16-byte entries of the large k-mer table that carry the 16 text
+ * (resident blocks per SM, rounds between two looks at the queue) = (6,1) (5,1) (5,2) (6,2) (5,4): tuning A/B), "query_blocks" (> 0: at most this many blocks for the fused query kernels; tests), "emit_fused" 0|1 (rich locate: hit offsets and
+ * positions in one pass over the ranges -- the scan's last phase and the emit kernel as one; FMX_EMIT_FUSED=0|1 at construction time), "table_ctx" 0|1 (16-byte entries of the large k-mer table that carry the 16 text
  * characters in front of one-row ranges: a pattern with <= 16 characters left after the table is finished by ONE
  * request; rebuilds the table; FMX_NO_TABLE_CTX=1 at construction time; built while afterwards at least as much HBM stays
  * free as the table takes, FMX_TABLE_CTX_FORCE=1 lifts that).  Environment at construction time: FMX_FORCE_WAVELET=1

@@ -796,9 +796,10 @@ def test_rich_mode_query_parity(kind, mc, env, monkeypatch):
         assert index.last_work()[0] == int(steps.sum())
         got = b.locate(piece_ids=kind == orc.MULTI)             # two-call path: dense k_locate_simple
         assert np.array_equal(got[0], ooff) and np.array_equal(got[1], opos)
-        for rows, width, phased in ((True, 8, 2), (False, 8, 2), (True, 4, 2), (False, 4, 2), (True, 8, 1), (False, 4, 1)):
+        for rows, width, phased, fused in ((True, 8, 2, 0), (False, 8, 2, 1), (True, 4, 2, 1), (False, 4, 2, 0), (True, 8, 1, 1), (False, 4, 1, 0)):
             if True:
                 index.set_option("search_phased", phased)       # 2: one fused kernel (default); 1: seed / steps / verify kernels
+                index.set_option("emit_fused", fused)           # 1: hit offsets + positions in one pass over the ranges (k_offsets_emit)
                 r = index.query_batch(pats, mode, rows=rows, counts=True, piece_ids=kind == orc.MULTI, width=width)
                 if rows:
                     assert np.array_equal(r["s"], s) and np.array_equal(r["e"], e)
@@ -947,10 +948,13 @@ def test_rich_mode_many_hits_and_pipeline():
     s, e = oracle.search_batch(flat, off)
     ooff, opos, _ = oracle.locate_batch(s, e)
     index.set_option("pipeline_chunk", 4_001)
-    for width in (8, 4):
+    for width, fused in ((8, 0), (4, 0), (8, 1), (4, 1)):        # emit_fused: k_offsets_emit instead of scan apply + k_emit_small
+        index.set_option("emit_fused", fused)
         r = index.query_batch(pats, width=width, capacity=int(ooff[-1]) + 3)
         assert r["total"] == int(ooff[-1])
         assert np.array_equal(r["hit_off"].astype(np.uint64), ooff) and np.array_equal(r["positions"].astype(np.uint64), opos)
+        with pytest.raises(fmx.Error, match="too small"):
+            index.query_batch(pats, width=width, capacity=int(ooff[-1]) - 5)
     r = index.query_batch(pats)                                  # default capacity is too small: retried with the exact size
     assert np.array_equal(r["positions"], opos)
     b, h, p = index.search_locate_batch(pats, capacity=int(ooff[-1]) + 3)

@@ -430,7 +430,8 @@ def reference_arm(args, name, w):
 
 PHASES = ["query kernel (rich: k_query_fused[_defer] = table lookup + rank steps + verify in one launch; compact: k_search; "
           "option search_phased=1: k_ph_seed)", "steps (k_ph_steps; search_phased=1 only)", "verify (k_ph_verify; search_phased=1 only)",
-          "steps, second pass (+ widen)", "counts + offsets scan", "emit / locate"]
+          "steps, second pass (+ widen)", "counts + offsets scan (rich, emit_fused: k_offsets_emit also writes the positions of ranges of <= 4 rows)",
+          "emit / locate (rich, emit_fused: k_emit_big only)"]
 
 
 class DeviceRun:
@@ -780,7 +781,7 @@ def roofline_block(args, w, index, mode_name, npat, hits, ms_step, ms_count, pha
     alg_bytes_locate = 32.0 * hits * ((Lw if kind != RLFM else Lw + 3) * (lf_steps / hits if lf_steps and hits else mean_walk) + 1)
     cap = ncu_capture(args.workload, npat, mode_name)
     t = ms_step * 1e-3
-    names = ["k_ph_seed", "k_ph_steps", "k_ph_verify", "k_ph_steps (second pass)", "scan", "k_emit_small + k_emit_big / k_locate_*"]
+    names = ["k_ph_seed", "k_ph_steps", "k_ph_verify", "k_ph_steps (second pass)", "scan (+ k_offsets_emit)", "k_emit_small + k_emit_big / k_locate_*"]
     opts = dict(kv.split("=") for kv in args.option)
     if not req_search or mode_name != "rich" or kind == RLFM:
         names[0] = "k_search"

@@ -587,7 +587,7 @@ __global__ void __launch_bounds__(256) k_emit_small(const __grid_constant__ FmxD
     if (g.req) warp_add(reqs, g.req);
 }
 
-#define FMX_EMIT_FUSED_DEFAULT 0
+#define FMX_EMIT_FUSED_DEFAULT 1
 // ---- counts -> offsets -> positions in ONE pass over the ranges (option "emit_fused"): the last phase of the scan
 // (k_scan_apply<LoadCount32>) and k_emit_small as one kernel.  The separate kernels read every range twice more and the
 // offsets once more than needed (1.6 GB per 100 M patterns).  Here a warp owns 256 consecutive patterns and visits them

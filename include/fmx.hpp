@@ -13,6 +13,8 @@
 //     for (Match& m : s.iter_matches()) m.locate();      // ascending SA rows   (wrapper.rs:203-217)
 //     m.iter_chars_backward(16); m.iter_chars_forward(20); m.piece_id();
 //     index.search_batch(patterns)                       // the batched entry the GPU path exists for
+//     index.query_batch(patterns)                        // counts + CSR matches from ONE fused call (fmx_query_batch)
+//     IndexGroup g(text, FMX_KIND_MULTI, 2, {0, 1}, FMX_GROUP_BY_PIECE);  g.query_batch(patterns);   // several GPUs
 //
 // Differences forced by the language: iterators are returned as vectors (iter_chars_* take the
 // number of characters, like `.take(k)`), errors are exceptions (fmx::InvalidText = Error::InvalidText;
@@ -105,6 +107,64 @@ struct SearchBatch {
     uint64_t count(size_t p) const { return e[p] - s[p]; }
 };
 
+// result of the fused batched query: Search::count per pattern + the matches as CSR (reference iteration order)
+struct QueryBatch {
+    std::vector<uint64_t> s, e;                           // only with with_ranges
+    std::vector<uint64_t> counts, hit_off, positions, piece_ids;
+    uint64_t total_hits = 0;
+};
+
+// fills a fmx_query over byte patterns with 64-bit outputs and runs `call`; a capacity guess that is too small is
+// retried once with the exact size the first call reported (FMX_ERR_CAPACITY leaves counts / hit_off filled)
+template <class Call>
+inline QueryBatch run_query_batch(Call call, const std::vector<std::string> &patterns, int mode, bool locate, bool piece_ids,
+                                  bool with_ranges) {
+    std::vector<uint8_t> flat;
+    std::vector<uint64_t> off{0};
+    for (auto &p : patterns) {
+        flat.insert(flat.end(), p.begin(), p.end());
+        off.push_back(flat.size());
+    }
+    const size_t n = patterns.size();
+    QueryBatch b;
+    b.counts.resize(n);
+    if (with_ranges) {
+        b.s.resize(n);
+        b.e.resize(n);
+    }
+    if (locate) b.hit_off.resize(n + 1);
+    uint64_t cap = locate ? (2 * n > 1024 ? 2 * n : 1024) : 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if (locate) b.positions.resize(cap);
+        if (piece_ids) b.piece_ids.resize(cap);
+        fmx_query q{};
+        q.mode = mode;
+        q.patterns = flat.data();
+        q.pat_off = off.data();
+        q.npat = n;
+        q.out_width = 8;
+        q.out_s = with_ranges ? b.s.data() : nullptr;
+        q.out_e = with_ranges ? b.e.data() : nullptr;
+        q.counts = b.counts.data();
+        q.hit_off = locate ? b.hit_off.data() : nullptr;
+        q.positions = locate ? b.positions.data() : nullptr;
+        q.piece_ids = piece_ids ? b.piece_ids.data() : nullptr;
+        q.capacity = cap;
+        uint64_t total = 0;
+        const int rc = call(&q, &total);
+        b.total_hits = total;
+        if (rc == FMX_ERR_CAPACITY && attempt == 0 && locate) {
+            cap = total;
+            continue;
+        }
+        check(rc);
+        break;
+    }
+    if (locate) b.positions.resize(b.total_hits);
+    if (piece_ids) b.piece_ids.resize(b.total_hits);
+    return b;
+}
+
 class IndexBase {
   public:
     IndexBase(const IndexBase &) = delete;
@@ -140,6 +200,13 @@ class IndexBase {
             fmx_free(pid);
         }
         return b;
+    }
+    // the same batch through ONE fused call (fmx_query_batch: counts, CSR hit offsets, positions, piece ids; no SA
+    // ranges unless asked for, which lets an HBM-rich index skip the inverse-suffix-array request)
+    QueryBatch query_batch(const std::vector<std::string> &patterns, int mode = FMX_SEARCH, bool with_ranges = false) const {
+        const fmx_index *h = h_;
+        return run_query_batch([h](const fmx_query *q, uint64_t *total) { return fmx_query_batch(h, q, total); }, patterns, mode,
+                               has_locate(), is_multi() && has_locate(), with_ranges);
     }
     const fmx_index *handle() const { return h_; }
     bool has_locate() const { return fmx_index_has_locate(h_) != 0; }
@@ -189,6 +256,40 @@ struct FMIndexMultiPieces : MultiPiecesBase {
 };
 struct FMIndexMultiPiecesWithLocate : MultiPiecesBase {
     FMIndexMultiPiecesWithLocate(const Text &t, size_t level, int device = 0) : MultiPiecesBase(t, (int)level, device) {}
+};
+
+// fmx_group: several GPUs of this process behind one handle (fmx.h, "multi-GPU").
+//   FMX_GROUP_REPLICATE  the index copied to every device, batches cut into shards; input order and the reference's
+//                        iteration order preserved
+//   FMX_GROUP_BY_PIECE   FMIndexMultiPieces: pieces partitioned over the devices (device ids may repeat), every member
+//                        answers the whole batch, parts merged on the first device; match SETS, counts, positions and
+//                        piece ids of the whole text (multi_pieces.rs:188-223), hits partition-major.  This is also how a
+//                        MultiPieces text of 2^32 symbols or more is served: every partition stays below 2^32, positions
+//                        are u64 in the coordinates of the whole text.
+class IndexGroup {
+  public:
+    IndexGroup(const Text &text, int kind, int level, const std::vector<int> &devices, int group_mode = FMX_GROUP_REPLICATE,
+               int index_mode = FMX_MODE_AUTO)
+        : kind_(kind), level_(level) {
+        check(fmx_group_create(devices.data(), (int)devices.size(), group_mode, text.text().data(), text.text().size(), 1,
+                               text.max_character(), kind, level, index_mode, &g_));
+    }
+    IndexGroup(const IndexGroup &) = delete;
+    IndexGroup &operator=(const IndexGroup &) = delete;
+    ~IndexGroup() { fmx_group_free(g_); }
+    int size() const { return fmx_group_size(g_); }
+    uint64_t len() const { return fmx_group_len(g_); }
+    uint64_t pieces_count() const { return fmx_group_pieces_count(g_); }
+    QueryBatch query_batch(const std::vector<std::string> &patterns, int mode = FMX_SEARCH) const {
+        const fmx_group *g = g_;
+        const bool locate = level_ >= 0;
+        return run_query_batch([g](const fmx_query *q, uint64_t *total) { return fmx_group_query_batch(g, q, total); }, patterns, mode,
+                               locate, locate && kind_ == FMX_KIND_MULTI, false);
+    }
+
+  private:
+    fmx_group *g_ = nullptr;
+    int kind_, level_;
 };
 
 // ---- Search

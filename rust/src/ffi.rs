@@ -7,6 +7,14 @@ pub struct fmx_index {
     _private: [u8; 0],
 }
 
+/// several GPUs of one process behind one handle (include/fmx.h, "multi-GPU")
+#[repr(C)]
+pub struct fmx_group {
+    _private: [u8; 0],
+}
+pub const FMX_GROUP_REPLICATE: c_int = 0;
+pub const FMX_GROUP_BY_PIECE: c_int = 1;
+
 pub const FMX_KIND_FM: c_int = 0;
 pub const FMX_KIND_RLFM: c_int = 1;
 pub const FMX_KIND_MULTI: c_int = 2;
@@ -67,4 +75,12 @@ extern "C" {
     pub fn fmx_extract_batch(idx: *const fmx_index, rows: *const u64, nrows: u64, k: u32, forward: c_int,
                              out: *mut u8, out_len: *mut u32) -> c_int;
     pub fn fmx_rows_op(idx: *const fmx_index, op: c_int, rows: *const u64, nrows: u64, out: *mut u64) -> c_int;
+    pub fn fmx_group_create(device_ids: *const c_int, ndev: c_int, group_mode: c_int, text: *const c_void, n: u64,
+                            char_width: u32, max_character: u64, kind: c_int, level: c_int, index_mode: c_int,
+                            out: *mut *mut fmx_group) -> c_int;
+    pub fn fmx_group_free(g: *mut fmx_group);
+    pub fn fmx_group_size(g: *const fmx_group) -> c_int;
+    pub fn fmx_group_len(g: *const fmx_group) -> u64;
+    pub fn fmx_group_pieces_count(g: *const fmx_group) -> u64;
+    pub fn fmx_group_query_batch(g: *const fmx_group, q: *const fmx_query, total_hits: *mut u64) -> c_int;
 }

@@ -440,6 +440,12 @@ pub struct BatchResult {
 }
 
 fn query_batch<C: Character, K: AsRef<[C]>>(core: &Core, mode: c_int, patterns: &[K], locate: bool, pieces: bool) -> BatchResult {
+    let h = core.h;
+    query_batch_with::<C, K, _>(|q, total| unsafe { ffi::fmx_query_batch(h, q, total) }, mode, patterns, locate, pieces)
+}
+
+fn query_batch_with<C: Character, K: AsRef<[C]>, F: Fn(*const ffi::fmx_query, *mut u64) -> c_int>(
+    call: F, mode: c_int, patterns: &[K], locate: bool, pieces: bool) -> BatchResult {
     let mut flat: Vec<C> = vec![];
     let mut off: Vec<u64> = vec![0];
     for p in patterns {
@@ -474,7 +480,7 @@ fn query_batch<C: Character, K: AsRef<[C]>>(core: &Core, mode: c_int, patterns: 
             capacity: cap as u64,
         };
         let mut total = 0u64;
-        let rc = unsafe { ffi::fmx_query_batch(core.h, &q, &mut total) };
+        let rc = call(&q, &mut total);
         if rc == ffi::FMX_ERR_CAPACITY {
             cap = total as usize; // hit_off and the total are valid: once more with room for every match
             continue;
@@ -483,6 +489,66 @@ fn query_batch<C: Character, K: AsRef<[C]>>(core: &Core, mode: c_int, patterns: 
         res.positions.truncate(total as usize);
         res.piece_ids.truncate(total as usize);
         return res;
+    }
+}
+
+// ------------------------------------------------------------------ several GPUs of this process (beyond the reference)
+
+/// How an [`IndexGroup`] uses its devices.
+pub enum GroupMode {
+    /// The index copied to every device, batches cut into shards: input order and the reference's iteration order
+    /// are preserved.
+    Replicate,
+    /// `FMIndexMultiPieces` only: the pieces partitioned over the devices (device ids may repeat), every member answers
+    /// the whole batch, the parts are merged on the first device.  Counts, match sets, positions and piece ids are
+    /// those of the whole text (`multi_pieces.rs:188-223`); the matches of a pattern come partition-major.  This is
+    /// also how a text of 2^32 symbols or more is served: every partition stays below 2^32.
+    ByPiece,
+}
+
+/// One handle over several GPUs (`fmx_group_*`); u8 texts.
+pub struct IndexGroup {
+    g: *mut ffi::fmx_group,
+    locate: bool,
+    multi: bool,
+}
+
+impl Drop for IndexGroup {
+    fn drop(&mut self) {
+        unsafe { ffi::fmx_group_free(self.g) }
+    }
+}
+
+impl IndexGroup {
+    /// `kind`: `ffi::FMX_KIND_*`; `level`: the sampling level of the `WithLocate` types, `None` for count-only ones.
+    pub fn new<T: AsRef<[u8]>>(text: &Text<u8, T>, kind: c_int, level: Option<usize>, devices: &[c_int], mode: GroupMode)
+                               -> Result<IndexGroup, Error> {
+        let t = text.text();
+        let mut g: *mut ffi::fmx_group = std::ptr::null_mut();
+        let gm = match mode { GroupMode::Replicate => ffi::FMX_GROUP_REPLICATE, GroupMode::ByPiece => ffi::FMX_GROUP_BY_PIECE };
+        let lvl = level.map(|l| l as c_int).unwrap_or(ffi::FMX_LEVEL_COUNT_ONLY);
+        let rc = unsafe {
+            ffi::fmx_group_create(devices.as_ptr(), devices.len() as c_int, gm, t.as_ptr().cast(), t.len() as u64, 1,
+                                  text.max_character().into_u64(), kind, lvl, ffi::FMX_MODE_AUTO, &mut g)
+        };
+        match rc {
+            0 => Ok(IndexGroup { g, locate: level.is_some(), multi: kind == ffi::FMX_KIND_MULTI }),
+            ffi::FMX_ERR_INVALID_TEXT => Err(invalid_text(&last_error())),
+            _ => panic!("fmx: {}", last_error()),
+        }
+    }
+    /// The size of the whole text, including the trailing `\0`.
+    pub fn len(&self) -> usize {
+        unsafe { ffi::fmx_group_len(self.g) as usize }
+    }
+    pub fn pieces_count(&self) -> usize {
+        unsafe { ffi::fmx_group_pieces_count(self.g) as usize }
+    }
+    /// Count (and locate) many patterns on all devices of the group.
+    pub fn search_batch<K: AsRef<[u8]>>(&self, patterns: &[K]) -> BatchResult {
+        let g = self.g;
+        query_batch_with::<u8, K, _>(|q, total| unsafe { ffi::fmx_group_query_batch(g, q, total) }, ffi::FMX_SEARCH, patterns,
+                                     self.locate, self.locate && self.multi)
     }
 }
 

@@ -11,7 +11,7 @@ timeout 400 ncu --metrics $M --clock-control none --profile-from-start off -o gp
 echo "ncu rich rc=$?"; tail -2 gpurun_out/r02_c17_step_target_rich.log
 timeout 600 python bench.py > gpurun_out/r02_c17_bench_target_dna1g.json 2> gpurun_out/r02_c17_bench_target_dna1g.err
 echo "bench default rc=$?"; tail -c 400 gpurun_out/r02_c17_bench_target_dna1g.err; head -c 600 gpurun_out/r02_c17_bench_target_dna1g.json
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 400 --csv --log-file gpurun_out/r02_c17_launches_target.csv \
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_c17_launches_target.csv \
    python bench.py --steps 2 --warmup 3 --no-compact --no-cpu-baseline --no-e2e --no-extract --no-gather-peak > gpurun_out/r02_c17_launches_target.log 2>&1
 echo "launch list rc=$?"
 B="--steps 3 --no-compact --no-cpu-baseline --no-e2e --no-gather-peak --no-extract --npat 20000000"

@@ -42,7 +42,7 @@ echo "ncu rich rc=$?"; grep "^{" gpurun_out/r02_c18_step_target_rich.log
 python tools/ncu_traffic.py gpurun_out/r02_c18_step_target_rich.ncu-rep:gpurun_out/r02_c18_step_target_rich.log   # the box's copy: the line below carries the capture
 timeout 600 python bench.py > gpurun_out/r02_c18_bench_target_dna1g.json 2> gpurun_out/r02_c18_bench_target_dna1g.err
 echo "bench default rc=$?"; tail -c 400 gpurun_out/r02_c18_bench_target_dna1g.err; head -c 300 gpurun_out/r02_c18_bench_target_dna1g.json; echo
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 400 --csv --log-file gpurun_out/r02_c18_launches_target.csv \
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_c18_launches_target.csv \
    python bench.py --steps 2 --warmup 3 --no-compact --no-cpu-baseline --no-e2e --no-extract --no-gather-peak > gpurun_out/r02_c18_launches_target.log 2>&1
 echo "launch list rc=$?"
 B2="--steps 3 --no-compact --no-cpu-baseline --no-e2e --no-gather-peak --no-extract --npat 20000000"

@@ -15,7 +15,7 @@ cp profiles/ncu_traffic.json gpurun_out/r02_c19_ncu_traffic.json
 ncu -i /tmp/step_rich.ncu-rep --page raw --csv > gpurun_out/r02_c19_step_target_rich_raw.csv 2>/dev/null
 timeout 600 python bench.py > gpurun_out/r02_c19_bench_target_dna1g.json 2> gpurun_out/r02_c19_bench_target_dna1g.err
 echo "bench default rc=$?"; tail -c 400 gpurun_out/r02_c19_bench_target_dna1g.err; head -c 300 gpurun_out/r02_c19_bench_target_dna1g.json; echo
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 400 --csv --log-file gpurun_out/r02_c19_launches_target.csv \
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_c19_launches_target.csv \
    python bench.py --steps 2 --warmup 3 --no-compact --no-cpu-baseline --no-e2e --no-extract --no-gather-peak > gpurun_out/r02_c19_launches_target.log 2>&1
 echo "launch list rc=$?"
 B2="--steps 3 --no-compact --no-cpu-baseline --no-e2e --no-gather-peak --no-extract --npat 20000000"

@@ -116,9 +116,10 @@ struct QueryBatch {
 
 // fills a fmx_query over byte patterns with 64-bit outputs and runs `call`; a capacity guess that is too small is
 // retried once with the exact size the first call reported (FMX_ERR_CAPACITY leaves counts / hit_off filled)
+// `offsets`: hit_off is wanted even without positions (a piece-partitioned group derives its counts from it)
 template <class Call>
 inline QueryBatch run_query_batch(Call call, const std::vector<std::string> &patterns, int mode, bool locate, bool piece_ids,
-                                  bool with_ranges) {
+                                  bool with_ranges, bool offsets = false) {
     std::vector<uint8_t> flat;
     std::vector<uint64_t> off{0};
     for (auto &p : patterns) {
@@ -132,7 +133,7 @@ inline QueryBatch run_query_batch(Call call, const std::vector<std::string> &pat
         b.s.resize(n);
         b.e.resize(n);
     }
-    if (locate) b.hit_off.resize(n + 1);
+    if (locate || offsets) b.hit_off.resize(n + 1);
     uint64_t cap = locate ? (2 * n > 1024 ? 2 * n : 1024) : 0;
     for (int attempt = 0; attempt < 2; attempt++) {
         if (locate) b.positions.resize(cap);
@@ -146,7 +147,7 @@ inline QueryBatch run_query_batch(Call call, const std::vector<std::string> &pat
         q.out_s = with_ranges ? b.s.data() : nullptr;
         q.out_e = with_ranges ? b.e.data() : nullptr;
         q.counts = b.counts.data();
-        q.hit_off = locate ? b.hit_off.data() : nullptr;
+        q.hit_off = (locate || offsets) ? b.hit_off.data() : nullptr;
         q.positions = locate ? b.positions.data() : nullptr;
         q.piece_ids = piece_ids ? b.piece_ids.data() : nullptr;
         q.capacity = cap;
@@ -284,7 +285,7 @@ class IndexGroup {
         const fmx_group *g = g_;
         const bool locate = level_ >= 0;
         return run_query_batch([g](const fmx_query *q, uint64_t *total) { return fmx_group_query_batch(g, q, total); }, patterns, mode,
-                               locate, locate && kind_ == FMX_KIND_MULTI, false);
+                               locate, locate && kind_ == FMX_KIND_MULTI, false, /*offsets=*/true);
     }
 
   private:

@@ -441,11 +441,12 @@ pub struct BatchResult {
 
 fn query_batch<C: Character, K: AsRef<[C]>>(core: &Core, mode: c_int, patterns: &[K], locate: bool, pieces: bool) -> BatchResult {
     let h = core.h;
-    query_batch_with::<C, K, _>(|q, total| unsafe { ffi::fmx_query_batch(h, q, total) }, mode, patterns, locate, pieces)
+    query_batch_with::<C, K, _>(|q, total| unsafe { ffi::fmx_query_batch(h, q, total) }, mode, patterns, locate, pieces, locate)
 }
 
+/// `offsets`: `hit_off` is wanted even without positions (a piece-partitioned group derives its counts from it).
 fn query_batch_with<C: Character, K: AsRef<[C]>, F: Fn(*const ffi::fmx_query, *mut u64) -> c_int>(
-    call: F, mode: c_int, patterns: &[K], locate: bool, pieces: bool) -> BatchResult {
+    call: F, mode: c_int, patterns: &[K], locate: bool, pieces: bool, offsets: bool) -> BatchResult {
     let mut flat: Vec<C> = vec![];
     let mut off: Vec<u64> = vec![0];
     for p in patterns {
@@ -474,7 +475,7 @@ fn query_batch_with<C: Character, K: AsRef<[C]>, F: Fn(*const ffi::fmx_query, *m
             out_s: std::ptr::null_mut(),
             out_e: std::ptr::null_mut(),
             counts: res.counts.as_mut_ptr().cast(),
-            hit_off: if locate { res.hit_off.as_mut_ptr().cast() } else { std::ptr::null_mut() },
+            hit_off: if locate || offsets { res.hit_off.as_mut_ptr().cast() } else { std::ptr::null_mut() },
             positions: if locate { res.positions.as_mut_ptr().cast() } else { std::ptr::null_mut() },
             piece_ids: if locate && pieces { res.piece_ids.as_mut_ptr().cast() } else { std::ptr::null_mut() },
             capacity: cap as u64,
@@ -548,7 +549,7 @@ impl IndexGroup {
     pub fn search_batch<K: AsRef<[u8]>>(&self, patterns: &[K]) -> BatchResult {
         let g = self.g;
         query_batch_with::<u8, K, _>(|q, total| unsafe { ffi::fmx_group_query_batch(g, q, total) }, ffi::FMX_SEARCH, patterns,
-                                     self.locate, self.locate && self.multi)
+                                     self.locate, self.locate && self.multi, true)
     }
 }
 
